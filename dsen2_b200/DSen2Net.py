@@ -1,0 +1,198 @@
+"""Host-side mirror of the reference ``utils/DSen2Net.py``: ``s2model(input_shape, num_layers, feature_size)``.
+
+The reference builds a Keras graph (DSen2Net.py:18-43):
+    concat(inputs) -> Conv3x3+ReLU -> num_layers x [Conv3x3, ReLU, Conv3x3, x0.1, +skip] -> Conv3x3 -> + last input
+Here ``s2model`` returns an ``S2Model`` exposing the Keras ``Model`` methods the reference's callers use
+(``load_weights``, ``predict``, ``count_params``; supres.py:63,65, supres_train.py:146,161,169) whose
+forward pass is the tcgen05 implicit-GEMM path behind ``dsen2_s2model_forward`` (include/dsen2_b200.h).
+"""
+import ctypes
+import math
+
+import numpy as np
+
+from . import _capi
+from .hdf5 import File, write_hdf5
+
+
+def resBlock(*_a, **_k):  # pragma: no cover - graph-construction helper of the reference, no standalone equivalent
+    raise NotImplementedError("resBlock is fused into the conv epilogues; build the network with s2model()")
+
+
+class S2Model:
+    def __init__(self, input_shape, num_layers=32, feature_size=256, seed=None):
+        if len(input_shape) not in (2, 3):
+            raise ValueError("s2model takes 2 or 3 inputs (10 m, 20 m[, 60 m])")
+        if feature_size not in (128, 256):
+            raise ValueError("feature_size must be 128 (DSen2) or 256 (VDSen2); got %r" % (feature_size,))
+        self.input_shape = tuple(tuple(s) for s in input_shape)
+        self.in_channels = [int(s[0]) for s in self.input_shape]
+        self.out_channels = self.in_channels[-1]                 # DSen2Net.py:35
+        self.num_layers, self.feature_size = int(num_layers), int(feature_size)
+        ctot, F = sum(self.in_channels), self.feature_size
+        self.layer_shapes = [(ctot, F)] + [(F, F)] * (2 * self.num_layers) + [(F, self.out_channels)]
+        rng = np.random.RandomState(seed)
+        self._weights = []
+        for cin, cout in self.layer_shapes:                      # he_uniform kernels, zero bias (:10,12,29,35)
+            lim = math.sqrt(6.0 / (9 * cin))
+            self._weights.append((rng.uniform(-lim, lim, size=(3, 3, cin, cout)).astype(np.float32),
+                                  np.zeros((cout,), np.float32)))
+        self._packed = {}        # device index -> (weights tensors, bias tensors, pointer arrays)
+        self._workspace = {}
+
+    # ---- Keras-like weight access -------------------------------------------------------- #
+    def count_params(self):
+        return int(sum(k.size + b.size for k, b in self._weights))
+
+    def get_weights(self):
+        return [a for kb in self._weights for a in kb]
+
+    def set_weights(self, arrays):
+        arrays = list(arrays)
+        if len(arrays) != 2 * len(self.layer_shapes):
+            raise ValueError("expected %d arrays (kernel, bias per conv layer), got %d"
+                             % (2 * len(self.layer_shapes), len(arrays)))
+        new = []
+        for i, (cin, cout) in enumerate(self.layer_shapes):
+            k = np.ascontiguousarray(arrays[2 * i], dtype=np.float32)
+            b = np.ascontiguousarray(arrays[2 * i + 1], dtype=np.float32)
+            if k.shape != (3, 3, cin, cout) or b.shape != (cout,):
+                raise ValueError("layer %d: expected kernel %s / bias %s, got %s / %s"
+                                 % (i, (3, 3, cin, cout), (cout,), k.shape, b.shape))
+            new.append((k, b))
+        self._weights = new
+        self._packed.clear()
+
+    def load_weights(self, filepath):
+        """Keras 2.x HDF5 weights or full-model file (``model.load_weights``, supres.py:63).
+
+        Layers are matched in ``layer_names`` order, restricted to layers that own weights (Keras'
+        topological load); auto-generated layer names differ between sessions and are ignored.
+        """
+        f = File(filepath)                                   # OSError if missing / not HDF5, like h5py
+        g = f
+        if 'layer_names' not in f.attrs and 'model_weights' in f.keys():
+            g = f['model_weights']                               # full-model save (supres_train.py:195-201)
+        if 'layer_names' not in g.attrs:
+            raise ValueError("%s is not a Keras weight file (no layer_names attribute)" % filepath)
+        arrays = []
+        for lname in np.atleast_1d(g.attrs['layer_names']):
+            lname = lname.decode('utf8') if isinstance(lname, bytes) else str(lname)
+            lg = g[lname]
+            wnames = np.atleast_1d(lg.attrs['weight_names']) if 'weight_names' in lg.attrs else []
+            for wn in wnames:
+                wn = wn.decode('utf8') if isinstance(wn, bytes) else str(wn)
+                arrays.append(np.asarray(lg[wn][()]))
+        if len(arrays) != 2 * len(self.layer_shapes):
+            raise ValueError("You are trying to load a weight file containing %d weight arrays into a model with %d"
+                             % (len(arrays), 2 * len(self.layer_shapes)))
+        self.set_weights(arrays)
+
+    def save_weights(self, filepath):
+        """Write a Keras-2-style weight file (layer_names / weight_names attributes, kernel:0 / bias:0)."""
+        tree, attrs, names = {}, {}, []
+        for i, (k, b) in enumerate(self._weights):
+            n = 'conv2d_%d' % (i + 1)
+            names.append(n.encode())
+            tree[n] = {n: {'kernel:0': k, 'bias:0': b}}
+            attrs['/' + n] = {'weight_names': np.array([('%s/kernel:0' % n).encode(), ('%s/bias:0' % n).encode()])}
+        attrs['/'] = {'layer_names': np.array(names), 'backend': np.bytes_(b'dsen2_b200'),
+                      'keras_version': np.bytes_(b'2.2.4')}
+        write_hdf5(filepath, tree, attrs)
+
+    # ---- device side ------------------------------------------------------------------- #
+    def _ensure_packed(self, device):
+        torch = _capi.require_cuda()
+        key = device.index if device.index is not None else torch.cuda.current_device()
+        if key in self._packed:
+            return self._packed[key]
+        lib = _capi.lib()
+        F = self.feature_size
+        ctot = sum(self.in_channels)
+        k_pad = (9 * ctot + 63) // 64 * 64
+        wts, biases = [], []
+        with torch.cuda.device(device):
+            for i, (k, b) in enumerate(self._weights):
+                cin, cout = self.layer_shapes[i]
+                head, tail = i == 0, i == len(self._weights) - 1
+                cin_pad = k_pad if head else F
+                cout_pad = 16 if tail else F
+                taps = 1 if head else 9
+                src = torch.from_numpy(k).to(device)
+                dst = torch.empty((taps, cout_pad, cin_pad), dtype=torch.float16, device=device)
+                _capi.check(lib.dsen2_pack_conv_weights(_capi.ptr(src), cin, cout, cin_pad, cout_pad, int(head),
+                                                        _capi.ptr(dst), None, _capi.stream_ptr()),
+                            "dsen2_pack_conv_weights")
+                bp = torch.zeros((max(cout_pad, 16),), dtype=torch.float32, device=device)
+                bp[:cout] = torch.from_numpy(b).to(device)
+                wts.append(dst)
+                biases.append(bp)
+            torch.cuda.current_stream().synchronize()
+        nl = len(wts)
+        wp = (ctypes.c_void_p * nl)(*[t.data_ptr() for t in wts])
+        bp_ = (ctypes.c_void_p * nl)(*[t.data_ptr() for t in biases])
+        self._packed[key] = (wts, biases, wp, bp_)
+        return self._packed[key]
+
+    def workspace_bytes(self, n, P):
+        return int(_capi.lib().dsen2_s2model_workspace_bytes(n, P, sum(self.in_channels), self.feature_size))
+
+    def forward_device(self, xs, out=None):
+        """xs: list of CUDA float32 (n, C_i, P, P) contiguous tensors -> CUDA float32 (n, Cout, P, P)."""
+        torch = _capi.require_cuda()
+        if len(xs) != len(self.in_channels):
+            raise ValueError("model expects %d inputs, got %d" % (len(self.in_channels), len(xs)))
+        n, _, P, P2 = xs[0].shape
+        for x, c in zip(xs, self.in_channels):
+            if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()):
+                raise ValueError("inputs must be contiguous CUDA float32 tensors")
+            if tuple(x.shape) != (n, c, P, P) or P != P2:
+                raise ValueError("expected input of shape %s, got %s" % ((n, c, P, P), tuple(x.shape)))
+        dev = xs[0].device
+        _wts, _b, wp, bp = self._ensure_packed(dev)
+        if out is None:
+            out = torch.empty((n, self.out_channels, P, P), dtype=torch.float32, device=dev)
+        if n == 0:
+            return out
+        need = self.workspace_bytes(n, P)
+        key = (dev.index, torch.cuda.current_stream().cuda_stream)
+        ws = self._workspace.get(key)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty((need,), dtype=torch.uint8, device=dev)
+            self._workspace[key] = ws
+        xp = (ctypes.c_void_p * len(xs))(*[x.data_ptr() for x in xs])
+        ch = (ctypes.c_int * len(xs))(*self.in_channels)
+        with torch.cuda.device(dev):
+            rc = _capi.lib().dsen2_s2model_forward(xp, ch, len(xs), n, P, self.num_layers, self.feature_size, wp, bp,
+                                                   _capi.ptr(ws), ws.numel(), _capi.ptr(out), _capi.stream_ptr())
+        _capi.check(rc, "dsen2_s2model_forward")
+        return out
+
+    def predict(self, x, batch_size=32, verbose=0, device_batch=None):
+        """``model.predict([x10, x20(, x60)])`` -> (N, Cout, P, P) float32 numpy (supres.py:65).
+
+        Patches are independent, so the result does not depend on ``batch_size``; the device batch is
+        chosen for occupancy (``device_batch``, default 64 patches of 128x128).
+        """
+        torch = _capi.require_cuda()
+        xs = [np.ascontiguousarray(a, dtype=np.float32) for a in (x if isinstance(x, (list, tuple)) else [x])]
+        N, P = xs[0].shape[0], xs[0].shape[2]
+        if device_batch is None:
+            device_batch = max(1, (64 * 128 * 128) // (P * P))
+        out = np.empty((N, self.out_channels, P, P), np.float32)
+        for i in range(0, N, device_batch):
+            dx = [torch.from_numpy(a[i:i + device_batch]).cuda() for a in xs]
+            out[i:i + device_batch] = self.forward_device(dx).cpu().numpy()
+            if verbose:
+                print("%d/%d" % (min(i + device_batch, N), N))
+        return out
+
+    def compile(self, *a, **k):
+        raise NotImplementedError("training (supres_train.py) is not part of this round's inference path")
+
+    fit = compile
+
+
+def s2model(input_shape, num_layers=32, feature_size=256, seed=None):
+    """Same signature as DSen2Net.py:18 (plus an optional ``seed`` for the he_uniform initialiser)."""
+    return S2Model(input_shape, num_layers=num_layers, feature_size=feature_size, seed=seed)

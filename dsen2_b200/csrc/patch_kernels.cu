@@ -1,0 +1,442 @@
+// HBM-bound kernels of the DSen2 path: patch extraction, bilinear / bicubic upsampling, stitching,
+// operand packing.  All are pure gathers with coalesced stores; grids are sized in multiples of the
+// SM count and grid-stride over the work.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace dsen2 {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+static dim3 grid_for(long long work_items, int block, int max_waves = 16) {
+  long long blocks = (work_items + block - 1) / block;
+  long long cap = (long long)sm_count() * max_waves;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return dim3((unsigned)blocks);
+}
+
+// ------------------------------------------------------------------------------------------ //
+// tiling arithmetic shared by host and device (patches.py:32-53)
+// ------------------------------------------------------------------------------------------ //
+struct Tiling {
+  int k_i, k_j;    // full strides per axis
+  int n_i, n_j;    // filled crop starts per axis
+  int stride;      // patch_lr - 2*border_lr
+  int last_i, last_j;  // clamped start (padded lr coords) of the extra crop, if any
+};
+
+__host__ __device__ inline Tiling make_tiling(int grid_h, int grid_w, int patch_lr, int border_lr) {
+  Tiling t;
+  t.stride = patch_lr - 2 * border_lr;
+  t.k_i = grid_h / t.stride;
+  t.k_j = grid_w / t.stride;
+  t.n_i = t.k_i + (grid_h % t.stride != 0);
+  t.n_j = t.k_j + (grid_w % t.stride != 0);
+  t.last_i = grid_h + 2 * border_lr - patch_lr;
+  t.last_j = grid_w + 2 * border_lr - patch_lr;
+  return t;
+}
+
+__device__ __forceinline__ int sym_index(int j, int n) {  // numpy pad(mode='symmetric')
+  if (j < 0) j = -j - 1;
+  if (j >= n) j = 2 * n - 1 - j;
+  return j;
+}
+
+// ------------------------------------------------------------------------------------------ //
+// extract: one thread per output pixel, all C bands (HWC gather -> C coalesced plane stores)
+// ------------------------------------------------------------------------------------------ //
+template <int C>
+__global__ void extract_patches_kernel(const float* __restrict__ img, int H, int W, int ratio, int p, int b,
+                                       Tiling tl, int first_patch, long long total, float divisor,
+                                       float* __restrict__ out) {
+  const long long pp = (long long)p * p;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int local = (int)(idx / pp);
+    const int rem = (int)(idx - (long long)local * pp);
+    const int y = rem / p, x = rem - y * p;
+    const int patch = first_patch + local;
+    float v[C];
+    if (patch < tl.n_i * tl.n_j) {
+      const int ti = patch / tl.n_j, tj = patch - ti * tl.n_j;
+      const int si = (ti < tl.k_i ? ti * tl.stride : tl.last_i) * ratio;
+      const int sj = (tj < tl.k_j ? tj * tl.stride : tl.last_j) * ratio;
+      const int sy = sym_index(si + y - b, H);
+      const int sx = sym_index(sj + x - b, W);
+      const float* src = img + ((long long)sy * W + sx) * C;
+      if (C == 4) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(src));
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3 % C] = q.w;
+      } else if (C % 2 == 0) {
+#pragma unroll
+        for (int c = 0; c < C; c += 2) {
+          const float2 q = __ldg(reinterpret_cast<const float2*>(src + c));
+          v[c] = q.x; v[(c + 1) % C] = q.y;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c) v[c] = __ldg(src + c);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) v[c] = 0.f;
+    }
+    float* dst = out + (long long)local * C * pp + rem;
+#pragma unroll
+    for (int c = 0; c < C; ++c) dst[c * pp] = (divisor == 1.0f) ? v[c] : __fdiv_rn(v[c], divisor);
+  }
+}
+
+__global__ void extract_patches_generic_kernel(const float* __restrict__ img, int H, int W, int C, int ratio, int p,
+                                               int b, Tiling tl, int first_patch, long long total, float divisor,
+                                               float* __restrict__ out) {
+  const long long pp = (long long)p * p;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int local = (int)(idx / pp);
+    const int rem = (int)(idx - (long long)local * pp);
+    const int y = rem / p, x = rem - y * p;
+    const int patch = first_patch + local;
+    float* dst = out + (long long)local * C * pp + rem;
+    if (patch < tl.n_i * tl.n_j) {
+      const int ti = patch / tl.n_j, tj = patch - ti * tl.n_j;
+      const int si = (ti < tl.k_i ? ti * tl.stride : tl.last_i) * ratio;
+      const int sj = (tj < tl.k_j ? tj * tl.stride : tl.last_j) * ratio;
+      const float* src = img + ((long long)sym_index(si + y - b, H) * W + sym_index(sj + x - b, W)) * C;
+      for (int c = 0; c < C; ++c) {
+        const float v = __ldg(src + c);
+        dst[c * pp] = (divisor == 1.0f) ? v : __fdiv_rn(v, divisor);
+      }
+    } else {
+      for (int c = 0; c < C; ++c) dst[c * pp] = 0.f;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ //
+// bilinear, mirror boundary, integer scale s (patches.py:11-16): u = (o + .5)/s - .5
+// ------------------------------------------------------------------------------------------ //
+__device__ __forceinline__ void bilin_tap(int o, int s, int n, int& a0, int& a1, float& f) {
+  const int t = 2 * o + 1 - s;               // u = t / (2 s)
+  int i0 = (t >= 0) ? t / (2 * s) : -((-t + 2 * s - 1) / (2 * s));
+  f = (float)(t - i0 * 2 * s) / (float)(2 * s);
+  int i1 = i0 + 1;
+  if (i0 < 0) i0 = -i0;                      // mirror: -1 -> 1
+  if (i1 > n - 1) i1 = 2 * (n - 1) - i1;     // mirror:  n -> n-2
+  if (i1 < 0) i1 = 0;                        // n == 1
+  a0 = i0; a1 = i1;
+}
+
+__global__ void bilinear_mirror_kernel(const float* __restrict__ in, int p, int s, long long total, float post_div,
+                                       float* __restrict__ out) {
+  const int P = p * s;
+  const long long PP = (long long)P * P;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long plane = idx / PP;
+    const int rem = (int)(idx - plane * PP);
+    const int oy = rem / P, ox = rem - oy * P;
+    int y0, y1, x0, x1;
+    float fy, fx;
+    bilin_tap(oy, s, p, y0, y1, fy);
+    bilin_tap(ox, s, p, x0, x1, fx);
+    const float* src = in + plane * (long long)p * p;
+    const float k = 30000.0f;                // the reference scales by 1/30000 around the resize
+    const float v00 = __fdiv_rn(__ldg(src + y0 * p + x0), k), v01 = __fdiv_rn(__ldg(src + y0 * p + x1), k);
+    const float v10 = __fdiv_rn(__ldg(src + y1 * p + x0), k), v11 = __fdiv_rn(__ldg(src + y1 * p + x1), k);
+    const float c0 = v00 * (1.0f - fy) + v10 * fy;   // rows first, then columns (as the oracle)
+    const float c1 = v01 * (1.0f - fy) + v11 * fy;
+    const float r = (c0 * (1.0f - fx) + c1 * fx) * k;
+    out[idx] = (post_div == 1.0f) ? r : __fdiv_rn(r, post_div);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ //
+// stitch: thread per (patch, interior pixel), writes the C contiguous HWC floats it owns
+// ------------------------------------------------------------------------------------------ //
+__device__ __forceinline__ int tile_of(int y, int size, int S, int n) {
+  return (size % S != 0 && y >= size - S) ? n - 1 : y / S;
+}
+
+__global__ void recompose_kernel(const float* __restrict__ pred, int first_patch, int C, int P, int border, int H,
+                                 int W, int ny, int nx, float mul, long long total, float* __restrict__ out) {
+  const int S = P - 2 * border;
+  const long long SS = (long long)S * S, PP = (long long)P * P;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int local = (int)(idx / SS);
+    const int rem = (int)(idx - (long long)local * SS);
+    const int yy = rem / S, xx = rem - yy * S;
+    const int patch = first_patch + local;
+    if (patch >= ny * nx) continue;
+    const int ty = patch / nx, tx = patch - ty * nx;
+    const int oy = min(ty * S, H - S), ox = min(tx * S, W - S);
+    const int y = oy + yy, x = ox + xx;
+    if (tile_of(y, H, S, ny) != ty || tile_of(x, W, S, nx) != tx) continue;   // a later patch overwrites it
+    const float* src = pred + (long long)local * C * PP + (long long)(border + yy) * P + (border + xx);
+    float* dst = out + ((long long)y * W + x) * C;
+    for (int c = 0; c < C; ++c) dst[c] = __ldg(src + c * PP) * mul;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ //
+// MATLAB bicubic (imresize.py:50-74): float64 products, left-to-right sums, no FMA contraction
+// ------------------------------------------------------------------------------------------ //
+template <typename TIn>
+__global__ void bicubic_kernel(const TIn* __restrict__ in, int h, int w, int C, const double* __restrict__ wy,
+                               const int32_t* __restrict__ iy, int ty, int out_h, const double* __restrict__ wx,
+                               const int32_t* __restrict__ ix, int tx, int out_w, int first_dim, long long total,
+                               double* __restrict__ out) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    const long long pix = idx / C;
+    const int ox = (int)(pix % out_w), oy = (int)(pix / out_w);
+    double acc = 0.0;
+    if (first_dim == 0) {  // rows first: inter[oy, col] then along x
+      for (int b = 0; b < tx; ++b) {
+        const int col = ix[ox * tx + b];
+        double inter = 0.0;
+        for (int a = 0; a < ty; ++a) {
+          const double v = (double)in[((long long)iy[oy * ty + a] * w + col) * C + c];
+          const double pr = __dmul_rn(v, wy[oy * ty + a]);
+          inter = (a == 0) ? pr : __dadd_rn(inter, pr);
+        }
+        const double pr = __dmul_rn(inter, wx[ox * tx + b]);
+        acc = (b == 0) ? pr : __dadd_rn(acc, pr);
+      }
+    } else {               // columns first
+      for (int a = 0; a < ty; ++a) {
+        const int row = iy[oy * ty + a];
+        double inter = 0.0;
+        for (int b = 0; b < tx; ++b) {
+          const double v = (double)in[((long long)row * w + ix[ox * tx + b]) * C + c];
+          const double pr = __dmul_rn(v, wx[ox * tx + b]);
+          inter = (b == 0) ? pr : __dadd_rn(inter, pr);
+        }
+        const double pr = __dmul_rn(inter, wy[oy * ty + a]);
+        acc = (a == 0) ? pr : __dadd_rn(acc, pr);
+      }
+    }
+    out[idx] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ //
+// operand packing for the tensor-core path
+// ------------------------------------------------------------------------------------------ //
+__global__ void pack_weights_kernel(const float* __restrict__ hwio, int cin, int cout, int cin_pad, int cout_pad,
+                                    int im2col, long long total, __half* __restrict__ out, __half* __restrict__ out_lo) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % cin_pad);
+    const int o = (int)((idx / cin_pad) % cout_pad);
+    const int t = (int)(idx / ((long long)cin_pad * cout_pad));
+    float v = 0.f;
+    if (o < cout) {
+      if (im2col) {
+        if (i < 9 * cin) v = hwio[(long long)i * cout + o];          // (ky,kx,c) flattened is already k-major
+      } else if (i < cin) {
+        v = hwio[((long long)t * cin + i) * cout + o];
+      }
+    }
+    const __half hi = __float2half_rn(v);
+    out[idx] = hi;
+    if (out_lo) out_lo[idx] = __float2half_rn(v - __half2float(hi));
+  }
+}
+
+// thread = (pixel, group of 8 k): zero-padded 3x3 neighbourhood of the concatenated inputs
+__global__ void pack_head_input_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x1, int c1,
+                                       const float* __restrict__ x2, int c2, int P, int k_pad, long long total,
+                                       __half* __restrict__ out, __half* __restrict__ out_lo) {
+  const int ctot = c0 + c1 + c2;
+  const int groups = k_pad / 8;
+  const long long PP = (long long)P * P;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % groups);
+    const long long pix = idx / groups;
+    const int n = (int)(pix / PP);
+    const int rem = (int)(pix - (long long)n * PP);
+    const int y = rem / P, x = rem - y * P;
+    __align__(16) __half hi[8];
+    __align__(16) __half lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = g * 8 + j;
+      float v = 0.f;
+      if (k < 9 * ctot) {
+        const int tap = k / ctot, c = k - tap * ctot;
+        const int sy = y + tap / 3 - 1, sx = x + tap % 3 - 1;
+        if (sy >= 0 && sy < P && sx >= 0 && sx < P) {
+          const float* src;
+          int cc = c, cn;
+          if (cc < c0) { src = x0; cn = c0; }
+          else if (cc < c0 + c1) { src = x1; cc -= c0; cn = c1; }
+          else { src = x2; cc -= c0 + c1; cn = c2; }
+          v = __ldg(src + ((long long)n * cn + cc) * PP + (long long)sy * P + sx);
+        }
+      }
+      hi[j] = __float2half_rn(v);
+      lo[j] = __float2half_rn(v - __half2float(hi[j]));
+    }
+    *reinterpret_cast<uint4*>(out + pix * k_pad + g * 8) = *reinterpret_cast<const uint4*>(hi);
+    if (out_lo) *reinterpret_cast<uint4*>(out_lo + pix * k_pad + g * 8) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
+}  // namespace dsen2
+
+// ============================================================================================ //
+// C ABI
+// ============================================================================================ //
+using namespace dsen2;
+
+extern "C" int dsen2_abi_version(void) { return DSEN2_ABI_VERSION; }
+extern "C" const char* dsen2_last_error(void) { return g_err; }
+
+extern "C" int dsen2_patch_counts(int grid_h, int grid_w, int patch_lr, int border_lr, int* allocated, int* filled) {
+  DSEN2_REQUIRE(grid_h > 0 && grid_w > 0 && patch_lr > 0 && border_lr >= 0 && patch_lr > 2 * border_lr, DSEN2_E_BADARG,
+                "dsen2_patch_counts: bad geometry (grid %dx%d patch %d border %d)", grid_h, grid_w, patch_lr, border_lr);
+  const Tiling t = make_tiling(grid_h, grid_w, patch_lr, border_lr);
+  if (allocated) *allocated = (t.k_i + 1) * (t.k_j + 1);
+  if (filled) *filled = t.n_i * t.n_j;
+  return 0;
+}
+
+extern "C" int dsen2_extract_patches(const float* d_img, int grid_h, int grid_w, int C, int ratio, int patch_lr,
+                                     int border_lr, int first_patch, int num_patches, float divisor, float* d_out,
+                                     void* stream) {
+  DSEN2_REQUIRE(d_img && d_out, DSEN2_E_BADARG, "dsen2_extract_patches: null pointer");
+  DSEN2_REQUIRE(grid_h > 0 && grid_w > 0 && C > 0 && ratio > 0 && patch_lr > 2 * border_lr && border_lr >= 0,
+                DSEN2_E_BADARG, "dsen2_extract_patches: bad geometry");
+  DSEN2_REQUIRE(grid_h + 2 * border_lr >= patch_lr && grid_w + 2 * border_lr >= patch_lr, DSEN2_E_BADARG,
+                "dsen2_extract_patches: image (%dx%d on the tiling grid) smaller than one patch (%d)", grid_h, grid_w,
+                patch_lr);
+  DSEN2_REQUIRE(first_patch >= 0 && num_patches >= 0 && divisor != 0.f, DSEN2_E_BADARG,
+                "dsen2_extract_patches: bad patch range / divisor");
+  if (num_patches == 0) return 0;
+  const Tiling tl = make_tiling(grid_h, grid_w, patch_lr, border_lr);
+  DSEN2_REQUIRE(first_patch + num_patches <= (tl.k_i + 1) * (tl.k_j + 1), DSEN2_E_BADARG,
+                "dsen2_extract_patches: patch range [%d,%d) exceeds the %d allocated patches", first_patch,
+                first_patch + num_patches, (tl.k_i + 1) * (tl.k_j + 1));
+  const int H = grid_h * ratio, W = grid_w * ratio, p = patch_lr * ratio, b = border_lr * ratio;
+  const long long total = (long long)num_patches * p * p;
+  const int block = 256;
+  const dim3 grid = grid_for(total, block);
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool aligned = ((uintptr_t)d_img % 16) == 0;
+  if (C == 4 && aligned)
+    extract_patches_kernel<4><<<grid, block, 0, s>>>(d_img, H, W, ratio, p, b, tl, first_patch, total, divisor, d_out);
+  else if (C == 6 && aligned)
+    extract_patches_kernel<6><<<grid, block, 0, s>>>(d_img, H, W, ratio, p, b, tl, first_patch, total, divisor, d_out);
+  else if (C == 2 && aligned)
+    extract_patches_kernel<2><<<grid, block, 0, s>>>(d_img, H, W, ratio, p, b, tl, first_patch, total, divisor, d_out);
+  else
+    extract_patches_generic_kernel<<<grid, block, 0, s>>>(d_img, H, W, C, ratio, p, b, tl, first_patch, total, divisor,
+                                                          d_out);
+  return check_launch("extract_patches");
+}
+
+extern "C" int dsen2_bilinear_mirror_up(const float* d_in, int planes, int p, int s, float post_divisor, float* d_out,
+                                        void* stream) {
+  DSEN2_REQUIRE(d_in && d_out, DSEN2_E_BADARG, "dsen2_bilinear_mirror_up: null pointer");
+  DSEN2_REQUIRE(planes >= 0 && p > 0 && s > 0 && post_divisor != 0.f, DSEN2_E_BADARG,
+                "dsen2_bilinear_mirror_up: bad sizes");
+  if (planes == 0) return 0;
+  const long long total = (long long)planes * p * s * p * s;
+  const int block = 256;
+  bilinear_mirror_kernel<<<grid_for(total, block), block, 0, (cudaStream_t)stream>>>(d_in, p, s, total, post_divisor,
+                                                                                     d_out);
+  return check_launch("bilinear_mirror_up");
+}
+
+extern "C" int dsen2_recompose(const float* d_pred, int first_patch, int num_patches, int C, int P, int border, int H,
+                               int W, float mul, float* d_out, void* stream) {
+  DSEN2_REQUIRE(d_pred && d_out, DSEN2_E_BADARG, "dsen2_recompose: null pointer");
+  const int S = P - 2 * border;
+  DSEN2_REQUIRE(C > 0 && P > 0 && border >= 0 && S > 0, DSEN2_E_BADARG, "dsen2_recompose: bad patch geometry");
+  DSEN2_REQUIRE(H >= S && W >= S, DSEN2_E_BADARG,
+                "dsen2_recompose: image %dx%d smaller than the patch interior %d (patches.py:394-401 needs size >= patch)",
+                H, W, S);
+  DSEN2_REQUIRE(first_patch >= 0 && num_patches >= 0, DSEN2_E_BADARG, "dsen2_recompose: bad patch range");
+  if (num_patches == 0) return 0;
+  const int ny = ceil_div(H, S), nx = ceil_div(W, S);
+  const long long total = (long long)num_patches * S * S;
+  const int block = 256;
+  recompose_kernel<<<grid_for(total, block), block, 0, (cudaStream_t)stream>>>(d_pred, first_patch, C, P, border, H, W,
+                                                                               ny, nx, mul, total, d_out);
+  return check_launch("recompose");
+}
+
+extern "C" int dsen2_bicubic_imresize(const void* d_in, int in_is_f64, int h, int w, int C, const double* d_wy,
+                                      const int32_t* d_iy, int taps_y, int out_h, const double* d_wx,
+                                      const int32_t* d_ix, int taps_x, int out_w, int first_dim, double* d_out,
+                                      void* stream) {
+  DSEN2_REQUIRE(d_in && d_wy && d_iy && d_wx && d_ix && d_out, DSEN2_E_BADARG, "dsen2_bicubic_imresize: null pointer");
+  DSEN2_REQUIRE(h > 0 && w > 0 && C > 0 && taps_y > 0 && taps_x > 0 && out_h > 0 && out_w > 0 &&
+                    (first_dim == 0 || first_dim == 1),
+                DSEN2_E_BADARG, "dsen2_bicubic_imresize: bad sizes");
+  const long long total = (long long)out_h * out_w * C;
+  const int block = 256;
+  const dim3 grid = grid_for(total, block);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (in_is_f64)
+    bicubic_kernel<double><<<grid, block, 0, s>>>((const double*)d_in, h, w, C, d_wy, d_iy, taps_y, out_h, d_wx, d_ix,
+                                                  taps_x, out_w, first_dim, total, d_out);
+  else
+    bicubic_kernel<float><<<grid, block, 0, s>>>((const float*)d_in, h, w, C, d_wy, d_iy, taps_y, out_h, d_wx, d_ix,
+                                                 taps_x, out_w, first_dim, total, d_out);
+  return check_launch("bicubic_imresize");
+}
+
+extern "C" int dsen2_pack_conv_weights(const float* d_hwio, int cin, int cout, int cin_pad, int cout_pad, int im2col,
+                                       void* d_packed_f16, void* d_packed_lo_f16, void* stream) {
+  DSEN2_REQUIRE(d_hwio && d_packed_f16, DSEN2_E_BADARG, "dsen2_pack_conv_weights: null pointer");
+  DSEN2_REQUIRE(cin > 0 && cout > 0 && cin_pad % 64 == 0 && cout_pad >= cout && cout_pad % 16 == 0, DSEN2_E_BADARG,
+                "dsen2_pack_conv_weights: bad channel padding (cin %d->%d, cout %d->%d)", cin, cin_pad, cout, cout_pad);
+  DSEN2_REQUIRE(im2col ? cin_pad >= 9 * cin : cin_pad >= cin, DSEN2_E_BADARG,
+                "dsen2_pack_conv_weights: cin_pad %d too small", cin_pad);
+  const int taps = im2col ? 1 : 9;
+  const long long total = (long long)taps * cout_pad * cin_pad;
+  const int block = 256;
+  pack_weights_kernel<<<grid_for(total, block), block, 0, (cudaStream_t)stream>>>(
+      d_hwio, cin, cout, cin_pad, cout_pad, im2col, total, (__half*)d_packed_f16, (__half*)d_packed_lo_f16);
+  return check_launch("pack_conv_weights");
+}
+
+extern "C" int dsen2_pack_head_input(const float* d_x0, int c0, const float* d_x1, int c1, const float* d_x2, int c2,
+                                     int n, int P, int k_pad, void* d_out_f16, void* d_out_lo_f16, void* stream) {
+  DSEN2_REQUIRE(d_x0 && d_x1 && d_out_f16 && (c2 == 0 || d_x2), DSEN2_E_BADARG, "dsen2_pack_head_input: null pointer");
+  DSEN2_REQUIRE(c0 > 0 && c1 > 0 && c2 >= 0 && n >= 0 && P > 0 && k_pad % 64 == 0 && k_pad >= 9 * (c0 + c1 + c2),
+                DSEN2_E_BADARG, "dsen2_pack_head_input: bad sizes (k_pad %d for %d channels)", k_pad, c0 + c1 + c2);
+  DSEN2_REQUIRE(((uintptr_t)d_out_f16 % 16) == 0 && ((uintptr_t)d_out_lo_f16 % 16) == 0, DSEN2_E_ALIGN,
+                "dsen2_pack_head_input: output must be 16-byte aligned");
+  if (n == 0) return 0;
+  const long long total = (long long)n * P * P * (k_pad / 8);
+  const int block = 256;
+  pack_head_input_kernel<<<grid_for(total, block), block, 0, (cudaStream_t)stream>>>(
+      d_x0, c0, d_x1, c1, d_x2, c2, P, k_pad, total, (__half*)d_out_f16, (__half*)d_out_lo_f16);
+  return check_launch("pack_head_input");
+}

@@ -1,0 +1,146 @@
+"""Host-side mirror of the reference ``utils/patches.py`` (test-time tiling / stitching).
+
+Same names, argument meaning and return shapes as the reference functions
+(``get_test_patches`` :19-80, ``get_test_patches60`` :83-156, ``interp_patches`` :11-16,
+``recompose_images`` :374-405); the arithmetic runs in the CUDA kernels of
+``csrc/patch_kernels.cu`` through the C ABI.  The ``*_device`` functions are the
+torch-tensor level used by the engine (no host round trips).
+"""
+from math import ceil
+
+import numpy as np
+
+from . import _capi
+
+VERBOSE = True   # recompose_images prints the canvas shape like the reference (patches.py:392)
+
+
+def patch_counts(grid_h, grid_w, patch_lr, border_lr):
+    """(allocated, filled) patch counts (patches.py:32-53)."""
+    import ctypes
+    a, f = ctypes.c_int(0), ctypes.c_int(0)
+    rc = _capi.lib().dsen2_patch_counts(grid_h, grid_w, patch_lr, border_lr, ctypes.byref(a), ctypes.byref(f))
+    if rc:
+        raise ValueError(_capi.lib().dsen2_last_error().decode())
+    return a.value, f.value
+
+
+# ------------------------------------------------------------------------------------------ #
+# device level
+# ------------------------------------------------------------------------------------------ #
+def extract_patches_device(img, ratio, patch_lr, border_lr, first_patch=0, num_patches=None, divisor=1.0, out=None):
+    """img: CUDA float32 (H, W, C) contiguous -> (num_patches, C, p, p) float32."""
+    torch = _capi.require_cuda()
+    assert img.is_cuda and img.dtype == torch.float32 and img.is_contiguous() and img.dim() == 3
+    H, W, C = img.shape
+    if H % ratio or W % ratio:
+        raise ValueError("image size %dx%d is not a multiple of the resolution ratio %d" % (H, W, ratio))
+    gh, gw = H // ratio, W // ratio
+    allocated, _ = patch_counts(gh, gw, patch_lr, border_lr)
+    if num_patches is None:
+        num_patches = allocated - first_patch
+    p = patch_lr * ratio
+    if out is None:
+        out = torch.empty((num_patches, C, p, p), dtype=torch.float32, device=img.device)
+    with torch.cuda.device(img.device):
+        rc = _capi.lib().dsen2_extract_patches(_capi.ptr(img), gh, gw, C, ratio, patch_lr, border_lr, first_patch,
+                                               num_patches, float(divisor), _capi.ptr(out), _capi.stream_ptr())
+    if rc == -1:
+        raise ValueError(_capi.lib().dsen2_last_error().decode())
+    _capi.check(rc, "dsen2_extract_patches")
+    return out
+
+
+def bilinear_up_device(x, scale, post_divisor=1.0, out=None):
+    """x: CUDA float32 (..., p, p) -> (..., p*scale, p*scale), mirror boundary (patches.py:11-16)."""
+    torch = _capi.require_cuda()
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+    p = x.shape[-1]
+    assert x.shape[-2] == p, "patches are square"
+    planes = x.numel() // (p * p)
+    if out is None:
+        out = torch.empty(tuple(x.shape[:-2]) + (p * scale, p * scale), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _capi.lib().dsen2_bilinear_mirror_up(_capi.ptr(x), planes, p, scale, float(post_divisor),
+                                                  _capi.ptr(out), _capi.stream_ptr())
+    _capi.check(rc, "dsen2_bilinear_mirror_up")
+    return out
+
+
+def recompose_device(pred, border, H, W, first_patch=0, mul=1.0, out=None):
+    """pred: CUDA float32 (n, C, P, P) holding patches [first_patch, first_patch+n) -> writes into (H, W, C)."""
+    torch = _capi.require_cuda()
+    assert pred.is_cuda and pred.dtype == torch.float32 and pred.is_contiguous() and pred.dim() == 4
+    n, C, P, _ = pred.shape
+    if out is None:
+        out = torch.zeros((H, W, C), dtype=torch.float32, device=pred.device)
+    with torch.cuda.device(pred.device):
+        rc = _capi.lib().dsen2_recompose(_capi.ptr(pred), first_patch, n, C, P, border, H, W, float(mul),
+                                         _capi.ptr(out), _capi.stream_ptr())
+    if rc == -1:
+        raise ValueError(_capi.lib().dsen2_last_error().decode())
+    _capi.check(rc, "dsen2_recompose")
+    return out
+
+
+# ------------------------------------------------------------------------------------------ #
+# numpy level: the reference's signatures
+# ------------------------------------------------------------------------------------------ #
+def _to_dev(a):
+    torch = _capi.require_cuda()
+    a = np.ascontiguousarray(np.asarray(a), dtype=np.float32)   # the reference casts on assignment into float32 stacks
+    return torch.from_numpy(a).cuda()
+
+
+def interp_patches(image_20, image_10_shape):
+    image_20 = np.asarray(image_20)
+    P = image_10_shape[2]
+    s = P // image_20.shape[2]
+    if image_20.shape[2] * s != P or tuple(image_10_shape[2:4]) != (P, P):
+        raise ValueError("interp_patches supports square integer-factor upsampling only")
+    if image_20.shape[0] == 0:
+        return np.zeros(image_20.shape[0:2] + tuple(image_10_shape[2:4]), np.float32)
+    return bilinear_up_device(_to_dev(image_20), s).cpu().numpy()
+
+
+def get_test_patches(dset_10, dset_20, patchSize=128, border=4, interp=True):
+    d10, d20 = _to_dev(dset_10), _to_dev(dset_20)
+    if d10.shape[0] != 2 * d20.shape[0] or d10.shape[1] != 2 * d20.shape[1]:
+        raise ValueError("dset_10 must be exactly twice the size of dset_20")
+    plr, blr = patchSize // 2, border // 2
+    image_10 = extract_patches_device(d10, 2, plr, blr)
+    image_20 = extract_patches_device(d20, 1, plr, blr)
+    if interp:
+        image_20 = bilinear_up_device(image_20, 2)
+    return image_10.cpu().numpy(), image_20.cpu().numpy()
+
+
+def get_test_patches60(dset_10, dset_20, dset_60, patchSize=128, border=8, interp=True):
+    d10, d20, d60 = _to_dev(dset_10), _to_dev(dset_20), _to_dev(dset_60)
+    if (d10.shape[0] != 6 * d60.shape[0] or d10.shape[1] != 6 * d60.shape[1] or
+            d20.shape[0] != 3 * d60.shape[0] or d20.shape[1] != 3 * d60.shape[1]):
+        raise ValueError("dset_10 / dset_20 must be exactly 6x / 3x the size of dset_60")
+    plr, blr = patchSize // 6, border // 6
+    image_10 = extract_patches_device(d10, 6, plr, blr)
+    image_20 = extract_patches_device(d20, 3, plr, blr)
+    image_60 = extract_patches_device(d60, 1, plr, blr)
+    if interp:
+        image_20 = bilinear_up_device(image_20, 2)
+        image_60 = bilinear_up_device(image_60, 6)
+    return image_10.cpu().numpy(), image_20.cpu().numpy(), image_60.cpu().numpy()
+
+
+def recompose_images(a, border, size=None):
+    a = np.asarray(a)
+    if a.shape[0] == 1:
+        images = np.ascontiguousarray(a[0], dtype=np.float32)   # returned uncropped (patches.py:375-376)
+        return images.transpose((1, 2, 0))
+    H, W = int(size[0]), int(size[1])
+    patch_size = a.shape[2] - border * 2
+    x_tiles, y_tiles = int(ceil(W / float(patch_size))), int(ceil(H / float(patch_size)))
+    if a.shape[0] < x_tiles * y_tiles:
+        raise IndexError("index %d is out of bounds for axis 0 with size %d" % (a.shape[0], a.shape[0]))
+    if VERBOSE:
+        print((a.shape[1], H, W))
+    used = a[:x_tiles * y_tiles]          # surplus (all-zero) patches are never read by the reference loop
+    return recompose_device(_to_dev(used), border, H, W).cpu().numpy()

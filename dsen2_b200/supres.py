@@ -1,0 +1,104 @@
+"""Host-side mirror of the reference ``testing/supres.py``: ``DSen2_20`` / ``DSen2_60``.
+
+Same signatures, ``SCALE`` / ``MDL_PATH`` module constants and weight-file naming (supres.py:11-12,57,60).
+The whole tile stays on the GPU between the upload of the inputs and the download of the stitched
+image: extract(/2000) -> bilinear(/2000) -> tcgen05 network -> stitch(x2000), streamed in patch batches.
+"""
+import os
+
+import numpy as np
+
+from . import _capi
+from .DSen2Net import s2model
+from .patches import bilinear_up_device, extract_patches_device, patch_counts, recompose_device
+
+SCALE = 2000
+MDL_PATH = '../models/'
+
+_GEOM = {False: dict(patch=128, border=8, ratio=2), True: dict(patch=192, border=12, ratio=6)}
+_model_cache = {}
+
+
+def weight_file(deep=False, run_60=False):
+    """File-name convention of supres.py:57,60."""
+    if deep:
+        return MDL_PATH + ('s2_034_lr_1e-04.hdf5' if run_60 else 's2_033_lr_1e-04.hdf5')
+    return MDL_PATH + ('s2_030_lr_1e-05.hdf5' if run_60 else 's2_032_lr_1e-04.hdf5')
+
+
+def _load_model(input_shape, deep, run_60):
+    path = weight_file(deep, run_60)
+    st = os.stat(path)                      # FileNotFoundError (OSError) when the weights are missing, as h5py
+    key = (os.path.abspath(path), st.st_mtime_ns, st.st_size)
+    if key not in _model_cache:
+        model = s2model(input_shape, num_layers=32, feature_size=256) if deep else \
+            s2model(input_shape, num_layers=6, feature_size=128)
+        print('Symbolic Model Created.')
+        model.load_weights(path)
+        _model_cache[key] = model
+    print("Predicting using file: {}".format(path))
+    return _model_cache[key]
+
+
+def super_resolve_device(model, d10, d20, d60=None, first_patch=0, num_patches=None, out=None, device_batch=None):
+    """Device-level pipeline.  d10/d20(/d60): CUDA float32 HWC tensors.  Processes patches
+    [first_patch, first_patch+num_patches) of the FILLED patch list (surplus zero patches of
+    patches.py:32-39 are never read by recompose_images, so they are skipped) and writes the pixels those
+    patches own into ``out`` (H, W, Cout) float32 (allocated zero-filled if None)."""
+    torch = _capi.require_cuda()
+    run_60 = d60 is not None
+    g = _GEOM[run_60]
+    r, P, B = g['ratio'], g['patch'], g['border']
+    H, W = int(d10.shape[0]), int(d10.shape[1])
+    if H % r or W % r:
+        raise ValueError("10 m image size %dx%d must be a multiple of %d" % (H, W, r))
+    plr, blr = P // r, B // r
+    _, filled = patch_counts(H // r, W // r, plr, blr)
+    if num_patches is None:
+        num_patches = filled - first_patch
+    if first_patch < 0 or first_patch + num_patches > filled:
+        raise ValueError("patch range [%d, %d) outside the %d patches of this tile"
+                         % (first_patch, first_patch + num_patches, filled))
+    if out is None:
+        out = torch.zeros((H, W, model.out_channels), dtype=torch.float32, device=d10.device)
+    if device_batch is None:
+        device_batch = max(1, (64 * 128 * 128) // (P * P))
+    single = filled == 1                     # recompose_images returns the lone patch uncropped (patches.py:375-376)
+    for p0 in range(first_patch, first_patch + num_patches, device_batch):
+        nb = min(device_batch, first_patch + num_patches - p0)
+        if run_60:
+            xs = [extract_patches_device(d10, 6, plr, blr, p0, nb, divisor=SCALE),
+                  bilinear_up_device(extract_patches_device(d20, 3, plr, blr, p0, nb), 2, post_divisor=SCALE),
+                  bilinear_up_device(extract_patches_device(d60, 1, plr, blr, p0, nb), 6, post_divisor=SCALE)]
+        else:
+            xs = [extract_patches_device(d10, 2, plr, blr, p0, nb, divisor=SCALE),
+                  bilinear_up_device(extract_patches_device(d20, 1, plr, blr, p0, nb), 2, post_divisor=SCALE)]
+        pred = model.forward_device(xs)
+        if single:
+            return (pred[0] * float(SCALE)).permute(1, 2, 0).contiguous()
+        recompose_device(pred, B, H, W, first_patch=p0, mul=float(SCALE), out=out)
+    return out
+
+
+def _run(model, arrays):
+    torch = _capi.require_cuda()
+    dev = [torch.from_numpy(np.ascontiguousarray(np.asarray(a), dtype=np.float32)).cuda() for a in arrays]
+    out = super_resolve_device(model, *dev)
+    return out.cpu().numpy()
+
+
+def DSen2_20(d10, d20, deep=False, model=None):
+    """supres.py:15-30.  d10 (H,W,4), d20 (H/2,W/2,6) -> (H,W,6) float32.  ``model`` (extension) supplies a
+    preloaded ``S2Model`` instead of the shipped hdf5 weights."""
+    input_shape = ((4, None, None), (6, None, None))
+    if model is None:
+        model = _load_model(input_shape, deep, run_60=False)
+    return _run(model, [d10, d20])
+
+
+def DSen2_60(d10, d20, d60, deep=False, model=None):
+    """supres.py:33-50.  + d60 (H/6,W/6,2) -> (H,W,2) float32."""
+    input_shape = ((4, None, None), (6, None, None), (2, None, None))
+    if model is None:
+        model = _load_model(input_shape, deep, run_60=True)
+    return _run(model, [d10, d20, d60])

@@ -1,0 +1,139 @@
+/*
+ * dsen2_b200 -- C ABI of the B200-native DSen2 / VDSen2 super-resolution hot path.
+ *
+ * The reference (ACMEAtronOmatic/DSen2) has no FFI layer: its hot path is Python
+ * calling numpy / scikit-image / Keras.  Each entry point below replaces one of
+ * those Python-level operations (file:line into the reference tree) and is what a
+ * ctypes binding on the reference side would call.
+ *
+ * Conventions
+ *   - every pointer named d_* is a DEVICE pointer owned by the caller; nothing is
+ *     allocated or freed by the library and there is no global mutable state
+ *     besides a thread-local error string;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued, not synchronised;
+ *   - return value: 0 = ok, >0 = cudaError_t, <0 = DSEN2_E_* argument error;
+ *     dsen2_last_error() returns a human-readable message for the calling thread.
+ */
+#ifndef DSEN2_B200_H_
+#define DSEN2_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSEN2_ABI_VERSION 1
+
+#define DSEN2_E_BADARG   (-1)  /* null pointer / non-positive size / unsupported combination */
+#define DSEN2_E_ALIGN    (-2)  /* pointer or channel count not aligned as the kernel requires */
+#define DSEN2_E_DRIVER   (-3)  /* cuTensorMapEncodeTiled unavailable or failed */
+#define DSEN2_E_NOTSM100 (-4)  /* device is not compute capability 10.x */
+
+int dsen2_abi_version(void);
+const char* dsen2_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Patch extraction -- utils/patches.py:19-80 (get_test_patches) and :83-156 (get_test_patches60).
+ * One call per resolution.  d_img is (H, W, C) float32 HWC with H = grid_h*ratio, W = grid_w*ratio
+ * where (grid_h, grid_w) is the size of the tiling grid (the 20 m grid for the 20 m path, the 60 m
+ * grid for the 60 m path) and ratio in {1,2,3,6}.  Patches are patch_lr*ratio square with a
+ * symmetric-padded border of border_lr*ratio; crop starts follow patches.py:45-53.  Writes patches
+ * [first_patch, first_patch+num_patches) of the ALLOCATED (k_i+1)*(k_j+1) stack (surplus patches are
+ * zero, patches.py:32-39) to d_out (num_patches, C, p, p) float32, each value divided by `divisor`
+ * (IEEE division; 1.0f = bit-exact copy; 2000.0f fuses supres.py:23-24).
+ * ------------------------------------------------------------------------------------------- */
+int dsen2_extract_patches(const float* d_img, int grid_h, int grid_w, int C, int ratio,
+                          int patch_lr, int border_lr, int first_patch, int num_patches,
+                          float divisor, float* d_out, void* stream);
+
+/* Number of allocated patches (k_i+1)*(k_j+1) and of filled patches n_i*n_j (patches.py:32-53). */
+int dsen2_patch_counts(int grid_h, int grid_w, int patch_lr, int border_lr, int* allocated, int* filled);
+
+/* ---------------------------------------------------------------------------------------------
+ * Bilinear upsample with mirror boundary, per (patch, band) plane -- utils/patches.py:11-16
+ * (skimage.transform.resize(order=1, mode='reflect')).  d_in (planes, p, p) -> d_out (planes, p*s, p*s);
+ * the result is divided by `post_divisor` (1.0f = none; 2000.0f fuses supres.py:24 / :43-44).
+ * ------------------------------------------------------------------------------------------- */
+int dsen2_bilinear_mirror_up(const float* d_in, int planes, int p, int s, float post_divisor, float* d_out,
+                             void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stitching -- utils/patches.py:374-405 (recompose_images), sequential-overwrite semantics restated
+ * as ownership: patch t writes exactly the output pixels whose LAST writer it is.  d_pred holds
+ * patches [first_patch, first_patch+num_patches) of the (N, C, P, P) prediction; d_out is the whole
+ * (H, W, C) float32 HWC canvas (the array the reference returns as a transposed view, :405);
+ * values are multiplied by `mul` (2000.0f fuses supres.py:29).
+ * ------------------------------------------------------------------------------------------- */
+int dsen2_recompose(const float* d_pred, int first_patch, int num_patches, int C, int P, int border,
+                    int H, int W, float mul, float* d_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * MATLAB-compatible bicubic imresize -- utils/imresize.py:50-74,80-112.  The tap tables
+ * (weights float64 (out, taps), indices int32 (out, taps)) are the ones imresize.py:28-48
+ * (`contributions`) produces; the kernel reproduces imresizemex's float64 products summed left to
+ * right, first along `first_dim` then along the other, so results are bit-identical.
+ * d_in (h, w, C) float32 or float64 (in_is_f64), d_out (out_h, out_w, C) float64.
+ * ------------------------------------------------------------------------------------------- */
+int dsen2_bicubic_imresize(const void* d_in, int in_is_f64, int h, int w, int C,
+                           const double* d_wy, const int32_t* d_iy, int taps_y, int out_h,
+                           const double* d_wx, const int32_t* d_ix, int taps_x, int out_w,
+                           int first_dim, double* d_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Network (utils/DSen2Net.py:9-43) -- tcgen05 implicit-GEMM convolutions, fp16 operands, fp32
+ * accumulation in TMEM, fp32-equivalent (fp16 hi + fp16 lo) residual trunk.
+ * Activations are NHWC fp16 with the channel count padded to a multiple of 64.
+ * ------------------------------------------------------------------------------------------- */
+
+/* Keras HWIO kernel (3,3,cin,cout) fp32 -> [tap][cout_pad][cin_pad] fp16 (K-major B operand).
+ * im2col != 0 packs the same kernel as a 1x1 convolution over the 9*cin im2col channels:
+ * [1][cout_pad][cin_pad >= 9*cin], k = (ky*3+kx)*cin + c  (head conv, DSen2Net.py:29).        */
+int dsen2_pack_conv_weights(const float* d_hwio, int cin, int cout, int cin_pad, int cout_pad,
+                            int im2col, void* d_packed_f16, void* d_packed_lo_f16 /* optional: f16(w - hi) */,
+                            void* stream);
+
+/* Concatenate (DSen2Net.py:24,26) the NCHW fp32 inputs (n, c_i, P, P) and write the zero-padded
+ * 3x3 im2col of the concatenation as NHWC fp16 (n, P, P, k_pad), k = (ky*3+kx)*sum(c_i) + c.      */
+int dsen2_pack_head_input(const float* d_x0, int c0, const float* d_x1, int c1, const float* d_x2, int c2,
+                          int n, int P, int k_pad, void* d_out_f16, void* d_out_lo_f16 /* optional */, void* stream);
+
+/* Epilogues of dsen2_conv3x3 */
+#define DSEN2_EPI_RELU      0  /* out_hi = f16(relu(acc+bias)); out_lo (optional) = f16(v - out_hi)      */
+#define DSEN2_EPI_RESIDUAL  1  /* v = (res_hi+res_lo) + res_scale*(acc+bias); out_hi/out_lo = split(v)   */
+#define DSEN2_EPI_TAIL_NCHW 2  /* out_f32[n,c,y,x] = acc + bias + skip_f32[n,c,y,x], c < cout_real        */
+
+/* One convolution layer over n patches of (H, W): taps = 9 (3x3, zero 'same' padding at the PATCH
+ * edge, Conv2D(padding='same')) or 1 (1x1, used with the im2col head input).
+ *   d_in       NHWC fp16 (n, H, W, cin_pad), cin_pad % 64 == 0
+ *   d_w        packed weights from dsen2_pack_conv_weights, d_bias fp32 (cout_pad)
+ *   cout_pad   16, 128 or 256 (UMMA N)
+ * RELU:     d_out_hi (n,H,W,cout_pad) fp16, d_out_lo optional
+ * RESIDUAL: d_res_hi/d_res_lo in, d_out_hi/d_out_lo out (may alias the res pointers)
+ * TAIL:     d_skip_f32 / d_out_f32 NCHW (n, cout_real, H, W) fp32                                */
+int dsen2_conv3x3(const void* d_in, const void* d_w, const float* d_bias,
+                  int n, int H, int W, int cin_pad, int cout_pad, int taps, int epilogue,
+                  const void* d_res_hi, const void* d_res_lo, float res_scale,
+                  void* d_out_hi, void* d_out_lo,
+                  const float* d_skip_f32, float* d_out_f32, int cout_real, void* stream);
+
+/* Whole s2model forward (model.predict on one batch, supres.py:65) for n patches of (P, P):
+ * head (im2col 1x1) -> num_layers x resBlock -> tail + global skip.  d_weights[i]/d_bias[i] are the
+ * packed layers in Keras topological order (2*num_layers+2 entries).  Workspace: see
+ * dsen2_s2model_workspace_bytes.  d_x[0..n_inputs) NCHW fp32 inputs; the last one is the global skip. */
+size_t dsen2_s2model_workspace_bytes(int n, int P, int in_channels, int feature_size);
+int dsen2_s2model_forward(const float* const* d_x, const int* channels, int n_inputs,
+                          int n, int P, int num_layers, int feature_size,
+                          const void* const* d_weights, const float* const* d_bias,
+                          void* d_workspace, size_t workspace_bytes,
+                          float* d_out_f32, void* stream);
+
+/* Debug / self-test hooks (used by tests only) */
+int dsen2_debug_umma_rowshift(const void* d_a_f16 /*(rows,64)*/, int rows, const void* d_b_f16 /*(128,64)*/,
+                              int shift_rows, int base_offset_mode, float* d_out /*(128,128)*/, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSEN2_B200_H_ */

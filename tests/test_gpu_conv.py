@@ -1,0 +1,177 @@
+"""tcgen05 convolution path against the fp32 CPU oracle (oracle/dsen2net_oracle.py).
+
+Tolerances: single layers are compared with a CPU convolution of the SAME fp16-rounded operands
+(only the fp32 accumulation order and the final fp16 rounding differ): rtol 2e-3 / atol 2e-3.
+Whole networks are held to the north-star gate: max |err| <= 5e-3 on the /2000-scaled output.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GATE = 5e-3
+
+
+@pytest.fixture(scope='module')
+def env():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from dsen2_b200 import _capi
+    return torch, _capi, _capi.lib()
+
+
+def _conv_ref(torch, x_nhwc, w_hwio, bias):
+    """fp32 conv of fp16-rounded operands; x (n,H,W,C) -> (n,H,W,Cout)."""
+    import torch.nn.functional as F
+    x = torch.from_numpy(x_nhwc.astype(np.float32)).permute(0, 3, 1, 2)
+    w = torch.from_numpy(w_hwio.astype(np.float16).astype(np.float32)).permute(3, 2, 0, 1).contiguous()
+    y = F.conv2d(x, w, torch.from_numpy(bias), padding=w_hwio.shape[0] // 2)
+    return y.permute(0, 2, 3, 1).contiguous().numpy()
+
+
+def _pack(torch, _capi, lib, w_hwio, cin_pad, cout_pad):
+    cin, cout = w_hwio.shape[2], w_hwio.shape[3]
+    src = torch.from_numpy(np.ascontiguousarray(w_hwio)).cuda()
+    dst = torch.empty((9, cout_pad, cin_pad), dtype=torch.float16, device='cuda')
+    _capi.check(lib.dsen2_pack_conv_weights(_capi.ptr(src), cin, cout, cin_pad, cout_pad, 0, _capi.ptr(dst), None,
+                                            _capi.stream_ptr()), 'pack')
+    return dst
+
+
+@pytest.mark.parametrize('shift', [0])
+def test_umma_single_tile(env, shift):
+    torch, _capi, lib = env
+    rng = np.random.RandomState(0)
+    a = (rng.rand(160, 64).astype(np.float32) - 0.5).astype(np.float16)
+    b = (rng.rand(128, 64).astype(np.float32) - 0.5).astype(np.float16)
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    out = torch.zeros((128, 128), device='cuda')
+    _capi.check(lib.dsen2_debug_umma_rowshift(_capi.ptr(ta), 160, _capi.ptr(tb), shift, 0, _capi.ptr(out),
+                                              _capi.stream_ptr()), 'umma')
+    torch.cuda.synchronize()
+    ref = a[shift:shift + 128].astype(np.float32) @ b.astype(np.float32).T
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize('shape', [(2, 32, 32), (1, 128, 128), (1, 192, 192), (3, 40, 24), (1, 8, 200)])
+@pytest.mark.parametrize('F', [128, 256])
+def test_conv3x3_relu_layer(env, shape, F):
+    torch, _capi, lib = env
+    n, H, W = shape
+    rng = np.random.RandomState(H * 7 + W + F)
+    x = (rng.randn(n, H, W, F).astype(np.float32)).astype(np.float16)
+    lim = np.sqrt(6.0 / (9 * F))
+    w = rng.uniform(-lim, lim, size=(3, 3, F, F)).astype(np.float32)
+    bias = rng.randn(F).astype(np.float32) * 0.1
+    tx = torch.from_numpy(x).cuda()
+    tw = _pack(torch, _capi, lib, w, F, F)
+    tb = torch.from_numpy(bias).cuda()
+    hi = torch.zeros((n, H, W, F), dtype=torch.float16, device='cuda')
+    lo = torch.zeros_like(hi)
+    _capi.check(lib.dsen2_conv3x3(_capi.ptr(tx), _capi.ptr(tw), _capi.ptr(tb), n, H, W, F, F, 9, _capi.EPI_RELU,
+                                  None, None, 0.0, _capi.ptr(hi), _capi.ptr(lo), None, None, 0, _capi.stream_ptr()),
+                'conv relu')
+    torch.cuda.synchronize()
+    ref = np.maximum(_conv_ref(torch, x, w, bias), 0)
+    got_hi = hi.cpu().numpy().astype(np.float32)
+    np.testing.assert_allclose(got_hi, ref, rtol=2e-3, atol=2e-3)
+    got = got_hi + lo.cpu().numpy().astype(np.float32)               # hi + lo carries ~22 bits
+    np.testing.assert_allclose(got, ref, rtol=1e-4, atol=1e-4)
+
+
+def test_conv3x3_residual_and_tail(env):
+    torch, _capi, lib = env
+    n, H, W, F = 2, 64, 64, 128
+    rng = np.random.RandomState(5)
+    t = np.maximum(rng.randn(n, H, W, F), 0).astype(np.float16)
+    xres = rng.randn(n, H, W, F).astype(np.float32)
+    lim = np.sqrt(6.0 / (9 * F))
+    w = rng.uniform(-lim, lim, size=(3, 3, F, F)).astype(np.float32)
+    bias = rng.randn(F).astype(np.float32) * 0.1
+    x_hi = xres.astype(np.float16)
+    x_lo = (xres - x_hi.astype(np.float32)).astype(np.float16)
+    tt, thi, tlo = (torch.from_numpy(a).cuda() for a in (t, x_hi, x_lo))
+    tw, tb = _pack(torch, _capi, lib, w, F, F), torch.from_numpy(bias).cuda()
+    _capi.check(lib.dsen2_conv3x3(_capi.ptr(tt), _capi.ptr(tw), _capi.ptr(tb), n, H, W, F, F, 9, _capi.EPI_RESIDUAL,
+                                  _capi.ptr(thi), _capi.ptr(tlo), 0.1, _capi.ptr(thi), _capi.ptr(tlo), None, None, 0,
+                                  _capi.stream_ptr()), 'conv residual')
+    torch.cuda.synchronize()
+    xin = x_hi.astype(np.float32) + x_lo.astype(np.float32)
+    ref = xin + np.float32(0.1) * _conv_ref(torch, t, w, bias)
+    got = thi.cpu().numpy().astype(np.float32) + tlo.cpu().numpy().astype(np.float32)
+    np.testing.assert_allclose(got, ref, rtol=1e-4, atol=1e-4)
+    # tail: 128 -> 6 bands + fp32 NCHW global skip
+    wt = rng.uniform(-lim, lim, size=(3, 3, F, 6)).astype(np.float32)
+    bt = rng.randn(6).astype(np.float32) * 0.1
+    skip = rng.rand(n, 6, H, W).astype(np.float32)
+    twt = _pack(torch, _capi, lib, wt, F, 16)
+    tbt = torch.zeros(16, device='cuda')
+    tbt[:6] = torch.from_numpy(bt).cuda()
+    tskip = torch.from_numpy(skip).cuda()
+    out = torch.zeros((n, 6, H, W), device='cuda')
+    xin16 = thi.cpu().numpy()
+    _capi.check(lib.dsen2_conv3x3(_capi.ptr(thi), _capi.ptr(twt), _capi.ptr(tbt), n, H, W, F, 16, 9,
+                                  _capi.EPI_TAIL_NCHW, None, None, 0.0, None, None, _capi.ptr(tskip), _capi.ptr(out),
+                                  6, _capi.stream_ptr()), 'conv tail')
+    torch.cuda.synchronize()
+    ref_t = _conv_ref(torch, xin16, wt, bt).transpose(0, 3, 1, 2) + skip
+    np.testing.assert_allclose(out.cpu().numpy(), ref_t, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize('cfg', [dict(inp=(4, 6), L=2, F=128, P=32, n=3), dict(inp=(4, 6), L=6, F=128, P=128, n=2),
+                                 dict(inp=(4, 6, 2), L=6, F=128, P=192, n=1), dict(inp=(4, 6), L=3, F=256, P=64, n=2)])
+def test_s2model_predict_vs_oracle(env, cfg):
+    from dsen2_b200.DSen2Net import s2model
+    from oracle import dsen2net_oracle as no
+    rng = np.random.RandomState(11)
+    shape = tuple((c, None, None) for c in cfg['inp'])
+    model = s2model(shape, num_layers=cfg['L'], feature_size=cfg['F'], seed=3)
+    # non-zero biases so the bias path is exercised
+    ws = model.get_weights()
+    for i in range(1, len(ws), 2):
+        ws[i] = (rng.randn(*ws[i].shape) * 0.05).astype(np.float32)
+    model.set_weights(ws)
+    xs = [(0.8 + 0.45 * rng.randn(cfg['n'], c, cfg['P'], cfg['P'])).clip(0, 6).astype(np.float32) for c in cfg['inp']]
+    got = model.predict(xs)
+    ref = no.predict(xs, [(ws[2 * i], ws[2 * i + 1]) for i in range(len(ws) // 2)])
+    assert got.shape == ref.shape and got.dtype == np.float32
+    err = np.abs(got - ref).max()
+    print('max abs err', err, 'rms', np.sqrt(np.mean((got - ref) ** 2)))
+    assert err <= GATE
+
+
+def test_DSen2_20_and_60_scene_vs_oracle(env, malmo):
+    from dsen2_b200 import supres
+    from dsen2_b200.DSen2Net import s2model
+    from oracle import dsen2net_oracle as no
+    d10, d20, d60 = malmo
+    for run_60 in (False, True):
+        shape = ((4, None, None), (6, None, None)) + (((2, None, None),) if run_60 else ())
+        model = s2model(shape, num_layers=6, feature_size=128, seed=0)
+        ws = model.get_weights()
+        wl = [(ws[2 * i], ws[2 * i + 1]) for i in range(len(ws) // 2)]
+        if run_60:
+            got = supres.DSen2_60(d10, d20, d60, model=model)
+            ref = no.DSen2_60(d10, d20, d60, wl)
+            assert got.shape == (600, 600, 2)
+        else:
+            got = supres.DSen2_20(d10, d20, model=model)
+            ref = no.DSen2_20(d10, d20, wl)
+            assert got.shape == (600, 600, 6)
+        assert got.dtype == np.float32
+        err = np.abs(got - ref).max() / supres.SCALE
+        print('run_60', run_60, 'max abs err (scaled)', err)
+        assert err <= GATE
+
+
+def test_missing_weight_file_raises_oserror(env):
+    from dsen2_b200 import supres
+    old = supres.MDL_PATH
+    supres.MDL_PATH = '/nonexistent/models/'
+    try:
+        with pytest.raises(OSError):
+            supres.DSen2_20(np.zeros((128, 128, 4), np.float32), np.zeros((64, 64, 6), np.float32))
+    finally:
+        supres.MDL_PATH = old

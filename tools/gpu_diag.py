@@ -1,0 +1,98 @@
+"""GPU bring-up diagnostics (development tool, not a test): each check runs in its own process with a timeout
+so that a hung kernel cannot take the whole gpurun call with it.  Usage: python tools/gpu_diag.py [check ...]"""
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def check_rowshift():
+    import numpy as np
+    import torch
+    from dsen2_b200 import _capi
+    lib = _capi.lib()
+    rng = np.random.RandomState(0)
+    a = (rng.rand(160, 64).astype(np.float32) - 0.5).astype(np.float16)
+    b = (rng.rand(128, 64).astype(np.float32) - 0.5).astype(np.float16)
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    for mode in (0, 1):
+        res = []
+        for shift in list(range(0, 18)) + [24, 31, 32]:
+            out = torch.zeros((128, 128), device='cuda')
+            _capi.check(lib.dsen2_debug_umma_rowshift(_capi.ptr(ta), 160, _capi.ptr(tb), shift, mode, _capi.ptr(out),
+                                                      _capi.stream_ptr()), 'umma')
+            torch.cuda.synchronize()
+            ref = a[shift:shift + 128].astype(np.float32) @ b.astype(np.float32).T
+            err = float(np.abs(out.cpu().numpy() - ref).max())
+            res.append((shift, round(err, 5)))
+        print('base_offset_mode', mode, res, flush=True)
+
+
+def check_conv_timing():
+    import numpy as np
+    import torch
+    from dsen2_b200 import _capi
+    lib = _capi.lib()
+    for F, n in ((128, 64), (256, 32)):
+        P = 128
+        x = torch.randn((n, P, P, F), device='cuda').half()
+        w = (torch.rand((9, F, F), device='cuda') - 0.5).half()
+        b = torch.zeros(F, device='cuda')
+        hi = torch.empty_like(x)
+        def run():
+            _capi.check(lib.dsen2_conv3x3(_capi.ptr(x), _capi.ptr(w), _capi.ptr(b), n, P, P, F, F, 9, 0, None, None,
+                                          0.0, _capi.ptr(hi), None, None, None, 0, _capi.stream_ptr()), 'conv')
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        iters = 10
+        for _ in range(iters):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        fl = 2.0 * n * P * P * 9 * F * F
+        print('conv3x3 F=%d n=%d: %.3f ms  %.1f TFLOP/s' % (F, n, ms, fl / ms / 1e9), flush=True)
+
+
+def check_model_timing():
+    import numpy as np
+    import torch
+    from dsen2_b200.DSen2Net import s2model
+    m = s2model(((4, None, None), (6, None, None)), 6, 128, seed=0)
+    n, P = 64, 128
+    xs = [torch.rand((n, 4, P, P), device='cuda'), torch.rand((n, 6, P, P), device='cuda')]
+    for _ in range(2):
+        m.forward_device(xs)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        m.forward_device(xs)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    fl = 3575808.0 * n * P * P
+    print('DSen2-20 forward n=%d: %.3f ms  %.1f TFLOP/s  %.2f Mpx/s(patch px)' % (n, ms, fl / ms / 1e9, n * P * P / ms / 1e3),
+          flush=True)
+
+
+CHECKS = {k[6:]: v for k, v in globals().items() if k.startswith('check_')}
+
+if __name__ == '__main__':
+    if len(sys.argv) > 2 and sys.argv[1] == '--one':
+        CHECKS[sys.argv[2]]()
+        sys.exit(0)
+    names = sys.argv[1:] or list(CHECKS)
+    for nme in names:
+        t = time.time()
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), '--one', nme], timeout=240)
+            print('[diag] %s exit %d in %.1fs' % (nme, r.returncode, time.time() - t), flush=True)
+        except subprocess.TimeoutExpired:
+            print('[diag] %s TIMEOUT' % nme, flush=True)

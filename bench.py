@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""Headline benchmark: output Mpixel/s of DSen2 20 m -> 10 m super-resolution of a synthetic full
+10980 x 10980 Sentinel-2 tile (BASELINE.json configs[2]), patches sharded across N B200s of one node.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
+
+One "step" = one pass of the hot path over the whole tile: extract(/2000) -> bilinear(/2000) -> 14 tcgen05
+convolutions -> stitch(x2000) for every patch the rank owns.  Rank 0 prints ONE JSON line.
+  value  : device-resident inputs/outputs, CUDA-event timed, max over ranks.
+  e2e    : same step through pinned HOST buffers (H2D of the rank's input rows + D2H of its output rows).
+  roofline: the resblock convolution kernel (12 of the 14 convs), CUDA events inside the timed region.
+  cpu_baseline: the CPU oracle (torch-CPU restatement of the Keras graph + numpy patch ops) on a bounded crop.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_PIXEL = {('dsen2', 20): 3575808, ('vdsen2', 20): 75571200, ('dsen2', 60): 3571200}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as fh:
+            p = json.load(fh)
+        return dict(hbm=p['hbm_gbs'], tf_burst=p['bf16_tflops'], tf_sust=p.get('bf16_tflops_sustained', p['bf16_tflops']),
+                    source='measured (MEASURED_PEAKS.json)')
+    except Exception:
+        return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, source='fallback (B200_PROFILING.md)')
+
+
+def synth_tile(torch, H, W, device, seed=20170928):
+    """integer DN, 1600 + 900*smooth + 150*noise clipped to [0, 12000]."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    F = torch.nn.functional
+
+    def field(h, w, c):
+        lo = torch.randn((1, c, h // 64 + 2, w // 64 + 2), generator=g, device=device)
+        smooth = F.interpolate(lo, size=(h, w), mode='bilinear', align_corners=False)[0]
+        out = torch.empty((h, w, c), device=device)
+        for k in range(c):                         # band by band to bound the temporaries
+            noise = torch.randn((h, w), generator=g, device=device)
+            out[:, :, k] = (1600 + 900 * smooth[k] + 150 * noise).clamp_(0, 12000).round_()
+        return out
+    return field(H, W, 4), field(H // 2, W // 2, 6)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, uuid):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', uuid, '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception as e:                      # pragma: no cover
+            log('clock sampler unavailable:', e)
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith('active'):
+                        reasons.add(nme)
+            except Exception:
+                continue
+        loaded = [s for s, p in zip(sm, pw) if p > 0.5 * max(pw)] if pw else sm
+        return {"sm_mhz": float(np.median(loaded)) if loaded else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------- #
+# CPU oracle legs
+# ---------------------------------------------------------------------------------------------- #
+def cpu_oracle_run(crop, steps, warmup, deep=False):
+    """Time the CPU oracle end to end on a crop x crop (10 m) synthetic scene; returns (Mpixel/s, s/step, threads)."""
+    import torch
+    from oracle import dsen2net_oracle as no
+    torch.set_num_threads(os.cpu_count() or 1)
+    rng = np.random.RandomState(20170928)
+    d10 = rng.randint(200, 6000, size=(crop, crop, 4)).astype(np.float32)
+    d20 = rng.randint(200, 6000, size=(crop // 2, crop // 2, 6)).astype(np.float32)
+    w = no.he_uniform_weights(10, 6, 32 if deep else 6, 256 if deep else 128, seed=0)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = no.DSen2_20(d10, d20, w)
+        dt = time.perf_counter() - t0
+        assert out.shape == (crop, crop, 6)
+        if i >= warmup:
+            times.append(dt)
+    per = float(np.mean(times))
+    return crop * crop / per / 1e6, per, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    crop = 448                                       # 16 patches of 128x128 per step (bounded sample)
+    mpx, per, threads = cpu_oracle_run(crop, args.steps, args.warmup, deep=args.model == 'vdsen2')
+    sample = ("%dx%d crop (16 patches) of the synthetic tile through the CPU oracle port "
+              "(numpy extract/bilinear/stitch + torch-CPU fp32 conv graph); TensorFlow/Keras not installable" % (crop, crop))
+    line = {"impl": "reference", "metric": "output_Mpixel_per_s", "value": mpx, "unit": "Mpixel/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": workload_config(args, cpu=True),
+            "cpu_baseline": {"value": mpx, "unit": "Mpixel/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": mpx, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, cpu=False):
+    T = args.tile
+    n = (-(-T // 112)) ** 2
+    return {"workload": "%s 20m->10m, synthetic %dx%d Sentinel-2 tile, %d patches 128x128 (border 8), "
+                        "he_uniform weights seed 0 (shipped hdf5 absent)" % ('VDSen2 (32x256)' if args.model == 'vdsen2'
+                                                                             else 'DSen2 (6x128)', T, T, n),
+            "tile": T, "patches": n, "device_batch": args.batch, "sharding": "contiguous patch ranges, no collective",
+            "l2": "inputs (2.6 GB) and activations larger than L2; no flush needed",
+            "cpu_sample_only": bool(cpu)}
+
+
+# ---------------------------------------------------------------------------------------------- #
+# GPU arm
+# ---------------------------------------------------------------------------------------------- #
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from dsen2_b200 import sharding, supres
+    from dsen2_b200.DSen2Net import s2model
+    from dsen2_b200.patches import patch_counts
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    T, P, B = args.tile, 128, 8
+    deep = args.model == 'vdsen2'
+    model = s2model(((4, None, None), (6, None, None)), num_layers=32 if deep else 6,
+                    feature_size=256 if deep else 128, seed=0)
+    d10, d20 = synth_tile(torch, T, T, dev)
+    _, filled = patch_counts(T // 2, T // 2, 64, 4)
+    first, count = sharding.shard_range(filled, rank, world)
+    out = torch.zeros((T, T, 6), dtype=torch.float32, device=dev)
+    n_batches = -(-count // args.batch)
+    launches_per_step = n_batches * (4 + model.launches_per_forward())   # 2 extract + bilinear + recompose + net
+
+    def step(timers=None):
+        supres.super_resolve_device(model, d10, d20, first_patch=first, num_patches=count, out=out,
+                                    device_batch=args.batch, timers=timers)
+
+    # ---- value: device-resident ---------------------------------------------------------------
+    for _ in range(args.warmup):
+        step()
+    timers = {}
+    barrier()
+    uuid = str(torch.cuda.get_device_properties(dev).uuid)
+    sampler = ClockSampler(uuid if uuid.startswith('GPU-') else 'GPU-' + uuid) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(timers)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_step = ms_total / args.steps
+    value = T * T / (ms_step * 1e-3) / 1e6
+
+    # roofline of the dominant kernel (resblock convolutions), from the events recorded in the timed region
+    pk = peaks()
+    F = model.feature_size
+    conv_ms, conv_n = [], []
+    for kind in ('conv_res1', 'conv_res2'):
+        for a, b, n in timers.get(kind, []):
+            conv_ms.append(a.elapsed_time(b)); conv_n.append(n)
+    kernel_ms = float(np.mean(conv_ms))
+    per_kind = {k: float(np.sum([a.elapsed_time(b) for a, b, _ in v])) / args.steps for k, v in timers.items()}
+    exec_flop = 2.0 * 9 * F * F * P * P * float(np.mean(conv_n))                 # executed per launch
+    algo_flop = exec_flop * (P - 2 * B) ** 2 / (P * P)                           # minus the patch-overlap recompute
+    roofline = {"bound": "tensor", "kernel": "conv_tcgen05_kernel<%d> (resblock 3x3 conv, %d of %d convs)" % (F, 2 * model.num_layers, 2 * model.num_layers + 2),
+                "achieved": algo_flop / kernel_ms / 1e9, "achieved_executed": exec_flop / kernel_ms / 1e9,
+                "peak": pk['tf_sust'], "peak_burst": pk['tf_burst'], "peak_source": pk['source'] + ", sustained figure (kernel timed inside a long step)",
+                "unit": "TFLOP/s", "frac": algo_flop / kernel_ms / 1e9 / pk['tf_sust'],
+                "frac_executed": exec_flop / kernel_ms / 1e9 / pk['tf_sust'],
+                "avg_launch_ms": kernel_ms, "patches_per_launch": float(np.mean(conv_n)),
+                "algorithmic_flop_per_launch": algo_flop, "traffic": None,
+                "ms_per_step_by_kernel": per_kind}
+
+    # ---- e2e: pinned host -> device -> pinned host every step ------------------------------------
+    r0, r1 = sharding.input_rows(first, count, T, T, P, B)
+    y0, y1 = sharding.output_rows(first, count, T, T, P, B)
+    h10 = torch.empty((r1 - r0, T, 4), dtype=torch.float32).pin_memory()
+    h20 = torch.empty((r1 // 2 - r0 // 2, T // 2, 6), dtype=torch.float32).pin_memory()
+    hout = torch.empty((y1 - y0, T, 6), dtype=torch.float32).pin_memory()
+    h10.copy_(d10[r0:r1]); h20.copy_(d20[r0 // 2:r1 // 2])
+    torch.cuda.synchronize()
+
+    def step_e2e():
+        d10[r0:r1].copy_(h10, non_blocking=True)
+        d20[r0 // 2:r1 // 2].copy_(h20, non_blocking=True)
+        step()
+        hout.copy_(out[y0:y1], non_blocking=True)
+
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    h2d = h10.numel() * 4 + h20.numel() * 4
+    d2h = hout.numel() * 4
+    if world > 1:
+        tb = torch.tensor([h2d, d2h], dtype=torch.float64, device=dev)
+        dist.all_reduce(tb)
+        h2d, d2h = int(tb[0].item()), int(tb[1].item())
+    checksum = float(hout[::97, ::89].double().sum())
+
+    if rank == 0:
+        line = {"metric": "output_Mpixel_per_s", "value": value, "unit": "Mpixel/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "fp16 (fp32 accumulate, fp16 hi+lo residual trunk)",
+                "data": "synthetic", "config": workload_config(args), "clocks": clocks,
+                "e2e": {"value": T * T / (e2e_ms * 1e-3) / 1e6, "unit": "Mpixel/s", "ms_per_step": e2e_ms,
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": launches_per_step * args.steps, "roofline": roofline,
+                "tflops_executed_whole_step": FLOP_PER_PIXEL[(args.model, 20)] * float(filled) * P * P / (ms_step * 1e-3) / 1e12,
+                "checksum": checksum}
+        if world == 1 and not args.no_cpu_baseline:
+            crop = 672
+            mpx, per, threads = cpu_oracle_run(crop, 1, 0, deep=deep)
+            line["cpu_baseline"] = {"value": mpx, "unit": "Mpixel/s", "cores": threads, "kind": "port",
+                                    "sample": "%dx%d crop (36 patches) through the CPU oracle port, %.1f s; "
+                                              "extrapolates linearly to the tile" % (crop, crop, per)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--model', default='dsen2', choices=['dsen2', 'vdsen2'])
+    ap.add_argument('--tile', type=int, default=10980)
+    ap.add_argument('--batch', type=int, default=64, help='patches per device batch')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

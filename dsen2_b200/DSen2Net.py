@@ -137,8 +137,26 @@ class S2Model:
     def workspace_bytes(self, n, P):
         return int(_capi.lib().dsen2_s2model_workspace_bytes(n, P, sum(self.in_channels), self.feature_size))
 
-    def forward_device(self, xs, out=None):
-        """xs: list of CUDA float32 (n, C_i, P, P) contiguous tensors -> CUDA float32 (n, Cout, P, P)."""
+    def _buffers(self, dev, n, P):
+        torch = _capi.require_cuda()
+        key = (dev.index, torch.cuda.current_stream().cuda_stream, n, P)
+        buf = self._workspace.get(key)
+        if buf is None:
+            if len(self._workspace) > 8:
+                self._workspace.clear()
+            F = self.feature_size
+            k_pad = (9 * sum(self.in_channels) + 63) // 64 * 64
+            mk = lambda c: torch.empty((n, P, P, c), dtype=torch.float16, device=dev)
+            buf = dict(a0=mk(k_pad), x_hi=mk(F), x_lo=mk(F), t=mk(F), k_pad=k_pad)
+            self._workspace[key] = buf
+        return buf
+
+    def forward_device(self, xs, out=None, timers=None):
+        """xs: list of CUDA float32 (n, C_i, P, P) contiguous tensors -> CUDA float32 (n, Cout, P, P).
+
+        One launch per layer (head im2col pack + 2*num_layers+2 tcgen05 convolutions) on the current
+        stream.  ``timers`` (optional dict) collects CUDA-event pairs per kernel kind for bench.py.
+        The same sequence is available to C callers as ``dsen2_s2model_forward``."""
         torch = _capi.require_cuda()
         if len(xs) != len(self.in_channels):
             raise ValueError("model expects %d inputs, got %d" % (len(self.in_channels), len(xs)))
@@ -149,24 +167,48 @@ class S2Model:
             if tuple(x.shape) != (n, c, P, P) or P != P2:
                 raise ValueError("expected input of shape %s, got %s" % ((n, c, P, P), tuple(x.shape)))
         dev = xs[0].device
-        _wts, _b, wp, bp = self._ensure_packed(dev)
+        wts, biases, _wp, _bp = self._ensure_packed(dev)
         if out is None:
             out = torch.empty((n, self.out_channels, P, P), dtype=torch.float32, device=dev)
         if n == 0:
             return out
-        need = self.workspace_bytes(n, P)
-        key = (dev.index, torch.cuda.current_stream().cuda_stream)
-        ws = self._workspace.get(key)
-        if ws is None or ws.numel() < need:
-            ws = torch.empty((need,), dtype=torch.uint8, device=dev)
-            self._workspace[key] = ws
-        xp = (ctypes.c_void_p * len(xs))(*[x.data_ptr() for x in xs])
-        ch = (ctypes.c_int * len(xs))(*self.in_channels)
+        lib, ptr = _capi.lib(), _capi.ptr
+        buf = self._buffers(dev, n, P)
+        F, L, k_pad = self.feature_size, self.num_layers, buf['k_pad']
+        a0, x_hi, x_lo, t = buf['a0'], buf['x_hi'], buf['x_lo'], buf['t']
+
+        def timed(kind, fn):
+            if timers is None:
+                return fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            timers.setdefault(kind, []).append((e0, e1, n))
+
         with torch.cuda.device(dev):
-            rc = _capi.lib().dsen2_s2model_forward(xp, ch, len(xs), n, P, self.num_layers, self.feature_size, wp, bp,
-                                                   _capi.ptr(ws), ws.numel(), _capi.ptr(out), _capi.stream_ptr())
-        _capi.check(rc, "dsen2_s2model_forward")
+            st = _capi.stream_ptr()
+            x2, c2 = (xs[2], self.in_channels[2]) if len(xs) == 3 else (None, 0)
+            timed('pack_head', lambda: _capi.check(lib.dsen2_pack_head_input(
+                ptr(xs[0]), self.in_channels[0], ptr(xs[1]), self.in_channels[1], ptr(x2), c2, n, P, k_pad,
+                ptr(a0), None, st), "dsen2_pack_head_input"))
+            timed('conv_head', lambda: _capi.check(lib.dsen2_conv3x3(
+                ptr(a0), ptr(wts[0]), ptr(biases[0]), n, P, P, k_pad, F, 1, _capi.EPI_RELU, None, None, 0.0,
+                ptr(x_hi), ptr(x_lo), None, None, 0, st), "dsen2_conv3x3(head)"))
+            for l in range(L):
+                timed('conv_res1', lambda: _capi.check(lib.dsen2_conv3x3(
+                    ptr(x_hi), ptr(wts[1 + 2 * l]), ptr(biases[1 + 2 * l]), n, P, P, F, F, 9, _capi.EPI_RELU, None,
+                    None, 0.0, ptr(t), None, None, None, 0, st), "dsen2_conv3x3(res conv1)"))
+                timed('conv_res2', lambda: _capi.check(lib.dsen2_conv3x3(
+                    ptr(t), ptr(wts[2 + 2 * l]), ptr(biases[2 + 2 * l]), n, P, P, F, F, 9, _capi.EPI_RESIDUAL,
+                    ptr(x_hi), ptr(x_lo), 0.1, ptr(x_hi), ptr(x_lo), None, None, 0, st), "dsen2_conv3x3(res conv2)"))
+            timed('conv_tail', lambda: _capi.check(lib.dsen2_conv3x3(
+                ptr(x_hi), ptr(wts[-1]), ptr(biases[-1]), n, P, P, F, 16, 9, _capi.EPI_TAIL_NCHW, None, None, 0.0,
+                None, None, ptr(xs[-1]), ptr(out), self.out_channels, st), "dsen2_conv3x3(tail)"))
         return out
+
+    def launches_per_forward(self):
+        return 2 * self.num_layers + 3
 
     def predict(self, x, batch_size=32, verbose=0, device_batch=None):
         """``model.predict([x10, x20(, x60)])`` -> (N, Cout, P, P) float32 numpy (supres.py:65).

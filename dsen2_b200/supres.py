@@ -40,7 +40,8 @@ def _load_model(input_shape, deep, run_60):
     return _model_cache[key]
 
 
-def super_resolve_device(model, d10, d20, d60=None, first_patch=0, num_patches=None, out=None, device_batch=None):
+def super_resolve_device(model, d10, d20, d60=None, first_patch=0, num_patches=None, out=None, device_batch=None,
+                         timers=None):
     """Device-level pipeline.  d10/d20(/d60): CUDA float32 HWC tensors.  Processes patches
     [first_patch, first_patch+num_patches) of the FILLED patch list (surplus zero patches of
     patches.py:32-39 are never read by recompose_images, so they are skipped) and writes the pixels those
@@ -73,7 +74,7 @@ def super_resolve_device(model, d10, d20, d60=None, first_patch=0, num_patches=N
         else:
             xs = [extract_patches_device(d10, 2, plr, blr, p0, nb, divisor=SCALE),
                   bilinear_up_device(extract_patches_device(d20, 1, plr, blr, p0, nb), 2, post_divisor=SCALE)]
-        pred = model.forward_device(xs)
+        pred = model.forward_device(xs, timers=timers)
         if single:
             return (pred[0] * float(SCALE)).permute(1, 2, 0).contiguous()
         recompose_device(pred, B, H, W, first_patch=p0, mul=float(SCALE), out=out)

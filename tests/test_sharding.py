@@ -1,0 +1,114 @@
+"""Host-side multi-rank logic on CPU: contiguous patch sharding, ownership rectangles, gloo world_size-2 assembly."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from dsen2_b200 import sharding
+from oracle import patches_oracle as po
+
+GEOMS = [(300, 412, 128, 8), (560, 560, 128, 8), (600, 348, 192, 12), (10980, 10980, 128, 8), (10980, 10980, 192, 12)]
+
+
+def test_shard_range_is_a_partition():
+    for n in (1, 7, 36, 9801, 4356):
+        for world in (1, 2, 3, 4, 8):
+            spans = [sharding.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and sum(c for _, c in spans) == n
+            assert all(spans[i][0] + spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+
+
+@pytest.mark.parametrize('geom', GEOMS)
+@pytest.mark.parametrize('world', [1, 2, 8])
+def test_owned_rects_tile_the_image_exactly_once(geom, world):
+    H, W, P, B = geom
+    ny, nx, S = sharding.tile_grid(H, W, P, B)
+    n = ny * nx
+    cover = np.zeros((H, W), np.uint8)
+    for r in range(world):
+        f, c = sharding.shard_range(n, r, world)
+        for (y0, y1, x0, x1) in sharding.owned_rects(f, c, H, W, P, B):
+            cover[y0:y1, x0:x1] += 1
+        r0, r1 = sharding.input_rows(f, c, H, W, P, B)
+        y0, y1 = sharding.output_rows(f, c, H, W, P, B)
+        assert 0 <= r0 <= y0 < y1 <= r1 <= H
+    assert cover.min() == 1 and cover.max() == 1
+
+
+def test_ownership_equals_sequential_overwrite():
+    for (H, W, P, B) in GEOMS[:3]:
+        ny, nx, S = sharding.tile_grid(H, W, P, B)
+        n = ny * nx
+        pred = np.empty((n, 1, P, P), np.float32)
+        for i in range(n):
+            pred[i] = i
+        ref = po.recompose_images(pred, B, (H, W))[:, :, 0]
+        for world in (2, 3):
+            for r in range(world):
+                f, c = sharding.shard_range(n, r, world)
+                for (y0, y1, x0, x1) in sharding.owned_rects(f, c, H, W, P, B):
+                    v = ref[y0:y1, x0:x1]
+                    assert v.min() >= f and v.max() < f + c
+
+
+def _worker(rank, world, port, tmp):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    H, W, P, B = 300, 412, 128, 8
+    ny, nx, S = sharding.tile_grid(H, W, P, B)
+    n = ny * nx
+    rng = np.random.RandomState(5)
+    pred = rng.rand(n, 3, P, P).astype(np.float32)                 # every rank regenerates the same "prediction"
+    f, c = sharding.shard_range(n, rank, world)
+    # what the rank's GPU would hold after super_resolve_device on its patch range: owned pixels only
+    canvas = np.zeros((H, W, 3), np.float32)
+    full = po.recompose_images(pred, B, (H, W))
+    for (y0, y1, x0, x1) in sharding.owned_rects(f, c, H, W, P, B):
+        canvas[y0:y1, x0:x1] = full[y0:y1, x0:x1]
+    y0, y1 = sharding.output_rows(f, c, H, W, P, B)
+    band = torch.from_numpy(np.ascontiguousarray(canvas[y0:y1]))
+    meta = [None] * world
+    dist.all_gather_object(meta, (f, c, y0, y1))
+    if rank == 0:
+        parts = [(f, c, y0, band.numpy(), P, B)]
+        for src in range(1, world):
+            fs, cs, ys0, ys1 = meta[src]
+            buf = torch.empty((ys1 - ys0, W, 3))
+            dist.recv(buf, src=src)
+            parts.append((fs, cs, ys0, buf.numpy(), P, B))
+        out = sharding.assemble(np.zeros((H, W, 3), np.float32), parts)
+        np.save(os.path.join(tmp, 'ok.npy'), np.array([np.array_equal(out, full)]))
+    else:
+        dist.send(band, dst=0)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_assembly(tmp_path):
+    import torch.multiprocessing as mp
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert np.load(str(tmp_path / 'ok.npy'))[0]
+
+
+def test_compat_shims_importable():
+    compat = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'dsen2_b200', 'compat')
+    sys.path.insert(0, compat)
+    try:
+        for m in ('supres', 'utils', 'utils.DSen2Net', 'utils.patches', 'utils.imresize'):
+            sys.modules.pop(m, None)
+        import supres as s
+        from utils.DSen2Net import s2model
+        from utils.imresize import imresize
+        from utils.patches import get_test_patches, get_test_patches60, recompose_images
+        assert s.SCALE == 2000 and callable(s.DSen2_20) and callable(s.DSen2_60)
+        assert callable(s2model) and callable(imresize) and callable(get_test_patches)
+        assert callable(get_test_patches60) and callable(recompose_images)
+    finally:
+        sys.path.remove(compat)
+        for m in ('supres', 'utils', 'utils.DSen2Net', 'utils.patches', 'utils.imresize'):
+            sys.modules.pop(m, None)

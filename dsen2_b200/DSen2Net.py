@@ -101,6 +101,12 @@ class S2Model:
         write_hdf5(filepath, tree, attrs)
 
     # ---- device side ------------------------------------------------------------------- #
+    @property
+    def fast_path(self):
+        """DSen2 (128 features): CTA-pair kernels with split-precision first / last layer (csrc/conv_pair.cu).
+        VDSen2 (256 features) runs the single-CTA streaming kernel (csrc/conv_tcgen05.cu)."""
+        return self.feature_size == 128 and sum(self.in_channels) <= 16 and self.out_channels <= 16
+
     def _ensure_packed(self, device):
         torch = _capi.require_cuda()
         key = device.index if device.index is not None else torch.cuda.current_device()
@@ -112,17 +118,28 @@ class S2Model:
         k_pad = (9 * ctot + 63) // 64 * 64
         wts, biases = [], []
         with torch.cuda.device(device):
+            st = _capi.stream_ptr()
             for i, (k, b) in enumerate(self._weights):
                 cin, cout = self.layer_shapes[i]
                 head, tail = i == 0, i == len(self._weights) - 1
-                cin_pad = k_pad if head else F
-                cout_pad = 16 if tail else F
-                taps = 1 if head else 9
                 src = torch.from_numpy(k).to(device)
-                dst = torch.empty((taps, cout_pad, cin_pad), dtype=torch.float16, device=device)
-                _capi.check(lib.dsen2_pack_conv_weights(_capi.ptr(src), cin, cout, cin_pad, cout_pad, int(head),
-                                                        _capi.ptr(dst), None, _capi.stream_ptr()),
-                            "dsen2_pack_conv_weights")
+                if head and self.fast_path:
+                    dst = torch.empty((3, 2 * F, 64), dtype=torch.float16, device=device)
+                    _capi.check(lib.dsen2_pack_head_weights(_capi.ptr(src), cin, F, _capi.ptr(dst), st),
+                                "dsen2_pack_head_weights")
+                    cout_pad = F
+                elif tail and self.fast_path:
+                    dst = torch.empty((9, 32, F), dtype=torch.float16, device=device)
+                    _capi.check(lib.dsen2_pack_tail_weights(_capi.ptr(src), F, cout, _capi.ptr(dst), st),
+                                "dsen2_pack_tail_weights")
+                    cout_pad = 16
+                else:
+                    cin_pad = k_pad if head else F
+                    cout_pad = 16 if tail else F
+                    taps = 1 if head else 9
+                    dst = torch.empty((taps, cout_pad, cin_pad), dtype=torch.float16, device=device)
+                    _capi.check(lib.dsen2_pack_conv_weights(_capi.ptr(src), cin, cout, cin_pad, cout_pad, int(head),
+                                                            _capi.ptr(dst), None, st), "dsen2_pack_conv_weights")
                 bp = torch.zeros((max(cout_pad, 16),), dtype=torch.float32, device=device)
                 bp[:cout] = torch.from_numpy(b).to(device)
                 wts.append(dst)
@@ -145,17 +162,51 @@ class S2Model:
             if len(self._workspace) > 8:
                 self._workspace.clear()
             F = self.feature_size
-            k_pad = (9 * sum(self.in_channels) + 63) // 64 * 64
             mk = lambda c: torch.empty((n, P, P, c), dtype=torch.float16, device=dev)
-            buf = dict(a0=mk(k_pad), x_hi=mk(F), x_lo=mk(F), t=mk(F), k_pad=k_pad)
+            if self.fast_path:
+                buf = dict(xin_hi=mk(64), xin_lo=mk(64), x_hi=mk(F), x_lo=mk(F), t=mk(F))
+            else:
+                k_pad = (9 * sum(self.in_channels) + 63) // 64 * 64
+                buf = dict(a0=mk(k_pad), x_hi=mk(F), x_lo=mk(F), t=mk(F), k_pad=k_pad)
             self._workspace[key] = buf
         return buf
+
+    @staticmethod
+    def _timed(timers, kind, n, fn):
+        if timers is None:
+            return fn()
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        timers.setdefault(kind, []).append((e0, e1, n))
+
+    def _trunk(self, buf, wts, biases, n, P, st, timers, first=None):
+        """head (if ``first`` is None: from x_in) + resblocks on the buffers; shared by both input forms."""
+        lib, ptr, F, L = _capi.lib(), _capi.ptr, self.feature_size, self.num_layers
+        x_hi, x_lo, t = buf['x_hi'], buf['x_lo'], buf['t']
+        if self.fast_path:
+            self._timed(timers, 'conv_head', n, lambda: _capi.check(lib.dsen2_conv_head(
+                ptr(buf['xin_hi']), ptr(buf['xin_lo']), ptr(wts[0]), ptr(biases[0]), n, P, P, F, ptr(x_hi), ptr(x_lo),
+                st), "dsen2_conv_head"))
+        else:
+            self._timed(timers, 'conv_head', n, lambda: _capi.check(lib.dsen2_conv3x3(
+                ptr(buf['a0']), ptr(wts[0]), ptr(biases[0]), n, P, P, buf['k_pad'], F, 1, _capi.EPI_RELU, None, None,
+                0.0, ptr(x_hi), ptr(x_lo), None, None, 0, st), "dsen2_conv3x3(head)"))
+        for l in range(L):
+            self._timed(timers, 'conv_res1', n, lambda: _capi.check(lib.dsen2_conv3x3(
+                ptr(x_hi), ptr(wts[1 + 2 * l]), ptr(biases[1 + 2 * l]), n, P, P, F, F, 9, _capi.EPI_RELU, None,
+                None, 0.0, ptr(t), None, None, None, 0, st), "dsen2_conv3x3(res conv1)"))
+            self._timed(timers, 'conv_res2', n, lambda: _capi.check(lib.dsen2_conv3x3(
+                ptr(t), ptr(wts[2 + 2 * l]), ptr(biases[2 + 2 * l]), n, P, P, F, F, 9, _capi.EPI_RESIDUAL,
+                ptr(x_hi), ptr(x_lo), 0.1, ptr(x_hi), ptr(x_lo), None, None, 0, st), "dsen2_conv3x3(res conv2)"))
 
     def forward_device(self, xs, out=None, timers=None):
         """xs: list of CUDA float32 (n, C_i, P, P) contiguous tensors -> CUDA float32 (n, Cout, P, P).
 
-        One launch per layer (head im2col pack + 2*num_layers+2 tcgen05 convolutions) on the current
-        stream.  ``timers`` (optional dict) collects CUDA-event pairs per kernel kind for bench.py.
+        One launch per layer on the current stream (input preparation + 2*num_layers+2 tcgen05
+        convolutions).  ``timers`` (optional dict) collects CUDA-event pairs per kernel kind for bench.py.
         The same sequence is available to C callers as ``dsen2_s2model_forward``."""
         torch = _capi.require_cuda()
         if len(xs) != len(self.in_channels):
@@ -174,41 +225,57 @@ class S2Model:
             return out
         lib, ptr = _capi.lib(), _capi.ptr
         buf = self._buffers(dev, n, P)
-        F, L, k_pad = self.feature_size, self.num_layers, buf['k_pad']
-        a0, x_hi, x_lo, t = buf['a0'], buf['x_hi'], buf['x_lo'], buf['t']
-
-        def timed(kind, fn):
-            if timers is None:
-                return fn()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            fn()
-            e1.record()
-            timers.setdefault(kind, []).append((e0, e1, n))
-
+        F = self.feature_size
         with torch.cuda.device(dev):
             st = _capi.stream_ptr()
             x2, c2 = (xs[2], self.in_channels[2]) if len(xs) == 3 else (None, 0)
-            timed('pack_head', lambda: _capi.check(lib.dsen2_pack_head_input(
-                ptr(xs[0]), self.in_channels[0], ptr(xs[1]), self.in_channels[1], ptr(x2), c2, n, P, k_pad,
-                ptr(a0), None, st), "dsen2_pack_head_input"))
-            timed('conv_head', lambda: _capi.check(lib.dsen2_conv3x3(
-                ptr(a0), ptr(wts[0]), ptr(biases[0]), n, P, P, k_pad, F, 1, _capi.EPI_RELU, None, None, 0.0,
-                ptr(x_hi), ptr(x_lo), None, None, 0, st), "dsen2_conv3x3(head)"))
-            for l in range(L):
-                timed('conv_res1', lambda: _capi.check(lib.dsen2_conv3x3(
-                    ptr(x_hi), ptr(wts[1 + 2 * l]), ptr(biases[1 + 2 * l]), n, P, P, F, F, 9, _capi.EPI_RELU, None,
-                    None, 0.0, ptr(t), None, None, None, 0, st), "dsen2_conv3x3(res conv1)"))
-                timed('conv_res2', lambda: _capi.check(lib.dsen2_conv3x3(
-                    ptr(t), ptr(wts[2 + 2 * l]), ptr(biases[2 + 2 * l]), n, P, P, F, F, 9, _capi.EPI_RESIDUAL,
-                    ptr(x_hi), ptr(x_lo), 0.1, ptr(x_hi), ptr(x_lo), None, None, 0, st), "dsen2_conv3x3(res conv2)"))
-            timed('conv_tail', lambda: _capi.check(lib.dsen2_conv3x3(
-                ptr(x_hi), ptr(wts[-1]), ptr(biases[-1]), n, P, P, F, 16, 9, _capi.EPI_TAIL_NCHW, None, None, 0.0,
-                None, None, ptr(xs[-1]), ptr(out), self.out_channels, st), "dsen2_conv3x3(tail)"))
+            if self.fast_path:
+                self._timed(timers, 'prep', n, lambda: _capi.check(lib.dsen2_prep_from_patches(
+                    ptr(xs[0]), self.in_channels[0], ptr(xs[1]), self.in_channels[1], ptr(x2), c2, n, P,
+                    ptr(buf['xin_hi']), ptr(buf['xin_lo']), st), "dsen2_prep_from_patches"))
+                self._trunk(buf, wts, biases, n, P, st, timers)
+                self._timed(timers, 'conv_tail', n, lambda: _capi.check(lib.dsen2_conv_tail(
+                    ptr(buf['x_hi']), ptr(buf['x_lo']), ptr(wts[-1]), ptr(biases[-1]), ptr(buf['xin_hi']),
+                    ptr(buf['xin_lo']), sum(self.in_channels) - self.out_channels, self.out_channels, n, P, P,
+                    ptr(out), st), "dsen2_conv_tail"))
+            else:
+                self._timed(timers, 'pack_head', n, lambda: _capi.check(lib.dsen2_pack_head_input(
+                    ptr(xs[0]), self.in_channels[0], ptr(xs[1]), self.in_channels[1], ptr(x2), c2, n, P, buf['k_pad'],
+                    ptr(buf['a0']), None, st), "dsen2_pack_head_input"))
+                self._trunk(buf, wts, biases, n, P, st, timers)
+                self._timed(timers, 'conv_tail', n, lambda: _capi.check(lib.dsen2_conv3x3(
+                    ptr(buf['x_hi']), ptr(wts[-1]), ptr(biases[-1]), n, P, P, F, 16, 9, _capi.EPI_TAIL_NCHW, None, None,
+                    0.0, None, None, ptr(xs[-1]), ptr(out), self.out_channels, st), "dsen2_conv3x3(tail)"))
         return out
 
+    def forward_images(self, d10, d20, d60, patch, border, first_patch, n, canvas, mul, timers=None):
+        """Fused tile pipeline of the fast path: patches [first_patch, first_patch+n) are gathered straight
+        from the HWC images (extract + bilinear + /mul), run through the network, and the pixels they own
+        are written x mul into ``canvas`` (H, W, Cout).  No patch stack or prediction stack exists."""
+        torch = _capi.require_cuda()
+        if not self.fast_path:
+            raise _capi.DSen2Error("forward_images needs the 128-feature fast path")
+        dev = d10.device
+        H, W = int(d10.shape[0]), int(d10.shape[1])
+        wts, biases, _wp, _bp = self._ensure_packed(dev)
+        if n == 0:
+            return canvas
+        lib, ptr = _capi.lib(), _capi.ptr
+        buf = self._buffers(dev, n, patch)
+        with torch.cuda.device(dev):
+            st = _capi.stream_ptr()
+            self._timed(timers, 'prep', n, lambda: _capi.check(lib.dsen2_prep_from_images(
+                ptr(d10), ptr(d20), ptr(d60), H, W, patch, border, first_patch, n, float(mul), ptr(buf['xin_hi']),
+                ptr(buf['xin_lo']), st), "dsen2_prep_from_images"))
+            self._trunk(buf, wts, biases, n, patch, st, timers)
+            self._timed(timers, 'conv_tail', n, lambda: _capi.check(lib.dsen2_conv_tail_stitch(
+                ptr(buf['x_hi']), ptr(buf['x_lo']), ptr(wts[-1]), ptr(biases[-1]), ptr(buf['xin_hi']),
+                ptr(buf['xin_lo']), sum(self.in_channels) - self.out_channels, self.out_channels, n, patch,
+                first_patch, border, H, W, float(mul), ptr(canvas), st), "dsen2_conv_tail_stitch"))
+        return canvas
+
     def launches_per_forward(self):
-        return 2 * self.num_layers + 3
+        return 2 * self.num_layers + 3          # input preparation + head + 2 per resblock + tail
 
     def predict(self, x, batch_size=32, verbose=0, device_batch=None):
         """``model.predict([x10, x20(, x60)])`` -> (N, Cout, P, P) float32 numpy (supres.py:65).

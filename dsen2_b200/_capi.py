@@ -28,6 +28,19 @@ SIGNATURES = {
     "dsen2_s2model_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "dsen2_s2model_forward": (c_int, [POINTER(c_void_p), POINTER(c_int), c_int, c_int, c_int, c_int, c_int,
                                       POINTER(c_void_p), POINTER(c_void_p), c_void_p, c_size_t, c_void_p, c_void_p]),
+    "dsen2_prep_from_patches": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p,
+                                        c_void_p, c_void_p]),
+    "dsen2_prep_from_images": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
+                                       c_void_p, c_void_p, c_void_p]),
+    "dsen2_pack_head_weights": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "dsen2_pack_tail_weights": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "dsen2_conv_head": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                c_void_p]),
+    "dsen2_conv_tail": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                c_int, c_void_p, c_void_p]),
+    "dsen2_conv_tail_stitch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                       c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
+    "dsen2_debug_force_v1": (c_int, [c_int]),
     "dsen2_debug_umma_rowshift": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
 }
 

@@ -1,0 +1,550 @@
+// DSen2 convolution layers as CTA-pair (cta_group::2) tcgen05 implicit GEMMs with RESIDENT weights.
+//
+// One tile = 16 rows x 8 pixels of one patch (M = 128); a CTA pair computes two horizontally adjacent
+// tiles with one M = 256 MMA stream issued by the leader CTA.  Per tile and 64-channel k-block the
+// producer makes ONE TMA load of the 18 x 10 pixel halo box ([y][x][64 ch], 128-byte swizzled rows);
+// the nine taps are nine smem descriptors into that box (start shifted by (dy*10 + dx) rows, 8-row
+// groups 10*128 B apart), so activations cross L2 -> SMEM once (x1.41 halo) instead of nine times.
+// TMA out-of-bounds zero fill is the Conv2D(padding='same') border of the PATCH (DSen2Net.py:10,12,29,35):
+// the patch index is its own tensor dimension, neighbours are never read.
+// The layer's weights stay in SMEM for the whole launch: in pair mode each CTA holds N/2 rows of every
+// [tap][k-block] slab (144 KB for 128->128), loaded once.
+//
+// Three layer shapes share the kernel (template parameters):
+//   RES   128 -> 128, 9 taps, 2 k-blocks, N = 128           epilogue RELU | RESIDUAL(x + 0.1*conv, hi+lo trunk)
+//   HEAD  (3 horizontal taps x 16 ch pre-gathered by dsen2_prep_*) -> 128, 3 vertical taps, A = hi | lo k-blocks,
+//         B = [W_hi ; W_lo] stacked along N (N = 256) and summed in the epilogue: fp32-equivalent first layer
+//   TAIL  128 -> cout <= 16, 9 taps, A = x_hi | x_lo (4 k-blocks), B = [W_hi ; W_lo] (N = 32), epilogue adds the
+//         global skip (DSen2Net.py:38,41), scales, and writes NCHW predictions or the stitched HWC canvas
+//         (patches.py:374-405 ownership rule, supres.py:29).
+//
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM alloc + MMA issue (leader CTA), warps 2-9 epilogue
+// (two warps per TMEM lane quarter, splitting the channels); two TMEM accumulator buffers.
+#include "common.cuh"
+
+namespace dsen2 {
+
+static constexpr int kPairThreads = 320;
+static constexpr int kEpiWarps = 8;
+static constexpr int kBoxH = 18;
+
+enum { kEpiRelu = 0, kEpiResidual = 1, kEpiTail = 2 };
+
+struct PairParams {
+  int n, H, W;
+  int tiles_x, tiles_y;
+  long long num_tiles;
+  const float* bias;
+  const __half* res_hi;
+  const __half* res_lo;
+  float res_scale;
+  __half* out_hi;
+  __half* out_lo;
+  // TAIL
+  const __half* skip_hi;   // prepared input (n,H,W,64): centre-tap channels 16..31 hold the network inputs
+  const __half* skip_lo;
+  int skip_ch0;            // first skip band inside the 16-channel group
+  int cout_real;
+  float out_mul;
+  float* out_f32;
+  int tail_mode;           // 0: NCHW (n,cout,H,W) predictions; 1: stitched HWC canvas
+  int first_patch, img_h, img_w, border, grid_ny, grid_nx;
+};
+
+template <int NTOT_, bool SPLIT_, int NMAPS_, int KPM_, int NTAPS_, int KSTEPS_, int STAGES_, int EPI_>
+struct PairCfg {
+  static constexpr int NTOT = NTOT_;            // UMMA N over the pair
+  static constexpr bool SPLIT = SPLIT_;         // B = [W_hi ; W_lo]: epilogue sums the two column halves
+  static constexpr int NMAPS = NMAPS_;          // A tensors (1, or 2 = hi then lo)
+  static constexpr int KPM = KPM_;              // 64-channel k-blocks per A tensor
+  static constexpr int KB = NMAPS_ * KPM_;      // pipeline stages consumed per tile
+  static constexpr int NTAPS = NTAPS_;          // 9 (3x3) or 3 (vertical; horizontal taps pre-gathered)
+  static constexpr int KSTEPS = KSTEPS_;        // K = 16 MMAs per tap and k-block
+  static constexpr int STAGES = STAGES_;
+  static constexpr int EPI = EPI_;
+  static constexpr int CH = SPLIT_ ? NTOT_ / 2 : NTOT_;   // output channels
+  static constexpr int BOXW = NTAPS_ == 9 ? 10 : 8;
+  static constexpr int BOX_BYTES = kBoxH * BOXW * 128;
+  static constexpr int STAGE_BYTES = (BOX_BYTES + 1023) / 1024 * 1024;
+  static constexpr int SLAB_ROWS = NTOT_ / 2;
+  static constexpr int SLAB_BYTES = SLAB_ROWS * 128;
+  static constexpr int NSLABS = NTAPS_ * KPM_;
+  static constexpr int W_BYTES = NSLABS * SLAB_BYTES;
+  static constexpr int TMEM_COLS = (2 * NTOT_ < 32) ? 32 : 2 * NTOT_;
+  static constexpr int BAR_BYTES = 1024;        // barriers + tmem pointer + bias
+  static constexpr int STG_BYTES = kEpiWarps * 1024;   // per-warp transpose buffers of the epilogue
+  static constexpr int SMEM_BYTES = W_BYTES + STAGES_ * STAGE_BYTES + BAR_BYTES + STG_BYTES + 1024 /*align slack*/;
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
+  static_assert(W_BYTES % 1024 == 0, "weight slabs must keep the stages 1024-byte aligned");
+  static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM allocation must be a power of two <= 512");
+  static_assert(CH * 4 + 256 <= BAR_BYTES, "bias does not fit next to the barriers");
+};
+
+__device__ __forceinline__ int stitch_tile_of(int y, int size, int S, int n) {
+  return (size % S != 0 && y >= size - S) ? n - 1 : y / S;
+}
+
+// ---- epilogue I/O --------------------------------------------------------------------------
+// After tcgen05.ld (32x32b) thread t of a warp owns pixel t of the warp's 32 tile rows and 64 consecutive
+// channels of it (128 B).  Written straight to NHWC memory that is 32 different cache lines per
+// instruction (L1TEX wavefront bound).  Instead each warp transposes through a 1 KB smem buffer, 8 pixels
+// (= the 8 pixels of one image row of the tile) at a time, so that 8 consecutive lanes move the 128
+// contiguous bytes of one pixel: 4 full lines per instruction.
+__device__ __forceinline__ uint32_t stg_off(int r, int chunk) { return (uint32_t)(r * 128 + ((chunk ^ r) & 7) * 16); }
+
+struct EpiGeom {
+  long long base;     // element offset of (image row of round 0, pixel 0 of the tile, first channel of this warp)
+  long long row_pitch;   // elements per image row
+  int ch;             // channels per pixel (pixel pitch)
+  int rows_valid;     // rounds (image rows) of this warp that are inside the patch
+  int px_valid;       // pixels of the tile row that are inside the patch
+};
+
+// registers (thread = pixel, v[q] = channels 8q..8q+7) -> global, coalesced
+__device__ __forceinline__ void staged_store(uint8_t* stg, const uint4 (&v)[8], __half* out, const EpiGeom& g,
+                                             int lane) {
+  const int k_own = lane >> 3, r_own = lane & 7, rr = lane >> 3, chunk = lane & 7;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    __syncwarp();
+    if (k_own == k) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(stg + stg_off(r_own, q)) = v[q];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int r = 4 * j + rr;
+      const uint4 val = *reinterpret_cast<const uint4*>(stg + stg_off(r, chunk));
+      if (k < g.rows_valid && r < g.px_valid)
+        *reinterpret_cast<uint4*>(out + g.base + k * g.row_pitch + (long long)r * g.ch + chunk * 8) = val;
+    }
+  }
+}
+
+// global -> registers (lane-coalesced layout: gl[k*2+j] = 16 B chunk `lane&7` of pixel 4j + lane>>3 of round k)
+// (plain loads: the RESIDUAL epilogue updates the trunk in place, the tensor is not read-only for the kernel)
+__device__ __forceinline__ void coalesced_load(uint4 (&gl)[8], const __half* in, const EpiGeom& g, int lane) {
+  const int rr = lane >> 3, chunk = lane & 7;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int r = 4 * j + rr;
+      gl[k * 2 + j] = (k < g.rows_valid && r < g.px_valid)
+                          ? *reinterpret_cast<const uint4*>(in + g.base + k * g.row_pitch + (long long)r * g.ch + chunk * 8)
+                          : make_uint4(0, 0, 0, 0);
+    }
+}
+
+// lane-coalesced registers -> thread = pixel registers
+__device__ __forceinline__ void staged_gather(uint8_t* stg, const uint4 (&gl)[8], uint4 (&v)[8], int lane) {
+  const int k_own = lane >> 3, r_own = lane & 7, rr = lane >> 3, chunk = lane & 7;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 2; ++j) *reinterpret_cast<uint4*>(stg + stg_off(4 * j + rr, chunk)) = gl[k * 2 + j];
+    __syncwarp();
+    if (k_own == k) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = *reinterpret_cast<const uint4*>(stg + stg_off(r_own, q));
+    }
+  }
+}
+
+template <class Cfg>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
+conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
+                 const __grid_constant__ CUtensorMap tm_w, const PairParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_w = smem;
+  uint8_t* s_a = smem + Cfg::W_BYTES;
+  uint8_t* bar_base = s_a + Cfg::STAGES * Cfg::STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(bar_base);      // leader's copies are the live ones
+  uint64_t* empty = full + Cfg::STAGES;                        // per CTA (multicast commit)
+  uint64_t* wfull = empty + Cfg::STAGES;                       // leader
+  uint64_t* tmem_full = wfull + 1;                             // per CTA (multicast commit)
+  uint64_t* tmem_empty = tmem_full + 2;                        // leader; 2 * kEpiWarps arrivals
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* s_bias = reinterpret_cast<float*>(bar_base + 256);
+  uint8_t* s_stg = bar_base + Cfg::BAR_BYTES;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const long long pair = blockIdx.x >> 1;
+  const long long npairs = gridDim.x >> 1;
+  const long long pair_tiles = (p.num_tiles + 1) >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a0);
+    if (Cfg::NMAPS == 2) tma_prefetch_desc(&tm_a1);
+    tma_prefetch_desc(&tm_w);
+    for (int i = 0; i < Cfg::STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(wfull, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 2 * kEpiWarps);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_ptr);
+  for (int i = threadIdx.x; i < Cfg::CH; i += kPairThreads) s_bias[i] = p.bias[i];
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();            // the peer's barriers exist before anything is signalled across the pair
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ================================ TMA producer (both CTAs) ================================
+    if (elect_one()) {
+      if (rank == 0) mbar_expect_tx(wfull, 2 * Cfg::W_BYTES);
+      for (int s = 0; s < Cfg::NSLABS; ++s)
+        tma_load_3d_pair(s_w + s * Cfg::SLAB_BYTES, &tm_w, wfull, (s % Cfg::KPM) * 64, (int)rank * Cfg::SLAB_ROWS,
+                         s / Cfg::KPM);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long pt = pair; pt < pair_tiles; pt += npairs) {
+        const long long tile = 2 * pt + rank;          // may equal num_tiles (odd count): b == n, all zero fill
+        const int tx = (int)(tile % p.tiles_x);
+        const int ty = (int)((tile / p.tiles_x) % p.tiles_y);
+        const int b = (int)(tile / ((long long)p.tiles_x * p.tiles_y));
+        const int bx = tx * 8 - (Cfg::NTAPS == 9 ? 1 : 0), by = ty * 16 - 1;
+#pragma unroll 1
+        for (int kb = 0; kb < Cfg::KB; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (rank == 0) mbar_expect_tx(&full[stage], 2 * Cfg::BOX_BYTES);
+          const CUtensorMap* m = (Cfg::NMAPS == 2 && kb >= Cfg::KPM) ? &tm_a1 : &tm_a0;
+          tma_load_4d_pair(s_a + stage * Cfg::STAGE_BYTES, m, &full[stage], (kb % Cfg::KPM) * 64, bx, by, b);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer (leader CTA) ==================================
+    if (rank == 0 && elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_f16(256, Cfg::NTOT);
+      mbar_wait(wfull, 0);
+      tc_fence_after();
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (long long pt = pair; pt < pair_tiles; pt += npairs) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * Cfg::NTOT);
+#pragma unroll 1
+        for (int kb = 0; kb < Cfg::KB; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(s_a + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = smem_u32(s_w) + (uint32_t)((kb % Cfg::KPM) * Cfg::SLAB_BYTES);
+#pragma unroll
+          for (int tap = 0; tap < Cfg::NTAPS; ++tap) {
+            const int dy = Cfg::NTAPS == 9 ? tap / 3 : tap;
+            const int dx = Cfg::NTAPS == 9 ? tap % 3 : 0;
+            const uint32_t a0 = sa + (uint32_t)((dy * Cfg::BOXW + dx) * 128);
+            const uint32_t b0 = sb + (uint32_t)(tap * Cfg::KPM * Cfg::SLAB_BYTES);
+#pragma unroll
+            for (int k = 0; k < Cfg::KSTEPS; ++k)
+              umma_f16_ss_pair(d_tmem, umma_desc_sw128_sbo(a0 + k * 32, Cfg::BOXW * 128),
+                               umma_desc_sw128_sbo(b0 + k * 32, 1024), idesc, (uint32_t)((kb | tap | k) != 0));
+          }
+          umma_commit_pair(&empty[stage]);                       // frees the slot in both CTAs
+          if (kb == Cfg::KB - 1) umma_commit_pair(&tmem_full[acc]);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ================================ epilogue (both CTAs) =====================================
+    const int wq = warp & 3;                       // TMEM lane quarter of this warp
+    const int half = (warp - 2) >> 2;              // which half of the channels
+    const int row = wq * 32 + lane;                // tile row = group * 8 + pixel
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (long long pt = pair; pt < pair_tiles; pt += npairs) {
+      const long long tile = 2 * pt + rank;
+      const int tx = (int)(tile % p.tiles_x);
+      const int ty = (int)((tile / p.tiles_x) % p.tiles_y);
+      const int b = (int)(tile / ((long long)p.tiles_x * p.tiles_y));
+      const int y = ty * 16 + (row >> 3);
+      const int x = tx * 8 + (row & 7);
+      const bool valid = (b < p.n) && (y < p.H) && (x < p.W);
+      const long long pix = ((long long)b * p.H + y) * p.W + x;
+      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * Cfg::NTOT);
+
+      if constexpr (Cfg::EPI == kEpiTail) {
+        // ------------------------------------------------------------------ tail: skip + scale + stitch
+        float skip[16];
+        bool write = valid && half == 0;
+        long long obase = 0, ostride = 0;
+        if (write) {
+          if (p.tail_mode == 0) {
+            ostride = (long long)p.H * p.W;
+            obase = (long long)b * p.cout_real * ostride + (long long)y * p.W + x;
+          } else {
+            const int S = p.H - 2 * p.border;
+            const int patch = p.first_patch + b;
+            const int pty = patch / p.grid_nx, ptx = patch - pty * p.grid_nx;
+            const int gy = min(pty * S, p.img_h - S) + y - p.border;
+            const int gx = min(ptx * S, p.img_w - S) + x - p.border;
+            write = y >= p.border && y < p.H - p.border && x >= p.border && x < p.W - p.border &&
+                    stitch_tile_of(gy, p.img_h, S, p.grid_ny) == pty && stitch_tile_of(gx, p.img_w, S, p.grid_nx) == ptx;
+            ostride = 1;
+            obase = ((long long)gy * p.img_w + gx) * p.cout_real;
+          }
+        }
+        if (write) {
+          const __half* sh = p.skip_hi + pix * 64 + 16 + p.skip_ch0;
+          const __half* sl = p.skip_lo + pix * 64 + 16 + p.skip_ch0;
+#pragma unroll
+          for (int c = 0; c < 16; ++c)
+            skip[c] = (c < p.cout_real) ? __half2float(__ldg(sh + c)) + __half2float(__ldg(sl + c)) : 0.f;
+        }
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        if (half == 0) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr, r);
+          tmem_ld_wait();
+          if (write) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c)
+              if (c < p.cout_real) {
+                const float v = (__uint_as_float(r[c]) + __uint_as_float(r[16 + c])) + s_bias[c];
+                p.out_f32[obase + c * ostride] = (v + skip[c]) * p.out_mul;   // Add (DSen2Net.py:38), then x SCALE
+              }
+          }
+        }
+      } else {
+        // ------------------------------------------------------------------ trunk layers
+        constexpr int CPT = Cfg::CH / 2;            // channels per thread (64)
+        static_assert(CPT == 64, "the staged epilogue moves 64 channels (128 B) per pixel and warp");
+        uint8_t* stg = s_stg + (warp - 2) * 1024;
+        EpiGeom g;
+        const int yw = ty * 16 + wq * 4;            // first image row of this warp's 4 rounds
+        g.ch = Cfg::CH;
+        g.row_pitch = (long long)p.W * Cfg::CH;
+        g.base = (((long long)b * p.H + yw) * p.W + tx * 8) * Cfg::CH + half * CPT;
+        g.rows_valid = (b < p.n) ? max(0, min(4, p.H - yw)) : 0;
+        g.px_valid = max(0, min(8, p.W - tx * 8));
+        uint4 vh[8], vl[8];                         // residual in, then outputs (thread = pixel layout)
+        if (Cfg::EPI == kEpiResidual) {             // before the accumulator is ready: latency hidden behind the MMAs
+          uint4 gh[8], gl[8];
+          coalesced_load(gh, p.res_hi, g, lane);
+          coalesced_load(gl, p.res_lo, g, lane);
+          staged_gather(stg, gh, vh, lane);
+          staged_gather(stg, gl, vl, lane);
+        }
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll
+        for (int chunk = 0; chunk < CPT / 32; ++chunk) {
+          const int c0 = half * CPT + chunk * 32;
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c0, r);
+          if (Cfg::SPLIT) {
+            uint32_t r2[32];
+            tmem_ld_32x32(taddr + Cfg::NTOT / 2 + c0, r2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+          } else {
+            tmem_ld_wait();
+          }
+          uint32_t* hw = reinterpret_cast<uint32_t*>(vh) + chunk * 16;
+          uint32_t* lw = reinterpret_cast<uint32_t*>(vl) + chunk * 16;
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float v0 = __uint_as_float(r[j]) + s_bias[c0 + j];
+            float v1 = __uint_as_float(r[j + 1]) + s_bias[c0 + j + 1];
+            if (Cfg::EPI == kEpiResidual) {
+              const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hw[j >> 1]));
+              const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&lw[j >> 1]));
+              v0 = (a.x + c.x) + v0 * p.res_scale;     // Lambda(x * scale) then Add (DSen2Net.py:13,15)
+              v1 = (a.y + c.y) + v1 * p.res_scale;
+            } else {
+              v0 = fmaxf(v0, 0.f);
+              v1 = fmaxf(v1, 0.f);
+            }
+            const __half2 h = __floats2half2_rn(v0, v1);
+            const float2 hf = __half22float2(h);
+            const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+            hw[j >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+            lw[j >> 1] = *reinterpret_cast<const uint32_t*>(&l);
+          }
+        }
+        // the accumulator has been read: hand the TMEM buffer back before the stores
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+        staged_store(stg, vh, p.out_hi, g, lane);
+        if (p.out_lo != nullptr) staged_store(stg, vl, p.out_lo, g, lane);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();            // nobody leaves while the peer may still signal it or read its smem
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------ //
+// host side
+// ------------------------------------------------------------------------------------------ //
+using CfgRelu = PairCfg<128, false, 1, 2, 9, 4, 3, kEpiRelu>;
+using CfgResidual = PairCfg<128, false, 1, 2, 9, 4, 3, kEpiResidual>;
+using CfgHead = PairCfg<256, true, 2, 1, 3, 3, 6, kEpiRelu>;
+using CfgTail = PairCfg<32, true, 2, 2, 9, 4, 6, kEpiTail>;
+
+template <class Cfg>
+static int launch_pair(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const PairParams& p,
+                       int sms, cudaStream_t stream, const char* what) {
+  static bool configured = false;
+  if (!configured) {
+    DSEN2_CUDA(cudaFuncSetAttribute(conv_pair_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const long long pair_tiles = (p.num_tiles + 1) / 2;
+  const long long max_pairs = sms / 2;
+  const int pairs = (int)(pair_tiles < max_pairs ? pair_tiles : max_pairs);
+  conv_pair_kernel<Cfg><<<2 * pairs, kPairThreads, Cfg::SMEM_BYTES, stream>>>(a0, a1, w, p);
+  return check_launch(what);
+}
+
+template <class Cfg>
+static int make_maps(CUtensorMap* a0, CUtensorMap* a1, CUtensorMap* w, const void* d_a0, const void* d_a1,
+                     const void* d_w, int n, int H, int W) {
+  const int ca = Cfg::KPM * 64;
+  const uint64_t dims[4] = {(uint64_t)ca, (uint64_t)W, (uint64_t)H, (uint64_t)n};
+  const uint32_t box[4] = {64, (uint32_t)Cfg::BOXW, (uint32_t)kBoxH, 1};
+  int rc = make_tmap_f16(a0, d_a0, 4, dims, box);
+  if (rc) return rc;
+  rc = make_tmap_f16(a1, d_a1 ? d_a1 : d_a0, 4, dims, box);
+  if (rc) return rc;
+  const uint64_t wd[3] = {(uint64_t)ca, (uint64_t)Cfg::NTOT, (uint64_t)Cfg::NTAPS};
+  const uint32_t wb[3] = {64, (uint32_t)Cfg::SLAB_ROWS, 1};
+  return make_tmap_f16(w, d_w, 3, wd, wb);
+}
+
+static void fill_tiles(PairParams& p, int n, int H, int W) {
+  p.n = n; p.H = H; p.W = W;
+  p.tiles_x = ceil_div(W, 8);
+  p.tiles_y = ceil_div(H, 16);
+  p.num_tiles = (long long)n * p.tiles_x * p.tiles_y;
+}
+
+// 128 -> 128 resblock convolution (called by dsen2_conv3x3 for feature_size 128)
+int conv_pair_res(const void* d_in, const void* d_w, const float* d_bias, int n, int H, int W, int epilogue,
+                  const void* d_res_hi, const void* d_res_lo, float res_scale, void* d_out_hi, void* d_out_lo,
+                  cudaStream_t stream) {
+  int sms = 0;
+  int rc = device_sm_count_and_check(&sms);
+  if (rc) return rc;
+  PairParams p{};
+  fill_tiles(p, n, H, W);
+  p.bias = d_bias;
+  p.res_hi = (const __half*)d_res_hi; p.res_lo = (const __half*)d_res_lo; p.res_scale = res_scale;
+  p.out_hi = (__half*)d_out_hi; p.out_lo = (__half*)d_out_lo;
+  CUtensorMap a0, a1, w;
+  rc = make_maps<CfgRelu>(&a0, &a1, &w, d_in, nullptr, d_w, n, H, W);
+  if (rc) return rc;
+  if (epilogue == DSEN2_EPI_RESIDUAL) return launch_pair<CfgResidual>(a0, a1, w, p, sms, stream, "conv_pair<residual>");
+  return launch_pair<CfgRelu>(a0, a1, w, p, sms, stream, "conv_pair<relu>");
+}
+
+}  // namespace dsen2
+
+using namespace dsen2;
+
+extern "C" int dsen2_conv_head(const void* d_xin_hi, const void* d_xin_lo, const void* d_w, const float* d_bias,
+                               int n, int H, int W, int feature_size, void* d_out_hi, void* d_out_lo, void* stream) {
+  DSEN2_REQUIRE(d_xin_hi && d_xin_lo && d_w && d_bias && d_out_hi && d_out_lo, DSEN2_E_BADARG,
+                "dsen2_conv_head: null pointer");
+  DSEN2_REQUIRE(feature_size == 128, DSEN2_E_BADARG, "dsen2_conv_head: the pair kernel serves feature_size 128 (got %d)",
+                feature_size);
+  DSEN2_REQUIRE(n >= 0 && H > 0 && W > 0, DSEN2_E_BADARG, "dsen2_conv_head: bad shape");
+  DSEN2_REQUIRE(((uintptr_t)d_xin_hi % 16) == 0 && ((uintptr_t)d_xin_lo % 16) == 0 && ((uintptr_t)d_w % 16) == 0 &&
+                    ((uintptr_t)d_out_hi % 16) == 0 && ((uintptr_t)d_out_lo % 16) == 0,
+                DSEN2_E_ALIGN, "dsen2_conv_head: pointers must be 16-byte aligned");
+  if (n == 0) return 0;
+  int sms = 0;
+  int rc = device_sm_count_and_check(&sms);
+  if (rc) return rc;
+  PairParams p{};
+  fill_tiles(p, n, H, W);
+  p.bias = d_bias;
+  p.out_hi = (__half*)d_out_hi; p.out_lo = (__half*)d_out_lo;
+  CUtensorMap a0, a1, w;
+  rc = make_maps<CfgHead>(&a0, &a1, &w, d_xin_hi, d_xin_lo, d_w, n, H, W);
+  if (rc) return rc;
+  return launch_pair<CfgHead>(a0, a1, w, p, sms, (cudaStream_t)stream, "conv_pair<head>");
+}
+
+static int tail_common(PairParams& p, const void* d_x_hi, const void* d_x_lo, const void* d_w, const float* d_bias,
+                       const void* d_xin_hi, const void* d_xin_lo, int skip_ch0, int cout, int n, int H, int W,
+                       float* d_out, void* stream) {
+  DSEN2_REQUIRE(d_x_hi && d_x_lo && d_w && d_bias && d_xin_hi && d_xin_lo && d_out, DSEN2_E_BADARG,
+                "dsen2_conv_tail: null pointer");
+  DSEN2_REQUIRE(n >= 0 && H > 0 && W > 0 && cout > 0 && cout <= 16 && skip_ch0 >= 0 && skip_ch0 + cout <= 16,
+                DSEN2_E_BADARG, "dsen2_conv_tail: bad shape (cout %d, skip_ch0 %d)", cout, skip_ch0);
+  DSEN2_REQUIRE(((uintptr_t)d_x_hi % 16) == 0 && ((uintptr_t)d_x_lo % 16) == 0 && ((uintptr_t)d_w % 16) == 0,
+                DSEN2_E_ALIGN, "dsen2_conv_tail: pointers must be 16-byte aligned");
+  if (n == 0) return 0;
+  int sms = 0;
+  int rc = device_sm_count_and_check(&sms);
+  if (rc) return rc;
+  fill_tiles(p, n, H, W);
+  p.bias = d_bias;
+  p.skip_hi = (const __half*)d_xin_hi; p.skip_lo = (const __half*)d_xin_lo; p.skip_ch0 = skip_ch0;
+  p.cout_real = cout; p.out_f32 = d_out;
+  CUtensorMap a0, a1, w;
+  rc = make_maps<CfgTail>(&a0, &a1, &w, d_x_hi, d_x_lo, d_w, n, H, W);
+  if (rc) return rc;
+  return launch_pair<CfgTail>(a0, a1, w, p, sms, (cudaStream_t)stream, "conv_pair<tail>");
+}
+
+extern "C" int dsen2_conv_tail(const void* d_x_hi, const void* d_x_lo, const void* d_w, const float* d_bias,
+                               const void* d_xin_hi, const void* d_xin_lo, int skip_ch0, int cout, int n, int H, int W,
+                               float* d_pred_nchw, void* stream) {
+  PairParams p{};
+  p.tail_mode = 0;
+  p.out_mul = 1.0f;
+  return tail_common(p, d_x_hi, d_x_lo, d_w, d_bias, d_xin_hi, d_xin_lo, skip_ch0, cout, n, H, W, d_pred_nchw, stream);
+}
+
+extern "C" int dsen2_conv_tail_stitch(const void* d_x_hi, const void* d_x_lo, const void* d_w, const float* d_bias,
+                                      const void* d_xin_hi, const void* d_xin_lo, int skip_ch0, int cout, int n, int P,
+                                      int first_patch, int border, int img_h, int img_w, float mul, float* d_canvas,
+                                      void* stream) {
+  const int S = P - 2 * border;
+  DSEN2_REQUIRE(P > 0 && border >= 0 && S > 0 && img_h >= S && img_w >= S && first_patch >= 0, DSEN2_E_BADARG,
+                "dsen2_conv_tail_stitch: bad stitch geometry (P %d border %d image %dx%d)", P, border, img_h, img_w);
+  PairParams p{};
+  p.tail_mode = 1;
+  p.out_mul = mul;
+  p.first_patch = first_patch; p.img_h = img_h; p.img_w = img_w; p.border = border;
+  p.grid_ny = ceil_div(img_h, S); p.grid_nx = ceil_div(img_w, S);
+  DSEN2_REQUIRE(first_patch + n <= p.grid_ny * p.grid_nx, DSEN2_E_BADARG,
+                "dsen2_conv_tail_stitch: patch range [%d,%d) exceeds the %d tiles of the canvas", first_patch,
+                first_patch + n, p.grid_ny * p.grid_nx);
+  return tail_common(p, d_x_hi, d_x_lo, d_w, d_bias, d_xin_hi, d_xin_lo, skip_ch0, cout, n, P, P, d_canvas, stream);
+}

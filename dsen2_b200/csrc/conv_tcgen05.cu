@@ -319,6 +319,12 @@ static int launch_conv(const CUtensorMap& tm_in, const CUtensorMap& tm_w, const 
 
 using namespace dsen2;
 
+static bool g_force_v1 = false;
+extern "C" int dsen2_debug_force_v1(int on) {   // tests / A-B timing: route 128-feature layers to the single-CTA kernel
+  g_force_v1 = on != 0;
+  return 0;
+}
+
 extern "C" int dsen2_conv3x3(const void* d_in, const void* d_w, const float* d_bias, int n, int H, int W, int cin_pad,
                              int cout_pad, int taps, int epilogue, const void* d_res_hi, const void* d_res_lo,
                              float res_scale, void* d_out_hi, void* d_out_lo, const float* d_skip_f32,
@@ -364,6 +370,17 @@ extern "C" int dsen2_conv3x3(const void* d_in, const void* d_w, const float* d_b
                 "dsen2_conv3x3: feature size must be 128 or 256 (got %d)", cout_pad);
   DSEN2_REQUIRE(d_out_hi && ((uintptr_t)d_out_hi % 16) == 0 && ((uintptr_t)d_out_lo % 16) == 0, DSEN2_E_ALIGN,
                 "dsen2_conv3x3: out_hi must be non-null and outputs 16-byte aligned");
+  if (cout_pad == 128 && cin_pad == 128 && taps == 9 && (epilogue == DSEN2_EPI_RELU || epilogue == DSEN2_EPI_RESIDUAL) &&
+      !g_force_v1) {
+    // DSen2 trunk layers: CTA-pair kernel with resident weights and halo-box activations (conv_pair.cu)
+    if (epilogue == DSEN2_EPI_RESIDUAL) {
+      DSEN2_REQUIRE(d_res_hi && d_res_lo && d_out_lo, DSEN2_E_BADARG,
+                    "dsen2_conv3x3: RESIDUAL epilogue needs res_hi, res_lo and out_lo");
+      DSEN2_REQUIRE(((uintptr_t)d_res_hi % 16) == 0 && ((uintptr_t)d_res_lo % 16) == 0, DSEN2_E_ALIGN,
+                    "dsen2_conv3x3: residual pointers must be 16-byte aligned");
+    }
+    return conv_pair_res(d_in, d_w, d_bias, n, H, W, epilogue, d_res_hi, d_res_lo, res_scale, d_out_hi, d_out_lo, s);
+  }
   if (epilogue == DSEN2_EPI_RELU) {
     return cout_pad == 128 ? launch_conv<128, DSEN2_EPI_RELU>(tm_in, tm_w, p, sms, s)
                            : launch_conv<256, DSEN2_EPI_RELU>(tm_in, tm_w, p, sms, s);
@@ -389,6 +406,8 @@ static int head_k_pad(int in_channels) { return (9 * in_channels + 63) / 64 * 64
 extern "C" size_t dsen2_s2model_workspace_bytes(int n, int P, int in_channels, int feature_size) {
   if (n <= 0 || P <= 0 || in_channels <= 0 || feature_size <= 0) return 0;
   const size_t pix = (size_t)n * P * P;
+  if (feature_size == 128)   // x_in hi/lo (64 ch) + trunk hi/lo + resblock intermediate
+    return 2 * align_up(pix * 64 * 2, 1024) + 3 * align_up(pix * feature_size * 2, 1024) + 1024;
   return align_up(pix * head_k_pad(in_channels) * 2, 1024) + 3 * align_up(pix * feature_size * 2, 1024) + 1024;
 }
 
@@ -411,9 +430,40 @@ extern "C" int dsen2_s2model_forward(const float* const* d_x, const int* channel
   DSEN2_REQUIRE(cout_real <= 16, DSEN2_E_BADARG, "dsen2_s2model_forward: at most 16 output bands");
   DSEN2_REQUIRE(workspace_bytes >= dsen2_s2model_workspace_bytes(n, P, ctot, feature_size), DSEN2_E_BADARG,
                 "dsen2_s2model_forward: workspace too small");
-  const int k_pad = head_k_pad(ctot);
   const size_t pix = (size_t)n * P * P;
   uint8_t* ws = reinterpret_cast<uint8_t*>(align_up((size_t)(uintptr_t)d_workspace, 1024));
+  int rc;
+
+  if (feature_size == 128) {
+    // DSen2: prepared input -> split-precision head -> CTA-pair trunk -> split-precision tail + global skip
+    DSEN2_REQUIRE(ctot <= 16, DSEN2_E_BADARG, "dsen2_s2model_forward: at most 16 input bands");
+    void* xin_hi = ws;
+    ws += align_up(pix * 64 * 2, 1024);
+    void* xin_lo = ws;
+    ws += align_up(pix * 64 * 2, 1024);
+    void* x_hi = ws;
+    ws += align_up(pix * 128 * 2, 1024);
+    void* x_lo = ws;
+    ws += align_up(pix * 128 * 2, 1024);
+    void* t = ws;
+    rc = dsen2_prep_from_patches(d_x[0], channels[0], d_x[1], channels[1], n_inputs == 3 ? d_x[2] : nullptr,
+                                 n_inputs == 3 ? channels[2] : 0, n, P, xin_hi, xin_lo, stream);
+    if (rc) return rc;
+    rc = dsen2_conv_head(xin_hi, xin_lo, d_weights[0], d_bias[0], n, P, P, 128, x_hi, x_lo, stream);
+    if (rc) return rc;
+    for (int l = 0; l < num_layers; ++l) {
+      rc = dsen2_conv3x3(x_hi, d_weights[1 + 2 * l], d_bias[1 + 2 * l], n, P, P, 128, 128, 9, DSEN2_EPI_RELU, nullptr,
+                         nullptr, 0.f, t, nullptr, nullptr, nullptr, 0, stream);
+      if (rc) return rc;
+      rc = dsen2_conv3x3(t, d_weights[2 + 2 * l], d_bias[2 + 2 * l], n, P, P, 128, 128, 9, DSEN2_EPI_RESIDUAL, x_hi,
+                         x_lo, 0.1f, x_hi, x_lo, nullptr, nullptr, 0, stream);
+      if (rc) return rc;
+    }
+    return dsen2_conv_tail(x_hi, x_lo, d_weights[2 * num_layers + 1], d_bias[2 * num_layers + 1], xin_hi, xin_lo,
+                           ctot - cout_real, cout_real, n, P, P, d_out_f32, stream);
+  }
+
+  const int k_pad = head_k_pad(ctot);
   void* a0 = ws;
   ws += align_up(pix * k_pad * 2, 1024);
   void* x_hi = ws;
@@ -422,8 +472,8 @@ extern "C" int dsen2_s2model_forward(const float* const* d_x, const int* channel
   ws += align_up(pix * feature_size * 2, 1024);
   void* t = ws;
 
-  int rc = dsen2_pack_head_input(d_x[0], channels[0], d_x[1], channels[1], n_inputs == 3 ? d_x[2] : nullptr,
-                                 n_inputs == 3 ? channels[2] : 0, n, P, k_pad, a0, nullptr, stream);
+  rc = dsen2_pack_head_input(d_x[0], channels[0], d_x[1], channels[1], n_inputs == 3 ? d_x[2] : nullptr,
+                             n_inputs == 3 ? channels[2] : 0, n, P, k_pad, a0, nullptr, stream);
   if (rc) return rc;
   rc = dsen2_conv3x3(a0, d_weights[0], d_bias[0], n, P, P, k_pad, feature_size, 1, DSEN2_EPI_RELU, nullptr, nullptr,
                      0.f, x_hi, x_lo, nullptr, nullptr, 0, stream);

@@ -4,6 +4,7 @@
 #include <stdarg.h>
 
 #include "common.cuh"
+#include "tiling.cuh"
 
 namespace dsen2 {
 
@@ -14,52 +15,6 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
-}
-
-static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
-  }
-  return n;
-}
-
-static dim3 grid_for(long long work_items, int block, int max_waves = 16) {
-  long long blocks = (work_items + block - 1) / block;
-  long long cap = (long long)sm_count() * max_waves;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  return dim3((unsigned)blocks);
-}
-
-// ------------------------------------------------------------------------------------------ //
-// tiling arithmetic shared by host and device (patches.py:32-53)
-// ------------------------------------------------------------------------------------------ //
-struct Tiling {
-  int k_i, k_j;    // full strides per axis
-  int n_i, n_j;    // filled crop starts per axis
-  int stride;      // patch_lr - 2*border_lr
-  int last_i, last_j;  // clamped start (padded lr coords) of the extra crop, if any
-};
-
-__host__ __device__ inline Tiling make_tiling(int grid_h, int grid_w, int patch_lr, int border_lr) {
-  Tiling t;
-  t.stride = patch_lr - 2 * border_lr;
-  t.k_i = grid_h / t.stride;
-  t.k_j = grid_w / t.stride;
-  t.n_i = t.k_i + (grid_h % t.stride != 0);
-  t.n_j = t.k_j + (grid_w % t.stride != 0);
-  t.last_i = grid_h + 2 * border_lr - patch_lr;
-  t.last_j = grid_w + 2 * border_lr - patch_lr;
-  return t;
-}
-
-__device__ __forceinline__ int sym_index(int j, int n) {  // numpy pad(mode='symmetric')
-  if (j < 0) j = -j - 1;
-  if (j >= n) j = 2 * n - 1 - j;
-  return j;
 }
 
 // ------------------------------------------------------------------------------------------ //
@@ -136,17 +91,6 @@ __global__ void extract_patches_generic_kernel(const float* __restrict__ img, in
 // ------------------------------------------------------------------------------------------ //
 // bilinear, mirror boundary, integer scale s (patches.py:11-16): u = (o + .5)/s - .5
 // ------------------------------------------------------------------------------------------ //
-__device__ __forceinline__ void bilin_tap(int o, int s, int n, int& a0, int& a1, float& f) {
-  const int t = 2 * o + 1 - s;               // u = t / (2 s)
-  int i0 = (t >= 0) ? t / (2 * s) : -((-t + 2 * s - 1) / (2 * s));
-  f = (float)(t - i0 * 2 * s) / (float)(2 * s);
-  int i1 = i0 + 1;
-  if (i0 < 0) i0 = -i0;                      // mirror: -1 -> 1
-  if (i1 > n - 1) i1 = 2 * (n - 1) - i1;     // mirror:  n -> n-2
-  if (i1 < 0) i1 = 0;                        // n == 1
-  a0 = i0; a1 = i1;
-}
-
 __global__ void bilinear_mirror_kernel(const float* __restrict__ in, int p, int s, long long total, float post_div,
                                        float* __restrict__ out) {
   const int P = p * s;
@@ -174,10 +118,6 @@ __global__ void bilinear_mirror_kernel(const float* __restrict__ in, int p, int 
 // ------------------------------------------------------------------------------------------ //
 // stitch: thread per (patch, interior pixel), writes the C contiguous HWC floats it owns
 // ------------------------------------------------------------------------------------------ //
-__device__ __forceinline__ int tile_of(int y, int size, int S, int n) {
-  return (size % S != 0 && y >= size - S) ? n - 1 : y / S;
-}
-
 __global__ void recompose_kernel(const float* __restrict__ pred, int first_patch, int C, int P, int border, int H,
                                  int W, int ny, int nx, float mul, long long total, float* __restrict__ out) {
   const int S = P - 2 * border;

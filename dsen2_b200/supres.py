@@ -2,7 +2,9 @@
 
 Same signatures, ``SCALE`` / ``MDL_PATH`` module constants and weight-file naming (supres.py:11-12,57,60).
 The whole tile stays on the GPU between the upload of the inputs and the download of the stitched
-image: extract(/2000) -> bilinear(/2000) -> tcgen05 network -> stitch(x2000), streamed in patch batches.
+image.  DSen2 (128 features): per patch batch one input-preparation kernel (extract + bilinear + /2000
+fused, straight from the images), 14 tcgen05 convolutions, the last one writing the stitched x2000 canvas.
+VDSen2 (256 features): extract(/2000) -> bilinear(/2000) -> tcgen05 network -> stitch(x2000).
 """
 import os
 
@@ -67,6 +69,9 @@ def super_resolve_device(model, d10, d20, d60=None, first_patch=0, num_patches=N
     single = filled == 1                     # recompose_images returns the lone patch uncropped (patches.py:375-376)
     for p0 in range(first_patch, first_patch + num_patches, device_batch):
         nb = min(device_batch, first_patch + num_patches - p0)
+        if model.fast_path and not single:       # fused: images -> x_in -> network -> stitched canvas
+            model.forward_images(d10, d20, d60, P, B, p0, nb, out, float(SCALE), timers=timers)
+            continue
         if run_60:
             xs = [extract_patches_device(d10, 6, plr, blr, p0, nb, divisor=SCALE),
                   bilinear_up_device(extract_patches_device(d20, 3, plr, blr, p0, nb), 2, post_divisor=SCALE),

@@ -118,10 +118,63 @@ int dsen2_conv3x3(const void* d_in, const void* d_w, const float* d_bias,
                   void* d_out_hi, void* d_out_lo,
                   const float* d_skip_f32, float* d_out_f32, int cout_real, void* stream);
 
-/* Whole s2model forward (model.predict on one batch, supres.py:65) for n patches of (P, P):
- * head (im2col 1x1) -> num_layers x resBlock -> tail + global skip.  d_weights[i]/d_bias[i] are the
- * packed layers in Keras topological order (2*num_layers+2 entries).  Workspace: see
- * dsen2_s2model_workspace_bytes.  d_x[0..n_inputs) NCHW fp32 inputs; the last one is the global skip. */
+/* ---------------------------------------------------------------------------------------------
+ * DSen2 (feature_size 128) fast path: CTA-pair (tcgen05 cta_group::2) kernels with the layer's weights
+ * resident in shared memory and one TMA halo-box load per tile (csrc/conv_pair.cu).  dsen2_conv3x3
+ * routes 128 -> 128 RELU / RESIDUAL layers there by itself; the first and last layer have their own
+ * entry points because they are computed at fp32-equivalent precision (operands split hi + lo).
+ *
+ * Prepared network input "x_in": two NHWC fp16 tensors (n, P, P, 64), hi and lo (value = hi + lo).
+ * Channel t*16 + c of pixel (y, x) holds input band c of pixel (y, x + t - 1) (t = 0..2; zero outside
+ * the patch; bands in DSen2Net.py:24,26 concatenation order; at most 16 bands).
+ * ------------------------------------------------------------------------------------------- */
+
+/* x_in from NCHW fp32 patch stacks -- the arrays model.predict receives (supres.py:27,47,65). */
+int dsen2_prep_from_patches(const float* d_x0, int c0, const float* d_x1, int c1, const float* d_x2, int c2,
+                            int n, int P, void* d_xin_hi, void* d_xin_lo, void* stream);
+
+/* x_in straight from the HWC float32 images: fuses get_test_patches / get_test_patches60
+ * (utils/patches.py:19-156), interp_patches (:11-16) and the /SCALE of supres.py:23-24,42-44 for
+ * patches [first_patch, first_patch + num_patches).  d_img60 == NULL selects the 20 m path
+ * (tiling grid = 20 m pixels), otherwise the 60 m path.  patch / border are the 10 m values of
+ * supres.py:22,41 (128 / 8 and 192 / 12).                                                        */
+int dsen2_prep_from_images(const float* d_img10, const float* d_img20, const float* d_img60, int H, int W,
+                           int patch, int border, int first_patch, int num_patches, float divisor,
+                           void* d_xin_hi, void* d_xin_lo, void* stream);
+
+/* First layer kernel (3,3,cin,F) fp32 HWIO -> [3 vertical taps][2F rows = W_hi ; W_lo][64] fp16. */
+int dsen2_pack_head_weights(const float* d_hwio, int cin, int feature_size, void* d_packed, void* stream);
+/* Last layer kernel (3,3,F,cout) fp32 HWIO -> [9 taps][32 rows = W_hi(16) ; W_lo(16)][F] fp16.    */
+int dsen2_pack_tail_weights(const float* d_hwio, int feature_size, int cout, void* d_packed, void* stream);
+
+/* Conv2D(F, 3x3, relu) on the concatenated inputs (DSen2Net.py:29): x_in -> trunk (hi, lo) NHWC fp16. */
+int dsen2_conv_head(const void* d_xin_hi, const void* d_xin_lo, const void* d_w, const float* d_bias,
+                    int n, int H, int W, int feature_size, void* d_out_hi, void* d_out_lo, void* stream);
+
+/* Conv2D(cout, 3x3) + Add(last input) (DSen2Net.py:35,38,41) on the trunk (hi, lo).  The global skip is
+ * read from x_in (centre tap, bands skip_ch0 .. skip_ch0+cout).  Output: NCHW fp32 predictions
+ * (n, cout, H, W) -- what model.predict returns.                                                  */
+int dsen2_conv_tail(const void* d_x_hi, const void* d_x_lo, const void* d_w, const float* d_bias,
+                    const void* d_xin_hi, const void* d_xin_lo, int skip_ch0, int cout,
+                    int n, int H, int W, float* d_pred_nchw, void* stream);
+
+/* Same, fused with recompose_images (utils/patches.py:374-405) and the x SCALE of supres.py:29,49: the
+ * n patches are patches [first_patch, first_patch + n) of the canvas tiling; each writes the pixels of
+ * the (img_h, img_w, cout) float32 HWC canvas whose LAST writer it is, multiplied by `mul`.          */
+int dsen2_conv_tail_stitch(const void* d_x_hi, const void* d_x_lo, const void* d_w, const float* d_bias,
+                           const void* d_xin_hi, const void* d_xin_lo, int skip_ch0, int cout,
+                           int n, int P, int first_patch, int border, int img_h, int img_w, float mul,
+                           float* d_canvas, void* stream);
+
+/* Whole s2model forward (model.predict on one batch, supres.py:65) for n patches of (P, P).
+ * d_weights[i] / d_bias[i] are the packed layers in Keras topological order (2*num_layers+2 entries):
+ *   feature_size 128: [0] dsen2_pack_head_weights, [1..2L] dsen2_pack_conv_weights(cin_pad=cout_pad=128),
+ *                     [2L+1] dsen2_pack_tail_weights; biases fp32 of length 128 / 128 / 16;
+ *                     pipeline: prep_from_patches -> conv_head -> L x (conv3x3 RELU, conv3x3 RESIDUAL) -> conv_tail
+ *   feature_size 256: [0] dsen2_pack_conv_weights(im2col=1), [1..2L] (256,256), [2L+1] cout_pad 16;
+ *                     pipeline: pack_head_input -> conv3x3 (1x1) -> ... -> conv3x3 TAIL_NCHW.
+ * Workspace: see dsen2_s2model_workspace_bytes.  d_x[0..n_inputs) NCHW fp32 inputs; the last one is
+ * the global skip. */
 size_t dsen2_s2model_workspace_bytes(int n, int P, int in_channels, int feature_size);
 int dsen2_s2model_forward(const float* const* d_x, const int* channels, int n_inputs,
                           int n, int P, int num_layers, int feature_size,
@@ -130,6 +183,7 @@ int dsen2_s2model_forward(const float* const* d_x, const int* channels, int n_in
                           float* d_out_f32, void* stream);
 
 /* Debug / self-test hooks (used by tests only) */
+int dsen2_debug_force_v1(int on);   /* route 128-feature layers of dsen2_conv3x3 to the single-CTA kernel */
 int dsen2_debug_umma_rowshift(const void* d_a_f16 /*(rows,64)*/, int rows, const void* d_b_f16 /*(128,64)*/,
                               int shift_rows, int base_offset_mode, float* d_out /*(128,128)*/, void* stream);
 

@@ -1,0 +1,249 @@
+"""CTA-pair (cta_group::2) DSen2 fast path: input preparation, split-precision head / tail, stitch fusion.
+
+Oracles: the prepared-input layout is checked bit-exactly against a numpy restatement of its definition
+(include/dsen2_b200.h) built on the CPU patch oracle; the head / tail layers against float64 convolutions
+of the SAME operands (hi + lo), so only accumulation order differs: rtol/atol 2e-5 (fp32-equivalent layers).
+"""
+import numpy as np
+import pytest
+
+from cases import CASES20, CASES60, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def env():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from dsen2_b200 import _capi
+    return torch, _capi, _capi.lib()
+
+
+def _split(v):
+    hi = v.astype(np.float16)
+    lo = (v - hi.astype(np.float32)).astype(np.float16)
+    return hi, lo
+
+
+def _xin_expected(xcat):
+    """xcat (n, C, P, P) float32 -> (hi, lo) (n, P, P, 64) float16 per the x_in definition."""
+    n, C, P, _ = xcat.shape
+    x = np.zeros((n, P, P + 2, 16), np.float32)
+    x[:, :, 1:P + 1, :C] = xcat.transpose(0, 2, 3, 1)
+    full = np.zeros((n, P, P, 64), np.float32)
+    for t in range(3):
+        full[..., t * 16:(t + 1) * 16] = x[:, :, t:t + P, :]
+    return _split(full)
+
+
+def _prep_patches(env, xs):
+    torch, _capi, lib = env
+    n, P = xs[0].shape[0], xs[0].shape[2]
+    dx = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in xs]
+    hi = torch.full((n, P, P, 64), 7.0, dtype=torch.float16, device='cuda')
+    lo = torch.full((n, P, P, 64), 7.0, dtype=torch.float16, device='cuda')
+    x2, c2 = (dx[2], xs[2].shape[1]) if len(xs) == 3 else (None, 0)
+    _capi.check(lib.dsen2_prep_from_patches(_capi.ptr(dx[0]), xs[0].shape[1], _capi.ptr(dx[1]), xs[1].shape[1],
+                                            _capi.ptr(x2), c2, n, P, _capi.ptr(hi), _capi.ptr(lo),
+                                            _capi.stream_ptr()), 'prep_from_patches')
+    torch.cuda.synchronize()
+    return hi, lo
+
+
+@pytest.mark.parametrize('chan', [(4, 6), (4, 6, 2)])
+def test_prep_from_patches_layout_bit_exact(env, chan):
+    rng = np.random.RandomState(sum(chan))
+    n, P = 2, 40
+    xs = [rng.uniform(0, 5, size=(n, c, P, P)).astype(np.float32) for c in chan]
+    hi, lo = _prep_patches(env, xs)
+    ehi, elo = _xin_expected(np.concatenate(xs, axis=1))
+    assert np.array_equal(hi.cpu().numpy().view(np.uint16), ehi.view(np.uint16))
+    assert np.array_equal(lo.cpu().numpy().view(np.uint16), elo.view(np.uint16))
+
+
+@pytest.mark.parametrize('tag', sorted(CASES20)[:3] + sorted(CASES60)[:2])
+def test_prep_from_images_matches_patch_oracle(env, tag):
+    """Fused extract + bilinear + /2000 == the CPU oracle's get_test_patches[60] then /2000, value for value
+    (10 m bands bit-exact; upsampled bands within the 2e-3 DN the standalone bilinear kernel is held to)."""
+    torch, _capi, lib = env
+    from oracle import patches_oracle as po
+    d10, d20, d60 = synth(tag)
+    run60 = tag in CASES60
+    if run60:
+        ps = po.get_test_patches60(d10, d20, d60, 192, 12)
+        P, B = 192, 12
+    else:
+        ps = po.get_test_patches(d10, d20, 128, 8)
+        P, B = 128, 8
+    H, W = d10.shape[:2]
+    S = P - 2 * B
+    filled = (-(-H // S)) * (-(-W // S))
+    n = ps[0].shape[0]
+    t10, t20 = torch.from_numpy(d10).cuda(), torch.from_numpy(d20).cuda()
+    t60 = torch.from_numpy(d60).cuda() if run60 else None
+    hi = torch.empty((n, P, P, 64), dtype=torch.float16, device='cuda')
+    lo = torch.empty_like(hi)
+    _capi.check(lib.dsen2_prep_from_images(_capi.ptr(t10), _capi.ptr(t20), _capi.ptr(t60), H, W, P, B, 0, n, 2000.0,
+                                           _capi.ptr(hi), _capi.ptr(lo), _capi.stream_ptr()), 'prep_from_images')
+    torch.cuda.synchronize()
+    got = hi.cpu().numpy().astype(np.float32) + lo.cpu().numpy().astype(np.float32)
+    xcat = np.concatenate([p / np.float32(2000) for p in ps], axis=1)
+    exp_hi, exp_lo = _xin_expected(xcat)
+    exp = exp_hi.astype(np.float32) + exp_lo.astype(np.float32)
+    assert n >= filled
+    # 10 m bands: pure indexing, then IEEE division -> identical bits in every tap slot
+    for t in range(3):
+        sl = slice(t * 16, t * 16 + 4)
+        assert np.array_equal(hi.cpu().numpy()[..., sl].view(np.uint16), exp_hi[..., sl].view(np.uint16))
+    np.testing.assert_allclose(got, exp, rtol=0, atol=2e-3 / 2000 + 1e-7)
+    if n > filled:   # surplus patches of the allocated stack are zero (patches.py:32-39)
+        assert not hi.cpu().numpy()[filled:].any()
+
+
+def _conv64(x_nhwc, w_hwio, bias):
+    """float64 3x3 'same' cross-correlation; x (n,H,W,C) -> (n,H,W,Cout)."""
+    import torch
+    import torch.nn.functional as F
+    x = torch.from_numpy(np.ascontiguousarray(x_nhwc, dtype=np.float64)).permute(0, 3, 1, 2)
+    w = torch.from_numpy(np.ascontiguousarray(w_hwio, dtype=np.float64)).permute(3, 2, 0, 1).contiguous()
+    y = F.conv2d(x, w, torch.from_numpy(bias.astype(np.float64)), padding=1)
+    return y.permute(0, 2, 3, 1).contiguous().numpy()
+
+
+@pytest.mark.parametrize('shape', [(2, 32, 32), (1, 128, 128), (3, 40, 24), (1, 8, 200), (5, 16, 8)])
+def test_conv_head_fp32_equivalent(env, shape):
+    torch, _capi, lib = env
+    n, H, W = shape
+    F, C = 128, 10
+    rng = np.random.RandomState(H + W)
+    # head runs on square patches in production, but the kernel is shape-generic: use the NHWC layout directly
+    xcat = rng.uniform(0, 5, size=(n, C, H, W)).astype(np.float32)
+    xp = np.zeros((n, H, W + 2, 16), np.float32)
+    xp[:, :, 1:W + 1, :C] = xcat.transpose(0, 2, 3, 1)
+    full = np.concatenate([xp[:, :, t:t + W, :] for t in range(3)] + [np.zeros((n, H, W, 16), np.float32)], axis=-1)
+    hi, lo = _split(full)
+    lim = np.sqrt(6.0 / (9 * C))
+    w = rng.uniform(-lim, lim, size=(3, 3, C, F)).astype(np.float32)
+    bias = (rng.randn(F) * 0.1).astype(np.float32)
+    tw = torch.empty((3, 2 * F, 64), dtype=torch.float16, device='cuda')
+    _capi.check(lib.dsen2_pack_head_weights(_capi.ptr(torch.from_numpy(w).cuda()), C, F, _capi.ptr(tw),
+                                            _capi.stream_ptr()), 'pack head')
+    thi, tlo = torch.from_numpy(hi).cuda(), torch.from_numpy(lo).cuda()
+    tb = torch.from_numpy(bias).cuda()
+    ohi = torch.zeros((n, H, W, F), dtype=torch.float16, device='cuda')
+    olo = torch.zeros_like(ohi)
+    _capi.check(lib.dsen2_conv_head(_capi.ptr(thi), _capi.ptr(tlo), _capi.ptr(tw), _capi.ptr(tb), n, H, W, F,
+                                    _capi.ptr(ohi), _capi.ptr(olo), _capi.stream_ptr()), 'conv head')
+    torch.cuda.synchronize()
+    xin = (hi.astype(np.float64) + lo.astype(np.float64))[..., 16:16 + C]          # centre tap = the input itself
+    w_hi = w.astype(np.float16)
+    w_eff = w_hi.astype(np.float64) + (w - w_hi.astype(np.float32)).astype(np.float16).astype(np.float64)
+    ref = np.maximum(_conv64(xin, w_eff, bias), 0)
+    got = ohi.cpu().numpy().astype(np.float64) + olo.cpu().numpy().astype(np.float64)
+    np.testing.assert_allclose(got, ref, rtol=2e-5, atol=2e-5)
+    assert np.abs(got - np.maximum(_conv64(xcat.transpose(0, 2, 3, 1), w, bias), 0)).max() < 5e-5   # vs true fp32 layer
+
+
+@pytest.mark.parametrize('shape,cout,ch0', [((2, 32, 32), 6, 4), ((1, 128, 128), 6, 4), ((1, 48, 48), 2, 10),
+                                            ((3, 40, 24), 6, 4)])
+def test_conv_tail_nchw_fp32_equivalent(env, shape, cout, ch0):
+    torch, _capi, lib = env
+    n, H, W = shape
+    F = 128
+    rng = np.random.RandomState(H * 3 + cout)
+    x = rng.randn(n, H, W, F).astype(np.float32)
+    x_hi, x_lo = _split(x)
+    xin = np.zeros((n, H, W, 64), np.float32)
+    xin[..., 16:32] = rng.uniform(0, 4, size=(n, H, W, 16)).astype(np.float32)
+    xin_hi, xin_lo = _split(xin)
+    lim = np.sqrt(6.0 / (9 * F))
+    w = rng.uniform(-lim, lim, size=(3, 3, F, cout)).astype(np.float32)
+    bias = np.zeros(16, np.float32)
+    bias[:cout] = rng.randn(cout) * 0.1
+    tw = torch.empty((9, 32, F), dtype=torch.float16, device='cuda')
+    _capi.check(lib.dsen2_pack_tail_weights(_capi.ptr(torch.from_numpy(w).cuda()), F, cout, _capi.ptr(tw),
+                                            _capi.stream_ptr()), 'pack tail')
+    dev = [torch.from_numpy(a).cuda() for a in (x_hi, x_lo, xin_hi, xin_lo, bias)]
+    out = torch.full((n, cout, H, W), -5.0, device='cuda')
+    _capi.check(lib.dsen2_conv_tail(_capi.ptr(dev[0]), _capi.ptr(dev[1]), _capi.ptr(tw), _capi.ptr(dev[4]),
+                                    _capi.ptr(dev[2]), _capi.ptr(dev[3]), ch0, cout, n, H, W, _capi.ptr(out),
+                                    _capi.stream_ptr()), 'conv tail')
+    torch.cuda.synchronize()
+    xe = x_hi.astype(np.float64) + x_lo.astype(np.float64)
+    w_hi = w.astype(np.float16)
+    w_eff = w_hi.astype(np.float64) + (w - w_hi.astype(np.float32)).astype(np.float16).astype(np.float64)
+    skip = (xin_hi.astype(np.float64) + xin_lo.astype(np.float64))[..., 16 + ch0:16 + ch0 + cout]
+    ref = (_conv64(xe, w_eff, bias[:cout]) + skip).transpose(0, 3, 1, 2)
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize('tag', ['a', 'b', 'd'])     # 'c' is a single patch: returned uncropped by the facade
+def test_conv_tail_stitch_matches_recompose(env, tag):
+    """tail + stitch fusion == tail (NCHW) then recompose_images (CPU oracle) x 2000, exactly."""
+    torch, _capi, lib = env
+    from oracle import patches_oracle as po
+    d10, _, _ = synth(tag)
+    H, W = d10.shape[:2]
+    P, B, F, cout = 128, 8, 128, 6
+    S = P - 2 * B
+    ny, nx = -(-H // S), -(-W // S)
+    n = ny * nx
+    rng = np.random.RandomState(n)
+    x_hi, x_lo = _split(rng.randn(n, P, P, F).astype(np.float32))
+    xin = np.zeros((n, P, P, 64), np.float32)
+    xin[..., 16:32] = rng.uniform(0, 4, size=(n, P, P, 16)).astype(np.float32)
+    xin_hi, xin_lo = _split(xin)
+    lim = np.sqrt(6.0 / (9 * F))
+    w = rng.uniform(-lim, lim, size=(3, 3, F, cout)).astype(np.float32)
+    bias = np.zeros(16, np.float32)
+    tw = torch.empty((9, 32, F), dtype=torch.float16, device='cuda')
+    _capi.check(lib.dsen2_pack_tail_weights(_capi.ptr(torch.from_numpy(w).cuda()), F, cout, _capi.ptr(tw),
+                                            _capi.stream_ptr()), 'pack tail')
+    dev = [torch.from_numpy(a).cuda() for a in (x_hi, x_lo, xin_hi, xin_lo, bias)]
+    pred = torch.empty((n, cout, P, P), device='cuda')
+    _capi.check(lib.dsen2_conv_tail(_capi.ptr(dev[0]), _capi.ptr(dev[1]), _capi.ptr(tw), _capi.ptr(dev[4]),
+                                    _capi.ptr(dev[2]), _capi.ptr(dev[3]), 4, cout, n, P, P, _capi.ptr(pred),
+                                    _capi.stream_ptr()), 'conv tail')
+    canvas = torch.full((H, W, cout), -1.0, device='cuda')
+    # two shards, second first: ownership (not launch order) decides every pixel
+    half = n // 2
+    for first, cnt in ((half, n - half), (0, half)):
+        if cnt == 0:
+            continue
+        sl = slice(first, first + cnt)
+        _capi.check(lib.dsen2_conv_tail_stitch(_capi.ptr(dev[0][sl]), _capi.ptr(dev[1][sl]), _capi.ptr(tw),
+                                               _capi.ptr(dev[4]), _capi.ptr(dev[2][sl]), _capi.ptr(dev[3][sl]), 4, cout,
+                                               cnt, P, first, B, H, W, 2000.0, _capi.ptr(canvas), _capi.stream_ptr()),
+                    'conv tail stitch')
+    torch.cuda.synchronize()
+    ref = po.recompose_images(pred.cpu().numpy(), B, (H, W)) * np.float32(2000)
+    assert np.array_equal(canvas.cpu().numpy(), ref)
+
+
+def test_pair_kernel_matches_single_cta_kernel(env):
+    """A/B: the CTA-pair trunk kernel and the single-CTA kernel compute the same layer (same operands; only the
+    fp32 accumulation order differs)."""
+    torch, _capi, lib = env
+    n, H, W, F = 3, 128, 128, 128
+    rng = np.random.RandomState(9)
+    x = torch.from_numpy(rng.randn(n, H, W, F).astype(np.float16)).cuda()
+    lim = np.sqrt(6.0 / (9 * F))
+    w = torch.from_numpy(rng.uniform(-lim, lim, size=(3, 3, F, F)).astype(np.float32)).cuda()
+    tw = torch.empty((9, F, F), dtype=torch.float16, device='cuda')
+    _capi.check(lib.dsen2_pack_conv_weights(_capi.ptr(w), F, F, F, F, 0, _capi.ptr(tw), None, _capi.stream_ptr()), 'pack')
+    tb = torch.from_numpy((rng.randn(F) * 0.1).astype(np.float32)).cuda()
+    outs = []
+    try:
+        for v1 in (0, 1):
+            lib.dsen2_debug_force_v1(v1)
+            hi = torch.zeros((n, H, W, F), dtype=torch.float16, device='cuda')
+            lo = torch.zeros_like(hi)
+            _capi.check(lib.dsen2_conv3x3(_capi.ptr(x), _capi.ptr(tw), _capi.ptr(tb), n, H, W, F, F, 9, _capi.EPI_RELU,
+                                          None, None, 0.0, _capi.ptr(hi), _capi.ptr(lo), None, None, 0,
+                                          _capi.stream_ptr()), 'conv')
+            torch.cuda.synchronize()
+            outs.append(hi.float().cpu().numpy() + lo.float().cpu().numpy())
+    finally:
+        lib.dsen2_debug_force_v1(0)
+    np.testing.assert_allclose(outs[0], outs[1], rtol=1e-5, atol=1e-5)

@@ -82,6 +82,60 @@ def check_model_timing():
           flush=True)
 
 
+def _time(torch, fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def check_pair_timing():
+    """Per-layer timings of the DSen2 fast path (CTA-pair kernels) next to the single-CTA kernel."""
+    import torch
+    from dsen2_b200 import _capi
+    lib, ptr = _capi.lib(), _capi.ptr
+    st = _capi.stream_ptr()
+    F, P = 128, 128
+    for n in (64, 8):
+        x = torch.randn((n, P, P, F), device='cuda').half()
+        w = (torch.rand((9, F, F), device='cuda') - 0.5).half()
+        b = torch.zeros(F, device='cuda')
+        hi, lo, t = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+        fl = 2.0 * n * P * P * 9 * F * F
+        for v1 in (0, 1):
+            lib.dsen2_debug_force_v1(v1)
+            ms = _time(torch, lambda: _capi.check(lib.dsen2_conv3x3(ptr(x), ptr(w), ptr(b), n, P, P, F, F, 9, 0, None, None,
+                                                                    0.0, ptr(t), None, None, None, 0, st), 'relu'))
+            print('n=%d %s RELU     : %.3f ms  %.1f TFLOP/s' % (n, 'v1  ' if v1 else 'pair', ms, fl / ms / 1e9), flush=True)
+            ms = _time(torch, lambda: _capi.check(lib.dsen2_conv3x3(ptr(t), ptr(w), ptr(b), n, P, P, F, F, 9, 1, ptr(hi),
+                                                                    ptr(lo), 0.1, ptr(hi), ptr(lo), None, None, 0, st), 'res'))
+            print('n=%d %s RESIDUAL : %.3f ms  %.1f TFLOP/s' % (n, 'v1  ' if v1 else 'pair', ms, fl / ms / 1e9), flush=True)
+        lib.dsen2_debug_force_v1(0)
+        xin_hi = torch.randn((n, P, P, 64), device='cuda').half()
+        xin_lo = (torch.randn((n, P, P, 64), device='cuda') * 1e-3).half()
+        wh = (torch.rand((3, 2 * F, 64), device='cuda') - 0.5).half()
+        ms = _time(torch, lambda: _capi.check(lib.dsen2_conv_head(ptr(xin_hi), ptr(xin_lo), ptr(wh), ptr(b), n, P, P, F,
+                                                                  ptr(hi), ptr(lo), st), 'head'))
+        print('n=%d head (split)      : %.3f ms' % (n, ms), flush=True)
+        wt = (torch.rand((9, 32, F), device='cuda') - 0.5).half()
+        pred = torch.empty((n, 6, P, P), device='cuda')
+        ms = _time(torch, lambda: _capi.check(lib.dsen2_conv_tail(ptr(hi), ptr(lo), ptr(wt), ptr(b), ptr(xin_hi),
+                                                                  ptr(xin_lo), 4, 6, n, P, P, ptr(pred), st), 'tail'))
+        print('n=%d tail (split)      : %.3f ms' % (n, ms), flush=True)
+        H = 112 * 8
+        d10 = torch.rand((H, H, 4), device='cuda') * 4000
+        d20 = torch.rand((H // 2, H // 2, 6), device='cuda') * 4000
+        ms = _time(torch, lambda: _capi.check(lib.dsen2_prep_from_images(ptr(d10), ptr(d20), None, H, H, 128, 8, 0, n,
+                                                                         2000.0, ptr(xin_hi), ptr(xin_lo), st), 'prep'))
+        print('n=%d prep_from_images  : %.3f ms  (%.0f GB/s written)' % (n, ms, n * P * P * 256 / ms / 1e6), flush=True)
+
+
 CHECKS = {k[6:]: v for k, v in globals().items() if k.startswith('check_')}
 
 if __name__ == '__main__':

@@ -118,9 +118,23 @@ __device__ __forceinline__ void cluster_sync_all() {
 // shared::cluster address of the same smem offset in the even (leader) CTA of a CTA pair
 static constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
 __device__ __forceinline__ uint32_t leader_smem_u32(const void* p) { return smem_u32(p) & kPeerBitMask; }
-__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {   // arrive on the leader CTA's copy
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(leader_smem_u32(bar)) : "memory");
+// Arrive on the leader CTA's copy.  Default (.release.cta) semantics on purpose: the only thing ordered through
+// this barrier is TMEM traffic, which tcgen05.fence::before_thread_sync covers; a cluster-scope release would
+// compile to MEMBAR.ALL.GPU in the epilogue's inner loop.
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(leader_smem_u32(bar)) : "memory");
 }
+
+// ---- explicit shared-space vector access (the generic path costs an address-space check per access) ------- //
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ---- TMA --------------------------------------------------------------------------------- //
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
@@ -162,6 +176,13 @@ __device__ __forceinline__ void tma_load_4d_pair(void* dst, const CUtensorMap* m
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
       "r"(c3)
       : "memory");
+}
+// L2 prefetch of a box (no smem, no barrier): issued a few tiles ahead so that the real load hits L2
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
 }
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(

@@ -20,6 +20,8 @@
 //
 // Warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM alloc + MMA issue (leader CTA), warps 2-9 epilogue
 // (two warps per TMEM lane quarter, splitting the channels); two TMEM accumulator buffers.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dsen2 {
@@ -27,6 +29,7 @@ namespace dsen2 {
 static constexpr int kPairThreads = 320;
 static constexpr int kEpiWarps = 8;
 static constexpr int kBoxH = 18;
+static constexpr int kPrefetchTiles = 2;   // L2 prefetch distance of the activation boxes, in tiles of this CTA
 
 enum { kEpiRelu = 0, kEpiResidual = 1, kEpiTail = 2 };
 
@@ -47,6 +50,7 @@ struct PairParams {
   int cout_real;
   float out_mul;
   float* out_f32;
+  int debug;               // profiling aid (DSEN2_PAIR_DEBUG): 1 = epilogue only hands TMEM back, 2 = no activation TMA
   int tail_mode;           // 0: NCHW (n,cout,H,W) predictions; 1: stitched HWC canvas
   int first_patch, img_h, img_w, border, grid_ny, grid_nx;
 };
@@ -100,8 +104,8 @@ struct EpiGeom {
   int px_valid;       // pixels of the tile row that are inside the patch
 };
 
-// registers (thread = pixel, v[q] = channels 8q..8q+7) -> global, coalesced
-__device__ __forceinline__ void staged_store(uint8_t* stg, const uint4 (&v)[8], __half* out, const EpiGeom& g,
+// registers (thread = pixel, v[q] = channels 8q..8q+7) -> global, coalesced.  `stg` is a shared-space address.
+__device__ __forceinline__ void staged_store(uint32_t stg, const uint4 (&v)[8], __half* out, const EpiGeom& g,
                                              int lane) {
   const int k_own = lane >> 3, r_own = lane & 7, rr = lane >> 3, chunk = lane & 7;
 #pragma unroll
@@ -109,13 +113,13 @@ __device__ __forceinline__ void staged_store(uint8_t* stg, const uint4 (&v)[8], 
     __syncwarp();
     if (k_own == k) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(stg + stg_off(r_own, q)) = v[q];
+      for (int q = 0; q < 8; ++q) sts128(stg + stg_off(r_own, q), v[q]);
     }
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const int r = 4 * j + rr;
-      const uint4 val = *reinterpret_cast<const uint4*>(stg + stg_off(r, chunk));
+      const uint4 val = lds128(stg + stg_off(r, chunk));
       if (k < g.rows_valid && r < g.px_valid)
         *reinterpret_cast<uint4*>(out + g.base + k * g.row_pitch + (long long)r * g.ch + chunk * 8) = val;
     }
@@ -137,20 +141,41 @@ __device__ __forceinline__ void coalesced_load(uint4 (&gl)[8], const __half* in,
     }
 }
 
+// one 128-byte line per lane: lane (k = lane>>3, r = lane&7) owns pixel r of round k
+__device__ __forceinline__ void prefetch_rows(const __half* in, const EpiGeom& g, int lane) {
+  const int k = lane >> 3, r = lane & 7;
+  if (k < g.rows_valid && r < g.px_valid) prefetch_l2(in + g.base + k * g.row_pitch + (long long)r * g.ch);
+}
+
 // lane-coalesced registers -> thread = pixel registers
-__device__ __forceinline__ void staged_gather(uint8_t* stg, const uint4 (&gl)[8], uint4 (&v)[8], int lane) {
+__device__ __forceinline__ void staged_gather(uint32_t stg, const uint4 (&gl)[8], uint4 (&v)[8], int lane) {
   const int k_own = lane >> 3, r_own = lane & 7, rr = lane >> 3, chunk = lane & 7;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     __syncwarp();
 #pragma unroll
-    for (int j = 0; j < 2; ++j) *reinterpret_cast<uint4*>(stg + stg_off(4 * j + rr, chunk)) = gl[k * 2 + j];
+    for (int j = 0; j < 2; ++j) sts128(stg + stg_off(4 * j + rr, chunk), gl[k * 2 + j]);
     __syncwarp();
     if (k_own == k) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) v[q] = *reinterpret_cast<const uint4*>(stg + stg_off(r_own, q));
+      for (int q = 0; q < 8; ++q) v[q] = lds128(stg + stg_off(r_own, q));
     }
   }
+}
+
+template <class Cfg>
+__device__ __forceinline__ EpiGeom epi_geom(const PairParams& p, long long tile, int wq, int half) {
+  const int tx = (int)(tile % p.tiles_x);
+  const int ty = (int)((tile / p.tiles_x) % p.tiles_y);
+  const int b = (int)(tile / ((long long)p.tiles_x * p.tiles_y));
+  const int yw = ty * 16 + wq * 4;            // first image row of this warp's 4 rounds
+  EpiGeom g;
+  g.ch = Cfg::CH;
+  g.row_pitch = (long long)p.W * Cfg::CH;
+  g.base = (((long long)b * p.H + yw) * p.W + tx * 8) * Cfg::CH + half * (Cfg::CH / 2);
+  g.rows_valid = (b < p.n) ? max(0, min(4, p.H - yw)) : 0;
+  g.px_valid = max(0, min(8, p.W - tx * 8));
+  return g;
 }
 
 template <class Cfg>
@@ -216,12 +241,25 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
         const int ty = (int)((tile / p.tiles_x) % p.tiles_y);
         const int b = (int)(tile / ((long long)p.tiles_x * p.tiles_y));
         const int bx = tx * 8 - (Cfg::NTAPS == 9 ? 1 : 0), by = ty * 16 - 1;
+        if (pt + kPrefetchTiles * npairs < pair_tiles && !(p.debug & 2)) {   // warm L2 for a tile this CTA loads later
+          const long long tn = 2 * (pt + kPrefetchTiles * npairs) + rank;
+          const int ntx = (int)(tn % p.tiles_x), nty = (int)((tn / p.tiles_x) % p.tiles_y);
+          const int nb = (int)(tn / ((long long)p.tiles_x * p.tiles_y));
+#pragma unroll
+          for (int kb = 0; kb < Cfg::KB; ++kb)
+            tma_prefetch_4d((Cfg::NMAPS == 2 && kb >= Cfg::KPM) ? &tm_a1 : &tm_a0, (kb % Cfg::KPM) * 64,
+                            ntx * 8 - (Cfg::NTAPS == 9 ? 1 : 0), nty * 16 - 1, nb);
+        }
 #pragma unroll 1
         for (int kb = 0; kb < Cfg::KB; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          if (rank == 0) mbar_expect_tx(&full[stage], 2 * Cfg::BOX_BYTES);
-          const CUtensorMap* m = (Cfg::NMAPS == 2 && kb >= Cfg::KPM) ? &tm_a1 : &tm_a0;
-          tma_load_4d_pair(s_a + stage * Cfg::STAGE_BYTES, m, &full[stage], (kb % Cfg::KPM) * 64, bx, by, b);
+          if (p.debug & 2) {                         // MMA-rate experiment: stale smem, no loads
+            if (rank == 0) mbar_arrive(&full[stage]);
+          } else {
+            if (rank == 0) mbar_expect_tx(&full[stage], 2 * Cfg::BOX_BYTES);
+            const CUtensorMap* m = (Cfg::NMAPS == 2 && kb >= Cfg::KPM) ? &tm_a1 : &tm_a0;
+            tma_load_4d_pair(s_a + stage * Cfg::STAGE_BYTES, m, &full[stage], (kb % Cfg::KPM) * 64, bx, by, b);
+          }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -281,6 +319,15 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
       const bool valid = (b < p.n) && (y < p.H) && (x < p.W);
       const long long pix = ((long long)b * p.H + y) * p.W + x;
       const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * Cfg::NTOT);
+      if (p.debug & 1) {                             // MMA-rate experiment: no epilogue work at all
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
 
       if constexpr (Cfg::EPI == kEpiTail) {
         // ------------------------------------------------------------------ tail: skip + scale + stitch
@@ -329,19 +376,18 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
         // ------------------------------------------------------------------ trunk layers
         constexpr int CPT = Cfg::CH / 2;            // channels per thread (64)
         static_assert(CPT == 64, "the staged epilogue moves 64 channels (128 B) per pixel and warp");
-        uint8_t* stg = s_stg + (warp - 2) * 1024;
-        EpiGeom g;
-        const int yw = ty * 16 + wq * 4;            // first image row of this warp's 4 rounds
-        g.ch = Cfg::CH;
-        g.row_pitch = (long long)p.W * Cfg::CH;
-        g.base = (((long long)b * p.H + yw) * p.W + tx * 8) * Cfg::CH + half * CPT;
-        g.rows_valid = (b < p.n) ? max(0, min(4, p.H - yw)) : 0;
-        g.px_valid = max(0, min(8, p.W - tx * 8));
+        const uint32_t stg = smem_u32(s_stg) + (uint32_t)((warp - 2) * 1024);
+        const EpiGeom g = epi_geom<Cfg>(p, tile, wq, half);
         uint4 vh[8], vl[8];                         // residual in, then outputs (thread = pixel layout)
         if (Cfg::EPI == kEpiResidual) {             // before the accumulator is ready: latency hidden behind the MMAs
           uint4 gh[8], gl[8];
           coalesced_load(gh, p.res_hi, g, lane);
           coalesced_load(gl, p.res_lo, g, lane);
+          if (pt + npairs < pair_tiles) {           // pull the NEXT tile's residual into L2 a whole tile time ahead
+            const EpiGeom gn = epi_geom<Cfg>(p, 2 * (pt + npairs) + rank, wq, half);
+            prefetch_rows(p.res_hi, gn, lane);
+            prefetch_rows(p.res_lo, gn, lane);
+          }
           staged_gather(stg, gh, vh, lane);
           staged_gather(stg, gl, vl, lane);
         }
@@ -364,23 +410,29 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
           uint32_t* hw = reinterpret_cast<uint32_t*>(vh) + chunk * 16;
           uint32_t* lw = reinterpret_cast<uint32_t*>(vl) + chunk * 16;
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float v0 = __uint_as_float(r[j]) + s_bias[c0 + j];
-            float v1 = __uint_as_float(r[j + 1]) + s_bias[c0 + j + 1];
-            if (Cfg::EPI == kEpiResidual) {
-              const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hw[j >> 1]));
-              const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&lw[j >> 1]));
-              v0 = (a.x + c.x) + v0 * p.res_scale;     // Lambda(x * scale) then Add (DSen2Net.py:13,15)
-              v1 = (a.y + c.y) + v1 * p.res_scale;
-            } else {
-              v0 = fmaxf(v0, 0.f);
-              v1 = fmaxf(v1, 0.f);
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bq = *reinterpret_cast<const float4*>(s_bias + c0 + j);   // broadcast LDS.128
+            const float bb[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+              const int jj = j + 2 * h2;
+              float v0 = __uint_as_float(r[jj]) + bb[2 * h2];
+              float v1 = __uint_as_float(r[jj + 1]) + bb[2 * h2 + 1];
+              if (Cfg::EPI == kEpiResidual) {
+                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hw[jj >> 1]));
+                const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&lw[jj >> 1]));
+                v0 = (a.x + c.x) + v0 * p.res_scale;     // Lambda(x * scale) then Add (DSen2Net.py:13,15)
+                v1 = (a.y + c.y) + v1 * p.res_scale;
+              } else {
+                v0 = fmaxf(v0, 0.f);
+                v1 = fmaxf(v1, 0.f);
+              }
+              const __half2 h = __floats2half2_rn(v0, v1);
+              const float2 hf = __half22float2(h);
+              const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+              hw[jj >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+              lw[jj >> 1] = *reinterpret_cast<const uint32_t*>(&l);
             }
-            const __half2 h = __floats2half2_rn(v0, v1);
-            const float2 hf = __half22float2(h);
-            const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
-            hw[j >> 1] = *reinterpret_cast<const uint32_t*>(&h);
-            lw[j >> 1] = *reinterpret_cast<const uint32_t*>(&l);
           }
         }
         // the accumulator has been read: hand the TMEM buffer back before the stores
@@ -446,6 +498,8 @@ static int make_maps(CUtensorMap* a0, CUtensorMap* a1, CUtensorMap* w, const voi
 }
 
 static void fill_tiles(PairParams& p, int n, int H, int W) {
+  static const int dbg = getenv("DSEN2_PAIR_DEBUG") ? atoi(getenv("DSEN2_PAIR_DEBUG")) : 0;
+  p.debug = dbg;
   p.n = n; p.H = H; p.W = W;
   p.tiles_x = ceil_div(W, 8);
   p.tiles_y = ceil_div(H, 16);

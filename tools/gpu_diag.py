@@ -136,6 +136,32 @@ def check_pair_timing():
         print('n=%d prep_from_images  : %.3f ms  (%.0f GB/s written)' % (n, ms, n * P * P * 256 / ms / 1e6), flush=True)
 
 
+def check_pair_relu_only():
+    """RELU / RESIDUAL trunk layer timing only (used with DSEN2_PAIR_DEBUG to bound the MMA rate)."""
+    import torch
+    from dsen2_b200 import _capi
+    lib, ptr = _capi.lib(), _capi.ptr
+    st = _capi.stream_ptr()
+    F, P, n = 128, 128, 64
+    x = torch.randn((n, P, P, F), device='cuda').half()
+    w = (torch.rand((9, F, F), device='cuda') - 0.5).half()
+    b = torch.zeros(F, device='cuda')
+    hi, lo, t = torch.zeros_like(x), torch.zeros_like(x), torch.empty_like(x)
+    fl = 2.0 * n * P * P * 9 * F * F
+    ms = _time(torch, lambda: _capi.check(lib.dsen2_conv3x3(ptr(x), ptr(w), ptr(b), n, P, P, F, F, 9, 0, None, None,
+                                                            0.0, ptr(t), None, None, None, 0, st), 'relu'))
+    print('DEBUG=%s RELU     : %.3f ms  %.1f TFLOP/s' % (os.environ.get('DSEN2_PAIR_DEBUG', '0'), ms, fl / ms / 1e9), flush=True)
+    ms = _time(torch, lambda: _capi.check(lib.dsen2_conv3x3(ptr(t), ptr(w), ptr(b), n, P, P, F, F, 9, 1, ptr(hi),
+                                                            ptr(lo), 0.1, ptr(hi), ptr(lo), None, None, 0, st), 'res'))
+    print('DEBUG=%s RESIDUAL : %.3f ms  %.1f TFLOP/s' % (os.environ.get('DSEN2_PAIR_DEBUG', '0'), ms, fl / ms / 1e9), flush=True)
+
+
+def check_pair_debug_sweep():
+    for dbg in ('0', '1', '2', '3'):
+        env = dict(os.environ, DSEN2_PAIR_DEBUG=dbg)
+        subprocess.run([sys.executable, os.path.abspath(__file__), '--one', 'pair_relu_only'], env=env, timeout=120)
+
+
 CHECKS = {k[6:]: v for k, v in globals().items() if k.startswith('check_')}
 
 if __name__ == '__main__':

@@ -164,7 +164,8 @@ class S2Model:
             F = self.feature_size
             mk = lambda c: torch.empty((n, P, P, c), dtype=torch.float16, device=dev)
             if self.fast_path:
-                buf = dict(xin_hi=mk(64), xin_lo=mk(64), x_hi=mk(F), x_lo=mk(F), t=mk(F))
+                buf = dict(xin_hi=mk(64), xin_lo=mk(64), x_hi=mk(F), x_lo=mk(F), t=mk(F),
+                           x32=torch.empty((n, P, F // 4, P, 4), dtype=torch.float32, device=dev))   # chunk-major trunk
             else:
                 k_pad = (9 * sum(self.in_channels) + 63) // 64 * 64
                 buf = dict(a0=mk(k_pad), x_hi=mk(F), x_lo=mk(F), t=mk(F), k_pad=k_pad)
@@ -187,13 +188,22 @@ class S2Model:
         lib, ptr, F, L = _capi.lib(), _capi.ptr, self.feature_size, self.num_layers
         x_hi, x_lo, t = buf['x_hi'], buf['x_lo'], buf['t']
         if self.fast_path:
+            # fp32 trunk (chunk-major) updated in place by every resblock; x_lo only for the tail's split operand
+            x32 = buf['x32']
             self._timed(timers, 'conv_head', n, lambda: _capi.check(lib.dsen2_conv_head(
-                ptr(buf['xin_hi']), ptr(buf['xin_lo']), ptr(wts[0]), ptr(biases[0]), n, P, P, F, ptr(x_hi), ptr(x_lo),
-                st), "dsen2_conv_head"))
-        else:
-            self._timed(timers, 'conv_head', n, lambda: _capi.check(lib.dsen2_conv3x3(
-                ptr(buf['a0']), ptr(wts[0]), ptr(biases[0]), n, P, P, buf['k_pad'], F, 1, _capi.EPI_RELU, None, None,
-                0.0, ptr(x_hi), ptr(x_lo), None, None, 0, st), "dsen2_conv3x3(head)"))
+                ptr(buf['xin_hi']), ptr(buf['xin_lo']), ptr(wts[0]), ptr(biases[0]), n, P, P, F, ptr(x_hi),
+                ptr(x_lo) if L == 0 else None, ptr(x32) if L > 0 else None, st), "dsen2_conv_head"))
+            for l in range(L):
+                self._timed(timers, 'conv_res1', n, lambda: _capi.check(lib.dsen2_conv3x3(
+                    ptr(x_hi), ptr(wts[1 + 2 * l]), ptr(biases[1 + 2 * l]), n, P, P, F, F, 9, _capi.EPI_RELU, None,
+                    None, 0.0, ptr(t), None, None, None, 0, st), "dsen2_conv3x3(res conv1)"))
+                self._timed(timers, 'conv_res2', n, lambda: _capi.check(lib.dsen2_conv_res32(
+                    ptr(t), ptr(wts[2 + 2 * l]), ptr(biases[2 + 2 * l]), n, P, P, 0.1, ptr(x32), ptr(x_hi),
+                    ptr(x_lo) if l == L - 1 else None, st), "dsen2_conv_res32"))
+            return
+        self._timed(timers, 'conv_head', n, lambda: _capi.check(lib.dsen2_conv3x3(
+            ptr(buf['a0']), ptr(wts[0]), ptr(biases[0]), n, P, P, buf['k_pad'], F, 1, _capi.EPI_RELU, None, None,
+            0.0, ptr(x_hi), ptr(x_lo), None, None, 0, st), "dsen2_conv3x3(head)"))
         for l in range(L):
             self._timed(timers, 'conv_res1', n, lambda: _capi.check(lib.dsen2_conv3x3(
                 ptr(x_hi), ptr(wts[1 + 2 * l]), ptr(biases[1 + 2 * l]), n, P, P, F, F, 9, _capi.EPI_RELU, None,

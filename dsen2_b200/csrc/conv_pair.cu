@@ -31,7 +31,7 @@ static constexpr int kEpiWarps = 8;
 static constexpr int kBoxH = 18;
 static constexpr int kPrefetchTiles = 2;   // L2 prefetch distance of the activation boxes, in tiles of this CTA
 
-enum { kEpiRelu = 0, kEpiResidual = 1, kEpiTail = 2 };
+enum { kEpiRelu = 0, kEpiResidual = 1, kEpiTail = 2, kEpiResidual32 = 3 };
 
 struct PairParams {
   int n, H, W;
@@ -43,6 +43,7 @@ struct PairParams {
   float res_scale;
   __half* out_hi;
   __half* out_lo;
+  float* x32;              // fp32 trunk, chunk-major (n, H, C/4, W, 4): RESIDUAL32 in/out, RELU (head) optional out
   // TAIL
   const __half* skip_hi;   // prepared input (n,H,W,64): centre-tap channels 16..31 hold the network inputs
   const __half* skip_lo;
@@ -372,6 +373,83 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
               }
           }
         }
+      } else if constexpr (Cfg::EPI == kEpiResidual32) {
+        // ------------------------------------------------------------------ resblock output, fp32 trunk
+        // x <- x + scale * (conv + bias) on the fp32 trunk (DSen2Net.py:13,15), which lives in a chunk-major
+        // layout (n, H, C/4, W, 4) so that thread = pixel access is coalesced: the 8 pixels of a tile row are
+        // 8 x 16 contiguous bytes for every 4-channel chunk.  The fp16 NHWC copy the next convolution's TMA
+        // reads goes through the staged (transposing) store; x_lo is only produced when the tail needs it.
+        constexpr int CPT = Cfg::CH / 2;
+        static_assert(CPT == 64 && !Cfg::SPLIT, "fp32-trunk epilogue: 64 channels per thread");
+        const uint32_t stg = smem_u32(s_stg) + (uint32_t)((warp - 2) * 1024);
+        const EpiGeom g = epi_geom<Cfg>(p, tile, wq, half);
+        const long long cpitch = (long long)p.W * 4;                    // floats between 4-channel chunks
+        float* xp = p.x32 + (((long long)b * p.H + y) * (Cfg::CH / 4) + half * (CPT / 4)) * cpitch + (long long)x * 4;
+        float4 xr[CPT / 4];
+        if (valid) {
+#pragma unroll
+          for (int q = 0; q < CPT / 4; ++q) xr[q] = *reinterpret_cast<const float4*>(xp + q * cpitch);
+        } else {
+#pragma unroll
+          for (int q = 0; q < CPT / 4; ++q) xr[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (pt + npairs < pair_tiles) {             // next tile's trunk lines -> L2 (64 lines per warp, 2 per lane)
+          const long long tn = 2 * (pt + npairs) + rank;
+          const int ntx = (int)(tn % p.tiles_x), nty = (int)((tn / p.tiles_x) % p.tiles_y);
+          const int nb = (int)(tn / ((long long)p.tiles_x * p.tiles_y));
+          const int ny = nty * 16 + wq * 4 + (lane >> 3);
+          if (nb < p.n && ny < p.H) {
+            const float* np = p.x32 + (((long long)nb * p.H + ny) * (Cfg::CH / 4) + half * (CPT / 4) + (lane & 7) * 2) * cpitch +
+                              (long long)ntx * 32;
+            prefetch_l2(np);
+            prefetch_l2(np + cpitch);
+          }
+        }
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        uint4 vh[8];
+#pragma unroll
+        for (int chunk = 0; chunk < CPT / 32; ++chunk) {
+          const int c0 = half * CPT + chunk * 32;
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c0, r);
+          tmem_ld_wait();
+          uint32_t* hw = reinterpret_cast<uint32_t*>(vh) + chunk * 16;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bq = *reinterpret_cast<const float4*>(s_bias + c0 + j);   // broadcast LDS.128
+            float4& xv = xr[chunk * 8 + (j >> 2)];
+            xv.x = fmaf(__uint_as_float(r[j]) + bq.x, p.res_scale, xv.x);
+            xv.y = fmaf(__uint_as_float(r[j + 1]) + bq.y, p.res_scale, xv.y);
+            xv.z = fmaf(__uint_as_float(r[j + 2]) + bq.z, p.res_scale, xv.z);
+            xv.w = fmaf(__uint_as_float(r[j + 3]) + bq.w, p.res_scale, xv.w);
+            const __half2 h0 = __floats2half2_rn(xv.x, xv.y), h1 = __floats2half2_rn(xv.z, xv.w);
+            hw[j >> 1] = *reinterpret_cast<const uint32_t*>(&h0);
+            hw[(j >> 1) + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+        if (valid) {
+#pragma unroll
+          for (int q = 0; q < CPT / 4; ++q) *reinterpret_cast<float4*>(xp + q * cpitch) = xr[q];
+        }
+        staged_store(stg, vh, p.out_hi, g, lane);
+        if (p.out_lo != nullptr) {                  // last resblock only: the tail's split operand needs x - fp16(x)
+          uint32_t* lw = reinterpret_cast<uint32_t*>(vh);
+#pragma unroll
+          for (int q = 0; q < CPT / 4; ++q) {
+            const float4 xv = xr[q];
+            const float2 f0 = __half22float2(__floats2half2_rn(xv.x, xv.y)), f1 = __half22float2(__floats2half2_rn(xv.z, xv.w));
+            const __half2 l0 = __floats2half2_rn(xv.x - f0.x, xv.y - f0.y), l1 = __floats2half2_rn(xv.z - f1.x, xv.w - f1.y);
+            lw[2 * q] = *reinterpret_cast<const uint32_t*>(&l0);
+            lw[2 * q + 1] = *reinterpret_cast<const uint32_t*>(&l1);
+          }
+          staged_store(stg, vh, p.out_lo, g, lane);
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
       } else {
         // ------------------------------------------------------------------ trunk layers
         constexpr int CPT = Cfg::CH / 2;            // channels per thread (64)
@@ -413,6 +491,12 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
           for (int j = 0; j < 32; j += 4) {
             const float4 bq = *reinterpret_cast<const float4*>(s_bias + c0 + j);   // broadcast LDS.128
             const float bb[4] = {bq.x, bq.y, bq.z, bq.w};
+            if (Cfg::EPI == kEpiRelu && p.x32 != nullptr && valid) {   // first layer: seed the fp32 trunk (chunk-major)
+              const float4 xv = make_float4(fmaxf(__uint_as_float(r[j]) + bq.x, 0.f), fmaxf(__uint_as_float(r[j + 1]) + bq.y, 0.f),
+                                            fmaxf(__uint_as_float(r[j + 2]) + bq.z, 0.f), fmaxf(__uint_as_float(r[j + 3]) + bq.w, 0.f));
+              *reinterpret_cast<float4*>(p.x32 + (((long long)b * p.H + y) * (Cfg::CH / 4) + ((c0 + j) >> 2)) * ((long long)p.W * 4) +
+                                         (long long)x * 4) = xv;
+            }
 #pragma unroll
             for (int h2 = 0; h2 < 2; ++h2) {
               const int jj = j + 2 * h2;
@@ -463,6 +547,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
 // ------------------------------------------------------------------------------------------ //
 using CfgRelu = PairCfg<128, false, 1, 2, 9, 4, 3, kEpiRelu>;
 using CfgResidual = PairCfg<128, false, 1, 2, 9, 4, 3, kEpiResidual>;
+using CfgResidual32 = PairCfg<128, false, 1, 2, 9, 4, 3, kEpiResidual32>;
 using CfgHead = PairCfg<256, true, 2, 1, 3, 3, 6, kEpiRelu>;
 using CfgTail = PairCfg<32, true, 2, 2, 9, 4, 6, kEpiTail>;
 
@@ -529,10 +614,34 @@ int conv_pair_res(const void* d_in, const void* d_w, const float* d_bias, int n,
 
 using namespace dsen2;
 
+extern "C" int dsen2_conv_res32(const void* d_in, const void* d_w, const float* d_bias, int n, int H, int W,
+                                float res_scale, float* d_trunk32, void* d_out_hi, void* d_out_lo, void* stream) {
+  DSEN2_REQUIRE(d_in && d_w && d_bias && d_trunk32 && d_out_hi, DSEN2_E_BADARG, "dsen2_conv_res32: null pointer");
+  DSEN2_REQUIRE(n >= 0 && H > 0 && W > 0, DSEN2_E_BADARG, "dsen2_conv_res32: bad shape");
+  DSEN2_REQUIRE(((uintptr_t)d_in % 16) == 0 && ((uintptr_t)d_w % 16) == 0 && ((uintptr_t)d_trunk32 % 16) == 0 &&
+                    ((uintptr_t)d_out_hi % 16) == 0 && ((uintptr_t)d_out_lo % 16) == 0,
+                DSEN2_E_ALIGN, "dsen2_conv_res32: pointers must be 16-byte aligned");
+  if (n == 0) return 0;
+  int sms = 0;
+  int rc = device_sm_count_and_check(&sms);
+  if (rc) return rc;
+  PairParams p{};
+  fill_tiles(p, n, H, W);
+  p.bias = d_bias;
+  p.res_scale = res_scale;
+  p.x32 = d_trunk32;
+  p.out_hi = (__half*)d_out_hi; p.out_lo = (__half*)d_out_lo;
+  CUtensorMap a0, a1, w;
+  rc = make_maps<CfgResidual32>(&a0, &a1, &w, d_in, nullptr, d_w, n, H, W);
+  if (rc) return rc;
+  return launch_pair<CfgResidual32>(a0, a1, w, p, sms, (cudaStream_t)stream, "conv_pair<residual32>");
+}
+
 extern "C" int dsen2_conv_head(const void* d_xin_hi, const void* d_xin_lo, const void* d_w, const float* d_bias,
-                               int n, int H, int W, int feature_size, void* d_out_hi, void* d_out_lo, void* stream) {
-  DSEN2_REQUIRE(d_xin_hi && d_xin_lo && d_w && d_bias && d_out_hi && d_out_lo, DSEN2_E_BADARG,
-                "dsen2_conv_head: null pointer");
+                               int n, int H, int W, int feature_size, void* d_out_hi, void* d_out_lo,
+                               float* d_trunk32, void* stream) {
+  DSEN2_REQUIRE(d_xin_hi && d_xin_lo && d_w && d_bias && d_out_hi, DSEN2_E_BADARG, "dsen2_conv_head: null pointer");
+  DSEN2_REQUIRE(((uintptr_t)d_trunk32 % 16) == 0, DSEN2_E_ALIGN, "dsen2_conv_head: trunk must be 16-byte aligned");
   DSEN2_REQUIRE(feature_size == 128, DSEN2_E_BADARG, "dsen2_conv_head: the pair kernel serves feature_size 128 (got %d)",
                 feature_size);
   DSEN2_REQUIRE(n >= 0 && H > 0 && W > 0, DSEN2_E_BADARG, "dsen2_conv_head: bad shape");
@@ -547,6 +656,7 @@ extern "C" int dsen2_conv_head(const void* d_xin_hi, const void* d_xin_lo, const
   fill_tiles(p, n, H, W);
   p.bias = d_bias;
   p.out_hi = (__half*)d_out_hi; p.out_lo = (__half*)d_out_lo;
+  p.x32 = d_trunk32;
   CUtensorMap a0, a1, w;
   rc = make_maps<CfgHead>(&a0, &a1, &w, d_xin_hi, d_xin_lo, d_w, n, H, W);
   if (rc) return rc;

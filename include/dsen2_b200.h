@@ -147,9 +147,22 @@ int dsen2_pack_head_weights(const float* d_hwio, int cin, int feature_size, void
 /* Last layer kernel (3,3,F,cout) fp32 HWIO -> [9 taps][32 rows = W_hi(16) ; W_lo(16)][F] fp16.    */
 int dsen2_pack_tail_weights(const float* d_hwio, int feature_size, int cout, void* d_packed, void* stream);
 
-/* Conv2D(F, 3x3, relu) on the concatenated inputs (DSen2Net.py:29): x_in -> trunk (hi, lo) NHWC fp16. */
+/* Conv2D(F, 3x3, relu) on the concatenated inputs (DSen2Net.py:29): x_in -> trunk.
+ *   d_out_hi   NHWC fp16 (n,H,W,F): fp16 rounding of the layer output (the next convolution's operand)
+ *   d_out_lo   optional NHWC fp16: out - out_hi (only the tail convolution reads it)
+ *   d_trunk32  optional fp32 trunk in CHUNK-MAJOR layout (n, H, F/4, W, 4): element (n,y,x,c) at
+ *              (((n*H + y)*(F/4) + c/4)*W + x)*4 + c%4 -- the layout dsen2_conv_res32 updates in place     */
 int dsen2_conv_head(const void* d_xin_hi, const void* d_xin_lo, const void* d_w, const float* d_bias,
-                    int n, int H, int W, int feature_size, void* d_out_hi, void* d_out_lo, void* stream);
+                    int n, int H, int W, int feature_size, void* d_out_hi, void* d_out_lo,
+                    float* d_trunk32, void* stream);
+
+/* Second convolution of a resBlock with the residual update on the fp32 trunk (DSen2Net.py:12-15):
+ *   trunk32 <- trunk32 + res_scale * (conv3x3(d_in) + bias)          (in place, chunk-major fp32)
+ *   d_out_hi <- fp16(trunk32) NHWC;  d_out_lo (optional) <- fp16(trunk32 - out_hi) NHWC
+ * d_in is the NHWC fp16 output of the block's first convolution (dsen2_conv3x3 RELU); d_w from
+ * dsen2_pack_conv_weights(cin_pad = cout_pad = 128).  feature_size 128 only.                              */
+int dsen2_conv_res32(const void* d_in, const void* d_w, const float* d_bias, int n, int H, int W,
+                     float res_scale, float* d_trunk32, void* d_out_hi, void* d_out_lo, void* stream);
 
 /* Conv2D(cout, 3x3) + Add(last input) (DSen2Net.py:35,38,41) on the trunk (hi, lo).  The global skip is
  * read from x_in (centre tap, bands skip_ch0 .. skip_ch0+cout).  Output: NCHW fp32 predictions
@@ -170,7 +183,7 @@ int dsen2_conv_tail_stitch(const void* d_x_hi, const void* d_x_lo, const void* d
  * d_weights[i] / d_bias[i] are the packed layers in Keras topological order (2*num_layers+2 entries):
  *   feature_size 128: [0] dsen2_pack_head_weights, [1..2L] dsen2_pack_conv_weights(cin_pad=cout_pad=128),
  *                     [2L+1] dsen2_pack_tail_weights; biases fp32 of length 128 / 128 / 16;
- *                     pipeline: prep_from_patches -> conv_head -> L x (conv3x3 RELU, conv3x3 RESIDUAL) -> conv_tail
+ *                     pipeline: prep_from_patches -> conv_head -> L x (conv3x3 RELU, conv_res32) -> conv_tail
  *   feature_size 256: [0] dsen2_pack_conv_weights(im2col=1), [1..2L] (256,256), [2L+1] cout_pad 16;
  *                     pipeline: pack_head_input -> conv3x3 (1x1) -> ... -> conv3x3 TAIL_NCHW.
  * Workspace: see dsen2_s2model_workspace_bytes.  d_x[0..n_inputs) NCHW fp32 inputs; the last one is

@@ -120,8 +120,12 @@ def check_pair_timing():
         xin_hi = torch.randn((n, P, P, 64), device='cuda').half()
         xin_lo = (torch.randn((n, P, P, 64), device='cuda') * 1e-3).half()
         wh = (torch.rand((3, 2 * F, 64), device='cuda') - 0.5).half()
+        x32 = torch.zeros((n, P, F // 4, P, 4), device='cuda')
+        ms = _time(torch, lambda: _capi.check(lib.dsen2_conv_res32(ptr(t), ptr(w), ptr(b), n, P, P, 0.1, ptr(x32), ptr(hi),
+                                                                   None, st), 'res32'))
+        print('n=%d pair RESIDUAL32 (fp32 trunk): %.3f ms  %.1f TFLOP/s' % (n, ms, fl / ms / 1e9), flush=True)
         ms = _time(torch, lambda: _capi.check(lib.dsen2_conv_head(ptr(xin_hi), ptr(xin_lo), ptr(wh), ptr(b), n, P, P, F,
-                                                                  ptr(hi), ptr(lo), st), 'head'))
+                                                                  ptr(hi), None, ptr(x32), st), 'head'))
         print('n=%d head (split)      : %.3f ms' % (n, ms), flush=True)
         wt = (torch.rand((9, 32, F), device='cuda') - 0.5).half()
         pred = torch.empty((n, 6, P, P), device='cuda')

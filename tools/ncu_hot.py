@@ -1,13 +1,13 @@
 #!/usr/bin/env python
-"""Top stalled SASS instructions of one captured launch:  tools/ncu_hot.py <report.ncu-rep> <launch-index> [N]"""
+"""Top stalled SASS instructions of one captured launch:  tools/ncu_hot.py <report.ncu-rep> <section-index> [N]"""
 import csv, io, subprocess, sys
 rep, idx = sys.argv[1], sys.argv[2]
 N = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--launch-skip', idx, '--launch-count', '1'],
-                     capture_output=True, text=True).stdout
+out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
 allrows = list(csv.reader(io.StringIO(out)))
 starts = [i for i, r in enumerate(allrows) if r and r[0] == 'Kernel Name']
-rows = allrows[starts[0]:starts[1] if len(starts) > 1 else None]
+sec = int(idx)            # section index (ncu prints two sections per captured launch)
+rows = allrows[starts[sec]:starts[sec + 1] if sec + 1 < len(starts) else None]
 hdr = rows[1]
 col = {h: i for i, h in enumerate(hdr)}
 stalls = [h for h in hdr if h.startswith('stall_') and 'Not Issued' not in h]

@@ -195,7 +195,9 @@ def run_ours(args):
     first, count = sharding.shard_range(filled, rank, world)
     out = torch.zeros((T, T, 6), dtype=torch.float32, device=dev)
     n_batches = -(-count // args.batch)
-    launches_per_step = n_batches * (4 + model.launches_per_forward())   # 2 extract + bilinear + recompose + net
+    # fast path (DSen2): 1 input-preparation kernel + 14 convolutions per batch (extract / bilinear / stitch are
+    # fused into them); VDSen2: 2 extract + bilinear + im2col pack + 66 convolutions + stitch
+    launches_per_step = n_batches * (model.launches_per_forward() if model.fast_path else 4 + model.launches_per_forward())
 
     def step(timers=None):
         supres.super_resolve_device(model, d10, d20, first_patch=first, num_patches=count, out=out,
@@ -229,30 +231,44 @@ def run_ours(args):
     kernel_ms = float(np.mean(conv_ms))
     per_kind = {k: float(np.sum([a.elapsed_time(b) for a, b, _ in v])) / args.steps for k, v in timers.items()}
     exec_flop = 2.0 * 9 * F * F * P * P * float(np.mean(conv_n))                 # executed per launch
-    algo_flop = exec_flop * (P - 2 * B) ** 2 / (P * P)                           # minus the patch-overlap recompute
-    roofline = {"bound": "tensor", "kernel": "conv_tcgen05_kernel<%d> (resblock 3x3 conv, %d of %d convs)" % (F, 2 * model.num_layers, 2 * model.num_layers + 2),
+    # algorithmic work = output pixels only: the reference tiling recomputes the patch overlap
+    algo_flop = exec_flop * (float(T) * T) / (float(filled) * P * P)
+    by_epi = {}
+    for kind, label in (('conv_res1', 'relu'), ('conv_res2', 'residual')):
+        ms = [a.elapsed_time(b) for a, b, _ in timers.get(kind, [])]
+        if ms:
+            by_epi[label] = {"avg_launch_ms": float(np.mean(ms)), "tflops_executed": exec_flop / float(np.mean(ms)) / 1e9,
+                             "frac_executed": exec_flop / float(np.mean(ms)) / 1e9 / pk['tf_sust']}
+    # DRAM bytes per launch from the ncu --set full capture profiles/r01_pair_kernels_ncu_full.txt
+    # (dram__bytes_read.sum + dram__bytes_write.sum, 57.14 patches per captured launch): RELU 492 MB, RESIDUAL32 1586 MB
+    traffic = (8.61e6 + 27.75e6) / 2 * float(np.mean(conv_n)) if model.fast_path else None
+    kname = ("conv_pair_kernel<N=128> (CTA-pair tcgen05 3x3 conv 128->128, RELU / RESIDUAL32 epilogues; %d of %d convs)"
+             if model.fast_path else "conv_tcgen05_kernel<%d>" % F + " (3x3 conv, RELU / RESIDUAL epilogues; %d of %d convs)")
+    roofline = {"bound": "tensor", "kernel": kname % (2 * model.num_layers, 2 * model.num_layers + 2),
                 "achieved": algo_flop / kernel_ms / 1e9, "achieved_executed": exec_flop / kernel_ms / 1e9,
                 "peak": pk['tf_sust'], "peak_burst": pk['tf_burst'], "peak_source": pk['source'] + ", sustained figure (kernel timed inside a long step)",
                 "unit": "TFLOP/s", "frac": algo_flop / kernel_ms / 1e9 / pk['tf_sust'],
                 "frac_executed": exec_flop / kernel_ms / 1e9 / pk['tf_sust'],
                 "avg_launch_ms": kernel_ms, "patches_per_launch": float(np.mean(conv_n)),
-                "algorithmic_flop_per_launch": algo_flop, "traffic": None,
-                "ms_per_step_by_kernel": per_kind}
+                "algorithmic_flop_per_launch": algo_flop, "executed_flop_per_launch": exec_flop, "traffic": traffic,
+                "traffic_source": "ncu dram__bytes_read+write per launch, scaled per patch (profiles/r01_pair_kernels_ncu_full.txt)",
+                "by_epilogue": by_epi, "ms_per_step_by_kernel": per_kind}
 
-    # ---- e2e: pinned host -> device -> pinned host every step ------------------------------------
-    r0, r1 = sharding.input_rows(first, count, T, T, P, B)
-    y0, y1 = sharding.output_rows(first, count, T, T, P, B)
-    h10 = torch.empty((r1 - r0, T, 4), dtype=torch.float32).pin_memory()
-    h20 = torch.empty((r1 // 2 - r0 // 2, T // 2, 6), dtype=torch.float32).pin_memory()
-    hout = torch.empty((y1 - y0, T, 6), dtype=torch.float32).pin_memory()
-    h10.copy_(d10[r0:r1]); h20.copy_(d20[r0 // 2:r1 // 2])
+    # ---- e2e: pinned host -> device -> pinned host every step, through the public host-buffer pipeline --------
+    # (supres.HostPipeline is what supres.DSen2_20 runs on numpy inputs: chunked uploads / compute / downloads
+    #  overlapped on three streams.)  Each rank moves only the input rows its patches read and the output
+    #  pixels they own.
+    h10 = torch.empty((T, T, 4), dtype=torch.float32).pin_memory()
+    h20 = torch.empty((T // 2, T // 2, 6), dtype=torch.float32).pin_memory()
+    hout = torch.zeros((T, T, 6), dtype=torch.float32).pin_memory()
+    h10.copy_(d10); h20.copy_(d20)
     torch.cuda.synchronize()
+    del d10, d20, out
+    torch.cuda.empty_cache()
+    pipe = supres.HostPipeline(model, T, T, run_60=False, device=dev, device_batch=args.batch)
 
     def step_e2e():
-        d10[r0:r1].copy_(h10, non_blocking=True)
-        d20[r0 // 2:r1 // 2].copy_(h20, non_blocking=True)
-        step()
-        hout.copy_(out[y0:y1], non_blocking=True)
+        pipe.run(h10, h20, hout=hout, first_patch=first, num_patches=count)
 
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()
@@ -264,18 +280,18 @@ def run_ours(args):
     e1.record()
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
-    h2d = h10.numel() * 4 + h20.numel() * 4
-    d2h = hout.numel() * 4
+    h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
     if world > 1:
         tb = torch.tensor([h2d, d2h], dtype=torch.float64, device=dev)
         dist.all_reduce(tb)
         h2d, d2h = int(tb[0].item()), int(tb[1].item())
-    checksum = float(hout[::97, ::89].double().sum())
+    y0, y1 = sharding.output_rows(first, count, T, T, P, B)
+    checksum = float(hout[y0:y1:97, ::89].double().sum())
 
     if rank == 0:
         line = {"metric": "output_Mpixel_per_s", "value": value, "unit": "Mpixel/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "fp16 (fp32 accumulate, fp16 hi+lo residual trunk)",
+                "scaling": "strong", "vs_baseline": None, "dtype": "fp16 operands, fp32 accumulate (TMEM), fp32 residual trunk; first/last layer split hi+lo (fp32-equivalent)",
                 "data": "synthetic", "config": workload_config(args), "clocks": clocks,
                 "e2e": {"value": T * T / (e2e_ms * 1e-3) / 1e6, "unit": "Mpixel/s", "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

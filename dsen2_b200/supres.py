@@ -10,7 +10,7 @@ import os
 
 import numpy as np
 
-from . import _capi
+from . import _capi, sharding
 from .DSen2Net import s2model
 from .patches import bilinear_up_device, extract_patches_device, patch_counts, recompose_device
 
@@ -86,11 +86,97 @@ def super_resolve_device(model, d10, d20, d60=None, first_patch=0, num_patches=N
     return out
 
 
+class HostPipeline:
+    """Host-buffer front end: tile inputs / output live in (pinned) HOST memory; the patch range is cut into
+    chunks of whole patch rows and chunk k+1's input rows upload while chunk k computes and chunk k-1's owned
+    output rows download (three CUDA streams, one device-resident tile).  Reusable across calls of one shape."""
+
+    def __init__(self, model, H, W, run_60=False, device=None, chunk_patch_rows=6, device_batch=None):
+        torch = _capi.require_cuda()
+        self.torch, self.model, self.run_60 = torch, model, run_60
+        self.H, self.W = int(H), int(W)
+        g = _GEOM[run_60]
+        self.r, self.P, self.B = g['ratio'], g['patch'], g['border']
+        if self.H % self.r or self.W % self.r:
+            raise ValueError("10 m image size %dx%d must be a multiple of %d" % (H, W, self.r))
+        self.dev = torch.device('cuda', torch.cuda.current_device()) if device is None else device
+        self.ny, self.nx, self.S = sharding.tile_grid(self.H, self.W, self.P, self.B)
+        self.chunk_rows, self.device_batch = int(chunk_patch_rows), device_batch
+        mk = lambda h, w, c: torch.empty((h, w, c), dtype=torch.float32, device=self.dev)
+        self.d10, self.d20 = mk(self.H, self.W, 4), mk(self.H // 2, self.W // 2, 6)
+        self.d60 = mk(self.H // 6, self.W // 6, 2) if run_60 else None
+        self.canvas = torch.zeros((self.H, self.W, model.out_channels), dtype=torch.float32, device=self.dev)
+        self.up, self.down = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
+        self.h2d_bytes = self.d2h_bytes = 0
+
+    def _upload(self, h, d, div, r0, r1, done):
+        """rows [r0, r1) of the 10 m grid -> rows of the (H/div) grid not uploaded yet."""
+        a, b = r0 // div, -(-r1 // div)
+        if done is not None:
+            a = max(a, done)
+        if b > a:
+            d[a:b].copy_(h[a:b], non_blocking=True)
+            self.h2d_bytes += (b - a) * d.shape[1] * d.shape[2] * 4
+        return b if done is None else max(done, b)
+
+    def run(self, h10, h20, h60=None, hout=None, first_patch=0, num_patches=None, timers=None):
+        torch = self.torch
+        filled = self.ny * self.nx
+        if num_patches is None:
+            num_patches = filled - first_patch
+        if hout is None:
+            hout = torch.empty((self.H, self.W, self.model.out_channels), dtype=torch.float32).pin_memory()
+        self.h2d_bytes = self.d2h_bytes = 0
+        main = torch.cuda.current_stream(self.dev)
+        self.up.wait_stream(main)
+        self.down.wait_stream(main)
+        end = first_patch + num_patches
+        done10 = done20 = done60 = None           # rows already resident on the device (per resolution)
+        p0 = first_patch
+        while p0 < end:
+            row = p0 // self.nx
+            p1 = min(end, (row + self.chunk_rows) * self.nx)
+            cnt = p1 - p0
+            r0, r1 = sharding.input_rows(p0, cnt, self.H, self.W, self.P, self.B)
+            with torch.cuda.stream(self.up):
+                done10 = self._upload(h10, self.d10, 1, r0, r1, done10)
+                done20 = self._upload(h20, self.d20, 2, r0, r1, done20)
+                if self.run_60:
+                    done60 = self._upload(h60, self.d60, 6, r0, r1, done60)
+                ev_up = torch.cuda.Event()
+                ev_up.record(self.up)
+            main.wait_event(ev_up)
+            super_resolve_device(self.model, self.d10, self.d20, self.d60, first_patch=p0, num_patches=cnt,
+                                 out=self.canvas, device_batch=self.device_batch, timers=timers)
+            ev_c = torch.cuda.Event()
+            ev_c.record(main)
+            self.down.wait_event(ev_c)
+            with torch.cuda.stream(self.down):
+                for (y0, y1, x0, x1) in sharding.owned_rects(p0, cnt, self.H, self.W, self.P, self.B):
+                    if x0 == 0 and x1 == self.W:
+                        hout[y0:y1].copy_(self.canvas[y0:y1], non_blocking=True)
+                    else:
+                        hout[y0:y1, x0:x1].copy_(self.canvas[y0:y1, x0:x1], non_blocking=True)
+                    self.d2h_bytes += (y1 - y0) * (x1 - x0) * self.canvas.shape[2] * 4
+            p0 = p1
+        main.wait_stream(self.down)
+        return hout
+
+
 def _run(model, arrays):
     torch = _capi.require_cuda()
-    dev = [torch.from_numpy(np.ascontiguousarray(np.asarray(a), dtype=np.float32)).cuda() for a in arrays]
-    out = super_resolve_device(model, *dev)
-    return out.cpu().numpy()
+    host = [torch.from_numpy(np.ascontiguousarray(np.asarray(a), dtype=np.float32)) for a in arrays]
+    H, W = int(host[0].shape[0]), int(host[0].shape[1])
+    run_60 = len(host) == 3
+    g = _GEOM[run_60]
+    ny, nx, _ = sharding.tile_grid(H, W, g['patch'], g['border'])
+    if ny * nx == 1 or not model.fast_path:      # single patch (returned uncropped) / VDSen2: plain device path
+        out = super_resolve_device(model, *[t.cuda() for t in host])
+        return out.cpu().numpy()
+    pipe = HostPipeline(model, H, W, run_60=run_60)
+    hout = pipe.run(*host)
+    torch.cuda.current_stream().synchronize()
+    return hout.numpy()
 
 
 def DSen2_20(d10, d20, deep=False, model=None):

@@ -36,7 +36,7 @@ enum { kEpiRelu = 0, kEpiResidual = 1, kEpiTail = 2, kEpiResidual32 = 3 };
 struct PairParams {
   int n, H, W;
   int tiles_x, tiles_y;
-  long long num_tiles;
+  uint32_t num_tiles;
   const float* bias;
   const __half* res_hi;
   const __half* res_lo;
@@ -84,6 +84,17 @@ struct PairCfg {
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM allocation must be a power of two <= 512");
   static_assert(CH * 4 + 256 <= BAR_BYTES, "bias does not fit next to the barriers");
 };
+
+// tile index -> (patch, tile row, tile column); 32-bit arithmetic (64-bit divisions cost ~100 instructions each)
+struct TileXY { int b, ty, tx; };
+__device__ __forceinline__ TileXY decode_tile(uint32_t tile, uint32_t tiles_x, uint32_t tiles_y) {
+  const uint32_t row = tile / tiles_x;
+  TileXY t;
+  t.tx = (int)(tile - row * tiles_x);
+  t.b = (int)(row / tiles_y);
+  t.ty = (int)(row - (uint32_t)t.b * tiles_y);
+  return t;
+}
 
 __device__ __forceinline__ int stitch_tile_of(int y, int size, int S, int n) {
   return (size % S != 0 && y >= size - S) ? n - 1 : y / S;
@@ -165,17 +176,14 @@ __device__ __forceinline__ void staged_gather(uint32_t stg, const uint4 (&gl)[8]
 }
 
 template <class Cfg>
-__device__ __forceinline__ EpiGeom epi_geom(const PairParams& p, long long tile, int wq, int half) {
-  const int tx = (int)(tile % p.tiles_x);
-  const int ty = (int)((tile / p.tiles_x) % p.tiles_y);
-  const int b = (int)(tile / ((long long)p.tiles_x * p.tiles_y));
-  const int yw = ty * 16 + wq * 4;            // first image row of this warp's 4 rounds
+__device__ __forceinline__ EpiGeom epi_geom(const PairParams& p, const TileXY& t, int wq, int half) {
+  const int yw = t.ty * 16 + wq * 4;            // first image row of this warp's 4 rounds
   EpiGeom g;
   g.ch = Cfg::CH;
   g.row_pitch = (long long)p.W * Cfg::CH;
-  g.base = (((long long)b * p.H + yw) * p.W + tx * 8) * Cfg::CH + half * (Cfg::CH / 2);
-  g.rows_valid = (b < p.n) ? max(0, min(4, p.H - yw)) : 0;
-  g.px_valid = max(0, min(8, p.W - tx * 8));
+  g.base = (((long long)t.b * p.H + yw) * p.W + t.tx * 8) * Cfg::CH + half * (Cfg::CH / 2);
+  g.rows_valid = (t.b < p.n) ? max(0, min(4, p.H - yw)) : 0;
+  g.px_valid = max(0, min(8, p.W - t.tx * 8));
   return g;
 }
 
@@ -200,9 +208,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
-  const long long pair = blockIdx.x >> 1;
-  const long long npairs = gridDim.x >> 1;
-  const long long pair_tiles = (p.num_tiles + 1) >> 1;
+  const uint32_t pair = blockIdx.x >> 1;
+  const uint32_t npairs = gridDim.x >> 1;
+  const uint32_t pair_tiles = (p.num_tiles + 1) >> 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a0);
@@ -236,20 +244,17 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
                          s / Cfg::KPM);
       int stage = 0;
       uint32_t phase = 0;
-      for (long long pt = pair; pt < pair_tiles; pt += npairs) {
-        const long long tile = 2 * pt + rank;          // may equal num_tiles (odd count): b == n, all zero fill
-        const int tx = (int)(tile % p.tiles_x);
-        const int ty = (int)((tile / p.tiles_x) % p.tiles_y);
-        const int b = (int)(tile / ((long long)p.tiles_x * p.tiles_y));
-        const int bx = tx * 8 - (Cfg::NTAPS == 9 ? 1 : 0), by = ty * 16 - 1;
+      for (uint32_t pt = pair; pt < pair_tiles; pt += npairs) {
+        // tile may equal num_tiles (odd count): then b == n and the whole box is zero fill
+        const TileXY t = decode_tile(2 * pt + rank, p.tiles_x, p.tiles_y);
+        const int b = t.b;
+        const int bx = t.tx * 8 - (Cfg::NTAPS == 9 ? 1 : 0), by = t.ty * 16 - 1;
         if (pt + kPrefetchTiles * npairs < pair_tiles && !(p.debug & 2)) {   // warm L2 for a tile this CTA loads later
-          const long long tn = 2 * (pt + kPrefetchTiles * npairs) + rank;
-          const int ntx = (int)(tn % p.tiles_x), nty = (int)((tn / p.tiles_x) % p.tiles_y);
-          const int nb = (int)(tn / ((long long)p.tiles_x * p.tiles_y));
+          const TileXY tn = decode_tile(2 * (pt + kPrefetchTiles * npairs) + rank, p.tiles_x, p.tiles_y);
 #pragma unroll
           for (int kb = 0; kb < Cfg::KB; ++kb)
             tma_prefetch_4d((Cfg::NMAPS == 2 && kb >= Cfg::KPM) ? &tm_a1 : &tm_a0, (kb % Cfg::KPM) * 64,
-                            ntx * 8 - (Cfg::NTAPS == 9 ? 1 : 0), nty * 16 - 1, nb);
+                            tn.tx * 8 - (Cfg::NTAPS == 9 ? 1 : 0), tn.ty * 16 - 1, tn.b);
         }
 #pragma unroll 1
         for (int kb = 0; kb < Cfg::KB; ++kb) {
@@ -275,7 +280,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (long long pt = pair; pt < pair_tiles; pt += npairs) {
+      for (uint32_t pt = pair; pt < pair_tiles; pt += npairs) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * Cfg::NTOT);
@@ -310,13 +315,11 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
     const int row = wq * 32 + lane;                // tile row = group * 8 + pixel
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (long long pt = pair; pt < pair_tiles; pt += npairs) {
-      const long long tile = 2 * pt + rank;
-      const int tx = (int)(tile % p.tiles_x);
-      const int ty = (int)((tile / p.tiles_x) % p.tiles_y);
-      const int b = (int)(tile / ((long long)p.tiles_x * p.tiles_y));
-      const int y = ty * 16 + (row >> 3);
-      const int x = tx * 8 + (row & 7);
+    for (uint32_t pt = pair; pt < pair_tiles; pt += npairs) {
+      const TileXY tc = decode_tile(2 * pt + rank, p.tiles_x, p.tiles_y);
+      const int b = tc.b;
+      const int y = tc.ty * 16 + (row >> 3);
+      const int x = tc.tx * 8 + (row & 7);
       const bool valid = (b < p.n) && (y < p.H) && (x < p.W);
       const long long pix = ((long long)b * p.H + y) * p.W + x;
       const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * Cfg::NTOT);
@@ -382,7 +385,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
         constexpr int CPT = Cfg::CH / 2;
         static_assert(CPT == 64 && !Cfg::SPLIT, "fp32-trunk epilogue: 64 channels per thread");
         const uint32_t stg = smem_u32(s_stg) + (uint32_t)((warp - 2) * 1024);
-        const EpiGeom g = epi_geom<Cfg>(p, tile, wq, half);
+        const EpiGeom g = epi_geom<Cfg>(p, tc, wq, half);
         const long long cpitch = (long long)p.W * 4;                    // floats between 4-channel chunks
         float* xp = p.x32 + (((long long)b * p.H + y) * (Cfg::CH / 4) + half * (CPT / 4)) * cpitch + (long long)x * 4;
         float4 xr[CPT / 4];
@@ -394,13 +397,11 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
           for (int q = 0; q < CPT / 4; ++q) xr[q] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         if (pt + npairs < pair_tiles) {             // next tile's trunk lines -> L2 (64 lines per warp, 2 per lane)
-          const long long tn = 2 * (pt + npairs) + rank;
-          const int ntx = (int)(tn % p.tiles_x), nty = (int)((tn / p.tiles_x) % p.tiles_y);
-          const int nb = (int)(tn / ((long long)p.tiles_x * p.tiles_y));
-          const int ny = nty * 16 + wq * 4 + (lane >> 3);
-          if (nb < p.n && ny < p.H) {
-            const float* np = p.x32 + (((long long)nb * p.H + ny) * (Cfg::CH / 4) + half * (CPT / 4) + (lane & 7) * 2) * cpitch +
-                              (long long)ntx * 32;
+          const TileXY tn = decode_tile(2 * (pt + npairs) + rank, p.tiles_x, p.tiles_y);
+          const int ny = tn.ty * 16 + wq * 4 + (lane >> 3);
+          if (tn.b < p.n && ny < p.H) {
+            const float* np = p.x32 + (((long long)tn.b * p.H + ny) * (Cfg::CH / 4) + half * (CPT / 4) + (lane & 7) * 2) * cpitch +
+                              (long long)tn.tx * 32;
             prefetch_l2(np);
             prefetch_l2(np + cpitch);
           }
@@ -455,14 +456,14 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
         constexpr int CPT = Cfg::CH / 2;            // channels per thread (64)
         static_assert(CPT == 64, "the staged epilogue moves 64 channels (128 B) per pixel and warp");
         const uint32_t stg = smem_u32(s_stg) + (uint32_t)((warp - 2) * 1024);
-        const EpiGeom g = epi_geom<Cfg>(p, tile, wq, half);
+        const EpiGeom g = epi_geom<Cfg>(p, tc, wq, half);
         uint4 vh[8], vl[8];                         // residual in, then outputs (thread = pixel layout)
         if (Cfg::EPI == kEpiResidual) {             // before the accumulator is ready: latency hidden behind the MMAs
           uint4 gh[8], gl[8];
           coalesced_load(gh, p.res_hi, g, lane);
           coalesced_load(gl, p.res_lo, g, lane);
           if (pt + npairs < pair_tiles) {           // pull the NEXT tile's residual into L2 a whole tile time ahead
-            const EpiGeom gn = epi_geom<Cfg>(p, 2 * (pt + npairs) + rank, wq, half);
+            const EpiGeom gn = epi_geom<Cfg>(p, decode_tile(2 * (pt + npairs) + rank, p.tiles_x, p.tiles_y), wq, half);
             prefetch_rows(p.res_hi, gn, lane);
             prefetch_rows(p.res_lo, gn, lane);
           }
@@ -560,7 +561,7 @@ static int launch_pair(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
                                     Cfg::SMEM_BYTES));
     configured = true;
   }
-  const long long pair_tiles = (p.num_tiles + 1) / 2;
+  const long long pair_tiles = ((long long)p.num_tiles + 1) / 2;
   const long long max_pairs = sms / 2;
   const int pairs = (int)(pair_tiles < max_pairs ? pair_tiles : max_pairs);
   conv_pair_kernel<Cfg><<<2 * pairs, kPairThreads, Cfg::SMEM_BYTES, stream>>>(a0, a1, w, p);
@@ -582,13 +583,16 @@ static int make_maps(CUtensorMap* a0, CUtensorMap* a1, CUtensorMap* w, const voi
   return make_tmap_f16(w, d_w, 3, wd, wb);
 }
 
-static void fill_tiles(PairParams& p, int n, int H, int W) {
+static int fill_tiles(PairParams& p, int n, int H, int W) {
   static const int dbg = getenv("DSEN2_PAIR_DEBUG") ? atoi(getenv("DSEN2_PAIR_DEBUG")) : 0;
   p.debug = dbg;
   p.n = n; p.H = H; p.W = W;
   p.tiles_x = ceil_div(W, 8);
   p.tiles_y = ceil_div(H, 16);
-  p.num_tiles = (long long)n * p.tiles_x * p.tiles_y;
+  const long long tiles = (long long)n * p.tiles_x * p.tiles_y;
+  DSEN2_REQUIRE(tiles < (1LL << 30), DSEN2_E_BADARG, "batch too large: %lld tiles of 16x8 pixels (limit 2^30)", tiles);
+  p.num_tiles = (uint32_t)tiles;
+  return 0;
 }
 
 // 128 -> 128 resblock convolution (called by dsen2_conv3x3 for feature_size 128)
@@ -599,7 +603,7 @@ int conv_pair_res(const void* d_in, const void* d_w, const float* d_bias, int n,
   int rc = device_sm_count_and_check(&sms);
   if (rc) return rc;
   PairParams p{};
-  fill_tiles(p, n, H, W);
+  if ((rc = fill_tiles(p, n, H, W)) != 0) return rc;
   p.bias = d_bias;
   p.res_hi = (const __half*)d_res_hi; p.res_lo = (const __half*)d_res_lo; p.res_scale = res_scale;
   p.out_hi = (__half*)d_out_hi; p.out_lo = (__half*)d_out_lo;
@@ -626,7 +630,7 @@ extern "C" int dsen2_conv_res32(const void* d_in, const void* d_w, const float* 
   int rc = device_sm_count_and_check(&sms);
   if (rc) return rc;
   PairParams p{};
-  fill_tiles(p, n, H, W);
+  if ((rc = fill_tiles(p, n, H, W)) != 0) return rc;
   p.bias = d_bias;
   p.res_scale = res_scale;
   p.x32 = d_trunk32;
@@ -653,7 +657,7 @@ extern "C" int dsen2_conv_head(const void* d_xin_hi, const void* d_xin_lo, const
   int rc = device_sm_count_and_check(&sms);
   if (rc) return rc;
   PairParams p{};
-  fill_tiles(p, n, H, W);
+  if ((rc = fill_tiles(p, n, H, W)) != 0) return rc;
   p.bias = d_bias;
   p.out_hi = (__half*)d_out_hi; p.out_lo = (__half*)d_out_lo;
   p.x32 = d_trunk32;
@@ -676,7 +680,7 @@ static int tail_common(PairParams& p, const void* d_x_hi, const void* d_x_lo, co
   int sms = 0;
   int rc = device_sm_count_and_check(&sms);
   if (rc) return rc;
-  fill_tiles(p, n, H, W);
+  if ((rc = fill_tiles(p, n, H, W)) != 0) return rc;
   p.bias = d_bias;
   p.skip_hi = (const __half*)d_xin_hi; p.skip_lo = (const __half*)d_xin_lo; p.skip_ch0 = skip_ch0;
   p.cout_real = cout; p.out_f32 = d_out;

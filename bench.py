@@ -240,8 +240,8 @@ def run_ours(args):
             by_epi[label] = {"avg_launch_ms": float(np.mean(ms)), "tflops_executed": exec_flop / float(np.mean(ms)) / 1e9,
                              "frac_executed": exec_flop / float(np.mean(ms)) / 1e9 / pk['tf_sust']}
     # DRAM bytes per launch from the ncu --set full capture profiles/r01_pair_kernels_ncu_full.txt
-    # (dram__bytes_read.sum + dram__bytes_write.sum, 57.14 patches per captured launch): RELU 492 MB, RESIDUAL32 1586 MB
-    traffic = (8.61e6 + 27.75e6) / 2 * float(np.mean(conv_n)) if model.fast_path else None
+    # (dram__bytes_read.sum + dram__bytes_write.sum, 57.14 patches per captured launch): RELU 492 MB, RESIDUAL32 1556 MB
+    traffic = (8.61e6 + 27.23e6) / 2 * float(np.mean(conv_n)) if model.fast_path else None
     kname = ("conv_pair_kernel<N=128> (CTA-pair tcgen05 3x3 conv 128->128, RELU / RESIDUAL32 epilogues; %d of %d convs)"
              if model.fast_path else "conv_tcgen05_kernel<%d>" % F + " (3x3 conv, RELU / RESIDUAL epilogues; %d of %d convs)")
     roofline = {"bound": "tensor", "kernel": kname % (2 * model.num_layers, 2 * model.num_layers + 2),

@@ -165,7 +165,8 @@ class S2Model:
             mk = lambda c: torch.empty((n, P, P, c), dtype=torch.float16, device=dev)
             if self.fast_path:
                 buf = dict(xin_hi=mk(64), xin_lo=mk(64), x_hi=mk(F), x_lo=mk(F), t=mk(F),
-                           x32=torch.empty((n, P, F // 4, P, 4), dtype=torch.float32, device=dev))   # chunk-major trunk
+                           x32=torch.empty((n, P, (P + 7) // 8, F // 4, 8, 4), dtype=torch.float32,
+                                           device=dev))                      # tile-row-major fp32 trunk
             else:
                 k_pad = (9 * sum(self.in_channels) + 63) // 64 * 64
                 buf = dict(a0=mk(k_pad), x_hi=mk(F), x_lo=mk(F), t=mk(F), k_pad=k_pad)
@@ -188,7 +189,7 @@ class S2Model:
         lib, ptr, F, L = _capi.lib(), _capi.ptr, self.feature_size, self.num_layers
         x_hi, x_lo, t = buf['x_hi'], buf['x_lo'], buf['t']
         if self.fast_path:
-            # fp32 trunk (chunk-major) updated in place by every resblock; x_lo only for the tail's split operand
+            # fp32 trunk (tile-row-major) updated in place by every resblock; x_lo only for the tail's split operand
             x32 = buf['x32']
             self._timed(timers, 'conv_head', n, lambda: _capi.check(lib.dsen2_conv_head(
                 ptr(buf['xin_hi']), ptr(buf['xin_lo']), ptr(wts[0]), ptr(biases[0]), n, P, P, F, ptr(x_hi),

@@ -29,7 +29,8 @@ namespace dsen2 {
 static constexpr int kPairThreads = 320;
 static constexpr int kEpiWarps = 8;
 static constexpr int kBoxH = 18;
-static constexpr int kPrefetchTiles = 2;   // L2 prefetch distance of the activation boxes, in tiles of this CTA
+static constexpr int kPrefetchTiles = 1;        // L2 prefetch distance of the activation boxes, in tiles of this CTA
+static constexpr int kTrunkPrefetchTiles = 1;   // same for the fp32 trunk lines the RESIDUAL32 epilogue reads
 
 enum { kEpiRelu = 0, kEpiResidual = 1, kEpiTail = 2, kEpiResidual32 = 3 };
 
@@ -43,7 +44,7 @@ struct PairParams {
   float res_scale;
   __half* out_hi;
   __half* out_lo;
-  float* x32;              // fp32 trunk, chunk-major (n, H, C/4, W, 4): RESIDUAL32 in/out, RELU (head) optional out
+  float* x32;              // fp32 trunk, tile-row-major (n, H, ceil(W/8), C/4, 8, 4): RESIDUAL32 in/out, RELU (head) optional out
   // TAIL
   const __half* skip_hi;   // prepared input (n,H,W,64): centre-tap channels 16..31 hold the network inputs
   const __half* skip_lo;
@@ -51,6 +52,7 @@ struct PairParams {
   int cout_real;
   float out_mul;
   float* out_f32;
+  int pf_a, pf_x, defer;   // tuning knobs (L2 prefetch distances in tiles, deferred fp16-copy store)
   int debug;               // profiling aid (DSEN2_PAIR_DEBUG): 1 = epilogue only hands TMEM back, 2 = no activation TMA
   int tail_mode;           // 0: NCHW (n,cout,H,W) predictions; 1: stitched HWC canvas
   int first_patch, img_h, img_w, border, grid_ny, grid_nx;
@@ -203,6 +205,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
   uint64_t* tmem_empty = tmem_full + 2;                        // leader; 2 * kEpiWarps arrivals
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* s_bias = reinterpret_cast<float*>(bar_base + 256);
+  const uint32_t s_bias_addr = smem_u32(s_bias);
   uint8_t* s_stg = bar_base + Cfg::BAR_BYTES;
 
   const int warp = threadIdx.x >> 5;
@@ -249,8 +252,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
         const TileXY t = decode_tile(2 * pt + rank, p.tiles_x, p.tiles_y);
         const int b = t.b;
         const int bx = t.tx * 8 - (Cfg::NTAPS == 9 ? 1 : 0), by = t.ty * 16 - 1;
-        if (pt + kPrefetchTiles * npairs < pair_tiles && !(p.debug & 2)) {   // warm L2 for a tile this CTA loads later
-          const TileXY tn = decode_tile(2 * (pt + kPrefetchTiles * npairs) + rank, p.tiles_x, p.tiles_y);
+        if (p.pf_a > 0 && pt + p.pf_a * npairs < pair_tiles && !(p.debug & 2)) {   // warm L2 for a tile this CTA loads later
+          const TileXY tn = decode_tile(2 * (pt + p.pf_a * npairs) + rank, p.tiles_x, p.tiles_y);
 #pragma unroll
           for (int kb = 0; kb < Cfg::KB; ++kb)
             tma_prefetch_4d((Cfg::NMAPS == 2 && kb >= Cfg::KPM) ? &tm_a1 : &tm_a0, (kb % Cfg::KPM) * 64,
@@ -315,6 +318,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
     const int row = wq * 32 + lane;                // tile row = group * 8 + pixel
     int acc = 0;
     uint32_t acc_phase = 0;
+    // RESIDUAL32: the fp16 copy of tile i is written out while tile i+1's trunk loads are in flight
+    uint4 vh_prev[8];
+    EpiGeom g_prev;
+    bool have_prev = false;
     for (uint32_t pt = pair; pt < pair_tiles; pt += npairs) {
       const TileXY tc = decode_tile(2 * pt + rank, p.tiles_x, p.tiles_y);
       const int b = tc.b;
@@ -378,16 +385,19 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
         }
       } else if constexpr (Cfg::EPI == kEpiResidual32) {
         // ------------------------------------------------------------------ resblock output, fp32 trunk
-        // x <- x + scale * (conv + bias) on the fp32 trunk (DSen2Net.py:13,15), which lives in a chunk-major
-        // layout (n, H, C/4, W, 4) so that thread = pixel access is coalesced: the 8 pixels of a tile row are
-        // 8 x 16 contiguous bytes for every 4-channel chunk.  The fp16 NHWC copy the next convolution's TMA
+        // x <- x + scale * (conv + bias) on the fp32 trunk (DSen2Net.py:13,15), which lives in a tile-row-major
+        // layout (n, H, W/8, C/4, 8, 4) so that thread = pixel access is coalesced: the 8 pixels of a tile row are
+        // 8 x 16 contiguous bytes for every 4-channel chunk, and the 32 chunks of that tile row are 4 KB contiguous
+        // (DRAM page locality).  The fp16 NHWC copy the next convolution's TMA
         // reads goes through the staged (transposing) store; x_lo is only produced when the tail needs it.
         constexpr int CPT = Cfg::CH / 2;
         static_assert(CPT == 64 && !Cfg::SPLIT, "fp32-trunk epilogue: 64 channels per thread");
         const uint32_t stg = smem_u32(s_stg) + (uint32_t)((warp - 2) * 1024);
         const EpiGeom g = epi_geom<Cfg>(p, tc, wq, half);
-        const long long cpitch = (long long)p.W * 4;                    // floats between 4-channel chunks
-        float* xp = p.x32 + (((long long)b * p.H + y) * (Cfg::CH / 4) + half * (CPT / 4)) * cpitch + (long long)x * 4;
+        // tile-row-major trunk: (n, H, W/8, C/4, 8 px, 4 ch) -- the 32 chunks of a tile row are 4 KB contiguous
+        constexpr long long cpitch = 32;                                // floats between 4-channel chunks
+        float* xp = p.x32 + ((((long long)b * p.H + y) * p.tiles_x + tc.tx) * (Cfg::CH / 4) + half * (CPT / 4)) * cpitch +
+                    (row & 7) * 4;
         float4 xr[CPT / 4];
         if (valid) {
 #pragma unroll
@@ -396,19 +406,20 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
 #pragma unroll
           for (int q = 0; q < CPT / 4; ++q) xr[q] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        if (pt + npairs < pair_tiles) {             // next tile's trunk lines -> L2 (64 lines per warp, 2 per lane)
-          const TileXY tn = decode_tile(2 * (pt + npairs) + rank, p.tiles_x, p.tiles_y);
+        if (p.pf_x > 0 && pt + p.pf_x * npairs < pair_tiles) {   // a later tile's trunk lines -> L2 (64 lines per warp, 2 per lane)
+          const TileXY tn = decode_tile(2 * (pt + p.pf_x * npairs) + rank, p.tiles_x, p.tiles_y);
           const int ny = tn.ty * 16 + wq * 4 + (lane >> 3);
           if (tn.b < p.n && ny < p.H) {
-            const float* np = p.x32 + (((long long)tn.b * p.H + ny) * (Cfg::CH / 4) + half * (CPT / 4) + (lane & 7) * 2) * cpitch +
-                              (long long)tn.tx * 32;
+            const float* np = p.x32 + ((((long long)tn.b * p.H + ny) * p.tiles_x + tn.tx) * (Cfg::CH / 4) + half * (CPT / 4) +
+                                       (lane & 7) * 2) * cpitch;
             prefetch_l2(np);
             prefetch_l2(np + cpitch);
           }
         }
+        if (have_prev) staged_store(stg, vh_prev, p.out_hi, g_prev, lane);   // overlaps the loads issued above
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
-        uint4 vh[8];
+        uint4 (&vh)[8] = vh_prev;
 #pragma unroll
         for (int chunk = 0; chunk < CPT / 32; ++chunk) {
           const int c0 = half * CPT + chunk * 32;
@@ -418,7 +429,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
           uint32_t* hw = reinterpret_cast<uint32_t*>(vh) + chunk * 16;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const float4 bq = *reinterpret_cast<const float4*>(s_bias + c0 + j);   // broadcast LDS.128
+            const float4 bq = lds_f4(s_bias_addr + (uint32_t)(c0 + j) * 4);   // broadcast LDS.128
             float4& xv = xr[chunk * 8 + (j >> 2)];
             xv.x = fmaf(__uint_as_float(r[j]) + bq.x, p.res_scale, xv.x);
             xv.y = fmaf(__uint_as_float(r[j + 1]) + bq.y, p.res_scale, xv.y);
@@ -436,7 +447,12 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
 #pragma unroll
           for (int q = 0; q < CPT / 4; ++q) *reinterpret_cast<float4*>(xp + q * cpitch) = xr[q];
         }
-        staged_store(stg, vh, p.out_hi, g, lane);
+        g_prev = g;
+        have_prev = true;
+        if (!p.defer || p.out_lo != nullptr) {
+          staged_store(stg, vh, p.out_hi, g, lane);
+          have_prev = false;
+        }
         if (p.out_lo != nullptr) {                  // last resblock only: the tail's split operand needs x - fp16(x)
           uint32_t* lw = reinterpret_cast<uint32_t*>(vh);
 #pragma unroll
@@ -458,6 +474,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
         const uint32_t stg = smem_u32(s_stg) + (uint32_t)((warp - 2) * 1024);
         const EpiGeom g = epi_geom<Cfg>(p, tc, wq, half);
         uint4 vh[8], vl[8];                         // residual in, then outputs (thread = pixel layout)
+        const bool want_lo = p.out_lo != nullptr;
         if (Cfg::EPI == kEpiResidual) {             // before the accumulator is ready: latency hidden behind the MMAs
           uint4 gh[8], gl[8];
           coalesced_load(gh, p.res_hi, g, lane);
@@ -490,13 +507,13 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
           uint32_t* lw = reinterpret_cast<uint32_t*>(vl) + chunk * 16;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const float4 bq = *reinterpret_cast<const float4*>(s_bias + c0 + j);   // broadcast LDS.128
+            const float4 bq = lds_f4(s_bias_addr + (uint32_t)(c0 + j) * 4);   // broadcast LDS.128
             const float bb[4] = {bq.x, bq.y, bq.z, bq.w};
-            if (Cfg::EPI == kEpiRelu && p.x32 != nullptr && valid) {   // first layer: seed the fp32 trunk (chunk-major)
+            if (Cfg::EPI == kEpiRelu && p.x32 != nullptr && valid) {   // first layer: seed the fp32 trunk (tile-row-major)
               const float4 xv = make_float4(fmaxf(__uint_as_float(r[j]) + bq.x, 0.f), fmaxf(__uint_as_float(r[j + 1]) + bq.y, 0.f),
                                             fmaxf(__uint_as_float(r[j + 2]) + bq.z, 0.f), fmaxf(__uint_as_float(r[j + 3]) + bq.w, 0.f));
-              *reinterpret_cast<float4*>(p.x32 + (((long long)b * p.H + y) * (Cfg::CH / 4) + ((c0 + j) >> 2)) * ((long long)p.W * 4) +
-                                         (long long)x * 4) = xv;
+              *reinterpret_cast<float4*>(p.x32 + ((((long long)b * p.H + y) * p.tiles_x + tc.tx) * (Cfg::CH / 4) + ((c0 + j) >> 2)) * 32 +
+                                         (row & 7) * 4) = xv;
             }
 #pragma unroll
             for (int h2 = 0; h2 < 2; ++h2) {
@@ -513,10 +530,12 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
                 v1 = fmaxf(v1, 0.f);
               }
               const __half2 h = __floats2half2_rn(v0, v1);
-              const float2 hf = __half22float2(h);
-              const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
               hw[jj >> 1] = *reinterpret_cast<const uint32_t*>(&h);
-              lw[jj >> 1] = *reinterpret_cast<const uint32_t*>(&l);
+              if (want_lo) {
+                const float2 hf = __half22float2(h);
+                const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+                lw[jj >> 1] = *reinterpret_cast<const uint32_t*>(&l);
+              }
             }
           }
         }
@@ -533,6 +552,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if constexpr (Cfg::EPI == kEpiResidual32) {
+      if (have_prev) staged_store(smem_u32(s_stg) + (uint32_t)((warp - 2) * 1024), vh_prev, p.out_hi, g_prev, lane);
     }
   }
 
@@ -585,7 +607,10 @@ static int make_maps(CUtensorMap* a0, CUtensorMap* a1, CUtensorMap* w, const voi
 
 static int fill_tiles(PairParams& p, int n, int H, int W) {
   static const int dbg = getenv("DSEN2_PAIR_DEBUG") ? atoi(getenv("DSEN2_PAIR_DEBUG")) : 0;
-  p.debug = dbg;
+  static const int pf_a = getenv("DSEN2_PAIR_PF_A") ? atoi(getenv("DSEN2_PAIR_PF_A")) : kPrefetchTiles;
+  static const int pf_x = getenv("DSEN2_PAIR_PF_X") ? atoi(getenv("DSEN2_PAIR_PF_X")) : kTrunkPrefetchTiles;
+  static const int defer = getenv("DSEN2_PAIR_DEFER") ? atoi(getenv("DSEN2_PAIR_DEFER")) : 0;
+  p.debug = dbg; p.pf_a = pf_a; p.pf_x = pf_x; p.defer = defer;
   p.n = n; p.H = H; p.W = W;
   p.tiles_x = ceil_div(W, 8);
   p.tiles_y = ceil_div(H, 16);

@@ -408,7 +408,7 @@ extern "C" size_t dsen2_s2model_workspace_bytes(int n, int P, int in_channels, i
   const size_t pix = (size_t)n * P * P;
   if (feature_size == 128)   // x_in hi/lo (64 ch) + trunk hi/lo + resblock intermediate + fp32 trunk
     return 2 * align_up(pix * 64 * 2, 1024) + 3 * align_up(pix * feature_size * 2, 1024) +
-           align_up(pix * feature_size * 4, 1024) + 1024;
+           align_up((size_t)n * P * ((P + 7) / 8 * 8) * feature_size * 4, 1024) + 1024;
   return align_up(pix * head_k_pad(in_channels) * 2, 1024) + 3 * align_up(pix * feature_size * 2, 1024) + 1024;
 }
 

@@ -68,6 +68,23 @@ def input_rows(first, count, H, W, P, border):
     return r0, r1
 
 
+def plan_chunks(first, count, H, W, P, border, chunk_patch_rows):
+    """Cut the patch range [first, first+count) into chunks of whole patch rows for the host-buffer pipeline.
+
+    Returns [(p0, cnt, (r0, r1), rects)]: the chunk's patch range, the 10 m input rows it reads and the output
+    rectangles it owns.  Consecutive chunks read monotonically advancing row ranges, so each input row needs to be
+    uploaded once (``supres.HostPipeline`` uploads only the rows beyond the previous chunk's)."""
+    ny, nx, _ = tile_grid(H, W, P, border)
+    plan, p0, end = [], first, first + count
+    while p0 < end:
+        row = p0 // nx
+        p1 = min(end, (row + chunk_patch_rows) * nx)
+        cnt = p1 - p0
+        plan.append((p0, cnt, input_rows(p0, cnt, H, W, P, border), owned_rects(p0, cnt, H, W, P, border)))
+        p0 = p1
+    return plan
+
+
 def assemble(canvas, parts):
     """Host-side assembly: parts = [(first, count, rows_y0, band ndarray (y1-y0, W, C))]; writes owned rects."""
     H, W = canvas.shape[:2]

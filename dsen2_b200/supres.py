@@ -130,14 +130,9 @@ class HostPipeline:
         main = torch.cuda.current_stream(self.dev)
         self.up.wait_stream(main)
         self.down.wait_stream(main)
-        end = first_patch + num_patches
         done10 = done20 = done60 = None           # rows already resident on the device (per resolution)
-        p0 = first_patch
-        while p0 < end:
-            row = p0 // self.nx
-            p1 = min(end, (row + self.chunk_rows) * self.nx)
-            cnt = p1 - p0
-            r0, r1 = sharding.input_rows(p0, cnt, self.H, self.W, self.P, self.B)
+        for p0, cnt, (r0, r1), rects in sharding.plan_chunks(first_patch, num_patches, self.H, self.W, self.P, self.B,
+                                                             self.chunk_rows):
             with torch.cuda.stream(self.up):
                 done10 = self._upload(h10, self.d10, 1, r0, r1, done10)
                 done20 = self._upload(h20, self.d20, 2, r0, r1, done20)
@@ -152,13 +147,12 @@ class HostPipeline:
             ev_c.record(main)
             self.down.wait_event(ev_c)
             with torch.cuda.stream(self.down):
-                for (y0, y1, x0, x1) in sharding.owned_rects(p0, cnt, self.H, self.W, self.P, self.B):
+                for (y0, y1, x0, x1) in rects:
                     if x0 == 0 and x1 == self.W:
                         hout[y0:y1].copy_(self.canvas[y0:y1], non_blocking=True)
                     else:
                         hout[y0:y1, x0:x1].copy_(self.canvas[y0:y1, x0:x1], non_blocking=True)
                     self.d2h_bytes += (y1 - y0) * (x1 - x0) * self.canvas.shape[2] * 4
-            p0 = p1
         main.wait_stream(self.down)
         return hout
 

@@ -150,14 +150,15 @@ int dsen2_pack_tail_weights(const float* d_hwio, int feature_size, int cout, voi
 /* Conv2D(F, 3x3, relu) on the concatenated inputs (DSen2Net.py:29): x_in -> trunk.
  *   d_out_hi   NHWC fp16 (n,H,W,F): fp16 rounding of the layer output (the next convolution's operand)
  *   d_out_lo   optional NHWC fp16: out - out_hi (only the tail convolution reads it)
- *   d_trunk32  optional fp32 trunk in CHUNK-MAJOR layout (n, H, F/4, W, 4): element (n,y,x,c) at
- *              (((n*H + y)*(F/4) + c/4)*W + x)*4 + c%4 -- the layout dsen2_conv_res32 updates in place     */
+ *   d_trunk32  optional fp32 trunk in TILE-ROW-MAJOR layout (n, H, ceil(W/8), F/4, 8, 4): element (n,y,x,c) at
+ *              ((((n*H + y)*ceil(W/8) + x/8)*(F/4) + c/4)*8 + x%8)*4 + c%4 -- the layout dsen2_conv_res32
+ *              updates in place (a thread that owns one pixel reads/writes it coalesced; 4 KB DRAM bursts)   */
 int dsen2_conv_head(const void* d_xin_hi, const void* d_xin_lo, const void* d_w, const float* d_bias,
                     int n, int H, int W, int feature_size, void* d_out_hi, void* d_out_lo,
                     float* d_trunk32, void* stream);
 
 /* Second convolution of a resBlock with the residual update on the fp32 trunk (DSen2Net.py:12-15):
- *   trunk32 <- trunk32 + res_scale * (conv3x3(d_in) + bias)          (in place, chunk-major fp32)
+ *   trunk32 <- trunk32 + res_scale * (conv3x3(d_in) + bias)          (in place, tile-row-major fp32)
  *   d_out_hi <- fp16(trunk32) NHWC;  d_out_lo (optional) <- fp16(trunk32 - out_hi) NHWC
  * d_in is the NHWC fp16 output of the block's first convolution (dsen2_conv3x3 RELU); d_w from
  * dsen2_pack_conv_weights(cin_pad = cout_pad = 128).  feature_size 128 only.                              */

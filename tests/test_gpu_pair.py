@@ -133,7 +133,7 @@ def test_conv_head_fp32_equivalent(env, shape):
     tb = torch.from_numpy(bias).cuda()
     ohi = torch.zeros((n, H, W, F), dtype=torch.float16, device='cuda')
     olo = torch.zeros_like(ohi)
-    x32 = torch.full((n, H, F // 4, W, 4), -3.0, device='cuda')
+    x32 = torch.full((n, H, W // 8, F // 4, 8, 4), -3.0, device='cuda')
     _capi.check(lib.dsen2_conv_head(_capi.ptr(thi), _capi.ptr(tlo), _capi.ptr(tw), _capi.ptr(tb), n, H, W, F,
                                     _capi.ptr(ohi), _capi.ptr(olo), _capi.ptr(x32), _capi.stream_ptr()), 'conv head')
     torch.cuda.synchronize()
@@ -144,8 +144,8 @@ def test_conv_head_fp32_equivalent(env, shape):
     got = ohi.cpu().numpy().astype(np.float64) + olo.cpu().numpy().astype(np.float64)
     np.testing.assert_allclose(got, ref, rtol=2e-5, atol=2e-5)
     assert np.abs(got - np.maximum(_conv64(xcat.transpose(0, 2, 3, 1), w, bias), 0)).max() < 5e-5   # vs true fp32 layer
-    # fp32 trunk seed, chunk-major (n, H, F/4, W, 4): the same values before the hi/lo split
-    trunk = x32.cpu().numpy().transpose(0, 1, 3, 2, 4).reshape(n, H, W, F)
+    # fp32 trunk seed, tile-row-major (n, H, W/8, F/4, 8, 4): the same values before the hi/lo split
+    trunk = x32.cpu().numpy().transpose(0, 1, 2, 4, 3, 5).reshape(n, H, W, F)
     np.testing.assert_allclose(trunk, ref, rtol=2e-5, atol=2e-5)
     assert np.array_equal(trunk.astype(np.float16).view(np.uint16), ohi.cpu().numpy().view(np.uint16))
 
@@ -257,7 +257,7 @@ def test_pair_kernel_matches_single_cta_kernel(env):
 @pytest.mark.parametrize('shape', [(2, 32, 32), (1, 128, 128), (3, 40, 24), (1, 8, 200), (2, 192, 192)])
 @pytest.mark.parametrize('want_lo', [False, True])
 def test_conv_res32_fp32_trunk_update(env, shape, want_lo):
-    """trunk32 <- trunk32 + 0.1 * (conv(t) + b) in place on the chunk-major fp32 trunk; fp16 hi (and lo) copies."""
+    """trunk32 <- trunk32 + 0.1 * (conv(t) + b) in place on the tile-row-major fp32 trunk; fp16 hi (and lo) copies."""
     torch, _capi, lib = env
     n, H, W = shape
     F = 128
@@ -270,7 +270,7 @@ def test_conv_res32_fp32_trunk_update(env, shape, want_lo):
     tw = torch.empty((9, F, F), dtype=torch.float16, device='cuda')
     _capi.check(lib.dsen2_pack_conv_weights(_capi.ptr(torch.from_numpy(w).cuda()), F, F, F, F, 0, _capi.ptr(tw), None,
                                             _capi.stream_ptr()), 'pack')
-    x_cm = np.ascontiguousarray(x.reshape(n, H, W, F // 4, 4).transpose(0, 1, 3, 2, 4))
+    x_cm = np.ascontiguousarray(x.reshape(n, H, W // 8, 8, F // 4, 4).transpose(0, 1, 2, 4, 3, 5))
     tx, tt, tb = torch.from_numpy(x_cm).cuda(), torch.from_numpy(t).cuda(), torch.from_numpy(bias).cuda()
     hi = torch.zeros((n, H, W, F), dtype=torch.float16, device='cuda')
     lo = torch.zeros_like(hi) if want_lo else None
@@ -278,7 +278,7 @@ def test_conv_res32_fp32_trunk_update(env, shape, want_lo):
                                      _capi.ptr(hi), _capi.ptr(lo), _capi.stream_ptr()), 'conv res32')
     torch.cuda.synchronize()
     ref = x.astype(np.float64) + 0.1 * _conv64(t.astype(np.float64), w.astype(np.float16).astype(np.float64), bias)
-    got = tx.cpu().numpy().transpose(0, 1, 3, 2, 4).reshape(n, H, W, F)
+    got = tx.cpu().numpy().transpose(0, 1, 2, 4, 3, 5).reshape(n, H, W, F)
     np.testing.assert_allclose(got, ref, rtol=2e-5, atol=2e-5)
     assert np.array_equal(hi.cpu().numpy().view(np.uint16), got.astype(np.float16).view(np.uint16))
     if want_lo:

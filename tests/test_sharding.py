@@ -37,6 +37,32 @@ def test_owned_rects_tile_the_image_exactly_once(geom, world):
     assert cover.min() == 1 and cover.max() == 1
 
 
+@pytest.mark.parametrize('geom', GEOMS)
+@pytest.mark.parametrize('world', [1, 3])
+@pytest.mark.parametrize('chunk_rows', [1, 6])
+def test_plan_chunks_covers_range_once_with_monotonic_uploads(geom, world, chunk_rows):
+    """Host-buffer pipeline plan: chunks partition the rank's patch range, every owned pixel is downloaded exactly
+    once, and uploading only the rows beyond the previous chunk's still gives every chunk all the rows it reads."""
+    H, W, P, B = geom
+    ny, nx, S = sharding.tile_grid(H, W, P, B)
+    cover = np.zeros((H, W), np.uint8)
+    for r in range(world):
+        first, count = sharding.shard_range(ny * nx, r, world)
+        plan = sharding.plan_chunks(first, count, H, W, P, B, chunk_rows)
+        assert [p for p, _, _, _ in plan] == sorted(p for p, _, _, _ in plan)
+        assert sum(c for _, c, _, _ in plan) == count and plan[0][0] == first
+        resident = None                                    # [lo, hi) rows on the device, as HostPipeline tracks them
+        for p0, cnt, (r0, r1), rects in plan:
+            assert cnt > 0 and 0 <= r0 < r1 <= H
+            lo, hi = (r0, r1) if resident is None else (resident[0], max(resident[1], r1))
+            assert resident is None or r0 >= resident[0], "row ranges must advance monotonically"
+            resident = (lo, hi)
+            assert resident[0] <= r0 and r1 <= resident[1]
+            for (y0, y1, x0, x1) in rects:
+                cover[y0:y1, x0:x1] += 1
+    assert cover.min() == 1 and cover.max() == 1
+
+
 def test_ownership_equals_sequential_overwrite():
     for (H, W, P, B) in GEOMS[:3]:
         ny, nx, S = sharding.tile_grid(H, W, P, B)

@@ -120,7 +120,7 @@ def check_pair_timing():
         xin_hi = torch.randn((n, P, P, 64), device='cuda').half()
         xin_lo = (torch.randn((n, P, P, 64), device='cuda') * 1e-3).half()
         wh = (torch.rand((3, 2 * F, 64), device='cuda') - 0.5).half()
-        x32 = torch.zeros((n, P, F // 4, P, 4), device='cuda')
+        x32 = torch.zeros((n, P, P // 8, F // 4, 8, 4), device='cuda')
         ms = _time(torch, lambda: _capi.check(lib.dsen2_conv_res32(ptr(t), ptr(w), ptr(b), n, P, P, 0.1, ptr(x32), ptr(hi),
                                                                    None, st), 'res32'))
         print('n=%d pair RESIDUAL32 (fp32 trunk): %.3f ms  %.1f TFLOP/s' % (n, ms, fl / ms / 1e9), flush=True)
@@ -158,6 +158,34 @@ def check_pair_relu_only():
     ms = _time(torch, lambda: _capi.check(lib.dsen2_conv3x3(ptr(t), ptr(w), ptr(b), n, P, P, F, F, 9, 1, ptr(hi),
                                                             ptr(lo), 0.1, ptr(hi), ptr(lo), None, None, 0, st), 'res'))
     print('DEBUG=%s RESIDUAL : %.3f ms  %.1f TFLOP/s' % (os.environ.get('DSEN2_PAIR_DEBUG', '0'), ms, fl / ms / 1e9), flush=True)
+
+
+def check_pair_res32_only():
+    import torch
+    from dsen2_b200 import _capi
+    lib, ptr = _capi.lib(), _capi.ptr
+    st = _capi.stream_ptr()
+    F, P, n = 128, 128, 64
+    x = torch.randn((n, P, P, F), device='cuda').half()
+    w = (torch.rand((9, F, F), device='cuda') - 0.5).half()
+    b = torch.zeros(F, device='cuda')
+    hi, t = torch.zeros_like(x), torch.empty_like(x)
+    x32 = torch.zeros((n, P, P // 8, F // 4, 8, 4), device='cuda')
+    fl = 2.0 * n * P * P * 9 * F * F
+    def both():
+        _capi.check(lib.dsen2_conv3x3(ptr(hi), ptr(w), ptr(b), n, P, P, F, F, 9, 0, None, None, 0.0, ptr(t), None, None, None, 0, st), 'relu')
+        _capi.check(lib.dsen2_conv_res32(ptr(t), ptr(w), ptr(b), n, P, P, 0.1, ptr(x32), ptr(hi), None, st), 'res32')
+    ms = _time(torch, both, iters=12)
+    print('PF_A=%s PF_X=%s DEFER=%s  resblock (RELU + RESIDUAL32): %.3f ms  %.1f TFLOP/s' % (
+        os.environ.get('DSEN2_PAIR_PF_A', 'd'), os.environ.get('DSEN2_PAIR_PF_X', 'd'), os.environ.get('DSEN2_PAIR_DEFER', 'd'),
+        ms, 2 * fl / ms / 1e9), flush=True)
+
+
+def check_pair_knob_sweep():
+    for pa, px, de in (('2', '1', '0'), ('2', '1', '1'), ('3', '2', '1'), ('3', '1', '0'), ('2', '2', '0'), ('1', '1', '0'),
+                       ('0', '0', '0'), ('4', '1', '0'), ('2', '3', '1')):
+        env = dict(os.environ, DSEN2_PAIR_PF_A=pa, DSEN2_PAIR_PF_X=px, DSEN2_PAIR_DEFER=de)
+        subprocess.run([sys.executable, os.path.abspath(__file__), '--one', 'pair_res32_only'], env=env, timeout=120)
 
 
 def check_pair_debug_sweep():

@@ -25,7 +25,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-FLOP_PER_PIXEL = {('dsen2', 20): 3575808, ('vdsen2', 20): 75571200, ('dsen2', 60): 3571200}
+FLOP_PER_PIXEL = {('dsen2', 20): 3575808, ('vdsen2', 20): 75571200, ('dsen2', 60): 3571200,
+                  ('vdsen2', 60): 75561984}
 
 
 def log(*a):
@@ -42,7 +43,7 @@ def peaks():
         return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, source='fallback (B200_PROFILING.md)')
 
 
-def synth_tile(torch, H, W, device, seed=20170928):
+def synth_tile(torch, H, W, device, seed=20170928, with_60=False):
     """integer DN, 1600 + 900*smooth + 150*noise clipped to [0, 12000]."""
     g = torch.Generator(device=device).manual_seed(seed)
     F = torch.nn.functional
@@ -55,7 +56,7 @@ def synth_tile(torch, H, W, device, seed=20170928):
             noise = torch.randn((h, w), generator=g, device=device)
             out[:, :, k] = (1600 + 900 * smooth[k] + 150 * noise).clamp_(0, 12000).round_()
         return out
-    return field(H, W, 4), field(H // 2, W // 2, 6)
+    return (field(H, W, 4), field(H // 2, W // 2, 6)) + ((field(H // 6, W // 6, 2),) if with_60 else ())
 
 
 class ClockSampler:
@@ -145,10 +146,11 @@ def run_reference(args):
 
 def workload_config(args, cpu=False):
     T = args.tile
-    n = (-(-T // 112)) ** 2
-    return {"workload": "%s 20m->10m, synthetic %dx%d Sentinel-2 tile, %d patches 128x128 (border 8), "
+    P, B = (192, 12) if args.path == 60 else (128, 8)
+    n = (-(-T // (P - 2 * B))) ** 2
+    return {"workload": "%s %dm->10m, synthetic %dx%d Sentinel-2 tile, %d patches %dx%d (border %d), "
                         "he_uniform weights seed 0 (shipped hdf5 absent)" % ('VDSen2 (32x256)' if args.model == 'vdsen2'
-                                                                             else 'DSen2 (6x128)', T, T, n),
+                                                                             else 'DSen2 (6x128)', args.path, T, T, n, P, P, B),
             "tile": T, "patches": n, "device_batch": args.batch, "sharding": "contiguous patch ranges, no collective",
             "l2": "inputs (2.6 GB) and activations larger than L2; no flush needed",
             "cpu_sample_only": bool(cpu)}
@@ -186,21 +188,27 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    T, P, B = args.tile, 128, 8
+    run_60 = args.path == 60
+    T, P, B, r = (args.tile, 192, 12, 6) if run_60 else (args.tile, 128, 8, 2)
+    if T % 6:
+        raise SystemExit("--tile must be a multiple of 6")
     deep = args.model == 'vdsen2'
-    model = s2model(((4, None, None), (6, None, None)), num_layers=32 if deep else 6,
-                    feature_size=256 if deep else 128, seed=0)
-    d10, d20 = synth_tile(torch, T, T, dev)
-    _, filled = patch_counts(T // 2, T // 2, 64, 4)
+    shape = ((4, None, None), (6, None, None)) + (((2, None, None),) if run_60 else ())
+    model = s2model(shape, num_layers=32 if deep else 6, feature_size=256 if deep else 128, seed=0)
+    tile = synth_tile(torch, T, T, dev, with_60=run_60)
+    d10, d20 = tile[0], tile[1]
+    d60 = tile[2] if run_60 else None
+    _, filled = patch_counts(T // r, T // r, P // r, B // r)
     first, count = sharding.shard_range(filled, rank, world)
-    out = torch.zeros((T, T, 6), dtype=torch.float32, device=dev)
+    cout = model.out_channels
+    out = torch.zeros((T, T, cout), dtype=torch.float32, device=dev)
     n_batches = -(-count // args.batch)
     # fast path (DSen2): 1 input-preparation kernel + 14 convolutions per batch (extract / bilinear / stitch are
     # fused into them); VDSen2: 2 extract + bilinear + im2col pack + 66 convolutions + stitch
     launches_per_step = n_batches * (model.launches_per_forward() if model.fast_path else 4 + model.launches_per_forward())
 
     def step(timers=None):
-        supres.super_resolve_device(model, d10, d20, first_patch=first, num_patches=count, out=out,
+        supres.super_resolve_device(model, d10, d20, d60, first_patch=first, num_patches=count, out=out,
                                     device_batch=args.batch, timers=timers)
 
     # ---- value: device-resident ---------------------------------------------------------------
@@ -260,15 +268,42 @@ def run_ours(args):
     #  pixels they own.
     h10 = torch.empty((T, T, 4), dtype=torch.float32).pin_memory()
     h20 = torch.empty((T // 2, T // 2, 6), dtype=torch.float32).pin_memory()
-    hout = torch.zeros((T, T, 6), dtype=torch.float32).pin_memory()
+    h60 = torch.empty((T // 6, T // 6, 2), dtype=torch.float32).pin_memory() if run_60 else None
+    hout = torch.zeros((T, T, cout), dtype=torch.float32).pin_memory()
     h10.copy_(d10); h20.copy_(d20)
+    if run_60:
+        h60.copy_(d60)
     torch.cuda.synchronize()
-    del d10, d20, out
+    del d10, d20, d60, tile, out
     torch.cuda.empty_cache()
-    pipe = supres.HostPipeline(model, T, T, run_60=False, device=dev, device_batch=args.batch)
+    if model.fast_path:
+        pipe = supres.HostPipeline(model, T, T, run_60=run_60, device=dev, device_batch=args.batch)
 
-    def step_e2e():
-        pipe.run(h10, h20, hout=hout, first_patch=first, num_patches=count)
+        def step_e2e():
+            pipe.run(h10, h20, h60, hout=hout, first_patch=first, num_patches=count)
+    else:                                   # VDSen2: plain upload -> device pipeline -> download of the rank's rows
+        r0, r1 = sharding.input_rows(first, count, T, T, P, B)
+        o0, o1 = sharding.output_rows(first, count, T, T, P, B)
+        g10 = torch.empty((T, T, 4), dtype=torch.float32, device=dev)
+        g20 = torch.empty((T // 2, T // 2, 6), dtype=torch.float32, device=dev)
+        g60 = torch.empty((T // 6, T // 6, 2), dtype=torch.float32, device=dev) if run_60 else None
+        gout = torch.zeros((T, T, cout), dtype=torch.float32, device=dev)
+
+        class _Plain:
+            h2d_bytes = d2h_bytes = 0
+        pipe = _Plain()
+
+        def step_e2e():
+            g10[r0:r1].copy_(h10[r0:r1], non_blocking=True)
+            g20[r0 // 2:-(-r1 // 2)].copy_(h20[r0 // 2:-(-r1 // 2)], non_blocking=True)
+            if run_60:
+                g60[r0 // 6:-(-r1 // 6)].copy_(h60[r0 // 6:-(-r1 // 6)], non_blocking=True)
+            supres.super_resolve_device(model, g10, g20, g60, first_patch=first, num_patches=count, out=gout,
+                                        device_batch=args.batch)
+            hout[o0:o1].copy_(gout[o0:o1], non_blocking=True)
+            pipe.h2d_bytes = (r1 - r0) * T * 16 + (-(-r1 // 2) - r0 // 2) * (T // 2) * 24 + \
+                ((-(-r1 // 6) - r0 // 6) * (T // 6) * 8 if run_60 else 0)
+            pipe.d2h_bytes = (o1 - o0) * T * cout * 4
 
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()
@@ -296,7 +331,7 @@ def run_ours(args):
                 "e2e": {"value": T * T / (e2e_ms * 1e-3) / 1e6, "unit": "Mpixel/s", "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches_per_step * args.steps, "roofline": roofline,
-                "tflops_executed_whole_step": FLOP_PER_PIXEL[(args.model, 20)] * float(filled) * P * P / (ms_step * 1e-3) / 1e12,
+                "tflops_executed_whole_step": FLOP_PER_PIXEL[(args.model, args.path)] * float(filled) * P * P / (ms_step * 1e-3) / 1e12,
                 "checksum": checksum}
         if world == 1 and not args.no_cpu_baseline:
             crop = 672
@@ -317,6 +352,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--model', default='dsen2', choices=['dsen2', 'vdsen2'])
     ap.add_argument('--tile', type=int, default=10980)
+    ap.add_argument('--path', type=int, default=20, choices=[20, 60], help='20 m -> 10 m (DSen2_20) or 60 m -> 10 m (DSen2_60)')
     ap.add_argument('--batch', type=int, default=64, help='patches per device batch')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()

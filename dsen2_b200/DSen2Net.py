@@ -307,10 +307,57 @@ class S2Model:
                 print("%d/%d" % (min(i + device_batch, N), N))
         return out
 
-    def compile(self, *a, **k):
-        raise NotImplementedError("training (supres_train.py) is not part of this round's inference path")
+    # ---- training (supres_train.py:137-144, 218-230) ------------------------------------------------------ #
+    def compile(self, optimizer=None, loss='mean_absolute_error', metrics=None):
+        """``model.compile(optimizer=Nadam(...), loss='mean_absolute_error', metrics=['mean_squared_error'])``."""
+        from .train import Nadam, Trainer
+        if loss != 'mean_absolute_error':
+            raise ValueError("only loss='mean_absolute_error' (the reference's) is implemented")
+        if optimizer is None or optimizer == 'nadam':
+            optimizer = Nadam()
+        self._trainer = Trainer(self, optimizer)
+        self.metrics_names = ['loss', 'mean_squared_error']
+        return self._trainer
 
-    fit = compile
+    def train_on_batch(self, x, y):
+        """One optimisation step on numpy (or CUDA tensor) inputs; returns [loss, mean_squared_error] like Keras."""
+        torch = _capi.require_cuda()
+        if getattr(self, '_trainer', None) is None:
+            raise RuntimeError("You must compile a model before training/testing. Use `model.compile(optimizer, loss)`.")
+        tr = self._trainer
+        to_dev = lambda a: a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(tr.dev)
+        loss, mse = tr.train_step([to_dev(a) for a in (x if isinstance(x, (list, tuple)) else [x])], to_dev(y))
+        self._weights_stale = True
+        return [float(loss), float(mse)]
+
+    def fit(self, x, y, batch_size=128, epochs=1, verbose=0, shuffle=True, seed=None, **_ignored):
+        """Minimal ``model.fit``: shuffled mini-batches, returns {'loss': [...], 'mean_squared_error': [...]} per epoch.
+        (Callbacks / validation of supres_train.py:195-230 are host-side bookkeeping outside the GPU path.)"""
+        xs = [np.asarray(a) for a in (x if isinstance(x, (list, tuple)) else [x])]
+        y = np.asarray(y)
+        n = y.shape[0]
+        rng = np.random.RandomState(seed)
+        hist = {'loss': [], 'mean_squared_error': []}
+        for ep in range(epochs):
+            order = rng.permutation(n) if shuffle else np.arange(n)
+            tot, tot_mse, cnt = 0.0, 0.0, 0
+            for i in range(0, n, batch_size):
+                idx = np.sort(order[i:i + batch_size])
+                l, q = self.train_on_batch([a[idx] for a in xs], y[idx])
+                tot, tot_mse, cnt = tot + l * len(idx), tot_mse + q * len(idx), cnt + len(idx)
+            hist['loss'].append(tot / cnt)
+            hist['mean_squared_error'].append(tot_mse / cnt)
+            if verbose:
+                print("Epoch %d/%d - loss: %.6f - mean_squared_error: %.6f" % (ep + 1, epochs, hist['loss'][-1],
+                                                                               hist['mean_squared_error'][-1]))
+        self.sync_weights_from_trainer()
+        return hist
+
+    def sync_weights_from_trainer(self):
+        """Pull the trained fp32 master weights back into the model (so predict / save_weights see them)."""
+        if getattr(self, '_trainer', None) is not None:
+            self.set_weights(self._trainer.get_weights())
+            self._weights_stale = False
 
 
 def s2model(input_shape, num_layers=32, feature_size=256, seed=None):

@@ -1,7 +1,7 @@
 """ctypes binding of the C ABI in ``include/dsen2_b200.h`` -- fails loudly, never falls back."""
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_size_t, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_longlong, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libdsen2_b200.so")
@@ -42,6 +42,17 @@ SIGNATURES = {
                                 c_int, c_void_p, c_void_p]),
     "dsen2_conv_tail_stitch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                        c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
+    "dsen2_pack_dgrad_weights": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
+    "dsen2_conv_relu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "dsen2_planar_pitch": (c_longlong, [c_int, c_int, c_int]),
+    "dsen2_nhwc_to_planar": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "dsen2_nchw_to_planar": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                     c_int, c_float, c_void_p, c_void_p]),
+    "dsen2_nchw_to_nhwc_f16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "dsen2_wgrad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
+    "dsen2_rowsum": (c_int, [c_void_p, c_int, c_longlong, c_float, c_void_p, c_void_p]),
+    "dsen2_mae_grad": (c_int, [c_void_p, c_void_p, c_longlong, c_float, c_void_p, c_void_p, c_void_p]),
+    "dsen2_nadam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong] + [c_float] * 10 + [c_void_p]),
     "dsen2_debug_force_v1": (c_int, [c_int]),
     "dsen2_debug_umma_rowshift": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
 }

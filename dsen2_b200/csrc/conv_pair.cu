@@ -37,7 +37,7 @@ static constexpr int kBoxH = 18;
 static constexpr int kPrefetchTiles = 1;        // L2 prefetch distance of the activation boxes, in tiles of this CTA
 static constexpr int kTrunkPrefetchTiles = 1;   // same for the fp32 trunk lines the RESIDUAL32 epilogue reads
 
-enum { kEpiRelu = 0, kEpiResidual = 1, kEpiTail = 2, kEpiResidual32 = 3 };
+enum { kEpiRelu = 0, kEpiResidual = 1, kEpiTail = 2, kEpiResidual32 = 3, kEpiMask = 4 };
 
 struct PairParams {
   int n, H, W;
@@ -492,6 +492,15 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
           staged_gather(stg, gh, vh, lane);
           staged_gather(stg, gl, vl, lane);
         }
+        if (Cfg::EPI == kEpiMask) {                 // ReLU backward: the forward activation decides which gradients pass
+          uint4 gm[8];
+          coalesced_load(gm, p.res_hi, g, lane);
+          if (pt + npairs < pair_tiles) {
+            const EpiGeom gn = epi_geom<Cfg>(p, decode_tile(2 * (pt + npairs) + rank, p.tiles_x, p.tiles_y), wq, half);
+            prefetch_rows(p.res_hi, gn, lane);
+          }
+          staged_gather(stg, gm, vh, lane);
+        }
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
 #pragma unroll
@@ -530,6 +539,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
                 const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&lw[jj >> 1]));
                 v0 = (a.x + c.x) + v0 * p.res_scale;     // Lambda(x * scale) then Add (DSen2Net.py:13,15)
                 v1 = (a.y + c.y) + v1 * p.res_scale;
+              } else if (Cfg::EPI == kEpiMask) {
+                const float2 m = __half22float2(*reinterpret_cast<const __half2*>(&hw[jj >> 1]));
+                v0 = m.x > 0.f ? v0 : 0.f;               // d relu(z) / dz = [z > 0]  (relu(z) > 0  <=>  z > 0)
+                v1 = m.y > 0.f ? v1 : 0.f;
               } else {
                 v0 = fmaxf(v0, 0.f);
                 v1 = fmaxf(v1, 0.f);
@@ -576,6 +589,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
 using CfgRelu = PairCfg<128, false, 1, 2, 9, 4, 3, kEpiRelu>;
 using CfgResidual = PairCfg<128, false, 1, 2, 9, 4, 3, kEpiResidual>;
 using CfgResidual32 = PairCfg<128, false, 1, 2, 9, 4, 3, kEpiResidual32>;
+using CfgMask = PairCfg<128, false, 1, 2, 9, 4, 3, kEpiMask>;
 using CfgHead = PairCfg<256, true, 2, 1, 3, 3, 6, kEpiRelu>;
 using CfgTail = PairCfg<32, true, 2, 2, 9, 4, 6, kEpiTail>;
 
@@ -647,6 +661,28 @@ int conv_pair_res(const void* d_in, const void* d_w, const float* d_bias, int n,
 }  // namespace dsen2
 
 using namespace dsen2;
+
+extern "C" int dsen2_conv_relu_bwd(const void* d_in, const void* d_w, const float* d_bias, const void* d_fwd_act, int n,
+                                   int H, int W, void* d_out, void* stream) {
+  DSEN2_REQUIRE(d_in && d_w && d_bias && d_fwd_act && d_out, DSEN2_E_BADARG, "dsen2_conv_relu_bwd: null pointer");
+  DSEN2_REQUIRE(n >= 0 && H > 0 && W > 0, DSEN2_E_BADARG, "dsen2_conv_relu_bwd: bad shape");
+  DSEN2_REQUIRE(((uintptr_t)d_in % 16) == 0 && ((uintptr_t)d_w % 16) == 0 && ((uintptr_t)d_fwd_act % 16) == 0 &&
+                    ((uintptr_t)d_out % 16) == 0,
+                DSEN2_E_ALIGN, "dsen2_conv_relu_bwd: pointers must be 16-byte aligned");
+  if (n == 0) return 0;
+  int sms = 0;
+  int rc = device_sm_count_and_check(&sms);
+  if (rc) return rc;
+  PairParams p{};
+  if ((rc = fill_tiles(p, n, H, W)) != 0) return rc;
+  p.bias = d_bias;
+  p.res_hi = (const __half*)d_fwd_act;
+  p.out_hi = (__half*)d_out;
+  CUtensorMap a0, a1, w;
+  rc = make_maps<CfgMask>(&a0, &a1, &w, d_in, nullptr, d_w, n, H, W);
+  if (rc) return rc;
+  return launch_pair<CfgMask>(a0, a1, w, p, sms, (cudaStream_t)stream, "conv_pair<relu_bwd>");
+}
 
 extern "C" int dsen2_conv_res32(const void* d_in, const void* d_w, const float* d_bias, int n, int H, int W,
                                 float res_scale, float* d_trunk32, void* d_out_hi, void* d_out_lo, void* stream) {

@@ -1,0 +1,256 @@
+"""Training step of the DSen2 network -- mirror of ``training/supres_train.py:137-144, 218-230``:
+
+    nadam = Nadam(lr=1e-4, beta_1=0.9, beta_2=0.999, epsilon=1e-8, schedule_decay=0.004)
+    model.compile(optimizer=nadam, loss='mean_absolute_error', metrics=['mean_squared_error'])
+    model.fit(x=train, y=label, batch_size=128, ...)
+
+One ``Trainer.train_step`` = forward + MAE loss + backward + (NCCL all-reduce of the flat gradient when the process
+group has more than one rank) + Keras-2 Nadam update, all in the CUDA kernels behind ``include/dsen2_b200.h``:
+the forward and backward-data convolutions are the CTA-pair tcgen05 kernels (``csrc/conv_pair.cu``; backward uses
+flipped / transposed operands), weight gradients are tcgen05 GEMMs over the pixel dimension
+(``csrc/train_kernels.cu``).  Activations and gradients are fp16 operands with fp32 accumulation; gradients carry a
+power-of-two loss scale so that the MAE gradient sign(pred-y)/N enters the fp16 data path as exactly +-2^-4.
+Master weights, gradients and the Nadam moments are fp32.  DSen2 (feature_size 128) only.
+"""
+import math
+
+import numpy as np
+
+from . import _capi
+
+
+class Nadam:
+    """Hyper-parameters of ``keras.optimizers.Nadam`` as the reference configures it (supres_train.py:137-141)."""
+
+    def __init__(self, lr=1e-4, beta_1=0.9, beta_2=0.999, epsilon=1e-8, schedule_decay=0.004):
+        self.lr, self.beta_1, self.beta_2, self.epsilon, self.schedule_decay = lr, beta_1, beta_2, epsilon, schedule_decay
+
+
+def nadam_schedule(t, m_schedule, opt):
+    """Keras-2 Nadam momentum schedule at (1-based) iteration t -> dict of the scalars the update kernel needs."""
+    mu_t = opt.beta_1 * (1.0 - 0.5 * 0.96 ** (t * opt.schedule_decay))
+    mu_next = opt.beta_1 * (1.0 - 0.5 * 0.96 ** ((t + 1) * opt.schedule_decay))
+    sched_new = m_schedule * mu_t
+    return dict(mu_t=mu_t, mu_next=mu_next, sched_new=sched_new, sched_next=sched_new * mu_next,
+                bias2=1.0 - opt.beta_2 ** t)
+
+
+def allreduce_gradients(flat, group=None):
+    """Sum the flat gradient over the ranks (NCCL on GPUs, gloo in the CPU tests); returns the world size to divide by."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1
+    world = dist.get_world_size(group)
+    if world > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    return world
+
+
+class Trainer:
+    GSCALE = 2.0 ** -4          # value of the scaled MAE gradient entering the fp16 backward path
+
+    def __init__(self, model, optimizer=None, device=None, group=None):
+        torch = _capi.require_cuda()
+        if not model.fast_path:
+            raise _capi.DSen2Error("training is implemented for the DSen2 (feature_size 128) network")
+        self.torch, self.model, self.opt, self.group = torch, model, optimizer or Nadam(), group
+        self.dev = torch.device('cuda', torch.cuda.current_device()) if device is None else device
+        self.F, self.L = model.feature_size, model.num_layers
+        self.ctot, self.cout = sum(model.in_channels), model.out_channels
+        shapes = model.layer_shapes
+        self.sizes = []
+        for cin, cout in shapes:
+            self.sizes += [9 * cin * cout, cout]
+        self.offsets = np.concatenate([[0], np.cumsum(self.sizes)]).astype(np.int64)
+        total = int(self.offsets[-1])
+        flat = np.concatenate([a.ravel() for a in model.get_weights()]).astype(np.float32)
+        assert flat.size == total
+        self.params = torch.from_numpy(flat).to(self.dev)
+        self.grads = torch.zeros(total, dtype=torch.float32, device=self.dev)
+        self.m = torch.zeros_like(self.grads)
+        self.v = torch.zeros_like(self.grads)
+        self.iterations, self.m_schedule = 0, 1.0
+        self.sums = torch.zeros(2, dtype=torch.float64, device=self.dev)
+        self.zero_bias = torch.zeros(128, dtype=torch.float32, device=self.dev)
+        self._bufs = {}
+        f16 = lambda *s: torch.empty(s, dtype=torch.float16, device=self.dev)
+        F, L = self.F, self.L
+        self.w_fwd = [f16(3, 2 * F, 64)] + [f16(9, F, F) for _ in range(2 * L)] + [f16(9, 32, F)]
+        self.w_bwd = [None] + [f16(9, F, F) for _ in range(2 * L)] + [f16(9, F, F)]
+        self.b_fwd = [torch.zeros(max(c, 16), dtype=torch.float32, device=self.dev) for _, c in shapes]
+        self.gw_head = torch.zeros((9, 128, 128), dtype=torch.float32, device=self.dev)
+        self.gw_tail = torch.zeros((9, 128, 16), dtype=torch.float32, device=self.dev)
+        self.gb_tail = torch.zeros(16, dtype=torch.float32, device=self.dev)
+        self.repack()
+
+    # ---- parameter views -------------------------------------------------------------------------------------
+    def _view(self, flat, i):
+        return flat[int(self.offsets[i]):int(self.offsets[i + 1])]
+
+    def kernel(self, layer, flat=None):
+        return self._view(self.params if flat is None else flat, 2 * layer)
+
+    def bias(self, layer, flat=None):
+        return self._view(self.params if flat is None else flat, 2 * layer + 1)
+
+    def get_weights(self):
+        """Keras order [kernel, bias, ...] as numpy arrays (HWIO kernels)."""
+        host = self.params.cpu().numpy()
+        out = []
+        for i, (cin, cout) in enumerate(self.model.layer_shapes):
+            out.append(host[self.offsets[2 * i]:self.offsets[2 * i + 1]].reshape(3, 3, cin, cout).copy())
+            out.append(host[self.offsets[2 * i + 1]:self.offsets[2 * i + 2]].copy())
+        return out
+
+    def repack(self):
+        """fp32 master weights -> fp16 operands of the forward and backward-data convolutions."""
+        lib, ptr, st = _capi.lib(), _capi.ptr, _capi.stream_ptr()
+        F, L, nl = self.F, self.L, 2 * self.L + 2
+        with self.torch.cuda.device(self.dev):
+            _capi.check(lib.dsen2_pack_head_weights(ptr(self.kernel(0)), self.ctot, F, ptr(self.w_fwd[0]), st), "pack head")
+            for i in range(1, nl - 1):
+                _capi.check(lib.dsen2_pack_conv_weights(ptr(self.kernel(i)), F, F, F, F, 0, ptr(self.w_fwd[i]), None, st),
+                            "pack trunk")
+                # second conv of a resBlock is followed by Lambda(x * 0.1) (DSen2Net.py:13): fold it into the operand
+                scale = 0.1 if i % 2 == 0 else 1.0
+                _capi.check(lib.dsen2_pack_dgrad_weights(ptr(self.kernel(i)), F, F, F, F, scale, ptr(self.w_bwd[i]), st),
+                            "pack dgrad")
+            _capi.check(lib.dsen2_pack_tail_weights(ptr(self.kernel(nl - 1)), F, self.cout, ptr(self.w_fwd[-1]), st), "pack tail")
+            _capi.check(lib.dsen2_pack_dgrad_weights(ptr(self.kernel(nl - 1)), F, self.cout, F, F, 1.0, ptr(self.w_bwd[-1]), st),
+                        "pack dgrad tail")
+            for i in range(nl):
+                c = self.model.layer_shapes[i][1]
+                self.b_fwd[i][:c].copy_(self.bias(i))
+
+    def _buffers(self, n, P):
+        key = (n, P)
+        b = self._bufs.get(key)
+        if b is None:
+            torch, F, L = self.torch, self.F, self.L
+            f16 = lambda *s: torch.empty(s, dtype=torch.float16, device=self.dev)
+            pitch = int(_capi.lib().dsen2_planar_pitch(n, P, P))
+            b = dict(xin_hi=f16(n, P, P, 64), xin_lo=f16(n, P, P, 64), x_hi=[f16(n, P, P, F) for _ in range(L + 1)],
+                     t=[f16(n, P, P, F) for _ in range(L)], x_lo=f16(n, P, P, F),
+                     x32=torch.empty((n, P, (P + 7) // 8, F // 4, 8, 4), dtype=torch.float32, device=self.dev),
+                     dx32=torch.empty((n, P, (P + 7) // 8, F // 4, 8, 4), dtype=torch.float32, device=self.dev),
+                     dx_hi=f16(n, P, P, F), g2=f16(n, P, P, F), dy_nhwc=f16(n, P, P, F),
+                     pred=torch.empty((n, self.cout, P, P), dtype=torch.float32, device=self.dev),
+                     dpred=torch.empty((n, self.cout, P, P), dtype=torch.float32, device=self.dev),
+                     pa=f16(3, 128, pitch), pb=f16(128, pitch), pt=f16(16, pitch), pitch=pitch)
+            self._bufs = {key: b}
+        return b
+
+    # ---- forward ---------------------------------------------------------------------------------------------
+    def forward(self, xs, b, n, P):
+        lib, ptr, st = _capi.lib(), _capi.ptr, _capi.stream_ptr()
+        F, L, ch = self.F, self.L, self.model.in_channels
+        x2, c2 = (xs[2], ch[2]) if len(xs) == 3 else (None, 0)
+        _capi.check(lib.dsen2_prep_from_patches(ptr(xs[0]), ch[0], ptr(xs[1]), ch[1], ptr(x2), c2, n, P, ptr(b['xin_hi']),
+                                                ptr(b['xin_lo']), st), "prep")
+        _capi.check(lib.dsen2_conv_head(ptr(b['xin_hi']), ptr(b['xin_lo']), ptr(self.w_fwd[0]), ptr(self.b_fwd[0]), n, P, P, F,
+                                        ptr(b['x_hi'][0]), ptr(b['x_lo']) if L == 0 else None,
+                                        ptr(b['x32']) if L > 0 else None, st), "head")
+        for l in range(L):
+            _capi.check(lib.dsen2_conv3x3(ptr(b['x_hi'][l]), ptr(self.w_fwd[1 + 2 * l]), ptr(self.b_fwd[1 + 2 * l]), n, P, P, F, F,
+                                          9, _capi.EPI_RELU, None, None, 0.0, ptr(b['t'][l]), None, None, None, 0, st), "conv1")
+            _capi.check(lib.dsen2_conv_res32(ptr(b['t'][l]), ptr(self.w_fwd[2 + 2 * l]), ptr(self.b_fwd[2 + 2 * l]), n, P, P, 0.1,
+                                             ptr(b['x32']), ptr(b['x_hi'][l + 1]), ptr(b['x_lo']) if l == L - 1 else None, st),
+                        "conv2")
+        _capi.check(lib.dsen2_conv_tail(ptr(b['x_hi'][L]), ptr(b['x_lo']), ptr(self.w_fwd[-1]), ptr(self.b_fwd[-1]),
+                                        ptr(b['xin_hi']), ptr(b['xin_lo']), self.ctot - self.cout, self.cout, n, P, P,
+                                        ptr(b['pred']), st), "tail")
+        return b['pred']
+
+    # ---- one optimisation step ----------------------------------------------------------------------------------
+    def train_step(self, xs, y, apply=True):
+        """xs: list of CUDA float32 (n,C_i,P,P); y: CUDA float32 (n,Cout,P,P).  Returns (loss, mse) device scalars
+        of THIS rank's batch (Keras reports the same quantities per batch).  ``apply=False`` stops after the gradient
+        (``self.grads``, flat fp32 in Keras weight order) for inspection."""
+        torch = self.torch
+        lib, ptr = _capi.lib(), _capi.ptr
+        n, P = int(xs[0].shape[0]), int(xs[0].shape[2])
+        F, L = self.F, self.L
+        b = self._buffers(n, P)
+        with torch.cuda.device(self.dev):
+            st = _capi.stream_ptr()
+            pred = self.forward(xs, b, n, P)
+            total = pred.numel()
+            S = self.GSCALE * total                     # loss scale: d(pred) = GSCALE * sign instead of sign / total
+            inv = 1.0 / S
+            self.sums.zero_()
+            self.grads.zero_()
+            self.gw_head.zero_()
+            self.gw_tail.zero_()
+            _capi.check(lib.dsen2_mae_grad(ptr(pred), ptr(y), total, self.GSCALE, ptr(b['dpred']), ptr(self.sums), st), "mae")
+            pa, pb, pt, pitch = b['pa'], b['pb'], b['pt'], b['pitch']
+            nl = 2 * L + 2
+
+            def planar(src, dst, mask=None, copies=1):
+                # copies=3: the X operand of the weight-gradient GEMM (three copies shifted by -1/0/+1 pixels)
+                _capi.check(lib.dsen2_nhwc_to_planar(ptr(src), ptr(mask), n, P, P, F, 128, copies, ptr(dst), st), "planar")
+
+            def wgrad(xp, dyp, ncols, scale, out):
+                _capi.check(lib.dsen2_wgrad(ptr(xp), ptr(dyp), n, P, P, ncols, scale, ptr(out), st), "wgrad")
+
+            def rowsum(src, rows, scale, out):
+                _capi.check(lib.dsen2_rowsum(ptr(src), rows, pitch, scale, ptr(out), st), "rowsum")
+
+            # ---- last layer: Conv2D(cout) (DSen2Net.py:35); the Add of the global skip passes the gradient through
+            _capi.check(lib.dsen2_nchw_to_planar(ptr(b['dpred']), self.cout, None, 0, None, 0, n, P, P, 16, 1, 1.0, ptr(pt), st),
+                        "dpred planar")
+            planar(b['x_hi'][L], pa, copies=3)
+            wgrad(pa, pt, 16, inv, self.gw_tail)
+            rowsum(pt, 16, inv, self.gb_tail)
+            _capi.check(lib.dsen2_nchw_to_nhwc_f16(ptr(b['dpred']), self.cout, n, P, P, F, ptr(b['dy_nhwc']), st), "dpred nhwc")
+            b['dx32'].zero_()
+            _capi.check(lib.dsen2_conv_res32(ptr(b['dy_nhwc']), ptr(self.w_bwd[-1]), ptr(self.zero_bias), n, P, P, 1.0,
+                                             ptr(b['dx32']), ptr(b['dx_hi']), None, st), "dgrad tail")
+            # ---- resBlocks, last to first (DSen2Net.py:9-15)
+            for l in range(L - 1, -1, -1):
+                i1, i2 = 1 + 2 * l, 2 + 2 * l
+                planar(b['dx_hi'], pb)                                           # d x_{l+1}
+                planar(b['t'][l], pa, copies=3)
+                wgrad(pa, pb, 128, 0.1 * inv, self.kernel(i2, self.grads))
+                rowsum(pb, 128, 0.1 * inv, self.bias(i2, self.grads))
+                _capi.check(lib.dsen2_conv_relu_bwd(ptr(b['dx_hi']), ptr(self.w_bwd[i2]), ptr(self.zero_bias), ptr(b['t'][l]),
+                                                    n, P, P, ptr(b['g2']), st), "dgrad conv2 + relu")
+                planar(b['g2'], pb)
+                planar(b['x_hi'][l], pa, copies=3)
+                wgrad(pa, pb, 128, inv, self.kernel(i1, self.grads))
+                rowsum(pb, 128, inv, self.bias(i1, self.grads))
+                _capi.check(lib.dsen2_conv_res32(ptr(b['g2']), ptr(self.w_bwd[i1]), ptr(self.zero_bias), n, P, P, 1.0,
+                                                 ptr(b['dx32']), ptr(b['dx_hi']), None, st), "dgrad conv1 + skip")
+            # ---- first layer: Conv2D(F, relu) on the concatenated inputs (DSen2Net.py:24-29)
+            planar(b['dx_hi'], pb, mask=b['x_hi'][0])
+            x2, c2 = (xs[2], self.model.in_channels[2]) if len(xs) == 3 else (None, 0)
+            _capi.check(lib.dsen2_nchw_to_planar(ptr(xs[0]), self.model.in_channels[0], ptr(xs[1]), self.model.in_channels[1],
+                                                 ptr(x2), c2, n, P, P, 128, 3, 1.0, ptr(pa), st), "input planar")
+            wgrad(pa, pb, 128, inv, self.gw_head)
+            rowsum(pb, 128, inv, self.bias(0, self.grads))
+            self.kernel(0, self.grads).view(9, self.ctot, F).copy_(self.gw_head[:, :self.ctot, :])
+            self.kernel(nl - 1, self.grads).view(9, F, self.cout).copy_(self.gw_tail[:, :, :self.cout])
+            self.bias(nl - 1, self.grads).copy_(self.gb_tail[:self.cout])
+            # ---- data-parallel exchange + Nadam
+            if apply:
+                world = allreduce_gradients(self.grads, self.group)
+                self.apply_gradients(1.0 / world)
+            loss = self.sums[0] / total
+            mse = self.sums[1] / total
+        return loss, mse
+
+    def apply_gradients(self, grad_mul=1.0):
+        lib, ptr, st = _capi.lib(), _capi.ptr, _capi.stream_ptr()
+        self.iterations += 1
+        s = nadam_schedule(self.iterations, self.m_schedule, self.opt)
+        self.m_schedule = s['sched_new']
+        o = self.opt
+        _capi.check(lib.dsen2_nadam_step(ptr(self.params), ptr(self.grads), ptr(self.m), ptr(self.v), self.params.numel(),
+                                         grad_mul, o.lr, o.beta_1, o.beta_2, o.epsilon, s['mu_t'], s['mu_next'], s['sched_new'],
+                                         s['sched_next'], s['bias2'], st), "nadam")
+        self.repack()
+
+    def launches_per_step(self):
+        L = self.L
+        fwd = 1 + 1 + 2 * L + 1
+        bwd = 1 + 4 + 2 + 1 + L * 10 + 4 + 3
+        return fwd + bwd + 1 + (2 * L + 2) * 2 + 1

@@ -196,6 +196,51 @@ int dsen2_s2model_forward(const float* const* d_x, const int* channels, int n_in
                           void* d_workspace, size_t workspace_bytes,
                           float* d_out_f32, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Training step -- training/supres_train.py:137-144 (Nadam, mean_absolute_error, mean_squared_error
+ * metric) and :218-230 (model.fit inner step), feature_size 128.  Forward = the inference kernels
+ * with per-layer activation buffers.  Backward data path = the same convolution kernels on
+ * dsen2_pack_dgrad_weights operands: dsen2_conv_relu_bwd (gradient through Conv2D + ReLU) and
+ * dsen2_conv_res32 with scale 1 (gradient through the Add of resBlock, accumulated on an fp32
+ * gradient trunk).  Weight gradients = dsen2_wgrad on planar zero-bordered fp16 operands.
+ * Gradients carry a power-of-two loss scale chosen by the host (see dsen2_b200/train.py).
+ * ------------------------------------------------------------------------------------------- */
+
+/* backward-data operand of a layer: packed[t][i][o] = scale * hwio[8-t][i][o], fp16, (9, rows_pad, k_pad) */
+int dsen2_pack_dgrad_weights(const float* d_hwio, int cin, int cout, int rows_pad, int k_pad, float scale,
+                             void* d_packed, void* stream);
+
+/* d_out = conv3x3(d_in, d_w) * [d_fwd_act > 0]   (NHWC fp16, 128 channels; d_bias must be zeros) */
+int dsen2_conv_relu_bwd(const void* d_in, const void* d_w, const float* d_bias, const void* d_fwd_act,
+                        int n, int H, int W, void* d_out, void* stream);
+
+/* planar zero-bordered fp16 operands of dsen2_wgrad: [copies][rows][pitch], k = (b*(H+2) + y+1)*Wp + x+1 with
+ * Wp = W+2 rounded up to 8; pitch = dsen2_planar_pitch(n, H, W) (k rounded up to 64, tail zero).  copies = 1 (dY) or
+ * 3 (X: copy d holds the tensor shifted by d-1 along k, so that every TMA coordinate stays 16-byte aligned).       */
+long long dsen2_planar_pitch(int n, int H, int W);
+int dsen2_nhwc_to_planar(const void* d_in_nhwc_f16, const void* d_mask_nhwc_f16 /* optional: keep where > 0 */,
+                         int n, int H, int W, int C, int rows, int copies, void* d_out, void* stream);
+int dsen2_nchw_to_planar(const float* d_x0, int c0, const float* d_x1, int c1, const float* d_x2, int c2,
+                         int n, int H, int W, int rows, int copies, float scale, void* d_out, void* stream);
+int dsen2_nchw_to_nhwc_f16(const float* d_in, int c, int n, int H, int W, int cpad, void* d_out, void* stream);
+
+/* d_dw (9, 128, n_cols) fp32 += scale * sum_px X[px + tap][ci] * dY[px][co]  (HWIO order; zero it first).
+ * X planar, 3 shifted copies of 128 rows; dY planar, 1 copy of n_cols = 16 or 128 rows.                */
+int dsen2_wgrad(const void* d_x_planar, const void* d_dy_planar, int n, int H, int W, int n_cols, float scale,
+                float* d_dw, void* stream);
+/* d_out[r] = scale * sum_k planar[r][k]  (bias gradients) */
+int dsen2_rowsum(const void* d_planar, int rows, long long kpitch, float scale, float* d_out, void* stream);
+
+/* mean_absolute_error: d_dpred = gscale * sign(pred - y); d_sums[0] += sum|pred-y|, d_sums[1] += sum (pred-y)^2 */
+int dsen2_mae_grad(const float* d_pred, const float* d_y, long long total, float gscale, float* d_dpred,
+                   double* d_sums, void* stream);
+
+/* Keras-2 Nadam update of a flat fp32 parameter vector (gradient multiplied by grad_mul first: 1/loss_scale/world).
+ * mu_t, mu_next, sched_new = prod(mu_1..mu_t), sched_next = sched_new*mu_next, bias2 = 1 - beta2^t (host).   */
+int dsen2_nadam_step(float* d_p, const float* d_g, float* d_m, float* d_v, long long total, float grad_mul,
+                     float lr, float beta1, float beta2, float eps, float mu_t, float mu_next,
+                     float sched_new, float sched_next, float bias2, void* stream);
+
 /* Debug / self-test hooks (used by tests only) */
 int dsen2_debug_force_v1(int on);   /* route 128-feature layers of dsen2_conv3x3 to the single-CTA kernel */
 int dsen2_debug_umma_rowshift(const void* d_a_f16 /*(rows,64)*/, int rows, const void* d_b_f16 /*(128,64)*/,

@@ -1,0 +1,194 @@
+"""Training step (supres_train.py:137-144,218-230) on the GPU against the fp32 CPU oracle (oracle/train_oracle.py,
+torch autograd + NAdam; parity unpinned by the reference -- Keras is not installable).
+
+Tolerances: gradients flow through fp16 operands (fp32 accumulation), so each gradient tensor is compared to the fp32
+autograd gradient relative to its own largest entry: max|g - g_ref| <= 2e-2 * max|g_ref|; building blocks are compared
+with float64 restatements on the SAME fp16-rounded operands (rtol/atol 1e-3 or tighter).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def env():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from dsen2_b200 import _capi
+    return torch, _capi, _capi.lib()
+
+
+def _planar(env, x_nhwc, mask=None, rows=128, copies=1):
+    torch, _capi, lib = env
+    n, H, W, C = x_nhwc.shape
+    pitch = int(lib.dsen2_planar_pitch(n, H, W))
+    out = torch.full((copies, rows, pitch), 9.0, dtype=torch.float16, device='cuda')
+    tx = torch.from_numpy(x_nhwc).cuda()
+    tm = torch.from_numpy(mask).cuda() if mask is not None else None
+    _capi.check(lib.dsen2_nhwc_to_planar(_capi.ptr(tx), _capi.ptr(tm), n, H, W, C, rows, copies, _capi.ptr(out),
+                                         _capi.stream_ptr()), 'planar')
+    torch.cuda.synchronize()
+    return out, pitch
+
+
+def _planar_ref(x_nhwc, rows, pitch, mask=None, copies=1):
+    n, H, W, C = x_nhwc.shape
+    wp = (W + 2 + 7) // 8 * 8
+    v = x_nhwc.astype(np.float32)
+    if mask is not None:
+        v = np.where(mask.astype(np.float32) > 0, v, 0)
+    p = np.zeros((rows, n, H + 2, wp), np.float32)
+    p[:C, :, 1:H + 1, 1:W + 1] = v.transpose(3, 0, 1, 2)
+    flat = np.zeros((rows, pitch + 2), np.float32)                 # one element of slack on both sides for the shifts
+    flat[:, 1:1 + n * (H + 2) * wp] = p.reshape(rows, -1)
+    shifts = (-1, 0, 1) if copies == 3 else (0,)
+    return np.stack([flat[:, 1 + d:1 + d + pitch] for d in shifts]).astype(np.float16)
+
+
+@pytest.mark.parametrize('shape', [(2, 32, 32, 128), (3, 16, 24, 128), (1, 8, 8, 64)])
+def test_planar_layout_bit_exact(env, shape):
+    rng = np.random.RandomState(shape[1])
+    x = rng.randn(*shape).astype(np.float16)
+    m = rng.randn(*shape).astype(np.float16)
+    got, pitch = _planar(env, x, copies=3)
+    assert np.array_equal(got.cpu().numpy().view(np.uint16), _planar_ref(x, 128, pitch, copies=3).view(np.uint16))
+    got, pitch = _planar(env, x, mask=m)
+    assert np.array_equal(got.cpu().numpy().view(np.uint16), _planar_ref(x, 128, pitch, mask=m).view(np.uint16))
+
+
+def _wgrad_ref(x_nhwc, dy_nhwc):
+    """dW[tap][ci][co] = sum_px X[px + off(tap)][ci] dY[px][co] with zero padding (float64)."""
+    n, H, W, Ci = x_nhwc.shape
+    xp = np.zeros((n, H + 2, W + 2, Ci), np.float64)
+    xp[:, 1:H + 1, 1:W + 1] = x_nhwc
+    dy = dy_nhwc.astype(np.float64)
+    out = np.zeros((9, Ci, dy.shape[-1]))
+    for t in range(9):
+        ky, kx = t // 3, t % 3
+        out[t] = np.einsum('nyxi,nyxo->io', xp[:, ky:ky + H, kx:kx + W], dy)
+    return out
+
+
+@pytest.mark.parametrize('shape,ncols', [((4, 32, 32), 128), ((128, 32, 32), 128), ((4, 32, 32), 16), ((3, 16, 24), 128)])
+def test_wgrad_gemm(env, shape, ncols):
+    torch, _capi, lib = env
+    n, H, W = shape
+    rng = np.random.RandomState(n + ncols)
+    x = rng.randn(n, H, W, 128).astype(np.float16)
+    dy = np.zeros((n, H, W, 128), np.float16)
+    dy[..., :ncols] = (rng.randn(n, H, W, ncols) * 0.1).astype(np.float16)
+    xp, _ = _planar(env, x, copies=3)
+    dyp, _ = _planar(env, dy[..., :ncols] if ncols == 128 else np.ascontiguousarray(dy[..., :16]), rows=ncols)
+    dw = torch.zeros((9, 128, ncols), device='cuda')
+    _capi.check(lib.dsen2_wgrad(_capi.ptr(xp), _capi.ptr(dyp), n, H, W, ncols, 0.5, _capi.ptr(dw), _capi.stream_ptr()), 'wgrad')
+    torch.cuda.synchronize()
+    ref = 0.5 * _wgrad_ref(x.astype(np.float64), dy[..., :ncols])
+    np.testing.assert_allclose(dw.cpu().numpy(), ref, rtol=1e-3, atol=1e-3 * np.abs(ref).max())
+
+
+def test_conv_relu_bwd_is_the_transposed_convolution(env):
+    torch, _capi, lib = env
+    import torch.nn.functional as F
+    n, H, W, C = 2, 32, 32, 128
+    rng = np.random.RandomState(3)
+    dy = (rng.randn(n, H, W, C) * 0.1).astype(np.float16)
+    act = np.maximum(rng.randn(n, H, W, C), 0).astype(np.float16)
+    lim = np.sqrt(6.0 / (9 * C))
+    w = rng.uniform(-lim, lim, size=(3, 3, C, C)).astype(np.float32)
+    tw = torch.empty((9, C, C), dtype=torch.float16, device='cuda')
+    _capi.check(lib.dsen2_pack_dgrad_weights(_capi.ptr(torch.from_numpy(w).cuda()), C, C, C, C, 0.1, _capi.ptr(tw),
+                                             _capi.stream_ptr()), 'pack dgrad')
+    zero = torch.zeros(C, device='cuda')
+    out = torch.zeros((n, H, W, C), dtype=torch.float16, device='cuda')
+    tdy, tact = torch.from_numpy(dy).cuda(), torch.from_numpy(act).cuda()      # keep both alive across the launch
+    _capi.check(lib.dsen2_conv_relu_bwd(_capi.ptr(tdy), _capi.ptr(tw), _capi.ptr(zero), _capi.ptr(tact), n, H, W,
+                                        _capi.ptr(out), _capi.stream_ptr()), 'relu bwd')
+    torch.cuda.synchronize()
+    # reference: gradient of y = conv(x, w) w.r.t. x, times 0.1, masked by the forward activation
+    wq = (np.float32(0.1) * w).astype(np.float16).astype(np.float64)           # operand as packed (scale folded, fp16)
+    wt = torch.from_numpy(wq).permute(3, 2, 0, 1).contiguous()                     # (Cout, Cin, 3, 3)
+    g = F.conv_transpose2d(torch.from_numpy(dy.astype(np.float64)).permute(0, 3, 1, 2), wt, padding=1)
+    ref = np.where(act.astype(np.float32) > 0, g.permute(0, 2, 3, 1).numpy(), 0)
+    np.testing.assert_allclose(out.cpu().numpy().astype(np.float64), ref, rtol=2e-3, atol=2e-3 * np.abs(ref).max())
+
+
+def _setup(L=2, n=4, P=32, run_60=False, seed=0):
+    from dsen2_b200.DSen2Net import s2model
+    chans = (4, 6, 2) if run_60 else (4, 6)
+    rng = np.random.RandomState(seed)
+    model = s2model(tuple((c, None, None) for c in chans), num_layers=L, feature_size=128, seed=7)
+    ws = model.get_weights()
+    for i in range(1, len(ws), 2):
+        ws[i] = (rng.randn(*ws[i].shape) * 0.05).astype(np.float32)
+    model.set_weights(ws)
+    xs = [(0.8 + 0.4 * rng.randn(n, c, P, P)).clip(0, 5).astype(np.float32) for c in chans]
+    y = (xs[-1] + 0.1 * rng.randn(*xs[-1].shape)).astype(np.float32)
+    return model, ws, xs, y
+
+
+@pytest.mark.parametrize('cfg', [dict(L=2, n=4, P=32), dict(L=6, n=8, P=32), dict(L=1, n=2, P=32, run_60=True),
+                                 dict(L=0, n=2, P=16)])
+def test_gradients_vs_autograd(env, cfg):
+    torch, _capi, lib = env
+    from dsen2_b200.train import Trainer
+    from oracle import train_oracle as to
+    model, ws, xs, y = _setup(**cfg)
+    tr = Trainer(model)
+    loss, mse = tr.train_step([torch.from_numpy(a).cuda() for a in xs], torch.from_numpy(y).cuda(), apply=False)
+    ref_loss, ref_mse, ref_g = to.loss_and_grads(xs, y, [(ws[2 * i], ws[2 * i + 1]) for i in range(len(ws) // 2)])
+    assert abs(float(loss) - ref_loss) <= 2e-3 * ref_loss + 1e-5
+    assert abs(float(mse) - ref_mse) <= 5e-3 * ref_mse + 1e-6
+    g = tr.grads.cpu().numpy()
+    worst = 0.0
+    for i, (gk, gb) in enumerate(ref_g):
+        for ref, (o0, o1) in ((gk, (tr.offsets[2 * i], tr.offsets[2 * i + 1])), (gb, (tr.offsets[2 * i + 1], tr.offsets[2 * i + 2]))):
+            got = g[o0:o1].reshape(ref.shape)
+            err = np.abs(got - ref).max() / (np.abs(ref).max() + 1e-12)
+            worst = max(worst, err)
+            assert err <= 2e-2, "layer %d %s: relative gradient error %.3e" % (i, ref.shape, err)
+    print('worst relative gradient error', worst)
+
+
+def test_nadam_steps_vs_oracle(env):
+    torch, _capi, lib = env
+    from dsen2_b200.train import Nadam, Trainer
+    from oracle import train_oracle as to
+    model, ws, xs, y = _setup(L=2, n=4, P=32)
+    lr = 1e-3
+    tr = Trainer(model, Nadam(lr=lr))
+    dx, dy = [torch.from_numpy(a).cuda() for a in xs], torch.from_numpy(y).cuda()
+    losses = [float(tr.train_step(dx, dy)[0]) for _ in range(4)]
+    ref_losses, ref_w = to.train_steps([(xs, y)] * 4, [(ws[2 * i], ws[2 * i + 1]) for i in range(len(ws) // 2)], lr=lr)
+    np.testing.assert_allclose(losses, ref_losses, rtol=5e-3)
+    assert losses[-1] < losses[0]
+    got = tr.get_weights()
+    # Nadam steps are ~lr per element and sign-like (an element whose tiny gradient flips sign under fp16 rounding moves
+    # the other way), so compare the UPDATES statistically, in units of lr * steps
+    d = np.concatenate([np.abs((got[2 * i + j] - ws[2 * i + j]) - (kb[j] - ws[2 * i + j])).ravel()
+                        for i, kb in enumerate(ref_w) for j in (0, 1)]) / (lr * 4)
+    print('update error / (lr*steps): median %.4f  p99 %.4f  max %.4f' % (np.median(d), np.percentile(d, 99), d.max()))
+    assert np.median(d) < 0.02 and np.mean(d > 0.25) < 0.02
+    # the exact Nadam arithmetic: feed the oracle's gradient through the kernel
+    ref_loss, _, ref_g = to.loss_and_grads(xs, y, [(ws[2 * i], ws[2 * i + 1]) for i in range(len(ws) // 2)])
+    tr2 = Trainer(model, Nadam(lr=lr))
+    flat_g = np.concatenate([a.ravel() for kb in ref_g for a in kb]).astype(np.float32)
+    p0 = tr2.params.cpu().numpy().astype(np.float64)
+    m = np.zeros_like(p0); v = np.zeros_like(p0); ms = 1.0
+    for t in range(1, 4):
+        tr2.grads.copy_(torch.from_numpy(flat_g).cuda())
+        tr2.apply_gradients(1.0)
+        p0, m, v, ms = to.nadam_reference(p0, flat_g.astype(np.float64), m, v, t, ms, lr=lr)
+        np.testing.assert_allclose(tr2.params.cpu().numpy(), p0, rtol=0, atol=5e-6)
+
+
+def test_keras_like_compile_fit(env):
+    model, ws, xs, y = _setup(L=1, n=8, P=32)
+    with pytest.raises(RuntimeError):
+        model.train_on_batch(xs, y)
+    model.compile(optimizer='nadam', loss='mean_absolute_error', metrics=['mean_squared_error'])
+    hist = model.fit(xs, y, batch_size=4, epochs=3, shuffle=True, seed=0)
+    assert len(hist['loss']) == 3 and hist['loss'][-1] < hist['loss'][0]
+    assert any(np.abs(a - b).max() > 0 for a, b in zip(model.get_weights(), ws))   # synced back into the model
+    pred = model.predict(xs)                       # ... and the inference path runs on the trained weights
+    assert abs(np.abs(pred - y).mean() - model.train_on_batch(xs, y)[0]) < 5e-3

@@ -344,6 +344,91 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------- #
+# config 5: data-parallel training step (supres_train.py:137-144,218-230), batch 128 per GPU of 32x32 patches
+# ---------------------------------------------------------------------------------------------- #
+def run_train(args):
+    import torch
+    import torch.distributed as dist
+    from dsen2_b200.DSen2Net import s2model
+    from dsen2_b200.train import Nadam, Trainer
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    n, P = args.train_batch, 32
+    model = s2model(((4, None, None), (6, None, None)), num_layers=6, feature_size=128, seed=0)
+    tr = Trainer(model, Nadam(lr=1e-4), device=dev)
+    g = torch.Generator().manual_seed(1234 + rank)
+    host = [torch.rand((n, c, P, P), generator=g).mul_(2.5).pin_memory() for c in (4, 6, 6)]
+    devb = [torch.empty((n, c, P, P), device=dev) for c in (4, 6, 6)]
+    for d, h in zip(devb, host):
+        d.copy_(h)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn):
+        for _ in range(args.warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) / args.steps
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    losses = []
+
+    def step_dev():
+        tr.train_step(devb[:2], devb[2])
+
+    def step_e2e():
+        for d, h in zip(devb, host):
+            d.copy_(h, non_blocking=True)
+        loss, _ = tr.train_step(devb[:2], devb[2])
+        losses.append(float(loss))                                      # device -> host read of the step's result
+
+    ms = timed(step_dev)
+    ms_e2e = timed(step_e2e)
+    flop = 3.0 * FLOP_PER_PIXEL[('dsen2', 20)] * n * P * P               # forward + backward-data + weight-gradient
+    if rank == 0:
+        pk = peaks()
+        line = {"metric": "train_samples_per_s", "value": world * n / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "fp16 operands / gradients (loss-scaled), fp32 accumulate, fp32 master weights + Nadam",
+                "data": "synthetic",
+                "config": {"workload": "DSen2 (6x128) training step, %d patches 32x32 per GPU, MAE + Keras-2 Nadam, "
+                                       "NCCL all-reduce of 1.79 M fp32 gradients" % n, "batch_per_gpu": n,
+                           "l2": "working set per step ~1.3 GB > L2"},
+                "e2e": {"value": world * n / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e,
+                        "h2d_bytes_per_step": world * sum(h.numel() * 4 for h in host), "d2h_bytes_per_step": world * 8},
+                "gpu_launches": tr.launches_per_step() * args.steps,
+                "roofline": {"bound": "tensor", "kernel": "whole step (conv_pair_kernel fwd/dgrad + wgrad_kernel)",
+                             "achieved": flop / ms / 1e9, "peak": pk['tf_burst'], "unit": "TFLOP/s",
+                             "frac": flop / ms / 1e9 / pk['tf_burst'], "traffic": None,
+                             "peak_source": pk['source'] + ", burst figure (millisecond-scale step)"},
+                "last_loss": losses[-1] if losses else None}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -355,8 +440,15 @@ def main():
     ap.add_argument('--path', type=int, default=20, choices=[20, 60], help='20 m -> 10 m (DSen2_20) or 60 m -> 10 m (DSen2_60)')
     ap.add_argument('--batch', type=int, default=64, help='patches per device batch')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--workload', default='tile', choices=['tile', 'train'],
+                    help="'tile' = the headline inference benchmark; 'train' = BASELINE.json configs[4] (training step)")
+    ap.add_argument('--train-batch', type=int, default=128)
     args = ap.parse_args()
-    if args.impl == 'reference':
+    if args.workload == 'train' and args.impl == 'ours':
+        if args.steps == 3:
+            args.steps, args.warmup = 50, 10
+        run_train(args)
+    elif args.impl == 'reference':
         run_reference(args)
     else:
         run_ours(args)

@@ -316,6 +316,30 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
   return d;
 }
 
+// MN-major operand, 128-byte swizzle: rows of 128 B hold 64 consecutive M (or N) elements of ONE k; 8-row groups
+// (8 consecutive k) are `sbo_bytes` apart, blocks of 64 further M/N elements are `lbo_bytes` apart
+// (cute::UMMA canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor with both operands MN-major (a_major = b_major = 1)
+__host__ __device__ constexpr uint32_t umma_idesc_f16_mn(int M, int N) {
+  return (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// smem -> global bulk reduction (fp32 add), tracked by the bulk async-group of the issuing thread
+__device__ __forceinline__ void bulk_reduce_add_f32(float* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gdst),
+               "r"(smem_u32(ssrc)), "r"(bytes)
+               : "memory");
+}
+
 // kind::f16 instruction descriptor: fp16 A/B (K-major), fp32 accumulate, M x N.
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
   return (1u << 4)                      // c_format = F32

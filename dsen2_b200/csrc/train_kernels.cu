@@ -87,16 +87,49 @@ __global__ void nchw_to_planar_kernel(const float* __restrict__ x0, int c0, cons
   }
 }
 
-// NCHW fp32 (n,c,H,W) -> NHWC fp16 (n,H,W,cpad), channels >= c zero
-__global__ void nchw_to_nhwc_f16_kernel(const float* __restrict__ in, int c, int n, int H, int W, int cpad, long long total,
+// up to three NCHW fp32 inputs (n,c_i,H,W) concatenated along channels -> NHWC fp16 (n,H,W,cpad), other channels zero
+__global__ void nchw_to_nhwc_f16_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x1, int c1,
+                                        const float* __restrict__ x2, int c2, int n, int H, int W, int cpad, long long total,
                                         __half* __restrict__ out) {
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int ch = (int)(idx % cpad);
     const long long pix = idx / cpad;
     const int x = (int)(pix % W), y = (int)((pix / W) % H), b = (int)(pix / ((long long)W * H));
-    out[idx] = __float2half_rn(ch < c ? in[(((long long)b * c + ch) * H + y) * W + x] : 0.f);
+    float v = 0.f;
+    if (ch < c0) v = x0[(((long long)b * c0 + ch) * H + y) * W + x];
+    else if (ch < c0 + c1) v = x1[(((long long)b * c1 + (ch - c0)) * H + y) * W + x];
+    else if (ch < c0 + c1 + c2) v = x2[(((long long)b * c2 + (ch - c0 - c1)) * H + y) * W + x];
+    out[idx] = __float2half_rn(v);
   }
+}
+
+// out = in where the forward activation is positive, else 0 (ReLU backward on NHWC fp16 tensors)
+__global__ void relu_mask_kernel(const uint4* __restrict__ in, const uint4* __restrict__ act, long long total16,
+                                 uint4* __restrict__ out) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total16;
+       idx += (long long)gridDim.x * blockDim.x) {
+    uint4 v = in[idx];
+    const uint4 a = act[idx];
+    __half* vh = reinterpret_cast<__half*>(&v);
+    const __half* ah = reinterpret_cast<const __half*>(&a);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (!(__half2float(ah[j]) > 0.f)) vh[j] = __float2half_rn(0.f);
+    out[idx] = v;
+  }
+}
+
+// out[c] += scale * sum_pixels in[pixel][c]   (bias gradients from an NHWC fp16 gradient tensor, C = 128)
+__global__ void colsum_nhwc_kernel(const __half* __restrict__ in, long long npix, float scale, float* __restrict__ out) {
+  // block: 256 threads = 2 pixel lanes x 128 channels; grid-stride over pixels
+  const int c = threadIdx.x & 127, lane_p = threadIdx.x >> 7;
+  float acc = 0.f;
+  for (long long p = (long long)blockIdx.x * 2 + lane_p; p < npix; p += (long long)gridDim.x * 2) acc += __half2float(in[p * 128 + c]);
+  __shared__ float red[256];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x < 128) atomicAdd(out + c, (red[threadIdx.x] + red[threadIdx.x + 128]) * scale);
 }
 
 // out[r] = scale * sum_k in[r][k]   (bias gradients: the planar gradient tensor has zero borders)
@@ -173,6 +206,27 @@ __global__ void nadam_kernel(float* __restrict__ p, const float* __restrict__ g,
   }
 }
 
+// same update with the step-dependent scalars read from device memory, so that a captured CUDA graph of the whole
+// training step can be replayed: hp = {grad_mul, lr, beta1, beta2, eps, mu_t, mu_next, sched_new, sched_next, bias2}
+__global__ void nadam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                 float* __restrict__ v, long long total, const float* __restrict__ hp) {
+  const float gmul = hp[0], lr = hp[1], beta1 = hp[2], beta2 = hp[3], eps = hp[4], mu_t = hp[5], mu_next = hp[6],
+              sched_new = hp[7], sched_next = hp[8], bias2 = hp[9];
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const float gr = g[idx] * gmul;
+    const float g_prime = gr / (1.f - sched_new);
+    const float m_t = beta1 * m[idx] + (1.f - beta1) * gr;
+    const float m_prime = m_t / (1.f - sched_next);
+    const float v_t = beta2 * v[idx] + (1.f - beta2) * gr * gr;
+    const float v_prime = v_t / bias2;
+    const float m_bar = (1.f - mu_t) * g_prime + mu_next * m_prime;
+    p[idx] = p[idx] - lr * m_bar / (sqrtf(v_prime) + eps);
+    m[idx] = m_t;
+    v[idx] = v_t;
+  }
+}
+
 // dgrad weights: the backward-data convolution is a forward convolution of dY with the taps flipped and the channel
 // roles swapped: packed[t][i][o] = scale * hwio[8 - t][i][o]   (rows = former input channels, k = former outputs)
 __global__ void pack_dgrad_weights_kernel(const float* __restrict__ hwio, int cin, int cout, int rows_pad, int k_pad,
@@ -186,6 +240,16 @@ __global__ void pack_dgrad_weights_kernel(const float* __restrict__ hwio, int ci
     if (i < cin && o < cout) v = scale * hwio[((long long)(8 - t) * cin + i) * cout + o];
     out[idx] = __float2half_rn(v);
   }
+}
+
+struct TileXY3 { int b, ty, tx; };
+__device__ __forceinline__ TileXY3 decode_tile3(uint32_t tile, uint32_t tiles_x, uint32_t tiles_y) {
+  const uint32_t row = tile / tiles_x;
+  TileXY3 t;
+  t.tx = (int)(tile - row * tiles_x);
+  t.b = (int)(row / tiles_y);
+  t.ty = (int)(row - (uint32_t)t.b * tiles_y);
+  return t;
 }
 
 // ------------------------------------------------------------------------------------------ //
@@ -293,9 +357,167 @@ static int launch_wgrad(const CUtensorMap& tx, const CUtensorMap& ty, int kblock
   return check_launch("wgrad_kernel");
 }
 
+// ------------------------------------------------------------------------------------------ //
+// weight gradient straight from the NHWC tensors (no layout change): MN-major operands
+// ------------------------------------------------------------------------------------------ //
+// dW[tap][ci][co] = sum_px X[px + off(tap)][ci] * dY[px][co]: the reduction runs over PIXELS, and in NHWC a pixel
+// is a 128-byte row of 64 channels -- exactly an MN-major (M = ci or N = co contiguous, K = pixel) UMMA operand.
+// So the TMA tiles of the forward convolution serve as they are: X as the halo box of a 16x8-pixel tile (the tap
+// offset is a shift of the descriptor start, zero padding is TMA out-of-bounds fill), dY as the plain tile.
+// One CTA owns ONE vertical tap (three accumulators = its three horizontal taps, 384 TMEM columns) and a slice
+// of the tiles; at the end the accumulators go TMEM -> smem -> cp.reduce.async.bulk (fp32 add) into dW.
+static constexpr int kWdThreads = 192;          // warp 0 TMA, warp 1 MMA + TMEM, warps 2-5 drain
+static constexpr int kWdXBox = 16 * 10 * 128;   // 16 rows x 10 pixels x 64 channels
+static constexpr int kWdYBox = 16 * 8 * 128;
+static constexpr int kWdStage = 2 * kWdXBox + 2 * kWdYBox;   // both channel halves of X and of dY: 73,728 B
+static constexpr int kWdStages = 3;
+
+__global__ void __launch_bounds__(kWdThreads, 1)
+wgrad_direct_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_dy, int tiles_x,
+                    int tiles_y, int num_tiles, int tiles_per_split, float scale, float* __restrict__ dw) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kWdStages * kWdStage);
+  uint64_t* empty = full + kWdStages;
+  uint64_t* done = empty + kWdStages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int dy = blockIdx.y;                                   // vertical tap 0..2
+  const int t0 = blockIdx.x * tiles_per_split;
+  const int t1 = min(num_tiles, t0 + tiles_per_split);
+  const int nt = t1 - t0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_dy);
+    for (int i = 0; i < kWdStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < nt; ++i) {
+        const TileXY3 t = decode_tile3((uint32_t)(t0 + i), (uint32_t)tiles_x, (uint32_t)tiles_y);
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* s = smem + stage * kWdStage;
+        mbar_expect_tx(&full[stage], kWdStage);
+        tma_load_4d(s, &tm_x, &full[stage], 0, t.tx * 8 - 1, t.ty * 16 + dy - 1, t.b);
+        tma_load_4d(s + kWdXBox, &tm_x, &full[stage], 64, t.tx * 8 - 1, t.ty * 16 + dy - 1, t.b);
+        tma_load_4d(s + 2 * kWdXBox, &tm_dy, &full[stage], 0, t.tx * 8, t.ty * 16, t.b);
+        tma_load_4d(s + 2 * kWdXBox + kWdYBox, &tm_dy, &full[stage], 64, t.tx * 8, t.ty * 16, t.b);
+        if (++stage == kWdStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_f16_mn(128, 128);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < nt; ++i) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t sx = smem_u32(smem + stage * kWdStage), sy = sx + 2 * kWdXBox;
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)            // 16 pixels (two tile rows) per MMA
+            umma_f16_ss(tmem_base + dx * 128, umma_desc_mn_sw128(sx + dx * 128 + j * 2 * 1280, kWdXBox, 1280),
+                        umma_desc_mn_sw128(sy + j * 2 * 1024, kWdYBox, 1024), idesc, (uint32_t)((i | j) != 0));
+        }
+        umma_commit(&empty[stage]);
+        if (i == nt - 1) umma_commit(done);
+        if (++stage == kWdStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // drain: accumulator dx (128 ci x 128 co fp32) -> smem (row-major, 64 KB, reusing the pipeline stages) -> bulk add
+    const int wq = warp & 3;
+    const int row = wq * 32 + lane;              // ci
+    mbar_wait(done, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int dx = 0; dx < 3; ++dx) {
+      float* sacc = reinterpret_cast<float*>(smem + dx * 65536);
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(wq * 32) << 16) + dx * 128 + c0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          // 16-byte chunk index rotated by the row: conflict-free smem stores; the bulk copy below is per row
+          const int ch = ((c0 + j) >> 2);
+          *reinterpret_cast<float4*>(sacc + row * 128 + (((ch + row) & 31) << 2)) =
+              make_float4(__uint_as_float(r[j]) * scale, __uint_as_float(r[j + 1]) * scale, __uint_as_float(r[j + 2]) * scale,
+                          __uint_as_float(r[j + 3]) * scale);
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    // each thread adds its own row of the three accumulators; the rotation is undone by splitting the row in two runs
+    for (int dx = 0; dx < 3; ++dx) {
+      const float* srow = reinterpret_cast<const float*>(smem + dx * 65536) + row * 128;
+      float* grow = dw + ((long long)(dy * 3 + dx) * 128 + row) * 128;
+      const int rot = (row & 31) << 2;           // element offset where column 0 of this row sits
+      bulk_reduce_add_f32(grow, srow + rot, (uint32_t)((128 - rot) * 4));
+      if (rot) bulk_reduce_add_f32(grow + (128 - rot), srow, (uint32_t)(rot * 4));
+    }
+    tma_store_commit();
+    tma_store_wait_all<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
 }  // namespace dsen2
 
 using namespace dsen2;
+
+extern "C" int dsen2_wgrad_nhwc(const void* d_x, const void* d_dy, int n, int H, int W, float scale, float* d_dw,
+                                void* stream) {
+  DSEN2_REQUIRE(d_x && d_dy && d_dw, DSEN2_E_BADARG, "dsen2_wgrad_nhwc: null pointer");
+  DSEN2_REQUIRE(n > 0 && H > 0 && W > 0, DSEN2_E_BADARG, "dsen2_wgrad_nhwc: bad shape");
+  DSEN2_REQUIRE(((uintptr_t)d_x % 16) == 0 && ((uintptr_t)d_dy % 16) == 0 && ((uintptr_t)d_dw % 16) == 0, DSEN2_E_ALIGN,
+                "dsen2_wgrad_nhwc: pointers must be 16-byte aligned");
+  int sms = 0;
+  int rc = device_sm_count_and_check(&sms);
+  if (rc) return rc;
+  const int tiles_x = ceil_div(W, 8), tiles_y = ceil_div(H, 16);
+  const long long tiles = (long long)n * tiles_x * tiles_y;
+  DSEN2_REQUIRE(tiles < (1LL << 30), DSEN2_E_BADARG, "dsen2_wgrad_nhwc: batch too large");
+  int splits = sms / 3;
+  if (splits > tiles) splits = (int)tiles;
+  const int per = (int)((tiles + splits - 1) / splits);
+  splits = (int)((tiles + per - 1) / per);
+  CUtensorMap tx, ty;
+  const uint64_t dims[4] = {128, (uint64_t)W, (uint64_t)H, (uint64_t)n};
+  const uint32_t bx[4] = {64, 10, 16, 1};
+  rc = make_tmap_f16(&tx, d_x, 4, dims, bx);
+  if (rc) return rc;
+  const uint32_t by[4] = {64, 8, 16, 1};
+  rc = make_tmap_f16(&ty, d_dy, 4, dims, by);
+  if (rc) return rc;
+  constexpr int SMEM = kWdStages * kWdStage + 256 + 1024;
+  static_assert(kWdStages * kWdStage >= 3 * 65536, "the drain reuses the pipeline stages for three 64 KB accumulators");
+  static bool configured = false;
+  if (!configured) {
+    DSEN2_CUDA(cudaFuncSetAttribute(wgrad_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    configured = true;
+  }
+  wgrad_direct_kernel<<<dim3(splits, 3), kWdThreads, SMEM, (cudaStream_t)stream>>>(tx, ty, tiles_x, tiles_y, (int)tiles, per,
+                                                                                 scale, d_dw);
+  return check_launch("wgrad_direct_kernel");
+}
 
 extern "C" long long dsen2_planar_pitch(int n, int H, int W) {
   const long long k = (long long)n * (H + 2) * planar_wp(W);
@@ -325,11 +547,31 @@ extern "C" int dsen2_nchw_to_planar(const float* d_x0, int c0, const float* d_x1
   return check_launch("nchw_to_planar");
 }
 
-extern "C" int dsen2_nchw_to_nhwc_f16(const float* d_in, int c, int n, int H, int W, int cpad, void* d_out, void* stream) {
-  DSEN2_REQUIRE(d_in && d_out && c > 0 && cpad >= c && n > 0 && H > 0 && W > 0, DSEN2_E_BADARG, "dsen2_nchw_to_nhwc_f16: bad arguments");
+extern "C" int dsen2_nchw_to_nhwc_f16(const float* d_x0, int c0, const float* d_x1, int c1, const float* d_x2, int c2,
+                                      int n, int H, int W, int cpad, void* d_out, void* stream) {
+  DSEN2_REQUIRE(d_x0 && d_out && (c1 == 0 || d_x1) && (c2 == 0 || d_x2) && c0 > 0 && c1 >= 0 && c2 >= 0 &&
+                    cpad >= c0 + c1 + c2 && n > 0 && H > 0 && W > 0,
+                DSEN2_E_BADARG, "dsen2_nchw_to_nhwc_f16: bad arguments");
   const long long total = (long long)n * H * W * cpad;
-  nchw_to_nhwc_f16_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d_in, c, n, H, W, cpad, total, (__half*)d_out);
+  nchw_to_nhwc_f16_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d_x0, c0, d_x1, c1, d_x2, c2, n, H, W, cpad,
+                                                                                  total, (__half*)d_out);
   return check_launch("nchw_to_nhwc_f16");
+}
+
+extern "C" int dsen2_relu_mask(const void* d_in, const void* d_act, long long total, void* d_out, void* stream) {
+  DSEN2_REQUIRE(d_in && d_act && d_out && total > 0 && total % 8 == 0, DSEN2_E_BADARG, "dsen2_relu_mask: bad arguments");
+  relu_mask_kernel<<<grid_for(total / 8, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)d_in, (const uint4*)d_act, total / 8,
+                                                                              (uint4*)d_out);
+  return check_launch("relu_mask");
+}
+
+extern "C" int dsen2_colsum_nhwc(const void* d_in, long long npix, float scale, float* d_out, void* stream) {
+  DSEN2_REQUIRE(d_in && d_out && npix > 0, DSEN2_E_BADARG, "dsen2_colsum_nhwc: bad arguments");
+  long long blocks = (npix + 1) / 2;
+  const long long cap = (long long)sm_count() * 4;
+  if (blocks > cap) blocks = cap;
+  colsum_nhwc_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __half*)d_in, npix, scale, d_out);
+  return check_launch("colsum_nhwc");
 }
 
 extern "C" int dsen2_rowsum(const void* d_planar, int rows, long long kpitch, float scale, float* d_out, void* stream) {
@@ -352,6 +594,13 @@ extern "C" int dsen2_nadam_step(float* d_p, const float* d_g, float* d_m, float*
   nadam_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d_p, d_g, d_m, d_v, total, grad_mul, lr, beta1, beta2,
                                                                       eps, mu_t, mu_next, sched_new, sched_next, bias2);
   return check_launch("nadam_step");
+}
+
+extern "C" int dsen2_nadam_step_dev(float* d_p, const float* d_g, float* d_m, float* d_v, long long total,
+                                    const float* d_hp, void* stream) {
+  DSEN2_REQUIRE(d_p && d_g && d_m && d_v && d_hp && total > 0, DSEN2_E_BADARG, "dsen2_nadam_step_dev: bad arguments");
+  nadam_dev_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d_p, d_g, d_m, d_v, total, d_hp);
+  return check_launch("nadam_step_dev");
 }
 
 extern "C" int dsen2_pack_dgrad_weights(const float* d_hwio, int cin, int cout, int rows_pad, int k_pad, float scale,

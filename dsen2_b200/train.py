@@ -13,6 +13,7 @@ power-of-two loss scale so that the MAE gradient sign(pred-y)/N enters the fp16 
 Master weights, gradients and the Nadam moments are fp32.  DSen2 (feature_size 128) only.
 """
 import math
+import os
 
 import numpy as np
 
@@ -73,14 +74,20 @@ class Trainer:
         self.sums = torch.zeros(2, dtype=torch.float64, device=self.dev)
         self.zero_bias = torch.zeros(128, dtype=torch.float32, device=self.dev)
         self._bufs = {}
+        # replay the whole step as one CUDA graph from the third call of a shape on (DSEN2_TRAIN_NO_GRAPH=1: eager, for ncu)
+        self.use_graph = not os.environ.get('DSEN2_TRAIN_NO_GRAPH')
+        self._graphs, self._calls = {}, {}
+        self.hp_host = torch.zeros(10, dtype=torch.float32).pin_memory()
+        self.hp_dev = torch.zeros(10, dtype=torch.float32, device=self.dev)
+        self.loss_out = torch.zeros(2, dtype=torch.float64, device=self.dev)
         f16 = lambda *s: torch.empty(s, dtype=torch.float16, device=self.dev)
         F, L = self.F, self.L
         self.w_fwd = [f16(3, 2 * F, 64)] + [f16(9, F, F) for _ in range(2 * L)] + [f16(9, 32, F)]
         self.w_bwd = [None] + [f16(9, F, F) for _ in range(2 * L)] + [f16(9, F, F)]
         self.b_fwd = [torch.zeros(max(c, 16), dtype=torch.float32, device=self.dev) for _, c in shapes]
         self.gw_head = torch.zeros((9, 128, 128), dtype=torch.float32, device=self.dev)
-        self.gw_tail = torch.zeros((9, 128, 16), dtype=torch.float32, device=self.dev)
-        self.gb_tail = torch.zeros(16, dtype=torch.float32, device=self.dev)
+        self.gw_tail = torch.zeros((9, 128, 128), dtype=torch.float32, device=self.dev)
+        self.gb_tail = torch.zeros(128, dtype=torch.float32, device=self.dev)
         self.repack()
 
     # ---- parameter views -------------------------------------------------------------------------------------
@@ -128,7 +135,6 @@ class Trainer:
         if b is None:
             torch, F, L = self.torch, self.F, self.L
             f16 = lambda *s: torch.empty(s, dtype=torch.float16, device=self.dev)
-            pitch = int(_capi.lib().dsen2_planar_pitch(n, P, P))
             b = dict(xin_hi=f16(n, P, P, 64), xin_lo=f16(n, P, P, 64), x_hi=[f16(n, P, P, F) for _ in range(L + 1)],
                      t=[f16(n, P, P, F) for _ in range(L)], x_lo=f16(n, P, P, F),
                      x32=torch.empty((n, P, (P + 7) // 8, F // 4, 8, 4), dtype=torch.float32, device=self.dev),
@@ -136,8 +142,8 @@ class Trainer:
                      dx_hi=f16(n, P, P, F), g2=f16(n, P, P, F), dy_nhwc=f16(n, P, P, F),
                      pred=torch.empty((n, self.cout, P, P), dtype=torch.float32, device=self.dev),
                      dpred=torch.empty((n, self.cout, P, P), dtype=torch.float32, device=self.dev),
-                     pa=f16(3, 128, pitch), pb=f16(128, pitch), pt=f16(16, pitch), pitch=pitch)
-            self._bufs = {key: b}
+                     )
+            self._bufs[key] = b          # kept for the lifetime of the trainer: captured graphs point into them
         return b
 
     # ---- forward ---------------------------------------------------------------------------------------------
@@ -163,6 +169,55 @@ class Trainer:
 
     # ---- one optimisation step ----------------------------------------------------------------------------------
     def train_step(self, xs, y, apply=True):
+        """One optimisation step (see ``_step_body``).  The first call of a batch shape runs eagerly (it also performs the
+        one-time kernel attribute set-up), the second is captured into a CUDA graph (~120 launches, an NCCL all-reduce
+        and the repacking of the weights), later calls copy the batch into the graph's static buffers, upload the ten
+        step-dependent Nadam scalars and replay it."""
+        torch = self.torch
+        n, P = int(xs[0].shape[0]), int(xs[0].shape[2])
+        key = (n, P, len(xs))
+        if not (apply and self.use_graph):
+            return self._step_body(xs, y, apply)
+        calls = self._calls.get(key, 0)
+        self._calls[key] = calls + 1
+        if calls == 0:
+            return self._step_body(xs, y, True)
+        b = self._buffers(n, P)
+        if 'in_x' not in b:
+            b['in_x'] = [torch.empty_like(x) for x in xs]
+            b['in_y'] = torch.empty_like(y)
+        with torch.cuda.device(self.dev):
+            for d, s_ in zip(b['in_x'], xs):
+                d.copy_(s_, non_blocking=True)
+            b['in_y'].copy_(y, non_blocking=True)
+            self._advance_schedule(1.0 / self._world())
+            if key not in self._graphs:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    loss, mse = self._step_body(b['in_x'], b['in_y'], True, dev_hp=True)
+                    self.loss_out[0].copy_(loss)
+                    self.loss_out[1].copy_(mse)
+                self._graphs[key] = g
+            self._graphs[key].replay()
+            return self.loss_out[0].clone(), self.loss_out[1].clone()
+
+    def _world(self):
+        import torch.distributed as dist
+        return dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
+
+    def _advance_schedule(self, grad_mul):
+        """Host side of one Nadam iteration: advance t and the momentum schedule, publish the scalars to the device."""
+        self.iterations += 1
+        s = nadam_schedule(self.iterations, self.m_schedule, self.opt)
+        self.m_schedule = s['sched_new']
+        o = self.opt
+        vals = [grad_mul, o.lr, o.beta_1, o.beta_2, o.epsilon, s['mu_t'], s['mu_next'], s['sched_new'], s['sched_next'], s['bias2']]
+        for i, v_ in enumerate(vals):
+            self.hp_host[i] = float(v_)
+        self.hp_dev.copy_(self.hp_host, non_blocking=True)
+        return s
+
+    def _step_body(self, xs, y, apply=True, dev_hp=False):
         """xs: list of CUDA float32 (n,C_i,P,P); y: CUDA float32 (n,Cout,P,P).  Returns (loss, mse) device scalars
         of THIS rank's batch (Keras reports the same quantities per batch).  ``apply=False`` stops after the gradient
         (``self.grads``, flat fp32 in Keras weight order) for inspection."""
@@ -181,59 +236,55 @@ class Trainer:
             self.grads.zero_()
             self.gw_head.zero_()
             self.gw_tail.zero_()
+            self.gb_tail.zero_()
             _capi.check(lib.dsen2_mae_grad(ptr(pred), ptr(y), total, self.GSCALE, ptr(b['dpred']), ptr(self.sums), st), "mae")
-            pa, pb, pt, pitch = b['pa'], b['pb'], b['pt'], b['pitch']
             nl = 2 * L + 2
+            npix = n * P * P
 
-            def planar(src, dst, mask=None, copies=1):
-                # copies=3: the X operand of the weight-gradient GEMM (three copies shifted by -1/0/+1 pixels)
-                _capi.check(lib.dsen2_nhwc_to_planar(ptr(src), ptr(mask), n, P, P, F, 128, copies, ptr(dst), st), "planar")
+            def wgrad(x_nhwc, dy_nhwc, scale, out):     # out (9,128,128) fp32 += scale * sum_px X[px+tap] (x) dY[px]
+                _capi.check(lib.dsen2_wgrad_nhwc(ptr(x_nhwc), ptr(dy_nhwc), n, P, P, scale, ptr(out), st), "wgrad")
 
-            def wgrad(xp, dyp, ncols, scale, out):
-                _capi.check(lib.dsen2_wgrad(ptr(xp), ptr(dyp), n, P, P, ncols, scale, ptr(out), st), "wgrad")
-
-            def rowsum(src, rows, scale, out):
-                _capi.check(lib.dsen2_rowsum(ptr(src), rows, pitch, scale, ptr(out), st), "rowsum")
+            def bgrad(dy_nhwc, scale, out):             # out (128,) fp32 += scale * sum_px dY[px]
+                _capi.check(lib.dsen2_colsum_nhwc(ptr(dy_nhwc), npix, scale, ptr(out), st), "bias grad")
 
             # ---- last layer: Conv2D(cout) (DSen2Net.py:35); the Add of the global skip passes the gradient through
-            _capi.check(lib.dsen2_nchw_to_planar(ptr(b['dpred']), self.cout, None, 0, None, 0, n, P, P, 16, 1, 1.0, ptr(pt), st),
-                        "dpred planar")
-            planar(b['x_hi'][L], pa, copies=3)
-            wgrad(pa, pt, 16, inv, self.gw_tail)
-            rowsum(pt, 16, inv, self.gb_tail)
-            _capi.check(lib.dsen2_nchw_to_nhwc_f16(ptr(b['dpred']), self.cout, n, P, P, F, ptr(b['dy_nhwc']), st), "dpred nhwc")
+            _capi.check(lib.dsen2_nchw_to_nhwc_f16(ptr(b['dpred']), self.cout, None, 0, None, 0, n, P, P, F, ptr(b['dy_nhwc']), st),
+                        "dpred nhwc")
+            wgrad(b['x_hi'][L], b['dy_nhwc'], inv, self.gw_tail)
+            bgrad(b['dy_nhwc'], inv, self.gb_tail)
             b['dx32'].zero_()
             _capi.check(lib.dsen2_conv_res32(ptr(b['dy_nhwc']), ptr(self.w_bwd[-1]), ptr(self.zero_bias), n, P, P, 1.0,
                                              ptr(b['dx32']), ptr(b['dx_hi']), None, st), "dgrad tail")
             # ---- resBlocks, last to first (DSen2Net.py:9-15)
             for l in range(L - 1, -1, -1):
                 i1, i2 = 1 + 2 * l, 2 + 2 * l
-                planar(b['dx_hi'], pb)                                           # d x_{l+1}
-                planar(b['t'][l], pa, copies=3)
-                wgrad(pa, pb, 128, 0.1 * inv, self.kernel(i2, self.grads))
-                rowsum(pb, 128, 0.1 * inv, self.bias(i2, self.grads))
+                wgrad(b['t'][l], b['dx_hi'], 0.1 * inv, self.kernel(i2, self.grads))       # d x_{l+1} -> conv2 (x 0.1)
+                bgrad(b['dx_hi'], 0.1 * inv, self.bias(i2, self.grads))
                 _capi.check(lib.dsen2_conv_relu_bwd(ptr(b['dx_hi']), ptr(self.w_bwd[i2]), ptr(self.zero_bias), ptr(b['t'][l]),
                                                     n, P, P, ptr(b['g2']), st), "dgrad conv2 + relu")
-                planar(b['g2'], pb)
-                planar(b['x_hi'][l], pa, copies=3)
-                wgrad(pa, pb, 128, inv, self.kernel(i1, self.grads))
-                rowsum(pb, 128, inv, self.bias(i1, self.grads))
+                wgrad(b['x_hi'][l], b['g2'], inv, self.kernel(i1, self.grads))
+                bgrad(b['g2'], inv, self.bias(i1, self.grads))
                 _capi.check(lib.dsen2_conv_res32(ptr(b['g2']), ptr(self.w_bwd[i1]), ptr(self.zero_bias), n, P, P, 1.0,
                                                  ptr(b['dx32']), ptr(b['dx_hi']), None, st), "dgrad conv1 + skip")
             # ---- first layer: Conv2D(F, relu) on the concatenated inputs (DSen2Net.py:24-29)
-            planar(b['dx_hi'], pb, mask=b['x_hi'][0])
+            _capi.check(lib.dsen2_relu_mask(ptr(b['dx_hi']), ptr(b['x_hi'][0]), npix * F, ptr(b['g2']), st), "relu mask")
             x2, c2 = (xs[2], self.model.in_channels[2]) if len(xs) == 3 else (None, 0)
-            _capi.check(lib.dsen2_nchw_to_planar(ptr(xs[0]), self.model.in_channels[0], ptr(xs[1]), self.model.in_channels[1],
-                                                 ptr(x2), c2, n, P, P, 128, 3, 1.0, ptr(pa), st), "input planar")
-            wgrad(pa, pb, 128, inv, self.gw_head)
-            rowsum(pb, 128, inv, self.bias(0, self.grads))
+            _capi.check(lib.dsen2_nchw_to_nhwc_f16(ptr(xs[0]), self.model.in_channels[0], ptr(xs[1]), self.model.in_channels[1],
+                                                   ptr(x2), c2, n, P, P, F, ptr(b['dy_nhwc']), st), "input nhwc")
+            wgrad(b['dy_nhwc'], b['g2'], inv, self.gw_head)
+            bgrad(b['g2'], inv, self.bias(0, self.grads))
             self.kernel(0, self.grads).view(9, self.ctot, F).copy_(self.gw_head[:, :self.ctot, :])
             self.kernel(nl - 1, self.grads).view(9, F, self.cout).copy_(self.gw_tail[:, :, :self.cout])
             self.bias(nl - 1, self.grads).copy_(self.gb_tail[:self.cout])
             # ---- data-parallel exchange + Nadam
             if apply:
                 world = allreduce_gradients(self.grads, self.group)
-                self.apply_gradients(1.0 / world)
+                if dev_hp:                                  # graph capture: scalars come from hp_dev (set by the caller)
+                    _capi.check(lib.dsen2_nadam_step_dev(ptr(self.params), ptr(self.grads), ptr(self.m), ptr(self.v),
+                                                         self.params.numel(), ptr(self.hp_dev), st), "nadam")
+                    self.repack()
+                else:
+                    self.apply_gradients(1.0 / world)
             loss = self.sums[0] / total
             mse = self.sums[1] / total
         return loss, mse
@@ -250,7 +301,8 @@ class Trainer:
         self.repack()
 
     def launches_per_step(self):
+        """Kernels of THIS library per step: forward, loss, backward (dgrad + wgrad + bias grads), Nadam, repacking."""
         L = self.L
         fwd = 1 + 1 + 2 * L + 1
-        bwd = 1 + 4 + 2 + 1 + L * 10 + 4 + 3
-        return fwd + bwd + 1 + (2 * L + 2) * 2 + 1
+        bwd = 1 + 1 + 3 + L * 6 + 4
+        return fwd + bwd + 1 + (2 * L + 2) * 2

@@ -222,7 +222,16 @@ int dsen2_nhwc_to_planar(const void* d_in_nhwc_f16, const void* d_mask_nhwc_f16 
                          int n, int H, int W, int C, int rows, int copies, void* d_out, void* stream);
 int dsen2_nchw_to_planar(const float* d_x0, int c0, const float* d_x1, int c1, const float* d_x2, int c2,
                          int n, int H, int W, int rows, int copies, float scale, void* d_out, void* stream);
-int dsen2_nchw_to_nhwc_f16(const float* d_in, int c, int n, int H, int W, int cpad, void* d_out, void* stream);
+/* up to three NCHW fp32 inputs concatenated along channels -> NHWC fp16 (n,H,W,cpad), remaining channels zero */
+int dsen2_nchw_to_nhwc_f16(const float* d_x0, int c0, const float* d_x1, int c1, const float* d_x2, int c2,
+                           int n, int H, int W, int cpad, void* d_out, void* stream);
+/* d_out = d_in where d_act > 0, else 0 (NHWC fp16, `total` elements, multiple of 8) */
+int dsen2_relu_mask(const void* d_in, const void* d_act, long long total, void* d_out, void* stream);
+/* d_out[c] += scale * sum over pixels of d_in[pixel][c]  (NHWC fp16, 128 channels; bias gradients) */
+int dsen2_colsum_nhwc(const void* d_in, long long npix, float scale, float* d_out, void* stream);
+/* Weight gradient straight from the NHWC fp16 tensors (128 channels each), MN-major tcgen05 operands:
+ * d_dw (9,128,128) fp32 += scale * sum_px X[px + tap][ci] * dY[px][co]   (HWIO order).                  */
+int dsen2_wgrad_nhwc(const void* d_x, const void* d_dy, int n, int H, int W, float scale, float* d_dw, void* stream);
 
 /* d_dw (9, 128, n_cols) fp32 += scale * sum_px X[px + tap][ci] * dY[px][co]  (HWIO order; zero it first).
  * X planar, 3 shifted copies of 128 rows; dY planar, 1 copy of n_cols = 16 or 128 rows.                */
@@ -240,6 +249,11 @@ int dsen2_mae_grad(const float* d_pred, const float* d_y, long long total, float
 int dsen2_nadam_step(float* d_p, const float* d_g, float* d_m, float* d_v, long long total, float grad_mul,
                      float lr, float beta1, float beta2, float eps, float mu_t, float mu_next,
                      float sched_new, float sched_next, float bias2, void* stream);
+
+/* Same update, step-dependent scalars in device memory (replayable inside a captured CUDA graph):
+ * d_hp = {grad_mul, lr, beta1, beta2, eps, mu_t, mu_next, sched_new, sched_next, bias2}.                     */
+int dsen2_nadam_step_dev(float* d_p, const float* d_g, float* d_m, float* d_v, long long total,
+                         const float* d_hp, void* stream);
 
 /* Debug / self-test hooks (used by tests only) */
 int dsen2_debug_force_v1(int on);   /* route 128-feature layers of dsen2_conv3x3 to the single-CTA kernel */

@@ -87,20 +87,27 @@ __global__ void nchw_to_planar_kernel(const float* __restrict__ x0, int c0, cons
   }
 }
 
-// up to three NCHW fp32 inputs (n,c_i,H,W) concatenated along channels -> NHWC fp16 (n,H,W,cpad), other channels zero
+// up to three NCHW fp32 inputs (n,c_i,H,W), at most 16 channels in total, concatenated along channels -> the first 16
+// channels of NHWC fp16 (n,H,W,cpad).  One thread per pixel: plane reads are coalesced across the warp, each thread
+// writes one 32-byte sector.  (The remaining channels are zeroed by a memset in the entry point.)
 __global__ void nchw_to_nhwc_f16_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x1, int c1,
-                                        const float* __restrict__ x2, int c2, int n, int H, int W, int cpad, long long total,
+                                        const float* __restrict__ x2, int c2, long long hw, int cpad, long long npix,
                                         __half* __restrict__ out) {
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int ch = (int)(idx % cpad);
-    const long long pix = idx / cpad;
-    const int x = (int)(pix % W), y = (int)((pix / W) % H), b = (int)(pix / ((long long)W * H));
-    float v = 0.f;
-    if (ch < c0) v = x0[(((long long)b * c0 + ch) * H + y) * W + x];
-    else if (ch < c0 + c1) v = x1[(((long long)b * c1 + (ch - c0)) * H + y) * W + x];
-    else if (ch < c0 + c1 + c2) v = x2[(((long long)b * c2 + (ch - c0 - c1)) * H + y) * W + x];
-    out[idx] = __float2half_rn(v);
+  for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < npix;
+       pix += (long long)gridDim.x * blockDim.x) {
+    const long long b = pix / hw, r = pix - b * hw;
+    __align__(16) __half v[16];
+#pragma unroll
+    for (int ch = 0; ch < 16; ++ch) {
+      float f = 0.f;
+      if (ch < c0) f = x0[(b * c0 + ch) * hw + r];
+      else if (ch < c0 + c1) f = x1[(b * c1 + (ch - c0)) * hw + r];
+      else if (ch < c0 + c1 + c2) f = x2[(b * c2 + (ch - c0 - c1)) * hw + r];
+      v[ch] = __float2half_rn(f);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out + pix * cpad);
+    dst[0] = reinterpret_cast<const uint4*>(v)[0];
+    dst[1] = reinterpret_cast<const uint4*>(v)[1];
   }
 }
 
@@ -121,18 +128,35 @@ __global__ void relu_mask_kernel(const uint4* __restrict__ in, const uint4* __re
 }
 
 // out[c] += scale * sum_pixels in[pixel][c]   (bias gradients from an NHWC fp16 gradient tensor, C = 128)
+// 256 threads = 16 pixel lanes x 16 chunks of 8 channels (one 16-byte load each); block partials -> atomics
 __global__ void colsum_nhwc_kernel(const __half* __restrict__ in, long long npix, float scale, float* __restrict__ out) {
-  // block: 256 threads = 2 pixel lanes x 128 channels; grid-stride over pixels
-  const int c = threadIdx.x & 127, lane_p = threadIdx.x >> 7;
-  float acc = 0.f;
-  for (long long p = (long long)blockIdx.x * 2 + lane_p; p < npix; p += (long long)gridDim.x * 2) acc += __half2float(in[p * 128 + c]);
-  __shared__ float red[256];
-  red[threadIdx.x] = acc;
+  const int chunk = threadIdx.x & 15, pl = threadIdx.x >> 4;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (long long p = (long long)blockIdx.x * 16 + pl; p < npix; p += (long long)gridDim.x * 16) {
+    const uint4 q = *reinterpret_cast<const uint4*>(in + p * 128 + chunk * 8);
+    const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h[j]);
+      acc[2 * j] += f.x;
+      acc[2 * j + 1] += f.y;
+    }
+  }
+  __shared__ float red[16][129];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[pl][chunk * 8 + j] = acc[j];
   __syncthreads();
-  if (threadIdx.x < 128) atomicAdd(out + c, (red[threadIdx.x] + red[threadIdx.x + 128]) * scale);
+  if (threadIdx.x < 128) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += red[i][threadIdx.x];
+    atomicAdd(out + threadIdx.x, s * scale);
+  }
 }
 
-// out[r] = scale * sum_k in[r][k]   (bias gradients: the planar gradient tensor has zero borders)
+// out[r] = scale * sum_k in[r][k]   (bias gradients from a planar gradient tensor: its borders are zero)
 __global__ void rowsum_kernel(const __half* __restrict__ in, long long kpitch, float scale, float* __restrict__ out) {
   const __half* row = in + (long long)blockIdx.x * kpitch;
   float acc = 0.f;
@@ -550,11 +574,13 @@ extern "C" int dsen2_nchw_to_planar(const float* d_x0, int c0, const float* d_x1
 extern "C" int dsen2_nchw_to_nhwc_f16(const float* d_x0, int c0, const float* d_x1, int c1, const float* d_x2, int c2,
                                       int n, int H, int W, int cpad, void* d_out, void* stream) {
   DSEN2_REQUIRE(d_x0 && d_out && (c1 == 0 || d_x1) && (c2 == 0 || d_x2) && c0 > 0 && c1 >= 0 && c2 >= 0 &&
-                    cpad >= c0 + c1 + c2 && n > 0 && H > 0 && W > 0,
-                DSEN2_E_BADARG, "dsen2_nchw_to_nhwc_f16: bad arguments");
-  const long long total = (long long)n * H * W * cpad;
-  nchw_to_nhwc_f16_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d_x0, c0, d_x1, c1, d_x2, c2, n, H, W, cpad,
-                                                                                  total, (__half*)d_out);
+                    c0 + c1 + c2 <= 16 && cpad >= 16 && cpad % 8 == 0 && n > 0 && H > 0 && W > 0,
+                DSEN2_E_BADARG, "dsen2_nchw_to_nhwc_f16: bad arguments (at most 16 channels, cpad a multiple of 8 >= 16)");
+  DSEN2_REQUIRE(((uintptr_t)d_out % 16) == 0, DSEN2_E_ALIGN, "dsen2_nchw_to_nhwc_f16: output must be 16-byte aligned");
+  const long long npix = (long long)n * H * W;
+  if (cpad > 16) DSEN2_CUDA(cudaMemsetAsync(d_out, 0, (size_t)npix * cpad * 2, (cudaStream_t)stream));
+  nchw_to_nhwc_f16_kernel<<<grid_for(npix, 256), 256, 0, (cudaStream_t)stream>>>(d_x0, c0, d_x1, c1, d_x2, c2, (long long)H * W,
+                                                                                 cpad, npix, (__half*)d_out);
   return check_launch("nchw_to_nhwc_f16");
 }
 
@@ -567,8 +593,8 @@ extern "C" int dsen2_relu_mask(const void* d_in, const void* d_act, long long to
 
 extern "C" int dsen2_colsum_nhwc(const void* d_in, long long npix, float scale, float* d_out, void* stream) {
   DSEN2_REQUIRE(d_in && d_out && npix > 0, DSEN2_E_BADARG, "dsen2_colsum_nhwc: bad arguments");
-  long long blocks = (npix + 1) / 2;
-  const long long cap = (long long)sm_count() * 4;
+  long long blocks = (npix + 15) / 16;
+  const long long cap = (long long)sm_count() * 2;
   if (blocks > cap) blocks = cap;
   colsum_nhwc_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __half*)d_in, npix, scale, d_out);
   return check_launch("colsum_nhwc");

@@ -191,15 +191,34 @@ class Trainer:
                 d.copy_(s_, non_blocking=True)
             b['in_y'].copy_(y, non_blocking=True)
             self._advance_schedule(1.0 / self._world())
+            multi = self._world() > 1
             if key not in self._graphs:
+                # one graph on a single GPU; with several ranks the NCCL all-reduce stays an eager call between a
+                # "gradient" graph and an "update" graph (a collective inside the capture deadlocked in testing)
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    loss, mse = self._step_body(b['in_x'], b['in_y'], True, dev_hp=True)
+                    loss, mse = self._step_body(b['in_x'], b['in_y'], not multi, dev_hp=True)
                     self.loss_out[0].copy_(loss)
                     self.loss_out[1].copy_(mse)
-                self._graphs[key] = g
-            self._graphs[key].replay()
+                g2 = None
+                if multi:
+                    g2 = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g2):
+                        self._update_dev()
+                self._graphs[key] = (g, g2)
+            g, g2 = self._graphs[key]
+            g.replay()
+            if multi:
+                allreduce_gradients(self.grads, self.group)
+                g2.replay()
             return self.loss_out[0].clone(), self.loss_out[1].clone()
+
+    def _update_dev(self):
+        """Nadam update with the scalars published in ``hp_dev`` + operand repacking (capturable)."""
+        lib, ptr, st = _capi.lib(), _capi.ptr, _capi.stream_ptr()
+        _capi.check(lib.dsen2_nadam_step_dev(ptr(self.params), ptr(self.grads), ptr(self.m), ptr(self.v), self.params.numel(),
+                                             ptr(self.hp_dev), st), "nadam")
+        self.repack()
 
     def _world(self):
         import torch.distributed as dist
@@ -277,14 +296,11 @@ class Trainer:
             self.kernel(nl - 1, self.grads).view(9, F, self.cout).copy_(self.gw_tail[:, :, :self.cout])
             self.bias(nl - 1, self.grads).copy_(self.gb_tail[:self.cout])
             # ---- data-parallel exchange + Nadam
-            if apply:
+            if apply and dev_hp:                            # single-GPU graph capture: scalars come from hp_dev
+                self._update_dev()
+            elif apply:
                 world = allreduce_gradients(self.grads, self.group)
-                if dev_hp:                                  # graph capture: scalars come from hp_dev (set by the caller)
-                    _capi.check(lib.dsen2_nadam_step_dev(ptr(self.params), ptr(self.grads), ptr(self.m), ptr(self.v),
-                                                         self.params.numel(), ptr(self.hp_dev), st), "nadam")
-                    self.repack()
-                else:
-                    self.apply_gradients(1.0 / world)
+                self.apply_gradients(1.0 / world)
             loss = self.sums[0] / total
             mse = self.sums[1] / total
         return loss, mse

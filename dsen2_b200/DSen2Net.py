@@ -259,6 +259,25 @@ class S2Model:
                     0.0, None, None, ptr(xs[-1]), ptr(out), self.out_channels, st), "dsen2_conv3x3(tail)"))
         return out
 
+    def forward_c(self, xs, out=None):
+        """Same as ``forward_device`` through the single C entry point ``dsen2_s2model_forward`` (what a C caller of
+        ``include/dsen2_b200.h`` uses): one call, workspace supplied by the caller."""
+        torch = _capi.require_cuda()
+        n, _, P, _ = xs[0].shape
+        dev = xs[0].device
+        _wts, _biases, wp, bp = self._ensure_packed(dev)
+        if out is None:
+            out = torch.empty((n, self.out_channels, P, P), dtype=torch.float32, device=dev)
+        nbytes = self.workspace_bytes(n, P)
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        xp = (ctypes.c_void_p * len(xs))(*[x.data_ptr() for x in xs])
+        ch = (ctypes.c_int * len(xs))(*self.in_channels)
+        with torch.cuda.device(dev):
+            _capi.check(_capi.lib().dsen2_s2model_forward(xp, ch, len(xs), n, P, self.num_layers, self.feature_size, wp, bp,
+                                                          _capi.ptr(ws), nbytes, _capi.ptr(out), _capi.stream_ptr()),
+                        "dsen2_s2model_forward")
+        return out
+
     def forward_images(self, d10, d20, d60, patch, border, first_patch, n, canvas, mul, timers=None):
         """Fused tile pipeline of the fast path: patches [first_patch, first_patch+n) are gathered straight
         from the HWC images (extract + bilinear + /mul), run through the network, and the pixels they own

@@ -142,6 +142,22 @@ def test_s2model_predict_vs_oracle(env, cfg):
     assert err <= GATE
 
 
+@pytest.mark.parametrize('cfg', [dict(inp=(4, 6), L=2, F=128, P=64, n=3), dict(inp=(4, 6, 2), L=1, F=128, P=48, n=2),
+                                 dict(inp=(4, 6), L=1, F=256, P=32, n=2), dict(inp=(4, 6), L=0, F=128, P=32, n=2)])
+def test_c_entry_point_whole_forward(env, cfg):
+    """dsen2_s2model_forward (the one-call C entry) == the per-layer sequence the Python host issues."""
+    torch, _capi, lib = env
+    from dsen2_b200.DSen2Net import s2model
+    rng = np.random.RandomState(5)
+    model = s2model(tuple((c, None, None) for c in cfg['inp']), num_layers=cfg['L'], feature_size=cfg['F'], seed=2)
+    xs = [torch.from_numpy((0.8 + 0.4 * rng.randn(cfg['n'], c, cfg['P'], cfg['P'])).clip(0, 5).astype(np.float32)).cuda()
+          for c in cfg['inp']]
+    a = model.forward_device(xs).clone()
+    b = model.forward_c(xs)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+
+
 def test_DSen2_20_and_60_scene_vs_oracle(env, malmo):
     from dsen2_b200 import supres
     from dsen2_b200.DSen2Net import s2model

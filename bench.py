@@ -190,6 +190,8 @@ def run_ours(args):
 
     run_60 = args.path == 60
     T, P, B, r = (args.tile, 192, 12, 6) if run_60 else (args.tile, 128, 8, 2)
+    if args.batch <= 0:
+        args.batch = supres.default_device_batch(T, P, B)
     if T % 6:
         raise SystemExit("--tile must be a multiple of 6")
     deep = args.model == 'vdsen2'
@@ -334,11 +336,11 @@ def run_ours(args):
                 "tflops_executed_whole_step": FLOP_PER_PIXEL[(args.model, args.path)] * float(filled) * P * P / (ms_step * 1e-3) / 1e12,
                 "checksum": checksum}
         if world == 1 and not args.no_cpu_baseline:
-            crop = 672
+            crop = 448 if deep else 1344             # ~10-20 s of host work
             mpx, per, threads = cpu_oracle_run(crop, 1, 0, deep=deep)
             line["cpu_baseline"] = {"value": mpx, "unit": "Mpixel/s", "cores": threads, "kind": "port",
-                                    "sample": "%dx%d crop (36 patches) through the CPU oracle port, %.1f s; "
-                                              "extrapolates linearly to the tile" % (crop, crop, per)}
+                                    "sample": "%dx%d crop (%d patches) through the CPU oracle port, %.1f s; "
+                                              "extrapolates linearly to the tile" % (crop, crop, (crop // 112) ** 2, per)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -438,7 +440,7 @@ def main():
     ap.add_argument('--model', default='dsen2', choices=['dsen2', 'vdsen2'])
     ap.add_argument('--tile', type=int, default=10980)
     ap.add_argument('--path', type=int, default=20, choices=[20, 60], help='20 m -> 10 m (DSen2_20) or 60 m -> 10 m (DSen2_60)')
-    ap.add_argument('--batch', type=int, default=64, help='patches per device batch')
+    ap.add_argument('--batch', type=int, default=0, help='patches per device batch (0 = whole patch rows, see supres.default_device_batch)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--workload', default='tile', choices=['tile', 'train'],
                     help="'tile' = the headline inference benchmark; 'train' = BASELINE.json configs[4] (training step)")

@@ -42,6 +42,17 @@ def _load_model(input_shape, deep, run_60):
     return _model_cache[key]
 
 
+def default_device_batch(W, P, B):
+    """Patches per launch: whole patch rows of the tile when a row is a reasonable batch (a full Sentinel-2 tile has 99
+    patches of 128 per row), so that the chunks of ``HostPipeline`` (whole rows) split into equal batches; about 1.5 M
+    patch pixels otherwise.  Larger batches only amortise launch overhead (~1 % between 64 and 128 patches)."""
+    nx = -(-W // (P - 2 * B))
+    target = max(1, (96 * 128 * 128) // (P * P))
+    if nx > 2 * target:
+        return target
+    return nx * max(1, target // nx)
+
+
 def super_resolve_device(model, d10, d20, d60=None, first_patch=0, num_patches=None, out=None, device_batch=None,
                          timers=None):
     """Device-level pipeline.  d10/d20(/d60): CUDA float32 HWC tensors.  Processes patches
@@ -65,7 +76,7 @@ def super_resolve_device(model, d10, d20, d60=None, first_patch=0, num_patches=N
     if out is None:
         out = torch.zeros((H, W, model.out_channels), dtype=torch.float32, device=d10.device)
     if device_batch is None:
-        device_batch = max(1, (64 * 128 * 128) // (P * P))
+        device_batch = default_device_batch(W, P, B)
     single = filled == 1                     # recompose_images returns the lone patch uncropped (patches.py:375-376)
     for p0 in range(first_patch, first_patch + num_patches, device_batch):
         nb = min(device_batch, first_patch + num_patches - p0)

@@ -40,11 +40,21 @@ inline int check_launch(const char* what) {
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// cudaFuncSetAttribute is per device: remember which devices a kernel has been configured on (a process may drive
+// several GPUs).  `flags` is a per-kernel static array.
+static inline bool needs_config(bool (&flags)[64]) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  if (flags[dev]) return false;
+  flags[dev] = true;
+  return true;
+}
+
 // conv_tcgen05.cu
 int make_tmap_f16(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint32_t* box);
 int device_sm_count_and_check(int* sms);
 // conv_pair.cu
-int conv_pair_res(const void* d_in, const void* d_w, const float* d_bias, int n, int H, int W, int epilogue,
+int conv_pair_res(const void* d_in, const void* d_w, const float* d_bias, int n, int H, int W, int features, int epilogue,
                   const void* d_res_hi, const void* d_res_lo, float res_scale, void* d_out_hi, void* d_out_lo,
                   cudaStream_t stream);
 

@@ -63,8 +63,10 @@ struct PairParams {
   int first_patch, img_h, img_w, border, grid_ny, grid_nx;
 };
 
-template <int NTOT_, bool SPLIT_, int NMAPS_, int KPM_, int NTAPS_, int KSTEPS_, int STAGES_, int EPI_>
+template <int NTOT_, bool SPLIT_, int NMAPS_, int KPM_, int NTAPS_, int KSTEPS_, int STAGES_, int EPI_, int WSTAGES_ = 0>
 struct PairCfg {
+  static constexpr int WSTAGES = WSTAGES_;      // 0: the layer's weights are resident in smem; > 0: ring of streamed slabs
+  static constexpr bool RESIDENT = WSTAGES_ == 0;
   static constexpr int NTOT = NTOT_;            // UMMA N over the pair
   static constexpr bool SPLIT = SPLIT_;         // B = [W_hi ; W_lo]: epilogue sums the two column halves
   static constexpr int NMAPS = NMAPS_;          // A tensors (1, or 2 = hi then lo)
@@ -81,15 +83,16 @@ struct PairCfg {
   static constexpr int SLAB_ROWS = NTOT_ / 2;
   static constexpr int SLAB_BYTES = SLAB_ROWS * 128;
   static constexpr int NSLABS = NTAPS_ * KPM_;
-  static constexpr int W_BYTES = NSLABS * SLAB_BYTES;
+  static constexpr int W_BYTES = (WSTAGES_ == 0 ? NSLABS : WSTAGES_) * SLAB_BYTES;
   static constexpr int TMEM_COLS = (2 * NTOT_ < 32) ? 32 : 2 * NTOT_;
-  static constexpr int BAR_BYTES = 1024;        // barriers + tmem pointer + bias
+  static constexpr int BAR_BYTES = 2048;        // barriers + tmem pointer (first 512 B) + bias
   static constexpr int STG_BYTES = kEpiWarps * 1024;   // per-warp transpose buffers of the epilogue
   static constexpr int SMEM_BYTES = W_BYTES + STAGES_ * STAGE_BYTES + BAR_BYTES + STG_BYTES + 1024 /*align slack*/;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
   static_assert(W_BYTES % 1024 == 0, "weight slabs must keep the stages 1024-byte aligned");
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM allocation must be a power of two <= 512");
-  static_assert(CH * 4 + 256 <= BAR_BYTES, "bias does not fit next to the barriers");
+  static_assert(CH * 4 + 512 <= BAR_BYTES, "bias does not fit next to the barriers");
+  static_assert((2 * STAGES_ + 6 + 2 * WSTAGES_) * 8 <= 512, "too many barriers");
 };
 
 // tile index -> (patch, tile row, tile column); 32-bit arithmetic (64-bit divisions cost ~100 instructions each)
@@ -183,12 +186,12 @@ __device__ __forceinline__ void staged_gather(uint32_t stg, const uint4 (&gl)[8]
 }
 
 template <class Cfg>
-__device__ __forceinline__ EpiGeom epi_geom(const PairParams& p, const TileXY& t, int wq, int half) {
+__device__ __forceinline__ EpiGeom epi_geom(const PairParams& p, const TileXY& t, int wq, int chan0) {
   const int yw = t.ty * 16 + wq * 4;            // first image row of this warp's 4 rounds
   EpiGeom g;
   g.ch = Cfg::CH;
   g.row_pitch = (long long)p.W * Cfg::CH;
-  g.base = (((long long)t.b * p.H + yw) * p.W + t.tx * 8) * Cfg::CH + half * (Cfg::CH / 2);
+  g.base = (((long long)t.b * p.H + yw) * p.W + t.tx * 8) * Cfg::CH + chan0;
   g.rows_valid = (t.b < p.n) ? max(0, min(4, p.H - yw)) : 0;
   g.px_valid = max(0, min(8, p.W - t.tx * 8));
   return g;
@@ -209,7 +212,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
   uint64_t* tmem_full = wfull + 1;                             // per CTA (multicast commit)
   uint64_t* tmem_empty = tmem_full + 2;                        // leader; 2 * kEpiWarps arrivals
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* s_bias = reinterpret_cast<float*>(bar_base + 256);
+  uint64_t* wr_full = tmem_empty + 3;                          // streamed-weight ring: leader's copies are live
+  uint64_t* wr_empty = wr_full + Cfg::WSTAGES;                 // per CTA (multicast commit)
+  float* s_bias = reinterpret_cast<float*>(bar_base + 512);
   const uint32_t s_bias_addr = smem_u32(s_bias);
   uint8_t* s_stg = bar_base + Cfg::BAR_BYTES;
 
@@ -229,6 +234,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
       mbar_init(&empty[i], 1);
     }
     mbar_init(wfull, 1);
+    for (int i = 0; i < Cfg::WSTAGES; ++i) {
+      mbar_init(&wr_full[i], 1);
+      mbar_init(&wr_empty[i], 1);
+    }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 2 * kEpiWarps);
@@ -246,12 +255,14 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
   if (warp == kProducerWarp) {
     // ================================ TMA producer (both CTAs) ================================
     if (elect_one()) {
-      if (rank == 0) mbar_expect_tx(wfull, 2 * Cfg::W_BYTES);
-      for (int s = 0; s < Cfg::NSLABS; ++s)
-        tma_load_3d_pair(s_w + s * Cfg::SLAB_BYTES, &tm_w, wfull, (s % Cfg::KPM) * 64, (int)rank * Cfg::SLAB_ROWS,
-                         s / Cfg::KPM);
-      int stage = 0;
-      uint32_t phase = 0;
+      if constexpr (Cfg::RESIDENT) {
+        if (rank == 0) mbar_expect_tx(wfull, 2 * Cfg::W_BYTES);
+        for (int s = 0; s < Cfg::NSLABS; ++s)
+          tma_load_3d_pair(s_w + s * Cfg::SLAB_BYTES, &tm_w, wfull, (s % Cfg::KPM) * 64, (int)rank * Cfg::SLAB_ROWS,
+                           s / Cfg::KPM);
+      }
+      int stage = 0, ws = 0;
+      uint32_t phase = 0, wphase = 0;
       for (uint32_t pt = pair; pt < pair_tiles; pt += npairs) {
         // tile may equal num_tiles (odd count): then b == n and the whole box is zero fill
         const TileXY t = decode_tile(2 * pt + rank, p.tiles_x, p.tiles_y);
@@ -275,6 +286,16 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
             tma_load_4d_pair(s_a + stage * Cfg::STAGE_BYTES, m, &full[stage], (kb % Cfg::KPM) * 64, bx, by, b);
           }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+          if constexpr (!Cfg::RESIDENT) {            // this k-block's nine weight slabs, in the order the MMAs use them
+#pragma unroll 1
+            for (int tap = 0; tap < Cfg::NTAPS; ++tap) {
+              mbar_wait(&wr_empty[ws], wphase ^ 1);
+              if (rank == 0) mbar_expect_tx(&wr_full[ws], 2 * Cfg::SLAB_BYTES);
+              tma_load_3d_pair(s_w + ws * Cfg::SLAB_BYTES, &tm_w, &wr_full[ws], (kb % Cfg::KPM) * 64,
+                               (int)rank * Cfg::SLAB_ROWS, tap);
+              if (++ws == Cfg::WSTAGES) { ws = 0; wphase ^= 1; }
+            }
+          }
         }
       }
     }
@@ -282,10 +303,12 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
     // ================================ MMA issuer (leader CTA) ==================================
     if (rank == 0 && elect_one()) {
       constexpr uint32_t idesc = umma_idesc_f16(256, Cfg::NTOT);
-      mbar_wait(wfull, 0);
-      tc_fence_after();
-      int stage = 0;
-      uint32_t phase = 0;
+      if constexpr (Cfg::RESIDENT) {
+        mbar_wait(wfull, 0);
+        tc_fence_after();
+      }
+      int stage = 0, ws = 0;
+      uint32_t phase = 0, wphase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (uint32_t pt = pair; pt < pair_tiles; pt += npairs) {
@@ -303,11 +326,20 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
             const int dy = Cfg::NTAPS == 9 ? tap / 3 : tap;
             const int dx = Cfg::NTAPS == 9 ? tap % 3 : 0;
             const uint32_t a0 = sa + (uint32_t)((dy * Cfg::BOXW + dx) * 128);
-            const uint32_t b0 = sb + (uint32_t)(tap * Cfg::KPM * Cfg::SLAB_BYTES);
+            uint32_t b0 = sb + (uint32_t)(tap * Cfg::KPM * Cfg::SLAB_BYTES);
+            if constexpr (!Cfg::RESIDENT) {
+              mbar_wait(&wr_full[ws], wphase);
+              tc_fence_after();
+              b0 = smem_u32(s_w) + (uint32_t)(ws * Cfg::SLAB_BYTES);
+            }
 #pragma unroll
             for (int k = 0; k < Cfg::KSTEPS; ++k)
               umma_f16_ss_pair(d_tmem, umma_desc_sw128_sbo(a0 + k * 32, Cfg::BOXW * 128),
                                umma_desc_sw128_sbo(b0 + k * 32, 1024), idesc, (uint32_t)((kb | tap | k) != 0));
+            if constexpr (!Cfg::RESIDENT) {
+              umma_commit_pair(&wr_empty[ws]);                   // frees the weight slot in both CTAs
+              if (++ws == Cfg::WSTAGES) { ws = 0; wphase ^= 1; }
+            }
           }
           umma_commit_pair(&empty[stage]);                       // frees the slot in both CTAs
           if (kb == Cfg::KB - 1) umma_commit_pair(&tmem_full[acc]);
@@ -398,7 +430,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
         constexpr int CPT = Cfg::CH / 2;
         static_assert(CPT == 64 && !Cfg::SPLIT, "fp32-trunk epilogue: 64 channels per thread");
         const uint32_t stg = smem_u32(s_stg) + (uint32_t)(warp * 1024);
-        const EpiGeom g = epi_geom<Cfg>(p, tc, wq, half);
+        const EpiGeom g = epi_geom<Cfg>(p, tc, wq, half * CPT);
         // tile-row-major trunk: (n, H, W/8, C/4, 8 px, 4 ch) -- the 32 chunks of a tile row are 4 KB contiguous
         constexpr long long cpitch = 32;                                // floats between 4-channel chunks
         float* xp = p.x32 + ((((long long)b * p.H + y) * p.tiles_x + tc.tx) * (Cfg::CH / 4) + half * (CPT / 4)) * cpitch +
@@ -474,95 +506,104 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
         continue;
       } else {
         // ------------------------------------------------------------------ trunk layers
-        constexpr int CPT = Cfg::CH / 2;            // channels per thread (64)
-        static_assert(CPT == 64, "the staged epilogue moves 64 channels (128 B) per pixel and warp");
+        // Each thread owns one pixel and CPT = CH/2 channels, processed as CPT/64 "super-chunks" of 64 channels
+        // (128 B per pixel: the unit the staged transposing load / store moves).  128 features: one; 256: two.
+        constexpr int CPT = Cfg::CH / 2;
+        static_assert(CPT % 64 == 0, "the staged epilogue moves 64 channels (128 B) per pixel, warp and super-chunk");
         const uint32_t stg = smem_u32(s_stg) + (uint32_t)(warp * 1024);
-        const EpiGeom g = epi_geom<Cfg>(p, tc, wq, half);
-        uint4 vh[8], vl[8];                         // residual in, then outputs (thread = pixel layout)
         const bool want_lo = p.out_lo != nullptr;
-        if (Cfg::EPI == kEpiResidual) {             // before the accumulator is ready: latency hidden behind the MMAs
-          uint4 gh[8], gl[8];
-          coalesced_load(gh, p.res_hi, g, lane);
-          coalesced_load(gl, p.res_lo, g, lane);
-          if (pt + npairs < pair_tiles) {           // pull the NEXT tile's residual into L2 a whole tile time ahead
-            const EpiGeom gn = epi_geom<Cfg>(p, decode_tile(2 * (pt + npairs) + rank, p.tiles_x, p.tiles_y), wq, half);
-            prefetch_rows(p.res_hi, gn, lane);
-            prefetch_rows(p.res_lo, gn, lane);
-          }
-          staged_gather(stg, gh, vh, lane);
-          staged_gather(stg, gl, vl, lane);
-        }
-        if (Cfg::EPI == kEpiMask) {                 // ReLU backward: the forward activation decides which gradients pass
-          uint4 gm[8];
-          coalesced_load(gm, p.res_hi, g, lane);
-          if (pt + npairs < pair_tiles) {
-            const EpiGeom gn = epi_geom<Cfg>(p, decode_tile(2 * (pt + npairs) + rank, p.tiles_x, p.tiles_y), wq, half);
-            prefetch_rows(p.res_hi, gn, lane);
-          }
-          staged_gather(stg, gm, vh, lane);
-        }
-        mbar_wait(&tmem_full[acc], acc_phase);
-        tc_fence_after();
-#pragma unroll
-        for (int chunk = 0; chunk < CPT / 32; ++chunk) {
-          const int c0 = half * CPT + chunk * 32;
-          uint32_t r[32];
-          tmem_ld_32x32(taddr + c0, r);
-          if (Cfg::SPLIT) {
-            uint32_t r2[32];
-            tmem_ld_32x32(taddr + Cfg::NTOT / 2 + c0, r2);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
-          } else {
-            tmem_ld_wait();
-          }
-          uint32_t* hw = reinterpret_cast<uint32_t*>(vh) + chunk * 16;
-          uint32_t* lw = reinterpret_cast<uint32_t*>(vl) + chunk * 16;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 bq = lds_f4(s_bias_addr + (uint32_t)(c0 + j) * 4);   // broadcast LDS.128
-            const float bb[4] = {bq.x, bq.y, bq.z, bq.w};
-            if (Cfg::EPI == kEpiRelu && p.x32 != nullptr && valid) {   // first layer: seed the fp32 trunk (tile-row-major)
-              const float4 xv = make_float4(fmaxf(__uint_as_float(r[j]) + bq.x, 0.f), fmaxf(__uint_as_float(r[j + 1]) + bq.y, 0.f),
-                                            fmaxf(__uint_as_float(r[j + 2]) + bq.z, 0.f), fmaxf(__uint_as_float(r[j + 3]) + bq.w, 0.f));
-              *reinterpret_cast<float4*>(p.x32 + ((((long long)b * p.H + y) * p.tiles_x + tc.tx) * (Cfg::CH / 4) + ((c0 + j) >> 2)) * 32 +
-                                         (row & 7) * 4) = xv;
+#pragma unroll 1
+        for (int sc = 0; sc < CPT / 64; ++sc) {
+          const int cb = half * CPT + sc * 64;        // first channel of this super-chunk
+          const EpiGeom g = epi_geom<Cfg>(p, tc, wq, cb);
+          uint4 vh[8], vl[8];                         // residual in, then outputs (thread = pixel layout)
+          if (Cfg::EPI == kEpiResidual) {             // before the accumulator is ready: latency hidden behind the MMAs
+            uint4 gh[8], gl[8];
+            coalesced_load(gh, p.res_hi, g, lane);
+            coalesced_load(gl, p.res_lo, g, lane);
+            if (pt + npairs < pair_tiles) {           // pull the NEXT tile's residual into L2 a whole tile time ahead
+              const EpiGeom gn = epi_geom<Cfg>(p, decode_tile(2 * (pt + npairs) + rank, p.tiles_x, p.tiles_y), wq, cb);
+              prefetch_rows(p.res_hi, gn, lane);
+              prefetch_rows(p.res_lo, gn, lane);
             }
+            staged_gather(stg, gh, vh, lane);
+            staged_gather(stg, gl, vl, lane);
+          }
+          if (Cfg::EPI == kEpiMask) {                 // ReLU backward: the forward activation decides which gradients pass
+            uint4 gm[8];
+            coalesced_load(gm, p.res_hi, g, lane);
+            if (pt + npairs < pair_tiles) {
+              const EpiGeom gn = epi_geom<Cfg>(p, decode_tile(2 * (pt + npairs) + rank, p.tiles_x, p.tiles_y), wq, cb);
+              prefetch_rows(p.res_hi, gn, lane);
+            }
+            staged_gather(stg, gm, vh, lane);
+          }
+          if (sc == 0) {
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+          }
 #pragma unroll
-            for (int h2 = 0; h2 < 2; ++h2) {
-              const int jj = j + 2 * h2;
-              float v0 = __uint_as_float(r[jj]) + bb[2 * h2];
-              float v1 = __uint_as_float(r[jj + 1]) + bb[2 * h2 + 1];
-              if (Cfg::EPI == kEpiResidual) {
-                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hw[jj >> 1]));
-                const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&lw[jj >> 1]));
-                v0 = (a.x + c.x) + v0 * p.res_scale;     // Lambda(x * scale) then Add (DSen2Net.py:13,15)
-                v1 = (a.y + c.y) + v1 * p.res_scale;
-              } else if (Cfg::EPI == kEpiMask) {
-                const float2 m = __half22float2(*reinterpret_cast<const __half2*>(&hw[jj >> 1]));
-                v0 = m.x > 0.f ? v0 : 0.f;               // d relu(z) / dz = [z > 0]  (relu(z) > 0  <=>  z > 0)
-                v1 = m.y > 0.f ? v1 : 0.f;
-              } else {
-                v0 = fmaxf(v0, 0.f);
-                v1 = fmaxf(v1, 0.f);
+          for (int chunk = 0; chunk < 2; ++chunk) {
+            const int c0 = cb + chunk * 32;
+            uint32_t r[32];
+            tmem_ld_32x32(taddr + c0, r);
+            if (Cfg::SPLIT) {
+              uint32_t r2[32];
+              tmem_ld_32x32(taddr + Cfg::NTOT / 2 + c0, r2);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+            } else {
+              tmem_ld_wait();
+            }
+            uint32_t* hw = reinterpret_cast<uint32_t*>(vh) + chunk * 16;
+            uint32_t* lw = reinterpret_cast<uint32_t*>(vl) + chunk * 16;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bq = lds_f4(s_bias_addr + (uint32_t)(c0 + j) * 4);   // broadcast LDS.128
+              const float bb[4] = {bq.x, bq.y, bq.z, bq.w};
+              if (Cfg::EPI == kEpiRelu && p.x32 != nullptr && valid) {   // first layer: seed the fp32 trunk (tile-row-major)
+                const float4 xv = make_float4(fmaxf(__uint_as_float(r[j]) + bq.x, 0.f), fmaxf(__uint_as_float(r[j + 1]) + bq.y, 0.f),
+                                              fmaxf(__uint_as_float(r[j + 2]) + bq.z, 0.f), fmaxf(__uint_as_float(r[j + 3]) + bq.w, 0.f));
+                *reinterpret_cast<float4*>(p.x32 + ((((long long)b * p.H + y) * p.tiles_x + tc.tx) * (Cfg::CH / 4) + ((c0 + j) >> 2)) * 32 +
+                                           (row & 7) * 4) = xv;
               }
-              const __half2 h = __floats2half2_rn(v0, v1);
-              hw[jj >> 1] = *reinterpret_cast<const uint32_t*>(&h);
-              if (want_lo) {
-                const float2 hf = __half22float2(h);
-                const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
-                lw[jj >> 1] = *reinterpret_cast<const uint32_t*>(&l);
+#pragma unroll
+              for (int h2 = 0; h2 < 2; ++h2) {
+                const int jj = j + 2 * h2;
+                float v0 = __uint_as_float(r[jj]) + bb[2 * h2];
+                float v1 = __uint_as_float(r[jj + 1]) + bb[2 * h2 + 1];
+                if (Cfg::EPI == kEpiResidual) {
+                  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hw[jj >> 1]));
+                  const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&lw[jj >> 1]));
+                  v0 = (a.x + c.x) + v0 * p.res_scale;     // Lambda(x * scale) then Add (DSen2Net.py:13,15)
+                  v1 = (a.y + c.y) + v1 * p.res_scale;
+                } else if (Cfg::EPI == kEpiMask) {
+                  const float2 m = __half22float2(*reinterpret_cast<const __half2*>(&hw[jj >> 1]));
+                  v0 = m.x > 0.f ? v0 : 0.f;               // d relu(z) / dz = [z > 0]  (relu(z) > 0  <=>  z > 0)
+                  v1 = m.y > 0.f ? v1 : 0.f;
+                } else {
+                  v0 = fmaxf(v0, 0.f);
+                  v1 = fmaxf(v1, 0.f);
+                }
+                const __half2 h = __floats2half2_rn(v0, v1);
+                hw[jj >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+                if (want_lo) {
+                  const float2 hf = __half22float2(h);
+                  const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+                  lw[jj >> 1] = *reinterpret_cast<const uint32_t*>(&l);
+                }
               }
             }
           }
+          if (sc == CPT / 64 - 1) {   // the accumulator has been read: hand the TMEM buffer back before the last stores
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+          }
+          staged_store(stg, vh, p.out_hi, g, lane);
+          if (want_lo) staged_store(stg, vl, p.out_lo, g, lane);
         }
-        // the accumulator has been read: hand the TMEM buffer back before the stores
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
-        staged_store(stg, vh, p.out_hi, g, lane);
-        if (p.out_lo != nullptr) staged_store(stg, vl, p.out_lo, g, lane);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         continue;
       }
@@ -590,17 +631,19 @@ using CfgRelu = PairCfg<128, false, 1, 2, 9, 4, 3, kEpiRelu>;
 using CfgResidual = PairCfg<128, false, 1, 2, 9, 4, 3, kEpiResidual>;
 using CfgResidual32 = PairCfg<128, false, 1, 2, 9, 4, 3, kEpiResidual32>;
 using CfgMask = PairCfg<128, false, 1, 2, 9, 4, 3, kEpiMask>;
+// VDSen2 trunk (256 -> 256): 1.18 MB of weights per layer cannot be resident -- ring of 8 streamed [tap][k-block] slabs
+using CfgRelu256 = PairCfg<256, false, 1, 4, 9, 4, 3, kEpiRelu, 8>;
+using CfgResidual256 = PairCfg<256, false, 1, 4, 9, 4, 3, kEpiResidual, 8>;
 using CfgHead = PairCfg<256, true, 2, 1, 3, 3, 6, kEpiRelu>;
 using CfgTail = PairCfg<32, true, 2, 2, 9, 4, 6, kEpiTail>;
 
 template <class Cfg>
 static int launch_pair(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const PairParams& p,
                        int sms, cudaStream_t stream, const char* what) {
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {};
+  if (needs_config(configured)) {
     DSEN2_CUDA(cudaFuncSetAttribute(conv_pair_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     Cfg::SMEM_BYTES));
-    configured = true;
   }
   const long long pair_tiles = ((long long)p.num_tiles + 1) / 2;
   const long long max_pairs = sms / 2;
@@ -639,8 +682,8 @@ static int fill_tiles(PairParams& p, int n, int H, int W) {
   return 0;
 }
 
-// 128 -> 128 resblock convolution (called by dsen2_conv3x3 for feature_size 128)
-int conv_pair_res(const void* d_in, const void* d_w, const float* d_bias, int n, int H, int W, int epilogue,
+// F -> F resblock convolution (called by dsen2_conv3x3 for feature_size 128 and 256), hi+lo NHWC trunk
+int conv_pair_res(const void* d_in, const void* d_w, const float* d_bias, int n, int H, int W, int features, int epilogue,
                   const void* d_res_hi, const void* d_res_lo, float res_scale, void* d_out_hi, void* d_out_lo,
                   cudaStream_t stream) {
   int sms = 0;
@@ -652,6 +695,13 @@ int conv_pair_res(const void* d_in, const void* d_w, const float* d_bias, int n,
   p.res_hi = (const __half*)d_res_hi; p.res_lo = (const __half*)d_res_lo; p.res_scale = res_scale;
   p.out_hi = (__half*)d_out_hi; p.out_lo = (__half*)d_out_lo;
   CUtensorMap a0, a1, w;
+  if (features == 256) {
+    rc = make_maps<CfgRelu256>(&a0, &a1, &w, d_in, nullptr, d_w, n, H, W);
+    if (rc) return rc;
+    if (epilogue == DSEN2_EPI_RESIDUAL)
+      return launch_pair<CfgResidual256>(a0, a1, w, p, sms, stream, "conv_pair<residual,256>");
+    return launch_pair<CfgRelu256>(a0, a1, w, p, sms, stream, "conv_pair<relu,256>");
+  }
   rc = make_maps<CfgRelu>(&a0, &a1, &w, d_in, nullptr, d_w, n, H, W);
   if (rc) return rc;
   if (epilogue == DSEN2_EPI_RESIDUAL) return launch_pair<CfgResidual>(a0, a1, w, p, sms, stream, "conv_pair<residual>");

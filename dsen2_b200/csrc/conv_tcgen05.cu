@@ -304,11 +304,10 @@ template <int N, int EPI>
 static int launch_conv(const CUtensorMap& tm_in, const CUtensorMap& tm_w, const ConvParams& p, int sms,
                        cudaStream_t stream) {
   using Cfg = ConvCfg<N>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {};
+  if (needs_config(configured)) {
     DSEN2_CUDA(cudaFuncSetAttribute(conv_tcgen05_kernel<N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     Cfg::kSmemBytes));
-    configured = true;
   }
   const int grid = (int)(p.num_tiles < sms ? p.num_tiles : sms);
   conv_tcgen05_kernel<N, EPI><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tm_in, tm_w, p);
@@ -370,16 +369,18 @@ extern "C" int dsen2_conv3x3(const void* d_in, const void* d_w, const float* d_b
                 "dsen2_conv3x3: feature size must be 128 or 256 (got %d)", cout_pad);
   DSEN2_REQUIRE(d_out_hi && ((uintptr_t)d_out_hi % 16) == 0 && ((uintptr_t)d_out_lo % 16) == 0, DSEN2_E_ALIGN,
                 "dsen2_conv3x3: out_hi must be non-null and outputs 16-byte aligned");
-  if (cout_pad == 128 && cin_pad == 128 && taps == 9 && (epilogue == DSEN2_EPI_RELU || epilogue == DSEN2_EPI_RESIDUAL) &&
-      !g_force_v1) {
-    // DSen2 trunk layers: CTA-pair kernel with resident weights and halo-box activations (conv_pair.cu)
+  if ((cout_pad == 128 || cout_pad == 256) && cin_pad == cout_pad && taps == 9 &&
+      (epilogue == DSEN2_EPI_RELU || epilogue == DSEN2_EPI_RESIDUAL) && !g_force_v1) {
+    // trunk layers: CTA-pair kernel with halo-box activations; weights resident (128) or streamed (256) (conv_pair.cu)
     if (epilogue == DSEN2_EPI_RESIDUAL) {
       DSEN2_REQUIRE(d_res_hi && d_res_lo && d_out_lo, DSEN2_E_BADARG,
                     "dsen2_conv3x3: RESIDUAL epilogue needs res_hi, res_lo and out_lo");
       DSEN2_REQUIRE(((uintptr_t)d_res_hi % 16) == 0 && ((uintptr_t)d_res_lo % 16) == 0, DSEN2_E_ALIGN,
                     "dsen2_conv3x3: residual pointers must be 16-byte aligned");
     }
-    return conv_pair_res(d_in, d_w, d_bias, n, H, W, epilogue, d_res_hi, d_res_lo, res_scale, d_out_hi, d_out_lo, s);
+    DSEN2_REQUIRE(d_out_hi && ((uintptr_t)d_out_hi % 16) == 0 && ((uintptr_t)d_out_lo % 16) == 0, DSEN2_E_ALIGN,
+                  "dsen2_conv3x3: out_hi must be non-null and outputs 16-byte aligned");
+    return conv_pair_res(d_in, d_w, d_bias, n, H, W, cout_pad, epilogue, d_res_hi, d_res_lo, res_scale, d_out_hi, d_out_lo, s);
   }
   if (epilogue == DSEN2_EPI_RELU) {
     return cout_pad == 128 ? launch_conv<128, DSEN2_EPI_RELU>(tm_in, tm_w, p, sms, s)

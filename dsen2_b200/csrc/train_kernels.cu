@@ -372,10 +372,9 @@ static int launch_wgrad(const CUtensorMap& tx, const CUtensorMap& ty, int kblock
                         float scale, float* dw, cudaStream_t stream) {
   constexpr int STAGE = 128 * 128 + (N * 128 < 1024 ? 1024 : N * 128);
   constexpr int SMEM = kWgStages * STAGE + 256 + 1024;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {};
+  if (needs_config(configured)) {
     DSEN2_CUDA(cudaFuncSetAttribute(wgrad_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    configured = true;
   }
   wgrad_kernel<N><<<dim3(splits, 9), kWgThreads, SMEM, stream>>>(tx, ty, kblocks, per, wp, scale, dw);
   return check_launch("wgrad_kernel");
@@ -533,10 +532,9 @@ extern "C" int dsen2_wgrad_nhwc(const void* d_x, const void* d_dy, int n, int H,
   if (rc) return rc;
   constexpr int SMEM = kWdStages * kWdStage + 256 + 1024;
   static_assert(kWdStages * kWdStage >= 3 * 65536, "the drain reuses the pipeline stages for three 64 KB accumulators");
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {};
+  if (needs_config(configured)) {
     DSEN2_CUDA(cudaFuncSetAttribute(wgrad_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    configured = true;
   }
   wgrad_direct_kernel<<<dim3(splits, 3), kWdThreads, SMEM, (cudaStream_t)stream>>>(tx, ty, tiles_x, tiles_y, (int)tiles, per,
                                                                                  scale, d_dw);

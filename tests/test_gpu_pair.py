@@ -226,13 +226,17 @@ def test_conv_tail_stitch_matches_recompose(env, tag):
     assert np.array_equal(canvas.cpu().numpy(), ref)
 
 
-def test_pair_kernel_matches_single_cta_kernel(env):
-    """A/B: the CTA-pair trunk kernel and the single-CTA kernel compute the same layer (same operands; only the
-    fp32 accumulation order differs)."""
+@pytest.mark.parametrize('F,shape', [(128, (3, 128, 128)), (256, (2, 128, 128)), (256, (3, 40, 24)), (256, (5, 16, 8))])
+def test_pair_kernel_matches_single_cta_kernel(env, F, shape):
+    """A/B: the CTA-pair trunk kernels (resident weights for 128 features, streamed weight ring for 256) and the
+    single-CTA kernel compute the same layers (same operands; only the fp32 accumulation order differs)."""
     torch, _capi, lib = env
-    n, H, W, F = 3, 128, 128, 128
-    rng = np.random.RandomState(9)
+    n, H, W = shape
+    rng = np.random.RandomState(9 + F)
     x = torch.from_numpy(rng.randn(n, H, W, F).astype(np.float16)).cuda()
+    res = rng.randn(n, H, W, F).astype(np.float32)
+    res_hi = res.astype(np.float16)
+    res_lo = (res - res_hi.astype(np.float32)).astype(np.float16)
     lim = np.sqrt(6.0 / (9 * F))
     w = torch.from_numpy(rng.uniform(-lim, lim, size=(3, 3, F, F)).astype(np.float32)).cuda()
     tw = torch.empty((9, F, F), dtype=torch.float16, device='cuda')
@@ -246,12 +250,18 @@ def test_pair_kernel_matches_single_cta_kernel(env):
             lo = torch.zeros_like(hi)
             _capi.check(lib.dsen2_conv3x3(_capi.ptr(x), _capi.ptr(tw), _capi.ptr(tb), n, H, W, F, F, 9, _capi.EPI_RELU,
                                           None, None, 0.0, _capi.ptr(hi), _capi.ptr(lo), None, None, 0,
-                                          _capi.stream_ptr()), 'conv')
+                                          _capi.stream_ptr()), 'conv relu')
+            rh, rl = torch.from_numpy(res_hi).cuda(), torch.from_numpy(res_lo).cuda()
+            _capi.check(lib.dsen2_conv3x3(_capi.ptr(x), _capi.ptr(tw), _capi.ptr(tb), n, H, W, F, F, 9, _capi.EPI_RESIDUAL,
+                                          _capi.ptr(rh), _capi.ptr(rl), 0.1, _capi.ptr(rh), _capi.ptr(rl), None, None, 0,
+                                          _capi.stream_ptr()), 'conv residual')
             torch.cuda.synchronize()
-            outs.append(hi.float().cpu().numpy() + lo.float().cpu().numpy())
+            outs.append((hi.float().cpu().numpy() + lo.float().cpu().numpy(), rh.float().cpu().numpy() + rl.float().cpu().numpy()))
     finally:
         lib.dsen2_debug_force_v1(0)
-    np.testing.assert_allclose(outs[0], outs[1], rtol=1e-5, atol=1e-5)
+    tol = 1e-5 if F == 128 else 3e-5          # fp32 accumulation order over K = 9*F terms
+    np.testing.assert_allclose(outs[0][0], outs[1][0], rtol=tol, atol=tol)
+    np.testing.assert_allclose(outs[0][1], outs[1][1], rtol=tol, atol=tol)
 
 
 @pytest.mark.parametrize('shape', [(2, 32, 32), (1, 128, 128), (3, 40, 24), (1, 8, 200), (2, 192, 192)])

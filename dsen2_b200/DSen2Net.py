@@ -349,26 +349,60 @@ class S2Model:
         self._weights_stale = True
         return [float(loss), float(mse)]
 
-    def fit(self, x, y, batch_size=128, epochs=1, verbose=0, shuffle=True, seed=None, **_ignored):
-        """Minimal ``model.fit``: shuffled mini-batches, returns {'loss': [...], 'mean_squared_error': [...]} per epoch.
-        (Callbacks / validation of supres_train.py:195-230 are host-side bookkeeping outside the GPU path.)"""
+    @property
+    def optimizer(self):
+        """``model.optimizer.lr`` as the reference's callbacks read / set it (supres_train.py:47)."""
+        if getattr(self, '_trainer', None) is None:
+            raise RuntimeError("You must compile a model before training/testing. Use `model.compile(optimizer, loss)`.")
+        return self._trainer.opt
+
+    def evaluate(self, x, y, batch_size=128, verbose=0):
+        """``model.evaluate`` -> [loss, mean_squared_error] (sample-weighted mean over the batches)."""
+        torch = _capi.require_cuda()
+        tr = self.optimizer and self._trainer
+        xs = [np.asarray(a) for a in (x if isinstance(x, (list, tuple)) else [x])]
+        y = np.asarray(y)
+        n = y.shape[0]
+        to_dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(tr.dev)
+        tot = np.zeros(2)
+        for i in range(0, n, batch_size):
+            l, q = tr.evaluate([to_dev(a[i:i + batch_size]) for a in xs], to_dev(y[i:i + batch_size]))
+            m = min(batch_size, n - i)
+            tot += np.array([float(l), float(q)]) * m
+        return list(tot / n)
+
+    def fit(self, x, y, batch_size=128, epochs=1, verbose=0, callbacks=None, validation_data=None, shuffle=True,
+            initial_epoch=0, seed=None, **_ignored):
+        """``model.fit`` as supres_train.py:218-230 calls it: shuffled mini-batches, optional ``validation_data`` and
+        ``callbacks`` (dsen2_b200.callbacks).  Returns the history dict {'loss', 'mean_squared_error'[, 'val_*']}."""
         xs = [np.asarray(a) for a in (x if isinstance(x, (list, tuple)) else [x])]
         y = np.asarray(y)
         n = y.shape[0]
         rng = np.random.RandomState(seed)
         hist = {'loss': [], 'mean_squared_error': []}
-        for ep in range(epochs):
+        callbacks = list(callbacks or [])
+        for cb in callbacks:
+            cb.set_model(self)
+            cb.on_train_begin()
+        for ep in range(initial_epoch, epochs):
             order = rng.permutation(n) if shuffle else np.arange(n)
             tot, tot_mse, cnt = 0.0, 0.0, 0
             for i in range(0, n, batch_size):
                 idx = np.sort(order[i:i + batch_size])
                 l, q = self.train_on_batch([a[idx] for a in xs], y[idx])
                 tot, tot_mse, cnt = tot + l * len(idx), tot_mse + q * len(idx), cnt + len(idx)
-            hist['loss'].append(tot / cnt)
-            hist['mean_squared_error'].append(tot_mse / cnt)
+            logs = {'loss': tot / cnt, 'mean_squared_error': tot_mse / cnt}
+            if validation_data is not None:
+                vl, vq = self.evaluate(validation_data[0], validation_data[1], batch_size=batch_size)
+                logs.update(val_loss=vl, val_mean_squared_error=vq)
+            for k, v in logs.items():
+                hist.setdefault(k, []).append(v)
             if verbose:
-                print("Epoch %d/%d - loss: %.6f - mean_squared_error: %.6f" % (ep + 1, epochs, hist['loss'][-1],
-                                                                               hist['mean_squared_error'][-1]))
+                print("Epoch %d/%d - " % (ep + 1, epochs) + " - ".join("%s: %.6f" % kv for kv in logs.items()))
+            if callbacks:
+                self.sync_weights_from_trainer()          # checkpoints see the current weights
+                for cb in callbacks:
+                    cb.on_epoch_end(ep, logs)
         self.sync_weights_from_trainer()
         return hist
 

@@ -1,3 +1,3 @@
 """Shim: ``from utils.patches import get_test_patches, get_test_patches60, recompose_images`` (utils/patches.py)."""
-from dsen2_b200.patches import (get_test_patches, get_test_patches60, interp_patches,  # noqa: F401
-                                recompose_images)
+from dsen2_b200.patches import (OpenDataFiles, OpenDataFilesTest, get_test_patches,  # noqa: F401
+                                get_test_patches60, interp_patches, recompose_images, splitTrainVal)

@@ -144,3 +144,59 @@ def recompose_images(a, border, size=None):
         print((a.shape[1], H, W))
     used = a[:x_tiles * y_tiles]          # surplus (all-zero) patches are never read by the reference loop
     return recompose_device(_to_dev(used), border, H, W).cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------ #
+# training / prediction data sets on disk (utils/patches.py:274-350): plain numpy file I/O
+# ------------------------------------------------------------------------------------------ #
+def splitTrainVal(train_path, train, label):
+    """utils/patches.py:274-285: boolean ``val_index.npy`` selects the validation patches."""
+    try:
+        val_ind = np.load(train_path + 'val_index.npy')
+    except IOError:
+        print("Please define the validation split indices, usually located in .../data/test/. To generate this file use"
+              " createRandom.py")
+        raise
+    val_tr = [p[val_ind] for p in train]
+    train = [p[~val_ind] for p in train]
+    val_lb, label = label[val_ind], label[~val_ind]
+    print("Loaded {} patches for training.".format(val_ind.shape[0]))
+    return train, label, val_tr, val_lb
+
+
+def OpenDataFiles(path, run_60, SCALE):
+    """utils/patches.py:288-324: concatenate the per-scene ``data10/20[/60][_gt].npy`` stacks under ``train/`` or
+    ``train60/``, divide by SCALE, split by ``val_index.npy`` -> (train list, label, val list, val label)."""
+    import glob
+    import os
+    train_path = path + ('train60/' if run_60 else 'train/')
+    names = ['data10', 'data20'] + (['data60', 'data60_gt'] if run_60 else ['data20_gt'])
+    stacks = {k: [] for k in names}
+    for dset in [os.path.basename(x) for x in sorted(glob.glob(train_path + '*SAFE'))]:
+        for k in names:
+            stacks[k].append(np.load(train_path + dset + '/' + k + '.npy'))
+    data = {k: (np.concatenate(v) if v else None) for k, v in stacks.items()}
+    if SCALE:
+        for k in names:
+            if data[k] is not None:
+                data[k] = data[k] / SCALE          # float32 stacks stay float32 (the reference divides in place)
+    if run_60:
+        return splitTrainVal(train_path, [data['data10'], data['data20'], data['data60']], data['data60_gt'])
+    return splitTrainVal(train_path, [data['data10'], data['data20']], data['data20_gt'])
+
+
+def OpenDataFilesTest(path, run_60, SCALE, true_scale=False):
+    """utils/patches.py:327-350: one scene's patch stacks + ``roi.json`` -> (input list, [height, width])."""
+    import json
+    if not SCALE:
+        SCALE = 1
+    train = [np.load(path + '/data10.npy') / SCALE, np.load(path + '/data20.npy') / SCALE]
+    if run_60:
+        train.append(np.load(path + '/data60.npy') / SCALE)
+    with open(path + '/roi.json') as fh:
+        roi = json.load(fh)
+    image_size = [(roi[2] - roi[0]), (roi[3] - roi[1])]
+    print("The image size is: {}".format(image_size))
+    print("The SCALE is: {}".format(SCALE))
+    print("The true_scale is: {}".format(true_scale))
+    return train, image_size

@@ -305,6 +305,19 @@ class Trainer:
             mse = self.sums[1] / total
         return loss, mse
 
+    def evaluate(self, xs, y):
+        """Forward + loss only: (mean_absolute_error, mean_squared_error) of one batch as device scalars."""
+        lib, ptr = _capi.lib(), _capi.ptr
+        n, P = int(xs[0].shape[0]), int(xs[0].shape[2])
+        b = self._buffers(n, P)
+        with self.torch.cuda.device(self.dev):
+            pred = self.forward(xs, b, n, P)
+            total = pred.numel()
+            self.sums.zero_()
+            _capi.check(lib.dsen2_mae_grad(ptr(pred), ptr(y), total, self.GSCALE, ptr(b['dpred']), ptr(self.sums),
+                                           _capi.stream_ptr()), "mae")
+            return self.sums[0] / total, self.sums[1] / total
+
     def apply_gradients(self, grad_mul=1.0):
         lib, ptr, st = _capi.lib(), _capi.ptr, _capi.stream_ptr()
         self.iterations += 1

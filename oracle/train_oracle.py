@@ -71,7 +71,7 @@ def train_steps(batches, weights, lr=1e-4, steps=None):
         loss = d.abs().mean()
         loss.backward()
         opt.step()
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
     out = [(ps[2 * i].detach().numpy().transpose(2, 3, 1, 0).copy(), ps[2 * i + 1].detach().numpy().copy())
            for i in range(len(ps) // 2)]
     return losses, out

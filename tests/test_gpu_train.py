@@ -243,3 +243,59 @@ def test_graph_replay_equals_eager_steps(env):
     # fp32 atomics in the weight-gradient reduction make the two runs differ in the last bits only
     d = np.abs(runs[0][1] - runs[1][1]) / (1e-3 * 5)
     assert np.median(d) < 1e-3 and np.mean(d > 0.25) < 0.01
+
+
+def test_fit_with_validation_and_callbacks(env, tmp_path):
+    """model.fit as supres_train.py:218-230 uses it: validation_data, best-only checkpoints, LR reduction; evaluate()
+    agrees with the oracle's loss; the checkpoint is a Keras-style weight file the model can load again."""
+    from dsen2_b200.callbacks import LossLog, ModelCheckpoint, ReduceLROnPlateau
+    from dsen2_b200.train import Nadam
+    from oracle import train_oracle as to
+    model, ws, xs, y = _setup(L=1, n=12, P=32)
+    model.compile(optimizer=Nadam(lr=2e-3), loss='mean_absolute_error', metrics=['mean_squared_error'])
+    ref_loss, ref_mse, _ = to.loss_and_grads([a[8:] for a in xs], y[8:], [(ws[2 * i], ws[2 * i + 1]) for i in range(len(ws) // 2)])
+    ev = model.evaluate([a[8:] for a in xs], y[8:], batch_size=4)
+    assert abs(ev[0] - ref_loss) <= 2e-3 * ref_loss and abs(ev[1] - ref_mse) <= 5e-3 * ref_mse
+    ck = str(tmp_path / 'ck.hdf5')
+    cbs = [ModelCheckpoint(ck, monitor='val_loss', save_best_only=True),
+           ReduceLROnPlateau(monitor='val_loss', factor=0.5, patience=1, epsilon=10.0, cooldown=0, min_lr=1e-4),
+           LossLog(str(tmp_path / 'log.txt'))]
+    hist = model.fit([a[:8] for a in xs], y[:8], batch_size=4, epochs=4, callbacks=cbs,
+                     validation_data=([a[8:] for a in xs], y[8:]), seed=0)
+    assert len(hist['val_loss']) == 4 and hist['loss'][-1] < hist['loss'][0]
+    assert model.optimizer.lr < 2e-3                      # epsilon = 10 makes every epoch a "plateau": the LR was cut
+    assert open(str(tmp_path / 'log.txt')).read().count('Finished epoch') == 4
+    from dsen2_b200.DSen2Net import s2model
+    again = s2model(((4, None, None), (6, None, None)), num_layers=1, feature_size=128)
+    again.load_weights(ck)
+    best = int(np.argmin(hist['val_loss']))
+    if best == 3:                                          # the last epoch was the best: the file holds the final weights
+        for a, b in zip(again.get_weights(), model.get_weights()):
+            assert np.array_equal(a, b)
+
+
+def test_supres_train_cli_trains_and_predicts(env, tmp_path):
+    """python -m dsen2_b200.supres_train on a tiny synthetic data set laid out like the reference's ../data/."""
+    import json
+    from dsen2_b200 import supres_train
+    rng = np.random.RandomState(3)
+    root = str(tmp_path) + '/'
+    d = tmp_path / 'train' / 'S2A_X.SAFE'
+    d.mkdir(parents=True)
+    x10 = (0.8 + 0.3 * rng.randn(16, 4, 32, 32)).clip(0, 4).astype(np.float32) * 2000
+    x20 = (0.8 + 0.3 * rng.randn(16, 6, 32, 32)).clip(0, 4).astype(np.float32) * 2000
+    np.save(d / 'data10.npy', x10); np.save(d / 'data20.npy', x20)
+    np.save(d / 'data20_gt.npy', (x20 + 50 * rng.randn(*x20.shape)).astype(np.float32))
+    val = np.zeros(16, bool); val[::4] = True
+    np.save(tmp_path / 'train' / 'val_index.npy', val)
+    assert supres_train.main(['--path', root, '--epochs', '2']) == 0
+    ck = root + 'network_data/' + supres_train.model_nr + 'lr_1e-04.hdf5'
+    import os
+    assert os.path.exists(ck) and 'Finished epoch' in open(root + 'network_data/' + supres_train.model_nr + '_lr_1.0e-04.txt').read()
+    t = tmp_path / 'test' / 'S2A_Y.SAFE'
+    t.mkdir(parents=True)
+    np.save(t / 'data10.npy', x10[:4]); np.save(t / 'data20.npy', x20[:4])
+    json.dump([0, 0, 48, 48], open(t / 'roi.json', 'w'))
+    assert supres_train.main(['--path', root, '--predict', ck]) == 0
+    out = np.load(str(t / (ck[-20:-13] + '-predict.npy')))
+    assert out.shape == (48, 48, 6) and np.isfinite(out).all()

@@ -75,3 +75,71 @@ def test_allreduce_is_identity_without_a_process_group():
     import torch
     flat = torch.ones(10)
     assert train.allreduce_gradients(flat) == 1 and torch.equal(flat, torch.ones(10))
+
+
+# ---- callbacks and data-set loaders (host-side bookkeeping around model.fit, supres_train.py:195-230) ------------
+class _FakeOpt:
+    lr = 1e-4
+
+
+class _FakeModel:
+    def __init__(self):
+        self.optimizer = _FakeOpt()
+        self.saved = []
+
+    def save_weights(self, path):
+        self.saved.append(path)
+
+
+def test_reduce_lr_on_plateau_follows_the_keras_state_machine():
+    from dsen2_b200.callbacks import ReduceLROnPlateau
+    m = _FakeModel()
+    cb = ReduceLROnPlateau(monitor='val_loss', factor=0.5, patience=2, epsilon=1e-6, cooldown=2, min_lr=3e-5)
+    cb.set_model(m)
+    cb.on_train_begin()
+    lrs = []
+    for ep, v in enumerate([1.0, 0.9, 0.9, 0.9, 0.9, 0.9, 0.9, 0.9, 0.9, 0.9, 0.9]):
+        cb.on_epoch_end(ep, {'val_loss': v})
+        lrs.append(m.optimizer.lr)
+    # improvement at epochs 0,1; plateau -> wait 1,2 -> reduce after epoch 3; cooldown 2 epochs; then patience again
+    assert lrs[:3] == [1e-4, 1e-4, 1e-4] and lrs[3] == 5e-5
+    assert lrs[4] == 5e-5 and lrs[5] == 5e-5          # cooling down
+    assert lrs[7] == 3e-5                              # second reduction clamps at min_lr
+    assert lrs[-1] == 3e-5                             # never below min_lr
+
+
+def test_model_checkpoint_saves_best_only():
+    from dsen2_b200.callbacks import ModelCheckpoint
+    m = _FakeModel()
+    cb = ModelCheckpoint('w_{epoch:02d}.hdf5', monitor='val_loss', save_best_only=True)
+    cb.set_model(m)
+    for ep, v in enumerate([1.0, 1.2, 0.8, 0.8, 0.7]):
+        cb.on_epoch_end(ep, {'val_loss': v})
+    assert m.saved == ['w_01.hdf5', 'w_03.hdf5', 'w_05.hdf5']
+
+
+def test_training_data_loaders(tmp_path):
+    from dsen2_b200 import patches
+    rng = np.random.RandomState(0)
+    root = str(tmp_path) + '/'
+    for i, name in enumerate(['A.SAFE', 'B.SAFE']):
+        d = tmp_path / 'train' / name
+        d.mkdir(parents=True)
+        np.save(d / 'data10.npy', rng.rand(5, 4, 8, 8).astype(np.float32) * 2000)
+        np.save(d / 'data20.npy', rng.rand(5, 6, 8, 8).astype(np.float32) * 2000)
+        np.save(d / 'data20_gt.npy', rng.rand(5, 6, 8, 8).astype(np.float32) * 2000)
+    val = np.zeros(10, bool)
+    val[[1, 7]] = True
+    np.save(tmp_path / 'train' / 'val_index.npy', val)
+    train, label, val_tr, val_lb = patches.OpenDataFiles(root, False, 2000)
+    assert [a.shape for a in train] == [(8, 4, 8, 8), (8, 6, 8, 8)] and label.shape == (8, 6, 8, 8)
+    assert [a.shape for a in val_tr] == [(2, 4, 8, 8), (2, 6, 8, 8)] and val_lb.shape == (2, 6, 8, 8)
+    assert train[0].dtype == np.float32 and 0 <= train[0].min() and train[0].max() <= 1.0
+    import json
+    t = tmp_path / 'test' / 'C.SAFE'
+    t.mkdir(parents=True)
+    np.save(t / 'data10.npy', rng.rand(4, 4, 32, 32).astype(np.float32))
+    np.save(t / 'data20.npy', rng.rand(4, 6, 32, 32).astype(np.float32))
+    json.dump([10, 20, 58, 68], open(t / 'roi.json', 'w'))
+    tr, size = patches.OpenDataFilesTest(str(t), False, 2000)
+    assert size == [48, 48] and len(tr) == 2 and tr[1].shape == (4, 6, 32, 32)

@@ -183,6 +183,52 @@ __global__ void bicubic_kernel(const TIn* __restrict__ in, int h, int w, int C, 
 }
 
 // ------------------------------------------------------------------------------------------ //
+// downPixelAggr (patches.py:353-371): scipy gaussian_filter(sigma = 1/s) per band, then s x s block mean.
+// scipy filters axis 0 then axis 1 in double precision, storing each pass in the array dtype (float32 here), with
+// 'reflect' (= numpy 'symmetric') boundaries and the symmetric-kernel summation order of correlate1d.
+// ------------------------------------------------------------------------------------------ //
+__device__ __forceinline__ double gauss_line(const float* __restrict__ base, long long stride, int pos, int n, const double* w,
+                                             int radius) {
+  double acc = __dmul_rn((double)base[(long long)pos * stride], w[radius]);
+  for (int i = 1; i <= radius; ++i) {
+    const double pair = __dadd_rn((double)base[(long long)sym_index(pos - i, n) * stride],
+                                  (double)base[(long long)sym_index(pos + i, n) * stride]);
+    acc = __dadd_rn(acc, __dmul_rn(pair, w[radius - i]));
+  }
+  return acc;
+}
+
+__global__ void gauss_rows_kernel(const float* __restrict__ img, int H, int W, int C, const double* __restrict__ w, int radius,
+                                  long long total, float* __restrict__ tmp) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long col = idx % ((long long)W * C);               // (x, c) flattened: contiguous across threads
+    const int y = (int)(idx / ((long long)W * C));
+    tmp[idx] = (float)gauss_line(img + col, (long long)W * C, y, H, w, radius);
+  }
+}
+
+__global__ void gauss_cols_mean_kernel(const float* __restrict__ tmp, int H, int W, int C, const double* __restrict__ w,
+                                       int radius, int s, long long total, double* __restrict__ out) {
+  const int ow = W / s;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    const int ox = (int)((idx / C) % ow);
+    const int oy = (int)(idx / ((long long)C * ow));
+    double sum = 0.0;
+    for (int dy = 0; dy < s; ++dy) {
+      const float* row = tmp + ((long long)(oy * s + dy) * W) * C + c;
+      for (int dx = 0; dx < s; ++dx) {
+        const float blurred = (float)gauss_line(row, C, ox * s + dx, W, w, radius);   // second pass, stored as float32
+        sum = (dy == 0 && dx == 0) ? (double)blurred : __dadd_rn(sum, (double)blurred);
+      }
+    }
+    out[idx] = __ddiv_rn(sum, (double)(s * s));
+  }
+}
+
+// ------------------------------------------------------------------------------------------ //
 // operand packing for the tensor-core path
 // ------------------------------------------------------------------------------------------ //
 __global__ void pack_weights_kernel(const float* __restrict__ hwio, int cin, int cout, int cin_pad, int cout_pad,
@@ -349,6 +395,22 @@ extern "C" int dsen2_bicubic_imresize(const void* d_in, int in_is_f64, int h, in
     bicubic_kernel<float><<<grid, block, 0, s>>>((const float*)d_in, h, w, C, d_wy, d_iy, taps_y, out_h, d_wx, d_ix,
                                                  taps_x, out_w, first_dim, total, d_out);
   return check_launch("bicubic_imresize");
+}
+
+extern "C" int dsen2_down_pixel_aggr(const float* d_img, int H, int W, int C, int scale, const double* d_weights, int radius,
+                                     float* d_tmp, double* d_out, void* stream) {
+  DSEN2_REQUIRE(d_img && d_weights && d_tmp && d_out, DSEN2_E_BADARG, "dsen2_down_pixel_aggr: null pointer");
+  DSEN2_REQUIRE(H > 0 && W > 0 && C > 0 && scale > 0 && radius >= 0 && H >= scale && W >= scale, DSEN2_E_BADARG,
+                "dsen2_down_pixel_aggr: bad sizes");
+  const long long total = (long long)H * W * C;
+  const int block = 256;
+  gauss_rows_kernel<<<grid_for(total, block), block, 0, (cudaStream_t)stream>>>(d_img, H, W, C, d_weights, radius, total, d_tmp);
+  int rc = check_launch("gauss_rows");
+  if (rc) return rc;
+  const long long ototal = (long long)(H / scale) * (W / scale) * C;
+  gauss_cols_mean_kernel<<<grid_for(ototal, block), block, 0, (cudaStream_t)stream>>>(d_tmp, H, W, C, d_weights, radius, scale,
+                                                                                    ototal, d_out);
+  return check_launch("gauss_cols_mean");
 }
 
 extern "C" int dsen2_pack_conv_weights(const float* d_hwio, int cin, int cout, int cin_pad, int cout_pad, int im2col,

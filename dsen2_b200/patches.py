@@ -200,3 +200,93 @@ def OpenDataFilesTest(path, run_60, SCALE, true_scale=False):
     print("The SCALE is: {}".format(SCALE))
     print("The true_scale is: {}".format(true_scale))
     return train, image_size
+
+
+# ------------------------------------------------------------------------------------------ #
+# training-data generation (utils/patches.py:159-271, 353-371; used by training/create_patches.py)
+# ------------------------------------------------------------------------------------------ #
+def downPixelAggr(img, SCALE=2):
+    """patches.py:353-371: Gaussian blur with sigma = 1/SCALE per band, then SCALE x SCALE pixel aggregation.
+    Returns float64 like the reference (``np.zeros`` default dtype), squeezed."""
+    torch = _capi.require_cuda()
+    img = np.asarray(img)
+    if img.ndim == 2:
+        img = img[:, :, None]
+    sigma = 1.0 / SCALE
+    radius = int(4.0 * sigma + 0.5)                      # scipy.ndimage.gaussian_filter1d, truncate = 4.0
+    x = np.arange(-radius, radius + 1)
+    w = np.exp(-0.5 / (sigma * sigma) * x ** 2)
+    w = w / w.sum()
+    H, W, C = img.shape
+    d = torch.from_numpy(np.ascontiguousarray(img, dtype=np.float32)).cuda()
+    dw = torch.from_numpy(w).cuda()
+    tmp = torch.empty_like(d)
+    out = torch.empty((H // SCALE, W // SCALE, C), dtype=torch.float64, device=d.device)
+    _capi.check(_capi.lib().dsen2_down_pixel_aggr(_capi.ptr(d), H, W, C, SCALE, _capi.ptr(dw), radius, _capi.ptr(tmp),
+                                                  _capi.ptr(out), _capi.stream_ptr()), "dsen2_down_pixel_aggr")
+    return np.squeeze(out.cpu().numpy())
+
+
+def save_test_patches(dset_10, dset_20, file, patchSize=128, border=4, interp=True):
+    """patches.py:159-167."""
+    image_10, data20_interp = get_test_patches(dset_10, dset_20, patchSize=patchSize, border=border, interp=interp)
+    print("Saving to file {}".format(file))
+    np.save(file + 'data10', image_10)
+    np.save(file + 'data20', data20_interp)
+    print('Done!')
+
+
+def save_test_patches60(dset_10, dset_20, dset_60, file, patchSize=192, border=12, interp=True):
+    """patches.py:170-180."""
+    image_10, data20_interp, data60_interp = get_test_patches60(dset_10, dset_20, dset_60, patchSize=patchSize,
+                                                                border=border, interp=interp)
+    print("Saving to file {}".format(file))
+    np.save(file + 'data10', image_10)
+    np.save(file + 'data20', data20_interp)
+    np.save(file + 'data60', data60_interp)
+    print('Done!')
+
+
+def _random_crops(lowest, sizes_lr, nr_crop):
+    from random import randrange
+    for _ in range(nr_crop):
+        x0 = randrange(0, lowest.shape[0] - sizes_lr[0])
+        y0 = randrange(0, lowest.shape[1] - sizes_lr[1])
+        yield x0, y0
+
+
+def _crop_chw(d, x0, y0, h, w):
+    return np.rollaxis(d[x0:x0 + h, y0:y0 + w], 2)
+
+
+def save_random_patches(dset_20gt, dset_10, dset_20, file, NR_CROP=8000):
+    """patches.py:183-224: random 16x16 (20 m) crops with their 32x32 counterparts; the 20 m stack is upsampled."""
+    label_20 = np.zeros((NR_CROP, dset_20.shape[2], 32, 32), np.float32)
+    image_20 = np.zeros((NR_CROP, dset_20.shape[2], 16, 16), np.float32)
+    image_10 = np.zeros((NR_CROP, dset_10.shape[2], 32, 32), np.float32)
+    for i, (x0, y0) in enumerate(_random_crops(dset_20, (16, 16), NR_CROP)):
+        label_20[i] = _crop_chw(dset_20gt, 2 * x0, 2 * y0, 32, 32)
+        image_20[i] = _crop_chw(dset_20, x0, y0, 16, 16)
+        image_10[i] = _crop_chw(dset_10, 2 * x0, 2 * y0, 32, 32)
+    np.save(file + 'data10', image_10)
+    np.save(file + 'data20_gt', label_20)
+    np.save(file + 'data20', interp_patches(image_20, image_10.shape))
+    print('Done!')
+
+
+def save_random_patches60(dset_60gt, dset_10, dset_20, dset_60, file, NR_CROP=500):
+    """patches.py:227-271: random 16x16 (60 m) crops with their 48x48 (20 m) and 96x96 (10 m) counterparts."""
+    label_60 = np.zeros((NR_CROP, dset_60.shape[2], 96, 96), np.float32)
+    image_10 = np.zeros((NR_CROP, dset_10.shape[2], 96, 96), np.float32)
+    image_20 = np.zeros((NR_CROP, dset_20.shape[2], 48, 48), np.float32)
+    image_60 = np.zeros((NR_CROP, dset_60.shape[2], 16, 16), np.float32)
+    for i, (x0, y0) in enumerate(_random_crops(dset_60, (16, 16), NR_CROP)):
+        label_60[i] = _crop_chw(dset_60gt, 6 * x0, 6 * y0, 96, 96)
+        image_10[i] = _crop_chw(dset_10, 6 * x0, 6 * y0, 96, 96)
+        image_20[i] = _crop_chw(dset_20, 3 * x0, 3 * y0, 48, 48)
+        image_60[i] = _crop_chw(dset_60, x0, y0, 16, 16)
+    np.save(file + 'data10', image_10)
+    np.save(file + 'data60_gt', label_60)
+    np.save(file + 'data20', interp_patches(image_20, image_10.shape))
+    np.save(file + 'data60', interp_patches(image_60, image_10.shape))
+    print('Done!')

@@ -82,6 +82,16 @@ int dsen2_bicubic_imresize(const void* d_in, int in_is_f64, int h, int w, int C,
                            int first_dim, double* d_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Training-data generation -- utils/patches.py:353-371 (downPixelAggr): per band scipy
+ * gaussian_filter(sigma = 1/scale) -- axis 0 then axis 1, double arithmetic, float32 storage between the
+ * passes, 'reflect' boundary, kernel radius int(4/scale + 0.5) -- followed by the scale x scale block mean.
+ * d_weights: the 2*radius+1 normalised Gaussian weights (host, scipy's _gaussian_kernel1d); d_tmp (H,W,C)
+ * float32 scratch; d_out (H/scale, W/scale, C) float64.
+ * ------------------------------------------------------------------------------------------- */
+int dsen2_down_pixel_aggr(const float* d_img, int H, int W, int C, int scale, const double* d_weights, int radius,
+                          float* d_tmp, double* d_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Network (utils/DSen2Net.py:9-43) -- tcgen05 implicit-GEMM convolutions, fp16 operands, fp32
  * accumulation in TMEM, fp32-equivalent (fp16 hi + fp16 lo) residual trunk.
  * Activations are NHWC fp16 with the channel count padded to a multiple of 64.

@@ -120,3 +120,21 @@ def recompose_images(a, border, size=None):
         images = a[p, :, (border + ys - oy)[:, None], (border + xs - ox)[None, :]]  # (H, W, C)
         images = np.ascontiguousarray(images.transpose(2, 0, 1)).astype(np.float32)
     return images.transpose((1, 2, 0))
+
+
+def downPixelAggr(img, SCALE=2):
+    """patches.py:353-371: Gaussian blur (sigma = 1/SCALE, per band) then SCALE x SCALE pixel aggregation (block mean).
+
+    Restated with ``scipy.ndimage.gaussian_filter`` (the reference's own call) and a reshape-mean in place of
+    ``skimage.measure.block_reduce`` (scikit-image is absent, so the reference function itself cannot run here:
+    parity unpinned by the reference, pinned against scipy)."""
+    from scipy.ndimage import gaussian_filter
+    img = np.asarray(img)
+    if img.ndim == 2:
+        img = img[:, :, None]
+    blur = np.zeros(img.shape)
+    for i in range(img.shape[2]):
+        blur[:, :, i] = gaussian_filter(img[:, :, i], 1 / SCALE)
+    h, w = img.shape[0] // SCALE, img.shape[1] // SCALE
+    lr = blur[:h * SCALE, :w * SCALE].reshape(h, SCALE, w, SCALE, img.shape[2]).transpose(0, 2, 4, 1, 3)
+    return np.squeeze(lr.reshape(h, w, img.shape[2], SCALE * SCALE).mean(axis=-1))

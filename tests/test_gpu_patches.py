@@ -153,3 +153,45 @@ def test_full_tile_roundtrip_property(mods):
         q10 = patches.extract_patches_device(d10, 6, 32, 2, p0, nb)
         patches.recompose_device(q10, 12, H, W, first_patch=p0, out=out)
     assert torch.equal(out, d10)
+
+
+@pytest.mark.parametrize('shape,scale', [((48, 60, 4), 2), ((48, 60, 6), 6), ((36, 36, 2), 6), ((20, 30, 1), 2)])
+def test_down_pixel_aggr_matches_scipy_oracle(mods, shape, scale):
+    """patches.py:353-371: gaussian_filter(sigma = 1/scale) + block mean; oracle = scipy's gaussian_filter itself."""
+    patches, _, po, _ = mods
+    rng = np.random.RandomState(shape[0] + scale)
+    img = (rng.rand(*shape) * 4000).astype(np.float32)
+    got = patches.downPixelAggr(img, SCALE=scale)
+    ref = po.downPixelAggr(img, SCALE=scale)
+    assert got.shape == ref.shape and got.dtype == np.float64
+    print('downPixelAggr max |diff| =', np.abs(got - ref).max())
+    assert np.array_equal(got, ref)       # same double arithmetic, float32 storage between the passes, same summation order
+    got2 = patches.downPixelAggr(img[:, :, 0], SCALE=scale)         # 2-D input is expanded and squeezed again
+    assert np.array_equal(got2, ref[..., 0] if ref.ndim == 3 else ref)
+
+
+def test_training_patch_writers(mods, tmp_path):
+    """save_test_patches / save_random_patches (patches.py:159-224) write the stacks supres_train.py loads."""
+    import random
+    patches, _, po, _ = mods
+    rng = np.random.RandomState(4)
+    gt20 = (rng.rand(96, 120, 6) * 3000).astype(np.float32)
+    d10 = (rng.rand(96, 120, 4) * 3000).astype(np.float32)
+    d20 = (rng.rand(48, 60, 6) * 3000).astype(np.float32)
+    pre = str(tmp_path) + '/'
+    random.seed(11)
+    patches.save_random_patches(gt20, d10, d20, pre, NR_CROP=7)
+    a10, a20, agt = (np.load(pre + k + '.npy') for k in ('data10', 'data20', 'data20_gt'))
+    assert a10.shape == (7, 4, 32, 32) and a20.shape == (7, 6, 32, 32) and agt.shape == (7, 6, 32, 32)
+    random.seed(11)                                                     # replay the crops with the oracle's upsampling
+    for i in range(7):
+        x0, y0 = random.randrange(0, 48 - 16), random.randrange(0, 60 - 16)
+        assert np.array_equal(a10[i], np.rollaxis(d10[2 * x0:2 * x0 + 32, 2 * y0:2 * y0 + 32], 2))
+        assert np.array_equal(agt[i], np.rollaxis(gt20[2 * x0:2 * x0 + 32, 2 * y0:2 * y0 + 32], 2))
+        lr = np.rollaxis(d20[x0:x0 + 16, y0:y0 + 16], 2)[None]
+        np.testing.assert_allclose(a20[i], po.interp_patches(lr, (1, 4, 32, 32))[0], rtol=0, atol=2e-3)
+    patches.save_test_patches(d10, d20, pre + 't_', patchSize=32, border=4)
+    t10, t20 = np.load(pre + 't_data10.npy'), np.load(pre + 't_data20.npy')
+    r10, r20 = po.get_test_patches(d10, d20, 32, 4)
+    assert np.array_equal(t10, r10)
+    np.testing.assert_allclose(t20, r20, rtol=0, atol=2e-3)

@@ -123,3 +123,22 @@ def test_dsen2net_oracle_shapes_and_params():
     # zero tail kernel => output is exactly the global skip (DSen2Net.py:41)
     small[-1] = (np.zeros_like(small[-1][0]), small[-1][1])
     assert np.array_equal(no.forward([x10, x20], small), x20)
+
+
+def test_down_pixel_aggr_oracle_against_an_independent_formula():
+    """oracle.downPixelAggr (scipy gaussian_filter + block mean, patches.py:353-371) vs a direct separable convolution
+    with symmetric padding -- pins the restatement of block_reduce and the kernel radius / boundary convention."""
+    from oracle import patches_oracle as po
+    rng = np.random.RandomState(8)
+    img = rng.rand(24, 30, 2) * 1000
+    for s in (2, 6):
+        sigma = 1.0 / s
+        r = int(4.0 * sigma + 0.5)
+        x = np.arange(-r, r + 1)
+        w = np.exp(-0.5 * (x / sigma) ** 2)
+        w /= w.sum()
+        pad = np.pad(img, ((r, r), (r, r), (0, 0)), mode='symmetric')
+        blur = sum(w[i] * pad[i:i + 24, :, :] for i in range(2 * r + 1))
+        blur = sum(w[j] * blur[:, j:j + 30, :] for j in range(2 * r + 1))
+        ref = blur.reshape(24 // s, s, 30 // s, s, 2).mean(axis=(1, 3))
+        np.testing.assert_allclose(po.downPixelAggr(img, s), ref, rtol=1e-12, atol=1e-9)

@@ -191,3 +191,19 @@ def test_missing_weight_file_raises_oserror(env):
             supres.DSen2_20(np.zeros((128, 128, 4), np.float32), np.zeros((64, 64, 6), np.float32))
     finally:
         supres.MDL_PATH = old
+
+
+def test_demo_driver_runs_on_a_scene_file(env, malmo, tmp_path, capsys):
+    """python -m dsen2_b200.demoDSen2 (mirror of testing/demoDSen2.py) on a scene written as HDF5 the way the .mat
+    files store it (arrays transposed), with random weights because the shipped hdf5 weights are missing blobs."""
+    from dsen2_b200 import demoDSen2
+    from dsen2_b200.hdf5 import write_hdf5
+    d10, d20, d60 = malmo
+    crop = lambda a, r: np.ascontiguousarray(a[:240 // r, :240 // r])
+    tree = {'im10': crop(d10, 1).transpose().copy(), 'im20': crop(d20, 2).transpose().copy(),
+            'im60': crop(d60, 6).transpose().copy()}
+    write_hdf5(str(tmp_path / 'S2A_MSIL1C_20170527_T33UUB.mat'), tree, {})
+    rc = demoDSen2.main(['--data', str(tmp_path) + '/', '--random-weights'])
+    out = capsys.readouterr().out
+    assert rc == 0 and out.count('super-resolved') == 2 and '(240, 240, 6)' in out and '(240, 240, 2)' in out
+    assert out.count('skipping') == 5                      # the other scenes of the demo are not in the directory

@@ -134,3 +134,20 @@ def test_weight_file_naming_convention():
     assert supres.weight_file(False, True).endswith('s2_030_lr_1e-05.hdf5')
     assert supres.weight_file(True, False).endswith('s2_033_lr_1e-04.hdf5')
     assert supres.weight_file(True, True).endswith('s2_034_lr_1e-04.hdf5')
+
+
+def test_demo_readh5_and_rmse(fingerprints, capsys):
+    """demoDSen2.py:14-35 mirrors: RMSE formula, readh5 on the shipped Malmoe scene when the reference tree is mounted."""
+    from dsen2_b200 import demoDSen2
+    a = np.arange(12, dtype=np.float32).reshape(3, 4)
+    b = a + np.float32(2)
+    assert demoDSen2.RMSE(a, b) == 2.0 and 'RMSE: 2.0000' in capsys.readouterr().out
+    path = '/root/reference/data/'
+    if not os.path.exists(path + 'S2A_MSIL1C_20170527_T33UUB.mat'):
+        pytest.skip('reference data not mounted')
+    old, demoDSen2.DATA_PATH = demoDSen2.DATA_PATH, path
+    try:
+        d10, d20, d60 = demoDSen2.readh5('S2A_MSIL1C_20170527_T33UUB.mat', im60=True)
+    finally:
+        demoDSen2.DATA_PATH = old
+    assert d10.shape == (600, 600, 4) and d20.shape == (300, 300, 6) and d60.shape == (100, 100, 2) and d10.dtype == np.float32

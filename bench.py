@@ -192,8 +192,8 @@ def run_ours(args):
     T, P, B, r = (args.tile, 192, 12, 6) if run_60 else (args.tile, 128, 8, 2)
     if args.batch <= 0:
         args.batch = supres.default_device_batch(T, P, B)
-    if T % 6:
-        raise SystemExit("--tile must be a multiple of 6")
+    if T % r:
+        raise SystemExit("--tile must be a multiple of %d for the %d m path" % (r, args.path))
     deep = args.model == 'vdsen2'
     shape = ((4, None, None), (6, None, None)) + (((2, None, None),) if run_60 else ())
     model = s2model(shape, num_layers=32 if deep else 6, feature_size=256 if deep else 128, seed=0)

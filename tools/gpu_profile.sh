@@ -4,7 +4,7 @@
 set -u
 TAG=${1:-r01}
 mkdir -p gpurun_out
-SMALL="python bench.py --tile 2240 --steps 1 --warmup 1 --no-cpu-baseline"
+SMALL="python bench.py --tile 2352 --steps 1 --warmup 1 --no-cpu-baseline"
 $SMALL > gpurun_out/${TAG}_plain_small.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/${TAG}_launches.csv $SMALL > gpurun_out/${TAG}_ncu_launches.log 2>&1
 echo "launch list rc=$?"

@@ -8,6 +8,7 @@ forward pass is the tcgen05 implicit-GEMM path behind ``dsen2_s2model_forward`` 
 """
 import ctypes
 import math
+import os
 
 import numpy as np
 
@@ -107,6 +108,13 @@ class S2Model:
         VDSen2 (256 features) runs the single-CTA streaming kernel (csrc/conv_tcgen05.cu)."""
         return self.feature_size == 128 and sum(self.in_channels) <= 16 and self.out_channels <= 16
 
+    @property
+    def trunk_format(self):
+        """How the residual trunk of the fast path lives in HBM between resblocks: 'q8' = the fp16 tensor the next
+        convolution reads + one extra byte per element (19 significant bits, 1024 B/pixel/resblock of traffic; default),
+        'fp32' = a separate fp32 tensor (1536 B/pixel/resblock; ``DSEN2_TRUNK=fp32``, what the training step uses)."""
+        return 'fp32' if os.environ.get('DSEN2_TRUNK', 'q8') == 'fp32' else 'q8'
+
     def _ensure_packed(self, device):
         torch = _capi.require_cuda()
         key = device.index if device.index is not None else torch.cuda.current_device()
@@ -164,9 +172,11 @@ class S2Model:
             F = self.feature_size
             mk = lambda c: torch.empty((n, P, P, c), dtype=torch.float16, device=dev)
             if self.fast_path:
-                buf = dict(xin_hi=mk(64), xin_lo=mk(64), x_hi=mk(F), x_lo=mk(F), t=mk(F),
-                           x32=torch.empty((n, P, (P + 7) // 8, F // 4, 8, 4), dtype=torch.float32,
-                                           device=dev))                      # tile-row-major fp32 trunk
+                buf = dict(xin_hi=mk(64), xin_lo=mk(64), x_hi=mk(F), x_lo=mk(F), t=mk(F))
+                if self.trunk_format == 'fp32':                              # tile-row-major fp32 trunk
+                    buf['x32'] = torch.empty((n, P, (P + 7) // 8, F // 4, 8, 4), dtype=torch.float32, device=dev)
+                else:                                                        # low bytes of the fp16 + 8 bit trunk
+                    buf['xq'] = torch.empty((n, P, (P + 7) // 8, F // 16, 8, 16), dtype=torch.uint8, device=dev)
             else:
                 k_pad = (9 * sum(self.in_channels) + 63) // 64 * 64
                 buf = dict(a0=mk(k_pad), x_hi=mk(F), x_lo=mk(F), t=mk(F), k_pad=k_pad)
@@ -188,9 +198,24 @@ class S2Model:
         """head (if ``first`` is None: from x_in) + resblocks on the buffers; shared by both input forms."""
         lib, ptr, F, L = _capi.lib(), _capi.ptr, self.feature_size, self.num_layers
         x_hi, x_lo, t = buf['x_hi'], buf['x_lo'], buf['t']
+        if self.fast_path and self.trunk_format != 'fp32' and L > 0:
+            # fp16 + 8 bit trunk: x_hi (NHWC, what the next convolution reads) updated in place + one byte per element
+            # (include/dsen2_b200.h, dsen2_conv_resq); the last block hands the tail x_hi, x_lo
+            xq = buf['xq']
+            self._timed(timers, 'conv_head', n, lambda: _capi.check(lib.dsen2_conv_head_q(
+                ptr(buf['xin_hi']), ptr(buf['xin_lo']), ptr(wts[0]), ptr(biases[0]), n, P, P, F, ptr(x_hi), ptr(xq), st),
+                "dsen2_conv_head_q"))
+            for l in range(L):
+                self._timed(timers, 'conv_res1', n, lambda: _capi.check(lib.dsen2_conv3x3(
+                    ptr(x_hi), ptr(wts[1 + 2 * l]), ptr(biases[1 + 2 * l]), n, P, P, F, F, 9, _capi.EPI_RELU, None,
+                    None, 0.0, ptr(t), None, None, None, 0, st), "dsen2_conv3x3(res conv1)"))
+                self._timed(timers, 'conv_res2', n, lambda: _capi.check(lib.dsen2_conv_resq(
+                    ptr(t), ptr(wts[2 + 2 * l]), ptr(biases[2 + 2 * l]), n, P, P, 0.1, ptr(x_hi), ptr(xq),
+                    ptr(x_lo) if l == L - 1 else None, st), "dsen2_conv_resq"))
+            return
         if self.fast_path:
             # fp32 trunk (tile-row-major) updated in place by every resblock; x_lo only for the tail's split operand
-            x32 = buf['x32']
+            x32 = buf.get('x32')
             self._timed(timers, 'conv_head', n, lambda: _capi.check(lib.dsen2_conv_head(
                 ptr(buf['xin_hi']), ptr(buf['xin_lo']), ptr(wts[0]), ptr(biases[0]), n, P, P, F, ptr(x_hi),
                 ptr(x_lo) if L == 0 else None, ptr(x32) if L > 0 else None, st), "dsen2_conv_head"))

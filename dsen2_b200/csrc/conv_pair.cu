@@ -37,7 +37,7 @@ static constexpr int kBoxH = 18;
 static constexpr int kPrefetchTiles = 1;        // L2 prefetch distance of the activation boxes, in tiles of this CTA
 static constexpr int kTrunkPrefetchTiles = 1;   // same for the fp32 trunk lines the RESIDUAL32 epilogue reads
 
-enum { kEpiRelu = 0, kEpiResidual = 1, kEpiTail = 2, kEpiResidual32 = 3, kEpiMask = 4 };
+enum { kEpiRelu = 0, kEpiResidual = 1, kEpiTail = 2, kEpiResidual32 = 3, kEpiMask = 4, kEpiResidualQ = 5, kEpiResidualQLast = 6 };
 
 struct PairParams {
   int n, H, W;
@@ -50,6 +50,7 @@ struct PairParams {
   __half* out_hi;
   __half* out_lo;
   float* x32;              // fp32 trunk, tile-row-major (n, H, ceil(W/8), C/4, 8, 4): RESIDUAL32 in/out, RELU (head) optional out
+  uint8_t* xq;             // low bytes of the fp16+8 trunk, tile-row-major (n, H, ceil(W/8), C/16, 8, 16): RESIDUALQ in/out, head out
   // TAIL
   const __half* skip_hi;   // prepared input (n,H,W,64): centre-tap channels 16..31 hold the network inputs
   const __half* skip_lo;
@@ -58,7 +59,8 @@ struct PairParams {
   float out_mul;
   float* out_f32;
   int pf_a, pf_x, defer;   // tuning knobs (L2 prefetch distances in tiles, deferred fp16-copy store)
-  int debug;               // profiling aid (DSEN2_PAIR_DEBUG): 1 = epilogue only hands TMEM back, 2 = no activation TMA
+  int debug;               // profiling aid (DSEN2_PAIR_DEBUG): 1 = epilogue only hands TMEM back, 2 = no activation TMA,
+                           // RESIDUAL32 only: 4 = no trunk load, 8 = no trunk store, 16 = no fp16 copy store
   int tail_mode;           // 0: NCHW (n,cout,H,W) predictions; 1: stitched HWC canvas
   int first_patch, img_h, img_w, border, grid_ny, grid_nx;
 };
@@ -104,6 +106,18 @@ __device__ __forceinline__ TileXY decode_tile(uint32_t tile, uint32_t tiles_x, u
   t.b = (int)(row / tiles_y);
   t.ty = (int)(row - (uint32_t)t.b * tiles_y);
   return t;
+}
+
+// the persistent loops step through the tile list with a fixed stride: advance (patch, row, column) with carries
+// instead of two divisions per tile
+__device__ __forceinline__ void advance_tile(TileXY& t, const TileXY& step, int tiles_x, int tiles_y) {
+  t.tx += step.tx;
+  const int cx = t.tx >= tiles_x;
+  t.tx -= cx ? tiles_x : 0;
+  t.ty += step.ty + cx;
+  const int cy = t.ty >= tiles_y;
+  t.ty -= cy ? tiles_y : 0;
+  t.b += step.b + cy;
 }
 
 __device__ __forceinline__ int stitch_tile_of(int y, int size, int S, int n) {
@@ -183,6 +197,47 @@ __device__ __forceinline__ void staged_gather(uint32_t stg, const uint4 (&gl)[8]
       for (int q = 0; q < 8; ++q) v[q] = lds128(stg + stg_off(r_own, q));
     }
   }
+}
+
+// ---- fp16 + 8 bit residual trunk ("Q" trunk) ---------------------------------------------------
+// The trunk value x of a resblock chain is kept as the fp16 tensor the next convolution's TMA reads anyway (h) plus ONE
+// extra byte per element: with s = bits(x) + 0x1010, h = fp16 of s truncated to 10 mantissa bits (x rounded to nearest
+// fp16, ties away from zero) and lo = bits 12..5 of s, stored biased by -128 as a signed byte.  Then
+//   bits(x) ~ bits(float(h)) + (lo << 5)          (|error| <= 16 fp32 ulps: 19 significant bits, unbiased)
+// which is pure integer arithmetic on both sides.  For |x| < 2^-14 h is an fp16 subnormal (its truncation point moves up):
+// the code then only keeps x to an absolute 2^-24, and lo is forced to 0 where h is zero.
+// The fp32 trunk costs 1536 B/pixel per resblock of HBM traffic (read t, read + write fp32, write the fp16 copy);
+// this one 1024 (read t, read + write fp16, read + write the bytes).
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+__device__ __forceinline__ uint32_t cvt_rz_f16x2(uint32_t hi_bits, uint32_t lo_bits) {
+  uint32_t d;
+  asm("cvt.rz.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi_bits)), "f"(__uint_as_float(lo_bits)));
+  return d;
+}
+// byte k of w, sign-extended (prmt replicates the sign of the selected byte when bit 3 of a selector nibble is set)
+template <int K>
+__device__ __forceinline__ int sext_byte(uint32_t w) {
+  return (int)prmt(w, 0u, 0x8880u + 0x1111u * K);
+}
+__device__ __forceinline__ float q_decode(float hf, int lo) {
+  return __uint_as_float(__float_as_uint(hf) + (uint32_t)(lo << 5));
+}
+// four trunk values -> two packed fp16 pairs + one word of low bytes
+__device__ __forceinline__ void q_encode4(float x0, float x1, float x2, float x3, uint32_t& h01, uint32_t& h23, uint32_t& lo) {
+  const uint32_t s0 = __float_as_uint(x0) + 0x1010u, s1 = __float_as_uint(x1) + 0x1010u;
+  const uint32_t s2 = __float_as_uint(x2) + 0x1010u, s3 = __float_as_uint(x3) + 0x1010u;
+  h01 = cvt_rz_f16x2(s1, s0);
+  h23 = cvt_rz_f16x2(s3, s2);
+  const uint32_t p01 = prmt(s0, s1, 0x5410u) >> 5, p23 = prmt(s2, s3, 0x5410u) >> 5;   // bits 12..5 land in bytes 0 and 2
+  // |x| < 2^-24 gives h = +-0: there is no binade for the byte to refine (a negative one would borrow through the sign
+  // bit on decode), so it must be 0.  0xffff per zero half -> 0xff per byte.
+  const uint32_t z01 = __heq2_mask(*reinterpret_cast<const __half2*>(&h01), __half2half2(__ushort_as_half(0)));
+  const uint32_t z23 = __heq2_mask(*reinterpret_cast<const __half2*>(&h23), __half2half2(__ushort_as_half(0)));
+  lo = (prmt(p01, p23, 0x6420u) ^ 0x80808080u) & ~prmt(z01, z23, 0x6420u);
 }
 
 template <class Cfg>
@@ -359,8 +414,14 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
     uint4 vh_prev[8];
     EpiGeom g_prev;
     bool have_prev = false;
-    for (uint32_t pt = pair; pt < pair_tiles; pt += npairs) {
-      const TileXY tc = decode_tile(2 * pt + rank, p.tiles_x, p.tiles_y);
+    // current tile and the tile whose epilogue operands are prefetched into L2 (pf_dist iterations ahead)
+    const TileXY tstep = decode_tile(2 * npairs, p.tiles_x, p.tiles_y);
+    const uint32_t pf_dist = (Cfg::EPI == kEpiResidual32 || Cfg::EPI == kEpiResidualQ || Cfg::EPI == kEpiResidualQLast)
+                                 ? (uint32_t)max(p.pf_x, 1) : 1u;
+    TileXY tc = decode_tile(2 * pair + rank, p.tiles_x, p.tiles_y);
+    TileXY tn = decode_tile(2 * (pair + pf_dist * npairs) + rank, p.tiles_x, p.tiles_y);
+    for (uint32_t pt = pair; pt < pair_tiles;
+         pt += npairs, advance_tile(tc, tstep, p.tiles_x, p.tiles_y), advance_tile(tn, tstep, p.tiles_x, p.tiles_y)) {
       const int b = tc.b;
       const int y = tc.ty * 16 + (row >> 3);
       const int x = tc.tx * 8 + (row & 7);
@@ -436,7 +497,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
         float* xp = p.x32 + ((((long long)b * p.H + y) * p.tiles_x + tc.tx) * (Cfg::CH / 4) + half * (CPT / 4)) * cpitch +
                     (row & 7) * 4;
         float4 xr[CPT / 4];
-        if (valid) {
+        if (valid && !(p.debug & 4)) {
 #pragma unroll
           for (int q = 0; q < CPT / 4; ++q) xr[q] = *reinterpret_cast<const float4*>(xp + q * cpitch);
         } else {
@@ -444,7 +505,6 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
           for (int q = 0; q < CPT / 4; ++q) xr[q] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         if (p.pf_x > 0 && pt + p.pf_x * npairs < pair_tiles) {   // a later tile's trunk lines -> L2 (64 lines per warp, 2 per lane)
-          const TileXY tn = decode_tile(2 * (pt + p.pf_x * npairs) + rank, p.tiles_x, p.tiles_y);
           const int ny = tn.ty * 16 + wq * 4 + (lane >> 3);
           if (tn.b < p.n && ny < p.H) {
             const float* np = p.x32 + ((((long long)tn.b * p.H + ny) * p.tiles_x + tn.tx) * (Cfg::CH / 4) + half * (CPT / 4) +
@@ -480,13 +540,15 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
-        if (valid) {
+        if (valid && !(p.debug & 8)) {
 #pragma unroll
           for (int q = 0; q < CPT / 4; ++q) *reinterpret_cast<float4*>(xp + q * cpitch) = xr[q];
         }
         g_prev = g;
         have_prev = true;
-        if (!p.defer || p.out_lo != nullptr) {
+        if (p.debug & 16) {
+          have_prev = false;
+        } else if (!p.defer || p.out_lo != nullptr) {
           staged_store(stg, vh, p.out_hi, g, lane);
           have_prev = false;
         }
@@ -502,6 +564,90 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
           }
           staged_store(stg, vh, p.out_lo, g, lane);
         }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      } else if constexpr (Cfg::EPI == kEpiResidualQ || Cfg::EPI == kEpiResidualQLast) {
+        // ------------------------------------------------------------------ resblock output, fp16 + 8 bit trunk
+        // x <- x + scale * (conv + bias) (DSen2Net.py:13,15) on the trunk held as x_hi (NHWC fp16, updated in place: this
+        // kernel's TMA reads t, never x_hi) + one byte per element (see q_encode4).  The LAST block of the chain writes
+        // x_hi = fp16(x) and x_lo = fp16(x - x_hi) instead: the tail's split operand (and nothing reads the bytes again).
+        constexpr int CPT = Cfg::CH / 2;
+        constexpr bool LAST = Cfg::EPI == kEpiResidualQLast;
+        static_assert(CPT == 64 && !Cfg::SPLIT, "Q-trunk epilogue: 64 channels per thread");
+        const uint32_t stg = smem_u32(s_stg) + (uint32_t)(warp * 1024);
+        const EpiGeom g = epi_geom<Cfg>(p, tc, wq, half * CPT);
+        uint4 vh[8];
+        uint4 lq[CPT / 16];
+        {
+          uint4 gh[8];
+          coalesced_load(gh, p.out_hi, g, lane);
+          // low bytes: (n, H, W/8, C/16, 8 px, 16 ch) -- thread = pixel reads 16 B, a tile row of one chunk is one 128 B line
+          uint8_t* qp = p.xq + ((((long long)b * p.H + y) * p.tiles_x + tc.tx) * (Cfg::CH / 16) + half * (CPT / 16)) * 128 +
+                        (row & 7) * 16;
+          if (valid) {
+#pragma unroll
+            for (int q = 0; q < CPT / 16; ++q) lq[q] = *reinterpret_cast<const uint4*>(qp + q * 128);
+          } else {
+#pragma unroll
+            for (int q = 0; q < CPT / 16; ++q) lq[q] = make_uint4(0, 0, 0, 0);
+          }
+          if (p.pf_x > 0 && pt + p.pf_x * npairs < pair_tiles) {   // a later tile's trunk lines -> L2
+              prefetch_rows(p.out_hi, epi_geom<Cfg>(p, tn, wq, half * CPT), lane);
+            const int ny = tn.ty * 16 + wq * 4 + (lane >> 2);      // 4 rows x 4 byte-chunk lines per warp
+            if (lane < 16 && tn.b < p.n && ny < p.H)
+              prefetch_l2(p.xq + ((((long long)tn.b * p.H + ny) * p.tiles_x + tn.tx) * (Cfg::CH / 16) + half * (CPT / 16) +
+                                  (lane & 3)) * 128);
+          }
+          staged_gather(stg, gh, vh, lane);
+        }
+        uint4 vl[LAST ? 8 : 1];
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll
+        for (int chunk = 0; chunk < CPT / 32; ++chunk) {
+          const int c0 = half * CPT + chunk * 32;
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c0, r);
+          tmem_ld_wait();
+          uint32_t* hw = reinterpret_cast<uint32_t*>(vh) + chunk * 16;
+          uint32_t* qw = reinterpret_cast<uint32_t*>(lq) + chunk * 8;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bq = lds_f4(s_bias_addr + (uint32_t)(c0 + j) * 4);   // broadcast LDS.128
+            const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&hw[j >> 1]));
+            const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&hw[(j >> 1) + 1]));
+            const uint32_t w = qw[j >> 2];
+            const float x0 = fmaf(__uint_as_float(r[j]) + bq.x, p.res_scale, q_decode(f01.x, sext_byte<0>(w)));
+            const float x1 = fmaf(__uint_as_float(r[j + 1]) + bq.y, p.res_scale, q_decode(f01.y, sext_byte<1>(w)));
+            const float x2 = fmaf(__uint_as_float(r[j + 2]) + bq.z, p.res_scale, q_decode(f23.x, sext_byte<2>(w)));
+            const float x3 = fmaf(__uint_as_float(r[j + 3]) + bq.w, p.res_scale, q_decode(f23.y, sext_byte<3>(w)));
+            if constexpr (LAST) {
+              const __half2 h0 = __floats2half2_rn(x0, x1), h1 = __floats2half2_rn(x2, x3);
+              const float2 g0 = __half22float2(h0), g1 = __half22float2(h1);
+              const __half2 l0 = __floats2half2_rn(x0 - g0.x, x1 - g0.y), l1 = __floats2half2_rn(x2 - g1.x, x3 - g1.y);
+              uint32_t* lw = reinterpret_cast<uint32_t*>(vl) + chunk * 16;
+              hw[j >> 1] = *reinterpret_cast<const uint32_t*>(&h0);
+              hw[(j >> 1) + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+              lw[j >> 1] = *reinterpret_cast<const uint32_t*>(&l0);
+              lw[(j >> 1) + 1] = *reinterpret_cast<const uint32_t*>(&l1);
+            } else {
+              q_encode4(x0, x1, x2, x3, hw[j >> 1], hw[(j >> 1) + 1], qw[j >> 2]);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+        if constexpr (!LAST) {
+          if (valid) {
+            uint8_t* qp = p.xq + ((((long long)b * p.H + y) * p.tiles_x + tc.tx) * (Cfg::CH / 16) + half * (CPT / 16)) * 128 +
+                          (row & 7) * 16;
+#pragma unroll
+            for (int q = 0; q < CPT / 16; ++q) *reinterpret_cast<uint4*>(qp + q * 128) = lq[q];
+          }
+        }
+        staged_store(stg, vh, p.out_hi, g, lane);
+        if constexpr (LAST) staged_store(stg, vl, p.out_lo, g, lane);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         continue;
       } else {
@@ -522,7 +668,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
             coalesced_load(gh, p.res_hi, g, lane);
             coalesced_load(gl, p.res_lo, g, lane);
             if (pt + npairs < pair_tiles) {           // pull the NEXT tile's residual into L2 a whole tile time ahead
-              const EpiGeom gn = epi_geom<Cfg>(p, decode_tile(2 * (pt + npairs) + rank, p.tiles_x, p.tiles_y), wq, cb);
+              const EpiGeom gn = epi_geom<Cfg>(p, tn, wq, cb);
               prefetch_rows(p.res_hi, gn, lane);
               prefetch_rows(p.res_lo, gn, lane);
             }
@@ -533,7 +679,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
             uint4 gm[8];
             coalesced_load(gm, p.res_hi, g, lane);
             if (pt + npairs < pair_tiles) {
-              const EpiGeom gn = epi_geom<Cfg>(p, decode_tile(2 * (pt + npairs) + rank, p.tiles_x, p.tiles_y), wq, cb);
+              const EpiGeom gn = epi_geom<Cfg>(p, tn, wq, cb);
               prefetch_rows(p.res_hi, gn, lane);
             }
             staged_gather(stg, gm, vh, lane);
@@ -562,6 +708,18 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
             for (int j = 0; j < 32; j += 4) {
               const float4 bq = lds_f4(s_bias_addr + (uint32_t)(c0 + j) * 4);   // broadcast LDS.128
               const float bb[4] = {bq.x, bq.y, bq.z, bq.w};
+              if constexpr (Cfg::EPI == kEpiRelu && Cfg::SPLIT) {
+                if (p.xq != nullptr) {                     // head: seed the fp16 + 8 bit trunk (x_hi + low bytes)
+                  uint32_t* qw = reinterpret_cast<uint32_t*>(vl);      // vl is free: the Q-trunk head has no x_lo output
+                  q_encode4(fmaxf(__uint_as_float(r[j]) + bq.x, 0.f), fmaxf(__uint_as_float(r[j + 1]) + bq.y, 0.f),
+                            fmaxf(__uint_as_float(r[j + 2]) + bq.z, 0.f), fmaxf(__uint_as_float(r[j + 3]) + bq.w, 0.f),
+                            hw[j >> 1], hw[(j >> 1) + 1], qw[(j >> 2) & 3]);
+                  if ((j & 12) == 12 && valid)
+                    *reinterpret_cast<uint4*>(p.xq + ((((long long)b * p.H + y) * p.tiles_x + tc.tx) * (Cfg::CH / 16) +
+                                                      ((c0 + j) >> 4)) * 128 + (row & 7) * 16) = vl[0];
+                  continue;
+                }
+              }
               if (Cfg::EPI == kEpiRelu && p.x32 != nullptr && valid) {   // first layer: seed the fp32 trunk (tile-row-major)
                 const float4 xv = make_float4(fmaxf(__uint_as_float(r[j]) + bq.x, 0.f), fmaxf(__uint_as_float(r[j + 1]) + bq.y, 0.f),
                                               fmaxf(__uint_as_float(r[j + 2]) + bq.z, 0.f), fmaxf(__uint_as_float(r[j + 3]) + bq.w, 0.f));
@@ -631,6 +789,8 @@ using CfgRelu = PairCfg<128, false, 1, 2, 9, 4, 3, kEpiRelu>;
 using CfgResidual = PairCfg<128, false, 1, 2, 9, 4, 3, kEpiResidual>;
 using CfgResidual32 = PairCfg<128, false, 1, 2, 9, 4, 3, kEpiResidual32>;
 using CfgMask = PairCfg<128, false, 1, 2, 9, 4, 3, kEpiMask>;
+using CfgResidualQ = PairCfg<128, false, 1, 2, 9, 4, 3, kEpiResidualQ>;
+using CfgResidualQLast = PairCfg<128, false, 1, 2, 9, 4, 3, kEpiResidualQLast>;
 // VDSen2 trunk (256 -> 256): 1.18 MB of weights per layer cannot be resident -- ring of 8 streamed [tap][k-block] slabs
 using CfgRelu256 = PairCfg<256, false, 1, 4, 9, 4, 3, kEpiRelu, 8>;
 using CfgResidual256 = PairCfg<256, false, 1, 4, 9, 4, 3, kEpiResidual, 8>;
@@ -757,17 +917,18 @@ extern "C" int dsen2_conv_res32(const void* d_in, const void* d_w, const float* 
   return launch_pair<CfgResidual32>(a0, a1, w, p, sms, (cudaStream_t)stream, "conv_pair<residual32>");
 }
 
-extern "C" int dsen2_conv_head(const void* d_xin_hi, const void* d_xin_lo, const void* d_w, const float* d_bias,
-                               int n, int H, int W, int feature_size, void* d_out_hi, void* d_out_lo,
-                               float* d_trunk32, void* stream) {
-  DSEN2_REQUIRE(d_xin_hi && d_xin_lo && d_w && d_bias && d_out_hi, DSEN2_E_BADARG, "dsen2_conv_head: null pointer");
-  DSEN2_REQUIRE(((uintptr_t)d_trunk32 % 16) == 0, DSEN2_E_ALIGN, "dsen2_conv_head: trunk must be 16-byte aligned");
-  DSEN2_REQUIRE(feature_size == 128, DSEN2_E_BADARG, "dsen2_conv_head: the pair kernel serves feature_size 128 (got %d)",
+static int head_common(const char* name, const void* d_xin_hi, const void* d_xin_lo, const void* d_w, const float* d_bias,
+                       int n, int H, int W, int feature_size, void* d_out_hi, void* d_out_lo, float* d_trunk32,
+                       void* d_trunk_lo8, void* stream) {
+  DSEN2_REQUIRE(d_xin_hi && d_xin_lo && d_w && d_bias && d_out_hi, DSEN2_E_BADARG, "%s: null pointer", name);
+  DSEN2_REQUIRE(((uintptr_t)d_trunk32 % 16) == 0 && ((uintptr_t)d_trunk_lo8 % 16) == 0, DSEN2_E_ALIGN,
+                "%s: trunk must be 16-byte aligned", name);
+  DSEN2_REQUIRE(feature_size == 128, DSEN2_E_BADARG, "%s: the pair kernel serves feature_size 128 (got %d)", name,
                 feature_size);
-  DSEN2_REQUIRE(n >= 0 && H > 0 && W > 0, DSEN2_E_BADARG, "dsen2_conv_head: bad shape");
+  DSEN2_REQUIRE(n >= 0 && H > 0 && W > 0, DSEN2_E_BADARG, "%s: bad shape", name);
   DSEN2_REQUIRE(((uintptr_t)d_xin_hi % 16) == 0 && ((uintptr_t)d_xin_lo % 16) == 0 && ((uintptr_t)d_w % 16) == 0 &&
                     ((uintptr_t)d_out_hi % 16) == 0 && ((uintptr_t)d_out_lo % 16) == 0,
-                DSEN2_E_ALIGN, "dsen2_conv_head: pointers must be 16-byte aligned");
+                DSEN2_E_ALIGN, "%s: pointers must be 16-byte aligned", name);
   if (n == 0) return 0;
   int sms = 0;
   int rc = device_sm_count_and_check(&sms);
@@ -777,10 +938,50 @@ extern "C" int dsen2_conv_head(const void* d_xin_hi, const void* d_xin_lo, const
   p.bias = d_bias;
   p.out_hi = (__half*)d_out_hi; p.out_lo = (__half*)d_out_lo;
   p.x32 = d_trunk32;
+  p.xq = (uint8_t*)d_trunk_lo8;
   CUtensorMap a0, a1, w;
   rc = make_maps<CfgHead>(&a0, &a1, &w, d_xin_hi, d_xin_lo, d_w, n, H, W);
   if (rc) return rc;
   return launch_pair<CfgHead>(a0, a1, w, p, sms, (cudaStream_t)stream, "conv_pair<head>");
+}
+
+extern "C" int dsen2_conv_head(const void* d_xin_hi, const void* d_xin_lo, const void* d_w, const float* d_bias,
+                               int n, int H, int W, int feature_size, void* d_out_hi, void* d_out_lo,
+                               float* d_trunk32, void* stream) {
+  return head_common("dsen2_conv_head", d_xin_hi, d_xin_lo, d_w, d_bias, n, H, W, feature_size, d_out_hi, d_out_lo,
+                     d_trunk32, nullptr, stream);
+}
+
+extern "C" int dsen2_conv_head_q(const void* d_xin_hi, const void* d_xin_lo, const void* d_w, const float* d_bias,
+                                 int n, int H, int W, int feature_size, void* d_x_hi, void* d_trunk_lo8, void* stream) {
+  DSEN2_REQUIRE(d_trunk_lo8, DSEN2_E_BADARG, "dsen2_conv_head_q: null pointer");
+  return head_common("dsen2_conv_head_q", d_xin_hi, d_xin_lo, d_w, d_bias, n, H, W, feature_size, d_x_hi, nullptr, nullptr,
+                     d_trunk_lo8, stream);
+}
+
+extern "C" int dsen2_conv_resq(const void* d_in, const void* d_w, const float* d_bias, int n, int H, int W,
+                               float res_scale, void* d_x_hi, void* d_trunk_lo8, void* d_out_lo, void* stream) {
+  DSEN2_REQUIRE(d_in && d_w && d_bias && d_x_hi && d_trunk_lo8, DSEN2_E_BADARG, "dsen2_conv_resq: null pointer");
+  DSEN2_REQUIRE(n >= 0 && H > 0 && W > 0, DSEN2_E_BADARG, "dsen2_conv_resq: bad shape");
+  DSEN2_REQUIRE(d_in != d_x_hi, DSEN2_E_BADARG, "dsen2_conv_resq: the convolution input must not alias x_hi (updated in place)");
+  DSEN2_REQUIRE(((uintptr_t)d_in % 16) == 0 && ((uintptr_t)d_w % 16) == 0 && ((uintptr_t)d_trunk_lo8 % 16) == 0 &&
+                    ((uintptr_t)d_x_hi % 16) == 0 && ((uintptr_t)d_out_lo % 16) == 0,
+                DSEN2_E_ALIGN, "dsen2_conv_resq: pointers must be 16-byte aligned");
+  if (n == 0) return 0;
+  int sms = 0;
+  int rc = device_sm_count_and_check(&sms);
+  if (rc) return rc;
+  PairParams p{};
+  if ((rc = fill_tiles(p, n, H, W)) != 0) return rc;
+  p.bias = d_bias;
+  p.res_scale = res_scale;
+  p.xq = (uint8_t*)d_trunk_lo8;
+  p.out_hi = (__half*)d_x_hi; p.out_lo = (__half*)d_out_lo;
+  CUtensorMap a0, a1, w;
+  rc = make_maps<CfgResidualQ>(&a0, &a1, &w, d_in, nullptr, d_w, n, H, W);
+  if (rc) return rc;
+  if (d_out_lo) return launch_pair<CfgResidualQLast>(a0, a1, w, p, sms, (cudaStream_t)stream, "conv_pair<residualq,last>");
+  return launch_pair<CfgResidualQ>(a0, a1, w, p, sms, (cudaStream_t)stream, "conv_pair<residualq>");
 }
 
 static int tail_common(PairParams& p, const void* d_x_hi, const void* d_x_lo, const void* d_w, const float* d_bias,

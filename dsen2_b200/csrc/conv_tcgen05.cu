@@ -407,9 +407,9 @@ static int head_k_pad(int in_channels) { return (9 * in_channels + 63) / 64 * 64
 extern "C" size_t dsen2_s2model_workspace_bytes(int n, int P, int in_channels, int feature_size) {
   if (n <= 0 || P <= 0 || in_channels <= 0 || feature_size <= 0) return 0;
   const size_t pix = (size_t)n * P * P;
-  if (feature_size == 128)   // x_in hi/lo (64 ch) + trunk hi/lo + resblock intermediate + fp32 trunk
+  if (feature_size == 128)   // x_in hi/lo (64 ch) + trunk hi/lo + resblock intermediate + low bytes of the fp16+8 trunk
     return 2 * align_up(pix * 64 * 2, 1024) + 3 * align_up(pix * feature_size * 2, 1024) +
-           align_up((size_t)n * P * ((P + 7) / 8 * 8) * feature_size * 4, 1024) + 1024;
+           align_up((size_t)n * P * ((P + 7) / 8 * 8) * feature_size, 1024) + 1024;
   return align_up(pix * head_k_pad(in_channels) * 2, 1024) + 3 * align_up(pix * feature_size * 2, 1024) + 1024;
 }
 
@@ -449,20 +449,22 @@ extern "C" int dsen2_s2model_forward(const float* const* d_x, const int* channel
     ws += align_up(pix * 128 * 2, 1024);
     void* t = ws;
     ws += align_up(pix * 128 * 2, 1024);
-    float* x32 = reinterpret_cast<float*>(ws);
+    void* xq = ws;               // low bytes of the fp16 + 8 bit trunk, tile-row-major (dsen2_conv_resq)
     rc = dsen2_prep_from_patches(d_x[0], channels[0], d_x[1], channels[1], n_inputs == 3 ? d_x[2] : nullptr,
                                  n_inputs == 3 ? channels[2] : 0, n, P, xin_hi, xin_lo, stream);
     if (rc) return rc;
     // the fp16 x_lo is only needed by the tail: the last trunk-producing layer writes it
-    rc = dsen2_conv_head(xin_hi, xin_lo, d_weights[0], d_bias[0], n, P, P, 128, x_hi, num_layers == 0 ? x_lo : nullptr,
-                         num_layers == 0 ? nullptr : x32, stream);
+    if (num_layers == 0)
+      rc = dsen2_conv_head(xin_hi, xin_lo, d_weights[0], d_bias[0], n, P, P, 128, x_hi, x_lo, nullptr, stream);
+    else
+      rc = dsen2_conv_head_q(xin_hi, xin_lo, d_weights[0], d_bias[0], n, P, P, 128, x_hi, xq, stream);
     if (rc) return rc;
     for (int l = 0; l < num_layers; ++l) {
       rc = dsen2_conv3x3(x_hi, d_weights[1 + 2 * l], d_bias[1 + 2 * l], n, P, P, 128, 128, 9, DSEN2_EPI_RELU, nullptr,
                          nullptr, 0.f, t, nullptr, nullptr, nullptr, 0, stream);
       if (rc) return rc;
-      rc = dsen2_conv_res32(t, d_weights[2 + 2 * l], d_bias[2 + 2 * l], n, P, P, 0.1f, x32, x_hi,
-                            l == num_layers - 1 ? x_lo : nullptr, stream);
+      rc = dsen2_conv_resq(t, d_weights[2 + 2 * l], d_bias[2 + 2 * l], n, P, P, 0.1f, x_hi, xq,
+                           l == num_layers - 1 ? x_lo : nullptr, stream);
       if (rc) return rc;
     }
     return dsen2_conv_tail(x_hi, x_lo, d_weights[2 * num_layers + 1], d_bias[2 * num_layers + 1], xin_hi, xin_lo,

@@ -175,6 +175,24 @@ int dsen2_conv_head(const void* d_xin_hi, const void* d_xin_lo, const void* d_w,
 int dsen2_conv_res32(const void* d_in, const void* d_w, const float* d_bias, int n, int H, int W,
                      float res_scale, float* d_trunk32, void* d_out_hi, void* d_out_lo, void* stream);
 
+/* The same two layers on the COMPACT trunk the inference path uses (fp16 + 8 bits, 19 significant bits):
+ * the trunk value x is held as the NHWC fp16 tensor x_hi the next convolution reads anyway plus one signed
+ * byte per element, lo, in tile-row-major layout (n, H, ceil(W/8), F/16, 8, 16): element (n,y,x,c) at
+ *   ((((n*H + y)*ceil(W/8) + x/8)*(F/16) + c/16)*8 + x%8)*16 + c%16.
+ * With s = bits(x) + 0x1010: x_hi = fp16 of s truncated (x rounded to the nearest fp16, ties away from zero),
+ * lo = ((s >> 5) & 0xff) - 128, and a reader recovers bits(x) ~ bits(float(x_hi)) + (lo << 5) (|error| <= 16 fp32
+ * ulps).  Below 2^-14 x_hi is an fp16 subnormal and the pair only keeps x to an absolute 2^-24; lo is 0 where x_hi
+ * is zero.  A resblock then moves 1024 B/pixel through HBM instead of the 1536 of the fp32 trunk above.
+ *   dsen2_conv_head_q:  x = relu(conv(x_in) + bias)  ->  d_x_hi, d_trunk_lo8                (DSen2Net.py:29)
+ *   dsen2_conv_resq:    x <- x + res_scale * (conv3x3(d_in) + bias), in place               (DSen2Net.py:12-15)
+ *                       d_out_lo != NULL marks the LAST block: x_hi <- fp16(x) (round to nearest even) and
+ *                       d_out_lo <- fp16(x - x_hi) NHWC for dsen2_conv_tail; d_trunk_lo8 is then only read.
+ * d_in must not alias d_x_hi.  feature_size 128 only.                                                       */
+int dsen2_conv_head_q(const void* d_xin_hi, const void* d_xin_lo, const void* d_w, const float* d_bias,
+                      int n, int H, int W, int feature_size, void* d_x_hi, void* d_trunk_lo8, void* stream);
+int dsen2_conv_resq(const void* d_in, const void* d_w, const float* d_bias, int n, int H, int W,
+                    float res_scale, void* d_x_hi, void* d_trunk_lo8, void* d_out_lo, void* stream);
+
 /* Conv2D(cout, 3x3) + Add(last input) (DSen2Net.py:35,38,41) on the trunk (hi, lo).  The global skip is
  * read from x_in (centre tap, bands skip_ch0 .. skip_ch0+cout).  Output: NCHW fp32 predictions
  * (n, cout, H, W) -- what model.predict returns.                                                  */

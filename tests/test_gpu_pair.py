@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 from cases import CASES20, CASES60, synth
+from qtrunk import NORMAL, q_decode as _q_decode, q_encode as _q_encode, q_from_tiles as _q_from_tiles, q_to_tiles as _q_to_tiles
 
 pytestmark = pytest.mark.gpu
 
@@ -294,3 +295,81 @@ def test_conv_res32_fp32_trunk_update(env, shape, want_lo):
     if want_lo:
         exp_lo = (got - got.astype(np.float16).astype(np.float32)).astype(np.float16)
         assert np.array_equal(lo.cpu().numpy().view(np.uint16), exp_lo.view(np.uint16))
+
+
+# ---- fp16 + 8 bit trunk (include/dsen2_b200.h: dsen2_conv_head_q / dsen2_conv_resq) ---------------------------------
+@pytest.mark.parametrize('shape', [(2, 32, 32), (1, 128, 128), (3, 40, 24), (1, 8, 200), (5, 16, 8)])
+def test_conv_head_q_seeds_the_trunk(env, shape):
+    torch, _capi, lib = env
+    n, H, W = shape
+    F, C = 128, 10
+    rng = np.random.RandomState(H + W)
+    xcat = rng.uniform(0, 5, size=(n, C, H, W)).astype(np.float32)
+    xp = np.zeros((n, H, W + 2, 16), np.float32)
+    xp[:, :, 1:W + 1, :C] = xcat.transpose(0, 2, 3, 1)
+    full = np.concatenate([xp[:, :, t:t + W, :] for t in range(3)] + [np.zeros((n, H, W, 16), np.float32)], axis=-1)
+    hi, lo = _split(full)
+    lim = np.sqrt(6.0 / (9 * C))
+    w = rng.uniform(-lim, lim, size=(3, 3, C, F)).astype(np.float32)
+    bias = (rng.randn(F) * 0.1).astype(np.float32)
+    tw = torch.empty((3, 2 * F, 64), dtype=torch.float16, device='cuda')
+    _capi.check(lib.dsen2_pack_head_weights(_capi.ptr(torch.from_numpy(w).cuda()), C, F, _capi.ptr(tw),
+                                            _capi.stream_ptr()), 'pack head')
+    thi, tlo, tb = torch.from_numpy(hi).cuda(), torch.from_numpy(lo).cuda(), torch.from_numpy(bias).cuda()
+    ohi = torch.zeros((n, H, W, F), dtype=torch.float16, device='cuda')
+    oq = torch.full((n, H, W // 8, F // 16, 8, 16), 77, dtype=torch.int8, device='cuda')
+    _capi.check(lib.dsen2_conv_head_q(_capi.ptr(thi), _capi.ptr(tlo), _capi.ptr(tw), _capi.ptr(tb), n, H, W, F,
+                                      _capi.ptr(ohi), _capi.ptr(oq), _capi.stream_ptr()), 'conv head q')
+    torch.cuda.synchronize()
+    ref = np.maximum(_conv64(xcat.transpose(0, 2, 3, 1), w, bias), 0)
+    h, q = ohi.cpu().numpy(), _q_from_tiles(oq.cpu().numpy())
+    got = _q_decode(h, q)
+    np.testing.assert_allclose(got, ref, rtol=2e-5, atol=2e-5)
+    ok = np.abs(got) >= 2 * NORMAL                                                      # codes are fixed points
+    h2, q2 = _q_encode(got[ok])
+    assert np.array_equal(h2.view(np.uint16), h[ok].view(np.uint16)) and np.array_equal(q2, q[ok])
+
+
+@pytest.mark.parametrize('shape', [(2, 32, 32), (1, 128, 128), (3, 40, 24), (1, 8, 200), (2, 192, 192)])
+@pytest.mark.parametrize('last', [False, True])
+def test_conv_resq_trunk_update(env, shape, last):
+    """x <- x + 0.1 * (conv(t) + b) on the fp16 + 8 bit trunk, in place; the last block emits x_hi, x_lo for the tail."""
+    torch, _capi, lib = env
+    n, H, W = shape
+    F = 128
+    rng = np.random.RandomState(H + 5 * W)
+    t = np.maximum(rng.randn(n, H, W, F), 0).astype(np.float16)
+    x = rng.randn(n, H, W, F).astype(np.float32)
+    x[0, 0, :, :4] = 0                                       # exact zeros stay exact zeros
+    lim = np.sqrt(6.0 / (9 * F))
+    w = rng.uniform(-lim, lim, size=(3, 3, F, F)).astype(np.float32)
+    bias = (rng.randn(F) * 0.1).astype(np.float32)
+    tw = torch.empty((9, F, F), dtype=torch.float16, device='cuda')
+    _capi.check(lib.dsen2_pack_conv_weights(_capi.ptr(torch.from_numpy(w).cuda()), F, F, F, F, 0, _capi.ptr(tw), None,
+                                            _capi.stream_ptr()), 'pack')
+    h0, q0 = _q_encode(x)
+    x_seen = _q_decode(h0, q0)
+    thi, tq = torch.from_numpy(h0).cuda(), torch.from_numpy(_q_to_tiles(q0)).cuda()
+    tt, tb = torch.from_numpy(t).cuda(), torch.from_numpy(bias).cuda()
+    lo = torch.zeros((n, H, W, F), dtype=torch.float16, device='cuda') if last else None
+    _capi.check(lib.dsen2_conv_resq(_capi.ptr(tt), _capi.ptr(tw), _capi.ptr(tb), n, H, W, 0.1, _capi.ptr(thi),
+                                    _capi.ptr(tq), _capi.ptr(lo), _capi.stream_ptr()), 'conv resq')
+    torch.cuda.synchronize()
+    ref = x_seen.astype(np.float64) + 0.1 * _conv64(t.astype(np.float64), w.astype(np.float16).astype(np.float64), bias)
+    h = thi.cpu().numpy()
+    if last:
+        got = h.astype(np.float64) + lo.cpu().numpy().astype(np.float64)
+        np.testing.assert_allclose(got, ref, rtol=2e-5, atol=2e-5)
+        # x_hi = fp16(x): re-rounding hi + lo differs only where x sits within 2^-22 of a rounding tie (~2^-11 of the elements)
+        assert np.mean(got.astype(np.float32).astype(np.float16).view(np.uint16) == h.view(np.uint16)) > 0.999
+        assert np.array_equal(_q_from_tiles(tq.cpu().numpy()), q0)                       # bytes only read
+    else:
+        q = _q_from_tiles(tq.cpu().numpy())
+        got = _q_decode(h, q)
+        np.testing.assert_allclose(got, ref, rtol=2e-5, atol=2e-5)
+        ok = np.abs(got) >= 2 * NORMAL
+        h2, q2 = _q_encode(got[ok])
+        assert np.array_equal(h2.view(np.uint16), h[ok].view(np.uint16)) and np.array_equal(q2, q[ok])
+        assert not got[0, 0, :, :4].any() or np.abs(ref[0, 0, :, :4]).min() > 0        # no spurious zeros
+    assert lib.dsen2_conv_resq(_capi.ptr(thi), _capi.ptr(tw), _capi.ptr(tb), n, H, W, 0.1, _capi.ptr(thi),
+                               _capi.ptr(tq), None, _capi.stream_ptr()) == -1           # aliasing is refused

@@ -5,6 +5,8 @@ import re
 import numpy as np
 import pytest
 
+from qtrunk import NORMAL, q_decode, q_encode
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -151,3 +153,22 @@ def test_demo_readh5_and_rmse(fingerprints, capsys):
     finally:
         demoDSen2.DATA_PATH = old
     assert d10.shape == (600, 600, 4) and d20.shape == (300, 300, 6) and d60.shape == (100, 100, 2) and d10.dtype == np.float32
+
+
+def test_q_trunk_code_properties():
+    """fp16 + 8 bit trunk code (include/dsen2_b200.h): 19 significant bits, unbiased, codes are fixed points."""
+    rng = np.random.RandomState(3)
+    x = np.concatenate([rng.randn(4096) * s for s in (1e-7, 1e-4, 1e-2, 1.0, 300.0)] +
+                       [np.array([0.0, -0.0, 2.0 ** -14, 2.0 ** -24, 1e-9, -1e-9, 1.0, -1.0, 65000.0, 0.99999994,
+                                  1.0009765])]).astype(np.float32)
+    h, lo = q_encode(x)
+    y = q_decode(h, lo)
+    assert np.isfinite(y).all()
+    big = np.abs(x) >= NORMAL
+    assert np.abs(y[big].astype(np.float64) / x[big] - 1).max() < 2.0 ** -18          # 19 significant bits
+    assert np.abs(y[~big].astype(np.float64) - x[~big]).max() <= 2.0 ** -24            # subnormal x_hi: absolute
+    assert (y[x == 0] == 0).all()
+    assert np.abs(h.astype(np.float64) - x)[big].max() <= np.abs(x[big]).max() * 2.0 ** -11   # x_hi is x rounded to fp16
+    h2, lo2 = q_encode(y[big])                                                         # codes are fixed points
+    assert np.array_equal(h2.view(np.uint16), h[big].view(np.uint16)) and np.array_equal(lo2, lo[big])
+    assert abs(np.mean((y[big].astype(np.float64) - x[big]) / x[big])) < 2.0 ** -22    # unbiased

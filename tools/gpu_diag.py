@@ -102,7 +102,7 @@ def check_pair_timing():
     lib, ptr = _capi.lib(), _capi.ptr
     st = _capi.stream_ptr()
     F, P = 128, 128
-    for n in (64, 8):
+    for n in [int(v) for v in os.environ.get('DSEN2_DIAG_N', '64,8').split(',')]:
         x = torch.randn((n, P, P, F), device='cuda').half()
         w = (torch.rand((9, F, F), device='cuda') - 0.5).half()
         b = torch.zeros(F, device='cuda')
@@ -132,7 +132,7 @@ def check_pair_timing():
         ms = _time(torch, lambda: _capi.check(lib.dsen2_conv_tail(ptr(hi), ptr(lo), ptr(wt), ptr(b), ptr(xin_hi),
                                                                   ptr(xin_lo), 4, 6, n, P, P, ptr(pred), st), 'tail'))
         print('n=%d tail (split)      : %.3f ms' % (n, ms), flush=True)
-        H = 112 * 8
+        H = 112 * max(8, int(n ** 0.5) + 1)
         d10 = torch.rand((H, H, 4), device='cuda') * 4000
         d20 = torch.rand((H // 2, H // 2, 6), device='cuda') * 4000
         ms = _time(torch, lambda: _capi.check(lib.dsen2_prep_from_images(ptr(d10), ptr(d20), None, H, H, 128, 8, 0, n,
@@ -179,6 +179,41 @@ def check_pair_res32_only():
     print('PF_A=%s PF_X=%s DEFER=%s  resblock (RELU + RESIDUAL32): %.3f ms  %.1f TFLOP/s' % (
         os.environ.get('DSEN2_PAIR_PF_A', 'd'), os.environ.get('DSEN2_PAIR_PF_X', 'd'), os.environ.get('DSEN2_PAIR_DEFER', 'd'),
         ms, 2 * fl / ms / 1e9), flush=True)
+
+
+def check_pair_res32_alone():
+    """RESIDUAL32 alone with parts of its epilogue disabled (DSEN2_PAIR_DEBUG bits 4/8/16), large and L2-sized batch."""
+    import torch
+    from dsen2_b200 import _capi
+    lib, ptr = _capi.lib(), _capi.ptr
+    st = _capi.stream_ptr()
+    F, P = 128, 128
+    for n in (84, 4):
+        w = (torch.rand((9, F, F), device='cuda') - 0.5).half()
+        b = torch.zeros(F, device='cuda')
+        t = torch.randn((n, P, P, F), device='cuda').half()
+        hi = torch.zeros_like(t)
+        x32 = torch.zeros((n, P, P // 8, F // 4, 8, 4), device='cuda')
+        ms = _time(torch, lambda: _capi.check(lib.dsen2_conv_res32(ptr(t), ptr(w), ptr(b), n, P, P, 0.1, ptr(x32), ptr(hi),
+                                                                   None, st), 'res32'), iters=20)
+        print('DEBUG=%-2s n=%d RESIDUAL32: %.4f ms  %.2f us/patch' % (os.environ.get('DSEN2_PAIR_DEBUG', '0'), n, ms, ms * 1e3 / n), flush=True)
+        xq = torch.zeros((n, P, P // 8, F // 16, 8, 16), dtype=torch.uint8, device='cuda')
+        lo = torch.zeros_like(t)
+        ms = _time(torch, lambda: _capi.check(lib.dsen2_conv_resq(ptr(t), ptr(w), ptr(b), n, P, P, 0.1, ptr(hi), ptr(xq),
+                                                                  None, st), 'resq'), iters=20)
+        print('DEBUG=%-2s n=%d RESIDUALQ : %.4f ms  %.2f us/patch' % (os.environ.get('DSEN2_PAIR_DEBUG', '0'), n, ms, ms * 1e3 / n), flush=True)
+        ms = _time(torch, lambda: _capi.check(lib.dsen2_conv_resq(ptr(t), ptr(w), ptr(b), n, P, P, 0.1, ptr(hi), ptr(xq),
+                                                                  ptr(lo), st), 'resq'), iters=20)
+        print('DEBUG=%-2s n=%d RESIDUALQ last: %.4f ms  %.2f us/patch' % (os.environ.get('DSEN2_PAIR_DEBUG', '0'), n, ms, ms * 1e3 / n), flush=True)
+        ms = _time(torch, lambda: _capi.check(lib.dsen2_conv3x3(ptr(hi), ptr(w), ptr(b), n, P, P, F, F, 9, 0, None, None,
+                                                                0.0, ptr(t), None, None, None, 0, st), 'relu'), iters=20)
+        print('DEBUG=%-2s n=%d RELU      : %.4f ms  %.2f us/patch' % (os.environ.get('DSEN2_PAIR_DEBUG', '0'), n, ms, ms * 1e3 / n), flush=True)
+
+
+def check_pair_res32_debug_sweep():
+    for dbg in ('0', '4', '8', '12', '16', '28', '1', '3'):
+        env = dict(os.environ, DSEN2_PAIR_DEBUG=dbg)
+        subprocess.run([sys.executable, os.path.abspath(__file__), '--one', 'pair_res32_alone'], env=env, timeout=120)
 
 
 def check_pair_knob_sweep():

@@ -26,13 +26,10 @@
 
 namespace dsen2 {
 
-static constexpr int kPairThreads = 320;
-static constexpr int kEpiWarps = 8;
 // Warp roles.  The warp scheduler prefers the HIGHEST warp id among eligible warps of a sub-partition, so the
 // two latency-critical single-thread roles get the highest ids: the MMA issuer must never queue behind the
 // instruction-heavy epilogue warps that share its sub-partition (measured: tensor pipe 59 % -> see profiles/).
-static constexpr int kProducerWarp = 8;
-static constexpr int kMmaWarp = 9;
+// (PairCfg::PRODUCER_WARP / MMA_WARP = the two warps after the epilogue warps)
 static constexpr int kBoxH = 18;
 static constexpr int kPrefetchTiles = 1;        // L2 prefetch distance of the activation boxes, in tiles of this CTA
 static constexpr int kTrunkPrefetchTiles = 1;   // same for the fp32 trunk lines the RESIDUAL32 epilogue reads
@@ -60,13 +57,18 @@ struct PairParams {
   float* out_f32;
   int pf_a, pf_x, defer;   // tuning knobs (L2 prefetch distances in tiles, deferred fp16-copy store)
   int debug;               // profiling aid (DSEN2_PAIR_DEBUG): 1 = epilogue only hands TMEM back, 2 = no activation TMA,
-                           // RESIDUAL32 only: 4 = no trunk load, 8 = no trunk store, 16 = no fp16 copy store
+                           // RESIDUAL32: 4 = no trunk load, 8 = no trunk store, 16 = no fp16 copy store; RESIDUALQ: 4 = no x_hi load,
+                           // 8 = no byte load / store, 16 = no x_hi store, 32 = no transposing gather
   int tail_mode;           // 0: NCHW (n,cout,H,W) predictions; 1: stitched HWC canvas
   int first_patch, img_h, img_w, border, grid_ny, grid_nx;
 };
 
 template <int NTOT_, bool SPLIT_, int NMAPS_, int KPM_, int NTAPS_, int KSTEPS_, int STAGES_, int EPI_, int WSTAGES_ = 0>
 struct PairCfg {
+  static constexpr int EPI_WARPS = 8;           // two per TMEM lane quarter, half of the channels each
+  static constexpr int PRODUCER_WARP = EPI_WARPS;
+  static constexpr int MMA_WARP = EPI_WARPS + 1;
+  static constexpr int THREADS = (EPI_WARPS + 2) * 32;
   static constexpr int WSTAGES = WSTAGES_;      // 0: the layer's weights are resident in smem; > 0: ring of streamed slabs
   static constexpr bool RESIDENT = WSTAGES_ == 0;
   static constexpr int NTOT = NTOT_;            // UMMA N over the pair
@@ -88,7 +90,7 @@ struct PairCfg {
   static constexpr int W_BYTES = (WSTAGES_ == 0 ? NSLABS : WSTAGES_) * SLAB_BYTES;
   static constexpr int TMEM_COLS = (2 * NTOT_ < 32) ? 32 : 2 * NTOT_;
   static constexpr int BAR_BYTES = 2048;        // barriers + tmem pointer (first 512 B) + bias
-  static constexpr int STG_BYTES = kEpiWarps * 1024;   // per-warp transpose buffers of the epilogue
+  static constexpr int STG_BYTES = EPI_WARPS * 1024;   // per-warp transpose buffers of the epilogue
   static constexpr int SMEM_BYTES = W_BYTES + STAGES_ * STAGE_BYTES + BAR_BYTES + STG_BYTES + 1024 /*align slack*/;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
   static_assert(W_BYTES % 1024 == 0, "weight slabs must keep the stages 1024-byte aligned");
@@ -252,8 +254,108 @@ __device__ __forceinline__ EpiGeom epi_geom(const PairParams& p, const TileXY& t
   return g;
 }
 
+// ---- resblock output on the fp16 + 8 bit trunk: one pass over CPT channels of this thread's pixel ----------------
+// x <- x + scale * (conv + bias) (DSen2Net.py:13,15) on the trunk held as x_hi (NHWC fp16, updated in place: this
+// kernel's TMA reads t, never x_hi) + one byte per element (see q_encode4).  The LAST block of the chain writes
+// x_hi = fp16(x) and x_lo = fp16(x - x_hi) instead: the tail's split operand (and nothing reads the bytes again).
+// `full` / `empty`: accumulator barriers to wait on before / arrive on after the TMEM reads of this pass (either may
+// be null when the pass is not the first / last one that touches the accumulator).
+template <class Cfg, int CPT>
+__device__ __forceinline__ void q_epilogue_pass(const PairParams& p, const TileXY& tc, const TileXY& tn, bool prefetch, int wq,
+                                                int chan0, int lane, int row, bool valid, uint32_t stg, uint32_t taddr,
+                                                uint32_t s_bias_addr, uint64_t* full, uint32_t full_phase, uint64_t* empty) {
+  constexpr bool LAST = Cfg::EPI == kEpiResidualQLast;
+  static_assert(CPT == 64 && !Cfg::SPLIT, "Q-trunk epilogue: 64 channels per thread");
+  const int y = tc.ty * 16 + (row >> 3);
+  const EpiGeom g = epi_geom<Cfg>(p, tc, wq, chan0);
+  uint4 vh[CPT / 8];
+  uint4 lq[CPT / 16];
+  // low bytes: (n, H, W/8, C/16, 8 px, 16 ch) -- thread = pixel reads 16 B, a tile row of one chunk is one 128 B line
+  uint8_t* const qp = p.xq + ((((long long)tc.b * p.H + y) * p.tiles_x + tc.tx) * (Cfg::CH / 16) + chan0 / 16) * 128 +
+                      (row & 7) * 16;
+  {
+    uint4 gh[CPT / 8];
+    if (p.debug & 4) {
+#pragma unroll
+      for (int q = 0; q < CPT / 8; ++q) gh[q] = make_uint4(0, 0, 0, 0);
+    } else {
+      coalesced_load(gh, p.out_hi, g, lane);
+    }
+    if (valid && !(p.debug & 8)) {
+#pragma unroll
+      for (int q = 0; q < CPT / 16; ++q) lq[q] = *reinterpret_cast<const uint4*>(qp + q * 128);
+    } else {
+#pragma unroll
+      for (int q = 0; q < CPT / 16; ++q) lq[q] = make_uint4(0, 0, 0, 0);
+    }
+    if (prefetch) {                                          // a later tile's trunk lines -> L2
+      prefetch_rows(p.out_hi, epi_geom<Cfg>(p, tn, wq, chan0), lane);
+      constexpr int QL = CPT / 16;                           // byte-chunk lines per tile row of this pass
+      const int ny = tn.ty * 16 + wq * 4 + lane / QL;        // 4 rows x QL lines per warp
+      if (lane < 4 * QL && tn.b < p.n && ny < p.H)
+        prefetch_l2(p.xq + ((((long long)tn.b * p.H + ny) * p.tiles_x + tn.tx) * (Cfg::CH / 16) + chan0 / 16 + (lane % QL)) * 128);
+    }
+    if (p.debug & 32) {
+#pragma unroll
+      for (int q = 0; q < CPT / 8; ++q) vh[q] = gh[q];
+    } else {
+      staged_gather(stg, gh, vh, lane);
+    }
+  }
+  uint4 vl[LAST ? CPT / 8 : 1];
+  if (full != nullptr) {
+    mbar_wait(full, full_phase);
+    tc_fence_after();
+  }
+#pragma unroll
+  for (int chunk = 0; chunk < CPT / 32; ++chunk) {
+    const int c0 = chan0 + chunk * 32;
+    uint32_t r[32];
+    tmem_ld_32x32(taddr + c0, r);
+    tmem_ld_wait();
+    uint32_t* hw = reinterpret_cast<uint32_t*>(vh) + chunk * 16;
+    uint32_t* qw = reinterpret_cast<uint32_t*>(lq) + chunk * 8;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 bq = lds_f4(s_bias_addr + (uint32_t)(c0 + j) * 4);   // broadcast LDS.128
+      const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&hw[j >> 1]));
+      const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&hw[(j >> 1) + 1]));
+      const uint32_t w = qw[j >> 2];
+      const float x0 = fmaf(__uint_as_float(r[j]) + bq.x, p.res_scale, q_decode(f01.x, sext_byte<0>(w)));
+      const float x1 = fmaf(__uint_as_float(r[j + 1]) + bq.y, p.res_scale, q_decode(f01.y, sext_byte<1>(w)));
+      const float x2 = fmaf(__uint_as_float(r[j + 2]) + bq.z, p.res_scale, q_decode(f23.x, sext_byte<2>(w)));
+      const float x3 = fmaf(__uint_as_float(r[j + 3]) + bq.w, p.res_scale, q_decode(f23.y, sext_byte<3>(w)));
+      if constexpr (LAST) {
+        const __half2 h0 = __floats2half2_rn(x0, x1), h1 = __floats2half2_rn(x2, x3);
+        const float2 g0 = __half22float2(h0), g1 = __half22float2(h1);
+        const __half2 l0 = __floats2half2_rn(x0 - g0.x, x1 - g0.y), l1 = __floats2half2_rn(x2 - g1.x, x3 - g1.y);
+        uint32_t* lw = reinterpret_cast<uint32_t*>(vl) + chunk * 16;
+        hw[j >> 1] = *reinterpret_cast<const uint32_t*>(&h0);
+        hw[(j >> 1) + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+        lw[j >> 1] = *reinterpret_cast<const uint32_t*>(&l0);
+        lw[(j >> 1) + 1] = *reinterpret_cast<const uint32_t*>(&l1);
+      } else {
+        q_encode4(x0, x1, x2, x3, hw[j >> 1], hw[(j >> 1) + 1], qw[j >> 2]);
+      }
+    }
+  }
+  if (empty != nullptr) {
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive_leader(empty);
+  }
+  if constexpr (!LAST) {
+    if (valid && !(p.debug & 8)) {
+#pragma unroll
+      for (int q = 0; q < CPT / 16; ++q) *reinterpret_cast<uint4*>(qp + q * 128) = lq[q];
+    }
+  }
+  if (!(p.debug & 16)) staged_store(stg, vh, p.out_hi, g, lane);
+  if constexpr (LAST) staged_store(stg, vl, p.out_lo, g, lane);
+}
+
 template <class Cfg>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg::THREADS, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
                  const __grid_constant__ CUtensorMap tm_w, const PairParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -265,7 +367,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
   uint64_t* empty = full + Cfg::STAGES;                        // per CTA (multicast commit)
   uint64_t* wfull = empty + Cfg::STAGES;                       // leader
   uint64_t* tmem_full = wfull + 1;                             // per CTA (multicast commit)
-  uint64_t* tmem_empty = tmem_full + 2;                        // leader; 2 * kEpiWarps arrivals
+  uint64_t* tmem_empty = tmem_full + 2;                        // leader; 2 * EPI_WARPS arrivals
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   uint64_t* wr_full = tmem_empty + 3;                          // streamed-weight ring: leader's copies are live
   uint64_t* wr_empty = wr_full + Cfg::WSTAGES;                 // per CTA (multicast commit)
@@ -280,7 +382,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
   const uint32_t npairs = gridDim.x >> 1;
   const uint32_t pair_tiles = (p.num_tiles + 1) >> 1;
 
-  if (warp == kProducerWarp && lane == 0) {
+  if (warp == Cfg::PRODUCER_WARP && lane == 0) {
     tma_prefetch_desc(&tm_a0);
     if (Cfg::NMAPS == 2) tma_prefetch_desc(&tm_a1);
     tma_prefetch_desc(&tm_w);
@@ -295,19 +397,19 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 2 * kEpiWarps);
+      mbar_init(&tmem_empty[i], 2 * Cfg::EPI_WARPS);
     }
     mbar_fence_init();
   }
-  if (warp == kMmaWarp) tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_ptr);
-  for (int i = threadIdx.x; i < Cfg::CH; i += kPairThreads) s_bias[i] = p.bias[i];
+  if (warp == Cfg::MMA_WARP) tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_ptr);
+  for (int i = threadIdx.x; i < Cfg::CH; i += Cfg::THREADS) s_bias[i] = p.bias[i];
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();            // the peer's barriers exist before anything is signalled across the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == kProducerWarp) {
+  if (warp == Cfg::PRODUCER_WARP) {
     // ================================ TMA producer (both CTAs) ================================
     if (elect_one()) {
       if constexpr (Cfg::RESIDENT) {
@@ -354,7 +456,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
         }
       }
     }
-  } else if (warp == kMmaWarp) {
+  } else if (warp == Cfg::MMA_WARP) {
     // ================================ MMA issuer (leader CTA) ==================================
     if (rank == 0 && elect_one()) {
       constexpr uint32_t idesc = umma_idesc_f16(256, Cfg::NTOT);
@@ -372,7 +474,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * Cfg::NTOT);
 #pragma unroll 1
         for (int kb = 0; kb < Cfg::KB; ++kb) {
-          mbar_wait(&full[stage], phase);
+          if (!(p.debug & 64)) mbar_wait(&full[stage], phase);   // 64: latency experiment, MMAs never wait for the loads
           tc_fence_after();
           const uint32_t sa = smem_u32(s_a + stage * Cfg::STAGE_BYTES);
           const uint32_t sb = smem_u32(s_w) + (uint32_t)((kb % Cfg::KPM) * Cfg::SLAB_BYTES);
@@ -568,86 +670,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
         continue;
       } else if constexpr (Cfg::EPI == kEpiResidualQ || Cfg::EPI == kEpiResidualQLast) {
         // ------------------------------------------------------------------ resblock output, fp16 + 8 bit trunk
-        // x <- x + scale * (conv + bias) (DSen2Net.py:13,15) on the trunk held as x_hi (NHWC fp16, updated in place: this
-        // kernel's TMA reads t, never x_hi) + one byte per element (see q_encode4).  The LAST block of the chain writes
-        // x_hi = fp16(x) and x_lo = fp16(x - x_hi) instead: the tail's split operand (and nothing reads the bytes again).
         constexpr int CPT = Cfg::CH / 2;
-        constexpr bool LAST = Cfg::EPI == kEpiResidualQLast;
-        static_assert(CPT == 64 && !Cfg::SPLIT, "Q-trunk epilogue: 64 channels per thread");
-        const uint32_t stg = smem_u32(s_stg) + (uint32_t)(warp * 1024);
-        const EpiGeom g = epi_geom<Cfg>(p, tc, wq, half * CPT);
-        uint4 vh[8];
-        uint4 lq[CPT / 16];
-        {
-          uint4 gh[8];
-          coalesced_load(gh, p.out_hi, g, lane);
-          // low bytes: (n, H, W/8, C/16, 8 px, 16 ch) -- thread = pixel reads 16 B, a tile row of one chunk is one 128 B line
-          uint8_t* qp = p.xq + ((((long long)b * p.H + y) * p.tiles_x + tc.tx) * (Cfg::CH / 16) + half * (CPT / 16)) * 128 +
-                        (row & 7) * 16;
-          if (valid) {
-#pragma unroll
-            for (int q = 0; q < CPT / 16; ++q) lq[q] = *reinterpret_cast<const uint4*>(qp + q * 128);
-          } else {
-#pragma unroll
-            for (int q = 0; q < CPT / 16; ++q) lq[q] = make_uint4(0, 0, 0, 0);
-          }
-          if (p.pf_x > 0 && pt + p.pf_x * npairs < pair_tiles) {   // a later tile's trunk lines -> L2
-              prefetch_rows(p.out_hi, epi_geom<Cfg>(p, tn, wq, half * CPT), lane);
-            const int ny = tn.ty * 16 + wq * 4 + (lane >> 2);      // 4 rows x 4 byte-chunk lines per warp
-            if (lane < 16 && tn.b < p.n && ny < p.H)
-              prefetch_l2(p.xq + ((((long long)tn.b * p.H + ny) * p.tiles_x + tn.tx) * (Cfg::CH / 16) + half * (CPT / 16) +
-                                  (lane & 3)) * 128);
-          }
-          staged_gather(stg, gh, vh, lane);
-        }
-        uint4 vl[LAST ? 8 : 1];
-        mbar_wait(&tmem_full[acc], acc_phase);
-        tc_fence_after();
-#pragma unroll
-        for (int chunk = 0; chunk < CPT / 32; ++chunk) {
-          const int c0 = half * CPT + chunk * 32;
-          uint32_t r[32];
-          tmem_ld_32x32(taddr + c0, r);
-          tmem_ld_wait();
-          uint32_t* hw = reinterpret_cast<uint32_t*>(vh) + chunk * 16;
-          uint32_t* qw = reinterpret_cast<uint32_t*>(lq) + chunk * 8;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 bq = lds_f4(s_bias_addr + (uint32_t)(c0 + j) * 4);   // broadcast LDS.128
-            const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&hw[j >> 1]));
-            const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&hw[(j >> 1) + 1]));
-            const uint32_t w = qw[j >> 2];
-            const float x0 = fmaf(__uint_as_float(r[j]) + bq.x, p.res_scale, q_decode(f01.x, sext_byte<0>(w)));
-            const float x1 = fmaf(__uint_as_float(r[j + 1]) + bq.y, p.res_scale, q_decode(f01.y, sext_byte<1>(w)));
-            const float x2 = fmaf(__uint_as_float(r[j + 2]) + bq.z, p.res_scale, q_decode(f23.x, sext_byte<2>(w)));
-            const float x3 = fmaf(__uint_as_float(r[j + 3]) + bq.w, p.res_scale, q_decode(f23.y, sext_byte<3>(w)));
-            if constexpr (LAST) {
-              const __half2 h0 = __floats2half2_rn(x0, x1), h1 = __floats2half2_rn(x2, x3);
-              const float2 g0 = __half22float2(h0), g1 = __half22float2(h1);
-              const __half2 l0 = __floats2half2_rn(x0 - g0.x, x1 - g0.y), l1 = __floats2half2_rn(x2 - g1.x, x3 - g1.y);
-              uint32_t* lw = reinterpret_cast<uint32_t*>(vl) + chunk * 16;
-              hw[j >> 1] = *reinterpret_cast<const uint32_t*>(&h0);
-              hw[(j >> 1) + 1] = *reinterpret_cast<const uint32_t*>(&h1);
-              lw[j >> 1] = *reinterpret_cast<const uint32_t*>(&l0);
-              lw[(j >> 1) + 1] = *reinterpret_cast<const uint32_t*>(&l1);
-            } else {
-              q_encode4(x0, x1, x2, x3, hw[j >> 1], hw[(j >> 1) + 1], qw[j >> 2]);
-            }
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
-        if constexpr (!LAST) {
-          if (valid) {
-            uint8_t* qp = p.xq + ((((long long)b * p.H + y) * p.tiles_x + tc.tx) * (Cfg::CH / 16) + half * (CPT / 16)) * 128 +
-                          (row & 7) * 16;
-#pragma unroll
-            for (int q = 0; q < CPT / 16; ++q) *reinterpret_cast<uint4*>(qp + q * 128) = lq[q];
-          }
-        }
-        staged_store(stg, vh, p.out_hi, g, lane);
-        if constexpr (LAST) staged_store(stg, vl, p.out_lo, g, lane);
+        q_epilogue_pass<Cfg, CPT>(p, tc, tn, p.pf_x > 0 && pt + p.pf_x * npairs < pair_tiles, wq, half * CPT, lane, row, valid,
+                                  smem_u32(s_stg) + (uint32_t)(warp * (CPT * 16)), taddr, s_bias_addr, &tmem_full[acc], acc_phase,
+                                  &tmem_empty[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         continue;
       } else {
@@ -779,7 +805,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
   __syncthreads();
   cluster_sync_all();            // nobody leaves while the peer may still signal it or read its smem
   tc_fence_after();
-  if (warp == kMmaWarp) tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base);
+  if (warp == Cfg::MMA_WARP) tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------ //
@@ -808,7 +834,7 @@ static int launch_pair(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
   const long long pair_tiles = ((long long)p.num_tiles + 1) / 2;
   const long long max_pairs = sms / 2;
   const int pairs = (int)(pair_tiles < max_pairs ? pair_tiles : max_pairs);
-  conv_pair_kernel<Cfg><<<2 * pairs, kPairThreads, Cfg::SMEM_BYTES, stream>>>(a0, a1, w, p);
+  conv_pair_kernel<Cfg><<<2 * pairs, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(a0, a1, w, p);
   return check_launch(what);
 }
 

@@ -188,7 +188,7 @@ def check_pair_res32_alone():
     lib, ptr = _capi.lib(), _capi.ptr
     st = _capi.stream_ptr()
     F, P = 128, 128
-    for n in (84, 4):
+    for n in [int(v) for v in os.environ.get('DSEN2_DIAG_N', '84,4').split(',')]:
         w = (torch.rand((9, F, F), device='cuda') - 0.5).half()
         b = torch.zeros(F, device='cuda')
         t = torch.randn((n, P, P, F), device='cuda').half()
@@ -211,7 +211,7 @@ def check_pair_res32_alone():
 
 
 def check_pair_res32_debug_sweep():
-    for dbg in ('0', '4', '8', '12', '16', '28', '1', '3'):
+    for dbg in os.environ.get('DSEN2_DIAG_DBG', '0,4,8,12,16,28,1,3').split(','):
         env = dict(os.environ, DSEN2_PAIR_DEBUG=dbg)
         subprocess.run([sys.executable, os.path.abspath(__file__), '--one', 'pair_res32_alone'], env=env, timeout=120)
 

@@ -33,6 +33,11 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+DTYPE_FP32 = "fp16 operands, fp32 accumulate (TMEM), fp32 residual trunk; first/last layer split hi+lo (fp32-equivalent)"
+DTYPE_Q8 = ("fp16 operands, fp32 accumulate (TMEM), residual trunk fp16 + 8 bits (19 significant bits); first/last layer split "
+            "hi+lo (fp32-equivalent)")
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as fh:
@@ -249,10 +254,14 @@ def run_ours(args):
         if ms:
             by_epi[label] = {"avg_launch_ms": float(np.mean(ms)), "tflops_executed": exec_flop / float(np.mean(ms)) / 1e9,
                              "frac_executed": exec_flop / float(np.mean(ms)) / 1e9 / pk['tf_sust']}
-    # DRAM bytes per launch from the ncu --set full capture profiles/r01_pair_kernels_ncu_full.txt
-    # (dram__bytes_read.sum + dram__bytes_write.sum, 57.14 patches per captured launch): RELU 492 MB, RESIDUAL32 1556 MB
-    traffic = (8.61e6 + 27.23e6) / 2 * float(np.mean(conv_n)) if model.fast_path else None
-    kname = ("conv_pair_kernel<N=128> (CTA-pair tcgen05 3x3 conv 128->128, RELU / RESIDUAL32 epilogues; %d of %d convs)"
+    # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum of ncu --set full captures, per patch):
+    #   fp16 + 8 bit trunk: RELU 660 MB, RESIDUALQ 1359 MB per 84 patches   (profiles/r01_q_trunk_ncu_full.txt)
+    #   fp32 trunk:         RELU 492 MB, RESIDUAL32 1556 MB per 57.14 patches (profiles/r01_pair_kernels_ncu_full.txt)
+    q8 = model.fast_path and model.trunk_format == 'q8'
+    per_patch = (7.86e6 + 16.18e6) / 2 if q8 else (8.61e6 + 27.23e6) / 2
+    traffic = per_patch * float(np.mean(conv_n)) if model.fast_path else None
+    traffic_src = "profiles/r01_q_trunk_ncu_full.txt" if q8 else "profiles/r01_pair_kernels_ncu_full.txt"
+    kname = ("conv_pair_kernel<N=128> (CTA-pair tcgen05 3x3 conv 128->128, RELU / RESIDUAL%s epilogues; %%d of %%d convs)" % ('Q' if q8 else '32')
              if model.fast_path else "conv_tcgen05_kernel<%d>" % F + " (3x3 conv, RELU / RESIDUAL epilogues; %d of %d convs)")
     roofline = {"bound": "tensor", "kernel": kname % (2 * model.num_layers, 2 * model.num_layers + 2),
                 "achieved": algo_flop / kernel_ms / 1e9, "achieved_executed": exec_flop / kernel_ms / 1e9,
@@ -261,7 +270,7 @@ def run_ours(args):
                 "frac_executed": exec_flop / kernel_ms / 1e9 / pk['tf_sust'],
                 "avg_launch_ms": kernel_ms, "patches_per_launch": float(np.mean(conv_n)),
                 "algorithmic_flop_per_launch": algo_flop, "executed_flop_per_launch": exec_flop, "traffic": traffic,
-                "traffic_source": "ncu dram__bytes_read+write per launch, scaled per patch (profiles/r01_pair_kernels_ncu_full.txt)",
+                "traffic_source": "ncu dram__bytes_read+write per launch, scaled per patch (%s)" % traffic_src,
                 "by_epilogue": by_epi, "ms_per_step_by_kernel": per_kind}
 
     # ---- e2e: pinned host -> device -> pinned host every step, through the public host-buffer pipeline --------
@@ -328,7 +337,7 @@ def run_ours(args):
     if rank == 0:
         line = {"metric": "output_Mpixel_per_s", "value": value, "unit": "Mpixel/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "fp16 operands, fp32 accumulate (TMEM), fp32 residual trunk; first/last layer split hi+lo (fp32-equivalent)",
+                "scaling": "strong", "vs_baseline": None, "dtype": DTYPE_Q8 if (model.fast_path and model.trunk_format == 'q8') else DTYPE_FP32,
                 "data": "synthetic", "config": workload_config(args), "clocks": clocks,
                 "e2e": {"value": T * T / (e2e_ms * 1e-3) / 1e6, "unit": "Mpixel/s", "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

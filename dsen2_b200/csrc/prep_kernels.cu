@@ -128,6 +128,116 @@ __device__ __forceinline__ void prep_gather(const PrepSource& src, int si, int s
   }
 }
 
+// ---- row-block variants (P <= 256): coalesced x_in stores ------------------------------------------------------
+// The thread-per-pixel kernels above write every 128-byte x_in row in six 32-byte pieces from three different threads
+// (24 scattered 16-byte stores per thread: 2.6 TB/s).  Here a block owns R = 256 / P whole patch rows: each thread
+// computes its pixel's 16-channel vector once, parks hi / lo in shared memory, and the block then writes the rows
+// out as contiguous 16-byte chunks (lane = chunk: a warp store covers four full 128-byte lines).
+__device__ __forceinline__ void rowblock_store(const Half16& hi, const Half16& lo, bool active, int r, int x, int P, int R,
+                                               long long first_row, long long total_rows, __half* __restrict__ out_hi,
+                                               __half* __restrict__ out_lo) {
+  extern __shared__ uint4 s_rows[];                       // [2 (hi, lo)][R][P + 2][2 x 16 B]; columns 0 and P + 1 are zero
+  const int pitch = (P + 2) * 2;
+  uint4* s_hi = s_rows;
+  uint4* s_lo = s_rows + R * pitch;
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < R * 2; i += blockDim.x) {  // guard columns
+    const int rr = i >> 1, side = i & 1;
+    const int col = side ? P + 1 : 0;
+    s_hi[rr * pitch + col * 2] = z; s_hi[rr * pitch + col * 2 + 1] = z;
+    s_lo[rr * pitch + col * 2] = z; s_lo[rr * pitch + col * 2 + 1] = z;
+  }
+  if (active) {
+    const uint4* h = reinterpret_cast<const uint4*>(&hi);
+    const uint4* l = reinterpret_cast<const uint4*>(&lo);
+    const int o = r * pitch + (x + 1) * 2;
+    s_hi[o] = h[0]; s_hi[o + 1] = h[1];
+    s_lo[o] = l[0]; s_lo[o + 1] = l[1];
+  }
+  __syncthreads();
+  // chunk c of pixel x: taps t = c / 2 (pixel x + t - 1 -> column x + t of the guarded row), half c % 2; chunks 6, 7 zero
+  const int chunks = R * P * 8;
+  for (int i = threadIdx.x; i < chunks; i += blockDim.x) {
+    const int pix = i >> 3, c = i & 7;
+    const int rr = pix / P, xx = pix - rr * P;
+    const long long row = first_row + rr;
+    if (row >= total_rows) break;
+    uint4 vh = z, vl = z;
+    if (c < 6) {
+      const int o = rr * pitch + (xx + (c >> 1)) * 2 + (c & 1);
+      vh = s_hi[o];
+      vl = s_lo[o];
+    }
+    const long long dst = (row * P + xx) * 8 + c;          // in 16-byte units
+    reinterpret_cast<uint4*>(out_hi)[dst] = vh;
+    reinterpret_cast<uint4*>(out_lo)[dst] = vl;
+  }
+}
+
+__global__ void prep_from_patches_rows_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x1, int c1,
+                                              const float* __restrict__ x2, int c2, int P, int R, long long total_rows,
+                                              __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+  const long long PP = (long long)P * P;
+  const long long first_row = (long long)blockIdx.x * R;
+  const int r = threadIdx.x / P, x = threadIdx.x - r * P;
+  const long long row = first_row + r;
+  const bool active = r < R && row < total_rows;
+  Half16 hi, lo;
+  if (active) {
+    const long long n = row / P;
+    const int rem = (int)(row - n * P) * P + x;
+    float v[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      float t = 0.f;
+      if (c < c0) t = __ldg(x0 + (n * c0 + c) * PP + rem);
+      else if (c < c0 + c1) t = __ldg(x1 + (n * c1 + (c - c0)) * PP + rem);
+      else if (c < c0 + c1 + c2) t = __ldg(x2 + (n * c2 + (c - c0 - c1)) * PP + rem);
+      v[c] = t;
+    }
+    split16(v, hi, lo);
+  }
+  rowblock_store(hi, lo, active, r, x, P, R, first_row, total_rows, out_hi, out_lo);
+}
+
+__global__ void prep_from_images_rows_kernel(PrepSource s0, PrepSource s1, PrepSource s2, int nsrc, int plr, int blr, int P,
+                                             int R, Tiling tl, int first_patch, long long total_rows, float divisor,
+                                             __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+  const long long first_row = (long long)blockIdx.x * R;
+  const int r = threadIdx.x / P, x = threadIdx.x - r * P;
+  const long long row = first_row + r;
+  const bool active = r < R && row < total_rows;
+  Half16 hi, lo;
+  if (active) {
+    const int local = (int)(row / P);
+    const int y = (int)(row - (long long)local * P);
+    const int patch = first_patch + local;
+    float v[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) v[c] = 0.f;
+    if (patch < tl.n_i * tl.n_j) {               // surplus patches of the allocated stack stay zero (patches.py:32-39)
+      const int ti = patch / tl.n_j, tj = patch - ti * tl.n_j;
+      const int si = ti < tl.k_i ? ti * tl.stride : tl.last_i;
+      const int sj = tj < tl.k_j ? tj * tl.stride : tl.last_j;
+      prep_gather<4, 0>(s0, si, sj, plr, blr, y, x, divisor, v);     // 10 m bands   (DSen2Net.py:24,26 order)
+      prep_gather<6, 4>(s1, si, sj, plr, blr, y, x, divisor, v);     // 20 m bands
+      if (nsrc == 3) prep_gather<2, 10>(s2, si, sj, plr, blr, y, x, divisor, v);   // 60 m bands
+    }
+    split16(v, hi, lo);
+  }
+  rowblock_store(hi, lo, active, r, x, P, R, first_row, total_rows, out_hi, out_lo);
+}
+
+// launch geometry of the row-block kernels: R rows per block, R * P threads rounded up to whole warps
+struct RowBlock { int R, threads; size_t smem; };
+static RowBlock row_block(int P) {
+  RowBlock g;
+  g.R = 256 / P > 0 ? 256 / P : 1;
+  g.threads = (g.R * P + 31) / 32 * 32;
+  g.smem = (size_t)2 * g.R * (P + 2) * 2 * sizeof(uint4);
+  return g;
+}
+
 __global__ void prep_from_images_kernel(PrepSource s0, PrepSource s1, PrepSource s2, int nsrc, int plr, int blr, int P,
                                         Tiling tl, int first_patch, long long total, float divisor,
                                         __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
@@ -201,6 +311,13 @@ extern "C" int dsen2_prep_from_patches(const float* d_x0, int c0, const float* d
                 "dsen2_prep_from_patches: outputs must be 16-byte aligned");
   if (n == 0) return 0;
   const long long total = (long long)n * P * P;
+  if (P <= 256) {
+    const RowBlock g = row_block(P);
+    const long long rows = (long long)n * P;
+    prep_from_patches_rows_kernel<<<(unsigned)((rows + g.R - 1) / g.R), g.threads, g.smem, (cudaStream_t)stream>>>(
+        d_x0, c0, d_x1, c1, d_x2, c2, P, g.R, rows, (__half*)d_xin_hi, (__half*)d_xin_lo);
+    return check_launch("prep_from_patches");
+  }
   const int block = 256;
   prep_from_patches_kernel<<<grid_for(total, block), block, 0, (cudaStream_t)stream>>>(
       d_x0, c0, d_x1, c1, d_x2, c2, P, total, (__half*)d_xin_hi, (__half*)d_xin_lo);
@@ -232,6 +349,14 @@ extern "C" int dsen2_prep_from_images(const float* d_img10, const float* d_img20
   PrepSource s1{d_img20, H / 2, W / 2, r / 2, 2};
   PrepSource s2{d_img60, H / 6, W / 6, 1, 6};
   const long long total = (long long)num_patches * patch * patch;
+  if (patch <= 256) {
+    const RowBlock g = row_block(patch);
+    const long long rows = (long long)num_patches * patch;
+    prep_from_images_rows_kernel<<<(unsigned)((rows + g.R - 1) / g.R), g.threads, g.smem, (cudaStream_t)stream>>>(
+        s0, s1, s2, d_img60 ? 3 : 2, plr, blr, patch, g.R, tl, first_patch, rows, divisor, (__half*)d_xin_hi,
+        (__half*)d_xin_lo);
+    return check_launch("prep_from_images");
+  }
   const int block = 256;
   prep_from_images_kernel<<<grid_for(total, block), block, 0, (cudaStream_t)stream>>>(
       s0, s1, s2, d_img60 ? 3 : 2, plr, blr, patch, tl, first_patch, total, divisor, (__half*)d_xin_hi,

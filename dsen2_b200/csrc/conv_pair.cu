@@ -38,7 +38,8 @@ enum { kEpiRelu = 0, kEpiResidual = 1, kEpiTail = 2, kEpiResidual32 = 3, kEpiMas
 
 struct PairParams {
   int n, H, W;
-  int tiles_x, tiles_y;
+  int tiles_x, tiles_y;    // tiles per patch; tile column t covers pixels 8 * (tx0 + t) ..
+  int tx0;                 // first tile column (the stitching tail skips the columns that lie inside the patch border)
   uint32_t num_tiles;
   const float* bias;
   const __half* res_hi;
@@ -424,13 +425,13 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
         // tile may equal num_tiles (odd count): then b == n and the whole box is zero fill
         const TileXY t = decode_tile(2 * pt + rank, p.tiles_x, p.tiles_y);
         const int b = t.b;
-        const int bx = t.tx * 8 - (Cfg::NTAPS == 9 ? 1 : 0), by = t.ty * 16 - 1;
+        const int bx = (t.tx + p.tx0) * 8 - (Cfg::NTAPS == 9 ? 1 : 0), by = t.ty * 16 - 1;
         if (p.pf_a > 0 && pt + p.pf_a * npairs < pair_tiles && !(p.debug & 2)) {   // warm L2 for a tile this CTA loads later
           const TileXY tn = decode_tile(2 * (pt + p.pf_a * npairs) + rank, p.tiles_x, p.tiles_y);
 #pragma unroll
           for (int kb = 0; kb < Cfg::KB; ++kb)
             tma_prefetch_4d((Cfg::NMAPS == 2 && kb >= Cfg::KPM) ? &tm_a1 : &tm_a0, (kb % Cfg::KPM) * 64,
-                            tn.tx * 8 - (Cfg::NTAPS == 9 ? 1 : 0), tn.ty * 16 - 1, tn.b);
+                            (tn.tx + p.tx0) * 8 - (Cfg::NTAPS == 9 ? 1 : 0), tn.ty * 16 - 1, tn.b);
         }
 #pragma unroll 1
         for (int kb = 0; kb < Cfg::KB; ++kb) {
@@ -520,10 +521,11 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
     const TileXY tstep = decode_tile(2 * npairs, p.tiles_x, p.tiles_y);
     const uint32_t pf_dist = (Cfg::EPI == kEpiResidual32 || Cfg::EPI == kEpiResidualQ || Cfg::EPI == kEpiResidualQLast)
                                  ? (uint32_t)max(p.pf_x, 1) : 1u;
-    TileXY tc = decode_tile(2 * pair + rank, p.tiles_x, p.tiles_y);
-    TileXY tn = decode_tile(2 * (pair + pf_dist * npairs) + rank, p.tiles_x, p.tiles_y);
+    TileXY tci = decode_tile(2 * pair + rank, p.tiles_x, p.tiles_y);
+    TileXY tni = decode_tile(2 * (pair + pf_dist * npairs) + rank, p.tiles_x, p.tiles_y);
     for (uint32_t pt = pair; pt < pair_tiles;
-         pt += npairs, advance_tile(tc, tstep, p.tiles_x, p.tiles_y), advance_tile(tn, tstep, p.tiles_x, p.tiles_y)) {
+         pt += npairs, advance_tile(tci, tstep, p.tiles_x, p.tiles_y), advance_tile(tni, tstep, p.tiles_x, p.tiles_y)) {
+      const TileXY tc = {tci.b, tci.ty, tci.tx + p.tx0}, tn = {tni.b, tni.ty, tni.tx + p.tx0};   // in patch tile coordinates
       const int b = tc.b;
       const int y = tc.ty * 16 + (row >> 3);
       const int x = tc.tx * 8 + (row & 7);
@@ -1024,6 +1026,13 @@ static int tail_common(PairParams& p, const void* d_x_hi, const void* d_x_lo, co
   int rc = device_sm_count_and_check(&sms);
   if (rc) return rc;
   if ((rc = fill_tiles(p, n, H, W)) != 0) return rc;
+  if (p.tail_mode == 1) {
+    // recompose_images copies only [border, P - border) of every patch (patches.py:402): tile columns that lie inside
+    // the border produce nothing -- leave them out of the tile list (P 128 / border 8: 14 of 16 columns)
+    p.tx0 = p.border / 8;
+    p.tiles_x = (W - p.border - 1) / 8 - p.tx0 + 1;
+    p.num_tiles = (uint32_t)((long long)n * p.tiles_x * p.tiles_y);
+  }
   p.bias = d_bias;
   p.skip_hi = (const __half*)d_xin_hi; p.skip_lo = (const __half*)d_xin_lo; p.skip_ch0 = skip_ch0;
   p.cout_real = cout; p.out_f32 = d_out;

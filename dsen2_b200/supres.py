@@ -102,7 +102,7 @@ class HostPipeline:
     chunks of whole patch rows and chunk k+1's input rows upload while chunk k computes and chunk k-1's owned
     output rows download (three CUDA streams, one device-resident tile).  Reusable across calls of one shape."""
 
-    def __init__(self, model, H, W, run_60=False, device=None, chunk_patch_rows=6, device_batch=None):
+    def __init__(self, model, H, W, run_60=False, device=None, chunk_patch_rows=None, device_batch=None):
         torch = _capi.require_cuda()
         self.torch, self.model, self.run_60 = torch, model, run_60
         self.H, self.W = int(H), int(W)
@@ -112,7 +112,7 @@ class HostPipeline:
             raise ValueError("10 m image size %dx%d must be a multiple of %d" % (H, W, self.r))
         self.dev = torch.device('cuda', torch.cuda.current_device()) if device is None else device
         self.ny, self.nx, self.S = sharding.tile_grid(self.H, self.W, self.P, self.B)
-        self.chunk_rows, self.device_batch = int(chunk_patch_rows), device_batch
+        self.chunk_rows, self.device_batch = chunk_patch_rows, device_batch
         mk = lambda h, w, c: torch.empty((h, w, c), dtype=torch.float32, device=self.dev)
         self.d10, self.d20 = mk(self.H, self.W, 4), mk(self.H // 2, self.W // 2, 6)
         self.d60 = mk(self.H // 6, self.W // 6, 2) if run_60 else None
@@ -142,8 +142,13 @@ class HostPipeline:
         self.up.wait_stream(main)
         self.down.wait_stream(main)
         done10 = done20 = done60 = None           # rows already resident on the device (per resolution)
+        # the first chunk's upload and the last chunk's download are not hidden behind compute: keep chunks small
+        # relative to this call's share of the tile (a rank of 8 holds ~12 patch rows of a full tile)
+        chunk_rows = self.chunk_rows
+        if chunk_rows is None:
+            chunk_rows = max(1, min(3, -(-num_patches // self.nx) // 12))
         for p0, cnt, (r0, r1), rects in sharding.plan_chunks(first_patch, num_patches, self.H, self.W, self.P, self.B,
-                                                             self.chunk_rows):
+                                                             int(chunk_rows)):
             with torch.cuda.stream(self.up):
                 done10 = self._upload(h10, self.d10, 1, r0, r1, done10)
                 done20 = self._upload(h20, self.d20, 2, r0, r1, done20)

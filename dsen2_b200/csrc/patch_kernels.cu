@@ -115,6 +115,66 @@ __global__ void bilinear_mirror_kernel(const float* __restrict__ in, int p, int 
   }
 }
 
+// Row-band form of the same arithmetic: a block owns kBilRows input rows of one plane (+ one mirrored halo row / column
+// on each side), divides every input value by 30000 ONCE into shared memory (the direct kernel does it four times per
+// output) and produces the s * kBilRows output rows from there; the x taps of a thread's columns are computed once.
+// Same operations per output as bilinear_mirror_kernel => same bits.
+constexpr int kBilRows = 16, kBilTX = 64, kBilTY = 4, kBilMaxX = 4;
+
+__device__ __forceinline__ int mirror_index(int g, int n) {
+  if (g < 0) g = -g;
+  if (g > n - 1) g = 2 * (n - 1) - g;
+  return g < 0 ? 0 : g;
+}
+
+__global__ void __launch_bounds__(kBilTX * kBilTY) bilinear_mirror_band_kernel(const float* __restrict__ in, int p, int s,
+                                                                              int bands, float post_div,
+                                                                              float* __restrict__ out) {
+  extern __shared__ float s_src[];                         // [kBilRows + 2][p + 2], value / 30000
+  const int plane = blockIdx.x / bands, band = blockIdx.x - plane * bands;
+  const int r0 = band * kBilRows, rows = min(kBilRows, p - r0);
+  const int pitch = p + 2, P = p * s;
+  const float k = 30000.0f;                                // the reference scales by 1/30000 around the resize
+  const float* src = in + (long long)plane * p * p;
+  const int tid = threadIdx.y * kBilTX + threadIdx.x;
+  for (int i = tid; i < (rows + 2) * pitch; i += kBilTX * kBilTY) {
+    const int lr = i / pitch, lc = i - lr * pitch;
+    s_src[i] = __fdiv_rn(__ldg(src + mirror_index(r0 - 1 + lr, p) * p + mirror_index(lc - 1, p)), k);
+  }
+  // x taps of this thread's output columns: local column of the left tap and the fraction
+  int xl[kBilMaxX];
+  float fx[kBilMaxX];
+#pragma unroll
+  for (int j = 0; j < kBilMaxX; ++j) {
+    const int ox = threadIdx.x + j * kBilTX;
+    const int t = 2 * ox + 1 - s;
+    const int i0 = (t >= 0) ? t / (2 * s) : -((-t + 2 * s - 1) / (2 * s));
+    fx[j] = (float)(t - i0 * 2 * s) / (float)(2 * s);
+    xl[j] = i0 + 1;
+  }
+  __syncthreads();
+  float* dst = out + (long long)plane * P * P;
+  for (int oyl = threadIdx.y; oyl < rows * s; oyl += kBilTY) {
+    const int oy = r0 * s + oyl;
+    const int t = 2 * oy + 1 - s;
+    const int i0 = (t >= 0) ? t / (2 * s) : -((-t + 2 * s - 1) / (2 * s));
+    const float fy = (float)(t - i0 * 2 * s) / (float)(2 * s);
+    const float* row0 = s_src + (i0 - (r0 - 1)) * pitch;
+    const float* row1 = row0 + pitch;
+#pragma unroll
+    for (int j = 0; j < kBilMaxX; ++j) {
+      const int ox = threadIdx.x + j * kBilTX;
+      if (ox < P) {
+        const float v00 = row0[xl[j]], v01 = row0[xl[j] + 1], v10 = row1[xl[j]], v11 = row1[xl[j] + 1];
+        const float c0 = v00 * (1.0f - fy) + v10 * fy;   // rows first, then columns (as the oracle)
+        const float c1 = v01 * (1.0f - fy) + v11 * fy;
+        const float r = (c0 * (1.0f - fx[j]) + c1 * fx[j]) * k;
+        dst[(long long)oy * P + ox] = (post_div == 1.0f) ? r : __fdiv_rn(r, post_div);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ //
 // stitch: thread per (patch, interior pixel), writes the C contiguous HWC floats it owns
 // ------------------------------------------------------------------------------------------ //
@@ -179,6 +239,163 @@ __global__ void bicubic_kernel(const TIn* __restrict__ in, int h, int w, int C, 
       }
     }
     out[idx] = acc;
+  }
+}
+
+// Tiled two-pass form of the same arithmetic (what resizeAlongDim does: dim `first` completely, then the other):
+// a block owns a TR x TC tile of output pixels, computes the first-pass intermediate it needs ONCE into shared
+// memory (float64, the values the reference stores in its intermediate array) and combines it along the second
+// dimension.  Per output 4 + ~2.4 products instead of 20, four + ~2.4 global loads instead of 16, 32-bit index
+// arithmetic, stores contiguous over (x, c).  Products and left-to-right sums are the same operations in the same
+// order as bicubic_kernel, so the result is bit-identical.  Falls back to the direct form for a tile whose
+// first-pass footprint exceeds the buffer (strong down-scaling).
+constexpr int kBicTR = 16;                                // output rows per tile (columns and the intermediate extent follow C)
+constexpr int kBicMaxTaps = 8;                            // taps per dimension the tiled path keeps in registers / smem
+
+template <typename TIn, bool FIRST0>
+__global__ void __launch_bounds__(256) bicubic_tiled_kernel(const TIn* __restrict__ in, int h, int w, int C,
+                                                            const double* __restrict__ wy, const int32_t* __restrict__ iy,
+                                                            int ty, int out_h, const double* __restrict__ wx,
+                                                            const int32_t* __restrict__ ix, int tx, int out_w,
+                                                            int kBicTC, int kBicSpan, double* __restrict__ out) {
+  extern __shared__ double s_inter[];                      // FIRST0: [TR][span][C]   else: [span][TC][C]
+  __shared__ int s_lo, s_hi;
+  __shared__ double s_wy[kBicTR * kBicMaxTaps];            // y taps of the tile's rows (uniform across a row's threads)
+  __shared__ int s_iy[kBicTR * kBicMaxTaps];
+  const int ox0 = blockIdx.x * kBicTC, oy0 = blockIdx.y * kBicTR;
+  const int tc = min(kBicTC, out_w - ox0), tr = min(kBicTR, out_h - oy0);
+  if (threadIdx.x == 0) { s_lo = 0x7fffffff; s_hi = -1; }
+  __syncthreads();
+  // footprint of the SECOND-pass taps along the dimension the intermediate keeps at input resolution
+  {
+    const int32_t* idx2 = FIRST0 ? ix + (long long)ox0 * tx : iy + (long long)oy0 * ty;
+    const int cnt = FIRST0 ? tc * tx : tr * ty;
+    int lo = 0x7fffffff, hi = -1;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const int v = idx2[i];
+      lo = min(lo, v); hi = max(hi, v);
+    }
+    if (hi >= 0) { atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
+  }
+  const bool taps_fit = ty <= kBicMaxTaps && tx <= kBicMaxTaps;
+  if (taps_fit)
+    for (int i = threadIdx.x; i < tr * ty; i += blockDim.x) {
+      s_wy[i] = wy[(long long)oy0 * ty + i];
+      s_iy[i] = iy[(long long)oy0 * ty + i];
+    }
+  __syncthreads();
+  const int lo = s_lo, span = s_hi - s_lo + 1;
+  if (span <= kBicSpan && taps_fit) {
+    const int rowc = tc * C;                               // (x, c) pairs of an output row of the tile
+    if (FIRST0) {
+      // pass 1 along y: inter[r][col][c] = sum_a in[iy[oy][a]][lo + col][c] * wy[oy][a]; a thread keeps its (col, c)
+      const int colc = span * C;
+      const long long wc = (long long)w * C;
+      for (int i = threadIdx.x; i < tr * colc; i += blockDim.x) {
+        const int r = i / colc, cc = i - r * colc;
+        const TIn* base = in + (long long)lo * C + cc;
+        double inter = 0.0;
+        for (int a = 0; a < ty; ++a) {
+          const double pr = __dmul_rn((double)base[s_iy[r * ty + a] * wc], s_wy[r * ty + a]);
+          inter = (a == 0) ? pr : __dadd_rn(inter, pr);
+        }
+        s_inter[i] = inter;
+      }
+      __syncthreads();
+      // pass 2 along x: a thread keeps its (x, c) and the x taps, walks the tile's rows
+      for (int xc = threadIdx.x; xc < rowc; xc += blockDim.x) {
+        const int x = xc / C, c = xc - x * C;
+        int off[kBicMaxTaps];
+        double wgt[kBicMaxTaps];
+#pragma unroll
+        for (int b = 0; b < kBicMaxTaps; ++b)
+          if (b < tx) {
+            off[b] = (ix[(ox0 + x) * tx + b] - lo) * C + c;
+            wgt[b] = wx[(ox0 + x) * tx + b];
+          }
+        double* dst = out + ((long long)oy0 * out_w + ox0) * C + xc;
+        for (int r = 0; r < tr; ++r) {
+          double acc = 0.0;
+#pragma unroll
+          for (int b = 0; b < kBicMaxTaps; ++b)
+            if (b < tx) {
+              const double pr = __dmul_rn(s_inter[r * colc + off[b]], wgt[b]);
+              acc = (b == 0) ? pr : __dadd_rn(acc, pr);
+            }
+          dst[(long long)r * out_w * C] = acc;
+        }
+      }
+    } else {
+      // pass 1 along x: inter[row][x][c] = sum_b in[lo + row][ix[ox][b]][c] * wx[ox][b]; a thread keeps (x, c) and the x taps
+      for (int xc = threadIdx.x; xc < rowc; xc += blockDim.x) {
+        const int x = xc / C, c = xc - x * C;
+        int off[kBicMaxTaps];
+        double wgt[kBicMaxTaps];
+#pragma unroll
+        for (int b = 0; b < kBicMaxTaps; ++b)
+          if (b < tx) {
+            off[b] = ix[(ox0 + x) * tx + b] * C + c;
+            wgt[b] = wx[(ox0 + x) * tx + b];
+          }
+        for (int row = 0; row < span; ++row) {
+          const TIn* base = in + (long long)(lo + row) * w * C;
+          double inter = 0.0;
+#pragma unroll
+          for (int b = 0; b < kBicMaxTaps; ++b)
+            if (b < tx) {
+              const double pr = __dmul_rn((double)base[off[b]], wgt[b]);
+              inter = (b == 0) ? pr : __dadd_rn(inter, pr);
+            }
+          s_inter[row * rowc + xc] = inter;
+        }
+      }
+      __syncthreads();
+      // pass 2 along y
+      for (int xc = threadIdx.x; xc < rowc; xc += blockDim.x) {
+        double* dst = out + ((long long)oy0 * out_w + ox0) * C + xc;
+        for (int r = 0; r < tr; ++r) {
+          double acc = 0.0;
+          for (int a = 0; a < ty; ++a) {
+            const double pr = __dmul_rn(s_inter[(s_iy[r * ty + a] - lo) * rowc + xc], s_wy[r * ty + a]);
+            acc = (a == 0) ? pr : __dadd_rn(acc, pr);
+          }
+          dst[(long long)r * out_w * C] = acc;
+        }
+      }
+    }
+    return;
+  }
+  // direct form (same operations as bicubic_kernel)
+  const int outs = tr * tc * C;
+  for (int i = threadIdx.x; i < outs; i += blockDim.x) {
+    const int r = i / (tc * C), xc = i - r * (tc * C);
+    const int x = xc / C, c = xc - x * C;
+    const int oy = oy0 + r, ox = ox0 + x;
+    double acc = 0.0;
+    if (FIRST0) {
+      for (int b = 0; b < tx; ++b) {
+        const int col = ix[ox * tx + b];
+        double inter = 0.0;
+        for (int a = 0; a < ty; ++a) {
+          const double pr = __dmul_rn((double)in[((long long)iy[oy * ty + a] * w + col) * C + c], wy[oy * ty + a]);
+          inter = (a == 0) ? pr : __dadd_rn(inter, pr);
+        }
+        const double pr = __dmul_rn(inter, wx[ox * tx + b]);
+        acc = (b == 0) ? pr : __dadd_rn(acc, pr);
+      }
+    } else {
+      for (int a = 0; a < ty; ++a) {
+        const int row = iy[oy * ty + a];
+        double inter = 0.0;
+        for (int b = 0; b < tx; ++b) {
+          const double pr = __dmul_rn((double)in[((long long)row * w + ix[ox * tx + b]) * C + c], wx[ox * tx + b]);
+          inter = (b == 0) ? pr : __dadd_rn(inter, pr);
+        }
+        const double pr = __dmul_rn(inter, wy[oy * ty + a]);
+        acc = (a == 0) ? pr : __dadd_rn(acc, pr);
+      }
+    }
+    out[((long long)oy * out_w + ox0) * C + xc] = acc;
   }
 }
 
@@ -352,6 +569,13 @@ extern "C" int dsen2_bilinear_mirror_up(const float* d_in, int planes, int p, in
                 "dsen2_bilinear_mirror_up: bad sizes");
   if (planes == 0) return 0;
   const long long total = (long long)planes * p * s * p * s;
+  const int bands = (p + kBilRows - 1) / kBilRows;
+  const size_t band_smem = (size_t)(kBilRows + 2) * (p + 2) * sizeof(float);
+  if (p >= 2 && p * s <= kBilTX * kBilMaxX && band_smem <= 48 * 1024 && (long long)planes * bands < (1LL << 31)) {
+    bilinear_mirror_band_kernel<<<(unsigned)(planes * bands), dim3(kBilTX, kBilTY), band_smem, (cudaStream_t)stream>>>(
+        d_in, p, s, bands, post_divisor, d_out);
+    return check_launch("bilinear_mirror_up");
+  }
   const int block = 256;
   bilinear_mirror_kernel<<<grid_for(total, block), block, 0, (cudaStream_t)stream>>>(d_in, p, s, total, post_divisor,
                                                                                      d_out);
@@ -385,9 +609,24 @@ extern "C" int dsen2_bicubic_imresize(const void* d_in, int in_is_f64, int h, in
                     (first_dim == 0 || first_dim == 1),
                 DSEN2_E_BADARG, "dsen2_bicubic_imresize: bad sizes");
   const long long total = (long long)out_h * out_w * C;
+  cudaStream_t s = (cudaStream_t)stream;
+  // tile: 16 rows x TC columns with TC * C ~ 256-384 (x, c) pairs per row; the intermediate gets 40 KB of shared memory
+  const int tcol = C >= 6 ? 64 : (C >= 3 ? 96 : 128);
+  const int span_cap = (int)((40 * 1024 / sizeof(double)) / ((size_t)(first_dim == 0 ? kBicTR : tcol) * C));
+  const size_t inter_bytes = (size_t)(first_dim == 0 ? kBicTR : tcol) * span_cap * C * sizeof(double);
+  const long long gy = ((long long)out_h + kBicTR - 1) / kBicTR;
+  if (span_cap >= 8 && gy <= 65535 && (long long)out_w * taps_x < (1LL << 29) && (long long)out_h * taps_y < (1LL << 29)) {
+    const dim3 tgrid((unsigned)((out_w + tcol - 1) / tcol), (unsigned)gy);
+#define DSEN2_BIC(T, F0)                                                                                           \
+  bicubic_tiled_kernel<T, F0><<<tgrid, 256, inter_bytes, s>>>((const T*)d_in, h, w, C, d_wy, d_iy, taps_y, out_h, \
+                                                              d_wx, d_ix, taps_x, out_w, tcol, span_cap, d_out)
+    if (in_is_f64) { if (first_dim == 0) DSEN2_BIC(double, true); else DSEN2_BIC(double, false); }
+    else           { if (first_dim == 0) DSEN2_BIC(float, true);  else DSEN2_BIC(float, false); }
+#undef DSEN2_BIC
+    return check_launch("bicubic_imresize");
+  }
   const int block = 256;
   const dim3 grid = grid_for(total, block);
-  cudaStream_t s = (cudaStream_t)stream;
   if (in_is_f64)
     bicubic_kernel<double><<<grid, block, 0, s>>>((const double*)d_in, h, w, C, d_wy, d_iy, taps_y, out_h, d_wx, d_ix,
                                                   taps_x, out_w, first_dim, total, d_out);

@@ -2,7 +2,7 @@
 
 ``imresize(I, scalar_scale=None, output_shape=None)`` as imresize.py:80-112.  The tap tables are
 built on the host in float64 (a few KB; same formulas as ``contributions`` :28-48) and the
-separable filter runs in ``bicubic_kernel`` (float64, left-to-right sums => bit-identical).
+separable filter runs in ``bicubic_tiled_kernel`` (float64, left-to-right sums => bit-identical).
 """
 from math import ceil
 
@@ -39,21 +39,37 @@ def tap_tables(in_length, out_length, scale, kernel_width=4.0):
     return np.ascontiguousarray(weights[:, keep]), np.ascontiguousarray(indices[:, keep].astype(np.int32))
 
 
+_TABLES = {}
+
+
+def _device_tables(dev, in_length, out_length, scale):
+    """Tap tables of one dimension on ``dev`` (cached: a tile is resized with the same tables every time)."""
+    key = (str(dev), in_length, out_length, scale)
+    hit = _TABLES.get(key)
+    if hit is None:
+        torch = _capi.require_cuda()
+        if len(_TABLES) > 32:
+            _TABLES.clear()
+        w, i = tap_tables(in_length, out_length, scale)
+        hit = _TABLES[key] = (torch.from_numpy(w).to(dev), torch.from_numpy(i).to(dev), int(w.shape[1]))
+    return hit
+
+
 def imresize_device(img, scale, output_size):
     """img: CUDA float32/float64 (h, w, C) -> CUDA float64 (out_h, out_w, C)."""
     torch = _capi.require_cuda()
     assert img.is_cuda and img.is_contiguous() and img.dim() == 3 and img.dtype in (torch.float32, torch.float64)
     h, w, C = img.shape
-    wy, iy = tap_tables(h, output_size[0], scale[0])
-    wx, ix = tap_tables(w, output_size[1], scale[1])
-    order = np.argsort(np.array(scale))           # imresize.py:95 (stable for equal scales: dim 0 first)
     dev = img.device
-    t = [torch.from_numpy(a).to(dev) for a in (wy, iy, wx, ix)]
+    wy, iy, ty_ = _device_tables(dev, h, int(output_size[0]), float(scale[0]))
+    wx, ix, tx_ = _device_tables(dev, w, int(output_size[1]), float(scale[1]))
+    order = np.argsort(np.array(scale))           # imresize.py:95 (stable for equal scales: dim 0 first)
+    t = [wy, iy, wx, ix]
     out = torch.empty((output_size[0], output_size[1], C), dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
         rc = _capi.lib().dsen2_bicubic_imresize(_capi.ptr(img), int(img.dtype == torch.float64), h, w, C,
-                                                _capi.ptr(t[0]), _capi.ptr(t[1]), wy.shape[1], output_size[0],
-                                                _capi.ptr(t[2]), _capi.ptr(t[3]), wx.shape[1], output_size[1],
+                                                _capi.ptr(t[0]), _capi.ptr(t[1]), ty_, output_size[0],
+                                                _capi.ptr(t[2]), _capi.ptr(t[3]), tx_, output_size[1],
                                                 int(order[0]), _capi.ptr(out), _capi.stream_ptr())
     _capi.check(rc, "dsen2_bicubic_imresize")
     return out

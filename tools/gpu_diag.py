@@ -216,6 +216,41 @@ def check_pair_res32_debug_sweep():
         subprocess.run([sys.executable, os.path.abspath(__file__), '--one', 'pair_res32_alone'], env=env, timeout=120)
 
 
+def check_hbm_kernels():
+    """Standalone drop-in kernels behind utils.patches / utils.imresize at full-tile sizes: ms and ALGORITHMIC GB/s
+    (extract reads + writes the patch stack, bilinear reads p^2 + writes (2p)^2 per plane, recompose
+    reads + writes the owned pixels, bicubic reads the input + writes the float64 output)."""
+    import torch
+    from dsen2_b200 import imresize, patches
+    T = 10980
+    gen = torch.Generator(device='cuda').manual_seed(1)
+    d10 = torch.rand((T, T, 4), device='cuda', generator=gen) * 4000
+    d20 = torch.rand((T // 2, T // 2, 6), device='cuda', generator=gen) * 4000
+    n = 99 * 20                                             # 20 patch rows of the 20 m path
+    out10 = torch.empty((n, 4, 128, 128), device='cuda')
+    ms = _time(torch, lambda: patches.extract_patches_device(d10, 2, 64, 4, 0, n, 2000.0, out10))
+    print('extract 10 m (n=%d, 4x128x128, /2000) : %.3f ms  %.0f GB/s' % (n, ms, 2 * out10.numel() * 4 / ms / 1e6), flush=True)
+    out20 = torch.empty((n, 6, 64, 64), device='cuda')
+    ms = _time(torch, lambda: patches.extract_patches_device(d20, 1, 64, 4, 0, n, 1.0, out20))
+    print('extract 20 m (n=%d, 6x64x64)          : %.3f ms  %.0f GB/s' % (n, ms, 2 * out20.numel() * 4 / ms / 1e6), flush=True)
+    up = torch.empty((n, 6, 128, 128), device='cuda')
+    ms = _time(torch, lambda: patches.bilinear_up_device(out20, 2, 2000.0, up))
+    print('bilinear mirror x2 (%d planes 64->128) : %.3f ms  %.0f GB/s' % (n * 6, ms, (out20.numel() + up.numel()) * 4 / ms / 1e6), flush=True)
+    canvas = torch.zeros((T, T, 6), device='cuda')
+    ms = _time(torch, lambda: patches.recompose_device(up, 8, T, T, 0, 2000.0, canvas))
+    owned = n * 112 * 112 * 6 * 4
+    print('recompose (n=%d, 6 bands, x2000)      : %.3f ms  %.0f GB/s' % (n, ms, 2 * owned / ms / 1e6), flush=True)
+    del out10, up, canvas, d10
+    torch.cuda.empty_cache()
+    ms = _time(torch, lambda: imresize.imresize_device(d20, (2.0, 2.0), (T, T)), iters=4, warm=2)
+    print('bicubic imresize x2 (5490^2x6 -> f64)  : %.3f ms  %.0f GB/s  (incl. tap tables on the host)' % (
+        ms, (d20.numel() * 4 + T * T * 6 * 8) / ms / 1e6), flush=True)
+    d60 = torch.rand((T // 6, T // 6, 2), device='cuda', generator=gen) * 4000
+    ms = _time(torch, lambda: imresize.imresize_device(d60, (6.0, 6.0), (T, T)), iters=4, warm=2)
+    print('bicubic imresize x6 (1830^2x2 -> f64)  : %.3f ms  %.0f GB/s  (incl. tap tables on the host)' % (
+        ms, (d60.numel() * 4 + T * T * 2 * 8) / ms / 1e6), flush=True)
+
+
 def check_pair_knob_sweep():
     for pa, px, de in (('2', '1', '0'), ('2', '1', '1'), ('3', '2', '1'), ('3', '1', '0'), ('2', '2', '0'), ('1', '1', '0'),
                        ('0', '0', '0'), ('4', '1', '0'), ('2', '3', '1')):

@@ -115,6 +115,13 @@ class S2Model:
         'fp32' = a separate fp32 tensor (1536 B/pixel/resblock; ``DSEN2_TRUNK=fp32``, what the training step uses)."""
         return 'fp32' if os.environ.get('DSEN2_TRUNK', 'q8') == 'fp32' else 'q8'
 
+    @property
+    def xin16(self):
+        """The default inference path prepares the network input un-gathered (16 channels, ``dsen2_prep16_*``) and
+        runs the first layer with nine taps (``dsen2_conv_head16_q``); the fp32-trunk variant and a network without
+        resblocks keep the 64-channel form with the three horizontal taps pre-gathered (what the training step uses)."""
+        return self.fast_path and self.trunk_format != 'fp32' and self.num_layers > 0
+
     def _ensure_packed(self, device):
         torch = _capi.require_cuda()
         key = device.index if device.index is not None else torch.cuda.current_device()
@@ -131,7 +138,12 @@ class S2Model:
                 cin, cout = self.layer_shapes[i]
                 head, tail = i == 0, i == len(self._weights) - 1
                 src = torch.from_numpy(k).to(device)
-                if head and self.fast_path:
+                if head and self.xin16:
+                    dst = torch.empty((9, 2 * F, 16), dtype=torch.float16, device=device)
+                    _capi.check(lib.dsen2_pack_head16_weights(_capi.ptr(src), cin, F, _capi.ptr(dst), st),
+                                "dsen2_pack_head16_weights")
+                    cout_pad = F
+                elif head and self.fast_path:
                     dst = torch.empty((3, 2 * F, 64), dtype=torch.float16, device=device)
                     _capi.check(lib.dsen2_pack_head_weights(_capi.ptr(src), cin, F, _capi.ptr(dst), st),
                                 "dsen2_pack_head_weights")
@@ -172,7 +184,8 @@ class S2Model:
             F = self.feature_size
             mk = lambda c: torch.empty((n, P, P, c), dtype=torch.float16, device=dev)
             if self.fast_path:
-                buf = dict(xin_hi=mk(64), xin_lo=mk(64), x_hi=mk(F), x_lo=mk(F), t=mk(F))
+                cx = 16 if self.xin16 else 64                                # prepared input: un-gathered / 3 taps gathered
+                buf = dict(xin_hi=mk(cx), xin_lo=mk(cx), x_hi=mk(F), x_lo=mk(F), t=mk(F))
                 if self.trunk_format == 'fp32':                              # tile-row-major fp32 trunk
                     buf['x32'] = torch.empty((n, P, (P + 7) // 8, F // 4, 8, 4), dtype=torch.float32, device=dev)
                 else:                                                        # low bytes of the fp16 + 8 bit trunk
@@ -202,9 +215,9 @@ class S2Model:
             # fp16 + 8 bit trunk: x_hi (NHWC, what the next convolution reads) updated in place + one byte per element
             # (include/dsen2_b200.h, dsen2_conv_resq); the last block hands the tail x_hi, x_lo
             xq = buf['xq']
-            self._timed(timers, 'conv_head', n, lambda: _capi.check(lib.dsen2_conv_head_q(
+            self._timed(timers, 'conv_head', n, lambda: _capi.check(lib.dsen2_conv_head16_q(
                 ptr(buf['xin_hi']), ptr(buf['xin_lo']), ptr(wts[0]), ptr(biases[0]), n, P, P, F, ptr(x_hi), ptr(xq), st),
-                "dsen2_conv_head_q"))
+                "dsen2_conv_head16_q"))
             for l in range(L):
                 self._timed(timers, 'conv_res1', n, lambda: _capi.check(lib.dsen2_conv3x3(
                     ptr(x_hi), ptr(wts[1 + 2 * l]), ptr(biases[1 + 2 * l]), n, P, P, F, F, 9, _capi.EPI_RELU, None,
@@ -266,11 +279,13 @@ class S2Model:
             st = _capi.stream_ptr()
             x2, c2 = (xs[2], self.in_channels[2]) if len(xs) == 3 else (None, 0)
             if self.fast_path:
-                self._timed(timers, 'prep', n, lambda: _capi.check(lib.dsen2_prep_from_patches(
+                prep = lib.dsen2_prep16_from_patches if self.xin16 else lib.dsen2_prep_from_patches
+                tail = lib.dsen2_conv_tail16 if self.xin16 else lib.dsen2_conv_tail
+                self._timed(timers, 'prep', n, lambda: _capi.check(prep(
                     ptr(xs[0]), self.in_channels[0], ptr(xs[1]), self.in_channels[1], ptr(x2), c2, n, P,
                     ptr(buf['xin_hi']), ptr(buf['xin_lo']), st), "dsen2_prep_from_patches"))
                 self._trunk(buf, wts, biases, n, P, st, timers)
-                self._timed(timers, 'conv_tail', n, lambda: _capi.check(lib.dsen2_conv_tail(
+                self._timed(timers, 'conv_tail', n, lambda: _capi.check(tail(
                     ptr(buf['x_hi']), ptr(buf['x_lo']), ptr(wts[-1]), ptr(biases[-1]), ptr(buf['xin_hi']),
                     ptr(buf['xin_lo']), sum(self.in_channels) - self.out_channels, self.out_channels, n, P, P,
                     ptr(out), st), "dsen2_conv_tail"))
@@ -288,6 +303,8 @@ class S2Model:
         """Same as ``forward_device`` through the single C entry point ``dsen2_s2model_forward`` (what a C caller of
         ``include/dsen2_b200.h`` uses): one call, workspace supplied by the caller."""
         torch = _capi.require_cuda()
+        if self.fast_path and self.num_layers > 0 and not self.xin16:
+            raise _capi.DSen2Error("dsen2_s2model_forward runs the fp16 + 8 bit trunk; unset DSEN2_TRUNK=fp32")
         n, _, P, _ = xs[0].shape
         dev = xs[0].device
         _wts, _biases, wp, bp = self._ensure_packed(dev)
@@ -319,11 +336,13 @@ class S2Model:
         buf = self._buffers(dev, n, patch)
         with torch.cuda.device(dev):
             st = _capi.stream_ptr()
-            self._timed(timers, 'prep', n, lambda: _capi.check(lib.dsen2_prep_from_images(
+            prep = lib.dsen2_prep16_from_images if self.xin16 else lib.dsen2_prep_from_images
+            tail = lib.dsen2_conv_tail16_stitch if self.xin16 else lib.dsen2_conv_tail_stitch
+            self._timed(timers, 'prep', n, lambda: _capi.check(prep(
                 ptr(d10), ptr(d20), ptr(d60), H, W, patch, border, first_patch, n, float(mul), ptr(buf['xin_hi']),
                 ptr(buf['xin_lo']), st), "dsen2_prep_from_images"))
             self._trunk(buf, wts, biases, n, patch, st, timers)
-            self._timed(timers, 'conv_tail', n, lambda: _capi.check(lib.dsen2_conv_tail_stitch(
+            self._timed(timers, 'conv_tail', n, lambda: _capi.check(tail(
                 ptr(buf['x_hi']), ptr(buf['x_lo']), ptr(wts[-1]), ptr(biases[-1]), ptr(buf['xin_hi']),
                 ptr(buf['xin_lo']), sum(self.in_channels) - self.out_channels, self.out_channels, n, patch,
                 first_patch, border, H, W, float(mul), ptr(canvas), st), "dsen2_conv_tail_stitch"))

@@ -52,6 +52,8 @@ static inline bool needs_config(bool (&flags)[64]) {
 
 // conv_tcgen05.cu
 int make_tmap_f16(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint32_t* box);
+// same with the shared-memory swizzle span chosen by the caller (128 or 32 bytes = the box's inner extent)
+int make_tmap_f16_sw(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint32_t* box, int swizzle_bytes);
 int device_sm_count_and_check(int* sms);
 // conv_pair.cu
 int conv_pair_res(const void* d_in, const void* d_w, const float* d_bias, int n, int H, int W, int features, int epilogue,
@@ -314,6 +316,19 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
+  return d;
+}
+// K-major operand whose rows are ROWB bytes (128: SWIZZLE_128B, layout type 2; 32: SWIZZLE_32B, layout type 6);
+// 8-row groups `sbo_bytes` apart
+template <int ROWB>
+__device__ __forceinline__ uint64_t umma_desc_k_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+  static_assert(ROWB == 128 || ROWB == 32, "row = one swizzle span of 128 or 32 bytes");
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  if (ROWB == 32) d |= (uint64_t)1 << 16;                   // LBO: not used for a K extent of one swizzle span (CUTLASS writes 1)
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(ROWB == 128 ? 2 : 6) << 61;
   return d;
 }
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t base_offset = 0) {

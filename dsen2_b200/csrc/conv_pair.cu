@@ -53,6 +53,7 @@ struct PairParams {
   const __half* skip_hi;   // prepared input (n,H,W,64): centre-tap channels 16..31 hold the network inputs
   const __half* skip_lo;
   int skip_ch0;            // first skip band inside the 16-channel group
+  int skip_pitch, skip_off;   // channels per pixel of the prepared input and offset of the centre tap (64 / 16, or 16 / 0)
   int cout_real;
   float out_mul;
   float* out_f32;
@@ -64,8 +65,12 @@ struct PairParams {
   int first_patch, img_h, img_w, border, grid_ny, grid_nx;
 };
 
-template <int NTOT_, bool SPLIT_, int NMAPS_, int KPM_, int NTAPS_, int KSTEPS_, int STAGES_, int EPI_, int WSTAGES_ = 0>
+template <int NTOT_, bool SPLIT_, int NMAPS_, int KPM_, int NTAPS_, int KSTEPS_, int STAGES_, int EPI_, int WSTAGES_ = 0,
+          int ROWB_ = 128>
 struct PairCfg {
+  static constexpr int ROWB = ROWB_;            // bytes per pixel row of a k-block in smem = swizzle span (128: 64 ch, 32: 16 ch)
+  static constexpr int KCH = ROWB_ / 2;         // channels per k-block
+  static_assert(KSTEPS_ * 32 <= ROWB_, "the K = 16 MMAs of a k-block stay inside its row");
   static constexpr int EPI_WARPS = 8;           // two per TMEM lane quarter, half of the channels each
   static constexpr int PRODUCER_WARP = EPI_WARPS;
   static constexpr int MMA_WARP = EPI_WARPS + 1;
@@ -83,10 +88,10 @@ struct PairCfg {
   static constexpr int EPI = EPI_;
   static constexpr int CH = SPLIT_ ? NTOT_ / 2 : NTOT_;   // output channels
   static constexpr int BOXW = NTAPS_ == 9 ? 10 : 8;
-  static constexpr int BOX_BYTES = kBoxH * BOXW * 128;
+  static constexpr int BOX_BYTES = kBoxH * BOXW * ROWB_;
   static constexpr int STAGE_BYTES = (BOX_BYTES + 1023) / 1024 * 1024;
   static constexpr int SLAB_ROWS = NTOT_ / 2;
-  static constexpr int SLAB_BYTES = SLAB_ROWS * 128;
+  static constexpr int SLAB_BYTES = SLAB_ROWS * ROWB_;
   static constexpr int NSLABS = NTAPS_ * KPM_;
   static constexpr int W_BYTES = (WSTAGES_ == 0 ? NSLABS : WSTAGES_) * SLAB_BYTES;
   static constexpr int TMEM_COLS = (2 * NTOT_ < 32) ? 32 : 2 * NTOT_;
@@ -416,7 +421,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
       if constexpr (Cfg::RESIDENT) {
         if (rank == 0) mbar_expect_tx(wfull, 2 * Cfg::W_BYTES);
         for (int s = 0; s < Cfg::NSLABS; ++s)
-          tma_load_3d_pair(s_w + s * Cfg::SLAB_BYTES, &tm_w, wfull, (s % Cfg::KPM) * 64, (int)rank * Cfg::SLAB_ROWS,
+          tma_load_3d_pair(s_w + s * Cfg::SLAB_BYTES, &tm_w, wfull, (s % Cfg::KPM) * Cfg::KCH, (int)rank * Cfg::SLAB_ROWS,
                            s / Cfg::KPM);
       }
       int stage = 0, ws = 0;
@@ -430,7 +435,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
           const TileXY tn = decode_tile(2 * (pt + p.pf_a * npairs) + rank, p.tiles_x, p.tiles_y);
 #pragma unroll
           for (int kb = 0; kb < Cfg::KB; ++kb)
-            tma_prefetch_4d((Cfg::NMAPS == 2 && kb >= Cfg::KPM) ? &tm_a1 : &tm_a0, (kb % Cfg::KPM) * 64,
+            tma_prefetch_4d((Cfg::NMAPS == 2 && kb >= Cfg::KPM) ? &tm_a1 : &tm_a0, (kb % Cfg::KPM) * Cfg::KCH,
                             (tn.tx + p.tx0) * 8 - (Cfg::NTAPS == 9 ? 1 : 0), tn.ty * 16 - 1, tn.b);
         }
 #pragma unroll 1
@@ -441,7 +446,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
           } else {
             if (rank == 0) mbar_expect_tx(&full[stage], 2 * Cfg::BOX_BYTES);
             const CUtensorMap* m = (Cfg::NMAPS == 2 && kb >= Cfg::KPM) ? &tm_a1 : &tm_a0;
-            tma_load_4d_pair(s_a + stage * Cfg::STAGE_BYTES, m, &full[stage], (kb % Cfg::KPM) * 64, bx, by, b);
+            tma_load_4d_pair(s_a + stage * Cfg::STAGE_BYTES, m, &full[stage], (kb % Cfg::KPM) * Cfg::KCH, bx, by, b);
           }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
           if constexpr (!Cfg::RESIDENT) {            // this k-block's nine weight slabs, in the order the MMAs use them
@@ -449,7 +454,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
             for (int tap = 0; tap < Cfg::NTAPS; ++tap) {
               mbar_wait(&wr_empty[ws], wphase ^ 1);
               if (rank == 0) mbar_expect_tx(&wr_full[ws], 2 * Cfg::SLAB_BYTES);
-              tma_load_3d_pair(s_w + ws * Cfg::SLAB_BYTES, &tm_w, &wr_full[ws], (kb % Cfg::KPM) * 64,
+              tma_load_3d_pair(s_w + ws * Cfg::SLAB_BYTES, &tm_w, &wr_full[ws], (kb % Cfg::KPM) * Cfg::KCH,
                                (int)rank * Cfg::SLAB_ROWS, tap);
               if (++ws == Cfg::WSTAGES) { ws = 0; wphase ^= 1; }
             }
@@ -483,7 +488,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
           for (int tap = 0; tap < Cfg::NTAPS; ++tap) {
             const int dy = Cfg::NTAPS == 9 ? tap / 3 : tap;
             const int dx = Cfg::NTAPS == 9 ? tap % 3 : 0;
-            const uint32_t a0 = sa + (uint32_t)((dy * Cfg::BOXW + dx) * 128);
+            const uint32_t a0 = sa + (uint32_t)((dy * Cfg::BOXW + dx) * Cfg::ROWB);
             uint32_t b0 = sb + (uint32_t)(tap * Cfg::KPM * Cfg::SLAB_BYTES);
             if constexpr (!Cfg::RESIDENT) {
               mbar_wait(&wr_full[ws], wphase);
@@ -492,8 +497,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
             }
 #pragma unroll
             for (int k = 0; k < Cfg::KSTEPS; ++k)
-              umma_f16_ss_pair(d_tmem, umma_desc_sw128_sbo(a0 + k * 32, Cfg::BOXW * 128),
-                               umma_desc_sw128_sbo(b0 + k * 32, 1024), idesc, (uint32_t)((kb | tap | k) != 0));
+              umma_f16_ss_pair(d_tmem, umma_desc_k_sbo<Cfg::ROWB>(a0 + k * 32, Cfg::BOXW * Cfg::ROWB),
+                               umma_desc_k_sbo<Cfg::ROWB>(b0 + k * 32, 8 * Cfg::ROWB), idesc,
+                               (uint32_t)((kb | tap | k) != 0));
             if constexpr (!Cfg::RESIDENT) {
               umma_commit_pair(&wr_empty[ws]);                   // frees the weight slot in both CTAs
               if (++ws == Cfg::WSTAGES) { ws = 0; wphase ^= 1; }
@@ -564,8 +570,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
           }
         }
         if (write) {
-          const __half* sh = p.skip_hi + pix * 64 + 16 + p.skip_ch0;
-          const __half* sl = p.skip_lo + pix * 64 + 16 + p.skip_ch0;
+          const __half* sh = p.skip_hi + pix * p.skip_pitch + p.skip_off + p.skip_ch0;
+          const __half* sl = p.skip_lo + pix * p.skip_pitch + p.skip_off + p.skip_ch0;
 #pragma unroll
           for (int c = 0; c < 16; ++c)
             skip[c] = (c < p.cout_real) ? __half2float(__ldg(sh + c)) + __half2float(__ldg(sl + c)) : 0.f;
@@ -823,6 +829,8 @@ using CfgResidualQLast = PairCfg<128, false, 1, 2, 9, 4, 3, kEpiResidualQLast>;
 using CfgRelu256 = PairCfg<256, false, 1, 4, 9, 4, 3, kEpiRelu, 8>;
 using CfgResidual256 = PairCfg<256, false, 1, 4, 9, 4, 3, kEpiResidual, 8>;
 using CfgHead = PairCfg<256, true, 2, 1, 3, 3, 6, kEpiRelu>;
+// first layer on the un-gathered 16-channel input: nine taps through shifted descriptors into a 32-byte-row halo box
+using CfgHead16 = PairCfg<256, true, 2, 1, 9, 1, 6, kEpiRelu, 0, 32>;
 using CfgTail = PairCfg<32, true, 2, 2, 9, 4, 6, kEpiTail>;
 
 template <class Cfg>
@@ -843,16 +851,16 @@ static int launch_pair(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
 template <class Cfg>
 static int make_maps(CUtensorMap* a0, CUtensorMap* a1, CUtensorMap* w, const void* d_a0, const void* d_a1,
                      const void* d_w, int n, int H, int W) {
-  const int ca = Cfg::KPM * 64;
+  const int ca = Cfg::KPM * Cfg::KCH;
   const uint64_t dims[4] = {(uint64_t)ca, (uint64_t)W, (uint64_t)H, (uint64_t)n};
-  const uint32_t box[4] = {64, (uint32_t)Cfg::BOXW, (uint32_t)kBoxH, 1};
-  int rc = make_tmap_f16(a0, d_a0, 4, dims, box);
+  const uint32_t box[4] = {(uint32_t)Cfg::KCH, (uint32_t)Cfg::BOXW, (uint32_t)kBoxH, 1};
+  int rc = make_tmap_f16_sw(a0, d_a0, 4, dims, box, Cfg::ROWB);
   if (rc) return rc;
-  rc = make_tmap_f16(a1, d_a1 ? d_a1 : d_a0, 4, dims, box);
+  rc = make_tmap_f16_sw(a1, d_a1 ? d_a1 : d_a0, 4, dims, box, Cfg::ROWB);
   if (rc) return rc;
   const uint64_t wd[3] = {(uint64_t)ca, (uint64_t)Cfg::NTOT, (uint64_t)Cfg::NTAPS};
-  const uint32_t wb[3] = {64, (uint32_t)Cfg::SLAB_ROWS, 1};
-  return make_tmap_f16(w, d_w, 3, wd, wb);
+  const uint32_t wb[3] = {(uint32_t)Cfg::KCH, (uint32_t)Cfg::SLAB_ROWS, 1};
+  return make_tmap_f16_sw(w, d_w, 3, wd, wb, Cfg::ROWB);
 }
 
 static int fill_tiles(PairParams& p, int n, int H, int W) {
@@ -945,6 +953,7 @@ extern "C" int dsen2_conv_res32(const void* d_in, const void* d_w, const float* 
   return launch_pair<CfgResidual32>(a0, a1, w, p, sms, (cudaStream_t)stream, "conv_pair<residual32>");
 }
 
+template <class CfgH>
 static int head_common(const char* name, const void* d_xin_hi, const void* d_xin_lo, const void* d_w, const float* d_bias,
                        int n, int H, int W, int feature_size, void* d_out_hi, void* d_out_lo, float* d_trunk32,
                        void* d_trunk_lo8, void* stream) {
@@ -968,23 +977,30 @@ static int head_common(const char* name, const void* d_xin_hi, const void* d_xin
   p.x32 = d_trunk32;
   p.xq = (uint8_t*)d_trunk_lo8;
   CUtensorMap a0, a1, w;
-  rc = make_maps<CfgHead>(&a0, &a1, &w, d_xin_hi, d_xin_lo, d_w, n, H, W);
+  rc = make_maps<CfgH>(&a0, &a1, &w, d_xin_hi, d_xin_lo, d_w, n, H, W);
   if (rc) return rc;
-  return launch_pair<CfgHead>(a0, a1, w, p, sms, (cudaStream_t)stream, "conv_pair<head>");
+  return launch_pair<CfgH>(a0, a1, w, p, sms, (cudaStream_t)stream, "conv_pair<head>");
 }
 
 extern "C" int dsen2_conv_head(const void* d_xin_hi, const void* d_xin_lo, const void* d_w, const float* d_bias,
                                int n, int H, int W, int feature_size, void* d_out_hi, void* d_out_lo,
                                float* d_trunk32, void* stream) {
-  return head_common("dsen2_conv_head", d_xin_hi, d_xin_lo, d_w, d_bias, n, H, W, feature_size, d_out_hi, d_out_lo,
+  return head_common<CfgHead>("dsen2_conv_head", d_xin_hi, d_xin_lo, d_w, d_bias, n, H, W, feature_size, d_out_hi, d_out_lo,
                      d_trunk32, nullptr, stream);
 }
 
 extern "C" int dsen2_conv_head_q(const void* d_xin_hi, const void* d_xin_lo, const void* d_w, const float* d_bias,
                                  int n, int H, int W, int feature_size, void* d_x_hi, void* d_trunk_lo8, void* stream) {
   DSEN2_REQUIRE(d_trunk_lo8, DSEN2_E_BADARG, "dsen2_conv_head_q: null pointer");
-  return head_common("dsen2_conv_head_q", d_xin_hi, d_xin_lo, d_w, d_bias, n, H, W, feature_size, d_x_hi, nullptr, nullptr,
-                     d_trunk_lo8, stream);
+  return head_common<CfgHead>("dsen2_conv_head_q", d_xin_hi, d_xin_lo, d_w, d_bias, n, H, W, feature_size, d_x_hi, nullptr,
+                              nullptr, d_trunk_lo8, stream);
+}
+
+extern "C" int dsen2_conv_head16_q(const void* d_xin_hi, const void* d_xin_lo, const void* d_w, const float* d_bias,
+                                   int n, int H, int W, int feature_size, void* d_x_hi, void* d_trunk_lo8, void* stream) {
+  DSEN2_REQUIRE(d_trunk_lo8, DSEN2_E_BADARG, "dsen2_conv_head16_q: null pointer");
+  return head_common<CfgHead16>("dsen2_conv_head16_q", d_xin_hi, d_xin_lo, d_w, d_bias, n, H, W, feature_size, d_x_hi,
+                                nullptr, nullptr, d_trunk_lo8, stream);
 }
 
 extern "C" int dsen2_conv_resq(const void* d_in, const void* d_w, const float* d_bias, int n, int H, int W,
@@ -1012,9 +1028,9 @@ extern "C" int dsen2_conv_resq(const void* d_in, const void* d_w, const float* d
   return launch_pair<CfgResidualQ>(a0, a1, w, p, sms, (cudaStream_t)stream, "conv_pair<residualq>");
 }
 
-static int tail_common(PairParams& p, const void* d_x_hi, const void* d_x_lo, const void* d_w, const float* d_bias,
-                       const void* d_xin_hi, const void* d_xin_lo, int skip_ch0, int cout, int n, int H, int W,
-                       float* d_out, void* stream) {
+static int tail_common(PairParams& p, bool xin16, const void* d_x_hi, const void* d_x_lo, const void* d_w,
+                       const float* d_bias, const void* d_xin_hi, const void* d_xin_lo, int skip_ch0, int cout, int n, int H,
+                       int W, float* d_out, void* stream) {
   DSEN2_REQUIRE(d_x_hi && d_x_lo && d_w && d_bias && d_xin_hi && d_xin_lo && d_out, DSEN2_E_BADARG,
                 "dsen2_conv_tail: null pointer");
   DSEN2_REQUIRE(n >= 0 && H > 0 && W > 0 && cout > 0 && cout <= 16 && skip_ch0 >= 0 && skip_ch0 + cout <= 16,
@@ -1035,6 +1051,7 @@ static int tail_common(PairParams& p, const void* d_x_hi, const void* d_x_lo, co
   }
   p.bias = d_bias;
   p.skip_hi = (const __half*)d_xin_hi; p.skip_lo = (const __half*)d_xin_lo; p.skip_ch0 = skip_ch0;
+  p.skip_pitch = xin16 ? 16 : 64; p.skip_off = xin16 ? 0 : 16;
   p.cout_real = cout; p.out_f32 = d_out;
   CUtensorMap a0, a1, w;
   rc = make_maps<CfgTail>(&a0, &a1, &w, d_x_hi, d_x_lo, d_w, n, H, W);
@@ -1042,19 +1059,31 @@ static int tail_common(PairParams& p, const void* d_x_hi, const void* d_x_lo, co
   return launch_pair<CfgTail>(a0, a1, w, p, sms, (cudaStream_t)stream, "conv_pair<tail>");
 }
 
-extern "C" int dsen2_conv_tail(const void* d_x_hi, const void* d_x_lo, const void* d_w, const float* d_bias,
-                               const void* d_xin_hi, const void* d_xin_lo, int skip_ch0, int cout, int n, int H, int W,
-                               float* d_pred_nchw, void* stream) {
+static int tail_nchw(bool xin16, const void* d_x_hi, const void* d_x_lo, const void* d_w, const float* d_bias,
+                     const void* d_xin_hi, const void* d_xin_lo, int skip_ch0, int cout, int n, int H, int W,
+                     float* d_pred_nchw, void* stream) {
   PairParams p{};
   p.tail_mode = 0;
   p.out_mul = 1.0f;
-  return tail_common(p, d_x_hi, d_x_lo, d_w, d_bias, d_xin_hi, d_xin_lo, skip_ch0, cout, n, H, W, d_pred_nchw, stream);
+  return tail_common(p, xin16, d_x_hi, d_x_lo, d_w, d_bias, d_xin_hi, d_xin_lo, skip_ch0, cout, n, H, W, d_pred_nchw,
+                     stream);
 }
 
-extern "C" int dsen2_conv_tail_stitch(const void* d_x_hi, const void* d_x_lo, const void* d_w, const float* d_bias,
-                                      const void* d_xin_hi, const void* d_xin_lo, int skip_ch0, int cout, int n, int P,
-                                      int first_patch, int border, int img_h, int img_w, float mul, float* d_canvas,
-                                      void* stream) {
+extern "C" int dsen2_conv_tail(const void* d_x_hi, const void* d_x_lo, const void* d_w, const float* d_bias,
+                               const void* d_xin_hi, const void* d_xin_lo, int skip_ch0, int cout, int n, int H, int W,
+                               float* d_pred_nchw, void* stream) {
+  return tail_nchw(false, d_x_hi, d_x_lo, d_w, d_bias, d_xin_hi, d_xin_lo, skip_ch0, cout, n, H, W, d_pred_nchw, stream);
+}
+
+extern "C" int dsen2_conv_tail16(const void* d_x_hi, const void* d_x_lo, const void* d_w, const float* d_bias,
+                                 const void* d_xin_hi, const void* d_xin_lo, int skip_ch0, int cout, int n, int H, int W,
+                                 float* d_pred_nchw, void* stream) {
+  return tail_nchw(true, d_x_hi, d_x_lo, d_w, d_bias, d_xin_hi, d_xin_lo, skip_ch0, cout, n, H, W, d_pred_nchw, stream);
+}
+
+static int tail_stitch(bool xin16, const void* d_x_hi, const void* d_x_lo, const void* d_w, const float* d_bias,
+                       const void* d_xin_hi, const void* d_xin_lo, int skip_ch0, int cout, int n, int P, int first_patch,
+                       int border, int img_h, int img_w, float mul, float* d_canvas, void* stream) {
   const int S = P - 2 * border;
   DSEN2_REQUIRE(P > 0 && border >= 0 && S > 0 && img_h >= S && img_w >= S && first_patch >= 0, DSEN2_E_BADARG,
                 "dsen2_conv_tail_stitch: bad stitch geometry (P %d border %d image %dx%d)", P, border, img_h, img_w);
@@ -1066,5 +1095,21 @@ extern "C" int dsen2_conv_tail_stitch(const void* d_x_hi, const void* d_x_lo, co
   DSEN2_REQUIRE(first_patch + n <= p.grid_ny * p.grid_nx, DSEN2_E_BADARG,
                 "dsen2_conv_tail_stitch: patch range [%d,%d) exceeds the %d tiles of the canvas", first_patch,
                 first_patch + n, p.grid_ny * p.grid_nx);
-  return tail_common(p, d_x_hi, d_x_lo, d_w, d_bias, d_xin_hi, d_xin_lo, skip_ch0, cout, n, P, P, d_canvas, stream);
+  return tail_common(p, xin16, d_x_hi, d_x_lo, d_w, d_bias, d_xin_hi, d_xin_lo, skip_ch0, cout, n, P, P, d_canvas, stream);
+}
+
+extern "C" int dsen2_conv_tail_stitch(const void* d_x_hi, const void* d_x_lo, const void* d_w, const float* d_bias,
+                                      const void* d_xin_hi, const void* d_xin_lo, int skip_ch0, int cout, int n, int P,
+                                      int first_patch, int border, int img_h, int img_w, float mul, float* d_canvas,
+                                      void* stream) {
+  return tail_stitch(false, d_x_hi, d_x_lo, d_w, d_bias, d_xin_hi, d_xin_lo, skip_ch0, cout, n, P, first_patch, border,
+                     img_h, img_w, mul, d_canvas, stream);
+}
+
+extern "C" int dsen2_conv_tail16_stitch(const void* d_x_hi, const void* d_x_lo, const void* d_w, const float* d_bias,
+                                        const void* d_xin_hi, const void* d_xin_lo, int skip_ch0, int cout, int n, int P,
+                                        int first_patch, int border, int img_h, int img_w, float mul, float* d_canvas,
+                                        void* stream) {
+  return tail_stitch(true, d_x_hi, d_x_lo, d_w, d_bias, d_xin_hi, d_xin_lo, skip_ch0, cout, n, P, first_patch, border,
+                     img_h, img_w, mul, d_canvas, stream);
 }

@@ -258,6 +258,10 @@ static EncodeTiledFn get_encode() {
 }
 
 int make_tmap_f16(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint32_t* box) {
+  return make_tmap_f16_sw(m, ptr, rank, dims, box, 128);
+}
+
+int make_tmap_f16_sw(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint32_t* box, int swizzle_bytes) {
   EncodeTiledFn enc = get_encode();
   DSEN2_REQUIRE(enc != nullptr, DSEN2_E_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t gdim[5], gstr[4];
@@ -271,7 +275,8 @@ int make_tmap_f16(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dim
     if (i < rank - 1) gstr[i] = stride;
   }
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(ptr), gdim, gstr, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DSEN2_REQUIRE(r == CUDA_SUCCESS, DSEN2_E_DRIVER, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return 0;
@@ -407,7 +412,8 @@ static int head_k_pad(int in_channels) { return (9 * in_channels + 63) / 64 * 64
 extern "C" size_t dsen2_s2model_workspace_bytes(int n, int P, int in_channels, int feature_size) {
   if (n <= 0 || P <= 0 || in_channels <= 0 || feature_size <= 0) return 0;
   const size_t pix = (size_t)n * P * P;
-  if (feature_size == 128)   // x_in hi/lo (64 ch) + trunk hi/lo + resblock intermediate + low bytes of the fp16+8 trunk
+  if (feature_size == 128)   // x_in hi/lo (64 ch; 16 are used when there are resblocks) + trunk hi/lo + resblock
+                             // intermediate + low bytes of the fp16+8 trunk
     return 2 * align_up(pix * 64 * 2, 1024) + 3 * align_up(pix * feature_size * 2, 1024) +
            align_up((size_t)n * P * ((P + 7) / 8 * 8) * feature_size, 1024) + 1024;
   return align_up(pix * head_k_pad(in_channels) * 2, 1024) + 3 * align_up(pix * feature_size * 2, 1024) + 1024;
@@ -450,14 +456,19 @@ extern "C" int dsen2_s2model_forward(const float* const* d_x, const int* channel
     void* t = ws;
     ws += align_up(pix * 128 * 2, 1024);
     void* xq = ws;               // low bytes of the fp16 + 8 bit trunk, tile-row-major (dsen2_conv_resq)
-    rc = dsen2_prep_from_patches(d_x[0], channels[0], d_x[1], channels[1], n_inputs == 3 ? d_x[2] : nullptr,
-                                 n_inputs == 3 ? channels[2] : 0, n, P, xin_hi, xin_lo, stream);
+    // with resblocks: un-gathered 16-channel input, nine-tap first layer (head weights from dsen2_pack_head16_weights);
+    // without: the 64-channel form (dsen2_pack_head_weights)
+    const bool xin16 = num_layers > 0;
+    rc = xin16 ? dsen2_prep16_from_patches(d_x[0], channels[0], d_x[1], channels[1], n_inputs == 3 ? d_x[2] : nullptr,
+                                           n_inputs == 3 ? channels[2] : 0, n, P, xin_hi, xin_lo, stream)
+               : dsen2_prep_from_patches(d_x[0], channels[0], d_x[1], channels[1], n_inputs == 3 ? d_x[2] : nullptr,
+                                         n_inputs == 3 ? channels[2] : 0, n, P, xin_hi, xin_lo, stream);
     if (rc) return rc;
     // the fp16 x_lo is only needed by the tail: the last trunk-producing layer writes it
     if (num_layers == 0)
       rc = dsen2_conv_head(xin_hi, xin_lo, d_weights[0], d_bias[0], n, P, P, 128, x_hi, x_lo, nullptr, stream);
     else
-      rc = dsen2_conv_head_q(xin_hi, xin_lo, d_weights[0], d_bias[0], n, P, P, 128, x_hi, xq, stream);
+      rc = dsen2_conv_head16_q(xin_hi, xin_lo, d_weights[0], d_bias[0], n, P, P, 128, x_hi, xq, stream);
     if (rc) return rc;
     for (int l = 0; l < num_layers; ++l) {
       rc = dsen2_conv3x3(x_hi, d_weights[1 + 2 * l], d_bias[1 + 2 * l], n, P, P, 128, 128, 9, DSEN2_EPI_RELU, nullptr,
@@ -467,8 +478,9 @@ extern "C" int dsen2_s2model_forward(const float* const* d_x, const int* channel
                            l == num_layers - 1 ? x_lo : nullptr, stream);
       if (rc) return rc;
     }
-    return dsen2_conv_tail(x_hi, x_lo, d_weights[2 * num_layers + 1], d_bias[2 * num_layers + 1], xin_hi, xin_lo,
-                           ctot - cout_real, cout_real, n, P, P, d_out_f32, stream);
+    return (xin16 ? dsen2_conv_tail16 : dsen2_conv_tail)(x_hi, x_lo, d_weights[2 * num_layers + 1],
+                                                         d_bias[2 * num_layers + 1], xin_hi, xin_lo, ctot - cout_real,
+                                                         cout_real, n, P, P, d_out_f32, stream);
   }
 
   const int k_pad = head_k_pad(ctot);

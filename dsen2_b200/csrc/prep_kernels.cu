@@ -128,6 +128,77 @@ __device__ __forceinline__ void prep_gather(const PrepSource& src, int si, int s
   }
 }
 
+// ---- un-gathered 16-channel prepared input (inference path) ---------------------------------------------------------
+// x_in16[n][y][x][c] = X[n][c][y][x] (c >= ctot zero), hi and lo tensors: 32 bytes per pixel each instead of 128.
+// The head convolution then runs all nine taps as shifted descriptors into a 32-byte-row halo box (conv_pair.cu,
+// CfgHead16); a thread writes its own pixel only, consecutive threads consecutive 32-byte chunks.
+__global__ void prep16_from_patches_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x1, int c1,
+                                           const float* __restrict__ x2, int c2, int P, long long total,
+                                           __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+  const long long PP = (long long)P * P;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long n = idx / PP;
+    const int rem = (int)(idx - n * PP);
+    float v[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      float t = 0.f;
+      if (c < c0) t = __ldg(x0 + (n * c0 + c) * PP + rem);
+      else if (c < c0 + c1) t = __ldg(x1 + (n * c1 + (c - c0)) * PP + rem);
+      else if (c < c0 + c1 + c2) t = __ldg(x2 + (n * c2 + (c - c0 - c1)) * PP + rem);
+      v[c] = t;
+    }
+    Half16 hi, lo;
+    split16(v, hi, lo);
+    store32(out_hi + idx * 16, hi);
+    store32(out_lo + idx * 16, lo);
+  }
+}
+
+__global__ void prep16_from_images_kernel(PrepSource s0, PrepSource s1, PrepSource s2, int nsrc, int plr, int blr, int P,
+                                          Tiling tl, int first_patch, long long total, float divisor,
+                                          __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+  const int PP = P * P;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int local = (int)(idx / PP);
+    const int rem = (int)(idx - (long long)local * PP);
+    const int y = rem / P, x = rem - y * P;
+    const int patch = first_patch + local;
+    float v[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) v[c] = 0.f;
+    if (patch < tl.n_i * tl.n_j) {               // surplus patches of the allocated stack stay zero (patches.py:32-39)
+      const int ti = patch / tl.n_j, tj = patch - ti * tl.n_j;
+      const int si = ti < tl.k_i ? ti * tl.stride : tl.last_i;
+      const int sj = tj < tl.k_j ? tj * tl.stride : tl.last_j;
+      prep_gather<4, 0>(s0, si, sj, plr, blr, y, x, divisor, v);     // 10 m bands   (DSen2Net.py:24,26 order)
+      prep_gather<6, 4>(s1, si, sj, plr, blr, y, x, divisor, v);     // 20 m bands
+      if (nsrc == 3) prep_gather<2, 10>(s2, si, sj, plr, blr, y, x, divisor, v);   // 60 m bands
+    }
+    Half16 hi, lo;
+    split16(v, hi, lo);
+    store32(out_hi + idx * 16, hi);
+    store32(out_lo + idx * 16, lo);
+  }
+}
+
+// head weights for the 16-channel input: [tap = dy*3+dx][2F rows = W_hi ; W_lo][16: c]
+__global__ void pack_head16_weights_kernel(const float* __restrict__ hwio, int cin, int F, long long total,
+                                           __half* __restrict__ out) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % 16);
+    const int r = (int)((idx / 16) % (2 * F));
+    const int tap = (int)(idx / (16LL * 2 * F));
+    float v = 0.f;
+    if (c < cin) v = hwio[((long long)tap * cin + c) * F + (r % F)];
+    const __half hi = __float2half_rn(v);
+    out[idx] = r < F ? hi : __float2half_rn(v - __half2float(hi));
+  }
+}
+
 // ---- row-block variants (P <= 256): coalesced x_in stores ------------------------------------------------------
 // The thread-per-pixel kernels above write every 128-byte x_in row in six 32-byte pieces from three different threads
 // (24 scattered 16-byte stores per thread: 2.6 TB/s).  Here a block owns R = 256 / P whole patch rows: each thread
@@ -384,4 +455,62 @@ extern "C" int dsen2_pack_tail_weights(const float* d_hwio, int feature_size, in
   pack_tail_weights_kernel<<<grid_for(total, block), block, 0, (cudaStream_t)stream>>>(d_hwio, feature_size, cout, total,
                                                                                        (__half*)d_packed);
   return check_launch("pack_tail_weights");
+}
+
+extern "C" int dsen2_prep16_from_patches(const float* d_x0, int c0, const float* d_x1, int c1, const float* d_x2, int c2,
+                                         int n, int P, void* d_xin_hi, void* d_xin_lo, void* stream) {
+  DSEN2_REQUIRE(d_x0 && d_x1 && d_xin_hi && d_xin_lo && (c2 == 0 || d_x2), DSEN2_E_BADARG,
+                "dsen2_prep16_from_patches: null pointer");
+  DSEN2_REQUIRE(c0 > 0 && c1 > 0 && c2 >= 0 && c0 + c1 + c2 <= 16 && n >= 0 && P > 0, DSEN2_E_BADARG,
+                "dsen2_prep16_from_patches: bad sizes (%d+%d+%d channels, at most 16)", c0, c1, c2);
+  DSEN2_REQUIRE(((uintptr_t)d_xin_hi % 16) == 0 && ((uintptr_t)d_xin_lo % 16) == 0, DSEN2_E_ALIGN,
+                "dsen2_prep16_from_patches: outputs must be 16-byte aligned");
+  if (n == 0) return 0;
+  const long long total = (long long)n * P * P;
+  const int block = 256;
+  prep16_from_patches_kernel<<<grid_for(total, block), block, 0, (cudaStream_t)stream>>>(
+      d_x0, c0, d_x1, c1, d_x2, c2, P, total, (__half*)d_xin_hi, (__half*)d_xin_lo);
+  return check_launch("prep16_from_patches");
+}
+
+extern "C" int dsen2_prep16_from_images(const float* d_img10, const float* d_img20, const float* d_img60, int H, int W,
+                                        int patch, int border, int first_patch, int num_patches, float divisor,
+                                        void* d_xin_hi, void* d_xin_lo, void* stream) {
+  DSEN2_REQUIRE(d_img10 && d_img20 && d_xin_hi && d_xin_lo, DSEN2_E_BADARG, "dsen2_prep16_from_images: null pointer");
+  const int r = d_img60 ? 6 : 2;                 // the tiling grid is the coarsest input (patches.py:45-53,114-122)
+  DSEN2_REQUIRE(H > 0 && W > 0 && H % r == 0 && W % r == 0, DSEN2_E_BADARG,
+                "dsen2_prep16_from_images: 10 m size %dx%d must be a multiple of %d", H, W, r);
+  DSEN2_REQUIRE(patch > 0 && border >= 0 && patch % r == 0 && border % r == 0 && patch > 2 * border, DSEN2_E_BADARG,
+                "dsen2_prep16_from_images: patch %d / border %d must be multiples of %d", patch, border, r);
+  DSEN2_REQUIRE(first_patch >= 0 && num_patches >= 0 && divisor != 0.f, DSEN2_E_BADARG,
+                "dsen2_prep16_from_images: bad patch range / divisor");
+  DSEN2_REQUIRE(((uintptr_t)d_xin_hi % 16) == 0 && ((uintptr_t)d_xin_lo % 16) == 0, DSEN2_E_ALIGN,
+                "dsen2_prep16_from_images: outputs must be 16-byte aligned");
+  const int plr = patch / r, blr = border / r, gh = H / r, gw = W / r;
+  DSEN2_REQUIRE(gh + 2 * blr >= plr && gw + 2 * blr >= plr, DSEN2_E_BADARG,
+                "dsen2_prep16_from_images: image %dx%d smaller than one patch (%d)", H, W, patch);
+  if (num_patches == 0) return 0;
+  const Tiling tl = make_tiling(gh, gw, plr, blr);
+  DSEN2_REQUIRE(first_patch + num_patches <= (tl.k_i + 1) * (tl.k_j + 1), DSEN2_E_BADARG,
+                "dsen2_prep16_from_images: patch range [%d,%d) exceeds the %d allocated patches", first_patch,
+                first_patch + num_patches, (tl.k_i + 1) * (tl.k_j + 1));
+  PrepSource s0{d_img10, H, W, r, 1};
+  PrepSource s1{d_img20, H / 2, W / 2, r / 2, 2};
+  PrepSource s2{d_img60, H / 6, W / 6, 1, 6};
+  const long long total = (long long)num_patches * patch * patch;
+  const int block = 256;
+  prep16_from_images_kernel<<<grid_for(total, block), block, 0, (cudaStream_t)stream>>>(
+      s0, s1, s2, d_img60 ? 3 : 2, plr, blr, patch, tl, first_patch, total, divisor, (__half*)d_xin_hi, (__half*)d_xin_lo);
+  return check_launch("prep16_from_images");
+}
+
+extern "C" int dsen2_pack_head16_weights(const float* d_hwio, int cin, int feature_size, void* d_packed, void* stream) {
+  DSEN2_REQUIRE(d_hwio && d_packed, DSEN2_E_BADARG, "dsen2_pack_head16_weights: null pointer");
+  DSEN2_REQUIRE(cin > 0 && cin <= 16 && feature_size > 0, DSEN2_E_BADARG,
+                "dsen2_pack_head16_weights: at most 16 input channels (got %d)", cin);
+  const long long total = 9LL * 2 * feature_size * 16;
+  const int block = 256;
+  pack_head16_weights_kernel<<<grid_for(total, block), block, 0, (cudaStream_t)stream>>>(d_hwio, cin, feature_size, total,
+                                                                                         (__half*)d_packed);
+  return check_launch("pack_head16_weights");
 }

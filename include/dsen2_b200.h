@@ -152,6 +152,18 @@ int dsen2_prep_from_images(const float* d_img10, const float* d_img20, const flo
                            int patch, int border, int first_patch, int num_patches, float divisor,
                            void* d_xin_hi, void* d_xin_lo, void* stream);
 
+/* The same preparation without the tap gather (what the inference path uses): x_in16 hi / lo, NHWC fp16
+ * (n, P, P, 16), channel c = band c of the concatenated inputs (DSen2Net.py:24,26), c >= sum(c_i) zero: 32 bytes per
+ * pixel and tensor instead of 128.  dsen2_conv_head16_q reads it with all nine taps; dsen2_conv_tail16[_stitch]
+ * take the global skip from it.  Arguments as dsen2_prep_from_patches / dsen2_prep_from_images.               */
+int dsen2_prep16_from_patches(const float* d_x0, int c0, const float* d_x1, int c1, const float* d_x2, int c2,
+                              int n, int P, void* d_xin_hi, void* d_xin_lo, void* stream);
+int dsen2_prep16_from_images(const float* d_img10, const float* d_img20, const float* d_img60, int H, int W,
+                             int patch, int border, int first_patch, int num_patches, float divisor,
+                             void* d_xin_hi, void* d_xin_lo, void* stream);
+/* First layer kernel (3,3,cin,F) fp32 HWIO -> [9 taps][2F rows = W_hi ; W_lo][16] fp16 (for dsen2_conv_head16_q). */
+int dsen2_pack_head16_weights(const float* d_hwio, int cin, int feature_size, void* d_packed, void* stream);
+
 /* First layer kernel (3,3,cin,F) fp32 HWIO -> [3 vertical taps][2F rows = W_hi ; W_lo][64] fp16. */
 int dsen2_pack_head_weights(const float* d_hwio, int cin, int feature_size, void* d_packed, void* stream);
 /* Last layer kernel (3,3,F,cout) fp32 HWIO -> [9 taps][32 rows = W_hi(16) ; W_lo(16)][F] fp16.    */
@@ -192,6 +204,10 @@ int dsen2_conv_head_q(const void* d_xin_hi, const void* d_xin_lo, const void* d_
                       int n, int H, int W, int feature_size, void* d_x_hi, void* d_trunk_lo8, void* stream);
 int dsen2_conv_resq(const void* d_in, const void* d_w, const float* d_bias, int n, int H, int W,
                     float res_scale, void* d_x_hi, void* d_trunk_lo8, void* d_out_lo, void* stream);
+/* dsen2_conv_head_q on the 16-channel prepared input (dsen2_prep16_*, weights from dsen2_pack_head16_weights): nine
+ * taps as shifted descriptors into a 32-byte-row (SWIZZLE_32B) halo box.                                       */
+int dsen2_conv_head16_q(const void* d_xin_hi, const void* d_xin_lo, const void* d_w, const float* d_bias,
+                        int n, int H, int W, int feature_size, void* d_x_hi, void* d_trunk_lo8, void* stream);
 
 /* Conv2D(cout, 3x3) + Add(last input) (DSen2Net.py:35,38,41) on the trunk (hi, lo).  The global skip is
  * read from x_in (centre tap, bands skip_ch0 .. skip_ch0+cout).  Output: NCHW fp32 predictions
@@ -208,11 +224,21 @@ int dsen2_conv_tail_stitch(const void* d_x_hi, const void* d_x_lo, const void* d
                            int n, int P, int first_patch, int border, int img_h, int img_w, float mul,
                            float* d_canvas, void* stream);
 
+/* dsen2_conv_tail / dsen2_conv_tail_stitch with the global skip read from the 16-channel prepared input. */
+int dsen2_conv_tail16(const void* d_x_hi, const void* d_x_lo, const void* d_w, const float* d_bias,
+                      const void* d_xin_hi, const void* d_xin_lo, int skip_ch0, int cout,
+                      int n, int H, int W, float* d_pred_nchw, void* stream);
+int dsen2_conv_tail16_stitch(const void* d_x_hi, const void* d_x_lo, const void* d_w, const float* d_bias,
+                             const void* d_xin_hi, const void* d_xin_lo, int skip_ch0, int cout,
+                             int n, int P, int first_patch, int border, int img_h, int img_w, float mul,
+                             float* d_canvas, void* stream);
+
 /* Whole s2model forward (model.predict on one batch, supres.py:65) for n patches of (P, P).
  * d_weights[i] / d_bias[i] are the packed layers in Keras topological order (2*num_layers+2 entries):
- *   feature_size 128: [0] dsen2_pack_head_weights, [1..2L] dsen2_pack_conv_weights(cin_pad=cout_pad=128),
- *                     [2L+1] dsen2_pack_tail_weights; biases fp32 of length 128 / 128 / 16;
- *                     pipeline: prep_from_patches -> conv_head -> L x (conv3x3 RELU, conv_res32) -> conv_tail
+ *   feature_size 128: [0] dsen2_pack_head16_weights (dsen2_pack_head_weights when num_layers == 0),
+ *                     [1..2L] dsen2_pack_conv_weights(cin_pad=cout_pad=128), [2L+1] dsen2_pack_tail_weights;
+ *                     biases fp32 of length 128 / 128 / 16;
+ *                     pipeline: prep16_from_patches -> conv_head16_q -> L x (conv3x3 RELU, conv_resq) -> conv_tail16
  *   feature_size 256: [0] dsen2_pack_conv_weights(im2col=1), [1..2L] (256,256), [2L+1] cout_pad 16;
  *                     pipeline: pack_head_input -> conv3x3 (1x1) -> ... -> conv3x3 TAIL_NCHW.
  * Workspace: see dsen2_s2model_workspace_bytes.  d_x[0..n_inputs) NCHW fp32 inputs; the last one is

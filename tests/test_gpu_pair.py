@@ -373,3 +373,86 @@ def test_conv_resq_trunk_update(env, shape, last):
         assert not got[0, 0, :, :4].any() or np.abs(ref[0, 0, :, :4]).min() > 0        # no spurious zeros
     assert lib.dsen2_conv_resq(_capi.ptr(thi), _capi.ptr(tw), _capi.ptr(tb), n, H, W, 0.1, _capi.ptr(thi),
                                _capi.ptr(tq), None, _capi.stream_ptr()) == -1           # aliasing is refused
+
+
+# ---- un-gathered 16-channel prepared input + nine-tap first layer (dsen2_prep16_* / dsen2_conv_head16_q) ------------
+def _xin16_expected(xcat):
+    """xcat (n, C, P, P) float32 -> (hi, lo) (n, P, P, 16) float16: channel c = band c, zero above C."""
+    n, C, P, _ = xcat.shape
+    full = np.zeros((n, P, P, 16), np.float32)
+    full[..., :C] = xcat.transpose(0, 2, 3, 1)
+    return _split(full)
+
+
+@pytest.mark.parametrize('chan', [(4, 6), (4, 6, 2)])
+def test_prep16_from_patches_layout_bit_exact(env, chan):
+    torch, _capi, lib = env
+    rng = np.random.RandomState(sum(chan))
+    n, P = 2, 40
+    xs = [rng.uniform(0, 5, size=(n, c, P, P)).astype(np.float32) for c in chan]
+    dx = [torch.from_numpy(a).cuda() for a in xs]
+    hi = torch.full((n, P, P, 16), 7.0, dtype=torch.float16, device='cuda')
+    lo = torch.full_like(hi, 7.0)
+    x2, c2 = (dx[2], chan[2]) if len(chan) == 3 else (None, 0)
+    _capi.check(lib.dsen2_prep16_from_patches(_capi.ptr(dx[0]), chan[0], _capi.ptr(dx[1]), chan[1], _capi.ptr(x2), c2, n, P,
+                                              _capi.ptr(hi), _capi.ptr(lo), _capi.stream_ptr()), 'prep16_from_patches')
+    torch.cuda.synchronize()
+    ehi, elo = _xin16_expected(np.concatenate(xs, axis=1))
+    assert np.array_equal(hi.cpu().numpy().view(np.uint16), ehi.view(np.uint16))
+    assert np.array_equal(lo.cpu().numpy().view(np.uint16), elo.view(np.uint16))
+
+
+@pytest.mark.parametrize('tag', sorted(CASES20)[:2] + sorted(CASES60)[:1])
+def test_prep16_from_images_equals_centre_tap_of_the_gathered_form(env, tag):
+    """Same arithmetic as dsen2_prep_from_images (checked against the patch oracle above): x_in16 must be bit-identical to
+    the centre-tap channels 16..31 of the 64-channel form, surplus patches zero."""
+    torch, _capi, lib = env
+    d10, d20, d60 = synth(tag)
+    run60 = tag in CASES60
+    P, B, r = (192, 12, 6) if run60 else (128, 8, 2)
+    H, W = d10.shape[:2]
+    n = (H // r // (P // r - 2 * (B // r)) + 1) * (W // r // (P // r - 2 * (B // r)) + 1)      # allocated (patches.py:32-39)
+    t10, t20 = torch.from_numpy(d10).cuda(), torch.from_numpy(d20).cuda()
+    t60 = torch.from_numpy(d60).cuda() if run60 else None
+    hi64 = torch.empty((n, P, P, 64), dtype=torch.float16, device='cuda')
+    lo64 = torch.empty_like(hi64)
+    hi16 = torch.full((n, P, P, 16), 7.0, dtype=torch.float16, device='cuda')
+    lo16 = torch.full_like(hi16, 7.0)
+    _capi.check(lib.dsen2_prep_from_images(_capi.ptr(t10), _capi.ptr(t20), _capi.ptr(t60), H, W, P, B, 0, n, 2000.0,
+                                           _capi.ptr(hi64), _capi.ptr(lo64), _capi.stream_ptr()), 'prep_from_images')
+    _capi.check(lib.dsen2_prep16_from_images(_capi.ptr(t10), _capi.ptr(t20), _capi.ptr(t60), H, W, P, B, 0, n, 2000.0,
+                                             _capi.ptr(hi16), _capi.ptr(lo16), _capi.stream_ptr()), 'prep16_from_images')
+    torch.cuda.synchronize()
+    assert torch.equal(hi16.view(torch.int16), hi64[..., 16:32].contiguous().view(torch.int16))
+    assert torch.equal(lo16.view(torch.int16), lo64[..., 16:32].contiguous().view(torch.int16))
+
+
+@pytest.mark.parametrize('shape', [(2, 32, 32), (1, 128, 128), (3, 40, 24), (1, 8, 200), (5, 16, 8), (1, 192, 192)])
+def test_conv_head16_q_nine_taps(env, shape):
+    """First layer on the 16-channel input: nine shifted 32-byte-row descriptors; fp32-equivalent (hi + lo operands)."""
+    torch, _capi, lib = env
+    n, H, W = shape
+    F, C = 128, 12
+    rng = np.random.RandomState(H + 3 * W)
+    xcat = rng.uniform(0, 5, size=(n, C, H, W)).astype(np.float32)
+    hi, lo = _xin16_expected(xcat) if H == W else _split(np.concatenate(
+        [xcat.transpose(0, 2, 3, 1), np.zeros((n, H, W, 16 - C), np.float32)], axis=-1))
+    lim = np.sqrt(6.0 / (9 * C))
+    w = rng.uniform(-lim, lim, size=(3, 3, C, F)).astype(np.float32)
+    bias = (rng.randn(F) * 0.1).astype(np.float32)
+    tw = torch.empty((9, 2 * F, 16), dtype=torch.float16, device='cuda')
+    _capi.check(lib.dsen2_pack_head16_weights(_capi.ptr(torch.from_numpy(w).cuda()), C, F, _capi.ptr(tw),
+                                              _capi.stream_ptr()), 'pack head16')
+    thi, tlo, tb = torch.from_numpy(hi).cuda(), torch.from_numpy(lo).cuda(), torch.from_numpy(bias).cuda()
+    ohi = torch.zeros((n, H, W, F), dtype=torch.float16, device='cuda')
+    oq = torch.full((n, H, W // 8, F // 16, 8, 16), 77, dtype=torch.int8, device='cuda')
+    _capi.check(lib.dsen2_conv_head16_q(_capi.ptr(thi), _capi.ptr(tlo), _capi.ptr(tw), _capi.ptr(tb), n, H, W, F,
+                                        _capi.ptr(ohi), _capi.ptr(oq), _capi.stream_ptr()), 'conv head16 q')
+    torch.cuda.synchronize()
+    xin = (hi.astype(np.float64) + lo.astype(np.float64))[..., :C]
+    w_hi = w.astype(np.float16)
+    w_eff = w_hi.astype(np.float64) + (w - w_hi.astype(np.float32)).astype(np.float16).astype(np.float64)
+    ref = np.maximum(_conv64(xin, w_eff, bias), 0)
+    got = _q_decode(ohi.cpu().numpy(), _q_from_tiles(oq.cpu().numpy()))
+    np.testing.assert_allclose(got, ref, rtol=2e-5, atol=2e-5)
+    assert np.abs(got - np.maximum(_conv64(xcat.transpose(0, 2, 3, 1), w, bias), 0)).max() < 5e-5   # vs the true fp32 layer

@@ -44,10 +44,11 @@ def _load_model(input_shape, deep, run_60):
 
 def default_device_batch(W, P, B):
     """Patches per launch: whole patch rows of the tile when a row is a reasonable batch (a full Sentinel-2 tile has 99
-    patches of 128 per row), so that the chunks of ``HostPipeline`` (whole rows) split into equal batches; about 1.5 M
-    patch pixels otherwise.  Larger batches only amortise launch overhead (~1 % between 64 and 128 patches)."""
+    patches of 128 per row), so that the chunks of ``HostPipeline`` (whole rows) split into equal batches; about 4.9 M
+    patch pixels otherwise.  Larger batches only amortise launch overhead and the last wave of each launch: measured on
+    one box 559-561 ms per tile with 99 patches per launch, 553-555 ms with 198 or 297."""
     nx = -(-W // (P - 2 * B))
-    target = max(1, (96 * 128 * 128) // (P * P))
+    target = max(1, (300 * 128 * 128) // (P * P))
     if nx > 2 * target:
         return target
     return nx * max(1, target // nx)

@@ -193,6 +193,8 @@ class S2Model:
             else:
                 k_pad = (9 * sum(self.in_channels) + 63) // 64 * 64
                 buf = dict(a0=mk(k_pad), x_hi=mk(F), x_lo=mk(F), t=mk(F), k_pad=k_pad)
+                if F == 256 and self.trunk_format != 'fp32':
+                    buf['xq'] = torch.empty((n, P, (P + 7) // 8, F // 16, 8, 16), dtype=torch.uint8, device=dev)
             self._workspace[key] = buf
         return buf
 
@@ -243,6 +245,19 @@ class S2Model:
         self._timed(timers, 'conv_head', n, lambda: _capi.check(lib.dsen2_conv3x3(
             ptr(buf['a0']), ptr(wts[0]), ptr(biases[0]), n, P, P, buf['k_pad'], F, 1, _capi.EPI_RELU, None, None,
             0.0, ptr(x_hi), ptr(x_lo), None, None, 0, st), "dsen2_conv3x3(head)"))
+        if 'xq' in buf and L > 0:
+            # VDSen2 on the fp16 + 8 bit trunk: the single-CTA first layer wrote hi + lo, re-code once, then as DSen2
+            xq = buf['xq']
+            self._timed(timers, 'conv_head', n, lambda: _capi.check(lib.dsen2_trunk_hilo_to_q(
+                ptr(x_hi), ptr(x_lo), ptr(xq), n, P, P, F, st), "dsen2_trunk_hilo_to_q"))
+            for l in range(L):
+                self._timed(timers, 'conv_res1', n, lambda: _capi.check(lib.dsen2_conv3x3(
+                    ptr(x_hi), ptr(wts[1 + 2 * l]), ptr(biases[1 + 2 * l]), n, P, P, F, F, 9, _capi.EPI_RELU, None,
+                    None, 0.0, ptr(t), None, None, None, 0, st), "dsen2_conv3x3(res conv1)"))
+                self._timed(timers, 'conv_res2', n, lambda: _capi.check(lib.dsen2_conv_resq256(
+                    ptr(t), ptr(wts[2 + 2 * l]), ptr(biases[2 + 2 * l]), n, P, P, 0.1, ptr(x_hi), ptr(xq), None, st),
+                    "dsen2_conv_resq256"))
+            return
         for l in range(L):
             self._timed(timers, 'conv_res1', n, lambda: _capi.check(lib.dsen2_conv3x3(
                 ptr(x_hi), ptr(wts[1 + 2 * l]), ptr(biases[1 + 2 * l]), n, P, P, F, F, 9, _capi.EPI_RELU, None,
@@ -349,7 +364,8 @@ class S2Model:
         return canvas
 
     def launches_per_forward(self):
-        return 2 * self.num_layers + 3          # input preparation + head + 2 per resblock + tail
+        recode = int(not self.fast_path and self.feature_size == 256 and self.trunk_format != 'fp32' and self.num_layers > 0)
+        return 2 * self.num_layers + 3 + recode    # input preparation + head (+ trunk re-coding) + 2 per resblock + tail
 
     def predict(self, x, batch_size=32, verbose=0, device_batch=None):
         """``model.predict([x10, x20(, x60)])`` -> (N, Cout, P, P) float32 numpy (supres.py:65).

@@ -23,6 +23,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "tiling.cuh"
 
 namespace dsen2 {
 
@@ -678,10 +679,15 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
         continue;
       } else if constexpr (Cfg::EPI == kEpiResidualQ || Cfg::EPI == kEpiResidualQLast) {
         // ------------------------------------------------------------------ resblock output, fp16 + 8 bit trunk
+        // a thread owns CH / 2 channels of its pixel: one pass of 64 (128 features) or two (256)
         constexpr int CPT = Cfg::CH / 2;
-        q_epilogue_pass<Cfg, CPT>(p, tc, tn, p.pf_x > 0 && pt + p.pf_x * npairs < pair_tiles, wq, half * CPT, lane, row, valid,
-                                  smem_u32(s_stg) + (uint32_t)(warp * (CPT * 16)), taddr, s_bias_addr, &tmem_full[acc], acc_phase,
-                                  &tmem_empty[acc]);
+        const bool pf = p.pf_x > 0 && pt + p.pf_x * npairs < pair_tiles;
+#pragma unroll 1
+        for (int sc = 0; sc < CPT / 64; ++sc)
+          q_epilogue_pass<Cfg, 64>(p, tc, tn, pf, wq, half * CPT + sc * 64, lane, row, valid,
+                                   smem_u32(s_stg) + (uint32_t)(warp * 1024), taddr, s_bias_addr,
+                                   sc == 0 ? &tmem_full[acc] : nullptr, acc_phase,
+                                   sc == CPT / 64 - 1 ? &tmem_empty[acc] : nullptr);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         continue;
       } else {
@@ -828,6 +834,8 @@ using CfgResidualQLast = PairCfg<128, false, 1, 2, 9, 4, 3, kEpiResidualQLast>;
 // VDSen2 trunk (256 -> 256): 1.18 MB of weights per layer cannot be resident -- ring of 8 streamed [tap][k-block] slabs
 using CfgRelu256 = PairCfg<256, false, 1, 4, 9, 4, 3, kEpiRelu, 8>;
 using CfgResidual256 = PairCfg<256, false, 1, 4, 9, 4, 3, kEpiResidual, 8>;
+using CfgResidualQ256 = PairCfg<256, false, 1, 4, 9, 4, 3, kEpiResidualQ, 8>;
+using CfgResidualQLast256 = PairCfg<256, false, 1, 4, 9, 4, 3, kEpiResidualQLast, 8>;
 using CfgHead = PairCfg<256, true, 2, 1, 3, 3, 6, kEpiRelu>;
 // first layer on the un-gathered 16-channel input: nine taps through shifted descriptors into a 32-byte-row halo box
 using CfgHead16 = PairCfg<256, true, 2, 1, 9, 1, 6, kEpiRelu, 0, 32>;
@@ -1003,8 +1011,8 @@ extern "C" int dsen2_conv_head16_q(const void* d_xin_hi, const void* d_xin_lo, c
                                 nullptr, nullptr, d_trunk_lo8, stream);
 }
 
-extern "C" int dsen2_conv_resq(const void* d_in, const void* d_w, const float* d_bias, int n, int H, int W,
-                               float res_scale, void* d_x_hi, void* d_trunk_lo8, void* d_out_lo, void* stream) {
+static int resq_common(int features, const void* d_in, const void* d_w, const float* d_bias, int n, int H, int W,
+                       float res_scale, void* d_x_hi, void* d_trunk_lo8, void* d_out_lo, void* stream) {
   DSEN2_REQUIRE(d_in && d_w && d_bias && d_x_hi && d_trunk_lo8, DSEN2_E_BADARG, "dsen2_conv_resq: null pointer");
   DSEN2_REQUIRE(n >= 0 && H > 0 && W > 0, DSEN2_E_BADARG, "dsen2_conv_resq: bad shape");
   DSEN2_REQUIRE(d_in != d_x_hi, DSEN2_E_BADARG, "dsen2_conv_resq: the convolution input must not alias x_hi (updated in place)");
@@ -1022,10 +1030,75 @@ extern "C" int dsen2_conv_resq(const void* d_in, const void* d_w, const float* d
   p.xq = (uint8_t*)d_trunk_lo8;
   p.out_hi = (__half*)d_x_hi; p.out_lo = (__half*)d_out_lo;
   CUtensorMap a0, a1, w;
+  if (features == 256) {
+    rc = make_maps<CfgResidualQ256>(&a0, &a1, &w, d_in, nullptr, d_w, n, H, W);
+    if (rc) return rc;
+    if (d_out_lo)
+      return launch_pair<CfgResidualQLast256>(a0, a1, w, p, sms, (cudaStream_t)stream, "conv_pair<residualq,last,256>");
+    return launch_pair<CfgResidualQ256>(a0, a1, w, p, sms, (cudaStream_t)stream, "conv_pair<residualq,256>");
+  }
   rc = make_maps<CfgResidualQ>(&a0, &a1, &w, d_in, nullptr, d_w, n, H, W);
   if (rc) return rc;
   if (d_out_lo) return launch_pair<CfgResidualQLast>(a0, a1, w, p, sms, (cudaStream_t)stream, "conv_pair<residualq,last>");
   return launch_pair<CfgResidualQ>(a0, a1, w, p, sms, (cudaStream_t)stream, "conv_pair<residualq>");
+}
+
+extern "C" int dsen2_conv_resq(const void* d_in, const void* d_w, const float* d_bias, int n, int H, int W,
+                               float res_scale, void* d_x_hi, void* d_trunk_lo8, void* d_out_lo, void* stream) {
+  return resq_common(128, d_in, d_w, d_bias, n, H, W, res_scale, d_x_hi, d_trunk_lo8, d_out_lo, stream);
+}
+
+extern "C" int dsen2_conv_resq256(const void* d_in, const void* d_w, const float* d_bias, int n, int H, int W,
+                                  float res_scale, void* d_x_hi, void* d_trunk_lo8, void* d_out_lo, void* stream) {
+  return resq_common(256, d_in, d_w, d_bias, n, H, W, res_scale, d_x_hi, d_trunk_lo8, d_out_lo, stream);
+}
+
+// ---- (x_hi, x_lo) NHWC fp16 pair -> fp16 + 8 bit trunk code (VDSen2: the single-CTA first layer writes hi + lo) ----
+__global__ void hilo_to_q_kernel(__half* __restrict__ x_hi, const __half* __restrict__ x_lo, uint8_t* __restrict__ xq, int H,
+                                 int W, int C, long long total) {
+  const int c16 = C / 16, tiles_x = (W + 7) / 8;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int chunk = (int)(idx % c16);
+    const long long pix = idx / c16;                      // (n * H + y) * W + x
+    const int x = (int)(pix % W);
+    const long long row = pix / W;                        // n * H + y
+    const uint4* ph = reinterpret_cast<const uint4*>(x_hi + pix * C + chunk * 16);
+    const uint4* pl = reinterpret_cast<const uint4*>(x_lo + pix * C + chunk * 16);
+    uint4 h[2] = {ph[0], ph[1]};
+    const uint4 l[2] = {pl[0], pl[1]};
+    uint4 q;
+    uint32_t* hw = reinterpret_cast<uint32_t*>(h);
+    const uint32_t* lw = reinterpret_cast<const uint32_t*>(l);
+    uint32_t* qw = reinterpret_cast<uint32_t*>(&q);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {                         // four channels per step
+      const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&hw[2 * j]));
+      const float2 a1 = __half22float2(*reinterpret_cast<const __half2*>(&hw[2 * j + 1]));
+      const float2 b0 = __half22float2(*reinterpret_cast<const __half2*>(&lw[2 * j]));
+      const float2 b1 = __half22float2(*reinterpret_cast<const __half2*>(&lw[2 * j + 1]));
+      q_encode4(a0.x + b0.x, a0.y + b0.y, a1.x + b1.x, a1.y + b1.y, hw[2 * j], hw[2 * j + 1], qw[j]);
+    }
+    uint4* oh = reinterpret_cast<uint4*>(x_hi + pix * C + chunk * 16);
+    oh[0] = h[0];
+    oh[1] = h[1];
+    *reinterpret_cast<uint4*>(xq + (((row * tiles_x + x / 8) * c16 + chunk) * 8 + (x & 7)) * 16) = q;
+  }
+}
+
+extern "C" int dsen2_trunk_hilo_to_q(void* d_x_hi, const void* d_x_lo, void* d_trunk_lo8, int n, int H, int W, int C,
+                                     void* stream) {
+  DSEN2_REQUIRE(d_x_hi && d_x_lo && d_trunk_lo8, DSEN2_E_BADARG, "dsen2_trunk_hilo_to_q: null pointer");
+  DSEN2_REQUIRE(n >= 0 && H > 0 && W > 0 && C > 0 && C % 16 == 0, DSEN2_E_BADARG,
+                "dsen2_trunk_hilo_to_q: channels must be a multiple of 16 (got %d)", C);
+  DSEN2_REQUIRE(((uintptr_t)d_x_hi % 16) == 0 && ((uintptr_t)d_x_lo % 16) == 0 && ((uintptr_t)d_trunk_lo8 % 16) == 0,
+                DSEN2_E_ALIGN, "dsen2_trunk_hilo_to_q: pointers must be 16-byte aligned");
+  if (n == 0) return 0;
+  const long long total = (long long)n * H * W * (C / 16);
+  const int block = 256;
+  hilo_to_q_kernel<<<grid_for(total, block), block, 0, (cudaStream_t)stream>>>((__half*)d_x_hi, (const __half*)d_x_lo,
+                                                                               (uint8_t*)d_trunk_lo8, H, W, C, total);
+  return check_launch("trunk_hilo_to_q");
 }
 
 static int tail_common(PairParams& p, bool xin16, const void* d_x_hi, const void* d_x_lo, const void* d_w,

@@ -416,7 +416,9 @@ extern "C" size_t dsen2_s2model_workspace_bytes(int n, int P, int in_channels, i
                              // intermediate + low bytes of the fp16+8 trunk
     return 2 * align_up(pix * 64 * 2, 1024) + 3 * align_up(pix * feature_size * 2, 1024) +
            align_up((size_t)n * P * ((P + 7) / 8 * 8) * feature_size, 1024) + 1024;
-  return align_up(pix * head_k_pad(in_channels) * 2, 1024) + 3 * align_up(pix * feature_size * 2, 1024) + 1024;
+  // im2col'd input + trunk hi/lo + resblock intermediate + low bytes of the fp16+8 trunk
+  return align_up(pix * head_k_pad(in_channels) * 2, 1024) + 3 * align_up(pix * feature_size * 2, 1024) +
+         align_up((size_t)n * P * ((P + 7) / 8 * 8) * feature_size, 1024) + 1024;
 }
 
 extern "C" int dsen2_s2model_forward(const float* const* d_x, const int* channels, int n_inputs, int n, int P,
@@ -491,6 +493,8 @@ extern "C" int dsen2_s2model_forward(const float* const* d_x, const int* channel
   void* x_lo = ws;
   ws += align_up(pix * feature_size * 2, 1024);
   void* t = ws;
+  ws += align_up(pix * feature_size * 2, 1024);
+  void* xq = ws;               // low bytes of the fp16 + 8 bit trunk (dsen2_conv_resq256)
 
   rc = dsen2_pack_head_input(d_x[0], channels[0], d_x[1], channels[1], n_inputs == 3 ? d_x[2] : nullptr,
                              n_inputs == 3 ? channels[2] : 0, n, P, k_pad, a0, nullptr, stream);
@@ -498,12 +502,15 @@ extern "C" int dsen2_s2model_forward(const float* const* d_x, const int* channel
   rc = dsen2_conv3x3(a0, d_weights[0], d_bias[0], n, P, P, k_pad, feature_size, 1, DSEN2_EPI_RELU, nullptr, nullptr,
                      0.f, x_hi, x_lo, nullptr, nullptr, 0, stream);
   if (rc) return rc;
+  if (num_layers > 0) {        // the single-CTA first layer writes hi + lo: re-code as x_hi + one byte per element
+    rc = dsen2_trunk_hilo_to_q(x_hi, x_lo, xq, n, P, P, feature_size, stream);
+    if (rc) return rc;
+  }
   for (int l = 0; l < num_layers; ++l) {
     rc = dsen2_conv3x3(x_hi, d_weights[1 + 2 * l], d_bias[1 + 2 * l], n, P, P, feature_size, feature_size, 9,
                        DSEN2_EPI_RELU, nullptr, nullptr, 0.f, t, nullptr, nullptr, nullptr, 0, stream);
     if (rc) return rc;
-    rc = dsen2_conv3x3(t, d_weights[2 + 2 * l], d_bias[2 + 2 * l], n, P, P, feature_size, feature_size, 9,
-                       DSEN2_EPI_RESIDUAL, x_hi, x_lo, 0.1f, x_hi, x_lo, nullptr, nullptr, 0, stream);
+    rc = dsen2_conv_resq256(t, d_weights[2 + 2 * l], d_bias[2 + 2 * l], n, P, P, 0.1f, x_hi, xq, nullptr, stream);
     if (rc) return rc;
   }
   return dsen2_conv3x3(x_hi, d_weights[2 * num_layers + 1], d_bias[2 * num_layers + 1], n, P, P, feature_size, 16, 9,

@@ -204,6 +204,12 @@ int dsen2_conv_head_q(const void* d_xin_hi, const void* d_xin_lo, const void* d_
                       int n, int H, int W, int feature_size, void* d_x_hi, void* d_trunk_lo8, void* stream);
 int dsen2_conv_resq(const void* d_in, const void* d_w, const float* d_bias, int n, int H, int W,
                     float res_scale, void* d_x_hi, void* d_trunk_lo8, void* d_out_lo, void* stream);
+/* The same resblock update for feature_size 256 (VDSen2; d_w from dsen2_pack_conv_weights(cin_pad = cout_pad = 256)),
+ * and the re-coding of an NHWC fp16 (hi, lo) pair as x_hi + bytes: x = hi + lo -> d_x_hi (in place), d_trunk_lo8.
+ * VDSen2's first layer (dsen2_conv3x3 on the im2col'd input) writes hi + lo.  C % 16 == 0.                     */
+int dsen2_conv_resq256(const void* d_in, const void* d_w, const float* d_bias, int n, int H, int W,
+                       float res_scale, void* d_x_hi, void* d_trunk_lo8, void* d_out_lo, void* stream);
+int dsen2_trunk_hilo_to_q(void* d_x_hi, const void* d_x_lo, void* d_trunk_lo8, int n, int H, int W, int C, void* stream);
 /* dsen2_conv_head_q on the 16-channel prepared input (dsen2_prep16_*, weights from dsen2_pack_head16_weights): nine
  * taps as shifted descriptors into a 32-byte-row (SWIZZLE_32B) halo box.                                       */
 int dsen2_conv_head16_q(const void* d_xin_hi, const void* d_xin_lo, const void* d_w, const float* d_bias,
@@ -240,7 +246,8 @@ int dsen2_conv_tail16_stitch(const void* d_x_hi, const void* d_x_lo, const void*
  *                     biases fp32 of length 128 / 128 / 16;
  *                     pipeline: prep16_from_patches -> conv_head16_q -> L x (conv3x3 RELU, conv_resq) -> conv_tail16
  *   feature_size 256: [0] dsen2_pack_conv_weights(im2col=1), [1..2L] (256,256), [2L+1] cout_pad 16;
- *                     pipeline: pack_head_input -> conv3x3 (1x1) -> ... -> conv3x3 TAIL_NCHW.
+ *                     pipeline: pack_head_input -> conv3x3 (1x1) -> trunk_hilo_to_q -> L x (conv3x3 RELU, conv_resq256)
+ *                     -> conv3x3 TAIL_NCHW.
  * Workspace: see dsen2_s2model_workspace_bytes.  d_x[0..n_inputs) NCHW fp32 inputs; the last one is
  * the global skip. */
 size_t dsen2_s2model_workspace_bytes(int n, int P, int in_channels, int feature_size);

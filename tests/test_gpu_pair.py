@@ -456,3 +456,52 @@ def test_conv_head16_q_nine_taps(env, shape):
     got = _q_decode(ohi.cpu().numpy(), _q_from_tiles(oq.cpu().numpy()))
     np.testing.assert_allclose(got, ref, rtol=2e-5, atol=2e-5)
     assert np.abs(got - np.maximum(_conv64(xcat.transpose(0, 2, 3, 1), w, bias), 0)).max() < 5e-5   # vs the true fp32 layer
+
+
+def test_trunk_hilo_to_q_recoding(env):
+    """(hi, lo) fp16 pair -> x_hi + one byte per element: the numpy code of x = hi + lo, bit for bit."""
+    torch, _capi, lib = env
+    rng = np.random.RandomState(11)
+    n, H, W, C = 2, 24, 40, 256
+    x = (rng.randn(n, H, W, C) * np.exp(rng.uniform(-6, 3, size=(n, H, W, C)))).astype(np.float32)
+    x[0, 0, :3] = 0
+    hi, lo = _split(x)
+    thi, tlo = torch.from_numpy(hi).cuda(), torch.from_numpy(lo).cuda()
+    tq = torch.full((n, H, W // 8, C // 16, 8, 16), 77, dtype=torch.int8, device='cuda')
+    _capi.check(lib.dsen2_trunk_hilo_to_q(_capi.ptr(thi), _capi.ptr(tlo), _capi.ptr(tq), n, H, W, C, _capi.stream_ptr()),
+                'hilo_to_q')
+    torch.cuda.synchronize()
+    eh, eq = _q_encode(hi.astype(np.float32) + lo.astype(np.float32))
+    assert np.array_equal(thi.cpu().numpy().view(np.uint16), eh.view(np.uint16))
+    assert np.array_equal(_q_from_tiles(tq.cpu().numpy()), eq)
+
+
+@pytest.mark.parametrize('shape', [(2, 32, 32), (1, 128, 128), (3, 40, 24)])
+def test_conv_resq256_trunk_update(env, shape):
+    """The 256-feature (VDSen2) resblock update on the fp16 + 8 bit trunk: two 64-channel passes per thread."""
+    torch, _capi, lib = env
+    n, H, W = shape
+    F = 256
+    rng = np.random.RandomState(H + 7 * W)
+    t = np.maximum(rng.randn(n, H, W, F), 0).astype(np.float16)
+    x = rng.randn(n, H, W, F).astype(np.float32)
+    lim = np.sqrt(6.0 / (9 * F))
+    w = rng.uniform(-lim, lim, size=(3, 3, F, F)).astype(np.float32)
+    bias = (rng.randn(F) * 0.1).astype(np.float32)
+    tw = torch.empty((9, F, F), dtype=torch.float16, device='cuda')
+    _capi.check(lib.dsen2_pack_conv_weights(_capi.ptr(torch.from_numpy(w).cuda()), F, F, F, F, 0, _capi.ptr(tw), None,
+                                            _capi.stream_ptr()), 'pack')
+    h0, q0 = _q_encode(x)
+    x_seen = _q_decode(h0, q0)
+    thi, tq = torch.from_numpy(h0).cuda(), torch.from_numpy(_q_to_tiles(q0)).cuda()
+    tt, tb = torch.from_numpy(t).cuda(), torch.from_numpy(bias).cuda()
+    _capi.check(lib.dsen2_conv_resq256(_capi.ptr(tt), _capi.ptr(tw), _capi.ptr(tb), n, H, W, 0.1, _capi.ptr(thi),
+                                       _capi.ptr(tq), None, _capi.stream_ptr()), 'conv resq256')
+    torch.cuda.synchronize()
+    ref = x_seen.astype(np.float64) + 0.1 * _conv64(t.astype(np.float64), w.astype(np.float16).astype(np.float64), bias)
+    h, q = thi.cpu().numpy(), _q_from_tiles(tq.cpu().numpy())
+    got = _q_decode(h, q)
+    np.testing.assert_allclose(got, ref, rtol=3e-5, atol=3e-5)
+    ok = np.abs(got) >= 2 * NORMAL
+    h2, q2 = _q_encode(got[ok])
+    assert np.array_equal(h2.view(np.uint16), h[ok].view(np.uint16)) and np.array_equal(q2, q[ok])

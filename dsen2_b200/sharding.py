@@ -85,6 +85,14 @@ def plan_chunks(first, count, H, W, P, border, chunk_patch_rows):
     return plan
 
 
+def auto_chunk_rows(num_patches, nx):
+    """Patch rows per host-pipeline chunk: the first chunk's upload and the last chunk's download are not hidden behind
+    compute, so a chunk is about a twelfth of the call's share of the tile, between 1 and 3 patch rows (a rank of 8
+    holds ~12 patch rows of a full Sentinel-2 tile, one GPU all 99)."""
+    rows = -(-int(num_patches) // int(nx))
+    return max(1, min(3, rows // 12))
+
+
 def assemble(canvas, parts):
     """Host-side assembly: parts = [(first, count, rows_y0, band ndarray (y1-y0, W, C))]; writes owned rects."""
     H, W = canvas.shape[:2]

@@ -143,11 +143,9 @@ class HostPipeline:
         self.up.wait_stream(main)
         self.down.wait_stream(main)
         done10 = done20 = done60 = None           # rows already resident on the device (per resolution)
-        # the first chunk's upload and the last chunk's download are not hidden behind compute: keep chunks small
-        # relative to this call's share of the tile (a rank of 8 holds ~12 patch rows of a full tile)
         chunk_rows = self.chunk_rows
         if chunk_rows is None:
-            chunk_rows = max(1, min(3, -(-num_patches // self.nx) // 12))
+            chunk_rows = sharding.auto_chunk_rows(num_patches, self.nx)
         for p0, cnt, (r0, r1), rects in sharding.plan_chunks(first_patch, num_patches, self.H, self.W, self.P, self.B,
                                                              int(chunk_rows)):
             with torch.cuda.stream(self.up):

@@ -138,3 +138,18 @@ def test_compat_shims_importable():
         sys.path.remove(compat)
         for m in ('supres', 'utils', 'utils.DSen2Net', 'utils.patches', 'utils.imresize'):
             sys.modules.pop(m, None)
+
+
+def test_batch_and_chunk_sizing_rules():
+    """Device batches are whole patch rows (so host-pipeline chunks split evenly); chunks follow the call's share."""
+    from dsen2_b200 import sharding
+    from dsen2_b200.supres import default_device_batch
+    assert default_device_batch(10980, 128, 8) == 3 * 99          # full tile, 20 m path: three patch rows
+    assert default_device_batch(10980, 192, 12) == 2 * 66         # 60 m path: two rows of 192-pixel patches
+    assert default_device_batch(600, 128, 8) >= 36                # a 600 x 600 scene is one launch
+    assert default_device_batch(2352, 128, 8) % 21 == 0
+    assert sharding.auto_chunk_rows(9801, 99) == 3                # one GPU: 99 patch rows
+    assert sharding.auto_chunk_rows(1226, 99) == 1                # a rank of 8
+    assert sharding.auto_chunk_rows(36, 6) == 1                   # small scene
+    plan = sharding.plan_chunks(0, 9801, 10980, 10980, 128, 8, sharding.auto_chunk_rows(9801, 99))
+    assert len(plan) == 33 and sum(c[1] for c in plan) == 9801 and all(c[1] == 297 for c in plan)

@@ -1,0 +1,33 @@
+"""Error budget of the precision design, on the CPU (no GPU needed): the roundings of the device path applied to a
+float64 evaluation of the DSen2 graph.  North-star gate: max |err| <= 5e-3 on the /2000-scaled output."""
+import numpy as np
+
+from emulate import forward_emulated, forward_exact
+from oracle import dsen2net_oracle as no
+
+
+def _case(seed=3, n=2, P=40):
+    rng = np.random.RandomState(seed)
+    xs = [(0.8 + 0.45 * rng.randn(n, c, P, P)).clip(0, 6).astype(np.float32) for c in (4, 6)]
+    w = no.he_uniform_weights(10, 6, 6, 128, seed=seed)
+    w = [(k, (0.05 * rng.randn(*b.shape)).astype(np.float32)) for k, b in w]
+    return xs, w
+
+
+def test_trunk_formats_against_the_exact_graph():
+    xs, w = _case()
+    ref = forward_exact(xs, w)
+    err = {t: np.abs(forward_emulated(xs, w, trunk=t) - ref).max() for t in ('fp32', 'q8', 'fp16')}
+    print('max abs error vs float64:', {k: float(v) for k, v in err.items()})
+    assert err['fp32'] < 2.5e-3 and err['q8'] < 2.5e-3            # gate 5e-3
+    assert abs(err['q8'] - err['fp32']) < 1e-4                     # 19 significant bits: indistinguishable from fp32
+    assert err['fp16'] > err['q8']                                 # an fp16 trunk is what the extra byte buys back
+
+
+def test_split_first_and_last_layer_matter():
+    xs, w = _case(seed=5)
+    ref = forward_exact(xs, w)
+    e_split = np.abs(forward_emulated(xs, w, trunk='q8', split_ends=True) - ref).max()
+    e_plain = np.abs(forward_emulated(xs, w, trunk='q8', split_ends=False) - ref).max()
+    print('split ends %.2e, fp16 ends %.2e' % (e_split, e_plain))
+    assert e_split < e_plain

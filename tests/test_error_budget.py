@@ -31,3 +31,20 @@ def test_split_first_and_last_layer_matter():
     e_plain = np.abs(forward_emulated(xs, w, trunk='q8', split_ends=False) - ref).max()
     print('split ends %.2e, fp16 ends %.2e' % (e_split, e_plain))
     assert e_split < e_plain
+
+
+def test_winograd_trunk_feasibility():
+    """Next-round study: Winograd F(2x2,3x3) trunk convolutions with fp16 transformed operands stay inside the gate
+    (the transform itself is exact: checked against the direct convolution in float64 first)."""
+    from emulate import conv_winograd_f16, forward_emulated_winograd, _conv64
+    rng = np.random.RandomState(1)
+    x = rng.randn(1, 8, 12, 12).astype(np.float16).astype(np.float32)
+    w = (rng.randn(3, 3, 8, 5) * 0.1).astype(np.float32)
+    b = rng.randn(5).astype(np.float32)
+    np.testing.assert_allclose(conv_winograd_f16(x, w, b), _conv64(x, w, b), rtol=0, atol=5e-3)   # fp16 operand rounding only
+    xs, wts = _case()
+    ref = forward_exact(xs, wts)
+    e_direct = np.abs(forward_emulated(xs, wts, trunk='q8') - ref).max()
+    e_wino = np.abs(forward_emulated_winograd(xs, wts) - ref).max()
+    print('direct %.2e, winograd %.2e' % (e_direct, e_wino))
+    assert e_wino < 5e-3

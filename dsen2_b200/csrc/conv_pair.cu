@@ -32,7 +32,10 @@ namespace dsen2 {
 // instruction-heavy epilogue warps that share its sub-partition (measured: tensor pipe 59 % -> see profiles/).
 // (PairCfg::PRODUCER_WARP / MMA_WARP = the two warps after the epilogue warps)
 static constexpr int kBoxH = 18;
-static constexpr int kPrefetchTiles = 1;        // L2 prefetch distance of the activation boxes, in tiles of this CTA
+// L2 prefetch distance of the activation boxes, in tiles of this CTA (DSEN2_PAIR_PF_A).  0 = off: with the compact trunk
+// the full tile measures 559-560 ms without it against 565-567 ms with distance 1 (same box, alternating runs); with the
+// fp32 trunk distance 1 was the better setting.
+static constexpr int kPrefetchTiles = 0;
 static constexpr int kTrunkPrefetchTiles = 1;   // same for the fp32 trunk lines the RESIDUAL32 epilogue reads
 
 enum { kEpiRelu = 0, kEpiResidual = 1, kEpiTail = 2, kEpiResidual32 = 3, kEpiMask = 4, kEpiResidualQ = 5, kEpiResidualQLast = 6 };

@@ -33,7 +33,6 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-DTYPE_FP32 = "fp16 operands, fp32 accumulate (TMEM), fp32 residual trunk; first/last layer split hi+lo (fp32-equivalent)"
 DTYPE_Q8 = ("fp16 operands, fp32 accumulate (TMEM), residual trunk fp16 + 8 bits (19 significant bits); first/last layer split "
             "hi+lo (fp32-equivalent)")
 
@@ -110,40 +109,56 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------- #
 # CPU oracle legs
 # ---------------------------------------------------------------------------------------------- #
-def cpu_oracle_run(crop, steps, warmup, deep=False):
-    """Time the CPU oracle end to end on a crop x crop (10 m) synthetic scene; returns (Mpixel/s, s/step, threads)."""
+def cpu_sample(deep):
+    """The bounded sample BOTH CPU legs time (the `--impl reference` arm and the GPU arm's `cpu_baseline`): a crop of the
+    synthetic scene whose patch count is a whole number of the reference's predict batches (32 for DSen2, 8 for VDSen2,
+    supres.py:65) and whose allocated patch stack has no surplus zero patches (H/2, W/2 not multiples of 56).
+    DSen2: 892 x 1340 = 8 x 12 = 96 patches (3 batches, ~5 s per pass on 16 cores); VDSen2: 444 x 444 = 16 patches."""
+    return (444, 444) if deep else (892, 1340)
+
+
+def cpu_oracle_run(shape, steps, warmup, deep=False):
+    """Time the CPU oracle end to end on an (H, W) 10 m synthetic scene; returns (Mpixel/s, s/step, threads, patches)."""
     import torch
     from oracle import dsen2net_oracle as no
     torch.set_num_threads(os.cpu_count() or 1)
+    H, W = shape
     rng = np.random.RandomState(20170928)
-    d10 = rng.randint(200, 6000, size=(crop, crop, 4)).astype(np.float32)
-    d20 = rng.randint(200, 6000, size=(crop // 2, crop // 2, 6)).astype(np.float32)
+    d10 = rng.randint(200, 6000, size=(H, W, 4)).astype(np.float32)
+    d20 = rng.randint(200, 6000, size=(H // 2, W // 2, 6)).astype(np.float32)
     w = no.he_uniform_weights(10, 6, 32 if deep else 6, 256 if deep else 128, seed=0)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         out = no.DSen2_20(d10, d20, w)
         dt = time.perf_counter() - t0
-        assert out.shape == (crop, crop, 6)
+        assert out.shape == (H, W, 6)
         if i >= warmup:
             times.append(dt)
     per = float(np.mean(times))
-    return crop * crop / per / 1e6, per, torch.get_num_threads()
+    patches = (-(-H // 112)) * (-(-W // 112))
+    return H * W / per / 1e6, per, torch.get_num_threads(), patches
+
+
+def cpu_sample_text(shape, patches, per):
+    return ("%dx%d crop (%d patches = whole predict batches) of the synthetic scene through the CPU oracle port (numpy "
+            "extract/bilinear/stitch + torch-CPU fp32 conv graph; TensorFlow/Keras not installable), %.1f s per pass; "
+            "extrapolates linearly to the tile" % (shape[0], shape[1], patches, per))
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    crop = 448                                       # 16 patches of 128x128 per step (bounded sample)
-    mpx, per, threads = cpu_oracle_run(crop, args.steps, args.warmup, deep=args.model == 'vdsen2')
-    sample = ("%dx%d crop (16 patches) of the synthetic tile through the CPU oracle port "
-              "(numpy extract/bilinear/stitch + torch-CPU fp32 conv graph); TensorFlow/Keras not installable" % (crop, crop))
+    deep = args.model == 'vdsen2'
+    shape = cpu_sample(deep)
+    mpx, per, threads, patches = cpu_oracle_run(shape, args.steps, args.warmup, deep=deep)
     line = {"impl": "reference", "metric": "output_Mpixel_per_s", "value": mpx, "unit": "Mpixel/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
             "config": workload_config(args, cpu=True),
-            "cpu_baseline": {"value": mpx, "unit": "Mpixel/s", "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": mpx, "unit": "Mpixel/s", "cores": threads, "kind": "port",
+                             "sample": cpu_sample_text(shape, patches, per)},
             "e2e": {"value": mpx, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -164,6 +179,12 @@ def workload_config(args, cpu=False):
 # ---------------------------------------------------------------------------------------------- #
 # GPU arm
 # ---------------------------------------------------------------------------------------------- #
+# DRAM bytes per patch and launch of the trunk convolutions, dram__bytes_read.sum + dram__bytes_write.sum of an
+# `ncu --set full` capture (a CONSTANT taken from the named file, not measured in the bench run): mean of the RELU layer
+# (660 MB per 84 patches) and the RESIDUALQ layer (1359 MB per 84 patches).
+NCU_TRAFFIC = {128: dict(bytes_per_patch=(7.86e6 + 16.18e6) / 2, source="profiles/r01_q_trunk_ncu_full.txt")}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -210,9 +231,8 @@ def run_ours(args):
     cout = model.out_channels
     out = torch.zeros((T, T, cout), dtype=torch.float32, device=dev)
     n_batches = -(-count // args.batch)
-    # fast path (DSen2): 1 input-preparation kernel + 14 convolutions per batch (extract / bilinear / stitch are
-    # fused into them); VDSen2: 2 extract + bilinear + im2col pack + 66 convolutions + stitch
-    launches_per_step = n_batches * (model.launches_per_forward() if model.fast_path else 4 + model.launches_per_forward())
+    # per batch: 1 input-preparation kernel + 2 + 2 * num_layers convolutions (extract / bilinear / stitch are fused into them)
+    launches_per_step = n_batches * model.launches_per_forward()
 
     def step(timers=None):
         supres.super_resolve_device(model, d10, d20, d60, first_patch=first, num_patches=count, out=out,
@@ -254,67 +274,43 @@ def run_ours(args):
         if ms:
             by_epi[label] = {"avg_launch_ms": float(np.mean(ms)), "tflops_executed": exec_flop / float(np.mean(ms)) / 1e9,
                              "frac_executed": exec_flop / float(np.mean(ms)) / 1e9 / pk['tf_sust']}
-    # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum of ncu --set full captures, per patch):
-    #   fp16 + 8 bit trunk: RELU 660 MB, RESIDUALQ 1359 MB per 84 patches   (profiles/r01_q_trunk_ncu_full.txt)
-    #   fp32 trunk:         RELU 492 MB, RESIDUAL32 1556 MB per 57.14 patches (profiles/r01_pair_kernels_ncu_full.txt)
-    q8 = model.fast_path and model.trunk_format == 'q8'
-    per_patch = (7.86e6 + 16.18e6) / 2 if q8 else (8.61e6 + 27.23e6) / 2
-    traffic = per_patch * float(np.mean(conv_n)) if model.fast_path else None
-    traffic_src = "profiles/r01_q_trunk_ncu_full.txt" if q8 else "profiles/r01_pair_kernels_ncu_full.txt"
-    kname = ("conv_pair_kernel<N=128> (CTA-pair tcgen05 3x3 conv 128->128, RELU / RESIDUAL%s epilogues; %%d of %%d convs)" % ('Q' if q8 else '32')
-             if model.fast_path else "conv_tcgen05_kernel<%d>" % F + " (3x3 conv, RELU / RESIDUAL epilogues; %d of %d convs)")
-    roofline = {"bound": "tensor", "kernel": kname % (2 * model.num_layers, 2 * model.num_layers + 2),
+    ncu = NCU_TRAFFIC.get(F)
+    traffic = ncu['bytes_per_patch'] * float(np.mean(conv_n)) if ncu else None
+    traffic_src = ("CONSTANT, not measured in this run: ncu --set full dram__bytes_read+write per launch of %s, scaled "
+                   "per patch" % ncu['source']) if ncu else "no ncu capture for this shape"
+    kname = ("conv_pair_kernel<N=%d> (CTA-pair tcgen05 3x3 conv %d->%d, %s weights, RELU / RESIDUALQ epilogues; %d of %d convs)"
+             % (F, F, F, 'shared-memory resident' if F == 128 else 'streamed', 2 * model.num_layers, 2 * model.num_layers + 2))
+    roofline = {"bound": "tensor", "kernel": kname,
                 "achieved": algo_flop / kernel_ms / 1e9, "achieved_executed": exec_flop / kernel_ms / 1e9,
                 "peak": pk['tf_sust'], "peak_burst": pk['tf_burst'], "peak_source": pk['source'] + ", sustained figure (kernel timed inside a long step)",
                 "unit": "TFLOP/s", "frac": algo_flop / kernel_ms / 1e9 / pk['tf_sust'],
                 "frac_executed": exec_flop / kernel_ms / 1e9 / pk['tf_sust'],
                 "avg_launch_ms": kernel_ms, "patches_per_launch": float(np.mean(conv_n)),
                 "algorithmic_flop_per_launch": algo_flop, "executed_flop_per_launch": exec_flop, "traffic": traffic,
-                "traffic_source": "ncu dram__bytes_read+write per launch, scaled per patch (%s)" % traffic_src,
-                "by_epilogue": by_epi, "ms_per_step_by_kernel": per_kind}
+                "traffic_source": traffic_src, "by_epilogue": by_epi, "ms_per_step_by_kernel": per_kind}
 
     # ---- e2e: pinned host -> device -> pinned host every step, through the public host-buffer pipeline --------
-    # (supres.HostPipeline is what supres.DSen2_20 runs on numpy inputs: chunked uploads / compute / downloads
-    #  overlapped on three streams.)  Each rank moves only the input rows its patches read and the output
-    #  pixels they own.
-    h10 = torch.empty((T, T, 4), dtype=torch.float32).pin_memory()
-    h20 = torch.empty((T // 2, T // 2, 6), dtype=torch.float32).pin_memory()
-    h60 = torch.empty((T // 6, T // 6, 2), dtype=torch.float32).pin_memory() if run_60 else None
+    # supres.HostPipeline is what supres.DSen2_20 runs: chunked uploads / compute / downloads overlapped on three
+    # streams.  Host inputs are uint16 digital numbers (what Sentinel-2 L1C holds and GDAL delivers,
+    # s2_tiles_supres.py:311-315; the synthetic DN are integers), the output float32 as the reference returns it.
+    # Each rank moves only the input rows its patches read and the output pixels they own.
+    y0, y1 = sharding.output_rows(first, count, T, T, P, B)
+    dev_rows = out[y0:y1].clone()                       # device-resident result, to check the e2e result against
+    h10 = torch.empty((T, T, 4), dtype=torch.uint16).pin_memory()
+    h20 = torch.empty((T // 2, T // 2, 6), dtype=torch.uint16).pin_memory()
+    h60 = torch.empty((T // 6, T // 6, 2), dtype=torch.uint16).pin_memory() if run_60 else None
     hout = torch.zeros((T, T, cout), dtype=torch.float32).pin_memory()
-    h10.copy_(d10); h20.copy_(d20)
+    h10.numpy()[...] = d10.cpu().numpy()                # integer-valued float32 -> uint16, exact
+    h20.numpy()[...] = d20.cpu().numpy()
     if run_60:
-        h60.copy_(d60)
+        h60.numpy()[...] = d60.cpu().numpy()
     torch.cuda.synchronize()
     del d10, d20, d60, tile, out
     torch.cuda.empty_cache()
-    if model.fast_path:
-        pipe = supres.HostPipeline(model, T, T, run_60=run_60, device=dev, device_batch=args.batch)
+    pipe = supres.HostPipeline(model, T, T, run_60=run_60, device=dev, device_batch=args.batch, dtype=torch.uint16)
 
-        def step_e2e():
-            pipe.run(h10, h20, h60, hout=hout, first_patch=first, num_patches=count)
-    else:                                   # VDSen2: plain upload -> device pipeline -> download of the rank's rows
-        r0, r1 = sharding.input_rows(first, count, T, T, P, B)
-        o0, o1 = sharding.output_rows(first, count, T, T, P, B)
-        g10 = torch.empty((T, T, 4), dtype=torch.float32, device=dev)
-        g20 = torch.empty((T // 2, T // 2, 6), dtype=torch.float32, device=dev)
-        g60 = torch.empty((T // 6, T // 6, 2), dtype=torch.float32, device=dev) if run_60 else None
-        gout = torch.zeros((T, T, cout), dtype=torch.float32, device=dev)
-
-        class _Plain:
-            h2d_bytes = d2h_bytes = 0
-        pipe = _Plain()
-
-        def step_e2e():
-            g10[r0:r1].copy_(h10[r0:r1], non_blocking=True)
-            g20[r0 // 2:-(-r1 // 2)].copy_(h20[r0 // 2:-(-r1 // 2)], non_blocking=True)
-            if run_60:
-                g60[r0 // 6:-(-r1 // 6)].copy_(h60[r0 // 6:-(-r1 // 6)], non_blocking=True)
-            supres.super_resolve_device(model, g10, g20, g60, first_patch=first, num_patches=count, out=gout,
-                                        device_batch=args.batch)
-            hout[o0:o1].copy_(gout[o0:o1], non_blocking=True)
-            pipe.h2d_bytes = (r1 - r0) * T * 16 + (-(-r1 // 2) - r0 // 2) * (T // 2) * 24 + \
-                ((-(-r1 // 6) - r0 // 6) * (T // 6) * 8 if run_60 else 0)
-            pipe.d2h_bytes = (o1 - o0) * T * cout * 4
+    def step_e2e():
+        pipe.run(h10, h20, h60, hout=hout, first_patch=first, num_patches=count)
 
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()
@@ -331,25 +327,53 @@ def run_ours(args):
         tb = torch.tensor([h2d, d2h], dtype=torch.float64, device=dev)
         dist.all_reduce(tb)
         h2d, d2h = int(tb[0].item()), int(tb[1].item())
-    y0, y1 = sharding.output_rows(first, count, T, T, P, B)
+    # the rows this rank owns completely: host-pipeline result (uint16 in, chunked) == device-resident result (float32 in)
+    rects = [rc for rc in sharding.owned_rects(first, count, T, T, P, B) if rc[2] == 0 and rc[3] == T]
+    same = all(bool(torch.equal(hout[a:b].to(dev), dev_rows[a - y0:b - y0])) for a, b, _, _ in rects)
     checksum = float(hout[y0:y1:97, ::89].double().sum())
+    del dev_rows
+
+    # ---- e2e through the facade itself: supres.DSen2_20(numpy, numpy, model=) -> numpy, pageable host arrays -----------
+    facade = None
+    if world == 1 and not args.no_facade:
+        n10, n20 = h10.numpy().copy(), h20.numpy().copy()          # ordinary (pageable) numpy arrays, uint16 DN
+        n60 = h60.numpy().copy() if run_60 else None
+        del pipe
+        torch.cuda.empty_cache()
+        call = (lambda **kw: supres.DSen2_60(n10, n20, n60, model=model, **kw)) if run_60 else \
+            (lambda **kw: supres.DSen2_20(n10, n20, model=model, **kw))
+        res = call()                                               # first call: allocates the pipeline + staging ring
+        fresh, reuse = [], []
+        for _ in range(2):
+            t0 = time.perf_counter(); res = call(); fresh.append(time.perf_counter() - t0)
+        for _ in range(2):
+            t0 = time.perf_counter(); call(out=res); reuse.append(time.perf_counter() - t0)
+        ok = bool(np.array_equal(res[y0:y1:97, ::89], hout[y0:y1:97, ::89].numpy()))
+        facade = {"call": "supres.DSen2_%d(numpy uint16 ..., model=) -> numpy float32, pageable host arrays" % args.path,
+                  "ms_fresh_output": float(np.mean(fresh)) * 1e3, "ms_reused_output": float(np.mean(reuse)) * 1e3,
+                  "value_fresh_output": T * T / float(np.mean(fresh)) / 1e6, "value_reused_output": T * T / float(np.mean(reuse)) / 1e6,
+                  "unit": "Mpixel/s", "timing": "host wall clock around the call (it synchronises), mean of 2",
+                  "matches_pinned_pipeline": ok}
 
     if rank == 0:
         line = {"metric": "output_Mpixel_per_s", "value": value, "unit": "Mpixel/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": DTYPE_Q8 if (model.fast_path and model.trunk_format == 'q8') else DTYPE_FP32,
+                "scaling": "strong", "vs_baseline": None, "dtype": DTYPE_Q8,
                 "data": "synthetic", "config": workload_config(args), "clocks": clocks,
                 "e2e": {"value": T * T / (e2e_ms * 1e-3) / 1e6, "unit": "Mpixel/s", "ms_per_step": e2e_ms,
-                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "host_buffers": "pinned; inputs uint16 DN, output float32",
+                        "matches_device_resident": same},
                 "gpu_launches": launches_per_step * args.steps, "roofline": roofline,
                 "tflops_executed_whole_step": FLOP_PER_PIXEL[(args.model, args.path)] * float(filled) * P * P / (ms_step * 1e-3) / 1e12,
                 "checksum": checksum}
+        if facade:
+            line["e2e_facade"] = facade
         if world == 1 and not args.no_cpu_baseline:
-            crop = 448 if deep else 1344             # ~10-20 s of host work
-            mpx, per, threads = cpu_oracle_run(crop, 1, 0, deep=deep)
+            shp = cpu_sample(deep)                   # the same sample the `--impl reference` arm times
+            mpx, per, threads, patches = cpu_oracle_run(shp, 1, 0, deep=deep)
             line["cpu_baseline"] = {"value": mpx, "unit": "Mpixel/s", "cores": threads, "kind": "port",
-                                    "sample": "%dx%d crop (%d patches) through the CPU oracle port, %.1f s; "
-                                              "extrapolates linearly to the tile" % (crop, crop, (crop // 112) ** 2, per)}
+                                    "sample": cpu_sample_text(shp, patches, per)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -451,6 +475,7 @@ def main():
     ap.add_argument('--path', type=int, default=20, choices=[20, 60], help='20 m -> 10 m (DSen2_20) or 60 m -> 10 m (DSen2_60)')
     ap.add_argument('--batch', type=int, default=0, help='patches per device batch (0 = whole patch rows, see supres.default_device_batch)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-facade', action='store_true', help='skip the e2e_facade leg (numpy -> supres.DSen2_20 -> numpy)')
     ap.add_argument('--workload', default='tile', choices=['tile', 'train'],
                     help="'tile' = the headline inference benchmark; 'train' = BASELINE.json configs[4] (training step)")
     ap.add_argument('--train-batch', type=int, default=128)

@@ -103,24 +103,12 @@ class S2Model:
 
     # ---- device side ------------------------------------------------------------------- #
     @property
-    def fast_path(self):
-        """DSen2 (128 features): CTA-pair kernels with split-precision first / last layer (csrc/conv_pair.cu).
-        VDSen2 (256 features) runs the single-CTA streaming kernel (csrc/conv_tcgen05.cu)."""
-        return self.feature_size == 128 and sum(self.in_channels) <= 16 and self.out_channels <= 16
-
-    @property
-    def trunk_format(self):
-        """How the residual trunk of the fast path lives in HBM between resblocks: 'q8' = the fp16 tensor the next
-        convolution reads + one extra byte per element (19 significant bits, 1024 B/pixel/resblock of traffic; default),
-        'fp32' = a separate fp32 tensor (1536 B/pixel/resblock; ``DSEN2_TRUNK=fp32``, what the training step uses)."""
-        return 'fp32' if os.environ.get('DSEN2_TRUNK', 'q8') == 'fp32' else 'q8'
-
-    @property
     def xin16(self):
-        """The default inference path prepares the network input un-gathered (16 channels, ``dsen2_prep16_*``) and
-        runs the first layer with nine taps (``dsen2_conv_head16_q``); the fp32-trunk variant and a network without
-        resblocks keep the 64-channel form with the three horizontal taps pre-gathered (what the training step uses)."""
-        return self.fast_path and self.trunk_format != 'fp32' and self.num_layers > 0
+        """Networks with resblocks (DSen2, VDSen2) prepare the input un-gathered (16 channels, ``dsen2_prep16_*``), run
+        the first layer with nine taps (``dsen2_conv_head16_q``) and keep the residual trunk as fp16 + 8 bits (include/
+        dsen2_b200.h).  A network WITHOUT resblocks (128 features only) keeps the 64-channel form with the three
+        horizontal taps pre-gathered, whose first layer hands the last one an fp16 hi + lo pair."""
+        return self.num_layers > 0
 
     def _ensure_packed(self, device):
         torch = _capi.require_cuda()
@@ -129,8 +117,6 @@ class S2Model:
             return self._packed[key]
         lib = _capi.lib()
         F = self.feature_size
-        ctot = sum(self.in_channels)
-        k_pad = (9 * ctot + 63) // 64 * 64
         wts, biases = [], []
         with torch.cuda.device(device):
             st = _capi.stream_ptr()
@@ -143,23 +129,21 @@ class S2Model:
                     _capi.check(lib.dsen2_pack_head16_weights(_capi.ptr(src), cin, F, _capi.ptr(dst), st),
                                 "dsen2_pack_head16_weights")
                     cout_pad = F
-                elif head and self.fast_path:
+                elif head:
                     dst = torch.empty((3, 2 * F, 64), dtype=torch.float16, device=device)
                     _capi.check(lib.dsen2_pack_head_weights(_capi.ptr(src), cin, F, _capi.ptr(dst), st),
                                 "dsen2_pack_head_weights")
                     cout_pad = F
-                elif tail and self.fast_path:
+                elif tail:
                     dst = torch.empty((9, 32, F), dtype=torch.float16, device=device)
                     _capi.check(lib.dsen2_pack_tail_weights(_capi.ptr(src), F, cout, _capi.ptr(dst), st),
                                 "dsen2_pack_tail_weights")
                     cout_pad = 16
                 else:
-                    cin_pad = k_pad if head else F
-                    cout_pad = 16 if tail else F
-                    taps = 1 if head else 9
-                    dst = torch.empty((taps, cout_pad, cin_pad), dtype=torch.float16, device=device)
-                    _capi.check(lib.dsen2_pack_conv_weights(_capi.ptr(src), cin, cout, cin_pad, cout_pad, int(head),
-                                                            _capi.ptr(dst), None, st), "dsen2_pack_conv_weights")
+                    cout_pad = F
+                    dst = torch.empty((9, F, F), dtype=torch.float16, device=device)
+                    _capi.check(lib.dsen2_pack_conv_weights(_capi.ptr(src), cin, cout, F, F, 0, _capi.ptr(dst), None, st),
+                                "dsen2_pack_conv_weights")
                 bp = torch.zeros((max(cout_pad, 16),), dtype=torch.float32, device=device)
                 bp[:cout] = torch.from_numpy(b).to(device)
                 wts.append(dst)
@@ -183,18 +167,10 @@ class S2Model:
                 self._workspace.clear()
             F = self.feature_size
             mk = lambda c: torch.empty((n, P, P, c), dtype=torch.float16, device=dev)
-            if self.fast_path:
-                cx = 16 if self.xin16 else 64                                # prepared input: un-gathered / 3 taps gathered
-                buf = dict(xin_hi=mk(cx), xin_lo=mk(cx), x_hi=mk(F), x_lo=mk(F), t=mk(F))
-                if self.trunk_format == 'fp32':                              # tile-row-major fp32 trunk
-                    buf['x32'] = torch.empty((n, P, (P + 7) // 8, F // 4, 8, 4), dtype=torch.float32, device=dev)
-                else:                                                        # low bytes of the fp16 + 8 bit trunk
-                    buf['xq'] = torch.empty((n, P, (P + 7) // 8, F // 16, 8, 16), dtype=torch.uint8, device=dev)
-            else:
-                k_pad = (9 * sum(self.in_channels) + 63) // 64 * 64
-                buf = dict(a0=mk(k_pad), x_hi=mk(F), x_lo=mk(F), t=mk(F), k_pad=k_pad)
-                if F == 256 and self.trunk_format != 'fp32':
-                    buf['xq'] = torch.empty((n, P, (P + 7) // 8, F // 16, 8, 16), dtype=torch.uint8, device=dev)
+            cx = 16 if self.xin16 else 64                                    # prepared input: un-gathered / 3 taps gathered
+            buf = dict(xin_hi=mk(cx), xin_lo=mk(cx), x_hi=mk(F), x_lo=mk(F), t=mk(F))
+            if self.xin16:                                                   # low bytes of the fp16 + 8 bit trunk
+                buf['xq'] = torch.empty((n, P, (P + 7) // 8, F // 16, 8, 16), dtype=torch.uint8, device=dev)
             self._workspace[key] = buf
         return buf
 
@@ -209,62 +185,35 @@ class S2Model:
         e1.record()
         timers.setdefault(kind, []).append((e0, e1, n))
 
-    def _trunk(self, buf, wts, biases, n, P, st, timers, first=None):
-        """head (if ``first`` is None: from x_in) + resblocks on the buffers; shared by both input forms."""
+    def _trunk(self, buf, wts, biases, n, P, st, timers):
+        """First layer + resblocks on the buffers; shared by the patch-stack and the image form of the input."""
         lib, ptr, F, L = _capi.lib(), _capi.ptr, self.feature_size, self.num_layers
         x_hi, x_lo, t = buf['x_hi'], buf['x_lo'], buf['t']
-        if self.fast_path and self.trunk_format != 'fp32' and L > 0:
-            # fp16 + 8 bit trunk: x_hi (NHWC, what the next convolution reads) updated in place + one byte per element
-            # (include/dsen2_b200.h, dsen2_conv_resq); the last block hands the tail x_hi, x_lo
-            xq = buf['xq']
-            self._timed(timers, 'conv_head', n, lambda: _capi.check(lib.dsen2_conv_head16_q(
-                ptr(buf['xin_hi']), ptr(buf['xin_lo']), ptr(wts[0]), ptr(biases[0]), n, P, P, F, ptr(x_hi), ptr(xq), st),
-                "dsen2_conv_head16_q"))
-            for l in range(L):
-                self._timed(timers, 'conv_res1', n, lambda: _capi.check(lib.dsen2_conv3x3(
-                    ptr(x_hi), ptr(wts[1 + 2 * l]), ptr(biases[1 + 2 * l]), n, P, P, F, F, 9, _capi.EPI_RELU, None,
-                    None, 0.0, ptr(t), None, None, None, 0, st), "dsen2_conv3x3(res conv1)"))
-                self._timed(timers, 'conv_res2', n, lambda: _capi.check(lib.dsen2_conv_resq(
-                    ptr(t), ptr(wts[2 + 2 * l]), ptr(biases[2 + 2 * l]), n, P, P, 0.1, ptr(x_hi), ptr(xq),
-                    ptr(x_lo) if l == L - 1 else None, st), "dsen2_conv_resq"))
-            return
-        if self.fast_path:
-            # fp32 trunk (tile-row-major) updated in place by every resblock; x_lo only for the tail's split operand
-            x32 = buf.get('x32')
+        if L == 0:
+            # no resblocks: the 64-channel first layer writes the fp16 hi + lo pair the last layer reads
             self._timed(timers, 'conv_head', n, lambda: _capi.check(lib.dsen2_conv_head(
-                ptr(buf['xin_hi']), ptr(buf['xin_lo']), ptr(wts[0]), ptr(biases[0]), n, P, P, F, ptr(x_hi),
-                ptr(x_lo) if L == 0 else None, ptr(x32) if L > 0 else None, st), "dsen2_conv_head"))
-            for l in range(L):
-                self._timed(timers, 'conv_res1', n, lambda: _capi.check(lib.dsen2_conv3x3(
-                    ptr(x_hi), ptr(wts[1 + 2 * l]), ptr(biases[1 + 2 * l]), n, P, P, F, F, 9, _capi.EPI_RELU, None,
-                    None, 0.0, ptr(t), None, None, None, 0, st), "dsen2_conv3x3(res conv1)"))
-                self._timed(timers, 'conv_res2', n, lambda: _capi.check(lib.dsen2_conv_res32(
-                    ptr(t), ptr(wts[2 + 2 * l]), ptr(biases[2 + 2 * l]), n, P, P, 0.1, ptr(x32), ptr(x_hi),
-                    ptr(x_lo) if l == L - 1 else None, st), "dsen2_conv_res32"))
+                ptr(buf['xin_hi']), ptr(buf['xin_lo']), ptr(wts[0]), ptr(biases[0]), n, P, P, F, ptr(x_hi), ptr(x_lo), None,
+                st), "dsen2_conv_head"))
             return
-        self._timed(timers, 'conv_head', n, lambda: _capi.check(lib.dsen2_conv3x3(
-            ptr(buf['a0']), ptr(wts[0]), ptr(biases[0]), n, P, P, buf['k_pad'], F, 1, _capi.EPI_RELU, None, None,
-            0.0, ptr(x_hi), ptr(x_lo), None, None, 0, st), "dsen2_conv3x3(head)"))
-        if 'xq' in buf and L > 0:
-            # VDSen2 on the fp16 + 8 bit trunk: the single-CTA first layer wrote hi + lo, re-code once, then as DSen2
-            xq = buf['xq']
-            self._timed(timers, 'conv_head', n, lambda: _capi.check(lib.dsen2_trunk_hilo_to_q(
-                ptr(x_hi), ptr(x_lo), ptr(xq), n, P, P, F, st), "dsen2_trunk_hilo_to_q"))
-            for l in range(L):
-                self._timed(timers, 'conv_res1', n, lambda: _capi.check(lib.dsen2_conv3x3(
-                    ptr(x_hi), ptr(wts[1 + 2 * l]), ptr(biases[1 + 2 * l]), n, P, P, F, F, 9, _capi.EPI_RELU, None,
-                    None, 0.0, ptr(t), None, None, None, 0, st), "dsen2_conv3x3(res conv1)"))
-                self._timed(timers, 'conv_res2', n, lambda: _capi.check(lib.dsen2_conv_resq256(
-                    ptr(t), ptr(wts[2 + 2 * l]), ptr(biases[2 + 2 * l]), n, P, P, 0.1, ptr(x_hi), ptr(xq), None, st),
-                    "dsen2_conv_resq256"))
-            return
+        # fp16 + 8 bit trunk: x_hi (NHWC, what the next convolution reads) updated in place + one byte per element
+        # (include/dsen2_b200.h, dsen2_conv_resq); the last block hands the last layer x_hi, x_lo
+        xq = buf['xq']
+        resq = lib.dsen2_conv_resq256 if F == 256 else lib.dsen2_conv_resq
+        self._timed(timers, 'conv_head', n, lambda: _capi.check(lib.dsen2_conv_head16_q(
+            ptr(buf['xin_hi']), ptr(buf['xin_lo']), ptr(wts[0]), ptr(biases[0]), n, P, P, F, ptr(x_hi), ptr(xq), st),
+            "dsen2_conv_head16_q"))
         for l in range(L):
             self._timed(timers, 'conv_res1', n, lambda: _capi.check(lib.dsen2_conv3x3(
                 ptr(x_hi), ptr(wts[1 + 2 * l]), ptr(biases[1 + 2 * l]), n, P, P, F, F, 9, _capi.EPI_RELU, None,
                 None, 0.0, ptr(t), None, None, None, 0, st), "dsen2_conv3x3(res conv1)"))
-            self._timed(timers, 'conv_res2', n, lambda: _capi.check(lib.dsen2_conv3x3(
-                ptr(t), ptr(wts[2 + 2 * l]), ptr(biases[2 + 2 * l]), n, P, P, F, F, 9, _capi.EPI_RESIDUAL,
-                ptr(x_hi), ptr(x_lo), 0.1, ptr(x_hi), ptr(x_lo), None, None, 0, st), "dsen2_conv3x3(res conv2)"))
+            self._timed(timers, 'conv_res2', n, lambda: _capi.check(resq(
+                ptr(t), ptr(wts[2 + 2 * l]), ptr(biases[2 + 2 * l]), n, P, P, 0.1, ptr(x_hi), ptr(xq),
+                ptr(x_lo) if l == L - 1 else None, st), "dsen2_conv_resq"))
+
+    def _tail_args(self, buf, wts, biases):
+        ptr = _capi.ptr
+        return (ptr(buf['x_hi']), ptr(buf['x_lo']), ptr(wts[-1]), ptr(biases[-1]), ptr(buf['xin_hi']), ptr(buf['xin_lo']),
+                sum(self.in_channels) - self.out_channels, self.out_channels)
 
     def forward_device(self, xs, out=None, timers=None):
         """xs: list of CUDA float32 (n, C_i, P, P) contiguous tensors -> CUDA float32 (n, Cout, P, P).
@@ -289,37 +238,26 @@ class S2Model:
             return out
         lib, ptr = _capi.lib(), _capi.ptr
         buf = self._buffers(dev, n, P)
-        F = self.feature_size
         with torch.cuda.device(dev):
             st = _capi.stream_ptr()
             x2, c2 = (xs[2], self.in_channels[2]) if len(xs) == 3 else (None, 0)
-            if self.fast_path:
-                prep = lib.dsen2_prep16_from_patches if self.xin16 else lib.dsen2_prep_from_patches
-                tail = lib.dsen2_conv_tail16 if self.xin16 else lib.dsen2_conv_tail
-                self._timed(timers, 'prep', n, lambda: _capi.check(prep(
-                    ptr(xs[0]), self.in_channels[0], ptr(xs[1]), self.in_channels[1], ptr(x2), c2, n, P,
-                    ptr(buf['xin_hi']), ptr(buf['xin_lo']), st), "dsen2_prep_from_patches"))
-                self._trunk(buf, wts, biases, n, P, st, timers)
-                self._timed(timers, 'conv_tail', n, lambda: _capi.check(tail(
-                    ptr(buf['x_hi']), ptr(buf['x_lo']), ptr(wts[-1]), ptr(biases[-1]), ptr(buf['xin_hi']),
-                    ptr(buf['xin_lo']), sum(self.in_channels) - self.out_channels, self.out_channels, n, P, P,
-                    ptr(out), st), "dsen2_conv_tail"))
+            prep = lib.dsen2_prep16_from_patches if self.xin16 else lib.dsen2_prep_from_patches
+            self._timed(timers, 'prep', n, lambda: _capi.check(prep(
+                ptr(xs[0]), self.in_channels[0], ptr(xs[1]), self.in_channels[1], ptr(x2), c2, n, P,
+                ptr(buf['xin_hi']), ptr(buf['xin_lo']), st), "dsen2_prep_from_patches"))
+            self._trunk(buf, wts, biases, n, P, st, timers)
+            if self.xin16:
+                self._timed(timers, 'conv_tail', n, lambda: _capi.check(lib.dsen2_conv_tail16(
+                    *self._tail_args(buf, wts, biases), self.feature_size, n, P, P, ptr(out), st), "dsen2_conv_tail16"))
             else:
-                self._timed(timers, 'pack_head', n, lambda: _capi.check(lib.dsen2_pack_head_input(
-                    ptr(xs[0]), self.in_channels[0], ptr(xs[1]), self.in_channels[1], ptr(x2), c2, n, P, buf['k_pad'],
-                    ptr(buf['a0']), None, st), "dsen2_pack_head_input"))
-                self._trunk(buf, wts, biases, n, P, st, timers)
-                self._timed(timers, 'conv_tail', n, lambda: _capi.check(lib.dsen2_conv3x3(
-                    ptr(buf['x_hi']), ptr(wts[-1]), ptr(biases[-1]), n, P, P, F, 16, 9, _capi.EPI_TAIL_NCHW, None, None,
-                    0.0, None, None, ptr(xs[-1]), ptr(out), self.out_channels, st), "dsen2_conv3x3(tail)"))
+                self._timed(timers, 'conv_tail', n, lambda: _capi.check(lib.dsen2_conv_tail(
+                    *self._tail_args(buf, wts, biases), n, P, P, ptr(out), st), "dsen2_conv_tail"))
         return out
 
     def forward_c(self, xs, out=None):
         """Same as ``forward_device`` through the single C entry point ``dsen2_s2model_forward`` (what a C caller of
         ``include/dsen2_b200.h`` uses): one call, workspace supplied by the caller."""
         torch = _capi.require_cuda()
-        if self.fast_path and self.num_layers > 0 and not self.xin16:
-            raise _capi.DSen2Error("dsen2_s2model_forward runs the fp16 + 8 bit trunk; unset DSEN2_TRUNK=fp32")
         n, _, P, _ = xs[0].shape
         dev = xs[0].device
         _wts, _biases, wp, bp = self._ensure_packed(dev)
@@ -338,12 +276,17 @@ class S2Model:
     def forward_images(self, d10, d20, d60, patch, border, first_patch, n, canvas, mul, timers=None):
         """Fused tile pipeline of the fast path: patches [first_patch, first_patch+n) are gathered straight
         from the HWC images (extract + bilinear + /mul), run through the network, and the pixels they own
-        are written x mul into ``canvas`` (H, W, Cout).  No patch stack or prediction stack exists."""
+        are written x mul into ``canvas`` (H, W, Cout).  No patch stack or prediction stack exists.  The images are
+        float32 or uint16 (digital numbers) HWC CUDA tensors."""
         torch = _capi.require_cuda()
-        if not self.fast_path:
-            raise _capi.DSen2Error("forward_images needs the 128-feature fast path")
+        if not self.xin16:
+            raise _capi.DSen2Error("forward_images needs a network with resblocks (num_layers > 0)")
         dev = d10.device
         H, W = int(d10.shape[0]), int(d10.shape[1])
+        imgs = [t for t in (d10, d20, d60) if t is not None]
+        if any(t.dtype != d10.dtype for t in imgs) or d10.dtype not in (torch.float32, torch.uint16):
+            raise ValueError("images must all be float32 or all be uint16")
+        img_dtype = _capi.IMG_U16 if d10.dtype == torch.uint16 else _capi.IMG_F32
         wts, biases, _wp, _bp = self._ensure_packed(dev)
         if n == 0:
             return canvas
@@ -351,21 +294,17 @@ class S2Model:
         buf = self._buffers(dev, n, patch)
         with torch.cuda.device(dev):
             st = _capi.stream_ptr()
-            prep = lib.dsen2_prep16_from_images if self.xin16 else lib.dsen2_prep_from_images
-            tail = lib.dsen2_conv_tail16_stitch if self.xin16 else lib.dsen2_conv_tail_stitch
-            self._timed(timers, 'prep', n, lambda: _capi.check(prep(
-                ptr(d10), ptr(d20), ptr(d60), H, W, patch, border, first_patch, n, float(mul), ptr(buf['xin_hi']),
-                ptr(buf['xin_lo']), st), "dsen2_prep_from_images"))
+            self._timed(timers, 'prep', n, lambda: _capi.check(lib.dsen2_prep16_from_images(
+                ptr(d10), ptr(d20), ptr(d60), img_dtype, H, W, patch, border, first_patch, n, float(mul),
+                ptr(buf['xin_hi']), ptr(buf['xin_lo']), st), "dsen2_prep16_from_images"))
             self._trunk(buf, wts, biases, n, patch, st, timers)
-            self._timed(timers, 'conv_tail', n, lambda: _capi.check(tail(
-                ptr(buf['x_hi']), ptr(buf['x_lo']), ptr(wts[-1]), ptr(biases[-1]), ptr(buf['xin_hi']),
-                ptr(buf['xin_lo']), sum(self.in_channels) - self.out_channels, self.out_channels, n, patch,
-                first_patch, border, H, W, float(mul), ptr(canvas), st), "dsen2_conv_tail_stitch"))
+            self._timed(timers, 'conv_tail', n, lambda: _capi.check(lib.dsen2_conv_tail16_stitch(
+                *self._tail_args(buf, wts, biases), self.feature_size, n, patch, first_patch, border, H, W, float(mul),
+                ptr(canvas), st), "dsen2_conv_tail16_stitch"))
         return canvas
 
     def launches_per_forward(self):
-        recode = int(not self.fast_path and self.feature_size == 256 and self.trunk_format != 'fp32' and self.num_layers > 0)
-        return 2 * self.num_layers + 3 + recode    # input preparation + head (+ trunk re-coding) + 2 per resblock + tail
+        return 2 * self.num_layers + 3             # input preparation + first layer + 2 per resblock + last layer
 
     def predict(self, x, batch_size=32, verbose=0, device_batch=None):
         """``model.predict([x10, x20(, x60)])`` -> (N, Cout, P, P) float32 numpy (supres.py:65).

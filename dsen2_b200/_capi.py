@@ -7,6 +7,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libdsen2_b200.so")
 
 EPI_RELU, EPI_RESIDUAL, EPI_TAIL_NCHW = 0, 1, 2
+IMG_F32, IMG_U16 = 0, 1
 
 # name -> (restype, argtypes); must list every symbol the header declares (checked by tests)
 SIGNATURES = {
@@ -39,28 +40,24 @@ SIGNATURES = {
                                 c_void_p, c_void_p]),
     "dsen2_conv_res32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                                  c_void_p, c_void_p]),
-    "dsen2_conv_head_q": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
-                                  c_void_p]),
     "dsen2_conv_resq": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                                 c_void_p, c_void_p]),
     "dsen2_prep16_from_patches": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p,
                                           c_void_p, c_void_p]),
-    "dsen2_prep16_from_images": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
+    "dsen2_prep16_from_images": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
                                          c_void_p, c_void_p, c_void_p]),
     "dsen2_pack_head16_weights": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "dsen2_conv_head16_q": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                     c_void_p]),
     "dsen2_conv_tail16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
-                                  c_int, c_void_p, c_void_p]),
+                                  c_int, c_int, c_void_p, c_void_p]),
     "dsen2_conv_tail16_stitch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
-                                         c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
+                                         c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "dsen2_conv_resq256": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                                    c_void_p, c_void_p]),
     "dsen2_trunk_hilo_to_q": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "dsen2_conv_tail": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                 c_int, c_void_p, c_void_p]),
-    "dsen2_conv_tail_stitch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
-                                       c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "dsen2_pack_dgrad_weights": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "dsen2_conv_relu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dsen2_planar_pitch": (c_longlong, [c_int, c_int, c_int]),
@@ -101,7 +98,7 @@ def lib():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)  # AttributeError if the symbol is not exported
             fn.restype, fn.argtypes = res, args
-        if handle.dsen2_abi_version() != 1:
+        if handle.dsen2_abi_version() != 2:
             raise DSen2Error("dsen2_b200: ABI version mismatch")
         _lib = handle
     return _lib

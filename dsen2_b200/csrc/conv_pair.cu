@@ -38,7 +38,14 @@ static constexpr int kBoxH = 18;
 static constexpr int kPrefetchTiles = 0;
 static constexpr int kTrunkPrefetchTiles = 1;   // same for the fp32 trunk lines the RESIDUAL32 epilogue reads
 
-enum { kEpiRelu = 0, kEpiResidual = 1, kEpiTail = 2, kEpiResidual32 = 3, kEpiMask = 4, kEpiResidualQ = 5, kEpiResidualQLast = 6 };
+enum { kEpiRelu = 0, kEpiResidual = 1, kEpiTail = 2, kEpiResidual32 = 3, kEpiMask = 4, kEpiResidualQ = 5, kEpiResidualQLast = 6,
+       kEpiHeadQ = 7 };
+// How a split-precision layer (operands v = hi + lo, fp16 each) lays out its products:
+//   kSplitStack  B = [W_hi ; W_lo] stacked along N, A = hi then lo k-blocks; the epilogue adds the two column halves
+//                (all four products; the tail, where N is tiny and the MMAs are bound by the A-operand reads)
+//   kSplit3      ONE accumulator of N = CH columns: hi*W_hi + hi*W_lo + lo*W_hi (lo*W_lo ~ 2^-22 of the result is dropped);
+//                three quarters of the MMAs and no accumulator-half sum in the epilogue (the first layer)
+enum { kSplitNone = 0, kSplitStack = 1, kSplit3 = 2 };
 
 struct PairParams {
   int n, H, W;
@@ -69,7 +76,7 @@ struct PairParams {
   int first_patch, img_h, img_w, border, grid_ny, grid_nx;
 };
 
-template <int NTOT_, bool SPLIT_, int NMAPS_, int KPM_, int NTAPS_, int KSTEPS_, int STAGES_, int EPI_, int WSTAGES_ = 0,
+template <int NTOT_, int SPLIT_, int NMAPS_, int KPM_, int NTAPS_, int KSTEPS_, int STAGES_, int EPI_, int WSTAGES_ = 0,
           int ROWB_ = 128>
 struct PairCfg {
   static constexpr int ROWB = ROWB_;            // bytes per pixel row of a k-block in smem = swizzle span (128: 64 ch, 32: 16 ch)
@@ -82,7 +89,9 @@ struct PairCfg {
   static constexpr int WSTAGES = WSTAGES_;      // 0: the layer's weights are resident in smem; > 0: ring of streamed slabs
   static constexpr bool RESIDENT = WSTAGES_ == 0;
   static constexpr int NTOT = NTOT_;            // UMMA N over the pair
-  static constexpr bool SPLIT = SPLIT_;         // B = [W_hi ; W_lo]: epilogue sums the two column halves
+  static constexpr bool SPLIT = SPLIT_ == kSplitStack;   // B = [W_hi ; W_lo]: epilogue sums the two column halves
+  static constexpr bool SPLIT3 = SPLIT_ == kSplit3;      // B slabs [tap][W_hi | W_lo], one accumulator (see kSplit3)
+  static_assert(SPLIT_ != kSplit3 || (NMAPS_ == 2 && WSTAGES_ == 0), "three-product split: hi and lo A tensors, resident weights");
   static constexpr int NMAPS = NMAPS_;          // A tensors (1, or 2 = hi then lo)
   static constexpr int KPM = KPM_;              // 64-channel k-blocks per A tensor
   static constexpr int KB = NMAPS_ * KPM_;      // pipeline stages consumed per tile
@@ -90,13 +99,14 @@ struct PairCfg {
   static constexpr int KSTEPS = KSTEPS_;        // K = 16 MMAs per tap and k-block
   static constexpr int STAGES = STAGES_;
   static constexpr int EPI = EPI_;
-  static constexpr int CH = SPLIT_ ? NTOT_ / 2 : NTOT_;   // output channels
+  static constexpr int CH = SPLIT ? NTOT_ / 2 : NTOT_;    // output channels
   static constexpr int BOXW = NTAPS_ == 9 ? 10 : 8;
   static constexpr int BOX_BYTES = kBoxH * BOXW * ROWB_;
   static constexpr int STAGE_BYTES = (BOX_BYTES + 1023) / 1024 * 1024;
   static constexpr int SLAB_ROWS = NTOT_ / 2;
   static constexpr int SLAB_BYTES = SLAB_ROWS * ROWB_;
-  static constexpr int NSLABS = NTAPS_ * KPM_;
+  static constexpr int WGROUPS = NTAPS_ * (SPLIT3 ? 2 : 1);   // slab groups of the weight tensor (its outermost dimension)
+  static constexpr int NSLABS = WGROUPS * KPM_;
   static constexpr int W_BYTES = (WSTAGES_ == 0 ? NSLABS : WSTAGES_) * SLAB_BYTES;
   static constexpr int TMEM_COLS = (2 * NTOT_ < 32) ? 32 : 2 * NTOT_;
   static constexpr int BAR_BYTES = 2048;        // barriers + tmem pointer (first 512 B) + bias
@@ -493,6 +503,19 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
             const int dy = Cfg::NTAPS == 9 ? tap / 3 : tap;
             const int dx = Cfg::NTAPS == 9 ? tap % 3 : 0;
             const uint32_t a0 = sa + (uint32_t)((dy * Cfg::BOXW + dx) * Cfg::ROWB);
+            if constexpr (Cfg::SPLIT3) {
+              // hi k-blocks meet W_hi and W_lo, lo k-blocks W_hi only; everything lands in the one accumulator
+              const int nb = kb < Cfg::KPM ? 2 : 1;
+              for (int hl = 0; hl < nb; ++hl) {
+                const uint32_t b3 = sb + (uint32_t)((tap * 2 + hl) * Cfg::KPM * Cfg::SLAB_BYTES);
+#pragma unroll
+                for (int k = 0; k < Cfg::KSTEPS; ++k)
+                  umma_f16_ss_pair(d_tmem, umma_desc_k_sbo<Cfg::ROWB>(a0 + k * 32, Cfg::BOXW * Cfg::ROWB),
+                                   umma_desc_k_sbo<Cfg::ROWB>(b3 + k * 32, 8 * Cfg::ROWB), idesc,
+                                   (uint32_t)((kb | tap | hl | k) != 0));
+              }
+              continue;
+            }
             uint32_t b0 = sb + (uint32_t)(tap * Cfg::KPM * Cfg::SLAB_BYTES);
             if constexpr (!Cfg::RESIDENT) {
               mbar_wait(&wr_full[ws], wphase);
@@ -693,6 +716,52 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
                                    sc == CPT / 64 - 1 ? &tmem_empty[acc] : nullptr);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         continue;
+      } else if constexpr (Cfg::EPI == kEpiHeadQ) {
+        // ------------------------------------------------------------------ first layer: seeds the fp16 + 8 bit trunk
+        // x = relu(conv + bias) (DSen2Net.py:29) -> x_hi (NHWC fp16, staged store) + one byte per element (see q_encode4)
+        constexpr int CPT = Cfg::CH / 2;
+        static_assert(CPT % 64 == 0 && !Cfg::SPLIT, "Q-trunk head: 64 channels per thread and pass, one accumulator");
+        const uint32_t stg = smem_u32(s_stg) + (uint32_t)(warp * 1024);
+#pragma unroll 1
+        for (int sc = 0; sc < CPT / 64; ++sc) {
+          const int cb = half * CPT + sc * 64;
+          const EpiGeom g = epi_geom<Cfg>(p, tc, wq, cb);
+          uint4 vh[8], lq[4];
+          if (sc == 0) {
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+          }
+#pragma unroll
+          for (int chunk = 0; chunk < 2; ++chunk) {
+            const int c0 = cb + chunk * 32;
+            uint32_t r[32];
+            tmem_ld_32x32(taddr + c0, r);
+            tmem_ld_wait();
+            uint32_t* hw = reinterpret_cast<uint32_t*>(vh) + chunk * 16;
+            uint32_t* qw = reinterpret_cast<uint32_t*>(lq) + chunk * 8;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bq = lds_f4(s_bias_addr + (uint32_t)(c0 + j) * 4);   // broadcast LDS.128
+              q_encode4(fmaxf(__uint_as_float(r[j]) + bq.x, 0.f), fmaxf(__uint_as_float(r[j + 1]) + bq.y, 0.f),
+                        fmaxf(__uint_as_float(r[j + 2]) + bq.z, 0.f), fmaxf(__uint_as_float(r[j + 3]) + bq.w, 0.f),
+                        hw[j >> 1], hw[(j >> 1) + 1], qw[j >> 2]);
+            }
+          }
+          if (sc == CPT / 64 - 1) {   // the accumulator has been read: hand the TMEM buffer back before the stores
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+          }
+          if (valid) {
+            uint8_t* const qp = p.xq + ((((long long)b * p.H + y) * p.tiles_x + tc.tx) * (Cfg::CH / 16) + cb / 16) * 128 +
+                                (row & 7) * 16;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(qp + q * 128) = lq[q];
+          }
+          staged_store(stg, vh, p.out_hi, g, lane);
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
       } else {
         // ------------------------------------------------------------------ trunk layers
         // Each thread owns one pixel and CPT = CH/2 channels, processed as CPT/64 "super-chunks" of 64 channels
@@ -751,18 +820,6 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
             for (int j = 0; j < 32; j += 4) {
               const float4 bq = lds_f4(s_bias_addr + (uint32_t)(c0 + j) * 4);   // broadcast LDS.128
               const float bb[4] = {bq.x, bq.y, bq.z, bq.w};
-              if constexpr (Cfg::EPI == kEpiRelu && Cfg::SPLIT) {
-                if (p.xq != nullptr) {                     // head: seed the fp16 + 8 bit trunk (x_hi + low bytes)
-                  uint32_t* qw = reinterpret_cast<uint32_t*>(vl);      // vl is free: the Q-trunk head has no x_lo output
-                  q_encode4(fmaxf(__uint_as_float(r[j]) + bq.x, 0.f), fmaxf(__uint_as_float(r[j + 1]) + bq.y, 0.f),
-                            fmaxf(__uint_as_float(r[j + 2]) + bq.z, 0.f), fmaxf(__uint_as_float(r[j + 3]) + bq.w, 0.f),
-                            hw[j >> 1], hw[(j >> 1) + 1], qw[(j >> 2) & 3]);
-                  if ((j & 12) == 12 && valid)
-                    *reinterpret_cast<uint4*>(p.xq + ((((long long)b * p.H + y) * p.tiles_x + tc.tx) * (Cfg::CH / 16) +
-                                                      ((c0 + j) >> 4)) * 128 + (row & 7) * 16) = vl[0];
-                  continue;
-                }
-              }
               if (Cfg::EPI == kEpiRelu && p.x32 != nullptr && valid) {   // first layer: seed the fp32 trunk (tile-row-major)
                 const float4 xv = make_float4(fmaxf(__uint_as_float(r[j]) + bq.x, 0.f), fmaxf(__uint_as_float(r[j + 1]) + bq.y, 0.f),
                                               fmaxf(__uint_as_float(r[j + 2]) + bq.z, 0.f), fmaxf(__uint_as_float(r[j + 3]) + bq.w, 0.f));
@@ -828,21 +885,24 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
 // ------------------------------------------------------------------------------------------ //
 // host side
 // ------------------------------------------------------------------------------------------ //
-using CfgRelu = PairCfg<128, false, 1, 2, 9, 4, 3, kEpiRelu>;
-using CfgResidual = PairCfg<128, false, 1, 2, 9, 4, 3, kEpiResidual>;
-using CfgResidual32 = PairCfg<128, false, 1, 2, 9, 4, 3, kEpiResidual32>;
-using CfgMask = PairCfg<128, false, 1, 2, 9, 4, 3, kEpiMask>;
-using CfgResidualQ = PairCfg<128, false, 1, 2, 9, 4, 3, kEpiResidualQ>;
-using CfgResidualQLast = PairCfg<128, false, 1, 2, 9, 4, 3, kEpiResidualQLast>;
+using CfgRelu = PairCfg<128, kSplitNone, 1, 2, 9, 4, 3, kEpiRelu>;
+using CfgResidual = PairCfg<128, kSplitNone, 1, 2, 9, 4, 3, kEpiResidual>;
+using CfgResidual32 = PairCfg<128, kSplitNone, 1, 2, 9, 4, 3, kEpiResidual32>;
+using CfgMask = PairCfg<128, kSplitNone, 1, 2, 9, 4, 3, kEpiMask>;
+using CfgResidualQ = PairCfg<128, kSplitNone, 1, 2, 9, 4, 3, kEpiResidualQ>;
+using CfgResidualQLast = PairCfg<128, kSplitNone, 1, 2, 9, 4, 3, kEpiResidualQLast>;
 // VDSen2 trunk (256 -> 256): 1.18 MB of weights per layer cannot be resident -- ring of 8 streamed [tap][k-block] slabs
-using CfgRelu256 = PairCfg<256, false, 1, 4, 9, 4, 3, kEpiRelu, 8>;
-using CfgResidual256 = PairCfg<256, false, 1, 4, 9, 4, 3, kEpiResidual, 8>;
-using CfgResidualQ256 = PairCfg<256, false, 1, 4, 9, 4, 3, kEpiResidualQ, 8>;
-using CfgResidualQLast256 = PairCfg<256, false, 1, 4, 9, 4, 3, kEpiResidualQLast, 8>;
-using CfgHead = PairCfg<256, true, 2, 1, 3, 3, 6, kEpiRelu>;
-// first layer on the un-gathered 16-channel input: nine taps through shifted descriptors into a 32-byte-row halo box
-using CfgHead16 = PairCfg<256, true, 2, 1, 9, 1, 6, kEpiRelu, 0, 32>;
-using CfgTail = PairCfg<32, true, 2, 2, 9, 4, 6, kEpiTail>;
+using CfgRelu256 = PairCfg<256, kSplitNone, 1, 4, 9, 4, 3, kEpiRelu, 8>;
+using CfgResidual256 = PairCfg<256, kSplitNone, 1, 4, 9, 4, 3, kEpiResidual, 8>;
+using CfgResidualQ256 = PairCfg<256, kSplitNone, 1, 4, 9, 4, 3, kEpiResidualQ, 8>;
+using CfgResidualQLast256 = PairCfg<256, kSplitNone, 1, 4, 9, 4, 3, kEpiResidualQLast, 8>;
+using CfgHead = PairCfg<256, kSplitStack, 2, 1, 3, 3, 6, kEpiRelu>;
+// first layer on the un-gathered 16-channel input: nine taps through shifted descriptors into a 32-byte-row halo box,
+// three products per tap into one accumulator (27 MMAs of N = F per tile pair)
+using CfgHead16 = PairCfg<128, kSplit3, 2, 1, 9, 1, 6, kEpiHeadQ, 0, 32>;
+using CfgHead16_256 = PairCfg<256, kSplit3, 2, 1, 9, 1, 6, kEpiHeadQ, 0, 32>;
+using CfgTail = PairCfg<32, kSplitStack, 2, 2, 9, 4, 6, kEpiTail>;
+using CfgTail256 = PairCfg<32, kSplitStack, 2, 4, 9, 4, 6, kEpiTail>;   // 256 -> cout: 8 k-blocks per tile, 72 KB of weights
 
 template <class Cfg>
 static int launch_pair(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const PairParams& p,
@@ -869,7 +929,7 @@ static int make_maps(CUtensorMap* a0, CUtensorMap* a1, CUtensorMap* w, const voi
   if (rc) return rc;
   rc = make_tmap_f16_sw(a1, d_a1 ? d_a1 : d_a0, 4, dims, box, Cfg::ROWB);
   if (rc) return rc;
-  const uint64_t wd[3] = {(uint64_t)ca, (uint64_t)Cfg::NTOT, (uint64_t)Cfg::NTAPS};
+  const uint64_t wd[3] = {(uint64_t)ca, (uint64_t)Cfg::NTOT, (uint64_t)Cfg::WGROUPS};
   const uint32_t wb[3] = {(uint32_t)Cfg::KCH, (uint32_t)Cfg::SLAB_ROWS, 1};
   return make_tmap_f16_sw(w, d_w, 3, wd, wb, Cfg::ROWB);
 }
@@ -966,13 +1026,11 @@ extern "C" int dsen2_conv_res32(const void* d_in, const void* d_w, const float* 
 
 template <class CfgH>
 static int head_common(const char* name, const void* d_xin_hi, const void* d_xin_lo, const void* d_w, const float* d_bias,
-                       int n, int H, int W, int feature_size, void* d_out_hi, void* d_out_lo, float* d_trunk32,
-                       void* d_trunk_lo8, void* stream) {
+                       int n, int H, int W, void* d_out_hi, void* d_out_lo, float* d_trunk32, void* d_trunk_lo8,
+                       void* stream) {
   DSEN2_REQUIRE(d_xin_hi && d_xin_lo && d_w && d_bias && d_out_hi, DSEN2_E_BADARG, "%s: null pointer", name);
   DSEN2_REQUIRE(((uintptr_t)d_trunk32 % 16) == 0 && ((uintptr_t)d_trunk_lo8 % 16) == 0, DSEN2_E_ALIGN,
                 "%s: trunk must be 16-byte aligned", name);
-  DSEN2_REQUIRE(feature_size == 128, DSEN2_E_BADARG, "%s: the pair kernel serves feature_size 128 (got %d)", name,
-                feature_size);
   DSEN2_REQUIRE(n >= 0 && H > 0 && W > 0, DSEN2_E_BADARG, "%s: bad shape", name);
   DSEN2_REQUIRE(((uintptr_t)d_xin_hi % 16) == 0 && ((uintptr_t)d_xin_lo % 16) == 0 && ((uintptr_t)d_w % 16) == 0 &&
                     ((uintptr_t)d_out_hi % 16) == 0 && ((uintptr_t)d_out_lo % 16) == 0,
@@ -990,28 +1048,27 @@ static int head_common(const char* name, const void* d_xin_hi, const void* d_xin
   CUtensorMap a0, a1, w;
   rc = make_maps<CfgH>(&a0, &a1, &w, d_xin_hi, d_xin_lo, d_w, n, H, W);
   if (rc) return rc;
-  return launch_pair<CfgH>(a0, a1, w, p, sms, (cudaStream_t)stream, "conv_pair<head>");
+  return launch_pair<CfgH>(a0, a1, w, p, sms, (cudaStream_t)stream, name);
 }
 
 extern "C" int dsen2_conv_head(const void* d_xin_hi, const void* d_xin_lo, const void* d_w, const float* d_bias,
                                int n, int H, int W, int feature_size, void* d_out_hi, void* d_out_lo,
                                float* d_trunk32, void* stream) {
-  return head_common<CfgHead>("dsen2_conv_head", d_xin_hi, d_xin_lo, d_w, d_bias, n, H, W, feature_size, d_out_hi, d_out_lo,
-                     d_trunk32, nullptr, stream);
-}
-
-extern "C" int dsen2_conv_head_q(const void* d_xin_hi, const void* d_xin_lo, const void* d_w, const float* d_bias,
-                                 int n, int H, int W, int feature_size, void* d_x_hi, void* d_trunk_lo8, void* stream) {
-  DSEN2_REQUIRE(d_trunk_lo8, DSEN2_E_BADARG, "dsen2_conv_head_q: null pointer");
-  return head_common<CfgHead>("dsen2_conv_head_q", d_xin_hi, d_xin_lo, d_w, d_bias, n, H, W, feature_size, d_x_hi, nullptr,
-                              nullptr, d_trunk_lo8, stream);
+  DSEN2_REQUIRE(feature_size == 128, DSEN2_E_BADARG, "dsen2_conv_head: feature_size 128 only (got %d)", feature_size);
+  return head_common<CfgHead>("dsen2_conv_head", d_xin_hi, d_xin_lo, d_w, d_bias, n, H, W, d_out_hi, d_out_lo, d_trunk32,
+                              nullptr, stream);
 }
 
 extern "C" int dsen2_conv_head16_q(const void* d_xin_hi, const void* d_xin_lo, const void* d_w, const float* d_bias,
                                    int n, int H, int W, int feature_size, void* d_x_hi, void* d_trunk_lo8, void* stream) {
   DSEN2_REQUIRE(d_trunk_lo8, DSEN2_E_BADARG, "dsen2_conv_head16_q: null pointer");
-  return head_common<CfgHead16>("dsen2_conv_head16_q", d_xin_hi, d_xin_lo, d_w, d_bias, n, H, W, feature_size, d_x_hi,
-                                nullptr, nullptr, d_trunk_lo8, stream);
+  DSEN2_REQUIRE(feature_size == 128 || feature_size == 256, DSEN2_E_BADARG,
+                "dsen2_conv_head16_q: feature_size must be 128 or 256 (got %d)", feature_size);
+  if (feature_size == 256)
+    return head_common<CfgHead16_256>("dsen2_conv_head16_q", d_xin_hi, d_xin_lo, d_w, d_bias, n, H, W, d_x_hi, nullptr,
+                                      nullptr, d_trunk_lo8, stream);
+  return head_common<CfgHead16>("dsen2_conv_head16_q", d_xin_hi, d_xin_lo, d_w, d_bias, n, H, W, d_x_hi, nullptr, nullptr,
+                                d_trunk_lo8, stream);
 }
 
 static int resq_common(int features, const void* d_in, const void* d_w, const float* d_bias, int n, int H, int W,
@@ -1104,11 +1161,13 @@ extern "C" int dsen2_trunk_hilo_to_q(void* d_x_hi, const void* d_x_lo, void* d_t
   return check_launch("trunk_hilo_to_q");
 }
 
-static int tail_common(PairParams& p, bool xin16, const void* d_x_hi, const void* d_x_lo, const void* d_w,
+static int tail_common(PairParams& p, bool xin16, int features, const void* d_x_hi, const void* d_x_lo, const void* d_w,
                        const float* d_bias, const void* d_xin_hi, const void* d_xin_lo, int skip_ch0, int cout, int n, int H,
                        int W, float* d_out, void* stream) {
   DSEN2_REQUIRE(d_x_hi && d_x_lo && d_w && d_bias && d_xin_hi && d_xin_lo && d_out, DSEN2_E_BADARG,
                 "dsen2_conv_tail: null pointer");
+  DSEN2_REQUIRE(features == 128 || features == 256, DSEN2_E_BADARG, "dsen2_conv_tail: feature_size must be 128 or 256 (got %d)",
+                features);
   DSEN2_REQUIRE(n >= 0 && H > 0 && W > 0 && cout > 0 && cout <= 16 && skip_ch0 >= 0 && skip_ch0 + cout <= 16,
                 DSEN2_E_BADARG, "dsen2_conv_tail: bad shape (cout %d, skip_ch0 %d)", cout, skip_ch0);
   DSEN2_REQUIRE(((uintptr_t)d_x_hi % 16) == 0 && ((uintptr_t)d_x_lo % 16) == 0 && ((uintptr_t)d_w % 16) == 0,
@@ -1130,62 +1189,51 @@ static int tail_common(PairParams& p, bool xin16, const void* d_x_hi, const void
   p.skip_pitch = xin16 ? 16 : 64; p.skip_off = xin16 ? 0 : 16;
   p.cout_real = cout; p.out_f32 = d_out;
   CUtensorMap a0, a1, w;
+  if (features == 256) {
+    rc = make_maps<CfgTail256>(&a0, &a1, &w, d_x_hi, d_x_lo, d_w, n, H, W);
+    if (rc) return rc;
+    return launch_pair<CfgTail256>(a0, a1, w, p, sms, (cudaStream_t)stream, "conv_pair<tail,256>");
+  }
   rc = make_maps<CfgTail>(&a0, &a1, &w, d_x_hi, d_x_lo, d_w, n, H, W);
   if (rc) return rc;
   return launch_pair<CfgTail>(a0, a1, w, p, sms, (cudaStream_t)stream, "conv_pair<tail>");
 }
 
-static int tail_nchw(bool xin16, const void* d_x_hi, const void* d_x_lo, const void* d_w, const float* d_bias,
-                     const void* d_xin_hi, const void* d_xin_lo, int skip_ch0, int cout, int n, int H, int W,
-                     float* d_pred_nchw, void* stream) {
-  PairParams p{};
-  p.tail_mode = 0;
-  p.out_mul = 1.0f;
-  return tail_common(p, xin16, d_x_hi, d_x_lo, d_w, d_bias, d_xin_hi, d_xin_lo, skip_ch0, cout, n, H, W, d_pred_nchw,
-                     stream);
-}
-
 extern "C" int dsen2_conv_tail(const void* d_x_hi, const void* d_x_lo, const void* d_w, const float* d_bias,
                                const void* d_xin_hi, const void* d_xin_lo, int skip_ch0, int cout, int n, int H, int W,
                                float* d_pred_nchw, void* stream) {
-  return tail_nchw(false, d_x_hi, d_x_lo, d_w, d_bias, d_xin_hi, d_xin_lo, skip_ch0, cout, n, H, W, d_pred_nchw, stream);
+  PairParams p{};
+  p.tail_mode = 0;
+  p.out_mul = 1.0f;
+  return tail_common(p, false, 128, d_x_hi, d_x_lo, d_w, d_bias, d_xin_hi, d_xin_lo, skip_ch0, cout, n, H, W, d_pred_nchw,
+                     stream);
 }
 
 extern "C" int dsen2_conv_tail16(const void* d_x_hi, const void* d_x_lo, const void* d_w, const float* d_bias,
-                                 const void* d_xin_hi, const void* d_xin_lo, int skip_ch0, int cout, int n, int H, int W,
-                                 float* d_pred_nchw, void* stream) {
-  return tail_nchw(true, d_x_hi, d_x_lo, d_w, d_bias, d_xin_hi, d_xin_lo, skip_ch0, cout, n, H, W, d_pred_nchw, stream);
+                                 const void* d_xin_hi, const void* d_xin_lo, int skip_ch0, int cout, int feature_size, int n,
+                                 int H, int W, float* d_pred_nchw, void* stream) {
+  PairParams p{};
+  p.tail_mode = 0;
+  p.out_mul = 1.0f;
+  return tail_common(p, true, feature_size, d_x_hi, d_x_lo, d_w, d_bias, d_xin_hi, d_xin_lo, skip_ch0, cout, n, H, W,
+                     d_pred_nchw, stream);
 }
 
-static int tail_stitch(bool xin16, const void* d_x_hi, const void* d_x_lo, const void* d_w, const float* d_bias,
-                       const void* d_xin_hi, const void* d_xin_lo, int skip_ch0, int cout, int n, int P, int first_patch,
-                       int border, int img_h, int img_w, float mul, float* d_canvas, void* stream) {
+extern "C" int dsen2_conv_tail16_stitch(const void* d_x_hi, const void* d_x_lo, const void* d_w, const float* d_bias,
+                                        const void* d_xin_hi, const void* d_xin_lo, int skip_ch0, int cout, int feature_size,
+                                        int n, int P, int first_patch, int border, int img_h, int img_w, float mul,
+                                        float* d_canvas, void* stream) {
   const int S = P - 2 * border;
   DSEN2_REQUIRE(P > 0 && border >= 0 && S > 0 && img_h >= S && img_w >= S && first_patch >= 0, DSEN2_E_BADARG,
-                "dsen2_conv_tail_stitch: bad stitch geometry (P %d border %d image %dx%d)", P, border, img_h, img_w);
+                "dsen2_conv_tail16_stitch: bad stitch geometry (P %d border %d image %dx%d)", P, border, img_h, img_w);
   PairParams p{};
   p.tail_mode = 1;
   p.out_mul = mul;
   p.first_patch = first_patch; p.img_h = img_h; p.img_w = img_w; p.border = border;
   p.grid_ny = ceil_div(img_h, S); p.grid_nx = ceil_div(img_w, S);
   DSEN2_REQUIRE(first_patch + n <= p.grid_ny * p.grid_nx, DSEN2_E_BADARG,
-                "dsen2_conv_tail_stitch: patch range [%d,%d) exceeds the %d tiles of the canvas", first_patch,
+                "dsen2_conv_tail16_stitch: patch range [%d,%d) exceeds the %d tiles of the canvas", first_patch,
                 first_patch + n, p.grid_ny * p.grid_nx);
-  return tail_common(p, xin16, d_x_hi, d_x_lo, d_w, d_bias, d_xin_hi, d_xin_lo, skip_ch0, cout, n, P, P, d_canvas, stream);
-}
-
-extern "C" int dsen2_conv_tail_stitch(const void* d_x_hi, const void* d_x_lo, const void* d_w, const float* d_bias,
-                                      const void* d_xin_hi, const void* d_xin_lo, int skip_ch0, int cout, int n, int P,
-                                      int first_patch, int border, int img_h, int img_w, float mul, float* d_canvas,
-                                      void* stream) {
-  return tail_stitch(false, d_x_hi, d_x_lo, d_w, d_bias, d_xin_hi, d_xin_lo, skip_ch0, cout, n, P, first_patch, border,
-                     img_h, img_w, mul, d_canvas, stream);
-}
-
-extern "C" int dsen2_conv_tail16_stitch(const void* d_x_hi, const void* d_x_lo, const void* d_w, const float* d_bias,
-                                        const void* d_xin_hi, const void* d_xin_lo, int skip_ch0, int cout, int n, int P,
-                                        int first_patch, int border, int img_h, int img_w, float mul, float* d_canvas,
-                                        void* stream) {
-  return tail_stitch(true, d_x_hi, d_x_lo, d_w, d_bias, d_xin_hi, d_xin_lo, skip_ch0, cout, n, P, first_patch, border,
-                     img_h, img_w, mul, d_canvas, stream);
+  return tail_common(p, true, feature_size, d_x_hi, d_x_lo, d_w, d_bias, d_xin_hi, d_xin_lo, skip_ch0, cout, n, P, P,
+                     d_canvas, stream);
 }

@@ -412,12 +412,9 @@ static int head_k_pad(int in_channels) { return (9 * in_channels + 63) / 64 * 64
 extern "C" size_t dsen2_s2model_workspace_bytes(int n, int P, int in_channels, int feature_size) {
   if (n <= 0 || P <= 0 || in_channels <= 0 || feature_size <= 0) return 0;
   const size_t pix = (size_t)n * P * P;
-  if (feature_size == 128)   // x_in hi/lo (64 ch; 16 are used when there are resblocks) + trunk hi/lo + resblock
-                             // intermediate + low bytes of the fp16+8 trunk
-    return 2 * align_up(pix * 64 * 2, 1024) + 3 * align_up(pix * feature_size * 2, 1024) +
-           align_up((size_t)n * P * ((P + 7) / 8 * 8) * feature_size, 1024) + 1024;
-  // im2col'd input + trunk hi/lo + resblock intermediate + low bytes of the fp16+8 trunk
-  return align_up(pix * head_k_pad(in_channels) * 2, 1024) + 3 * align_up(pix * feature_size * 2, 1024) +
+  // x_in hi/lo (64 ch; 16 are used when there are resblocks) + trunk hi/lo + resblock intermediate + low bytes of the
+  // fp16 + 8 bit trunk
+  return 2 * align_up(pix * 64 * 2, 1024) + 3 * align_up(pix * feature_size * 2, 1024) +
          align_up((size_t)n * P * ((P + 7) / 8 * 8) * feature_size, 1024) + 1024;
 }
 
@@ -430,6 +427,8 @@ extern "C" int dsen2_s2model_forward(const float* const* d_x, const int* channel
   DSEN2_REQUIRE(n_inputs == 2 || n_inputs == 3, DSEN2_E_BADARG, "dsen2_s2model_forward: s2model takes 2 or 3 inputs");
   DSEN2_REQUIRE(n >= 0 && P > 0 && num_layers >= 0 && (feature_size == 128 || feature_size == 256), DSEN2_E_BADARG,
                 "dsen2_s2model_forward: bad sizes (n %d, P %d, layers %d, features %d)", n, P, num_layers, feature_size);
+  DSEN2_REQUIRE(num_layers > 0 || feature_size == 128, DSEN2_E_BADARG,
+                "dsen2_s2model_forward: a network without resblocks is only served for feature_size 128");
   if (n == 0) return 0;
   int ctot = 0;
   for (int i = 0; i < n_inputs; ++i) {
@@ -437,83 +436,52 @@ extern "C" int dsen2_s2model_forward(const float* const* d_x, const int* channel
     ctot += channels[i];
   }
   const int cout_real = channels[n_inputs - 1];   // DSen2Net.py:35
-  DSEN2_REQUIRE(cout_real <= 16, DSEN2_E_BADARG, "dsen2_s2model_forward: at most 16 output bands");
+  DSEN2_REQUIRE(cout_real <= 16 && ctot <= 16, DSEN2_E_BADARG, "dsen2_s2model_forward: at most 16 input / output bands");
   DSEN2_REQUIRE(workspace_bytes >= dsen2_s2model_workspace_bytes(n, P, ctot, feature_size), DSEN2_E_BADARG,
                 "dsen2_s2model_forward: workspace too small");
   const size_t pix = (size_t)n * P * P;
+  const int F = feature_size;
   uint8_t* ws = reinterpret_cast<uint8_t*>(align_up((size_t)(uintptr_t)d_workspace, 1024));
   int rc;
 
-  if (feature_size == 128) {
-    // DSen2: prepared input -> split-precision head -> CTA-pair trunk -> split-precision tail + global skip
-    DSEN2_REQUIRE(ctot <= 16, DSEN2_E_BADARG, "dsen2_s2model_forward: at most 16 input bands");
-    void* xin_hi = ws;
-    ws += align_up(pix * 64 * 2, 1024);
-    void* xin_lo = ws;
-    ws += align_up(pix * 64 * 2, 1024);
-    void* x_hi = ws;
-    ws += align_up(pix * 128 * 2, 1024);
-    void* x_lo = ws;
-    ws += align_up(pix * 128 * 2, 1024);
-    void* t = ws;
-    ws += align_up(pix * 128 * 2, 1024);
-    void* xq = ws;               // low bytes of the fp16 + 8 bit trunk, tile-row-major (dsen2_conv_resq)
-    // with resblocks: un-gathered 16-channel input, nine-tap first layer (head weights from dsen2_pack_head16_weights);
-    // without: the 64-channel form (dsen2_pack_head_weights)
-    const bool xin16 = num_layers > 0;
-    rc = xin16 ? dsen2_prep16_from_patches(d_x[0], channels[0], d_x[1], channels[1], n_inputs == 3 ? d_x[2] : nullptr,
-                                           n_inputs == 3 ? channels[2] : 0, n, P, xin_hi, xin_lo, stream)
-               : dsen2_prep_from_patches(d_x[0], channels[0], d_x[1], channels[1], n_inputs == 3 ? d_x[2] : nullptr,
-                                         n_inputs == 3 ? channels[2] : 0, n, P, xin_hi, xin_lo, stream);
-    if (rc) return rc;
-    // the fp16 x_lo is only needed by the tail: the last trunk-producing layer writes it
-    if (num_layers == 0)
-      rc = dsen2_conv_head(xin_hi, xin_lo, d_weights[0], d_bias[0], n, P, P, 128, x_hi, x_lo, nullptr, stream);
-    else
-      rc = dsen2_conv_head16_q(xin_hi, xin_lo, d_weights[0], d_bias[0], n, P, P, 128, x_hi, xq, stream);
-    if (rc) return rc;
-    for (int l = 0; l < num_layers; ++l) {
-      rc = dsen2_conv3x3(x_hi, d_weights[1 + 2 * l], d_bias[1 + 2 * l], n, P, P, 128, 128, 9, DSEN2_EPI_RELU, nullptr,
-                         nullptr, 0.f, t, nullptr, nullptr, nullptr, 0, stream);
-      if (rc) return rc;
-      rc = dsen2_conv_resq(t, d_weights[2 + 2 * l], d_bias[2 + 2 * l], n, P, P, 0.1f, x_hi, xq,
-                           l == num_layers - 1 ? x_lo : nullptr, stream);
-      if (rc) return rc;
-    }
-    return (xin16 ? dsen2_conv_tail16 : dsen2_conv_tail)(x_hi, x_lo, d_weights[2 * num_layers + 1],
-                                                         d_bias[2 * num_layers + 1], xin_hi, xin_lo, ctot - cout_real,
-                                                         cout_real, n, P, P, d_out_f32, stream);
-  }
-
-  const int k_pad = head_k_pad(ctot);
-  void* a0 = ws;
-  ws += align_up(pix * k_pad * 2, 1024);
+  // prepared input -> split-precision first layer -> CTA-pair trunk (fp16 + 8 bit) -> split-precision last layer + global skip
+  void* xin_hi = ws;
+  ws += align_up(pix * 64 * 2, 1024);
+  void* xin_lo = ws;
+  ws += align_up(pix * 64 * 2, 1024);
   void* x_hi = ws;
-  ws += align_up(pix * feature_size * 2, 1024);
+  ws += align_up(pix * F * 2, 1024);
   void* x_lo = ws;
-  ws += align_up(pix * feature_size * 2, 1024);
+  ws += align_up(pix * F * 2, 1024);
   void* t = ws;
-  ws += align_up(pix * feature_size * 2, 1024);
-  void* xq = ws;               // low bytes of the fp16 + 8 bit trunk (dsen2_conv_resq256)
-
-  rc = dsen2_pack_head_input(d_x[0], channels[0], d_x[1], channels[1], n_inputs == 3 ? d_x[2] : nullptr,
-                             n_inputs == 3 ? channels[2] : 0, n, P, k_pad, a0, nullptr, stream);
-  if (rc) return rc;
-  rc = dsen2_conv3x3(a0, d_weights[0], d_bias[0], n, P, P, k_pad, feature_size, 1, DSEN2_EPI_RELU, nullptr, nullptr,
-                     0.f, x_hi, x_lo, nullptr, nullptr, 0, stream);
-  if (rc) return rc;
-  if (num_layers > 0) {        // the single-CTA first layer writes hi + lo: re-code as x_hi + one byte per element
-    rc = dsen2_trunk_hilo_to_q(x_hi, x_lo, xq, n, P, P, feature_size, stream);
+  ws += align_up(pix * F * 2, 1024);
+  void* xq = ws;               // low bytes of the fp16 + 8 bit trunk, tile-row-major (dsen2_conv_resq)
+  const float* x2 = n_inputs == 3 ? d_x[2] : nullptr;
+  const int c2 = n_inputs == 3 ? channels[2] : 0;
+  if (num_layers == 0) {
+    // no resblocks: the 64-channel form (three horizontal taps pre-gathered, dsen2_pack_head_weights), whose first layer
+    // writes the x_hi + x_lo pair the last layer reads
+    rc = dsen2_prep_from_patches(d_x[0], channels[0], d_x[1], channels[1], x2, c2, n, P, xin_hi, xin_lo, stream);
     if (rc) return rc;
+    rc = dsen2_conv_head(xin_hi, xin_lo, d_weights[0], d_bias[0], n, P, P, 128, x_hi, x_lo, nullptr, stream);
+    if (rc) return rc;
+    return dsen2_conv_tail(x_hi, x_lo, d_weights[1], d_bias[1], xin_hi, xin_lo, ctot - cout_real, cout_real, n, P, P,
+                           d_out_f32, stream);
   }
+  // un-gathered 16-channel input, nine-tap first layer (weights from dsen2_pack_head16_weights)
+  rc = dsen2_prep16_from_patches(d_x[0], channels[0], d_x[1], channels[1], x2, c2, n, P, xin_hi, xin_lo, stream);
+  if (rc) return rc;
+  rc = dsen2_conv_head16_q(xin_hi, xin_lo, d_weights[0], d_bias[0], n, P, P, F, x_hi, xq, stream);
+  if (rc) return rc;
   for (int l = 0; l < num_layers; ++l) {
-    rc = dsen2_conv3x3(x_hi, d_weights[1 + 2 * l], d_bias[1 + 2 * l], n, P, P, feature_size, feature_size, 9,
-                       DSEN2_EPI_RELU, nullptr, nullptr, 0.f, t, nullptr, nullptr, nullptr, 0, stream);
+    rc = dsen2_conv3x3(x_hi, d_weights[1 + 2 * l], d_bias[1 + 2 * l], n, P, P, F, F, 9, DSEN2_EPI_RELU, nullptr, nullptr,
+                       0.f, t, nullptr, nullptr, nullptr, 0, stream);
     if (rc) return rc;
-    rc = dsen2_conv_resq256(t, d_weights[2 + 2 * l], d_bias[2 + 2 * l], n, P, P, 0.1f, x_hi, xq, nullptr, stream);
+    // the fp16 x_lo is only needed by the last layer: the last resblock writes it
+    rc = (F == 256 ? dsen2_conv_resq256 : dsen2_conv_resq)(t, d_weights[2 + 2 * l], d_bias[2 + 2 * l], n, P, P, 0.1f, x_hi,
+                                                           xq, l == num_layers - 1 ? x_lo : nullptr, stream);
     if (rc) return rc;
   }
-  return dsen2_conv3x3(x_hi, d_weights[2 * num_layers + 1], d_bias[2 * num_layers + 1], n, P, P, feature_size, 16, 9,
-                       DSEN2_EPI_TAIL_NCHW, nullptr, nullptr, 0.f, nullptr, nullptr, d_x[n_inputs - 1], d_out_f32,
-                       cout_real, stream);
+  return dsen2_conv_tail16(x_hi, x_lo, d_weights[2 * num_layers + 1], d_bias[2 * num_layers + 1], xin_hi, xin_lo,
+                           ctot - cout_real, cout_real, F, n, P, P, d_out_f32, stream);
 }

@@ -88,22 +88,28 @@ __global__ void prep_from_patches_kernel(const float* __restrict__ x0, int c0, c
 }
 
 struct PrepSource {
-  const float* img;   // (H, W, C) float32 HWC; C = 4 / 6 / 2 for the 10 / 20 / 60 m inputs
+  const void* img;    // (H, W, C) HWC, float32 or uint16 DN; C = 4 / 6 / 2 for the 10 / 20 / 60 m inputs
   int H, W;
   int ratio;          // source pixels per tiling-grid pixel
   int s;              // upsampling factor to the 10 m patch (1 = none)
 };
 
+// image element -> float: exact for uint16 digital numbers (what GDAL hands s2_tiles_supres.py:311-315), so a
+// uint16 image and its float32 copy prepare bit-identical inputs
+__device__ __forceinline__ float ld_px(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ld_px(const uint16_t* p) { return (float)__ldg(p); }
+
 // value of band c of `src` at 10 m patch pixel (y, x): crop + symmetric pad (+ mirror bilinear) + /divisor
-template <int C, int OFF>
+template <typename T, int C, int OFF>
 __device__ __forceinline__ void prep_gather(const PrepSource& src, int si, int sj, int plr, int blr, int y, int x,
                                             float divisor, float (&v)[16]) {
+  const T* img = reinterpret_cast<const T*>(src.img);
   const int p = plr * src.ratio, b = blr * src.ratio;
   const int oi = si * src.ratio - b, oj = sj * src.ratio - b;
   if (src.s == 1) {
-    const float* q = src.img + ((long long)sym_index(oi + y, src.H) * src.W + sym_index(oj + x, src.W)) * C;
+    const T* q = img + ((long long)sym_index(oi + y, src.H) * src.W + sym_index(oj + x, src.W)) * C;
 #pragma unroll
-    for (int c = 0; c < C; ++c) v[OFF + c] = __fdiv_rn(__ldg(q + c), divisor);
+    for (int c = 0; c < C; ++c) v[OFF + c] = __fdiv_rn(ld_px(q + c), divisor);
     return;
   }
   int y0, y1, x0, x1;
@@ -112,15 +118,15 @@ __device__ __forceinline__ void prep_gather(const PrepSource& src, int si, int s
   bilin_tap(x, src.s, p, x0, x1, fx);
   const long long r0 = (long long)sym_index(oi + y0, src.H) * src.W, r1 = (long long)sym_index(oi + y1, src.H) * src.W;
   const int q0 = sym_index(oj + x0, src.W), q1 = sym_index(oj + x1, src.W);
-  const float* p00 = src.img + (r0 + q0) * C;
-  const float* p01 = src.img + (r0 + q1) * C;
-  const float* p10 = src.img + (r1 + q0) * C;
-  const float* p11 = src.img + (r1 + q1) * C;
+  const T* p00 = img + (r0 + q0) * C;
+  const T* p01 = img + (r0 + q1) * C;
+  const T* p10 = img + (r1 + q0) * C;
+  const T* p11 = img + (r1 + q1) * C;
   const float k = 30000.0f;                  // the reference scales by 1/30000 around the resize (patches.py:15)
 #pragma unroll
   for (int c = 0; c < C; ++c) {
-    const float v00 = __fdiv_rn(__ldg(p00 + c), k), v01 = __fdiv_rn(__ldg(p01 + c), k);
-    const float v10 = __fdiv_rn(__ldg(p10 + c), k), v11 = __fdiv_rn(__ldg(p11 + c), k);
+    const float v00 = __fdiv_rn(ld_px(p00 + c), k), v01 = __fdiv_rn(ld_px(p01 + c), k);
+    const float v10 = __fdiv_rn(ld_px(p10 + c), k), v11 = __fdiv_rn(ld_px(p11 + c), k);
     const float c0 = v00 * (1.0f - fy) + v10 * fy;   // rows first, then columns (as bilinear_mirror_kernel)
     const float c1 = v01 * (1.0f - fy) + v11 * fy;
     const float r = (c0 * (1.0f - fx) + c1 * fx) * k;
@@ -156,6 +162,7 @@ __global__ void prep16_from_patches_kernel(const float* __restrict__ x0, int c0,
   }
 }
 
+template <typename T>
 __global__ void prep16_from_images_kernel(PrepSource s0, PrepSource s1, PrepSource s2, int nsrc, int plr, int blr, int P,
                                           Tiling tl, int first_patch, long long total, float divisor,
                                           __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
@@ -173,9 +180,9 @@ __global__ void prep16_from_images_kernel(PrepSource s0, PrepSource s1, PrepSour
       const int ti = patch / tl.n_j, tj = patch - ti * tl.n_j;
       const int si = ti < tl.k_i ? ti * tl.stride : tl.last_i;
       const int sj = tj < tl.k_j ? tj * tl.stride : tl.last_j;
-      prep_gather<4, 0>(s0, si, sj, plr, blr, y, x, divisor, v);     // 10 m bands   (DSen2Net.py:24,26 order)
-      prep_gather<6, 4>(s1, si, sj, plr, blr, y, x, divisor, v);     // 20 m bands
-      if (nsrc == 3) prep_gather<2, 10>(s2, si, sj, plr, blr, y, x, divisor, v);   // 60 m bands
+      prep_gather<T, 4, 0>(s0, si, sj, plr, blr, y, x, divisor, v);     // 10 m bands   (DSen2Net.py:24,26 order)
+      prep_gather<T, 6, 4>(s1, si, sj, plr, blr, y, x, divisor, v);     // 20 m bands
+      if (nsrc == 3) prep_gather<T, 2, 10>(s2, si, sj, plr, blr, y, x, divisor, v);   // 60 m bands
     }
     Half16 hi, lo;
     split16(v, hi, lo);
@@ -290,9 +297,9 @@ __global__ void prep_from_images_rows_kernel(PrepSource s0, PrepSource s1, PrepS
       const int ti = patch / tl.n_j, tj = patch - ti * tl.n_j;
       const int si = ti < tl.k_i ? ti * tl.stride : tl.last_i;
       const int sj = tj < tl.k_j ? tj * tl.stride : tl.last_j;
-      prep_gather<4, 0>(s0, si, sj, plr, blr, y, x, divisor, v);     // 10 m bands   (DSen2Net.py:24,26 order)
-      prep_gather<6, 4>(s1, si, sj, plr, blr, y, x, divisor, v);     // 20 m bands
-      if (nsrc == 3) prep_gather<2, 10>(s2, si, sj, plr, blr, y, x, divisor, v);   // 60 m bands
+      prep_gather<float, 4, 0>(s0, si, sj, plr, blr, y, x, divisor, v);     // 10 m bands   (DSen2Net.py:24,26 order)
+      prep_gather<float, 6, 4>(s1, si, sj, plr, blr, y, x, divisor, v);     // 20 m bands
+      if (nsrc == 3) prep_gather<float, 2, 10>(s2, si, sj, plr, blr, y, x, divisor, v);   // 60 m bands
     }
     split16(v, hi, lo);
   }
@@ -326,9 +333,9 @@ __global__ void prep_from_images_kernel(PrepSource s0, PrepSource s1, PrepSource
       const int ti = patch / tl.n_j, tj = patch - ti * tl.n_j;
       const int si = ti < tl.k_i ? ti * tl.stride : tl.last_i;
       const int sj = tj < tl.k_j ? tj * tl.stride : tl.last_j;
-      prep_gather<4, 0>(s0, si, sj, plr, blr, y, x, divisor, v);     // 10 m bands   (DSen2Net.py:24,26 order)
-      prep_gather<6, 4>(s1, si, sj, plr, blr, y, x, divisor, v);     // 20 m bands
-      if (nsrc == 3) prep_gather<2, 10>(s2, si, sj, plr, blr, y, x, divisor, v);   // 60 m bands
+      prep_gather<float, 4, 0>(s0, si, sj, plr, blr, y, x, divisor, v);     // 10 m bands   (DSen2Net.py:24,26 order)
+      prep_gather<float, 6, 4>(s1, si, sj, plr, blr, y, x, divisor, v);     // 20 m bands
+      if (nsrc == 3) prep_gather<float, 2, 10>(s2, si, sj, plr, blr, y, x, divisor, v);   // 60 m bands
     }
     Half16 hi, lo;
     split16(v, hi, lo);
@@ -473,10 +480,12 @@ extern "C" int dsen2_prep16_from_patches(const float* d_x0, int c0, const float*
   return check_launch("prep16_from_patches");
 }
 
-extern "C" int dsen2_prep16_from_images(const float* d_img10, const float* d_img20, const float* d_img60, int H, int W,
-                                        int patch, int border, int first_patch, int num_patches, float divisor,
+extern "C" int dsen2_prep16_from_images(const void* d_img10, const void* d_img20, const void* d_img60, int img_dtype, int H,
+                                        int W, int patch, int border, int first_patch, int num_patches, float divisor,
                                         void* d_xin_hi, void* d_xin_lo, void* stream) {
   DSEN2_REQUIRE(d_img10 && d_img20 && d_xin_hi && d_xin_lo, DSEN2_E_BADARG, "dsen2_prep16_from_images: null pointer");
+  DSEN2_REQUIRE(img_dtype == DSEN2_IMG_F32 || img_dtype == DSEN2_IMG_U16, DSEN2_E_BADARG,
+                "dsen2_prep16_from_images: img_dtype must be DSEN2_IMG_F32 or DSEN2_IMG_U16 (got %d)", img_dtype);
   const int r = d_img60 ? 6 : 2;                 // the tiling grid is the coarsest input (patches.py:45-53,114-122)
   DSEN2_REQUIRE(H > 0 && W > 0 && H % r == 0 && W % r == 0, DSEN2_E_BADARG,
                 "dsen2_prep16_from_images: 10 m size %dx%d must be a multiple of %d", H, W, r);
@@ -499,8 +508,12 @@ extern "C" int dsen2_prep16_from_images(const float* d_img10, const float* d_img
   PrepSource s2{d_img60, H / 6, W / 6, 1, 6};
   const long long total = (long long)num_patches * patch * patch;
   const int block = 256;
-  prep16_from_images_kernel<<<grid_for(total, block), block, 0, (cudaStream_t)stream>>>(
-      s0, s1, s2, d_img60 ? 3 : 2, plr, blr, patch, tl, first_patch, total, divisor, (__half*)d_xin_hi, (__half*)d_xin_lo);
+  if (img_dtype == DSEN2_IMG_U16)
+    prep16_from_images_kernel<uint16_t><<<grid_for(total, block), block, 0, (cudaStream_t)stream>>>(
+        s0, s1, s2, d_img60 ? 3 : 2, plr, blr, patch, tl, first_patch, total, divisor, (__half*)d_xin_hi, (__half*)d_xin_lo);
+  else
+    prep16_from_images_kernel<float><<<grid_for(total, block), block, 0, (cudaStream_t)stream>>>(
+        s0, s1, s2, d_img60 ? 3 : 2, plr, blr, patch, tl, first_patch, total, divisor, (__half*)d_xin_hi, (__half*)d_xin_lo);
   return check_launch("prep16_from_images");
 }
 

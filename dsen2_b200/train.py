@@ -52,7 +52,7 @@ class Trainer:
 
     def __init__(self, model, optimizer=None, device=None, group=None):
         torch = _capi.require_cuda()
-        if not model.fast_path:
+        if model.feature_size != 128:
             raise _capi.DSen2Error("training is implemented for the DSen2 (feature_size 128) network")
         self.torch, self.model, self.opt, self.group = torch, model, optimizer or Nadam(), group
         self.dev = torch.device('cuda', torch.cuda.current_device()) if device is None else device

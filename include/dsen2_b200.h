@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define DSEN2_ABI_VERSION 1
+#define DSEN2_ABI_VERSION 2
 
 #define DSEN2_E_BADARG   (-1)  /* null pointer / non-positive size / unsupported combination */
 #define DSEN2_E_ALIGN    (-2)  /* pointer or channel count not aligned as the kernel requires */
@@ -158,7 +158,12 @@ int dsen2_prep_from_images(const float* d_img10, const float* d_img20, const flo
  * take the global skip from it.  Arguments as dsen2_prep_from_patches / dsen2_prep_from_images.               */
 int dsen2_prep16_from_patches(const float* d_x0, int c0, const float* d_x1, int c1, const float* d_x2, int c2,
                               int n, int P, void* d_xin_hi, void* d_xin_lo, void* stream);
-int dsen2_prep16_from_images(const float* d_img10, const float* d_img20, const float* d_img60, int H, int W,
+/* dsen2_prep16_from_images reads the images as float32 or, natively, as the uint16 digital numbers GDAL hands
+ * testing/s2_tiles_supres.py:311-315 (half the bytes to upload; uint16 -> float is exact, so both give bit-identical
+ * prepared inputs).                                                                                              */
+#define DSEN2_IMG_F32 0
+#define DSEN2_IMG_U16 1
+int dsen2_prep16_from_images(const void* d_img10, const void* d_img20, const void* d_img60, int img_dtype, int H, int W,
                              int patch, int border, int first_patch, int num_patches, float divisor,
                              void* d_xin_hi, void* d_xin_lo, void* stream);
 /* First layer kernel (3,3,cin,F) fp32 HWIO -> [9 taps][2F rows = W_hi ; W_lo][16] fp16 (for dsen2_conv_head16_q). */
@@ -195,23 +200,22 @@ int dsen2_conv_res32(const void* d_in, const void* d_w, const float* d_bias, int
  * lo = ((s >> 5) & 0xff) - 128, and a reader recovers bits(x) ~ bits(float(x_hi)) + (lo << 5) (|error| <= 16 fp32
  * ulps).  Below 2^-14 x_hi is an fp16 subnormal and the pair only keeps x to an absolute 2^-24; lo is 0 where x_hi
  * is zero.  A resblock then moves 1024 B/pixel through HBM instead of the 1536 of the fp32 trunk above.
- *   dsen2_conv_head_q:  x = relu(conv(x_in) + bias)  ->  d_x_hi, d_trunk_lo8                (DSen2Net.py:29)
+ *   dsen2_conv_head16_q: x = relu(conv(x_in16) + bias)  ->  d_x_hi, d_trunk_lo8           (DSen2Net.py:29; below)
  *   dsen2_conv_resq:    x <- x + res_scale * (conv3x3(d_in) + bias), in place               (DSen2Net.py:12-15)
  *                       d_out_lo != NULL marks the LAST block: x_hi <- fp16(x) (round to nearest even) and
  *                       d_out_lo <- fp16(x - x_hi) NHWC for dsen2_conv_tail; d_trunk_lo8 is then only read.
  * d_in must not alias d_x_hi.  feature_size 128 only.                                                       */
-int dsen2_conv_head_q(const void* d_xin_hi, const void* d_xin_lo, const void* d_w, const float* d_bias,
-                      int n, int H, int W, int feature_size, void* d_x_hi, void* d_trunk_lo8, void* stream);
 int dsen2_conv_resq(const void* d_in, const void* d_w, const float* d_bias, int n, int H, int W,
                     float res_scale, void* d_x_hi, void* d_trunk_lo8, void* d_out_lo, void* stream);
-/* The same resblock update for feature_size 256 (VDSen2; d_w from dsen2_pack_conv_weights(cin_pad = cout_pad = 256)),
- * and the re-coding of an NHWC fp16 (hi, lo) pair as x_hi + bytes: x = hi + lo -> d_x_hi (in place), d_trunk_lo8.
- * VDSen2's first layer (dsen2_conv3x3 on the im2col'd input) writes hi + lo.  C % 16 == 0.                     */
+/* The same resblock update for feature_size 256 (VDSen2; d_w from dsen2_pack_conv_weights(cin_pad = cout_pad = 256):
+ * 1.18 MB of weights per layer stream through an 8-slot shared-memory ring instead of staying resident), and the
+ * re-coding of an NHWC fp16 (hi, lo) pair as x_hi + bytes: x = hi + lo -> d_x_hi (in place), d_trunk_lo8.  C % 16 == 0. */
 int dsen2_conv_resq256(const void* d_in, const void* d_w, const float* d_bias, int n, int H, int W,
                        float res_scale, void* d_x_hi, void* d_trunk_lo8, void* d_out_lo, void* stream);
 int dsen2_trunk_hilo_to_q(void* d_x_hi, const void* d_x_lo, void* d_trunk_lo8, int n, int H, int W, int C, void* stream);
-/* dsen2_conv_head_q on the 16-channel prepared input (dsen2_prep16_*, weights from dsen2_pack_head16_weights): nine
- * taps as shifted descriptors into a 32-byte-row (SWIZZLE_32B) halo box.                                       */
+/* First layer on the 16-channel prepared input (dsen2_prep16_*, weights from dsen2_pack_head16_weights), feature_size 128
+ * or 256: nine taps as shifted descriptors into a 32-byte-row (SWIZZLE_32B) halo box; per tap the three products
+ * hi*W_hi + hi*W_lo + lo*W_hi accumulate into ONE TMEM accumulator (fp32-equivalent first layer).               */
 int dsen2_conv_head16_q(const void* d_xin_hi, const void* d_xin_lo, const void* d_w, const float* d_bias,
                         int n, int H, int W, int feature_size, void* d_x_hi, void* d_trunk_lo8, void* stream);
 
@@ -222,32 +226,25 @@ int dsen2_conv_tail(const void* d_x_hi, const void* d_x_lo, const void* d_w, con
                     const void* d_xin_hi, const void* d_xin_lo, int skip_ch0, int cout,
                     int n, int H, int W, float* d_pred_nchw, void* stream);
 
+/* dsen2_conv_tail with the global skip read from the 16-channel prepared input; feature_size 128 or 256.            */
+int dsen2_conv_tail16(const void* d_x_hi, const void* d_x_lo, const void* d_w, const float* d_bias,
+                      const void* d_xin_hi, const void* d_xin_lo, int skip_ch0, int cout, int feature_size,
+                      int n, int H, int W, float* d_pred_nchw, void* stream);
 /* Same, fused with recompose_images (utils/patches.py:374-405) and the x SCALE of supres.py:29,49: the
  * n patches are patches [first_patch, first_patch + n) of the canvas tiling; each writes the pixels of
  * the (img_h, img_w, cout) float32 HWC canvas whose LAST writer it is, multiplied by `mul`.          */
-int dsen2_conv_tail_stitch(const void* d_x_hi, const void* d_x_lo, const void* d_w, const float* d_bias,
-                           const void* d_xin_hi, const void* d_xin_lo, int skip_ch0, int cout,
-                           int n, int P, int first_patch, int border, int img_h, int img_w, float mul,
-                           float* d_canvas, void* stream);
-
-/* dsen2_conv_tail / dsen2_conv_tail_stitch with the global skip read from the 16-channel prepared input. */
-int dsen2_conv_tail16(const void* d_x_hi, const void* d_x_lo, const void* d_w, const float* d_bias,
-                      const void* d_xin_hi, const void* d_xin_lo, int skip_ch0, int cout,
-                      int n, int H, int W, float* d_pred_nchw, void* stream);
 int dsen2_conv_tail16_stitch(const void* d_x_hi, const void* d_x_lo, const void* d_w, const float* d_bias,
-                             const void* d_xin_hi, const void* d_xin_lo, int skip_ch0, int cout,
+                             const void* d_xin_hi, const void* d_xin_lo, int skip_ch0, int cout, int feature_size,
                              int n, int P, int first_patch, int border, int img_h, int img_w, float mul,
                              float* d_canvas, void* stream);
 
 /* Whole s2model forward (model.predict on one batch, supres.py:65) for n patches of (P, P).
  * d_weights[i] / d_bias[i] are the packed layers in Keras topological order (2*num_layers+2 entries):
- *   feature_size 128: [0] dsen2_pack_head16_weights (dsen2_pack_head_weights when num_layers == 0),
- *                     [1..2L] dsen2_pack_conv_weights(cin_pad=cout_pad=128), [2L+1] dsen2_pack_tail_weights;
- *                     biases fp32 of length 128 / 128 / 16;
- *                     pipeline: prep16_from_patches -> conv_head16_q -> L x (conv3x3 RELU, conv_resq) -> conv_tail16
- *   feature_size 256: [0] dsen2_pack_conv_weights(im2col=1), [1..2L] (256,256), [2L+1] cout_pad 16;
- *                     pipeline: pack_head_input -> conv3x3 (1x1) -> trunk_hilo_to_q -> L x (conv3x3 RELU, conv_resq256)
- *                     -> conv3x3 TAIL_NCHW.
+ *   [0] dsen2_pack_head16_weights (dsen2_pack_head_weights when num_layers == 0, feature_size 128 only),
+ *   [1..2L] dsen2_pack_conv_weights(cin_pad = cout_pad = feature_size), [2L+1] dsen2_pack_tail_weights;
+ *   biases fp32 of length F / F / 16;
+ *   pipeline: prep16_from_patches -> conv_head16_q -> L x (conv3x3 RELU, conv_resq[256]) -> conv_tail16
+ *   for feature_size 128 (DSen2) and 256 (VDSen2) alike.
  * Workspace: see dsen2_s2model_workspace_bytes.  d_x[0..n_inputs) NCHW fp32 inputs; the last one is
  * the global skip. */
 size_t dsen2_s2model_workspace_bytes(int n, int P, int in_channels, int feature_size);

@@ -182,6 +182,55 @@ def test_DSen2_20_and_60_scene_vs_oracle(env, malmo):
         assert err <= GATE
 
 
+def test_VDSen2_depth32_scene_vs_oracle(env):
+    """VDSen2 at its real depth (32 resblocks x 256 features, supres.py:55-57 deep=True shapes) through the facade:
+    DSen2_20 on a 220 x 220 scene (4 patches of 128) and DSen2_60 on a 180 x 180 scene (4 patches of 192) -- sizes whose
+    allocated patch stack has no surplus zero patches for the CPU oracle to grind through -- he_uniform weights with
+    non-zero biases, against the fp32 CPU oracle.  Gate 5e-3 on the /2000-scaled output."""
+    from dsen2_b200 import supres
+    from dsen2_b200.DSen2Net import s2model
+    from oracle import dsen2net_oracle as no
+    rng = np.random.RandomState(32)
+    for run_60, (H, W) in ((False, (220, 220)), (True, (180, 180))):
+        shape = ((4, None, None), (6, None, None)) + (((2, None, None),) if run_60 else ())
+        model = s2model(shape, num_layers=32, feature_size=256, seed=1)
+        ws = model.get_weights()
+        for i in range(1, len(ws), 2):
+            ws[i] = (rng.randn(*ws[i].shape) * 0.02).astype(np.float32)
+        model.set_weights(ws)
+        wl = [(ws[2 * i], ws[2 * i + 1]) for i in range(len(ws) // 2)]
+        d10 = rng.randint(200, 6000, size=(H, W, 4)).astype(np.float32)
+        d20 = rng.randint(200, 6000, size=(H // 2, W // 2, 6)).astype(np.float32)
+        if run_60:
+            d60 = rng.randint(200, 6000, size=(H // 6, W // 6, 2)).astype(np.float32)
+            got, ref = supres.DSen2_60(d10, d20, d60, model=model), no.DSen2_60(d10, d20, d60, wl)
+            assert got.shape == (H, W, 2)
+        else:
+            got, ref = supres.DSen2_20(d10, d20, model=model), no.DSen2_20(d10, d20, wl)
+            assert got.shape == (H, W, 6)
+        err = np.abs(got - ref).max() / supres.SCALE
+        print('VDSen2 32x256 run_60', run_60, 'max abs err (scaled)', err, 'output range', ref.min() / supres.SCALE,
+              ref.max() / supres.SCALE)
+        assert err <= GATE
+
+
+def test_DSen2_20_single_filled_patch_is_stitched_and_cropped(env):
+    """112 x 112 (golden case 'c'): one filled patch of four allocated -> recompose_images crops it (patches.py:375 keys
+    on the allocated count); the facade must return (112, 112, 6), not the uncropped 128 x 128 patch."""
+    from dsen2_b200 import supres
+    from dsen2_b200.DSen2Net import s2model
+    from oracle import dsen2net_oracle as no
+    rng = np.random.RandomState(7)
+    d10 = rng.randint(200, 6000, size=(112, 112, 4)).astype(np.float32)
+    d20 = rng.randint(200, 6000, size=(56, 56, 6)).astype(np.float32)
+    model = s2model(((4, None, None), (6, None, None)), num_layers=2, feature_size=128, seed=4)
+    ws = model.get_weights()
+    got = supres.DSen2_20(d10, d20, model=model)
+    ref = no.DSen2_20(d10, d20, [(ws[2 * i], ws[2 * i + 1]) for i in range(len(ws) // 2)])
+    assert got.shape == ref.shape == (112, 112, 6)
+    assert np.abs(got - ref).max() / supres.SCALE <= GATE
+
+
 def test_missing_weight_file_raises_oserror(env):
     from dsen2_b200 import supres
     old = supres.MDL_PATH

@@ -184,22 +184,52 @@ def test_conv_tail_nchw_fp32_equivalent(env, shape, cout, ch0):
     np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=2e-5, atol=2e-5)
 
 
-@pytest.mark.parametrize('tag', ['a', 'b', 'd'])     # 'c' is a single patch: returned uncropped by the facade
-def test_conv_tail_stitch_matches_recompose(env, tag):
-    """tail + stitch fusion == tail (NCHW) then recompose_images (CPU oracle) x 2000, exactly."""
+@pytest.mark.parametrize('shape,cout,ch0,F', [((2, 32, 32), 6, 4, 128), ((1, 128, 128), 6, 4, 256), ((1, 48, 48), 2, 10, 256),
+                                              ((3, 40, 24), 6, 4, 256), ((1, 192, 192), 2, 10, 128)])
+def test_conv_tail16_nchw_fp32_equivalent(env, shape, cout, ch0, F):
+    """Last layer (F -> cout, split hi + lo operands) + global skip from the 16-channel prepared input, F = 128 / 256."""
+    torch, _capi, lib = env
+    n, H, W = shape
+    rng = np.random.RandomState(H * 3 + cout + F)
+    x_hi, x_lo = _split(rng.randn(n, H, W, F).astype(np.float32))
+    xin_hi, xin_lo = _split(rng.uniform(0, 4, size=(n, H, W, 16)).astype(np.float32))
+    lim = np.sqrt(6.0 / (9 * F))
+    w = rng.uniform(-lim, lim, size=(3, 3, F, cout)).astype(np.float32)
+    bias = np.zeros(16, np.float32)
+    bias[:cout] = rng.randn(cout) * 0.1
+    tw = torch.empty((9, 32, F), dtype=torch.float16, device='cuda')
+    _capi.check(lib.dsen2_pack_tail_weights(_capi.ptr(torch.from_numpy(w).cuda()), F, cout, _capi.ptr(tw),
+                                            _capi.stream_ptr()), 'pack tail')
+    dev = [torch.from_numpy(a).cuda() for a in (x_hi, x_lo, xin_hi, xin_lo, bias)]
+    out = torch.full((n, cout, H, W), -5.0, device='cuda')
+    _capi.check(lib.dsen2_conv_tail16(_capi.ptr(dev[0]), _capi.ptr(dev[1]), _capi.ptr(tw), _capi.ptr(dev[4]),
+                                      _capi.ptr(dev[2]), _capi.ptr(dev[3]), ch0, cout, F, n, H, W, _capi.ptr(out),
+                                      _capi.stream_ptr()), 'conv tail16')
+    torch.cuda.synchronize()
+    xe = x_hi.astype(np.float64) + x_lo.astype(np.float64)
+    w_hi = w.astype(np.float16)
+    w_eff = w_hi.astype(np.float64) + (w - w_hi.astype(np.float32)).astype(np.float16).astype(np.float64)
+    skip = (xin_hi.astype(np.float64) + xin_lo.astype(np.float64))[..., ch0:ch0 + cout]
+    ref = (_conv64(xe, w_eff, bias[:cout]) + skip).transpose(0, 3, 1, 2)
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize('tag,F', [('a', 128), ('b', 128), ('c', 128), ('d', 128), ('b', 256)])
+def test_conv_tail_stitch_matches_recompose(env, tag, F):
+    """tail + stitch fusion == tail (NCHW) then recompose_images (CPU oracle) x 2000, exactly.  Case 'c' (112 x 112)
+    fills ONE patch of the four allocated ones: it is stitched and cropped like any other (patches.py:375 keys on the
+    allocated count)."""
     torch, _capi, lib = env
     from oracle import patches_oracle as po
     d10, _, _ = synth(tag)
     H, W = d10.shape[:2]
-    P, B, F, cout = 128, 8, 128, 6
+    P, B, cout = 128, 8, 6
     S = P - 2 * B
     ny, nx = -(-H // S), -(-W // S)
     n = ny * nx
     rng = np.random.RandomState(n)
     x_hi, x_lo = _split(rng.randn(n, P, P, F).astype(np.float32))
-    xin = np.zeros((n, P, P, 64), np.float32)
-    xin[..., 16:32] = rng.uniform(0, 4, size=(n, P, P, 16)).astype(np.float32)
-    xin_hi, xin_lo = _split(xin)
+    xin_hi, xin_lo = _split(rng.uniform(0, 4, size=(n, P, P, 16)).astype(np.float32))
     lim = np.sqrt(6.0 / (9 * F))
     w = rng.uniform(-lim, lim, size=(3, 3, F, cout)).astype(np.float32)
     bias = np.zeros(16, np.float32)
@@ -208,9 +238,9 @@ def test_conv_tail_stitch_matches_recompose(env, tag):
                                             _capi.stream_ptr()), 'pack tail')
     dev = [torch.from_numpy(a).cuda() for a in (x_hi, x_lo, xin_hi, xin_lo, bias)]
     pred = torch.empty((n, cout, P, P), device='cuda')
-    _capi.check(lib.dsen2_conv_tail(_capi.ptr(dev[0]), _capi.ptr(dev[1]), _capi.ptr(tw), _capi.ptr(dev[4]),
-                                    _capi.ptr(dev[2]), _capi.ptr(dev[3]), 4, cout, n, P, P, _capi.ptr(pred),
-                                    _capi.stream_ptr()), 'conv tail')
+    _capi.check(lib.dsen2_conv_tail16(_capi.ptr(dev[0]), _capi.ptr(dev[1]), _capi.ptr(tw), _capi.ptr(dev[4]),
+                                      _capi.ptr(dev[2]), _capi.ptr(dev[3]), 4, cout, F, n, P, P, _capi.ptr(pred),
+                                      _capi.stream_ptr()), 'conv tail16')
     canvas = torch.full((H, W, cout), -1.0, device='cuda')
     # two shards, second first: ownership (not launch order) decides every pixel
     half = n // 2
@@ -218,12 +248,16 @@ def test_conv_tail_stitch_matches_recompose(env, tag):
         if cnt == 0:
             continue
         sl = slice(first, first + cnt)
-        _capi.check(lib.dsen2_conv_tail_stitch(_capi.ptr(dev[0][sl]), _capi.ptr(dev[1][sl]), _capi.ptr(tw),
-                                               _capi.ptr(dev[4]), _capi.ptr(dev[2][sl]), _capi.ptr(dev[3][sl]), 4, cout,
-                                               cnt, P, first, B, H, W, 2000.0, _capi.ptr(canvas), _capi.stream_ptr()),
-                    'conv tail stitch')
+        _capi.check(lib.dsen2_conv_tail16_stitch(_capi.ptr(dev[0][sl]), _capi.ptr(dev[1][sl]), _capi.ptr(tw),
+                                                 _capi.ptr(dev[4]), _capi.ptr(dev[2][sl]), _capi.ptr(dev[3][sl]), 4, cout, F,
+                                                 cnt, P, first, B, H, W, 2000.0, _capi.ptr(canvas), _capi.stream_ptr()),
+                    'conv tail16 stitch')
     torch.cuda.synchronize()
-    ref = po.recompose_images(pred.cpu().numpy(), B, (H, W)) * np.float32(2000)
+    allocated = (H // 2 // 56 + 1) * (W // 2 // 56 + 1)
+    full = np.zeros((allocated, cout, P, P), np.float32)      # the reference's stack carries the surplus zero patches
+    full[:n] = pred.cpu().numpy()
+    ref = po.recompose_images(full, B, (H, W)) * np.float32(2000)
+    assert ref.shape == (H, W, cout)
     assert np.array_equal(canvas.cpu().numpy(), ref)
 
 
@@ -297,39 +331,7 @@ def test_conv_res32_fp32_trunk_update(env, shape, want_lo):
         assert np.array_equal(lo.cpu().numpy().view(np.uint16), exp_lo.view(np.uint16))
 
 
-# ---- fp16 + 8 bit trunk (include/dsen2_b200.h: dsen2_conv_head_q / dsen2_conv_resq) ---------------------------------
-@pytest.mark.parametrize('shape', [(2, 32, 32), (1, 128, 128), (3, 40, 24), (1, 8, 200), (5, 16, 8)])
-def test_conv_head_q_seeds_the_trunk(env, shape):
-    torch, _capi, lib = env
-    n, H, W = shape
-    F, C = 128, 10
-    rng = np.random.RandomState(H + W)
-    xcat = rng.uniform(0, 5, size=(n, C, H, W)).astype(np.float32)
-    xp = np.zeros((n, H, W + 2, 16), np.float32)
-    xp[:, :, 1:W + 1, :C] = xcat.transpose(0, 2, 3, 1)
-    full = np.concatenate([xp[:, :, t:t + W, :] for t in range(3)] + [np.zeros((n, H, W, 16), np.float32)], axis=-1)
-    hi, lo = _split(full)
-    lim = np.sqrt(6.0 / (9 * C))
-    w = rng.uniform(-lim, lim, size=(3, 3, C, F)).astype(np.float32)
-    bias = (rng.randn(F) * 0.1).astype(np.float32)
-    tw = torch.empty((3, 2 * F, 64), dtype=torch.float16, device='cuda')
-    _capi.check(lib.dsen2_pack_head_weights(_capi.ptr(torch.from_numpy(w).cuda()), C, F, _capi.ptr(tw),
-                                            _capi.stream_ptr()), 'pack head')
-    thi, tlo, tb = torch.from_numpy(hi).cuda(), torch.from_numpy(lo).cuda(), torch.from_numpy(bias).cuda()
-    ohi = torch.zeros((n, H, W, F), dtype=torch.float16, device='cuda')
-    oq = torch.full((n, H, W // 8, F // 16, 8, 16), 77, dtype=torch.int8, device='cuda')
-    _capi.check(lib.dsen2_conv_head_q(_capi.ptr(thi), _capi.ptr(tlo), _capi.ptr(tw), _capi.ptr(tb), n, H, W, F,
-                                      _capi.ptr(ohi), _capi.ptr(oq), _capi.stream_ptr()), 'conv head q')
-    torch.cuda.synchronize()
-    ref = np.maximum(_conv64(xcat.transpose(0, 2, 3, 1), w, bias), 0)
-    h, q = ohi.cpu().numpy(), _q_from_tiles(oq.cpu().numpy())
-    got = _q_decode(h, q)
-    np.testing.assert_allclose(got, ref, rtol=2e-5, atol=2e-5)
-    ok = np.abs(got) >= 2 * NORMAL                                                      # codes are fixed points
-    h2, q2 = _q_encode(got[ok])
-    assert np.array_equal(h2.view(np.uint16), h[ok].view(np.uint16)) and np.array_equal(q2, q[ok])
-
-
+# ---- fp16 + 8 bit trunk (include/dsen2_b200.h: dsen2_conv_head16_q / dsen2_conv_resq) -------------------------------
 @pytest.mark.parametrize('shape', [(2, 32, 32), (1, 128, 128), (3, 40, 24), (1, 8, 200), (2, 192, 192)])
 @pytest.mark.parametrize('last', [False, True])
 def test_conv_resq_trunk_update(env, shape, last):
@@ -420,20 +422,32 @@ def test_prep16_from_images_equals_centre_tap_of_the_gathered_form(env, tag):
     lo16 = torch.full_like(hi16, 7.0)
     _capi.check(lib.dsen2_prep_from_images(_capi.ptr(t10), _capi.ptr(t20), _capi.ptr(t60), H, W, P, B, 0, n, 2000.0,
                                            _capi.ptr(hi64), _capi.ptr(lo64), _capi.stream_ptr()), 'prep_from_images')
-    _capi.check(lib.dsen2_prep16_from_images(_capi.ptr(t10), _capi.ptr(t20), _capi.ptr(t60), H, W, P, B, 0, n, 2000.0,
-                                             _capi.ptr(hi16), _capi.ptr(lo16), _capi.stream_ptr()), 'prep16_from_images')
+    _capi.check(lib.dsen2_prep16_from_images(_capi.ptr(t10), _capi.ptr(t20), _capi.ptr(t60), _capi.IMG_F32, H, W, P, B, 0, n,
+                                             2000.0, _capi.ptr(hi16), _capi.ptr(lo16), _capi.stream_ptr()), 'prep16_from_images')
     torch.cuda.synchronize()
     assert torch.equal(hi16.view(torch.int16), hi64[..., 16:32].contiguous().view(torch.int16))
     assert torch.equal(lo16.view(torch.int16), lo64[..., 16:32].contiguous().view(torch.int16))
+    # the same images as uint16 digital numbers (what GDAL delivers): bit-identical prepared input
+    assert all(np.array_equal(a, a.astype(np.uint16)) for a in (d10, d20) + ((d60,) if run60 else ()))
+    u10, u20 = torch.from_numpy(d10.astype(np.uint16)).cuda(), torch.from_numpy(d20.astype(np.uint16)).cuda()
+    u60 = torch.from_numpy(d60.astype(np.uint16)).cuda() if run60 else None
+    hi_u = torch.full((n, P, P, 16), 7.0, dtype=torch.float16, device='cuda')
+    lo_u = torch.full_like(hi_u, 7.0)
+    _capi.check(lib.dsen2_prep16_from_images(_capi.ptr(u10), _capi.ptr(u20), _capi.ptr(u60), _capi.IMG_U16, H, W, P, B, 0, n,
+                                             2000.0, _capi.ptr(hi_u), _capi.ptr(lo_u), _capi.stream_ptr()), 'prep16 u16')
+    torch.cuda.synchronize()
+    assert torch.equal(hi_u.view(torch.int16), hi16.view(torch.int16)) and torch.equal(lo_u.view(torch.int16), lo16.view(torch.int16))
 
 
 @pytest.mark.parametrize('shape', [(2, 32, 32), (1, 128, 128), (3, 40, 24), (1, 8, 200), (5, 16, 8), (1, 192, 192)])
-def test_conv_head16_q_nine_taps(env, shape):
-    """First layer on the 16-channel input: nine shifted 32-byte-row descriptors; fp32-equivalent (hi + lo operands)."""
+@pytest.mark.parametrize('F', [128, 256])
+def test_conv_head16_q_nine_taps(env, shape, F):
+    """First layer on the 16-channel input: nine shifted 32-byte-row descriptors, three products (hi*W_hi + hi*W_lo +
+    lo*W_hi) per tap into one accumulator; fp32-equivalent.  F = 128 (DSen2) and 256 (VDSen2)."""
     torch, _capi, lib = env
     n, H, W = shape
-    F, C = 128, 12
-    rng = np.random.RandomState(H + 3 * W)
+    C = 12
+    rng = np.random.RandomState(H + 3 * W + F)
     xcat = rng.uniform(0, 5, size=(n, C, H, W)).astype(np.float32)
     hi, lo = _xin16_expected(xcat) if H == W else _split(np.concatenate(
         [xcat.transpose(0, 2, 3, 1), np.zeros((n, H, W, 16 - C), np.float32)], axis=-1))
@@ -452,7 +466,7 @@ def test_conv_head16_q_nine_taps(env, shape):
     xin = (hi.astype(np.float64) + lo.astype(np.float64))[..., :C]
     w_hi = w.astype(np.float16)
     w_eff = w_hi.astype(np.float64) + (w - w_hi.astype(np.float32)).astype(np.float16).astype(np.float64)
-    ref = np.maximum(_conv64(xin, w_eff, bias), 0)
+    ref = np.maximum(_conv64(xin, w_eff, bias), 0)         # (the kernel drops lo * W_lo: ~2^-22 of a product)
     got = _q_decode(ohi.cpu().numpy(), _q_from_tiles(oq.cpu().numpy()))
     np.testing.assert_allclose(got, ref, rtol=2e-5, atol=2e-5)
     assert np.abs(got - np.maximum(_conv64(xcat.transpose(0, 2, 3, 1), w, bias), 0)).max() < 5e-5   # vs the true fp32 layer
@@ -477,8 +491,10 @@ def test_trunk_hilo_to_q_recoding(env):
 
 
 @pytest.mark.parametrize('shape', [(2, 32, 32), (1, 128, 128), (3, 40, 24)])
-def test_conv_resq256_trunk_update(env, shape):
-    """The 256-feature (VDSen2) resblock update on the fp16 + 8 bit trunk: two 64-channel passes per thread."""
+@pytest.mark.parametrize('last', [False, True])
+def test_conv_resq256_trunk_update(env, shape, last):
+    """The 256-feature (VDSen2) resblock update on the fp16 + 8 bit trunk: two 64-channel passes per thread; the last
+    block emits x_hi, x_lo for the last layer."""
     torch, _capi, lib = env
     n, H, W = shape
     F = 256
@@ -495,10 +511,15 @@ def test_conv_resq256_trunk_update(env, shape):
     x_seen = _q_decode(h0, q0)
     thi, tq = torch.from_numpy(h0).cuda(), torch.from_numpy(_q_to_tiles(q0)).cuda()
     tt, tb = torch.from_numpy(t).cuda(), torch.from_numpy(bias).cuda()
+    lo = torch.zeros((n, H, W, F), dtype=torch.float16, device='cuda') if last else None
     _capi.check(lib.dsen2_conv_resq256(_capi.ptr(tt), _capi.ptr(tw), _capi.ptr(tb), n, H, W, 0.1, _capi.ptr(thi),
-                                       _capi.ptr(tq), None, _capi.stream_ptr()), 'conv resq256')
+                                       _capi.ptr(tq), _capi.ptr(lo), _capi.stream_ptr()), 'conv resq256')
     torch.cuda.synchronize()
     ref = x_seen.astype(np.float64) + 0.1 * _conv64(t.astype(np.float64), w.astype(np.float16).astype(np.float64), bias)
+    if last:
+        got = thi.cpu().numpy().astype(np.float64) + lo.cpu().numpy().astype(np.float64)
+        np.testing.assert_allclose(got, ref, rtol=3e-5, atol=3e-5)
+        return
     h, q = thi.cpu().numpy(), _q_from_tiles(tq.cpu().numpy())
     got = _q_decode(h, q)
     np.testing.assert_allclose(got, ref, rtol=3e-5, atol=3e-5)

@@ -32,11 +32,9 @@ namespace dsen2 {
 // instruction-heavy epilogue warps that share its sub-partition (measured: tensor pipe 59 % -> see profiles/).
 // (PairCfg::PRODUCER_WARP / MMA_WARP = the two warps after the epilogue warps)
 static constexpr int kBoxH = 18;
-// L2 prefetch distance of the activation boxes, in tiles of this CTA (DSEN2_PAIR_PF_A).  0 = off: with the compact trunk
-// the full tile measures 559-560 ms without it against 565-567 ms with distance 1 (same box, alternating runs); with the
-// fp32 trunk distance 1 was the better setting.
-static constexpr int kPrefetchTiles = 0;
-static constexpr int kTrunkPrefetchTiles = 1;   // same for the fp32 trunk lines the RESIDUAL32 epilogue reads
+// (An L2 prefetch of the next tile's activation boxes was measured and dropped: 559-560 ms per full tile without it
+// against 565-567 ms with distance 1 on the same box.  The trunk lines the residual epilogues read ARE prefetched, one
+// tile ahead.)
 
 enum { kEpiRelu = 0, kEpiResidual = 1, kEpiTail = 2, kEpiResidual32 = 3, kEpiMask = 4, kEpiResidualQ = 5, kEpiResidualQLast = 6,
        kEpiHeadQ = 7 };
@@ -68,17 +66,17 @@ struct PairParams {
   int cout_real;
   float out_mul;
   float* out_f32;
-  int pf_a, pf_x, defer;   // tuning knobs (L2 prefetch distances in tiles, deferred fp16-copy store)
-  int debug;               // profiling aid (DSEN2_PAIR_DEBUG): 1 = epilogue only hands TMEM back, 2 = no activation TMA,
-                           // RESIDUAL32: 4 = no trunk load, 8 = no trunk store, 16 = no fp16 copy store; RESIDUALQ: 4 = no x_hi load,
-                           // 8 = no byte load / store, 16 = no x_hi store, 32 = no transposing gather
   int tail_mode;           // 0: NCHW (n,cout,H,W) predictions; 1: stitched HWC canvas
   int first_patch, img_h, img_w, border, grid_ny, grid_nx;
 };
 
 template <int NTOT_, int SPLIT_, int NMAPS_, int KPM_, int NTAPS_, int KSTEPS_, int STAGES_, int EPI_, int WSTAGES_ = 0,
-          int ROWB_ = 128>
+          int ROWB_ = 128, bool XT_ = false>
 struct PairCfg {
+  // XT: the epilogue moves its x_hi tiles through the async proxy -- every epilogue warp owns a 4 KB shared-memory tile
+  // ([4 rows x 8 pixels][64 channels], 128-byte swizzled = TMA box {64, 8, 4, 1} of the NHWC tensor) that a TMA load fills
+  // with the residual and a TMA store writes back in place, instead of LSU loads / stores through a transposing 1 KB buffer
+  static constexpr bool XT = XT_;
   static constexpr int ROWB = ROWB_;            // bytes per pixel row of a k-block in smem = swizzle span (128: 64 ch, 32: 16 ch)
   static constexpr int KCH = ROWB_ / 2;         // channels per k-block
   static_assert(KSTEPS_ * 32 <= ROWB_, "the K = 16 MMAs of a k-block stay inside its row");
@@ -110,13 +108,13 @@ struct PairCfg {
   static constexpr int W_BYTES = (WSTAGES_ == 0 ? NSLABS : WSTAGES_) * SLAB_BYTES;
   static constexpr int TMEM_COLS = (2 * NTOT_ < 32) ? 32 : 2 * NTOT_;
   static constexpr int BAR_BYTES = 2048;        // barriers + tmem pointer (first 512 B) + bias
-  static constexpr int STG_BYTES = EPI_WARPS * 1024;   // per-warp transpose buffers of the epilogue
+  static constexpr int STG_BYTES = EPI_WARPS * (XT_ ? 4096 : 1024);   // per-warp x_hi tiles / transpose buffers of the epilogue
   static constexpr int SMEM_BYTES = W_BYTES + STAGES_ * STAGE_BYTES + BAR_BYTES + STG_BYTES + 1024 /*align slack*/;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
   static_assert(W_BYTES % 1024 == 0, "weight slabs must keep the stages 1024-byte aligned");
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM allocation must be a power of two <= 512");
   static_assert(CH * 4 + 512 <= BAR_BYTES, "bias does not fit next to the barriers");
-  static_assert((2 * STAGES_ + 6 + 2 * WSTAGES_) * 8 <= 512, "too many barriers");
+  static_assert((2 * STAGES_ + 6 + 2 * WSTAGES_ + EPI_WARPS) * 8 <= 512, "too many barriers");
 };
 
 // tile index -> (patch, tile row, tile column); 32-bit arithmetic (64-bit divisions cost ~100 instructions each)
@@ -295,13 +293,8 @@ __device__ __forceinline__ void q_epilogue_pass(const PairParams& p, const TileX
                       (row & 7) * 16;
   {
     uint4 gh[CPT / 8];
-    if (p.debug & 4) {
-#pragma unroll
-      for (int q = 0; q < CPT / 8; ++q) gh[q] = make_uint4(0, 0, 0, 0);
-    } else {
-      coalesced_load(gh, p.out_hi, g, lane);
-    }
-    if (valid && !(p.debug & 8)) {
+    coalesced_load(gh, p.out_hi, g, lane);
+    if (valid) {
 #pragma unroll
       for (int q = 0; q < CPT / 16; ++q) lq[q] = *reinterpret_cast<const uint4*>(qp + q * 128);
     } else {
@@ -315,12 +308,7 @@ __device__ __forceinline__ void q_epilogue_pass(const PairParams& p, const TileX
       if (lane < 4 * QL && tn.b < p.n && ny < p.H)
         prefetch_l2(p.xq + ((((long long)tn.b * p.H + ny) * p.tiles_x + tn.tx) * (Cfg::CH / 16) + chan0 / 16 + (lane % QL)) * 128);
     }
-    if (p.debug & 32) {
-#pragma unroll
-      for (int q = 0; q < CPT / 8; ++q) vh[q] = gh[q];
-    } else {
-      staged_gather(stg, gh, vh, lane);
-    }
+    staged_gather(stg, gh, vh, lane);
   }
   uint4 vl[LAST ? CPT / 8 : 1];
   if (full != nullptr) {
@@ -365,19 +353,138 @@ __device__ __forceinline__ void q_epilogue_pass(const PairParams& p, const TileX
     if (lane == 0) mbar_arrive_leader(empty);
   }
   if constexpr (!LAST) {
-    if (valid && !(p.debug & 8)) {
+    if (valid) {
 #pragma unroll
       for (int q = 0; q < CPT / 16; ++q) *reinterpret_cast<uint4*>(qp + q * 128) = lq[q];
     }
   }
-  if (!(p.debug & 16)) staged_store(stg, vh, p.out_hi, g, lane);
+  staged_store(stg, vh, p.out_hi, g, lane);
   if constexpr (LAST) staged_store(stg, vl, p.out_lo, g, lane);
+}
+
+// ---- x_hi tiles through the async proxy (PairCfg::XT) ------------------------------------------------------------
+// An epilogue warp's 32 pixels (4 image rows x 8 pixels of the tile) x 64 channels are one TMA box {64 ch, 8 px, 4 rows, 1}
+// of the NHWC fp16 tensor = 4 KB of shared memory in the 128-byte-swizzled layout: pixel r (= lane) at r * 128, its 16-byte
+// chunk q at ((q ^ (r & 7)) * 16) -- a quarter warp touches eight different chunks, so thread = pixel LDS.128 / STS.128
+// are conflict-free.  Out-of-patch rows / pixels are zero-filled by the load and clipped by the store.
+__device__ __forceinline__ uint32_t xt_off(int lane, int q) { return (uint32_t)(lane * 128 + ((q ^ (lane & 7)) << 4)); }
+
+// registers (thread = pixel, 64 channels) -> the warp's tile -> global, one TMA store issued by lane 0
+__device__ __forceinline__ void xt_store(uint32_t xt, const uint4 (&v)[8], const CUtensorMap* m, int c0, int x0, int y0, int b,
+                                         int lane) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) sts128(xt + xt_off(lane, q), v[q]);
+  fence_proxy_async_smem();                         // generic-proxy writes -> visible to the TMA engine
+  __syncwarp();
+  if (lane == 0) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)), "r"(xt), "r"(c0), "r"(x0), "r"(y0), "r"(b)
+                 : "memory");
+    tma_store_commit();
+  }
+}
+// lane 0: the TMA engine has read the tile (it may be overwritten); then, optionally, fetch the next tile's box into it
+__device__ __forceinline__ void xt_release_and_fetch(uint32_t xt, const CUtensorMap* m, uint64_t* bar, bool fetch, int c0, int x0,
+                                                     int y0, int b, int lane) {
+  if (lane == 0) {
+    tma_store_wait_read<0>();
+    if (fetch) {
+      mbar_expect_tx(bar, 4096);
+      asm volatile(
+          "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+          ::"r"(xt), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(x0), "r"(y0), "r"(b)
+          : "memory");
+    }
+  }
+  __syncwarp();
+}
+
+// RESIDUALQ / RESIDUALQ-last epilogue of one tile for one warp, x_hi in and out through the warp's TMA tile (128 features:
+// a thread owns 64 channels = one pass).  Same arithmetic as q_epilogue_pass; the residual arrives by a TMA load issued one
+// tile ahead (as soon as the previous store has been read out of the buffer) and the new x_hi leaves by a TMA store, in place
+// (this kernel's activation TMA reads t, never x_hi).  Measured against two alternatives on full tiles: LSU
+// loads / stores through the transposing 1 KB buffer (q_epilogue_pass) and register-prefetched LSU loads + TMA store.
+template <class Cfg>
+__device__ __forceinline__ void q_epilogue_xt(const PairParams& p, const CUtensorMap* tm_xhi, const CUtensorMap* tm_xlo,
+                                              const TileXY& tc, const TileXY& tn, bool has_next, int wq, int chan0, int lane,
+                                              int row, bool valid, uint32_t xt, uint64_t* xbar, uint32_t xphase, uint32_t taddr,
+                                              uint32_t s_bias_addr, uint64_t* full, uint32_t full_phase, uint64_t* empty) {
+  constexpr bool LAST = Cfg::EPI == kEpiResidualQLast;
+  static_assert(Cfg::CH == 128 && !Cfg::SPLIT, "XT Q-trunk epilogue: 128 features, 64 channels per thread");
+  const int y = tc.ty * 16 + (row >> 3);
+  uint4 vh[8], lq[4];
+  uint8_t* const qp = p.xq + ((((long long)tc.b * p.H + y) * p.tiles_x + tc.tx) * (Cfg::CH / 16) + chan0 / 16) * 128 +
+                      (row & 7) * 16;
+  if (valid) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) lq[q] = *reinterpret_cast<const uint4*>(qp + q * 128);
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) lq[q] = make_uint4(0, 0, 0, 0);
+  }
+  if (has_next) {                                            // the next tile's byte lines -> L2 (4 rows x 4 lines per warp)
+    const int ny = tn.ty * 16 + wq * 4 + lane / 4;
+    if (lane < 16 && tn.b < p.n && ny < p.H)
+      prefetch_l2(p.xq + ((((long long)tn.b * p.H + ny) * p.tiles_x + tn.tx) * (Cfg::CH / 16) + chan0 / 16 + (lane % 4)) * 128);
+  }
+  mbar_wait(xbar, xphase);                                   // the residual tile has landed
+#pragma unroll
+  for (int q = 0; q < 8; ++q) vh[q] = lds128(xt + xt_off(lane, q));
+  uint4 vl[LAST ? 8 : 1];
+  mbar_wait(full, full_phase);
+  tc_fence_after();
+#pragma unroll
+  for (int chunk = 0; chunk < 2; ++chunk) {
+    const int c0 = chan0 + chunk * 32;
+    uint32_t r[32];
+    tmem_ld_32x32(taddr + c0, r);
+    tmem_ld_wait();
+    uint32_t* hw = reinterpret_cast<uint32_t*>(vh) + chunk * 16;
+    uint32_t* qw = reinterpret_cast<uint32_t*>(lq) + chunk * 8;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 bq = lds_f4(s_bias_addr + (uint32_t)(c0 + j) * 4);   // broadcast LDS.128
+      const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&hw[j >> 1]));
+      const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&hw[(j >> 1) + 1]));
+      const uint32_t w = qw[j >> 2];
+      const float x0 = fmaf(__uint_as_float(r[j]) + bq.x, p.res_scale, q_decode(f01.x, sext_byte<0>(w)));
+      const float x1 = fmaf(__uint_as_float(r[j + 1]) + bq.y, p.res_scale, q_decode(f01.y, sext_byte<1>(w)));
+      const float x2 = fmaf(__uint_as_float(r[j + 2]) + bq.z, p.res_scale, q_decode(f23.x, sext_byte<2>(w)));
+      const float x3 = fmaf(__uint_as_float(r[j + 3]) + bq.w, p.res_scale, q_decode(f23.y, sext_byte<3>(w)));
+      if constexpr (LAST) {
+        const __half2 h0 = __floats2half2_rn(x0, x1), h1 = __floats2half2_rn(x2, x3);
+        const float2 g0 = __half22float2(h0), g1 = __half22float2(h1);
+        const __half2 l0 = __floats2half2_rn(x0 - g0.x, x1 - g0.y), l1 = __floats2half2_rn(x2 - g1.x, x3 - g1.y);
+        uint32_t* lw = reinterpret_cast<uint32_t*>(vl) + chunk * 16;
+        hw[j >> 1] = *reinterpret_cast<const uint32_t*>(&h0);
+        hw[(j >> 1) + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+        lw[j >> 1] = *reinterpret_cast<const uint32_t*>(&l0);
+        lw[(j >> 1) + 1] = *reinterpret_cast<const uint32_t*>(&l1);
+      } else {
+        q_encode4(x0, x1, x2, x3, hw[j >> 1], hw[(j >> 1) + 1], qw[j >> 2]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive_leader(empty);
+  const int gx = tc.tx * 8, gy = tc.ty * 16 + wq * 4;
+  xt_store(xt, vh, tm_xhi, chan0, gx, gy, tc.b, lane);
+  if constexpr (LAST) {
+    xt_release_and_fetch(xt, tm_xhi, xbar, false, 0, 0, 0, 0, lane);
+    xt_store(xt, vl, tm_xlo, chan0, gx, gy, tc.b, lane);        // x_lo = fp16(x - x_hi): the last layer's split operand
+  } else if (valid) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(qp + q * 128) = lq[q];
+  }
+  xt_release_and_fetch(xt, tm_xhi, xbar, has_next, chan0, tn.tx * 8, tn.ty * 16 + wq * 4, tn.b, lane);
 }
 
 template <class Cfg>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg::THREADS, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
-                 const __grid_constant__ CUtensorMap tm_w, const PairParams p) {
+                 const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x0,
+                 const __grid_constant__ CUtensorMap tm_x1, const PairParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* s_w = smem;
@@ -391,6 +498,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   uint64_t* wr_full = tmem_empty + 3;                          // streamed-weight ring: leader's copies are live
   uint64_t* wr_empty = wr_full + Cfg::WSTAGES;                 // per CTA (multicast commit)
+  uint64_t* xfull = wr_empty + Cfg::WSTAGES;                   // per epilogue warp: its x_hi tile has landed (XT)
   float* s_bias = reinterpret_cast<float*>(bar_base + 512);
   const uint32_t s_bias_addr = smem_u32(s_bias);
   uint8_t* s_stg = bar_base + Cfg::BAR_BYTES;
@@ -406,6 +514,11 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
     tma_prefetch_desc(&tm_a0);
     if (Cfg::NMAPS == 2) tma_prefetch_desc(&tm_a1);
     tma_prefetch_desc(&tm_w);
+    if (Cfg::XT) {
+      tma_prefetch_desc(&tm_x0);
+      if (Cfg::EPI == kEpiResidualQLast) tma_prefetch_desc(&tm_x1);
+      for (int i = 0; i < Cfg::EPI_WARPS; ++i) mbar_init(&xfull[i], 1);
+    }
     for (int i = 0; i < Cfg::STAGES; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
@@ -445,23 +558,12 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
         const TileXY t = decode_tile(2 * pt + rank, p.tiles_x, p.tiles_y);
         const int b = t.b;
         const int bx = (t.tx + p.tx0) * 8 - (Cfg::NTAPS == 9 ? 1 : 0), by = t.ty * 16 - 1;
-        if (p.pf_a > 0 && pt + p.pf_a * npairs < pair_tiles && !(p.debug & 2)) {   // warm L2 for a tile this CTA loads later
-          const TileXY tn = decode_tile(2 * (pt + p.pf_a * npairs) + rank, p.tiles_x, p.tiles_y);
-#pragma unroll
-          for (int kb = 0; kb < Cfg::KB; ++kb)
-            tma_prefetch_4d((Cfg::NMAPS == 2 && kb >= Cfg::KPM) ? &tm_a1 : &tm_a0, (kb % Cfg::KPM) * Cfg::KCH,
-                            (tn.tx + p.tx0) * 8 - (Cfg::NTAPS == 9 ? 1 : 0), tn.ty * 16 - 1, tn.b);
-        }
 #pragma unroll 1
         for (int kb = 0; kb < Cfg::KB; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          if (p.debug & 2) {                         // MMA-rate experiment: stale smem, no loads
-            if (rank == 0) mbar_arrive(&full[stage]);
-          } else {
-            if (rank == 0) mbar_expect_tx(&full[stage], 2 * Cfg::BOX_BYTES);
-            const CUtensorMap* m = (Cfg::NMAPS == 2 && kb >= Cfg::KPM) ? &tm_a1 : &tm_a0;
-            tma_load_4d_pair(s_a + stage * Cfg::STAGE_BYTES, m, &full[stage], (kb % Cfg::KPM) * Cfg::KCH, bx, by, b);
-          }
+          if (rank == 0) mbar_expect_tx(&full[stage], 2 * Cfg::BOX_BYTES);
+          const CUtensorMap* m = (Cfg::NMAPS == 2 && kb >= Cfg::KPM) ? &tm_a1 : &tm_a0;
+          tma_load_4d_pair(s_a + stage * Cfg::STAGE_BYTES, m, &full[stage], (kb % Cfg::KPM) * Cfg::KCH, bx, by, b);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
           if constexpr (!Cfg::RESIDENT) {            // this k-block's nine weight slabs, in the order the MMAs use them
 #pragma unroll 1
@@ -494,7 +596,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * Cfg::NTOT);
 #pragma unroll 1
         for (int kb = 0; kb < Cfg::KB; ++kb) {
-          if (!(p.debug & 64)) mbar_wait(&full[stage], phase);   // 64: latency experiment, MMAs never wait for the loads
+          mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(s_a + stage * Cfg::STAGE_BYTES);
           const uint32_t sb = smem_u32(s_w) + (uint32_t)((kb % Cfg::KPM) * Cfg::SLAB_BYTES);
@@ -546,16 +648,17 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
     const int row = wq * 32 + lane;                // tile row = group * 8 + pixel
     int acc = 0;
     uint32_t acc_phase = 0;
-    // RESIDUAL32: the fp16 copy of tile i is written out while tile i+1's trunk loads are in flight
-    uint4 vh_prev[8];
-    EpiGeom g_prev;
-    bool have_prev = false;
-    // current tile and the tile whose epilogue operands are prefetched into L2 (pf_dist iterations ahead)
+    // current tile and this CTA's next one (whose epilogue operands are prefetched into L2 / loaded by TMA)
     const TileXY tstep = decode_tile(2 * npairs, p.tiles_x, p.tiles_y);
-    const uint32_t pf_dist = (Cfg::EPI == kEpiResidual32 || Cfg::EPI == kEpiResidualQ || Cfg::EPI == kEpiResidualQLast)
-                                 ? (uint32_t)max(p.pf_x, 1) : 1u;
     TileXY tci = decode_tile(2 * pair + rank, p.tiles_x, p.tiles_y);
-    TileXY tni = decode_tile(2 * (pair + pf_dist * npairs) + rank, p.tiles_x, p.tiles_y);
+    TileXY tni = decode_tile(2 * (pair + npairs) + rank, p.tiles_x, p.tiles_y);     // this CTA's next tile
+    const uint32_t xt = smem_u32(s_stg) + (uint32_t)(warp * 4096);                  // XT: this warp's x_hi tile
+    uint32_t xphase = 0;
+    if constexpr (Cfg::XT && (Cfg::EPI == kEpiResidualQ || Cfg::EPI == kEpiResidualQLast)) {
+      // residual of the first tile (nothing to release yet: wait_group.read returns at once)
+      xt_release_and_fetch(xt, &tm_x0, &xfull[warp], pair < pair_tiles, half * (Cfg::CH / 2), (tci.tx + p.tx0) * 8,
+                           tci.ty * 16 + wq * 4, tci.b, lane);
+    }
     for (uint32_t pt = pair; pt < pair_tiles;
          pt += npairs, advance_tile(tci, tstep, p.tiles_x, p.tiles_y), advance_tile(tni, tstep, p.tiles_x, p.tiles_y)) {
       const TileXY tc = {tci.b, tci.ty, tci.tx + p.tx0}, tn = {tni.b, tni.ty, tni.tx + p.tx0};   // in patch tile coordinates
@@ -565,16 +668,6 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
       const bool valid = (b < p.n) && (y < p.H) && (x < p.W);
       const long long pix = ((long long)b * p.H + y) * p.W + x;
       const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * Cfg::NTOT);
-      if (p.debug & 1) {                             // MMA-rate experiment: no epilogue work at all
-        mbar_wait(&tmem_full[acc], acc_phase);
-        tc_fence_after();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-        continue;
-      }
-
       if constexpr (Cfg::EPI == kEpiTail) {
         // ------------------------------------------------------------------ tail: skip + scale + stitch
         float skip[16];
@@ -634,14 +727,14 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
         float* xp = p.x32 + ((((long long)b * p.H + y) * p.tiles_x + tc.tx) * (Cfg::CH / 4) + half * (CPT / 4)) * cpitch +
                     (row & 7) * 4;
         float4 xr[CPT / 4];
-        if (valid && !(p.debug & 4)) {
+        if (valid) {
 #pragma unroll
           for (int q = 0; q < CPT / 4; ++q) xr[q] = *reinterpret_cast<const float4*>(xp + q * cpitch);
         } else {
 #pragma unroll
           for (int q = 0; q < CPT / 4; ++q) xr[q] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        if (p.pf_x > 0 && pt + p.pf_x * npairs < pair_tiles) {   // a later tile's trunk lines -> L2 (64 lines per warp, 2 per lane)
+        if (pt + npairs < pair_tiles) {   // the next tile's trunk lines -> L2 (64 lines per warp, 2 per lane)
           const int ny = tn.ty * 16 + wq * 4 + (lane >> 3);
           if (tn.b < p.n && ny < p.H) {
             const float* np = p.x32 + ((((long long)tn.b * p.H + ny) * p.tiles_x + tn.tx) * (Cfg::CH / 4) + half * (CPT / 4) +
@@ -650,10 +743,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
             prefetch_l2(np + cpitch);
           }
         }
-        if (have_prev) staged_store(stg, vh_prev, p.out_hi, g_prev, lane);   // overlaps the loads issued above
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
-        uint4 (&vh)[8] = vh_prev;
+        uint4 vh[8];
 #pragma unroll
         for (int chunk = 0; chunk < CPT / 32; ++chunk) {
           const int c0 = half * CPT + chunk * 32;
@@ -677,18 +769,11 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
-        if (valid && !(p.debug & 8)) {
+        if (valid) {
 #pragma unroll
           for (int q = 0; q < CPT / 4; ++q) *reinterpret_cast<float4*>(xp + q * cpitch) = xr[q];
         }
-        g_prev = g;
-        have_prev = true;
-        if (p.debug & 16) {
-          have_prev = false;
-        } else if (!p.defer || p.out_lo != nullptr) {
-          staged_store(stg, vh, p.out_hi, g, lane);
-          have_prev = false;
-        }
+        staged_store(stg, vh, p.out_hi, g, lane);
         if (p.out_lo != nullptr) {                  // last resblock only: the tail's split operand needs x - fp16(x)
           uint32_t* lw = reinterpret_cast<uint32_t*>(vh);
 #pragma unroll
@@ -707,13 +792,19 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
         // ------------------------------------------------------------------ resblock output, fp16 + 8 bit trunk
         // a thread owns CH / 2 channels of its pixel: one pass of 64 (128 features) or two (256)
         constexpr int CPT = Cfg::CH / 2;
-        const bool pf = p.pf_x > 0 && pt + p.pf_x * npairs < pair_tiles;
+        const bool pf = pt + npairs < pair_tiles;
+        if constexpr (Cfg::XT) {
+          q_epilogue_xt<Cfg>(p, &tm_x0, &tm_x1, tc, tn, pf, wq, half * CPT, lane, row, valid, xt, &xfull[warp], xphase, taddr,
+                             s_bias_addr, &tmem_full[acc], acc_phase, &tmem_empty[acc]);
+          xphase ^= 1;
+        } else {
 #pragma unroll 1
-        for (int sc = 0; sc < CPT / 64; ++sc)
-          q_epilogue_pass<Cfg, 64>(p, tc, tn, pf, wq, half * CPT + sc * 64, lane, row, valid,
-                                   smem_u32(s_stg) + (uint32_t)(warp * 1024), taddr, s_bias_addr,
-                                   sc == 0 ? &tmem_full[acc] : nullptr, acc_phase,
-                                   sc == CPT / 64 - 1 ? &tmem_empty[acc] : nullptr);
+          for (int sc = 0; sc < CPT / 64; ++sc)
+            q_epilogue_pass<Cfg, 64>(p, tc, tn, pf, wq, half * CPT + sc * 64, lane, row, valid,
+                                     smem_u32(s_stg) + (uint32_t)(warp * 1024), taddr, s_bias_addr,
+                                     sc == 0 ? &tmem_full[acc] : nullptr, acc_phase,
+                                     sc == CPT / 64 - 1 ? &tmem_empty[acc] : nullptr);
+        }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         continue;
       } else if constexpr (Cfg::EPI == kEpiHeadQ) {
@@ -758,7 +849,12 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
 #pragma unroll
             for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(qp + q * 128) = lq[q];
           }
-          staged_store(stg, vh, p.out_hi, g, lane);
+          if constexpr (Cfg::XT) {
+            xt_release_and_fetch(xt, &tm_x0, nullptr, false, 0, 0, 0, 0, lane);   // the previous store has left the tile
+            xt_store(xt, vh, &tm_x0, cb, tc.tx * 8, tc.ty * 16 + wq * 4, b, lane);
+          } else {
+            staged_store(stg, vh, p.out_hi, g, lane);
+          }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         continue;
@@ -870,11 +966,11 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
       if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if constexpr (Cfg::EPI == kEpiResidual32) {
-      if (have_prev) staged_store(smem_u32(s_stg) + (uint32_t)(warp * 1024), vh_prev, p.out_hi, g_prev, lane);
-    }
   }
 
+  if constexpr (Cfg::XT) {
+    if (warp < Cfg::EPI_WARPS && lane == 0) tma_store_wait_all<0>();   // the last tile's store has left shared memory
+  }
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();            // nobody leaves while the peer may still signal it or read its smem
@@ -889,8 +985,10 @@ using CfgRelu = PairCfg<128, kSplitNone, 1, 2, 9, 4, 3, kEpiRelu>;
 using CfgResidual = PairCfg<128, kSplitNone, 1, 2, 9, 4, 3, kEpiResidual>;
 using CfgResidual32 = PairCfg<128, kSplitNone, 1, 2, 9, 4, 3, kEpiResidual32>;
 using CfgMask = PairCfg<128, kSplitNone, 1, 2, 9, 4, 3, kEpiMask>;
-using CfgResidualQ = PairCfg<128, kSplitNone, 1, 2, 9, 4, 3, kEpiResidualQ>;
-using CfgResidualQLast = PairCfg<128, kSplitNone, 1, 2, 9, 4, 3, kEpiResidualQLast>;
+// fp16 + 8 bit trunk update: epilogue-bound, not load-bound -- two activation stages are enough (measured: 3 -> 2 stages costs
+// the RELU layer 9 % and this one nothing), which frees the shared memory for the eight 4 KB x_hi tiles of the XT epilogue
+using CfgResidualQ = PairCfg<128, kSplitNone, 1, 2, 9, 4, 2, kEpiResidualQ, 0, 128, true>;
+using CfgResidualQLast = PairCfg<128, kSplitNone, 1, 2, 9, 4, 2, kEpiResidualQLast, 0, 128, true>;
 // VDSen2 trunk (256 -> 256): 1.18 MB of weights per layer cannot be resident -- ring of 8 streamed [tap][k-block] slabs
 using CfgRelu256 = PairCfg<256, kSplitNone, 1, 4, 9, 4, 3, kEpiRelu, 8>;
 using CfgResidual256 = PairCfg<256, kSplitNone, 1, 4, 9, 4, 3, kEpiResidual, 8>;
@@ -899,14 +997,17 @@ using CfgResidualQLast256 = PairCfg<256, kSplitNone, 1, 4, 9, 4, 3, kEpiResidual
 using CfgHead = PairCfg<256, kSplitStack, 2, 1, 3, 3, 6, kEpiRelu>;
 // first layer on the un-gathered 16-channel input: nine taps through shifted descriptors into a 32-byte-row halo box,
 // three products per tap into one accumulator (27 MMAs of N = F per tile pair)
-using CfgHead16 = PairCfg<128, kSplit3, 2, 1, 9, 1, 6, kEpiHeadQ, 0, 32>;
-using CfgHead16_256 = PairCfg<256, kSplit3, 2, 1, 9, 1, 6, kEpiHeadQ, 0, 32>;
+using CfgHead16 = PairCfg<128, kSplit3, 2, 1, 9, 1, 6, kEpiHeadQ, 0, 32, true>;
+using CfgHead16_256 = PairCfg<256, kSplit3, 2, 1, 9, 1, 6, kEpiHeadQ, 0, 32, true>;
 using CfgTail = PairCfg<32, kSplitStack, 2, 2, 9, 4, 6, kEpiTail>;
 using CfgTail256 = PairCfg<32, kSplitStack, 2, 4, 9, 4, 6, kEpiTail>;   // 256 -> cout: 8 k-blocks per tile, 72 KB of weights
 
+// x0 / x1: tensor maps of the epilogue's x_hi / x_lo tiles (PairCfg::XT kernels only)
 template <class Cfg>
 static int launch_pair(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const PairParams& p,
-                       int sms, cudaStream_t stream, const char* what) {
+                       int sms, cudaStream_t stream, const char* what, const CUtensorMap* x0 = nullptr,
+                       const CUtensorMap* x1 = nullptr) {
+  DSEN2_REQUIRE(!Cfg::XT || x0 != nullptr, DSEN2_E_BADARG, "%s: internal error, epilogue tensor map missing", what);
   static bool configured[64] = {};
   if (needs_config(configured)) {
     DSEN2_CUDA(cudaFuncSetAttribute(conv_pair_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -915,7 +1016,7 @@ static int launch_pair(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
   const long long pair_tiles = ((long long)p.num_tiles + 1) / 2;
   const long long max_pairs = sms / 2;
   const int pairs = (int)(pair_tiles < max_pairs ? pair_tiles : max_pairs);
-  conv_pair_kernel<Cfg><<<2 * pairs, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(a0, a1, w, p);
+  conv_pair_kernel<Cfg><<<2 * pairs, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(a0, a1, w, x0 ? *x0 : a0, x1 ? *x1 : (x0 ? *x0 : a0), p);
   return check_launch(what);
 }
 
@@ -934,12 +1035,14 @@ static int make_maps(CUtensorMap* a0, CUtensorMap* a1, CUtensorMap* w, const voi
   return make_tmap_f16_sw(w, d_w, 3, wd, wb, Cfg::ROWB);
 }
 
+// epilogue tile map of an NHWC fp16 tensor (n, H, W, C): box = 64 channels x 8 pixels x 4 rows (one warp's share of a tile)
+static int make_xt_map(CUtensorMap* m, const void* d_x, int n, int H, int W, int C) {
+  const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)n};
+  const uint32_t box[4] = {64, 8, 4, 1};
+  return make_tmap_f16_sw(m, d_x, 4, dims, box, 128);
+}
+
 static int fill_tiles(PairParams& p, int n, int H, int W) {
-  static const int dbg = getenv("DSEN2_PAIR_DEBUG") ? atoi(getenv("DSEN2_PAIR_DEBUG")) : 0;
-  static const int pf_a = getenv("DSEN2_PAIR_PF_A") ? atoi(getenv("DSEN2_PAIR_PF_A")) : kPrefetchTiles;
-  static const int pf_x = getenv("DSEN2_PAIR_PF_X") ? atoi(getenv("DSEN2_PAIR_PF_X")) : kTrunkPrefetchTiles;
-  static const int defer = getenv("DSEN2_PAIR_DEFER") ? atoi(getenv("DSEN2_PAIR_DEFER")) : 0;
-  p.debug = dbg; p.pf_a = pf_a; p.pf_x = pf_x; p.defer = defer;
   p.n = n; p.H = H; p.W = W;
   p.tiles_x = ceil_div(W, 8);
   p.tiles_y = ceil_div(H, 16);
@@ -1048,7 +1151,9 @@ static int head_common(const char* name, const void* d_xin_hi, const void* d_xin
   CUtensorMap a0, a1, w;
   rc = make_maps<CfgH>(&a0, &a1, &w, d_xin_hi, d_xin_lo, d_w, n, H, W);
   if (rc) return rc;
-  return launch_pair<CfgH>(a0, a1, w, p, sms, (cudaStream_t)stream, name);
+  CUtensorMap x0;
+  if (CfgH::XT && (rc = make_xt_map(&x0, d_out_hi, n, H, W, CfgH::CH)) != 0) return rc;
+  return launch_pair<CfgH>(a0, a1, w, p, sms, (cudaStream_t)stream, name, CfgH::XT ? &x0 : nullptr);
 }
 
 extern "C" int dsen2_conv_head(const void* d_xin_hi, const void* d_xin_lo, const void* d_w, const float* d_bias,
@@ -1099,8 +1204,13 @@ static int resq_common(int features, const void* d_in, const void* d_w, const fl
   }
   rc = make_maps<CfgResidualQ>(&a0, &a1, &w, d_in, nullptr, d_w, n, H, W);
   if (rc) return rc;
-  if (d_out_lo) return launch_pair<CfgResidualQLast>(a0, a1, w, p, sms, (cudaStream_t)stream, "conv_pair<residualq,last>");
-  return launch_pair<CfgResidualQ>(a0, a1, w, p, sms, (cudaStream_t)stream, "conv_pair<residualq>");
+  CUtensorMap x0, x1;
+  if ((rc = make_xt_map(&x0, d_x_hi, n, H, W, 128)) != 0) return rc;
+  if (d_out_lo) {
+    if ((rc = make_xt_map(&x1, d_out_lo, n, H, W, 128)) != 0) return rc;
+    return launch_pair<CfgResidualQLast>(a0, a1, w, p, sms, (cudaStream_t)stream, "conv_pair<residualq,last>", &x0, &x1);
+  }
+  return launch_pair<CfgResidualQ>(a0, a1, w, p, sms, (cudaStream_t)stream, "conv_pair<residualq>", &x0);
 }
 
 extern "C" int dsen2_conv_resq(const void* d_in, const void* d_w, const float* d_bias, int n, int H, int W,

@@ -407,8 +407,6 @@ extern "C" int dsen2_conv3x3(const void* d_in, const void* d_w, const float* d_b
 // ------------------------------------------------------------------------------------------ //
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-static int head_k_pad(int in_channels) { return (9 * in_channels + 63) / 64 * 64; }
-
 extern "C" size_t dsen2_s2model_workspace_bytes(int n, int P, int in_channels, int feature_size) {
   if (n <= 0 || P <= 0 || in_channels <= 0 || feature_size <= 0) return 0;
   const size_t pix = (size_t)n * P * P;

@@ -73,9 +73,9 @@ struct PairParams {
 template <int NTOT_, int SPLIT_, int NMAPS_, int KPM_, int NTAPS_, int KSTEPS_, int STAGES_, int EPI_, int WSTAGES_ = 0,
           int ROWB_ = 128, bool XT_ = false>
 struct PairCfg {
-  // XT: the epilogue moves its x_hi tiles through the async proxy -- every epilogue warp owns a 4 KB shared-memory tile
-  // ([4 rows x 8 pixels][64 channels], 128-byte swizzled = TMA box {64, 8, 4, 1} of the NHWC tensor) that a TMA load fills
-  // with the residual and a TMA store writes back in place, instead of LSU loads / stores through a transposing 1 KB buffer
+  // XT: the epilogue moves its x_hi tiles through the async proxy -- every epilogue warp owns 4 KB of shared memory holding
+  // its 4 rows x 8 pixels x 64 channels in the layout TMA boxes of the NHWC tensor produce; TMA loads bring the residual,
+  // TMA stores write the result back in place, instead of LSU loads / stores through a transposing 1 KB buffer
   static constexpr bool XT = XT_;
   static constexpr int ROWB = ROWB_;            // bytes per pixel row of a k-block in smem = swizzle span (128: 64 ch, 32: 16 ch)
   static constexpr int KCH = ROWB_ / 2;         // channels per k-block
@@ -114,7 +114,7 @@ struct PairCfg {
   static_assert(W_BYTES % 1024 == 0, "weight slabs must keep the stages 1024-byte aligned");
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM allocation must be a power of two <= 512");
   static_assert(CH * 4 + 512 <= BAR_BYTES, "bias does not fit next to the barriers");
-  static_assert((2 * STAGES_ + 6 + 2 * WSTAGES_ + EPI_WARPS) * 8 <= 512, "too many barriers");
+  static_assert((2 * STAGES_ + 6 + 2 * WSTAGES_ + 2 * EPI_WARPS) * 8 <= 512, "too many barriers");
 };
 
 // tile index -> (patch, tile row, tile column); 32-bit arithmetic (64-bit divisions cost ~100 instructions each)
@@ -383,36 +383,56 @@ __device__ __forceinline__ void xt_store(uint32_t xt, const uint4 (&v)[8], const
     tma_store_commit();
   }
 }
-// lane 0: the TMA engine has read the tile (it may be overwritten); then, optionally, fetch the next tile's box into it
-__device__ __forceinline__ void xt_release_and_fetch(uint32_t xt, const CUtensorMap* m, uint64_t* bar, bool fetch, int c0, int x0,
-                                                     int y0, int b, int lane) {
-  if (lane == 0) {
-    tma_store_wait_read<0>();
-    if (fetch) {
-      mbar_expect_tx(bar, 4096);
-      asm volatile(
-          "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-          ::"r"(xt), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(x0), "r"(y0), "r"(b)
-          : "memory");
-    }
-  }
+// the TMA engine has read the warp's tile out of shared memory (all but the N most recent stores): it may be overwritten
+template <int N>
+__device__ __forceinline__ void xt_release(int lane) {
+  if (lane == 0) tma_store_wait_read<N>();
   __syncwarp();
 }
 
-// RESIDUALQ / RESIDUALQ-last epilogue of one tile for one warp, x_hi in and out through the warp's TMA tile (128 features:
-// a thread owns 64 channels = one pass).  Same arithmetic as q_epilogue_pass; the residual arrives by a TMA load issued one
-// tile ahead (as soon as the previous store has been read out of the buffer) and the new x_hi leaves by a TMA store, in place
-// (this kernel's activation TMA reads t, never x_hi).  Measured against two alternatives on full tiles: LSU
-// loads / stores through the transposing 1 KB buffer (q_epilogue_pass) and register-prefetched LSU loads + TMA store.
+// Half tiles: 32 pixels x 32 channels = TMA box {32 ch, 8 px, 4 rows, 1}, 2 KB, 64-byte rows in the 64-byte-swizzled layout
+// (16-byte chunk q of pixel r at r * 64 + ((q ^ ((r >> 1) & 3)) * 16): conflict-free thread = pixel access again).
+__device__ __forceinline__ uint32_t xh_off(int lane, int q) { return (uint32_t)(lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)); }
+__device__ __forceinline__ void xh_fetch(uint32_t xh, const CUtensorMap* m, uint64_t* bar, int c0, int x0, int y0, int b) {
+  mbar_expect_tx(bar, 2048);
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(xh), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(x0), "r"(y0), "r"(b)
+      : "memory");
+}
+__device__ __forceinline__ void xh_store(uint32_t xh, const uint4 (&v)[4], const CUtensorMap* m, int c0, int x0, int y0, int b,
+                                         int lane) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) sts128(xh + xh_off(lane, q), v[q]);
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)), "r"(xh), "r"(c0), "r"(x0), "r"(y0), "r"(b)
+                 : "memory");
+    tma_store_commit();
+  }
+}
+
+// RESIDUALQ / RESIDUALQ-last epilogue of one tile for one warp (128 features: a thread owns 64 channels), x_hi in and out
+// through the async proxy.  Same arithmetic as q_epilogue_pass.  The warp's 4 KB of shared memory are two half tiles A, B
+// (channels 0..31 / 32..63 of its 64 = the two 32-column TMEM reads); each is filled by a TMA load of the residual, updated
+// in place by its threads and written back by a TMA store (in place in global memory too: this kernel's activation TMA
+// reads t, never x_hi).  The halves ping-pong so that nobody waits for the TMA engine: while half A of tile i is being
+// updated, B's store of tile i-1 is awaited and B(i) fetched; while B(i) is updated, A's store is awaited and A(i+1)
+// fetched.  (With ONE 4 KB tile per warp -- store, wait, load, wait -- 40 % of the epilogue warps' samples sat on those
+// two waits, profiles/r02_whole_batch_xt1_ncu.txt.)
 template <class Cfg>
 __device__ __forceinline__ void q_epilogue_xt(const PairParams& p, const CUtensorMap* tm_xhi, const CUtensorMap* tm_xlo,
-                                              const TileXY& tc, const TileXY& tn, bool has_next, int wq, int chan0, int lane,
-                                              int row, bool valid, uint32_t xt, uint64_t* xbar, uint32_t xphase, uint32_t taddr,
-                                              uint32_t s_bias_addr, uint64_t* full, uint32_t full_phase, uint64_t* empty) {
+                                              const TileXY& tc, const TileXY& tn, bool first, bool has_next, int wq, int chan0,
+                                              int lane, int row, bool valid, uint32_t xt, uint64_t* xbar, uint32_t xphase,
+                                              uint32_t taddr, uint32_t s_bias_addr, uint64_t* full, uint32_t full_phase,
+                                              uint64_t* empty) {
   constexpr bool LAST = Cfg::EPI == kEpiResidualQLast;
   static_assert(Cfg::CH == 128 && !Cfg::SPLIT, "XT Q-trunk epilogue: 128 features, 64 channels per thread");
   const int y = tc.ty * 16 + (row >> 3);
-  uint4 vh[8], lq[4];
+  const int gx = tc.tx * 8, gy = tc.ty * 16 + wq * 4;
+  uint4 lq[4];
   uint8_t* const qp = p.xq + ((((long long)tc.b * p.H + y) * p.tiles_x + tc.tx) * (Cfg::CH / 16) + chan0 / 16) * 128 +
                       (row & 7) * 16;
   if (valid) {
@@ -427,22 +447,35 @@ __device__ __forceinline__ void q_epilogue_xt(const PairParams& p, const CUtenso
     if (lane < 16 && tn.b < p.n && ny < p.H)
       prefetch_l2(p.xq + ((((long long)tn.b * p.H + ny) * p.tiles_x + tn.tx) * (Cfg::CH / 16) + chan0 / 16 + (lane % 4)) * 128);
   }
-  mbar_wait(xbar, xphase);                                   // the residual tile has landed
 #pragma unroll
-  for (int q = 0; q < 8; ++q) vh[q] = lds128(xt + xt_off(lane, q));
-  uint4 vl[LAST ? 8 : 1];
-  mbar_wait(full, full_phase);
-  tc_fence_after();
+  for (int h = 0; h < 2; ++h) {
+    const uint32_t xh = xt + (uint32_t)(h * 2048);
+    const int c0 = chan0 + h * 32;
+    uint4 vh[4], vl[LAST ? 4 : 1];
+    mbar_wait(xbar + h, xphase);                             // this half of the residual has landed
 #pragma unroll
-  for (int chunk = 0; chunk < 2; ++chunk) {
-    const int c0 = chan0 + chunk * 32;
+    for (int q = 0; q < 4; ++q) vh[q] = lds128(xh + xh_off(lane, q));
+    if (h == 0) {
+      mbar_wait(full, full_phase);
+      tc_fence_after();
+    }
     uint32_t r[32];
     tmem_ld_32x32(taddr + c0, r);
     tmem_ld_wait();
-    uint32_t* hw = reinterpret_cast<uint32_t*>(vh) + chunk * 16;
-    uint32_t* qw = reinterpret_cast<uint32_t*>(lq) + chunk * 8;
+    uint32_t* hw = reinterpret_cast<uint32_t*>(vh);
+    uint32_t* qw = reinterpret_cast<uint32_t*>(lq) + h * 8;
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
+      if (j == 16 && lane == 0) {
+        // Half-way through this half's arithmetic the OTHER half's last store (issued ~half a tile period ago) has been
+        // read out of shared memory: fetch its next residual -- B of this tile while A is being updated, A of the next
+        // tile while B is.  (The first tile's B came with the prologue.)
+        if (h == 0 ? !first : has_next) {
+          tma_store_wait_read<0>();
+          if (h == 0) xh_fetch(xt + 2048, tm_xhi, xbar + 1, chan0 + 32, gx, gy, tc.b);
+          else xh_fetch(xt, tm_xhi, xbar, chan0, tn.tx * 8, tn.ty * 16 + wq * 4, tn.b);
+        }
+      }
       const float4 bq = lds_f4(s_bias_addr + (uint32_t)(c0 + j) * 4);   // broadcast LDS.128
       const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&hw[j >> 1]));
       const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&hw[(j >> 1) + 1]));
@@ -455,7 +488,7 @@ __device__ __forceinline__ void q_epilogue_xt(const PairParams& p, const CUtenso
         const __half2 h0 = __floats2half2_rn(x0, x1), h1 = __floats2half2_rn(x2, x3);
         const float2 g0 = __half22float2(h0), g1 = __half22float2(h1);
         const __half2 l0 = __floats2half2_rn(x0 - g0.x, x1 - g0.y), l1 = __floats2half2_rn(x2 - g1.x, x3 - g1.y);
-        uint32_t* lw = reinterpret_cast<uint32_t*>(vl) + chunk * 16;
+        uint32_t* lw = reinterpret_cast<uint32_t*>(vl);
         hw[j >> 1] = *reinterpret_cast<const uint32_t*>(&h0);
         hw[(j >> 1) + 1] = *reinterpret_cast<const uint32_t*>(&h1);
         lw[j >> 1] = *reinterpret_cast<const uint32_t*>(&l0);
@@ -464,20 +497,23 @@ __device__ __forceinline__ void q_epilogue_xt(const PairParams& p, const CUtenso
         q_encode4(x0, x1, x2, x3, hw[j >> 1], hw[(j >> 1) + 1], qw[j >> 2]);
       }
     }
+    if (h == 1) {                                            // the accumulator has been read: hand the TMEM buffer back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(empty);
+    }
+    xh_store(xh, vh, tm_xhi, c0, gx, gy, tc.b, lane);
+    if constexpr (LAST) {                                    // x_lo = fp16(x - x_hi): the last layer's split operand
+      xt_release<0>(lane);
+      xh_store(xh, vl, tm_xlo, c0, gx, gy, tc.b, lane);
+    }
   }
-  tc_fence_before();
-  __syncwarp();
-  if (lane == 0) mbar_arrive_leader(empty);
-  const int gx = tc.tx * 8, gy = tc.ty * 16 + wq * 4;
-  xt_store(xt, vh, tm_xhi, chan0, gx, gy, tc.b, lane);
-  if constexpr (LAST) {
-    xt_release_and_fetch(xt, tm_xhi, xbar, false, 0, 0, 0, 0, lane);
-    xt_store(xt, vl, tm_xlo, chan0, gx, gy, tc.b, lane);        // x_lo = fp16(x - x_hi): the last layer's split operand
-  } else if (valid) {
+  if constexpr (!LAST) {
+    if (valid) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(qp + q * 128) = lq[q];
+      for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(qp + q * 128) = lq[q];
+    }
   }
-  xt_release_and_fetch(xt, tm_xhi, xbar, has_next, chan0, tn.tx * 8, tn.ty * 16 + wq * 4, tn.b, lane);
 }
 
 template <class Cfg>
@@ -498,7 +534,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   uint64_t* wr_full = tmem_empty + 3;                          // streamed-weight ring: leader's copies are live
   uint64_t* wr_empty = wr_full + Cfg::WSTAGES;                 // per CTA (multicast commit)
-  uint64_t* xfull = wr_empty + Cfg::WSTAGES;                   // per epilogue warp: its x_hi tile has landed (XT)
+  uint64_t* xfull = wr_empty + Cfg::WSTAGES;                   // per epilogue warp and half: its x_hi half tile has landed (XT)
   float* s_bias = reinterpret_cast<float*>(bar_base + 512);
   const uint32_t s_bias_addr = smem_u32(s_bias);
   uint8_t* s_stg = bar_base + Cfg::BAR_BYTES;
@@ -517,7 +553,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
     if (Cfg::XT) {
       tma_prefetch_desc(&tm_x0);
       if (Cfg::EPI == kEpiResidualQLast) tma_prefetch_desc(&tm_x1);
-      for (int i = 0; i < Cfg::EPI_WARPS; ++i) mbar_init(&xfull[i], 1);
+      for (int i = 0; i < 2 * Cfg::EPI_WARPS; ++i) mbar_init(&xfull[i], 1);
     }
     for (int i = 0; i < Cfg::STAGES; ++i) {
       mbar_init(&full[i], 1);
@@ -655,9 +691,12 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
     const uint32_t xt = smem_u32(s_stg) + (uint32_t)(warp * 4096);                  // XT: this warp's x_hi tile
     uint32_t xphase = 0;
     if constexpr (Cfg::XT && (Cfg::EPI == kEpiResidualQ || Cfg::EPI == kEpiResidualQLast)) {
-      // residual of the first tile (nothing to release yet: wait_group.read returns at once)
-      xt_release_and_fetch(xt, &tm_x0, &xfull[warp], pair < pair_tiles, half * (Cfg::CH / 2), (tci.tx + p.tx0) * 8,
-                           tci.ty * 16 + wq * 4, tci.b, lane);
+      if (lane == 0 && pair < pair_tiles) {        // both halves of the first tile's residual
+        const int c0 = half * (Cfg::CH / 2), gx = (tci.tx + p.tx0) * 8, gy = tci.ty * 16 + wq * 4;
+        xh_fetch(xt, &tm_x0, &xfull[2 * warp], c0, gx, gy, tci.b);
+        xh_fetch(xt + 2048, &tm_x0, &xfull[2 * warp + 1], c0 + 32, gx, gy, tci.b);
+      }
+      __syncwarp();
     }
     for (uint32_t pt = pair; pt < pair_tiles;
          pt += npairs, advance_tile(tci, tstep, p.tiles_x, p.tiles_y), advance_tile(tni, tstep, p.tiles_x, p.tiles_y)) {
@@ -794,8 +833,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
         constexpr int CPT = Cfg::CH / 2;
         const bool pf = pt + npairs < pair_tiles;
         if constexpr (Cfg::XT) {
-          q_epilogue_xt<Cfg>(p, &tm_x0, &tm_x1, tc, tn, pf, wq, half * CPT, lane, row, valid, xt, &xfull[warp], xphase, taddr,
-                             s_bias_addr, &tmem_full[acc], acc_phase, &tmem_empty[acc]);
+          q_epilogue_xt<Cfg>(p, &tm_x0, &tm_x1, tc, tn, pt == pair, pf, wq, half * CPT, lane, row, valid, xt, &xfull[2 * warp],
+                             xphase, taddr, s_bias_addr, &tmem_full[acc], acc_phase, &tmem_empty[acc]);
           xphase ^= 1;
         } else {
 #pragma unroll 1
@@ -850,7 +889,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
             for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(qp + q * 128) = lq[q];
           }
           if constexpr (Cfg::XT) {
-            xt_release_and_fetch(xt, &tm_x0, nullptr, false, 0, 0, 0, 0, lane);   // the previous store has left the tile
+            xt_release<0>(lane);                                                    // the previous store has left the tile
             xt_store(xt, vh, &tm_x0, cb, tc.tx * 8, tc.ty * 16 + wq * 4, b, lane);
           } else {
             staged_store(stg, vh, p.out_hi, g, lane);
@@ -1035,11 +1074,12 @@ static int make_maps(CUtensorMap* a0, CUtensorMap* a1, CUtensorMap* w, const voi
   return make_tmap_f16_sw(w, d_w, 3, wd, wb, Cfg::ROWB);
 }
 
-// epilogue tile map of an NHWC fp16 tensor (n, H, W, C): box = 64 channels x 8 pixels x 4 rows (one warp's share of a tile)
-static int make_xt_map(CUtensorMap* m, const void* d_x, int n, int H, int W, int C) {
+// epilogue tile map of an NHWC fp16 tensor (n, H, W, C): box = box_ch (64 or 32) channels x 8 pixels x 4 rows (one warp's
+// share of a tile, or half of it), swizzle span = the box row
+static int make_xt_map(CUtensorMap* m, const void* d_x, int n, int H, int W, int C, int box_ch) {
   const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)n};
-  const uint32_t box[4] = {64, 8, 4, 1};
-  return make_tmap_f16_sw(m, d_x, 4, dims, box, 128);
+  const uint32_t box[4] = {(uint32_t)box_ch, 8, 4, 1};
+  return make_tmap_f16_sw(m, d_x, 4, dims, box, box_ch * 2);
 }
 
 static int fill_tiles(PairParams& p, int n, int H, int W) {
@@ -1152,7 +1192,7 @@ static int head_common(const char* name, const void* d_xin_hi, const void* d_xin
   rc = make_maps<CfgH>(&a0, &a1, &w, d_xin_hi, d_xin_lo, d_w, n, H, W);
   if (rc) return rc;
   CUtensorMap x0;
-  if (CfgH::XT && (rc = make_xt_map(&x0, d_out_hi, n, H, W, CfgH::CH)) != 0) return rc;
+  if (CfgH::XT && (rc = make_xt_map(&x0, d_out_hi, n, H, W, CfgH::CH, 64)) != 0) return rc;
   return launch_pair<CfgH>(a0, a1, w, p, sms, (cudaStream_t)stream, name, CfgH::XT ? &x0 : nullptr);
 }
 
@@ -1205,9 +1245,9 @@ static int resq_common(int features, const void* d_in, const void* d_w, const fl
   rc = make_maps<CfgResidualQ>(&a0, &a1, &w, d_in, nullptr, d_w, n, H, W);
   if (rc) return rc;
   CUtensorMap x0, x1;
-  if ((rc = make_xt_map(&x0, d_x_hi, n, H, W, 128)) != 0) return rc;
+  if ((rc = make_xt_map(&x0, d_x_hi, n, H, W, 128, 32)) != 0) return rc;
   if (d_out_lo) {
-    if ((rc = make_xt_map(&x1, d_out_lo, n, H, W, 128)) != 0) return rc;
+    if ((rc = make_xt_map(&x1, d_out_lo, n, H, W, 128, 32)) != 0) return rc;
     return launch_pair<CfgResidualQLast>(a0, a1, w, p, sms, (cudaStream_t)stream, "conv_pair<residualq,last>", &x0, &x1);
   }
   return launch_pair<CfgResidualQ>(a0, a1, w, p, sms, (cudaStream_t)stream, "conv_pair<residualq>", &x0);

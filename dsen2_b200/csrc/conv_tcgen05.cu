@@ -275,7 +275,9 @@ int make_tmap_f16_sw(CUtensorMap* m, const void* ptr, int rank, const uint64_t* 
     if (i < rank - 1) gstr[i] = stride;
   }
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(ptr), gdim, gstr, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                       : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DSEN2_REQUIRE(r == CUDA_SUCCESS, DSEN2_E_DRIVER, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);

@@ -40,15 +40,31 @@ class S2Model:
                                   np.zeros((cout,), np.float32)))
         self._packed = {}        # device index -> (weights tensors, bias tensors, pointer arrays)
         self._workspace = {}
+        self._trainer = None     # set by compile(); owns the fp32 master weights while training
+        self._weights_stale = False   # the trainer's weights are newer than self._weights
 
     # ---- Keras-like weight access -------------------------------------------------------- #
     def count_params(self):
         return int(sum(k.size + b.size for k, b in self._weights))
 
     def get_weights(self):
+        self._pull_trained_weights()
         return [a for kb in self._weights for a in kb]
 
+    def _pull_trained_weights(self):
+        """After ``train_on_batch`` the current weights live in the trainer; Keras' predict / get_weights / save_weights see
+        them, so pull them back before any of those."""
+        if self._weights_stale and self._trainer is not None:
+            self._weights_stale = False
+            self._set_weights_local(self._trainer.get_weights())
+
     def set_weights(self, arrays):
+        self._set_weights_local(arrays)
+        self._weights_stale = False
+        if self._trainer is not None:            # compile() then load_weights() (supres_train.py:143,183): train from them
+            self._trainer.set_weights(self.get_weights())
+
+    def _set_weights_local(self, arrays):
         arrays = list(arrays)
         if len(arrays) != 2 * len(self.layer_shapes):
             raise ValueError("expected %d arrays (kernel, bias per conv layer), got %d"
@@ -91,6 +107,7 @@ class S2Model:
 
     def save_weights(self, filepath):
         """Write a Keras-2-style weight file (layer_names / weight_names attributes, kernel:0 / bias:0)."""
+        self._pull_trained_weights()
         tree, attrs, names = {}, {}, []
         for i, (k, b) in enumerate(self._weights):
             n = 'conv2d_%d' % (i + 1)
@@ -112,6 +129,7 @@ class S2Model:
 
     def _ensure_packed(self, device):
         torch = _capi.require_cuda()
+        self._pull_trained_weights()
         key = device.index if device.index is not None else torch.cuda.current_device()
         if key in self._packed:
             return self._packed[key]
@@ -340,7 +358,7 @@ class S2Model:
     def train_on_batch(self, x, y):
         """One optimisation step on numpy (or CUDA tensor) inputs; returns [loss, mean_squared_error] like Keras."""
         torch = _capi.require_cuda()
-        if getattr(self, '_trainer', None) is None:
+        if self._trainer is None:
             raise RuntimeError("You must compile a model before training/testing. Use `model.compile(optimizer, loss)`.")
         tr = self._trainer
         to_dev = lambda a: a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(tr.dev)
@@ -351,7 +369,7 @@ class S2Model:
     @property
     def optimizer(self):
         """``model.optimizer.lr`` as the reference's callbacks read / set it (supres_train.py:47)."""
-        if getattr(self, '_trainer', None) is None:
+        if self._trainer is None:
             raise RuntimeError("You must compile a model before training/testing. Use `model.compile(optimizer, loss)`.")
         return self._trainer.opt
 
@@ -406,10 +424,32 @@ class S2Model:
         return hist
 
     def sync_weights_from_trainer(self):
-        """Pull the trained fp32 master weights back into the model (so predict / save_weights see them)."""
-        if getattr(self, '_trainer', None) is not None:
-            self.set_weights(self._trainer.get_weights())
-            self._weights_stale = False
+        """Pull the trained fp32 master weights back into the model (predict / get_weights / save_weights do it lazily)."""
+        self._pull_trained_weights()
+
+    def to_yaml(self):
+        """``model.to_yaml()`` (supres_train.py:191-193 writes it next to the checkpoints): the architecture as YAML -- the
+        arguments ``s2model`` was built with and the layer list of DSen2Net.py:18-43, enough to rebuild the network."""
+        lines = ['backend: dsen2_b200', 'class_name: Model', 'config:', '  name: s2model',
+                 '  input_shape: [%s]' % ', '.join('[%d, null, null]' % c for c in self.in_channels),
+                 '  num_layers: %d' % self.num_layers, '  feature_size: %d' % self.feature_size,
+                 '  data_format: channels_first', '  layers:']
+        F = self.feature_size
+        add = lambda name, **kw: lines.append('  - {name: %s, %s}' % (name, ', '.join('%s: %s' % kv for kv in kw.items())))
+        add('concatenate_1', class_name='Concatenate', axis=1)
+        add('conv2d_1', class_name='Conv2D', filters=F, kernel_size='[3, 3]', padding='same', activation='relu',
+            kernel_initializer='he_uniform')
+        for l in range(self.num_layers):
+            add('conv2d_%d' % (2 * l + 2), class_name='Conv2D', filters=F, kernel_size='[3, 3]', padding='same', activation='relu',
+                kernel_initializer='he_uniform')
+            add('conv2d_%d' % (2 * l + 3), class_name='Conv2D', filters=F, kernel_size='[3, 3]', padding='same',
+                activation='linear', kernel_initializer='he_uniform')
+            add('lambda_%d' % (l + 1), class_name='Lambda', scale=0.1)
+            add('add_%d' % (l + 1), class_name='Add')
+        add('conv2d_%d' % (2 * self.num_layers + 2), class_name='Conv2D', filters=self.out_channels, kernel_size='[3, 3]',
+            padding='same', activation='linear', kernel_initializer='he_uniform')
+        add('add_%d' % (self.num_layers + 1), class_name='Add', skip='last input')
+        return '\n'.join(lines) + '\n'
 
 
 def s2model(input_shape, num_layers=32, feature_size=256, seed=None):

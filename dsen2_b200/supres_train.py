@@ -17,7 +17,7 @@ import numpy as np
 from .callbacks import LossLog, ModelCheckpoint, ReduceLROnPlateau
 from .DSen2Net import s2model
 from .patches import OpenDataFiles, OpenDataFilesTest, recompose_images
-from .train import Nadam
+from .train import Nadam, broadcast_weights, dist_setup, shard_training_set
 
 model_nr = 's2_038_'          # supres_train.py:23-25
 SCALE = 2000
@@ -38,6 +38,8 @@ def main(argv=None):
     out_path = os.path.join(path, 'network_data/')
     os.makedirs(out_path, exist_ok=True)
     nr = model_nr
+    # one process per GPU: device choice and process group come first -- the model's trainer lives on the CURRENT device
+    rank, world = dist_setup()
 
     input_shape = ((4, None, None), (6, None, None)) + (((2, None, None),) if args.run_60 else ())
     if args.deep:
@@ -72,18 +74,15 @@ def main(argv=None):
         print('Changing the model number to: {}'.format(nr))
     else:
         print('Model number is {}'.format(nr))
+        if rank == 0:                                                   # supres_train.py:191-193
+            with open(out_path + nr + "model.yaml", 'w') as yaml_file:
+                yaml_file.write(model.to_yaml())
+    broadcast_weights(model)            # he_uniform draws differ per process: every replica starts from rank 0's weights
     model.compile(optimizer=Nadam(lr=lr, beta_1=0.9, beta_2=0.999, epsilon=1e-8, schedule_decay=0.004),
                   loss='mean_absolute_error', metrics=['mean_squared_error'])
     print('Model compiled.')
     print(model.count_params())
 
-    rank, world = 0, 1
-    if 'RANK' in os.environ and int(os.environ.get('WORLD_SIZE', '1')) > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
-        dist.init_process_group('nccl')
-        rank, world = dist.get_rank(), dist.get_world_size()
     callbacks = [ReduceLROnPlateau(monitor='val_loss', factor=0.5, patience=5, verbose=1, epsilon=1e-6, cooldown=20, min_lr=1e-5)]
     if rank == 0:
         callbacks = [ModelCheckpoint(out_path + nr + 'lr_{:.0e}.hdf5'.format(lr), monitor='val_loss', verbose=1,
@@ -92,8 +91,8 @@ def main(argv=None):
 
     print('Loading the training data...')
     train, label, val_tr, val_lb = OpenDataFiles(path, args.run_60, SCALE)
-    if world > 1:                                                       # same patches everywhere, strided shares
-        train, label = [a[rank::world] for a in train], label[rank::world]
+    if world > 1:                                      # same patches everywhere, strided shares of EQUAL length
+        train, label = shard_training_set(train, label, rank, world)
     print('Training starts...')
     model.fit(x=train, y=label, batch_size=batch_size, epochs=args.epochs, verbose=1, callbacks=callbacks,
               validation_data=(val_tr, val_lb), shuffle=True, seed=0)

@@ -36,6 +36,51 @@ def nadam_schedule(t, m_schedule, opt):
                 bias2=1.0 - opt.beta_2 ** t)
 
 
+def dist_setup(backend=None):
+    """One process per GPU under ``torch.distributed.run``: pick this rank's device and join the process group BEFORE any
+    model / trainer state is created (a Trainer lives on the current CUDA device).  Returns (rank, world).  Without the
+    launcher's environment: (0, 1) and nothing is initialised."""
+    if 'RANK' not in os.environ or int(os.environ.get('WORLD_SIZE', '1')) <= 1:
+        return 0, 1
+    import torch
+    import torch.distributed as dist
+    if backend is None:
+        backend = 'nccl' if torch.cuda.is_available() else 'gloo'
+    if torch.cuda.is_available():
+        torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+    if not dist.is_initialized():
+        dist.init_process_group(backend)
+    return dist.get_rank(), dist.get_world_size()
+
+
+def broadcast_weights(model, src=0, group=None):
+    """Replicas must start from the same parameters (he_uniform draws differ per process): rank ``src``'s weights replace
+    everybody's.  Works on the model's host arrays, so it runs under NCCL and gloo alike."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return model
+    ws = model.get_weights()
+    flat = torch.from_numpy(np.concatenate([a.ravel() for a in ws]).astype(np.float32))
+    if dist.get_backend(group) == 'nccl':
+        flat = flat.cuda()
+    dist.broadcast(flat, src=src, group=group)
+    flat = flat.cpu().numpy()
+    out, o = [], 0
+    for a in ws:
+        out.append(flat[o:o + a.size].reshape(a.shape).copy())
+        o += a.size
+    model.set_weights(out)
+    return model
+
+
+def shard_training_set(arrays, label, rank, world):
+    """Strided shares of the (identically ordered) training set, truncated to the SAME length on every rank: all ranks then
+    run the same number of steps per epoch, so every gradient all-reduce has all its participants."""
+    n = (label.shape[0] // world) * world
+    return [a[rank:n:world] for a in arrays], label[rank:n:world]
+
+
 def allreduce_gradients(flat, group=None):
     """Sum the flat gradient over the ranks (NCCL on GPUs, gloo in the CPU tests); returns the world size to divide by."""
     import torch.distributed as dist
@@ -77,7 +122,9 @@ class Trainer:
         # replay the whole step as one CUDA graph from the third call of a shape on (DSEN2_TRAIN_NO_GRAPH=1: eager, for ncu)
         self.use_graph = not os.environ.get('DSEN2_TRAIN_NO_GRAPH')
         self._graphs, self._calls = {}, {}
-        self.hp_host = torch.zeros(10, dtype=torch.float32).pin_memory()
+        # step-dependent Nadam scalars travel through a ring of pinned staging buffers: a slot is rewritten only after the
+        # asynchronous upload that last used it has completed (train_step returns without synchronising)
+        self.hp_ring = [[torch.zeros(10, dtype=torch.float32).pin_memory(), None] for _ in range(8)]
         self.hp_dev = torch.zeros(10, dtype=torch.float32, device=self.dev)
         self.loss_out = torch.zeros(2, dtype=torch.float64, device=self.dev)
         f16 = lambda *s: torch.empty(s, dtype=torch.float16, device=self.dev)
@@ -108,6 +155,15 @@ class Trainer:
             out.append(host[self.offsets[2 * i]:self.offsets[2 * i + 1]].reshape(3, 3, cin, cout).copy())
             out.append(host[self.offsets[2 * i + 1]:self.offsets[2 * i + 2]].copy())
         return out
+
+    def set_weights(self, arrays):
+        """New master weights (``model.load_weights`` / ``set_weights`` after ``compile``); the optimizer state is kept, as
+        Keras keeps it."""
+        flat = np.concatenate([np.asarray(a, np.float32).ravel() for a in arrays])
+        if flat.size != self.params.numel():
+            raise ValueError("expected %d parameters, got %d" % (self.params.numel(), flat.size))
+        self.params.copy_(self.torch.from_numpy(flat).to(self.dev))
+        self.repack()
 
     def repack(self):
         """fp32 master weights -> fp16 operands of the forward and backward-data convolutions."""
@@ -231,9 +287,14 @@ class Trainer:
         self.m_schedule = s['sched_new']
         o = self.opt
         vals = [grad_mul, o.lr, o.beta_1, o.beta_2, o.epsilon, s['mu_t'], s['mu_next'], s['sched_new'], s['sched_next'], s['bias2']]
+        slot = self.hp_ring[self.iterations % len(self.hp_ring)]
+        if slot[1] is not None:
+            slot[1].synchronize()
         for i, v_ in enumerate(vals):
-            self.hp_host[i] = float(v_)
-        self.hp_dev.copy_(self.hp_host, non_blocking=True)
+            slot[0][i] = float(v_)
+        self.hp_dev.copy_(slot[0], non_blocking=True)
+        slot[1] = self.torch.cuda.Event()
+        slot[1].record()
         return s
 
     def _step_body(self, xs, y, apply=True, dev_hp=False):

@@ -299,3 +299,54 @@ def test_supres_train_cli_trains_and_predicts(env, tmp_path):
     assert supres_train.main(['--path', root, '--predict', ck]) == 0
     out = np.load(str(t / (ck[-20:-13] + '-predict.npy')))
     assert out.shape == (48, 48, 6) and np.isfinite(out).all()
+
+
+def test_model_and_trainer_weights_stay_in_sync(env, tmp_path):
+    """Keras semantics around compile(): load_weights AFTER compile trains from the loaded weights (supres_train.py:143,183),
+    and predict / get_weights / save_weights after train_on_batch see the UPDATED weights."""
+    torch, _capi, lib = env
+    from dsen2_b200.DSen2Net import s2model
+    from dsen2_b200.train import Nadam
+    model, ws, xs, y = _setup(L=1, n=4, P=32)
+    other = s2model(((4, None, None), (6, None, None)), num_layers=1, feature_size=128, seed=77)
+    wf = str(tmp_path / 'w.hdf5')
+    other.save_weights(wf)
+    model.compile(optimizer=Nadam(lr=1e-3), loss='mean_absolute_error', metrics=['mean_squared_error'])
+    model.load_weights(wf)                                  # compile, THEN load: the trainer must pick the new weights up
+    for a, b in zip(model._trainer.get_weights(), other.get_weights()):
+        assert np.array_equal(a, b)
+    before = model.predict(xs)
+    assert np.array_equal(before, other.predict(xs))
+    for _ in range(3):
+        model.train_on_batch(xs, y)
+    after_w = model.get_weights()                           # no explicit sync call
+    assert not np.array_equal(after_w[0], other.get_weights()[0])
+    for a, b in zip(after_w, model._trainer.get_weights()):
+        assert np.array_equal(a, b)
+    after = model.predict(xs)
+    assert not np.array_equal(after, before)
+    model.save_weights(wf)
+    again = s2model(((4, None, None), (6, None, None)), num_layers=1, feature_size=128)
+    again.load_weights(wf)
+    assert np.array_equal(again.predict(xs), after)
+
+
+def test_back_to_back_graph_steps_use_their_own_nadam_scalars(env):
+    """train_step returns without synchronising: the step-dependent scalars (mu_t, bias correction ...) must not be
+    overwritten on the host before their upload has run.  Unsynchronised back-to-back steps == synchronised steps."""
+    torch, _capi, lib = env
+    from dsen2_b200.train import Nadam, Trainer
+    model, ws, xs, y = _setup(L=1, n=4, P=32)
+    dx, dy = [torch.from_numpy(a).cuda() for a in xs], torch.from_numpy(y).cuda()
+    outs = []
+    for sync in (True, False):
+        model.set_weights(ws)
+        tr = Trainer(model, Nadam(lr=1e-3))
+        for _ in range(12):
+            tr.train_step(dx, dy)
+            if sync:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        outs.append(tr.params.cpu().numpy())
+    d = np.abs(outs[0] - outs[1]) / (1e-3 * 12)
+    assert np.median(d) < 1e-3 and np.mean(d > 0.25) < 0.01     # fp32 atomics in the weight gradients: last-bit noise only

@@ -71,6 +71,56 @@ def test_gloo_world2_gradient_allreduce(tmp_path):
     assert np.load(str(tmp_path / 'ok.npy'))[0]
 
 
+def _worker_setup(rank, world, port, tmp):
+    """What ``python -m torch.distributed.run -m dsen2_b200.supres_train`` does before training, on the gloo backend:
+    process group first, rank 0's weights everywhere, equal-length shards."""
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    from dsen2_b200.DSen2Net import s2model
+    assert train.dist_setup('gloo') == (rank, world)
+    model = s2model(((4, None, None), (6, None, None)), num_layers=1, feature_size=128, seed=100 + rank)   # different draws
+    before = model.get_weights()[0].copy()
+    train.broadcast_weights(model)
+    ref = s2model(((4, None, None), (6, None, None)), num_layers=1, feature_size=128, seed=100).get_weights()
+    same = all(np.array_equal(a, b) for a, b in zip(model.get_weights(), ref))
+    changed = rank == 0 or not np.array_equal(before, model.get_weights()[0])
+    xs, y = [np.arange(11 * 2).reshape(11, 2), np.arange(11 * 3).reshape(11, 3)], np.arange(11)
+    sx, sy = train.shard_training_set(xs, y, rank, world)
+    np.save(os.path.join(tmp, 'r%d.npy' % rank), np.array([same and changed, len(sy), len(sx[0]), int(sy[0]), int(sx[1][0, 0])]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_distributed_setup_broadcast_and_equal_shards(tmp_path):
+    import torch.multiprocessing as mp
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_worker_setup, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = np.load(str(tmp_path / 'r0.npy')), np.load(str(tmp_path / 'r1.npy'))
+    assert r0[0] == 1 and r1[0] == 1                  # both replicas hold rank 0's weights
+    assert r0[1] == r1[1] == 5 and r0[2] == r1[2] == 5   # 11 samples over 2 ranks: 5 + 5, the odd one is dropped
+    assert (r0[3], r1[3]) == (0, 1) and (r0[4], r1[4]) == (0, 3)
+
+
+def test_dist_setup_without_a_launcher_is_a_no_op():
+    env = {k: os.environ.pop(k) for k in ('RANK', 'WORLD_SIZE') if k in os.environ}
+    try:
+        assert train.dist_setup() == (0, 1)
+    finally:
+        os.environ.update(env)
+
+
+def test_to_yaml_describes_the_network():
+    import yaml
+    from dsen2_b200.DSen2Net import s2model
+    m = s2model(((4, None, None), (6, None, None), (2, None, None)), num_layers=6, feature_size=128)
+    d = yaml.safe_load(m.to_yaml())
+    cfg = d['config']
+    assert cfg['num_layers'] == 6 and cfg['feature_size'] == 128 and cfg['input_shape'] == [[4, None, None], [6, None, None], [2, None, None]]
+    convs = [l for l in cfg['layers'] if l['class_name'] == 'Conv2D']
+    assert len(convs) == 14 and convs[0]['filters'] == 128 and convs[-1]['filters'] == 2
+    assert sum(l['class_name'] == 'Add' for l in cfg['layers']) == 7
+
+
 def test_allreduce_is_identity_without_a_process_group():
     import torch
     flat = torch.ones(10)

@@ -160,7 +160,7 @@ class S2Model:
                 else:
                     cout_pad = F
                     dst = torch.empty((9, F, F), dtype=torch.float16, device=device)
-                    _capi.check(lib.dsen2_pack_conv_weights(_capi.ptr(src), cin, cout, F, F, 0, _capi.ptr(dst), None, st),
+                    _capi.check(lib.dsen2_pack_conv_weights(_capi.ptr(src), cin, cout, F, F, _capi.ptr(dst), st),
                                 "dsen2_pack_conv_weights")
                 bp = torch.zeros((max(cout_pad, 16),), dtype=torch.float32, device=device)
                 bp[:cout] = torch.from_numpy(b).to(device)
@@ -221,9 +221,8 @@ class S2Model:
             ptr(buf['xin_hi']), ptr(buf['xin_lo']), ptr(wts[0]), ptr(biases[0]), n, P, P, F, ptr(x_hi), ptr(xq), st),
             "dsen2_conv_head16_q"))
         for l in range(L):
-            self._timed(timers, 'conv_res1', n, lambda: _capi.check(lib.dsen2_conv3x3(
-                ptr(x_hi), ptr(wts[1 + 2 * l]), ptr(biases[1 + 2 * l]), n, P, P, F, F, 9, _capi.EPI_RELU, None,
-                None, 0.0, ptr(t), None, None, None, 0, st), "dsen2_conv3x3(res conv1)"))
+            self._timed(timers, 'conv_res1', n, lambda: _capi.check(lib.dsen2_conv_relu(
+                ptr(x_hi), ptr(wts[1 + 2 * l]), ptr(biases[1 + 2 * l]), n, P, P, F, ptr(t), st), "dsen2_conv_relu"))
             self._timed(timers, 'conv_res2', n, lambda: _capi.check(resq(
                 ptr(t), ptr(wts[2 + 2 * l]), ptr(biases[2 + 2 * l]), n, P, P, 0.1, ptr(x_hi), ptr(xq),
                 ptr(x_lo) if l == L - 1 else None, st), "dsen2_conv_resq"))

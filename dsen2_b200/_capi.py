@@ -6,7 +6,6 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_longl
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libdsen2_b200.so")
 
-EPI_RELU, EPI_RESIDUAL, EPI_TAIL_NCHW = 0, 1, 2
 IMG_F32, IMG_U16 = 0, 1
 
 # name -> (restype, argtypes); must list every symbol the header declares (checked by tests)
@@ -22,18 +21,13 @@ SIGNATURES = {
     "dsen2_bicubic_imresize": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
                                        c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dsen2_down_pixel_aggr": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
-    "dsen2_pack_conv_weights": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
-    "dsen2_pack_head_input": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
-                                      c_void_p, c_void_p, c_void_p]),
-    "dsen2_conv3x3": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                              c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "dsen2_pack_conv_weights": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "dsen2_conv_relu": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dsen2_s2model_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "dsen2_s2model_forward": (c_int, [POINTER(c_void_p), POINTER(c_int), c_int, c_int, c_int, c_int, c_int,
                                       POINTER(c_void_p), POINTER(c_void_p), c_void_p, c_size_t, c_void_p, c_void_p]),
     "dsen2_prep_from_patches": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p,
                                         c_void_p, c_void_p]),
-    "dsen2_prep_from_images": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
-                                       c_void_p, c_void_p, c_void_p]),
     "dsen2_pack_head_weights": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "dsen2_pack_tail_weights": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "dsen2_conv_head": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
@@ -55,27 +49,18 @@ SIGNATURES = {
                                          c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "dsen2_conv_resq256": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                                    c_void_p, c_void_p]),
-    "dsen2_trunk_hilo_to_q": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "dsen2_conv_tail": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                 c_int, c_void_p, c_void_p]),
     "dsen2_pack_dgrad_weights": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "dsen2_conv_relu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
-    "dsen2_planar_pitch": (c_longlong, [c_int, c_int, c_int]),
-    "dsen2_nhwc_to_planar": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
-    "dsen2_nchw_to_planar": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                                     c_int, c_float, c_void_p, c_void_p]),
     "dsen2_nchw_to_nhwc_f16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                        c_void_p, c_void_p]),
     "dsen2_relu_mask": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p]),
     "dsen2_colsum_nhwc": (c_int, [c_void_p, c_longlong, c_float, c_void_p, c_void_p]),
     "dsen2_wgrad_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
-    "dsen2_wgrad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
-    "dsen2_rowsum": (c_int, [c_void_p, c_int, c_longlong, c_float, c_void_p, c_void_p]),
     "dsen2_mae_grad": (c_int, [c_void_p, c_void_p, c_longlong, c_float, c_void_p, c_void_p, c_void_p]),
     "dsen2_nadam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong] + [c_float] * 10 + [c_void_p]),
     "dsen2_nadam_step_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p]),
-    "dsen2_debug_force_v1": (c_int, [c_int]),
-    "dsen2_debug_umma_rowshift": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
 }
 
 

@@ -50,15 +50,10 @@ static inline bool needs_config(bool (&flags)[64]) {
   return true;
 }
 
-// conv_tcgen05.cu
-int make_tmap_f16(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint32_t* box);
-// same with the shared-memory swizzle span chosen by the caller (128 or 32 bytes = the box's inner extent)
+// conv_api.cu: NHWC fp16 tensor map with the shared-memory swizzle span chosen by the caller (128, 64 or 32 bytes = the
+// box's inner extent); device check
 int make_tmap_f16_sw(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint32_t* box, int swizzle_bytes);
 int device_sm_count_and_check(int* sms);
-// conv_pair.cu
-int conv_pair_res(const void* d_in, const void* d_w, const float* d_bias, int n, int H, int W, int features, int epilogue,
-                  const void* d_res_hi, const void* d_res_lo, float res_scale, void* d_out_hi, void* d_out_lo,
-                  cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------ //
 // device-side PTX wrappers
@@ -104,15 +99,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded spin: a protocol bug must surface as a trapped launch, never as a hung GPU box.
+// Bounded spin: a protocol bug must surface as a trapped launch, never as a hung GPU box.  The fast path is one try_wait;
+// the guard (a poll counter, the clock only every 64 K polls) is off the critical path of a wait that succeeds.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  uint32_t polls = 0;
+  long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {   // ~2 s at 2 GHz
-      printf("dsen2_b200: mbarrier wait timed out (block %d thread %d bar %p parity %u)\n", (int)blockIdx.x,
-             (int)threadIdx.x, (void*)bar, parity);
-      __trap();
+    if ((++polls & 0xffffu) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 4000000000LL) {   // ~2 s at 2 GHz
+        printf("dsen2_b200: mbarrier wait timed out (block %d thread %d bar %p parity %u)\n", (int)blockIdx.x,
+               (int)threadIdx.x, (void*)bar, parity);
+        __trap();
+      }
     }
   }
 }

@@ -11,9 +11,11 @@
 // [tap][k-block] slab (144 KB for 128->128), loaded once.
 //
 // Three layer shapes share the kernel (template parameters):
-//   RES   128 -> 128, 9 taps, 2 k-blocks, N = 128           epilogue RELU | RESIDUAL(x + 0.1*conv, hi+lo trunk)
-//   HEAD  (3 horizontal taps x 16 ch pre-gathered by dsen2_prep_*) -> 128, 3 vertical taps, A = hi | lo k-blocks,
-//         B = [W_hi ; W_lo] stacked along N (N = 256) and summed in the epilogue: fp32-equivalent first layer
+//   RES   F -> F (128: resident weights; 256: streamed through a ring), 9 taps, N = F
+//         epilogues RELU | RESIDUALQ (x + 0.1*conv on the fp16 + 8 bit trunk) | RESIDUAL32 / MASK (training step)
+//   HEAD  16-channel input (32-byte rows) -> F, 9 taps, A = hi | lo k-blocks, three products per tap (hi*W_hi, hi*W_lo,
+//         lo*W_hi) into ONE accumulator: fp32-equivalent first layer.  (The training step uses the older form on three
+//         pre-gathered horizontal taps x 16 ch, B = [W_hi ; W_lo] stacked along N and summed in the epilogue.)
 //   TAIL  128 -> cout <= 16, 9 taps, A = x_hi | x_lo (4 k-blocks), B = [W_hi ; W_lo] (N = 32), epilogue adds the
 //         global skip (DSen2Net.py:38,41), scales, and writes NCHW predictions or the stitched HWC canvas
 //         (patches.py:374-405 ownership rule, supres.py:29).
@@ -36,7 +38,7 @@ static constexpr int kBoxH = 18;
 // against 565-567 ms with distance 1 on the same box.  The trunk lines the residual epilogues read ARE prefetched, one
 // tile ahead.)
 
-enum { kEpiRelu = 0, kEpiResidual = 1, kEpiTail = 2, kEpiResidual32 = 3, kEpiMask = 4, kEpiResidualQ = 5, kEpiResidualQLast = 6,
+enum { kEpiRelu = 0, kEpiTail = 2, kEpiResidual32 = 3, kEpiMask = 4, kEpiResidualQ = 5, kEpiResidualQLast = 6,
        kEpiHeadQ = 7 };
 // How a split-precision layer (operands v = hi + lo, fp16 each) lays out its products:
 //   kSplitStack  B = [W_hi ; W_lo] stacked along N, A = hi then lo k-blocks; the epilogue adds the two column halves
@@ -52,7 +54,6 @@ struct PairParams {
   uint32_t num_tiles;
   const float* bias;
   const __half* res_hi;
-  const __half* res_lo;
   float res_scale;
   __half* out_hi;
   __half* out_lo;
@@ -910,18 +911,6 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
           const int cb = half * CPT + sc * 64;        // first channel of this super-chunk
           const EpiGeom g = epi_geom<Cfg>(p, tc, wq, cb);
           uint4 vh[8], vl[8];                         // residual in, then outputs (thread = pixel layout)
-          if (Cfg::EPI == kEpiResidual) {             // before the accumulator is ready: latency hidden behind the MMAs
-            uint4 gh[8], gl[8];
-            coalesced_load(gh, p.res_hi, g, lane);
-            coalesced_load(gl, p.res_lo, g, lane);
-            if (pt + npairs < pair_tiles) {           // pull the NEXT tile's residual into L2 a whole tile time ahead
-              const EpiGeom gn = epi_geom<Cfg>(p, tn, wq, cb);
-              prefetch_rows(p.res_hi, gn, lane);
-              prefetch_rows(p.res_lo, gn, lane);
-            }
-            staged_gather(stg, gh, vh, lane);
-            staged_gather(stg, gl, vl, lane);
-          }
           if (Cfg::EPI == kEpiMask) {                 // ReLU backward: the forward activation decides which gradients pass
             uint4 gm[8];
             coalesced_load(gm, p.res_hi, g, lane);
@@ -966,12 +955,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
                 const int jj = j + 2 * h2;
                 float v0 = __uint_as_float(r[jj]) + bb[2 * h2];
                 float v1 = __uint_as_float(r[jj + 1]) + bb[2 * h2 + 1];
-                if (Cfg::EPI == kEpiResidual) {
-                  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hw[jj >> 1]));
-                  const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&lw[jj >> 1]));
-                  v0 = (a.x + c.x) + v0 * p.res_scale;     // Lambda(x * scale) then Add (DSen2Net.py:13,15)
-                  v1 = (a.y + c.y) + v1 * p.res_scale;
-                } else if (Cfg::EPI == kEpiMask) {
+                if (Cfg::EPI == kEpiMask) {
                   const float2 m = __half22float2(*reinterpret_cast<const __half2*>(&hw[jj >> 1]));
                   v0 = m.x > 0.f ? v0 : 0.f;               // d relu(z) / dz = [z > 0]  (relu(z) > 0  <=>  z > 0)
                   v1 = m.y > 0.f ? v1 : 0.f;
@@ -1021,7 +1005,6 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
 // host side
 // ------------------------------------------------------------------------------------------ //
 using CfgRelu = PairCfg<128, kSplitNone, 1, 2, 9, 4, 3, kEpiRelu>;
-using CfgResidual = PairCfg<128, kSplitNone, 1, 2, 9, 4, 3, kEpiResidual>;
 using CfgResidual32 = PairCfg<128, kSplitNone, 1, 2, 9, 4, 3, kEpiResidual32>;
 using CfgMask = PairCfg<128, kSplitNone, 1, 2, 9, 4, 3, kEpiMask>;
 // fp16 + 8 bit trunk update: epilogue-bound, not load-bound -- two activation stages are enough (measured: 3 -> 2 stages costs
@@ -1030,7 +1013,6 @@ using CfgResidualQ = PairCfg<128, kSplitNone, 1, 2, 9, 4, 2, kEpiResidualQ, 0, 1
 using CfgResidualQLast = PairCfg<128, kSplitNone, 1, 2, 9, 4, 2, kEpiResidualQLast, 0, 128, true>;
 // VDSen2 trunk (256 -> 256): 1.18 MB of weights per layer cannot be resident -- ring of 8 streamed [tap][k-block] slabs
 using CfgRelu256 = PairCfg<256, kSplitNone, 1, 4, 9, 4, 3, kEpiRelu, 8>;
-using CfgResidual256 = PairCfg<256, kSplitNone, 1, 4, 9, 4, 3, kEpiResidual, 8>;
 using CfgResidualQ256 = PairCfg<256, kSplitNone, 1, 4, 9, 4, 3, kEpiResidualQ, 8>;
 using CfgResidualQLast256 = PairCfg<256, kSplitNone, 1, 4, 9, 4, 3, kEpiResidualQLast, 8>;
 using CfgHead = PairCfg<256, kSplitStack, 2, 1, 3, 3, 6, kEpiRelu>;
@@ -1092,35 +1074,37 @@ static int fill_tiles(PairParams& p, int n, int H, int W) {
   return 0;
 }
 
-// F -> F resblock convolution (called by dsen2_conv3x3 for feature_size 128 and 256), hi+lo NHWC trunk
-int conv_pair_res(const void* d_in, const void* d_w, const float* d_bias, int n, int H, int W, int features, int epilogue,
-                  const void* d_res_hi, const void* d_res_lo, float res_scale, void* d_out_hi, void* d_out_lo,
-                  cudaStream_t stream) {
+}  // namespace dsen2
+
+using namespace dsen2;
+
+// first convolution of a resBlock: relu(conv3x3(x) + b) -> NHWC fp16 (DSen2Net.py:10-11), F = 128 or 256
+extern "C" int dsen2_conv_relu(const void* d_in, const void* d_w, const float* d_bias, int n, int H, int W, int feature_size,
+                               void* d_out, void* stream) {
+  DSEN2_REQUIRE(d_in && d_w && d_bias && d_out, DSEN2_E_BADARG, "dsen2_conv_relu: null pointer");
+  DSEN2_REQUIRE(n >= 0 && H > 0 && W > 0, DSEN2_E_BADARG, "dsen2_conv_relu: bad shape (n %d, %dx%d)", n, H, W);
+  DSEN2_REQUIRE(feature_size == 128 || feature_size == 256, DSEN2_E_BADARG,
+                "dsen2_conv_relu: feature size must be 128 or 256 (got %d)", feature_size);
+  DSEN2_REQUIRE(((uintptr_t)d_in % 16) == 0 && ((uintptr_t)d_w % 16) == 0 && ((uintptr_t)d_out % 16) == 0, DSEN2_E_ALIGN,
+                "dsen2_conv_relu: pointers must be 16-byte aligned");
+  if (n == 0) return 0;
   int sms = 0;
   int rc = device_sm_count_and_check(&sms);
   if (rc) return rc;
   PairParams p{};
   if ((rc = fill_tiles(p, n, H, W)) != 0) return rc;
   p.bias = d_bias;
-  p.res_hi = (const __half*)d_res_hi; p.res_lo = (const __half*)d_res_lo; p.res_scale = res_scale;
-  p.out_hi = (__half*)d_out_hi; p.out_lo = (__half*)d_out_lo;
+  p.out_hi = (__half*)d_out;
   CUtensorMap a0, a1, w;
-  if (features == 256) {
+  if (feature_size == 256) {
     rc = make_maps<CfgRelu256>(&a0, &a1, &w, d_in, nullptr, d_w, n, H, W);
     if (rc) return rc;
-    if (epilogue == DSEN2_EPI_RESIDUAL)
-      return launch_pair<CfgResidual256>(a0, a1, w, p, sms, stream, "conv_pair<residual,256>");
-    return launch_pair<CfgRelu256>(a0, a1, w, p, sms, stream, "conv_pair<relu,256>");
+    return launch_pair<CfgRelu256>(a0, a1, w, p, sms, (cudaStream_t)stream, "conv_pair<relu,256>");
   }
   rc = make_maps<CfgRelu>(&a0, &a1, &w, d_in, nullptr, d_w, n, H, W);
   if (rc) return rc;
-  if (epilogue == DSEN2_EPI_RESIDUAL) return launch_pair<CfgResidual>(a0, a1, w, p, sms, stream, "conv_pair<residual>");
-  return launch_pair<CfgRelu>(a0, a1, w, p, sms, stream, "conv_pair<relu>");
+  return launch_pair<CfgRelu>(a0, a1, w, p, sms, (cudaStream_t)stream, "conv_pair<relu>");
 }
-
-}  // namespace dsen2
-
-using namespace dsen2;
 
 extern "C" int dsen2_conv_relu_bwd(const void* d_in, const void* d_w, const float* d_bias, const void* d_fwd_act, int n,
                                    int H, int W, void* d_out, void* stream) {
@@ -1261,54 +1245,6 @@ extern "C" int dsen2_conv_resq(const void* d_in, const void* d_w, const float* d
 extern "C" int dsen2_conv_resq256(const void* d_in, const void* d_w, const float* d_bias, int n, int H, int W,
                                   float res_scale, void* d_x_hi, void* d_trunk_lo8, void* d_out_lo, void* stream) {
   return resq_common(256, d_in, d_w, d_bias, n, H, W, res_scale, d_x_hi, d_trunk_lo8, d_out_lo, stream);
-}
-
-// ---- (x_hi, x_lo) NHWC fp16 pair -> fp16 + 8 bit trunk code (VDSen2: the single-CTA first layer writes hi + lo) ----
-__global__ void hilo_to_q_kernel(__half* __restrict__ x_hi, const __half* __restrict__ x_lo, uint8_t* __restrict__ xq, int H,
-                                 int W, int C, long long total) {
-  const int c16 = C / 16, tiles_x = (W + 7) / 8;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int chunk = (int)(idx % c16);
-    const long long pix = idx / c16;                      // (n * H + y) * W + x
-    const int x = (int)(pix % W);
-    const long long row = pix / W;                        // n * H + y
-    const uint4* ph = reinterpret_cast<const uint4*>(x_hi + pix * C + chunk * 16);
-    const uint4* pl = reinterpret_cast<const uint4*>(x_lo + pix * C + chunk * 16);
-    uint4 h[2] = {ph[0], ph[1]};
-    const uint4 l[2] = {pl[0], pl[1]};
-    uint4 q;
-    uint32_t* hw = reinterpret_cast<uint32_t*>(h);
-    const uint32_t* lw = reinterpret_cast<const uint32_t*>(l);
-    uint32_t* qw = reinterpret_cast<uint32_t*>(&q);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {                         // four channels per step
-      const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&hw[2 * j]));
-      const float2 a1 = __half22float2(*reinterpret_cast<const __half2*>(&hw[2 * j + 1]));
-      const float2 b0 = __half22float2(*reinterpret_cast<const __half2*>(&lw[2 * j]));
-      const float2 b1 = __half22float2(*reinterpret_cast<const __half2*>(&lw[2 * j + 1]));
-      q_encode4(a0.x + b0.x, a0.y + b0.y, a1.x + b1.x, a1.y + b1.y, hw[2 * j], hw[2 * j + 1], qw[j]);
-    }
-    uint4* oh = reinterpret_cast<uint4*>(x_hi + pix * C + chunk * 16);
-    oh[0] = h[0];
-    oh[1] = h[1];
-    *reinterpret_cast<uint4*>(xq + (((row * tiles_x + x / 8) * c16 + chunk) * 8 + (x & 7)) * 16) = q;
-  }
-}
-
-extern "C" int dsen2_trunk_hilo_to_q(void* d_x_hi, const void* d_x_lo, void* d_trunk_lo8, int n, int H, int W, int C,
-                                     void* stream) {
-  DSEN2_REQUIRE(d_x_hi && d_x_lo && d_trunk_lo8, DSEN2_E_BADARG, "dsen2_trunk_hilo_to_q: null pointer");
-  DSEN2_REQUIRE(n >= 0 && H > 0 && W > 0 && C > 0 && C % 16 == 0, DSEN2_E_BADARG,
-                "dsen2_trunk_hilo_to_q: channels must be a multiple of 16 (got %d)", C);
-  DSEN2_REQUIRE(((uintptr_t)d_x_hi % 16) == 0 && ((uintptr_t)d_x_lo % 16) == 0 && ((uintptr_t)d_trunk_lo8 % 16) == 0,
-                DSEN2_E_ALIGN, "dsen2_trunk_hilo_to_q: pointers must be 16-byte aligned");
-  if (n == 0) return 0;
-  const long long total = (long long)n * H * W * (C / 16);
-  const int block = 256;
-  hilo_to_q_kernel<<<grid_for(total, block), block, 0, (cudaStream_t)stream>>>((__half*)d_x_hi, (const __half*)d_x_lo,
-                                                                               (uint8_t*)d_trunk_lo8, H, W, C, total);
-  return check_launch("trunk_hilo_to_q");
 }
 
 static int tail_common(PairParams& p, bool xin16, int features, const void* d_x_hi, const void* d_x_lo, const void* d_w,

@@ -449,63 +449,15 @@ __global__ void gauss_cols_mean_kernel(const float* __restrict__ tmp, int H, int
 // operand packing for the tensor-core path
 // ------------------------------------------------------------------------------------------ //
 __global__ void pack_weights_kernel(const float* __restrict__ hwio, int cin, int cout, int cin_pad, int cout_pad,
-                                    int im2col, long long total, __half* __restrict__ out, __half* __restrict__ out_lo) {
+                                    long long total, __half* __restrict__ out) {
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int i = (int)(idx % cin_pad);
     const int o = (int)((idx / cin_pad) % cout_pad);
     const int t = (int)(idx / ((long long)cin_pad * cout_pad));
     float v = 0.f;
-    if (o < cout) {
-      if (im2col) {
-        if (i < 9 * cin) v = hwio[(long long)i * cout + o];          // (ky,kx,c) flattened is already k-major
-      } else if (i < cin) {
-        v = hwio[((long long)t * cin + i) * cout + o];
-      }
-    }
-    const __half hi = __float2half_rn(v);
-    out[idx] = hi;
-    if (out_lo) out_lo[idx] = __float2half_rn(v - __half2float(hi));
-  }
-}
-
-// thread = (pixel, group of 8 k): zero-padded 3x3 neighbourhood of the concatenated inputs
-__global__ void pack_head_input_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x1, int c1,
-                                       const float* __restrict__ x2, int c2, int P, int k_pad, long long total,
-                                       __half* __restrict__ out, __half* __restrict__ out_lo) {
-  const int ctot = c0 + c1 + c2;
-  const int groups = k_pad / 8;
-  const long long PP = (long long)P * P;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(idx % groups);
-    const long long pix = idx / groups;
-    const int n = (int)(pix / PP);
-    const int rem = (int)(pix - (long long)n * PP);
-    const int y = rem / P, x = rem - y * P;
-    __align__(16) __half hi[8];
-    __align__(16) __half lo[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = g * 8 + j;
-      float v = 0.f;
-      if (k < 9 * ctot) {
-        const int tap = k / ctot, c = k - tap * ctot;
-        const int sy = y + tap / 3 - 1, sx = x + tap % 3 - 1;
-        if (sy >= 0 && sy < P && sx >= 0 && sx < P) {
-          const float* src;
-          int cc = c, cn;
-          if (cc < c0) { src = x0; cn = c0; }
-          else if (cc < c0 + c1) { src = x1; cc -= c0; cn = c1; }
-          else { src = x2; cc -= c0 + c1; cn = c2; }
-          v = __ldg(src + ((long long)n * cn + cc) * PP + (long long)sy * P + sx);
-        }
-      }
-      hi[j] = __float2half_rn(v);
-      lo[j] = __float2half_rn(v - __half2float(hi[j]));
-    }
-    *reinterpret_cast<uint4*>(out + pix * k_pad + g * 8) = *reinterpret_cast<const uint4*>(hi);
-    if (out_lo) *reinterpret_cast<uint4*>(out_lo + pix * k_pad + g * 8) = *reinterpret_cast<const uint4*>(lo);
+    if (o < cout && i < cin) v = hwio[((long long)t * cin + i) * cout + o];
+    out[idx] = __float2half_rn(v);
   }
 }
 
@@ -652,32 +604,15 @@ extern "C" int dsen2_down_pixel_aggr(const float* d_img, int H, int W, int C, in
   return check_launch("gauss_cols_mean");
 }
 
-extern "C" int dsen2_pack_conv_weights(const float* d_hwio, int cin, int cout, int cin_pad, int cout_pad, int im2col,
-                                       void* d_packed_f16, void* d_packed_lo_f16, void* stream) {
+extern "C" int dsen2_pack_conv_weights(const float* d_hwio, int cin, int cout, int cin_pad, int cout_pad, void* d_packed_f16,
+                                       void* stream) {
   DSEN2_REQUIRE(d_hwio && d_packed_f16, DSEN2_E_BADARG, "dsen2_pack_conv_weights: null pointer");
-  DSEN2_REQUIRE(cin > 0 && cout > 0 && cin_pad % 64 == 0 && cout_pad >= cout && cout_pad % 16 == 0, DSEN2_E_BADARG,
-                "dsen2_pack_conv_weights: bad channel padding (cin %d->%d, cout %d->%d)", cin, cin_pad, cout, cout_pad);
-  DSEN2_REQUIRE(im2col ? cin_pad >= 9 * cin : cin_pad >= cin, DSEN2_E_BADARG,
-                "dsen2_pack_conv_weights: cin_pad %d too small", cin_pad);
-  const int taps = im2col ? 1 : 9;
-  const long long total = (long long)taps * cout_pad * cin_pad;
+  DSEN2_REQUIRE(cin > 0 && cout > 0 && cin_pad % 64 == 0 && cin_pad >= cin && cout_pad >= cout && cout_pad % 16 == 0,
+                DSEN2_E_BADARG, "dsen2_pack_conv_weights: bad channel padding (cin %d->%d, cout %d->%d)", cin, cin_pad, cout,
+                cout_pad);
+  const long long total = 9LL * cout_pad * cin_pad;
   const int block = 256;
-  pack_weights_kernel<<<grid_for(total, block), block, 0, (cudaStream_t)stream>>>(
-      d_hwio, cin, cout, cin_pad, cout_pad, im2col, total, (__half*)d_packed_f16, (__half*)d_packed_lo_f16);
+  pack_weights_kernel<<<grid_for(total, block), block, 0, (cudaStream_t)stream>>>(d_hwio, cin, cout, cin_pad, cout_pad, total,
+                                                                                  (__half*)d_packed_f16);
   return check_launch("pack_conv_weights");
-}
-
-extern "C" int dsen2_pack_head_input(const float* d_x0, int c0, const float* d_x1, int c1, const float* d_x2, int c2,
-                                     int n, int P, int k_pad, void* d_out_f16, void* d_out_lo_f16, void* stream) {
-  DSEN2_REQUIRE(d_x0 && d_x1 && d_out_f16 && (c2 == 0 || d_x2), DSEN2_E_BADARG, "dsen2_pack_head_input: null pointer");
-  DSEN2_REQUIRE(c0 > 0 && c1 > 0 && c2 >= 0 && n >= 0 && P > 0 && k_pad % 64 == 0 && k_pad >= 9 * (c0 + c1 + c2),
-                DSEN2_E_BADARG, "dsen2_pack_head_input: bad sizes (k_pad %d for %d channels)", k_pad, c0 + c1 + c2);
-  DSEN2_REQUIRE(((uintptr_t)d_out_f16 % 16) == 0 && ((uintptr_t)d_out_lo_f16 % 16) == 0, DSEN2_E_ALIGN,
-                "dsen2_pack_head_input: output must be 16-byte aligned");
-  if (n == 0) return 0;
-  const long long total = (long long)n * P * P * (k_pad / 8);
-  const int block = 256;
-  pack_head_input_kernel<<<grid_for(total, block), block, 0, (cudaStream_t)stream>>>(
-      d_x0, c0, d_x1, c1, d_x2, c2, P, k_pad, total, (__half*)d_out_f16, (__half*)d_out_lo_f16);
-  return check_launch("pack_head_input");
 }

@@ -1,16 +1,15 @@
 // Network-input preparation and weight packing for the CTA-pair convolution kernels (conv_pair.cu).
 //
-// "Prepared input" x_in: NHWC fp16, 64 channels per pixel, as a hi tensor and a lo tensor (v = hi + lo to
-// ~22 bits).  The 64 channels are the three HORIZONTAL taps of the first 3x3 convolution, pre-gathered:
-//     x_in[n][y][x][t*16 + c] = X[n][c][y][x + t - 1]     t = 0,1,2;  zero outside the patch;  c >= ctot zero
-// where X is the channel concatenation of the network inputs (DSen2Net.py:24,26).  The head convolution
-// then needs only its three vertical taps (TMA zero fill above / below the patch).
-//
-// dsen2_prep_from_patches : X given as NCHW fp32 patch stacks (model.predict drop-in, supres.py:65)
-// dsen2_prep_from_images  : X gathered straight from the HWC images -- fuses get_test_patches /
-//                           get_test_patches60 (patches.py:19-156: symmetric pad, crop), interp_patches
-//                           (patches.py:11-16: per-patch bilinear with mirror boundary) and the /2000 scaling
-//                           (supres.py:23-24,42-44) with the arithmetic of the standalone kernels.
+// Inference: "x_in16", NHWC fp16 with 16 channels per pixel as a hi tensor and a lo tensor (v = hi + lo to ~22 bits);
+// channel c = band c of the channel concatenation X of the network inputs (DSen2Net.py:24,26), zero above.
+//   dsen2_prep16_from_patches : X given as NCHW fp32 patch stacks (model.predict drop-in, supres.py:65)
+//   dsen2_prep16_from_images  : X gathered straight from the HWC images (float32 or uint16 DN) -- fuses get_test_patches /
+//                               get_test_patches60 (patches.py:19-156: symmetric pad, crop), interp_patches
+//                               (patches.py:11-16: per-patch bilinear with mirror boundary) and the /2000 scaling
+//                               (supres.py:23-24,42-44) with the arithmetic of the standalone kernels.
+// Training step (and networks without resblocks): "x_in", 64 channels per pixel = the three HORIZONTAL taps of the first
+// 3x3 convolution pre-gathered, x_in[n][y][x][t*16 + c] = X[n][c][y][x + t - 1] (zero outside the patch), because the
+// first layer's weight-gradient GEMM wants 128-byte pixel rows (dsen2_prep_from_patches).
 #include "common.cuh"
 #include "tiling.cuh"
 
@@ -33,58 +32,6 @@ __device__ __forceinline__ void store32(__half* dst, const Half16& h) {
   uint4* d = reinterpret_cast<uint4*>(dst);
   d[0] = s[0];
   d[1] = s[1];
-}
-
-// write the 16-channel vector of pixel (row, x) into the three tap slots that see it
-__device__ __forceinline__ void store_xin(__half* __restrict__ out_hi, __half* __restrict__ out_lo, long long row_base,
-                                          int x, int P, const Half16& hi, const Half16& lo) {
-  Half16 z;
-#pragma unroll
-  for (int c = 0; c < 16; ++c) z.v[c] = __float2half_rn(0.f);
-  __half* rh = out_hi + (row_base + x) * 64;
-  __half* rl = out_lo + (row_base + x) * 64;
-  store32(rh + 16, hi);
-  store32(rl + 16, lo);
-  store32(rh + 48, z);
-  store32(rl + 48, z);
-  if (x > 0) {
-    store32(rh - 64 + 32, hi);
-    store32(rl - 64 + 32, lo);
-  } else {
-    store32(rh, z);
-    store32(rl, z);
-  }
-  if (x < P - 1) {
-    store32(rh + 64, hi);
-    store32(rl + 64, lo);
-  } else {
-    store32(rh + 32, z);
-    store32(rl + 32, z);
-  }
-}
-
-__global__ void prep_from_patches_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x1, int c1,
-                                         const float* __restrict__ x2, int c2, int P, long long total,
-                                         __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
-  const long long PP = (long long)P * P;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const long long n = idx / PP;
-    const int rem = (int)(idx - n * PP);
-    const int x = rem % P;
-    float v[16];
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      float t = 0.f;
-      if (c < c0) t = __ldg(x0 + (n * c0 + c) * PP + rem);
-      else if (c < c0 + c1) t = __ldg(x1 + (n * c1 + (c - c0)) * PP + rem);
-      else if (c < c0 + c1 + c2) t = __ldg(x2 + (n * c2 + (c - c0 - c1)) * PP + rem);
-      v[c] = t;
-    }
-    Half16 hi, lo;
-    split16(v, hi, lo);
-    store_xin(out_hi, out_lo, idx - x, x, P, hi, lo);
-  }
 }
 
 struct PrepSource {
@@ -206,9 +153,8 @@ __global__ void pack_head16_weights_kernel(const float* __restrict__ hwio, int c
   }
 }
 
-// ---- row-block variants (P <= 256): coalesced x_in stores ------------------------------------------------------
-// The thread-per-pixel kernels above write every 128-byte x_in row in six 32-byte pieces from three different threads
-// (24 scattered 16-byte stores per thread: 2.6 TB/s).  Here a block owns R = 256 / P whole patch rows: each thread
+// ---- 64-channel form (P <= 256): coalesced x_in stores ---------------------------------------------------------
+// A block owns R = 256 / P whole patch rows: each thread
 // computes its pixel's 16-channel vector once, parks hi / lo in shared memory, and the block then writes the rows
 // out as contiguous 16-byte chunks (lane = chunk: a warp store covers four full 128-byte lines).
 __device__ __forceinline__ void rowblock_store(const Half16& hi, const Half16& lo, bool active, int r, int x, int P, int R,
@@ -278,34 +224,6 @@ __global__ void prep_from_patches_rows_kernel(const float* __restrict__ x0, int 
   rowblock_store(hi, lo, active, r, x, P, R, first_row, total_rows, out_hi, out_lo);
 }
 
-__global__ void prep_from_images_rows_kernel(PrepSource s0, PrepSource s1, PrepSource s2, int nsrc, int plr, int blr, int P,
-                                             int R, Tiling tl, int first_patch, long long total_rows, float divisor,
-                                             __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
-  const long long first_row = (long long)blockIdx.x * R;
-  const int r = threadIdx.x / P, x = threadIdx.x - r * P;
-  const long long row = first_row + r;
-  const bool active = r < R && row < total_rows;
-  Half16 hi, lo;
-  if (active) {
-    const int local = (int)(row / P);
-    const int y = (int)(row - (long long)local * P);
-    const int patch = first_patch + local;
-    float v[16];
-#pragma unroll
-    for (int c = 0; c < 16; ++c) v[c] = 0.f;
-    if (patch < tl.n_i * tl.n_j) {               // surplus patches of the allocated stack stay zero (patches.py:32-39)
-      const int ti = patch / tl.n_j, tj = patch - ti * tl.n_j;
-      const int si = ti < tl.k_i ? ti * tl.stride : tl.last_i;
-      const int sj = tj < tl.k_j ? tj * tl.stride : tl.last_j;
-      prep_gather<float, 4, 0>(s0, si, sj, plr, blr, y, x, divisor, v);     // 10 m bands   (DSen2Net.py:24,26 order)
-      prep_gather<float, 6, 4>(s1, si, sj, plr, blr, y, x, divisor, v);     // 20 m bands
-      if (nsrc == 3) prep_gather<float, 2, 10>(s2, si, sj, plr, blr, y, x, divisor, v);   // 60 m bands
-    }
-    split16(v, hi, lo);
-  }
-  rowblock_store(hi, lo, active, r, x, P, R, first_row, total_rows, out_hi, out_lo);
-}
-
 // launch geometry of the row-block kernels: R rows per block, R * P threads rounded up to whole warps
 struct RowBlock { int R, threads; size_t smem; };
 static RowBlock row_block(int P) {
@@ -314,33 +232,6 @@ static RowBlock row_block(int P) {
   g.threads = (g.R * P + 31) / 32 * 32;
   g.smem = (size_t)2 * g.R * (P + 2) * 2 * sizeof(uint4);
   return g;
-}
-
-__global__ void prep_from_images_kernel(PrepSource s0, PrepSource s1, PrepSource s2, int nsrc, int plr, int blr, int P,
-                                        Tiling tl, int first_patch, long long total, float divisor,
-                                        __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
-  const long long PP = (long long)P * P;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int local = (int)(idx / PP);
-    const int rem = (int)(idx - (long long)local * PP);
-    const int y = rem / P, x = rem - y * P;
-    const int patch = first_patch + local;
-    float v[16];
-#pragma unroll
-    for (int c = 0; c < 16; ++c) v[c] = 0.f;
-    if (patch < tl.n_i * tl.n_j) {               // surplus patches of the allocated stack stay zero (patches.py:32-39)
-      const int ti = patch / tl.n_j, tj = patch - ti * tl.n_j;
-      const int si = ti < tl.k_i ? ti * tl.stride : tl.last_i;
-      const int sj = tj < tl.k_j ? tj * tl.stride : tl.last_j;
-      prep_gather<float, 4, 0>(s0, si, sj, plr, blr, y, x, divisor, v);     // 10 m bands   (DSen2Net.py:24,26 order)
-      prep_gather<float, 6, 4>(s1, si, sj, plr, blr, y, x, divisor, v);     // 20 m bands
-      if (nsrc == 3) prep_gather<float, 2, 10>(s2, si, sj, plr, blr, y, x, divisor, v);   // 60 m bands
-    }
-    Half16 hi, lo;
-    split16(v, hi, lo);
-    store_xin(out_hi, out_lo, idx - x, x, P, hi, lo);
-  }
 }
 
 // head weights: [dy][2F rows = W_hi ; W_lo][64: k = dxi*16 + c]
@@ -387,59 +278,13 @@ extern "C" int dsen2_prep_from_patches(const float* d_x0, int c0, const float* d
                 "dsen2_prep_from_patches: bad sizes (%d+%d+%d channels, at most 16)", c0, c1, c2);
   DSEN2_REQUIRE(((uintptr_t)d_xin_hi % 16) == 0 && ((uintptr_t)d_xin_lo % 16) == 0, DSEN2_E_ALIGN,
                 "dsen2_prep_from_patches: outputs must be 16-byte aligned");
+  DSEN2_REQUIRE(P <= 256, DSEN2_E_BADARG, "dsen2_prep_from_patches: patches of at most 256 x 256 (got %d)", P);
   if (n == 0) return 0;
-  const long long total = (long long)n * P * P;
-  if (P <= 256) {
-    const RowBlock g = row_block(P);
-    const long long rows = (long long)n * P;
-    prep_from_patches_rows_kernel<<<(unsigned)((rows + g.R - 1) / g.R), g.threads, g.smem, (cudaStream_t)stream>>>(
-        d_x0, c0, d_x1, c1, d_x2, c2, P, g.R, rows, (__half*)d_xin_hi, (__half*)d_xin_lo);
-    return check_launch("prep_from_patches");
-  }
-  const int block = 256;
-  prep_from_patches_kernel<<<grid_for(total, block), block, 0, (cudaStream_t)stream>>>(
-      d_x0, c0, d_x1, c1, d_x2, c2, P, total, (__half*)d_xin_hi, (__half*)d_xin_lo);
+  const RowBlock g = row_block(P);
+  const long long rows = (long long)n * P;
+  prep_from_patches_rows_kernel<<<(unsigned)((rows + g.R - 1) / g.R), g.threads, g.smem, (cudaStream_t)stream>>>(
+      d_x0, c0, d_x1, c1, d_x2, c2, P, g.R, rows, (__half*)d_xin_hi, (__half*)d_xin_lo);
   return check_launch("prep_from_patches");
-}
-
-extern "C" int dsen2_prep_from_images(const float* d_img10, const float* d_img20, const float* d_img60, int H, int W,
-                                      int patch, int border, int first_patch, int num_patches, float divisor,
-                                      void* d_xin_hi, void* d_xin_lo, void* stream) {
-  DSEN2_REQUIRE(d_img10 && d_img20 && d_xin_hi && d_xin_lo, DSEN2_E_BADARG, "dsen2_prep_from_images: null pointer");
-  const int r = d_img60 ? 6 : 2;                 // the tiling grid is the coarsest input (patches.py:45-53,114-122)
-  DSEN2_REQUIRE(H > 0 && W > 0 && H % r == 0 && W % r == 0, DSEN2_E_BADARG,
-                "dsen2_prep_from_images: 10 m size %dx%d must be a multiple of %d", H, W, r);
-  DSEN2_REQUIRE(patch > 0 && border >= 0 && patch % r == 0 && border % r == 0 && patch > 2 * border, DSEN2_E_BADARG,
-                "dsen2_prep_from_images: patch %d / border %d must be multiples of %d", patch, border, r);
-  DSEN2_REQUIRE(first_patch >= 0 && num_patches >= 0 && divisor != 0.f, DSEN2_E_BADARG,
-                "dsen2_prep_from_images: bad patch range / divisor");
-  DSEN2_REQUIRE(((uintptr_t)d_xin_hi % 16) == 0 && ((uintptr_t)d_xin_lo % 16) == 0, DSEN2_E_ALIGN,
-                "dsen2_prep_from_images: outputs must be 16-byte aligned");
-  const int plr = patch / r, blr = border / r, gh = H / r, gw = W / r;
-  DSEN2_REQUIRE(gh + 2 * blr >= plr && gw + 2 * blr >= plr, DSEN2_E_BADARG,
-                "dsen2_prep_from_images: image %dx%d smaller than one patch (%d)", H, W, patch);
-  if (num_patches == 0) return 0;
-  const Tiling tl = make_tiling(gh, gw, plr, blr);
-  DSEN2_REQUIRE(first_patch + num_patches <= (tl.k_i + 1) * (tl.k_j + 1), DSEN2_E_BADARG,
-                "dsen2_prep_from_images: patch range [%d,%d) exceeds the %d allocated patches", first_patch,
-                first_patch + num_patches, (tl.k_i + 1) * (tl.k_j + 1));
-  PrepSource s0{d_img10, H, W, r, 1};
-  PrepSource s1{d_img20, H / 2, W / 2, r / 2, 2};
-  PrepSource s2{d_img60, H / 6, W / 6, 1, 6};
-  const long long total = (long long)num_patches * patch * patch;
-  if (patch <= 256) {
-    const RowBlock g = row_block(patch);
-    const long long rows = (long long)num_patches * patch;
-    prep_from_images_rows_kernel<<<(unsigned)((rows + g.R - 1) / g.R), g.threads, g.smem, (cudaStream_t)stream>>>(
-        s0, s1, s2, d_img60 ? 3 : 2, plr, blr, patch, g.R, tl, first_patch, rows, divisor, (__half*)d_xin_hi,
-        (__half*)d_xin_lo);
-    return check_launch("prep_from_images");
-  }
-  const int block = 256;
-  prep_from_images_kernel<<<grid_for(total, block), block, 0, (cudaStream_t)stream>>>(
-      s0, s1, s2, d_img60 ? 3 : 2, plr, blr, patch, tl, first_patch, total, divisor, (__half*)d_xin_hi,
-      (__half*)d_xin_lo);
-  return check_launch("prep_from_images");
 }
 
 extern "C" int dsen2_pack_head_weights(const float* d_hwio, int cin, int feature_size, void* d_packed, void* stream) {

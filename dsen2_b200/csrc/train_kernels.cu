@@ -3,14 +3,10 @@
 //   backward data path   = the CTA-pair convolution kernels of conv_pair.cu on flipped / transposed weights
 //                          (dsen2_pack_dgrad_weights), with the ReLU-backward mask or the fp32 "gradient trunk"
 //                          accumulate epilogue -- no new convolution code;
-//   weight gradients     = dsen2_wgrad: per tap a K-major tcgen05 GEMM over the pixel dimension,
+//   weight gradients     = dsen2_wgrad_nhwc: a tcgen05 GEMM over the pixel dimension straight from the NHWC tensors,
 //                              dW[tap][ci][co] = sum_px X[px + off(tap)][ci] * dY[px][co]
-//                          on PLANAR, zero-bordered fp16 copies of X and dY ([channel][n][H+2][Wp], Wp = W+2 rounded
-//                          up to 8): the vertical tap offset is then a shift of the K coordinate of the TMA box by a
-//                          multiple of Wp (TMA needs 16-byte aligned inner coordinates -- measured: odd shifts fault),
-//                          the horizontal offset picks one of three pre-shifted copies of X, and the zero border of
-//                          dY makes every out-of-patch product vanish (Conv2D 'same' padding, DSen2Net.py:10,12);
-//   the rest             = layout changes, bias gradients (row sums), MAE loss + gradient, Keras-2 Nadam.
+//                          (MN-major operands, see wgrad_direct_kernel);
+//   the rest             = layout changes, bias gradients (column sums), MAE loss + gradient, Keras-2 Nadam.
 // Gradients flow in fp16 with a power-of-two loss scale chosen by the host so that d(pred) = +-2^-4 exactly.
 #include <stdlib.h>
 
@@ -22,71 +18,6 @@ namespace dsen2 {
 // ------------------------------------------------------------------------------------------ //
 // layout changes
 // ------------------------------------------------------------------------------------------ //
-__host__ __device__ inline int planar_wp(int W) { return (W + 2 + 7) / 8 * 8; }
-
-// NHWC fp16 (n,H,W,C) [optionally masked by a forward activation > 0] -> planar zero-bordered [copies][rows][kpitch]
-// fp16, k = (b*(H+2) + y+1)*Wp + x+1.  Copy d (blockIdx.z, three copies) holds the tensor shifted by d-1 along k:
-// out_d[c][k] = planar[c][k + d - 1].  64(k) x 64(c) tiles through shared memory: coalesced on both sides.
-__global__ void nhwc_to_planar_kernel(const __half* __restrict__ in, const __half* __restrict__ mask, int n, int H, int W,
-                                      int C, int rows, long long kpitch, int copies, __half* __restrict__ out) {
-  __shared__ __half tile[64][66];
-  const int Hp = H + 2, Wp = planar_wp(W);
-  const long long ktot = (long long)n * Hp * Wp;
-  const long long k0 = (long long)blockIdx.x * 64;
-  const int c0 = blockIdx.y * 64;
-  const int d = copies == 3 ? (int)blockIdx.z - 1 : 0;
-  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;      // 256 threads: 4 rows of 64
-  for (int kk = ty; kk < 64; kk += 4) {                       // load: threads along channels
-    const long long k = k0 + kk + d;
-    __half v = __float2half_rn(0.f);
-    const int c = c0 + tx;
-    if (k >= 0 && k < ktot && c < C) {
-      const int xp = (int)(k % Wp), yp = (int)((k / Wp) % Hp), b = (int)(k / ((long long)Wp * Hp));
-      if (xp >= 1 && xp <= W && yp >= 1 && yp <= H) {
-        const long long idx = (((long long)b * H + (yp - 1)) * W + (xp - 1)) * C + c;
-        v = in[idx];
-        if (mask != nullptr && !(__half2float(mask[idx]) > 0.f)) v = __float2half_rn(0.f);
-      }
-    }
-    tile[kk][tx] = v;
-  }
-  __syncthreads();
-  __half* dst = out + (long long)blockIdx.z * rows * kpitch;
-  for (int cc = ty; cc < 64; cc += 4) {                       // store: threads along k
-    const int c = c0 + cc;
-    const long long k = k0 + tx;
-    if (c < rows && k < kpitch) dst[(long long)c * kpitch + k] = tile[tx][cc];
-  }
-}
-
-// up to three NCHW fp32 inputs (n,c_i,H,W), concatenated along channels, times `scale` -> planar zero-bordered fp16
-__global__ void nchw_to_planar_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x1, int c1,
-                                      const float* __restrict__ x2, int c2, int n, int H, int W, int rows, long long kpitch,
-                                      int copies, float scale, __half* __restrict__ out) {
-  const int Hp = H + 2, Wp = planar_wp(W);
-  const long long ktot = (long long)n * Hp * Wp, per = (long long)rows * kpitch, total = per * copies;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int copy = (int)(idx / per);
-    const long long rem = idx - copy * per;
-    const int c = (int)(rem / kpitch);
-    const long long k = rem - (long long)c * kpitch + (copies == 3 ? copy - 1 : 0);
-    float v = 0.f;
-    if (k >= 0 && k < ktot && c < c0 + c1 + c2) {
-      const int xp = (int)(k % Wp), yp = (int)((k / Wp) % Hp), b = (int)(k / ((long long)Wp * Hp));
-      if (xp >= 1 && xp <= W && yp >= 1 && yp <= H) {
-        const float* src;
-        int cc = c, cn;
-        if (cc < c0) { src = x0; cn = c0; }
-        else if (cc < c0 + c1) { src = x1; cc -= c0; cn = c1; }
-        else { src = x2; cc -= c0 + c1; cn = c2; }
-        v = src[(((long long)b * cn + cc) * H + (yp - 1)) * W + (xp - 1)] * scale;
-      }
-    }
-    out[idx] = __float2half_rn(v);
-  }
-}
-
 // up to three NCHW fp32 inputs (n,c_i,H,W), at most 16 channels in total, concatenated along channels -> the first 16
 // channels of NHWC fp16 (n,H,W,cpad).  One thread per pixel: plane reads are coalesced across the warp, each thread
 // writes one 32-byte sector.  (The remaining channels are zeroed by a memset in the entry point.)
@@ -153,30 +84,6 @@ __global__ void colsum_nhwc_kernel(const __half* __restrict__ in, long long npix
 #pragma unroll
     for (int i = 0; i < 16; ++i) s += red[i][threadIdx.x];
     atomicAdd(out + threadIdx.x, s * scale);
-  }
-}
-
-// out[r] = scale * sum_k in[r][k]   (bias gradients from a planar gradient tensor: its borders are zero)
-__global__ void rowsum_kernel(const __half* __restrict__ in, long long kpitch, float scale, float* __restrict__ out) {
-  const __half* row = in + (long long)blockIdx.x * kpitch;
-  float acc = 0.f;
-  for (long long k = threadIdx.x * 8LL; k + 8 <= kpitch; k += blockDim.x * 8LL) {
-    const uint4 q = *reinterpret_cast<const uint4*>(row + k);
-    const __half2* h = reinterpret_cast<const __half2*>(&q);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = __half22float2(h[j]);
-      acc += f.x + f.y;
-    }
-  }
-  __shared__ float red[32];
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    acc = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (threadIdx.x == 0) out[blockIdx.x] = acc * scale;
   }
 }
 
@@ -276,112 +183,6 @@ __device__ __forceinline__ TileXY3 decode_tile3(uint32_t tile, uint32_t tiles_x,
   return t;
 }
 
-// ------------------------------------------------------------------------------------------ //
-// weight gradient GEMM (tcgen05, one CTA per (K split, tap))
-// ------------------------------------------------------------------------------------------ //
-static constexpr int kWgStages = 6;
-static constexpr int kWgThreads = 192;          // warp 0 TMA, warp 1 MMA + TMEM, warps 2-5 epilogue
-
-template <int N>
-__global__ void __launch_bounds__(kWgThreads, 1)
-wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_dy, int kblocks_total,
-             int kblocks_per_split, int wp, float scale, float* __restrict__ dw) {
-  constexpr int A_BYTES = 128 * 128, B_BYTES = N * 128;
-  constexpr int STAGE = A_BYTES + (B_BYTES < 1024 ? 1024 : B_BYTES);
-  constexpr int TMEM_COLS = N < 32 ? 32 : N;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kWgStages * STAGE);
-  uint64_t* empty = full + kWgStages;
-  uint64_t* done = empty + kWgStages;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done + 1);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tap = blockIdx.y;
-  const int shift = (tap / 3 - 1) * wp;        // vertical tap: multiple of 8 elements (16-byte aligned TMA coordinate)
-  const int copy = tap % 3;                    // horizontal tap: pre-shifted copy of X
-  const int kb0 = blockIdx.x * kblocks_per_split;
-  const int kb1 = min(kblocks_total, kb0 + kblocks_per_split);
-  const int nkb = kb1 - kb0;                    // >= 1 by construction of the grid
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_x);
-    tma_prefetch_desc(&tm_dy);
-    for (int i = 0; i < kWgStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    mbar_init(done, 1);
-    mbar_fence_init();
-  }
-  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_ptr);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-
-  if (warp == 0) {
-    if (elect_one()) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int i = 0; i < nkb; ++i) {
-        mbar_wait(&empty[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * STAGE;
-        mbar_expect_tx(&full[stage], A_BYTES + B_BYTES);
-        tma_load_3d(sa, &tm_x, &full[stage], (kb0 + i) * 64 + shift, 0, copy);   // X window of this tap (OOB = zero)
-        tma_load_2d(sa + A_BYTES, &tm_dy, &full[stage], (kb0 + i) * 64, 0);
-        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_f16(128, N);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int i = 0; i < nkb; ++i) {
-        mbar_wait(&full[stage], phase);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * STAGE), sb = sa + A_BYTES;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16_ss(tmem_base, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sb + k * 32), idesc, (uint32_t)((i | k) != 0));
-        umma_commit(&empty[stage]);
-        if (i == nkb - 1) umma_commit(done);
-        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else {
-    const int wq = warp & 3;                     // warps 2,3,4,5 -> lane quarters 2,3,0,1
-    mbar_wait(done, 0);
-    tc_fence_after();
-    const int row = wq * 32 + lane;              // input channel
-    float* dst = dw + ((long long)tap * 128 + row) * N;
-#pragma unroll 1
-    for (int c0 = 0; c0 < N; c0 += 16) {
-      uint32_t r[16];
-      tmem_ld_32x16(tmem_base + ((uint32_t)(wq * 32) << 16) + c0, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 16; ++j) atomicAdd(dst + c0 + j, __uint_as_float(r[j]) * scale);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
-}
-
-template <int N>
-static int launch_wgrad(const CUtensorMap& tx, const CUtensorMap& ty, int kblocks, int splits, int per, int wp,
-                        float scale, float* dw, cudaStream_t stream) {
-  constexpr int STAGE = 128 * 128 + (N * 128 < 1024 ? 1024 : N * 128);
-  constexpr int SMEM = kWgStages * STAGE + 256 + 1024;
-  static bool configured[64] = {};
-  if (needs_config(configured)) {
-    DSEN2_CUDA(cudaFuncSetAttribute(wgrad_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-  }
-  wgrad_kernel<N><<<dim3(splits, 9), kWgThreads, SMEM, stream>>>(tx, ty, kblocks, per, wp, scale, dw);
-  return check_launch("wgrad_kernel");
-}
-
-// ------------------------------------------------------------------------------------------ //
-// weight gradient straight from the NHWC tensors (no layout change): MN-major operands
 // ------------------------------------------------------------------------------------------ //
 // dW[tap][ci][co] = sum_px X[px + off(tap)][ci] * dY[px][co]: the reduction runs over PIXELS, and in NHWC a pixel
 // is a 128-byte row of 64 channels -- exactly an MN-major (M = ci or N = co contiguous, K = pixel) UMMA operand.
@@ -525,10 +326,10 @@ extern "C" int dsen2_wgrad_nhwc(const void* d_x, const void* d_dy, int n, int H,
   CUtensorMap tx, ty;
   const uint64_t dims[4] = {128, (uint64_t)W, (uint64_t)H, (uint64_t)n};
   const uint32_t bx[4] = {64, 10, 16, 1};
-  rc = make_tmap_f16(&tx, d_x, 4, dims, bx);
+  rc = make_tmap_f16_sw(&tx, d_x, 4, dims, bx, 128);
   if (rc) return rc;
   const uint32_t by[4] = {64, 8, 16, 1};
-  rc = make_tmap_f16(&ty, d_dy, 4, dims, by);
+  rc = make_tmap_f16_sw(&ty, d_dy, 4, dims, by, 128);
   if (rc) return rc;
   constexpr int SMEM = kWdStages * kWdStage + 256 + 1024;
   static_assert(kWdStages * kWdStage >= 3 * 65536, "the drain reuses the pipeline stages for three 64 KB accumulators");
@@ -539,34 +340,6 @@ extern "C" int dsen2_wgrad_nhwc(const void* d_x, const void* d_dy, int n, int H,
   wgrad_direct_kernel<<<dim3(splits, 3), kWdThreads, SMEM, (cudaStream_t)stream>>>(tx, ty, tiles_x, tiles_y, (int)tiles, per,
                                                                                  scale, d_dw);
   return check_launch("wgrad_direct_kernel");
-}
-
-extern "C" long long dsen2_planar_pitch(int n, int H, int W) {
-  const long long k = (long long)n * (H + 2) * planar_wp(W);
-  return (k + 63) / 64 * 64;
-}
-
-extern "C" int dsen2_nhwc_to_planar(const void* d_in, const void* d_mask, int n, int H, int W, int C, int rows,
-                                    int copies, void* d_out, void* stream) {
-  DSEN2_REQUIRE(d_in && d_out, DSEN2_E_BADARG, "dsen2_nhwc_to_planar: null pointer");
-  DSEN2_REQUIRE(n > 0 && H > 0 && W > 0 && C > 0 && rows >= C && (copies == 1 || copies == 3), DSEN2_E_BADARG,
-                "dsen2_nhwc_to_planar: bad sizes");
-  const long long kpitch = dsen2_planar_pitch(n, H, W);
-  dim3 grid((unsigned)(kpitch / 64), (unsigned)((rows + 63) / 64), (unsigned)copies);
-  nhwc_to_planar_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)d_in, (const __half*)d_mask, n, H, W, C, rows,
-                                                                 kpitch, copies, (__half*)d_out);
-  return check_launch("nhwc_to_planar");
-}
-
-extern "C" int dsen2_nchw_to_planar(const float* d_x0, int c0, const float* d_x1, int c1, const float* d_x2, int c2, int n,
-                                    int H, int W, int rows, int copies, float scale, void* d_out, void* stream) {
-  DSEN2_REQUIRE(d_x0 && d_out && (c1 == 0 || d_x1) && (c2 == 0 || d_x2), DSEN2_E_BADARG, "dsen2_nchw_to_planar: null pointer");
-  DSEN2_REQUIRE(n > 0 && H > 0 && W > 0 && c0 > 0 && c1 >= 0 && c2 >= 0 && rows >= c0 + c1 + c2 && (copies == 1 || copies == 3),
-                DSEN2_E_BADARG, "dsen2_nchw_to_planar: bad sizes");
-  const long long kpitch = dsen2_planar_pitch(n, H, W), total = kpitch * rows * copies;
-  nchw_to_planar_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d_x0, c0, d_x1, c1, d_x2, c2, n, H, W, rows,
-                                                                                kpitch, copies, scale, (__half*)d_out);
-  return check_launch("nchw_to_planar");
 }
 
 extern "C" int dsen2_nchw_to_nhwc_f16(const float* d_x0, int c0, const float* d_x1, int c1, const float* d_x2, int c2,
@@ -596,12 +369,6 @@ extern "C" int dsen2_colsum_nhwc(const void* d_in, long long npix, float scale, 
   if (blocks > cap) blocks = cap;
   colsum_nhwc_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __half*)d_in, npix, scale, d_out);
   return check_launch("colsum_nhwc");
-}
-
-extern "C" int dsen2_rowsum(const void* d_planar, int rows, long long kpitch, float scale, float* d_out, void* stream) {
-  DSEN2_REQUIRE(d_planar && d_out && rows > 0 && kpitch > 0 && kpitch % 8 == 0, DSEN2_E_BADARG, "dsen2_rowsum: bad arguments");
-  rowsum_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>((const __half*)d_planar, kpitch, scale, d_out);
-  return check_launch("rowsum");
 }
 
 extern "C" int dsen2_mae_grad(const float* d_pred, const float* d_y, long long total, float gscale, float* d_dpred,
@@ -637,33 +404,3 @@ extern "C" int dsen2_pack_dgrad_weights(const float* d_hwio, int cin, int cout, 
   return check_launch("pack_dgrad_weights");
 }
 
-extern "C" int dsen2_wgrad(const void* d_x_planar, const void* d_dy_planar, int n, int H, int W, int n_cols, float scale,
-                           float* d_dw, void* stream) {
-  DSEN2_REQUIRE(d_x_planar && d_dy_planar && d_dw, DSEN2_E_BADARG, "dsen2_wgrad: null pointer");
-  DSEN2_REQUIRE(n > 0 && H > 0 && W > 0 && (n_cols == 16 || n_cols == 128), DSEN2_E_BADARG,
-                "dsen2_wgrad: dY must have 16 or 128 planar rows (got %d)", n_cols);
-  DSEN2_REQUIRE(((uintptr_t)d_x_planar % 16) == 0 && ((uintptr_t)d_dy_planar % 16) == 0, DSEN2_E_ALIGN,
-                "dsen2_wgrad: operands must be 16-byte aligned");
-  int sms = 0;
-  int rc = device_sm_count_and_check(&sms);
-  if (rc) return rc;
-  const long long kpitch = dsen2_planar_pitch(n, H, W);
-  const int kblocks = (int)(kpitch / 64);
-  int splits = sms / 9;                                   // one wave: splits x 9 taps CTAs
-  if (splits > kblocks) splits = kblocks;
-  if (splits < 1) splits = 1;
-  const int per = (kblocks + splits - 1) / splits;
-  splits = (kblocks + per - 1) / per;
-  CUtensorMap tx, ty;
-  const uint64_t dx[3] = {(uint64_t)kpitch, 128, 3};
-  const uint32_t bx[3] = {64, 128, 1};
-  rc = make_tmap_f16(&tx, d_x_planar, 3, dx, bx);
-  if (rc) return rc;
-  const uint64_t dy[2] = {(uint64_t)kpitch, (uint64_t)n_cols};
-  const uint32_t by[2] = {64, (uint32_t)n_cols};
-  rc = make_tmap_f16(&ty, d_dy_planar, 2, dy, by);
-  if (rc) return rc;
-  const int wp = planar_wp(W);
-  if (n_cols == 128) return launch_wgrad<128>(tx, ty, kblocks, splits, per, wp, scale, d_dw, (cudaStream_t)stream);
-  return launch_wgrad<16>(tx, ty, kblocks, splits, per, wp, scale, d_dw, (cudaStream_t)stream);
-}

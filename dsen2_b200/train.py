@@ -172,7 +172,7 @@ class Trainer:
         with self.torch.cuda.device(self.dev):
             _capi.check(lib.dsen2_pack_head_weights(ptr(self.kernel(0)), self.ctot, F, ptr(self.w_fwd[0]), st), "pack head")
             for i in range(1, nl - 1):
-                _capi.check(lib.dsen2_pack_conv_weights(ptr(self.kernel(i)), F, F, F, F, 0, ptr(self.w_fwd[i]), None, st),
+                _capi.check(lib.dsen2_pack_conv_weights(ptr(self.kernel(i)), F, F, F, F, ptr(self.w_fwd[i]), st),
                             "pack trunk")
                 # second conv of a resBlock is followed by Lambda(x * 0.1) (DSen2Net.py:13): fold it into the operand
                 scale = 0.1 if i % 2 == 0 else 1.0
@@ -213,8 +213,8 @@ class Trainer:
                                         ptr(b['x_hi'][0]), ptr(b['x_lo']) if L == 0 else None,
                                         ptr(b['x32']) if L > 0 else None, st), "head")
         for l in range(L):
-            _capi.check(lib.dsen2_conv3x3(ptr(b['x_hi'][l]), ptr(self.w_fwd[1 + 2 * l]), ptr(self.b_fwd[1 + 2 * l]), n, P, P, F, F,
-                                          9, _capi.EPI_RELU, None, None, 0.0, ptr(b['t'][l]), None, None, None, 0, st), "conv1")
+            _capi.check(lib.dsen2_conv_relu(ptr(b['x_hi'][l]), ptr(self.w_fwd[1 + 2 * l]), ptr(self.b_fwd[1 + 2 * l]), n, P, P, F,
+                                            ptr(b['t'][l]), st), "conv1")
             _capi.check(lib.dsen2_conv_res32(ptr(b['t'][l]), ptr(self.w_fwd[2 + 2 * l]), ptr(self.b_fwd[2 + 2 * l]), n, P, P, 0.1,
                                              ptr(b['x32']), ptr(b['x_hi'][l + 1]), ptr(b['x_lo']) if l == L - 1 else None, st),
                         "conv2")

@@ -92,70 +92,40 @@ int dsen2_down_pixel_aggr(const float* d_img, int H, int W, int C, int scale, co
                           float* d_tmp, double* d_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Network (utils/DSen2Net.py:9-43) -- tcgen05 implicit-GEMM convolutions, fp16 operands, fp32
- * accumulation in TMEM, fp32-equivalent (fp16 hi + fp16 lo) residual trunk.
- * Activations are NHWC fp16 with the channel count padded to a multiple of 64.
+ * Network (utils/DSen2Net.py:9-43): tcgen05 implicit-GEMM convolutions on CTA pairs (cta_group::2), fp16 operands,
+ * fp32 accumulation in TMEM (csrc/conv_pair.cu).  Activations are NHWC fp16.  One TMA halo-box load per tile and
+ * 64-channel k-block serves all nine taps; zero 'same' padding at the PATCH edge is TMA out-of-bounds fill.  The
+ * first and last layer are computed at fp32-equivalent precision (operands split v = hi + lo, fp16 each); the
+ * residual trunk between resblocks is held as fp16 + 8 bits (below).  feature_size 128 (DSen2: the layer's weights
+ * stay resident in shared memory) or 256 (VDSen2: weights stream through a shared-memory ring).
  * ------------------------------------------------------------------------------------------- */
 
-/* Keras HWIO kernel (3,3,cin,cout) fp32 -> [tap][cout_pad][cin_pad] fp16 (K-major B operand).
- * im2col != 0 packs the same kernel as a 1x1 convolution over the 9*cin im2col channels:
- * [1][cout_pad][cin_pad >= 9*cin], k = (ky*3+kx)*cin + c  (head conv, DSen2Net.py:29).        */
-int dsen2_pack_conv_weights(const float* d_hwio, int cin, int cout, int cin_pad, int cout_pad,
-                            int im2col, void* d_packed_f16, void* d_packed_lo_f16 /* optional: f16(w - hi) */,
+/* Keras HWIO kernel (3,3,cin,cout) fp32 -> [tap][cout_pad][cin_pad] fp16 (K-major B operand of a trunk layer). */
+int dsen2_pack_conv_weights(const float* d_hwio, int cin, int cout, int cin_pad, int cout_pad, void* d_packed_f16,
                             void* stream);
 
-/* Concatenate (DSen2Net.py:24,26) the NCHW fp32 inputs (n, c_i, P, P) and write the zero-padded
- * 3x3 im2col of the concatenation as NHWC fp16 (n, P, P, k_pad), k = (ky*3+kx)*sum(c_i) + c.      */
-int dsen2_pack_head_input(const float* d_x0, int c0, const float* d_x1, int c1, const float* d_x2, int c2,
-                          int n, int P, int k_pad, void* d_out_f16, void* d_out_lo_f16 /* optional */, void* stream);
+/* First convolution of a resBlock (DSen2Net.py:10-11): d_out = f16(relu(conv3x3(d_in) + bias)).
+ * d_in / d_out NHWC fp16 (n, H, W, F); d_w from dsen2_pack_conv_weights(cin_pad = cout_pad = F); d_bias fp32 (F).   */
+int dsen2_conv_relu(const void* d_in, const void* d_w, const float* d_bias, int n, int H, int W, int feature_size,
+                    void* d_out, void* stream);
 
-/* Epilogues of dsen2_conv3x3 */
-#define DSEN2_EPI_RELU      0  /* out_hi = f16(relu(acc+bias)); out_lo (optional) = f16(v - out_hi)      */
-#define DSEN2_EPI_RESIDUAL  1  /* v = (res_hi+res_lo) + res_scale*(acc+bias); out_hi/out_lo = split(v)   */
-#define DSEN2_EPI_TAIL_NCHW 2  /* out_f32[n,c,y,x] = acc + bias + skip_f32[n,c,y,x], c < cout_real        */
-
-/* One convolution layer over n patches of (H, W): taps = 9 (3x3, zero 'same' padding at the PATCH
- * edge, Conv2D(padding='same')) or 1 (1x1, used with the im2col head input).
- *   d_in       NHWC fp16 (n, H, W, cin_pad), cin_pad % 64 == 0
- *   d_w        packed weights from dsen2_pack_conv_weights, d_bias fp32 (cout_pad)
- *   cout_pad   16, 128 or 256 (UMMA N)
- * RELU:     d_out_hi (n,H,W,cout_pad) fp16, d_out_lo optional
- * RESIDUAL: d_res_hi/d_res_lo in, d_out_hi/d_out_lo out (may alias the res pointers)
- * TAIL:     d_skip_f32 / d_out_f32 NCHW (n, cout_real, H, W) fp32                                */
-int dsen2_conv3x3(const void* d_in, const void* d_w, const float* d_bias,
-                  int n, int H, int W, int cin_pad, int cout_pad, int taps, int epilogue,
-                  const void* d_res_hi, const void* d_res_lo, float res_scale,
-                  void* d_out_hi, void* d_out_lo,
-                  const float* d_skip_f32, float* d_out_f32, int cout_real, void* stream);
-
-/* ---------------------------------------------------------------------------------------------
- * DSen2 (feature_size 128) fast path: CTA-pair (tcgen05 cta_group::2) kernels with the layer's weights
- * resident in shared memory and one TMA halo-box load per tile (csrc/conv_pair.cu).  dsen2_conv3x3
- * routes 128 -> 128 RELU / RESIDUAL layers there by itself; the first and last layer have their own
- * entry points because they are computed at fp32-equivalent precision (operands split hi + lo).
- *
- * Prepared network input "x_in": two NHWC fp16 tensors (n, P, P, 64), hi and lo (value = hi + lo).
- * Channel t*16 + c of pixel (y, x) holds input band c of pixel (y, x + t - 1) (t = 0..2; zero outside
- * the patch; bands in DSen2Net.py:24,26 concatenation order; at most 16 bands).
- * ------------------------------------------------------------------------------------------- */
+/* Prepared network input of the TRAINING step (and of a network without resblocks), "x_in": two NHWC fp16 tensors
+ * (n, P, P, 64), hi and lo (value = hi + lo).  Channel t*16 + c of pixel (y, x) holds input band c of pixel
+ * (y, x + t - 1) (t = 0..2; zero outside the patch; bands in DSen2Net.py:24,26 concatenation order; at most 16 bands):
+ * the first layer's weight-gradient GEMM wants 128-byte pixel rows.  Inference uses the 16-channel form below.   */
 
 /* x_in from NCHW fp32 patch stacks -- the arrays model.predict receives (supres.py:27,47,65). */
 int dsen2_prep_from_patches(const float* d_x0, int c0, const float* d_x1, int c1, const float* d_x2, int c2,
                             int n, int P, void* d_xin_hi, void* d_xin_lo, void* stream);
 
-/* x_in straight from the HWC float32 images: fuses get_test_patches / get_test_patches60
- * (utils/patches.py:19-156), interp_patches (:11-16) and the /SCALE of supres.py:23-24,42-44 for
- * patches [first_patch, first_patch + num_patches).  d_img60 == NULL selects the 20 m path
- * (tiling grid = 20 m pixels), otherwise the 60 m path.  patch / border are the 10 m values of
- * supres.py:22,41 (128 / 8 and 192 / 12).                                                        */
-int dsen2_prep_from_images(const float* d_img10, const float* d_img20, const float* d_img60, int H, int W,
-                           int patch, int border, int first_patch, int num_patches, float divisor,
-                           void* d_xin_hi, void* d_xin_lo, void* stream);
-
-/* The same preparation without the tap gather (what the inference path uses): x_in16 hi / lo, NHWC fp16
- * (n, P, P, 16), channel c = band c of the concatenated inputs (DSen2Net.py:24,26), c >= sum(c_i) zero: 32 bytes per
- * pixel and tensor instead of 128.  dsen2_conv_head16_q reads it with all nine taps; dsen2_conv_tail16[_stitch]
- * take the global skip from it.  Arguments as dsen2_prep_from_patches / dsen2_prep_from_images.               */
+/* Prepared input of the inference path: x_in16 hi / lo, NHWC fp16 (n, P, P, 16), channel c = band c of the concatenated
+ * inputs (DSen2Net.py:24,26), c >= sum(c_i) zero.  dsen2_conv_head16_q reads it with all nine taps;
+ * dsen2_conv_tail16[_stitch] take the global skip from it.
+ *   dsen2_prep16_from_patches: from the NCHW fp32 patch stacks model.predict receives (supres.py:27,47,65);
+ *   dsen2_prep16_from_images:  straight from the HWC images -- fuses get_test_patches / get_test_patches60
+ *       (utils/patches.py:19-156), interp_patches (:11-16) and the /SCALE of supres.py:23-24,42-44 for patches
+ *       [first_patch, first_patch + num_patches).  d_img60 == NULL selects the 20 m path (tiling grid = 20 m pixels),
+ *       otherwise the 60 m path.  patch / border are the 10 m values of supres.py:22,41 (128 / 8 and 192 / 12).   */
 int dsen2_prep16_from_patches(const float* d_x0, int c0, const float* d_x1, int c1, const float* d_x2, int c2,
                               int n, int P, void* d_xin_hi, void* d_xin_lo, void* stream);
 /* dsen2_prep16_from_images reads the images as float32 or, natively, as the uint16 digital numbers GDAL hands
@@ -174,9 +144,9 @@ int dsen2_pack_head_weights(const float* d_hwio, int cin, int feature_size, void
 /* Last layer kernel (3,3,F,cout) fp32 HWIO -> [9 taps][32 rows = W_hi(16) ; W_lo(16)][F] fp16.    */
 int dsen2_pack_tail_weights(const float* d_hwio, int feature_size, int cout, void* d_packed, void* stream);
 
-/* Conv2D(F, 3x3, relu) on the concatenated inputs (DSen2Net.py:29): x_in -> trunk.
+/* Conv2D(F, 3x3, relu) on the concatenated inputs (DSen2Net.py:29), 64-channel x_in -> trunk; feature_size 128.
  *   d_out_hi   NHWC fp16 (n,H,W,F): fp16 rounding of the layer output (the next convolution's operand)
- *   d_out_lo   optional NHWC fp16: out - out_hi (only the tail convolution reads it)
+ *   d_out_lo   optional NHWC fp16: out - out_hi (a network without resblocks hands it to dsen2_conv_tail)
  *   d_trunk32  optional fp32 trunk in TILE-ROW-MAJOR layout (n, H, ceil(W/8), F/4, 8, 4): element (n,y,x,c) at
  *              ((((n*H + y)*ceil(W/8) + x/8)*(F/4) + c/4)*8 + x%8)*4 + c%4 -- the layout dsen2_conv_res32
  *              updates in place (a thread that owns one pixel reads/writes it coalesced; 4 KB DRAM bursts)   */
@@ -187,12 +157,12 @@ int dsen2_conv_head(const void* d_xin_hi, const void* d_xin_lo, const void* d_w,
 /* Second convolution of a resBlock with the residual update on the fp32 trunk (DSen2Net.py:12-15):
  *   trunk32 <- trunk32 + res_scale * (conv3x3(d_in) + bias)          (in place, tile-row-major fp32)
  *   d_out_hi <- fp16(trunk32) NHWC;  d_out_lo (optional) <- fp16(trunk32 - out_hi) NHWC
- * d_in is the NHWC fp16 output of the block's first convolution (dsen2_conv3x3 RELU); d_w from
+ * d_in is the NHWC fp16 output of the block's first convolution (dsen2_conv_relu); d_w from
  * dsen2_pack_conv_weights(cin_pad = cout_pad = 128).  feature_size 128 only.                              */
 int dsen2_conv_res32(const void* d_in, const void* d_w, const float* d_bias, int n, int H, int W,
                      float res_scale, float* d_trunk32, void* d_out_hi, void* d_out_lo, void* stream);
 
-/* The same two layers on the COMPACT trunk the inference path uses (fp16 + 8 bits, 19 significant bits):
+/* The trunk of the inference path (fp16 + 8 bits, 19 significant bits):
  * the trunk value x is held as the NHWC fp16 tensor x_hi the next convolution reads anyway plus one signed
  * byte per element, lo, in tile-row-major layout (n, H, ceil(W/8), F/16, 8, 16): element (n,y,x,c) at
  *   ((((n*H + y)*ceil(W/8) + x/8)*(F/16) + c/16)*8 + x%8)*16 + c%16.
@@ -208,11 +178,9 @@ int dsen2_conv_res32(const void* d_in, const void* d_w, const float* d_bias, int
 int dsen2_conv_resq(const void* d_in, const void* d_w, const float* d_bias, int n, int H, int W,
                     float res_scale, void* d_x_hi, void* d_trunk_lo8, void* d_out_lo, void* stream);
 /* The same resblock update for feature_size 256 (VDSen2; d_w from dsen2_pack_conv_weights(cin_pad = cout_pad = 256):
- * 1.18 MB of weights per layer stream through an 8-slot shared-memory ring instead of staying resident), and the
- * re-coding of an NHWC fp16 (hi, lo) pair as x_hi + bytes: x = hi + lo -> d_x_hi (in place), d_trunk_lo8.  C % 16 == 0. */
+ * 1.18 MB of weights per layer stream through an 8-slot shared-memory ring instead of staying resident).         */
 int dsen2_conv_resq256(const void* d_in, const void* d_w, const float* d_bias, int n, int H, int W,
                        float res_scale, void* d_x_hi, void* d_trunk_lo8, void* d_out_lo, void* stream);
-int dsen2_trunk_hilo_to_q(void* d_x_hi, const void* d_x_lo, void* d_trunk_lo8, int n, int H, int W, int C, void* stream);
 /* First layer on the 16-channel prepared input (dsen2_prep16_*, weights from dsen2_pack_head16_weights), feature_size 128
  * or 256: nine taps as shifted descriptors into a 32-byte-row (SWIZZLE_32B) halo box; per tap the three products
  * hi*W_hi + hi*W_lo + lo*W_hi accumulate into ONE TMEM accumulator (fp32-equivalent first layer).               */
@@ -243,7 +211,7 @@ int dsen2_conv_tail16_stitch(const void* d_x_hi, const void* d_x_lo, const void*
  *   [0] dsen2_pack_head16_weights (dsen2_pack_head_weights when num_layers == 0, feature_size 128 only),
  *   [1..2L] dsen2_pack_conv_weights(cin_pad = cout_pad = feature_size), [2L+1] dsen2_pack_tail_weights;
  *   biases fp32 of length F / F / 16;
- *   pipeline: prep16_from_patches -> conv_head16_q -> L x (conv3x3 RELU, conv_resq[256]) -> conv_tail16
+ *   pipeline: prep16_from_patches -> conv_head16_q -> L x (conv_relu, conv_resq[256]) -> conv_tail16
  *   for feature_size 128 (DSen2) and 256 (VDSen2) alike.
  * Workspace: see dsen2_s2model_workspace_bytes.  d_x[0..n_inputs) NCHW fp32 inputs; the last one is
  * the global skip. */
@@ -260,7 +228,7 @@ int dsen2_s2model_forward(const float* const* d_x, const int* channels, int n_in
  * with per-layer activation buffers.  Backward data path = the same convolution kernels on
  * dsen2_pack_dgrad_weights operands: dsen2_conv_relu_bwd (gradient through Conv2D + ReLU) and
  * dsen2_conv_res32 with scale 1 (gradient through the Add of resBlock, accumulated on an fp32
- * gradient trunk).  Weight gradients = dsen2_wgrad on planar zero-bordered fp16 operands.
+ * gradient trunk).  Weight gradients = dsen2_wgrad_nhwc, a tcgen05 GEMM over the pixel dimension.
  * Gradients carry a power-of-two loss scale chosen by the host (see dsen2_b200/train.py).
  * ------------------------------------------------------------------------------------------- */
 
@@ -272,14 +240,6 @@ int dsen2_pack_dgrad_weights(const float* d_hwio, int cin, int cout, int rows_pa
 int dsen2_conv_relu_bwd(const void* d_in, const void* d_w, const float* d_bias, const void* d_fwd_act,
                         int n, int H, int W, void* d_out, void* stream);
 
-/* planar zero-bordered fp16 operands of dsen2_wgrad: [copies][rows][pitch], k = (b*(H+2) + y+1)*Wp + x+1 with
- * Wp = W+2 rounded up to 8; pitch = dsen2_planar_pitch(n, H, W) (k rounded up to 64, tail zero).  copies = 1 (dY) or
- * 3 (X: copy d holds the tensor shifted by d-1 along k, so that every TMA coordinate stays 16-byte aligned).       */
-long long dsen2_planar_pitch(int n, int H, int W);
-int dsen2_nhwc_to_planar(const void* d_in_nhwc_f16, const void* d_mask_nhwc_f16 /* optional: keep where > 0 */,
-                         int n, int H, int W, int C, int rows, int copies, void* d_out, void* stream);
-int dsen2_nchw_to_planar(const float* d_x0, int c0, const float* d_x1, int c1, const float* d_x2, int c2,
-                         int n, int H, int W, int rows, int copies, float scale, void* d_out, void* stream);
 /* up to three NCHW fp32 inputs concatenated along channels -> NHWC fp16 (n,H,W,cpad), remaining channels zero */
 int dsen2_nchw_to_nhwc_f16(const float* d_x0, int c0, const float* d_x1, int c1, const float* d_x2, int c2,
                            int n, int H, int W, int cpad, void* d_out, void* stream);
@@ -290,13 +250,6 @@ int dsen2_colsum_nhwc(const void* d_in, long long npix, float scale, float* d_ou
 /* Weight gradient straight from the NHWC fp16 tensors (128 channels each), MN-major tcgen05 operands:
  * d_dw (9,128,128) fp32 += scale * sum_px X[px + tap][ci] * dY[px][co]   (HWIO order).                  */
 int dsen2_wgrad_nhwc(const void* d_x, const void* d_dy, int n, int H, int W, float scale, float* d_dw, void* stream);
-
-/* d_dw (9, 128, n_cols) fp32 += scale * sum_px X[px + tap][ci] * dY[px][co]  (HWIO order; zero it first).
- * X planar, 3 shifted copies of 128 rows; dY planar, 1 copy of n_cols = 16 or 128 rows.                */
-int dsen2_wgrad(const void* d_x_planar, const void* d_dy_planar, int n, int H, int W, int n_cols, float scale,
-                float* d_dw, void* stream);
-/* d_out[r] = scale * sum_k planar[r][k]  (bias gradients) */
-int dsen2_rowsum(const void* d_planar, int rows, long long kpitch, float scale, float* d_out, void* stream);
 
 /* mean_absolute_error: d_dpred = gscale * sign(pred - y); d_sums[0] += sum|pred-y|, d_sums[1] += sum (pred-y)^2 */
 int dsen2_mae_grad(const float* d_pred, const float* d_y, long long total, float gscale, float* d_dpred,
@@ -312,11 +265,6 @@ int dsen2_nadam_step(float* d_p, const float* d_g, float* d_m, float* d_v, long 
  * d_hp = {grad_mul, lr, beta1, beta2, eps, mu_t, mu_next, sched_new, sched_next, bias2}.                     */
 int dsen2_nadam_step_dev(float* d_p, const float* d_g, float* d_m, float* d_v, long long total,
                          const float* d_hp, void* stream);
-
-/* Debug / self-test hooks (used by tests only) */
-int dsen2_debug_force_v1(int on);   /* route 128-feature layers of dsen2_conv3x3 to the single-CTA kernel */
-int dsen2_debug_umma_rowshift(const void* d_a_f16 /*(rows,64)*/, int rows, const void* d_b_f16 /*(128,64)*/,
-                              int shift_rows, int base_offset_mode, float* d_out /*(128,128)*/, void* stream);
 
 #ifdef __cplusplus
 }

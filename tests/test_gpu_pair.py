@@ -64,9 +64,10 @@ def test_prep_from_patches_layout_bit_exact(env, chan):
 
 
 @pytest.mark.parametrize('tag', sorted(CASES20)[:3] + sorted(CASES60)[:2])
-def test_prep_from_images_matches_patch_oracle(env, tag):
+def test_prep16_from_images_matches_patch_oracle(env, tag):
     """Fused extract + bilinear + /2000 == the CPU oracle's get_test_patches[60] then /2000, value for value
-    (10 m bands bit-exact; upsampled bands within the 2e-3 DN the standalone bilinear kernel is held to)."""
+    (10 m bands bit-exact; upsampled bands within the 2e-3 DN the standalone bilinear kernel is held to); the same
+    images as uint16 digital numbers (what GDAL delivers) prepare bit-identical inputs."""
     torch, _capi, lib = env
     from oracle import patches_oracle as po
     d10, d20, d60 = synth(tag)
@@ -80,26 +81,39 @@ def test_prep_from_images_matches_patch_oracle(env, tag):
     H, W = d10.shape[:2]
     S = P - 2 * B
     filled = (-(-H // S)) * (-(-W // S))
-    n = ps[0].shape[0]
-    t10, t20 = torch.from_numpy(d10).cuda(), torch.from_numpy(d20).cuda()
-    t60 = torch.from_numpy(d60).cuda() if run60 else None
-    hi = torch.empty((n, P, P, 64), dtype=torch.float16, device='cuda')
-    lo = torch.empty_like(hi)
-    _capi.check(lib.dsen2_prep_from_images(_capi.ptr(t10), _capi.ptr(t20), _capi.ptr(t60), H, W, P, B, 0, n, 2000.0,
-                                           _capi.ptr(hi), _capi.ptr(lo), _capi.stream_ptr()), 'prep_from_images')
-    torch.cuda.synchronize()
-    got = hi.cpu().numpy().astype(np.float32) + lo.cpu().numpy().astype(np.float32)
+    n = ps[0].shape[0]                                   # allocated (patches.py:32-39): surplus patches stay zero
+    imgs = (d10, d20) + ((d60,) if run60 else ())
+    outs = []
+    for dt, code in ((np.float32, _capi.IMG_F32), (np.uint16, _capi.IMG_U16)):
+        assert all(np.array_equal(a, a.astype(dt)) for a in imgs)
+        t = [torch.from_numpy(a.astype(dt)).cuda() for a in imgs] + ([None] if not run60 else [])
+        hi = torch.full((n, P, P, 16), 7.0, dtype=torch.float16, device='cuda')
+        lo = torch.full_like(hi, 7.0)
+        _capi.check(lib.dsen2_prep16_from_images(_capi.ptr(t[0]), _capi.ptr(t[1]), _capi.ptr(t[2]), code, H, W, P, B, 0, n,
+                                                 2000.0, _capi.ptr(hi), _capi.ptr(lo), _capi.stream_ptr()), 'prep16_from_images')
+        torch.cuda.synchronize()
+        outs.append((hi.cpu().numpy(), lo.cpu().numpy()))
+    hi, lo = outs[0]
+    assert np.array_equal(hi.view(np.uint16), outs[1][0].view(np.uint16)) and np.array_equal(lo.view(np.uint16), outs[1][1].view(np.uint16))
+    got = hi.astype(np.float32) + lo.astype(np.float32)
     xcat = np.concatenate([p / np.float32(2000) for p in ps], axis=1)
-    exp_hi, exp_lo = _xin_expected(xcat)
+    exp_hi, exp_lo = _xin16_expected(xcat)
     exp = exp_hi.astype(np.float32) + exp_lo.astype(np.float32)
     assert n >= filled
-    # 10 m bands: pure indexing, then IEEE division -> identical bits in every tap slot
-    for t in range(3):
-        sl = slice(t * 16, t * 16 + 4)
-        assert np.array_equal(hi.cpu().numpy()[..., sl].view(np.uint16), exp_hi[..., sl].view(np.uint16))
+    # 10 m bands: pure indexing, then IEEE division -> identical bits
+    assert np.array_equal(hi[..., :4].view(np.uint16), exp_hi[..., :4].view(np.uint16))
+    assert np.array_equal(lo[..., :4].view(np.uint16), exp_lo[..., :4].view(np.uint16))
     np.testing.assert_allclose(got, exp, rtol=0, atol=2e-3 / 2000 + 1e-7)
     if n > filled:   # surplus patches of the allocated stack are zero (patches.py:32-39)
-        assert not hi.cpu().numpy()[filled:].any()
+        assert not hi[filled:].any()
+
+
+def _xin16_expected(xcat):
+    """xcat (n, C, P, P) float32 -> (hi, lo) (n, P, P, 16) float16: channel c = band c, zero above C."""
+    n, C, P, _ = xcat.shape
+    full = np.zeros((n, P, P, 16), np.float32)
+    full[..., :C] = xcat.transpose(0, 2, 3, 1)
+    return _split(full)
 
 
 def _conv64(x_nhwc, w_hwio, bias):
@@ -262,44 +276,6 @@ def test_conv_tail_stitch_matches_recompose(env, tag, F):
     assert np.array_equal(canvas.cpu().numpy(), ref)
 
 
-@pytest.mark.parametrize('F,shape', [(128, (3, 128, 128)), (256, (2, 128, 128)), (256, (3, 40, 24)), (256, (5, 16, 8))])
-def test_pair_kernel_matches_single_cta_kernel(env, F, shape):
-    """A/B: the CTA-pair trunk kernels (resident weights for 128 features, streamed weight ring for 256) and the
-    single-CTA kernel compute the same layers (same operands; only the fp32 accumulation order differs)."""
-    torch, _capi, lib = env
-    n, H, W = shape
-    rng = np.random.RandomState(9 + F)
-    x = torch.from_numpy(rng.randn(n, H, W, F).astype(np.float16)).cuda()
-    res = rng.randn(n, H, W, F).astype(np.float32)
-    res_hi = res.astype(np.float16)
-    res_lo = (res - res_hi.astype(np.float32)).astype(np.float16)
-    lim = np.sqrt(6.0 / (9 * F))
-    w = torch.from_numpy(rng.uniform(-lim, lim, size=(3, 3, F, F)).astype(np.float32)).cuda()
-    tw = torch.empty((9, F, F), dtype=torch.float16, device='cuda')
-    _capi.check(lib.dsen2_pack_conv_weights(_capi.ptr(w), F, F, F, F, 0, _capi.ptr(tw), None, _capi.stream_ptr()), 'pack')
-    tb = torch.from_numpy((rng.randn(F) * 0.1).astype(np.float32)).cuda()
-    outs = []
-    try:
-        for v1 in (0, 1):
-            lib.dsen2_debug_force_v1(v1)
-            hi = torch.zeros((n, H, W, F), dtype=torch.float16, device='cuda')
-            lo = torch.zeros_like(hi)
-            _capi.check(lib.dsen2_conv3x3(_capi.ptr(x), _capi.ptr(tw), _capi.ptr(tb), n, H, W, F, F, 9, _capi.EPI_RELU,
-                                          None, None, 0.0, _capi.ptr(hi), _capi.ptr(lo), None, None, 0,
-                                          _capi.stream_ptr()), 'conv relu')
-            rh, rl = torch.from_numpy(res_hi).cuda(), torch.from_numpy(res_lo).cuda()
-            _capi.check(lib.dsen2_conv3x3(_capi.ptr(x), _capi.ptr(tw), _capi.ptr(tb), n, H, W, F, F, 9, _capi.EPI_RESIDUAL,
-                                          _capi.ptr(rh), _capi.ptr(rl), 0.1, _capi.ptr(rh), _capi.ptr(rl), None, None, 0,
-                                          _capi.stream_ptr()), 'conv residual')
-            torch.cuda.synchronize()
-            outs.append((hi.float().cpu().numpy() + lo.float().cpu().numpy(), rh.float().cpu().numpy() + rl.float().cpu().numpy()))
-    finally:
-        lib.dsen2_debug_force_v1(0)
-    tol = 1e-5 if F == 128 else 3e-5          # fp32 accumulation order over K = 9*F terms
-    np.testing.assert_allclose(outs[0][0], outs[1][0], rtol=tol, atol=tol)
-    np.testing.assert_allclose(outs[0][1], outs[1][1], rtol=tol, atol=tol)
-
-
 @pytest.mark.parametrize('shape', [(2, 32, 32), (1, 128, 128), (3, 40, 24), (1, 8, 200), (2, 192, 192)])
 @pytest.mark.parametrize('want_lo', [False, True])
 def test_conv_res32_fp32_trunk_update(env, shape, want_lo):
@@ -314,8 +290,7 @@ def test_conv_res32_fp32_trunk_update(env, shape, want_lo):
     w = rng.uniform(-lim, lim, size=(3, 3, F, F)).astype(np.float32)
     bias = (rng.randn(F) * 0.1).astype(np.float32)
     tw = torch.empty((9, F, F), dtype=torch.float16, device='cuda')
-    _capi.check(lib.dsen2_pack_conv_weights(_capi.ptr(torch.from_numpy(w).cuda()), F, F, F, F, 0, _capi.ptr(tw), None,
-                                            _capi.stream_ptr()), 'pack')
+    _capi.check(lib.dsen2_pack_conv_weights(_capi.ptr(torch.from_numpy(w).cuda()), F, F, F, F, _capi.ptr(tw), _capi.stream_ptr()), 'pack')
     x_cm = np.ascontiguousarray(x.reshape(n, H, W // 8, 8, F // 4, 4).transpose(0, 1, 2, 4, 3, 5))
     tx, tt, tb = torch.from_numpy(x_cm).cuda(), torch.from_numpy(t).cuda(), torch.from_numpy(bias).cuda()
     hi = torch.zeros((n, H, W, F), dtype=torch.float16, device='cuda')
@@ -348,8 +323,7 @@ def test_conv_resq_trunk_update(env, shape, last):
     w = rng.uniform(-lim, lim, size=(3, 3, F, F)).astype(np.float32)
     bias = (rng.randn(F) * 0.1).astype(np.float32)
     tw = torch.empty((9, F, F), dtype=torch.float16, device='cuda')
-    _capi.check(lib.dsen2_pack_conv_weights(_capi.ptr(torch.from_numpy(w).cuda()), F, F, F, F, 0, _capi.ptr(tw), None,
-                                            _capi.stream_ptr()), 'pack')
+    _capi.check(lib.dsen2_pack_conv_weights(_capi.ptr(torch.from_numpy(w).cuda()), F, F, F, F, _capi.ptr(tw), _capi.stream_ptr()), 'pack')
     h0, q0 = _q_encode(x)
     x_seen = _q_decode(h0, q0)
     thi, tq = torch.from_numpy(h0).cuda(), torch.from_numpy(_q_to_tiles(q0)).cuda()
@@ -379,14 +353,6 @@ def test_conv_resq_trunk_update(env, shape, last):
 
 
 # ---- un-gathered 16-channel prepared input + nine-tap first layer (dsen2_prep16_* / dsen2_conv_head16_q) ------------
-def _xin16_expected(xcat):
-    """xcat (n, C, P, P) float32 -> (hi, lo) (n, P, P, 16) float16: channel c = band c, zero above C."""
-    n, C, P, _ = xcat.shape
-    full = np.zeros((n, P, P, 16), np.float32)
-    full[..., :C] = xcat.transpose(0, 2, 3, 1)
-    return _split(full)
-
-
 @pytest.mark.parametrize('chan', [(4, 6), (4, 6, 2)])
 def test_prep16_from_patches_layout_bit_exact(env, chan):
     torch, _capi, lib = env
@@ -403,41 +369,6 @@ def test_prep16_from_patches_layout_bit_exact(env, chan):
     ehi, elo = _xin16_expected(np.concatenate(xs, axis=1))
     assert np.array_equal(hi.cpu().numpy().view(np.uint16), ehi.view(np.uint16))
     assert np.array_equal(lo.cpu().numpy().view(np.uint16), elo.view(np.uint16))
-
-
-@pytest.mark.parametrize('tag', sorted(CASES20)[:2] + sorted(CASES60)[:1])
-def test_prep16_from_images_equals_centre_tap_of_the_gathered_form(env, tag):
-    """Same arithmetic as dsen2_prep_from_images (checked against the patch oracle above): x_in16 must be bit-identical to
-    the centre-tap channels 16..31 of the 64-channel form, surplus patches zero."""
-    torch, _capi, lib = env
-    d10, d20, d60 = synth(tag)
-    run60 = tag in CASES60
-    P, B, r = (192, 12, 6) if run60 else (128, 8, 2)
-    H, W = d10.shape[:2]
-    n = (H // r // (P // r - 2 * (B // r)) + 1) * (W // r // (P // r - 2 * (B // r)) + 1)      # allocated (patches.py:32-39)
-    t10, t20 = torch.from_numpy(d10).cuda(), torch.from_numpy(d20).cuda()
-    t60 = torch.from_numpy(d60).cuda() if run60 else None
-    hi64 = torch.empty((n, P, P, 64), dtype=torch.float16, device='cuda')
-    lo64 = torch.empty_like(hi64)
-    hi16 = torch.full((n, P, P, 16), 7.0, dtype=torch.float16, device='cuda')
-    lo16 = torch.full_like(hi16, 7.0)
-    _capi.check(lib.dsen2_prep_from_images(_capi.ptr(t10), _capi.ptr(t20), _capi.ptr(t60), H, W, P, B, 0, n, 2000.0,
-                                           _capi.ptr(hi64), _capi.ptr(lo64), _capi.stream_ptr()), 'prep_from_images')
-    _capi.check(lib.dsen2_prep16_from_images(_capi.ptr(t10), _capi.ptr(t20), _capi.ptr(t60), _capi.IMG_F32, H, W, P, B, 0, n,
-                                             2000.0, _capi.ptr(hi16), _capi.ptr(lo16), _capi.stream_ptr()), 'prep16_from_images')
-    torch.cuda.synchronize()
-    assert torch.equal(hi16.view(torch.int16), hi64[..., 16:32].contiguous().view(torch.int16))
-    assert torch.equal(lo16.view(torch.int16), lo64[..., 16:32].contiguous().view(torch.int16))
-    # the same images as uint16 digital numbers (what GDAL delivers): bit-identical prepared input
-    assert all(np.array_equal(a, a.astype(np.uint16)) for a in (d10, d20) + ((d60,) if run60 else ()))
-    u10, u20 = torch.from_numpy(d10.astype(np.uint16)).cuda(), torch.from_numpy(d20.astype(np.uint16)).cuda()
-    u60 = torch.from_numpy(d60.astype(np.uint16)).cuda() if run60 else None
-    hi_u = torch.full((n, P, P, 16), 7.0, dtype=torch.float16, device='cuda')
-    lo_u = torch.full_like(hi_u, 7.0)
-    _capi.check(lib.dsen2_prep16_from_images(_capi.ptr(u10), _capi.ptr(u20), _capi.ptr(u60), _capi.IMG_U16, H, W, P, B, 0, n,
-                                             2000.0, _capi.ptr(hi_u), _capi.ptr(lo_u), _capi.stream_ptr()), 'prep16 u16')
-    torch.cuda.synchronize()
-    assert torch.equal(hi_u.view(torch.int16), hi16.view(torch.int16)) and torch.equal(lo_u.view(torch.int16), lo16.view(torch.int16))
 
 
 @pytest.mark.parametrize('shape', [(2, 32, 32), (1, 128, 128), (3, 40, 24), (1, 8, 200), (5, 16, 8), (1, 192, 192)])
@@ -473,24 +404,6 @@ def test_conv_head16_q_nine_taps(env, shape, F):
     assert np.abs(got - np.maximum(_conv64(xcat.transpose(0, 2, 3, 1), w, bias), 0)).max() < 5e-5   # vs the true fp32 layer
 
 
-def test_trunk_hilo_to_q_recoding(env):
-    """(hi, lo) fp16 pair -> x_hi + one byte per element: the numpy code of x = hi + lo, bit for bit."""
-    torch, _capi, lib = env
-    rng = np.random.RandomState(11)
-    n, H, W, C = 2, 24, 40, 256
-    x = (rng.randn(n, H, W, C) * np.exp(rng.uniform(-6, 3, size=(n, H, W, C)))).astype(np.float32)
-    x[0, 0, :3] = 0
-    hi, lo = _split(x)
-    thi, tlo = torch.from_numpy(hi).cuda(), torch.from_numpy(lo).cuda()
-    tq = torch.full((n, H, W // 8, C // 16, 8, 16), 77, dtype=torch.int8, device='cuda')
-    _capi.check(lib.dsen2_trunk_hilo_to_q(_capi.ptr(thi), _capi.ptr(tlo), _capi.ptr(tq), n, H, W, C, _capi.stream_ptr()),
-                'hilo_to_q')
-    torch.cuda.synchronize()
-    eh, eq = _q_encode(hi.astype(np.float32) + lo.astype(np.float32))
-    assert np.array_equal(thi.cpu().numpy().view(np.uint16), eh.view(np.uint16))
-    assert np.array_equal(_q_from_tiles(tq.cpu().numpy()), eq)
-
-
 @pytest.mark.parametrize('shape', [(2, 32, 32), (1, 128, 128), (3, 40, 24)])
 @pytest.mark.parametrize('last', [False, True])
 def test_conv_resq256_trunk_update(env, shape, last):
@@ -506,8 +419,7 @@ def test_conv_resq256_trunk_update(env, shape, last):
     w = rng.uniform(-lim, lim, size=(3, 3, F, F)).astype(np.float32)
     bias = (rng.randn(F) * 0.1).astype(np.float32)
     tw = torch.empty((9, F, F), dtype=torch.float16, device='cuda')
-    _capi.check(lib.dsen2_pack_conv_weights(_capi.ptr(torch.from_numpy(w).cuda()), F, F, F, F, 0, _capi.ptr(tw), None,
-                                            _capi.stream_ptr()), 'pack')
+    _capi.check(lib.dsen2_pack_conv_weights(_capi.ptr(torch.from_numpy(w).cuda()), F, F, F, F, _capi.ptr(tw), _capi.stream_ptr()), 'pack')
     h0, q0 = _q_encode(x)
     x_seen = _q_decode(h0, q0)
     thi, tq = torch.from_numpy(h0).cuda(), torch.from_numpy(_q_to_tiles(q0)).cuda()

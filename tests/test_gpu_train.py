@@ -19,44 +19,6 @@ def env():
     return torch, _capi, _capi.lib()
 
 
-def _planar(env, x_nhwc, mask=None, rows=128, copies=1):
-    torch, _capi, lib = env
-    n, H, W, C = x_nhwc.shape
-    pitch = int(lib.dsen2_planar_pitch(n, H, W))
-    out = torch.full((copies, rows, pitch), 9.0, dtype=torch.float16, device='cuda')
-    tx = torch.from_numpy(x_nhwc).cuda()
-    tm = torch.from_numpy(mask).cuda() if mask is not None else None
-    _capi.check(lib.dsen2_nhwc_to_planar(_capi.ptr(tx), _capi.ptr(tm), n, H, W, C, rows, copies, _capi.ptr(out),
-                                         _capi.stream_ptr()), 'planar')
-    torch.cuda.synchronize()
-    return out, pitch
-
-
-def _planar_ref(x_nhwc, rows, pitch, mask=None, copies=1):
-    n, H, W, C = x_nhwc.shape
-    wp = (W + 2 + 7) // 8 * 8
-    v = x_nhwc.astype(np.float32)
-    if mask is not None:
-        v = np.where(mask.astype(np.float32) > 0, v, 0)
-    p = np.zeros((rows, n, H + 2, wp), np.float32)
-    p[:C, :, 1:H + 1, 1:W + 1] = v.transpose(3, 0, 1, 2)
-    flat = np.zeros((rows, pitch + 2), np.float32)                 # one element of slack on both sides for the shifts
-    flat[:, 1:1 + n * (H + 2) * wp] = p.reshape(rows, -1)
-    shifts = (-1, 0, 1) if copies == 3 else (0,)
-    return np.stack([flat[:, 1 + d:1 + d + pitch] for d in shifts]).astype(np.float16)
-
-
-@pytest.mark.parametrize('shape', [(2, 32, 32, 128), (3, 16, 24, 128), (1, 8, 8, 64)])
-def test_planar_layout_bit_exact(env, shape):
-    rng = np.random.RandomState(shape[1])
-    x = rng.randn(*shape).astype(np.float16)
-    m = rng.randn(*shape).astype(np.float16)
-    got, pitch = _planar(env, x, copies=3)
-    assert np.array_equal(got.cpu().numpy().view(np.uint16), _planar_ref(x, 128, pitch, copies=3).view(np.uint16))
-    got, pitch = _planar(env, x, mask=m)
-    assert np.array_equal(got.cpu().numpy().view(np.uint16), _planar_ref(x, 128, pitch, mask=m).view(np.uint16))
-
-
 def _wgrad_ref(x_nhwc, dy_nhwc):
     """dW[tap][ci][co] = sum_px X[px + off(tap)][ci] dY[px][co] with zero padding (float64)."""
     n, H, W, Ci = x_nhwc.shape
@@ -68,23 +30,6 @@ def _wgrad_ref(x_nhwc, dy_nhwc):
         ky, kx = t // 3, t % 3
         out[t] = np.einsum('nyxi,nyxo->io', xp[:, ky:ky + H, kx:kx + W], dy)
     return out
-
-
-@pytest.mark.parametrize('shape,ncols', [((4, 32, 32), 128), ((128, 32, 32), 128), ((4, 32, 32), 16), ((3, 16, 24), 128)])
-def test_wgrad_gemm(env, shape, ncols):
-    torch, _capi, lib = env
-    n, H, W = shape
-    rng = np.random.RandomState(n + ncols)
-    x = rng.randn(n, H, W, 128).astype(np.float16)
-    dy = np.zeros((n, H, W, 128), np.float16)
-    dy[..., :ncols] = (rng.randn(n, H, W, ncols) * 0.1).astype(np.float16)
-    xp, _ = _planar(env, x, copies=3)
-    dyp, _ = _planar(env, dy[..., :ncols] if ncols == 128 else np.ascontiguousarray(dy[..., :16]), rows=ncols)
-    dw = torch.zeros((9, 128, ncols), device='cuda')
-    _capi.check(lib.dsen2_wgrad(_capi.ptr(xp), _capi.ptr(dyp), n, H, W, ncols, 0.5, _capi.ptr(dw), _capi.stream_ptr()), 'wgrad')
-    torch.cuda.synchronize()
-    ref = 0.5 * _wgrad_ref(x.astype(np.float64), dy[..., :ncols])
-    np.testing.assert_allclose(dw.cpu().numpy(), ref, rtol=1e-3, atol=1e-3 * np.abs(ref).max())
 
 
 @pytest.mark.parametrize('shape', [(4, 32, 32), (128, 32, 32), (3, 16, 24), (2, 40, 8)])

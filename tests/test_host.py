@@ -39,8 +39,7 @@ def test_argument_errors_are_reported_without_a_gpu():
     lib = _capi.lib()
     assert lib.dsen2_extract_patches(None, 10, 10, 4, 2, 64, 4, 0, 1, 1.0, None, None) == -1
     assert b'null pointer' in lib.dsen2_last_error()
-    assert lib.dsen2_conv3x3(None, None, None, 1, 8, 8, 64, 128, 9, 0, None, None, 0.0, None, None, None, None, 0,
-                             None) == -1
+    assert lib.dsen2_conv_relu(None, None, None, 1, 8, 8, 128, None, None) == -1
     assert lib.dsen2_s2model_workspace_bytes(1, 128, 10, 128) >= 128 * 128 * (128 + 3 * 128) * 2
 
 

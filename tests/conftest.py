@@ -27,10 +27,25 @@ def golden():
     return dict(np.load(os.path.join(GOLDEN, 'reference_golden.npz')))
 
 
+def _scene(name):
+    z = np.load(os.path.join(GOLDEN, 'scene_%s_u16.npz' % name))
+    return tuple(z[k].astype(np.float32) for k in ('im10', 'im20', 'im60'))
+
+
 @pytest.fixture(scope='session')
 def malmo():
-    z = np.load(os.path.join(GOLDEN, 'scene_malmo_u16.npz'))
-    return tuple(z[k].astype(np.float32) for k in ('im10', 'im20', 'im60'))
+    return _scene('malmo')
+
+
+@pytest.fixture(scope='session')
+def shark():
+    return _scene('shark')
+
+
+@pytest.fixture(scope='session', params=['malmo', 'shark'])
+def scene(request):
+    """The two scenes of the reference's data/ directory that are present in the mount (name, im10, im20, im60)."""
+    return (request.param,) + _scene(request.param)
 
 
 def sha16(a):

@@ -5,8 +5,8 @@ only ``interp_patches`` touches it) and ``/root/reference/utils/imresize.py``
 unmodified, runs them on the two scenes present in the mount and on small
 synthetic inputs, and writes
 
-* ``tests/golden/scene_malmo_u16.npz``   -- the Malmo scene as uint16 (CC BY 4.0,
-  Copernicus / ESA; values are integer DN so the cast is lossless),
+* ``tests/golden/scene_malmo_u16.npz``, ``scene_shark_u16.npz`` -- the two scenes present in the mount (Malmo,
+  Shark Bay) as uint16 (CC BY 4.0, Copernicus / ESA; values are integer DN so the cast is lossless),
 * ``tests/golden/reference_golden.npz``  -- small outputs of the reference code,
 * ``tests/golden/fingerprints.json``     -- sha1 of the large outputs.
 
@@ -55,11 +55,10 @@ def main():
         d10, d20, d60 = (raw[k].transpose() for k in ('im10', 'im20', 'im60'))
         for k in raw:
             fp['%s.%s' % (name, k)] = hashlib.sha1(np.ascontiguousarray(raw[k]).tobytes()).hexdigest()[:12]
-        if name == 'malmo':
-            for a in (d10, d20, d60):
-                assert np.array_equal(a, a.astype(np.uint16))
-            np.savez_compressed(os.path.join(HERE, 'scene_malmo_u16.npz'),
-                                im10=d10.astype(np.uint16), im20=d20.astype(np.uint16), im60=d60.astype(np.uint16))
+        for a in (d10, d20, d60):                  # both shipped scenes travel to the GPU box as uint16 fixtures
+            assert np.array_equal(a, a.astype(np.uint16))
+        np.savez_compressed(os.path.join(HERE, 'scene_%s_u16.npz' % name),
+                            im10=d10.astype(np.uint16), im20=d20.astype(np.uint16), im60=d60.astype(np.uint16))
         p10, p20 = rp.get_test_patches(d10, d20, 128, 8, interp=False)
         q10, q20, q60 = rp.get_test_patches60(d10, d20, d60, 192, 12, interp=False)
         fp.update({name + '.p10': sha(p10), name + '.p20': sha(p20), name + '.q10': sha(q10),

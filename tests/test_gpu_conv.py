@@ -102,11 +102,12 @@ def test_c_entry_point_whole_forward(env, cfg):
     assert torch.equal(a, b)
 
 
-def test_DSen2_20_and_60_scene_vs_oracle(env, malmo):
+def test_DSen2_20_and_60_scene_vs_oracle(env, scene):
+    """Both scenes of the reference's data/ directory that are present (Malmo, Shark Bay), 20 m and 60 m path."""
     from dsen2_b200 import supres
     from dsen2_b200.DSen2Net import s2model
     from oracle import dsen2net_oracle as no
-    d10, d20, d60 = malmo
+    name, d10, d20, d60 = scene
     for run_60 in (False, True):
         shape = ((4, None, None), (6, None, None)) + (((2, None, None),) if run_60 else ())
         model = s2model(shape, num_layers=6, feature_size=128, seed=0)
@@ -122,8 +123,96 @@ def test_DSen2_20_and_60_scene_vs_oracle(env, malmo):
             assert got.shape == (600, 600, 6)
         assert got.dtype == np.float32
         err = np.abs(got - ref).max() / supres.SCALE
-        print('run_60', run_60, 'max abs err (scaled)', err)
+        print(name, 'run_60', run_60, 'max abs err (scaled)', err)
         assert err <= GATE
+
+
+@pytest.mark.parametrize('seed', [11, 12, 13])
+def test_DSen2_60_synthetic_scenes_vs_oracle(env, seed):
+    """BASELINE config 2 names five 600 x 600 scenes for the 60 m path; two exist in the mount (above), the other three are
+    seeded synthetic scenes with the dynamic range of the real ones (uint16 DN, smooth field + noise)."""
+    from dsen2_b200 import supres
+    from dsen2_b200.DSen2Net import s2model
+    from oracle import dsen2net_oracle as no
+    rng = np.random.RandomState(seed)
+
+    def field(h, w, c):
+        lo = rng.randn(h // 50 + 2, w // 50 + 2, c)
+        up = np.kron(lo, np.ones((50, 50, 1)))[:h, :w]
+        return np.clip(1600 + 900 * up + 150 * rng.randn(h, w, c), 0, 12000).round().astype(np.uint16)
+    d10, d20, d60 = field(600, 600, 4), field(300, 300, 6), field(100, 100, 2)
+    model = s2model(((4, None, None), (6, None, None), (2, None, None)), num_layers=6, feature_size=128, seed=seed)
+    ws = model.get_weights()
+    got = supres.DSen2_60(d10, d20, d60, model=model)                     # uint16 in, as GDAL delivers
+    ref = no.DSen2_60(d10.astype(np.float32), d20.astype(np.float32), d60.astype(np.float32),
+                      [(ws[2 * i], ws[2 * i + 1]) for i in range(len(ws) // 2)])
+    err = np.abs(got - ref).max() / supres.SCALE
+    print('synthetic scene', seed, 'max abs err (scaled)', err)
+    assert got.shape == (600, 600, 2) and err <= GATE
+
+
+def test_rmse_gate_on_the_shipped_scenes_when_the_blobs_exist(env):
+    """The north-star acceptance gate: DSen2 RMSE against the simulated ground truth within 0.5 % of the notebook's recorded
+    values (Running_Demo_in_the_colab.ipynb:170,209,236).  The three ground-truth scenes and both weight files are listed
+    in the reference's .MISSING_LARGE_BLOBS, so this is skipped until they are supplied (DSEN2_DATA / DSEN2_MODELS, or
+    ../data and ../models relative to the test directory)."""
+    import os
+    from dsen2_b200 import demoDSen2, supres
+    data = os.environ.get('DSEN2_DATA', os.path.join(os.path.dirname(__file__), '..', '..', 'data'))
+    models = os.environ.get('DSEN2_MODELS', os.path.join(os.path.dirname(__file__), '..', '..', 'models'))
+    cases = [('S2B_MSIL1C_20170725_T43WFQ.mat', False, 31.2404), ('S2A_MSIL1C_20171028_T34HCH.mat', True, 20.4089),
+             ('S2B_MSIL1C_20170928_T18TWL.mat', False, 64.2276)]
+    weights = [os.path.join(models, f) for f in ('s2_032_lr_1e-04.hdf5', 's2_030_lr_1e-05.hdf5')]
+    have = [c for c in cases if os.path.exists(os.path.join(data, c[0]))]
+    if not have or not all(os.path.exists(w) for w in weights):
+        pytest.skip("ground-truth scenes / shipped weights are missing blobs in this mount")
+    old, old_data = supres.MDL_PATH, demoDSen2.DATA_PATH
+    supres.MDL_PATH, demoDSen2.DATA_PATH = models.rstrip('/') + '/', data.rstrip('/') + '/'
+    try:
+        for fn, run_60, expected in have:
+            if run_60:
+                d10, d20, d60, gt = demoDSen2.readh5(fn, im60=True, imGT=True)
+                sr = supres.DSen2_60(d10, d20, d60)
+            else:
+                d10, d20, gt = demoDSen2.readh5(fn, imGT=True)
+                sr = supres.DSen2_20(d10, d20)
+            rmse = demoDSen2.RMSE(sr, gt)
+            print(fn, 'RMSE', rmse, 'notebook', expected)
+            assert abs(rmse - expected) <= 0.005 * expected
+    finally:
+        supres.MDL_PATH, demoDSen2.DATA_PATH = old, old_data
+
+
+def test_tile_driver_on_an_npz_product(env, tmp_path):
+    """python -m dsen2_b200.s2_tiles_supres end to end (ROI, 60 m then 20 m network, npz output) == the facade calls on the
+    same windows (testing/s2_tiles_supres.py:311-342,385-420)."""
+    from dsen2_b200 import s2_tiles_supres as st, supres
+    from dsen2_b200.DSen2Net import s2model
+    rng = np.random.RandomState(2)
+    H, W = 360, 420
+    desc10 = ["B4, central wavelength 665 nm", "B3, central wavelength 560 nm", "B2, central wavelength 490 nm",
+              "B8, central wavelength 842 nm"]
+    desc20 = ["B%s, central wavelength %d nm" % b for b in (('5', 705), ('6', 740), ('7', 783), ('8A', 865), ('11', 1610), ('12', 2190))]
+    desc60 = ["B1, central wavelength 443 nm", "B9, central wavelength 945 nm", "B10, central wavelength 1375 nm"]
+    prod = str(tmp_path / 'p.npz')
+    np.savez(prod, data10=rng.randint(0, 9000, (H, W, 4)).astype(np.uint16), data20=rng.randint(0, 9000, (H // 2, W // 2, 6)).astype(np.uint16),
+             data60=rng.randint(0, 9000, (H // 6, W // 6, 3)).astype(np.uint16), desc10=np.array(desc10), desc20=np.array(desc20),
+             desc60=np.array(desc60))
+    models = {'20': s2model(((4, None, None), (6, None, None)), num_layers=1, feature_size=128, seed=1),
+              '60': s2model(((4, None, None), (6, None, None), (2, None, None)), num_layers=1, feature_size=128, seed=2)}
+    out = str(tmp_path / 'o.npz')
+    assert st.main([prod, out, '--roi_x_y', '20,10,400,340', '--run_60', '--output_file_format', 'npz'], models=models) == 0
+    bands = np.load(out, allow_pickle=True)['bands'].item()
+    z = np.load(prod)
+    xmin, ymin, xmax, ymax = st.clamp_roi(20., 10., 400., 340., W, H)
+    w10, w20, w60 = st.read_windows(xmin, ymin, xmax, ymax)
+    cut = lambda a, w, idx: np.ascontiguousarray(a[w[1]:w[1] + w[3], w[0]:w[0] + w[2]][:, :, idx])
+    d10, d20, d60 = cut(z['data10'], w10, [0, 1, 2, 3]), cut(z['data20'], w20, list(range(6))), cut(z['data60'], w60, [0, 1])
+    sr20 = supres.DSen2_20(d10, d20, model=models['20'])
+    sr60 = supres.DSen2_60(d10, d20, d60, model=models['60'])
+    assert list(bands) == ['SRB5 (705 nm)', 'SRB6 (740 nm)', 'SRB7 (783 nm)', 'SRB8A (865 nm)', 'SRB11 (1610 nm)', 'SRB12 (2190 nm)',
+                           'SRB1 (443 nm)', 'SRB9 (945 nm)']
+    assert np.array_equal(bands['SRB7 (783 nm)'], sr20[:, :, 2]) and np.array_equal(bands['SRB9 (945 nm)'], sr60[:, :, 1])
 
 
 def test_VDSen2_depth32_scene_vs_oracle(env):

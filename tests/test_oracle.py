@@ -8,22 +8,29 @@ from oracle import imresize_oracle as io_
 from oracle import patches_oracle as po
 
 
-def test_scene_fixture_matches_reference_fingerprint(malmo, fingerprints):
+def test_scene_fixture_matches_reference_fingerprint(scene, fingerprints):
     import hashlib
-    d10, d20, d60 = malmo
+    name, d10, d20, d60 = scene
     for a, k in ((d10, 'im10'), (d20, 'im20'), (d60, 'im60')):
         h5order = np.ascontiguousarray(a.transpose())  # readh5 applies .transpose() (demoDSen2.py:16-23)
-        assert hashlib.sha1(h5order.tobytes()).hexdigest()[:12] == fingerprints['malmo.' + k]
+        assert hashlib.sha1(h5order.tobytes()).hexdigest()[:12] == fingerprints['%s.%s' % (name, k)]
 
 
-def test_extract_scene_matches_reference(malmo, fingerprints):
-    d10, d20, d60 = malmo
+def test_extract_scene_matches_reference(scene, fingerprints):
+    name, d10, d20, d60 = scene
     p10, p20 = po.get_test_patches(d10, d20, 128, 8, interp=False)
     assert p10.shape == (36, 4, 128, 128) and p20.shape == (36, 6, 64, 64)
-    assert sha16(p10) == fingerprints['malmo.p10'] and sha16(p20) == fingerprints['malmo.p20']
+    assert sha16(p10) == fingerprints[name + '.p10'] and sha16(p20) == fingerprints[name + '.p20']
     q10, q20, q60 = po.get_test_patches60(d10, d20, d60, 192, 12, interp=False)
     assert q10.shape == (16, 4, 192, 192) and q60.shape == (16, 2, 32, 32)
-    assert (sha16(q10), sha16(q20), sha16(q60)) == tuple(fingerprints['malmo.' + k] for k in ('q10', 'q20', 'q60'))
+    assert (sha16(q10), sha16(q20), sha16(q60)) == tuple(fingerprints['%s.%s' % (name, k)] for k in ('q10', 'q20', 'q60'))
+
+
+def test_bicubic_scene_matches_reference(shark, fingerprints):
+    """imresize of the second scene (the Malmo one is covered below): sha1 of the float64 output of the reference's own run."""
+    _, d20, d60 = shark
+    assert sha16(io_.imresize(d20, 2)) == fingerprints['shark.bic2']
+    assert sha16(io_.imresize(d60, 6)) == fingerprints['shark.bic6']
 
 
 @pytest.mark.parametrize('tag', sorted(CASES20))
@@ -123,6 +130,39 @@ def test_dsen2net_oracle_shapes_and_params():
     # zero tail kernel => output is exactly the global skip (DSen2Net.py:41)
     small[-1] = (np.zeros_like(small[-1][0]), small[-1][1])
     assert np.array_equal(no.forward([x10, x20], small), x20)
+
+
+def test_dsen2net_oracle_against_an_independent_float64_direct_convolution():
+    """The CNN oracle is unpinned by any reference artefact (Keras and the weight files are absent), so at least pin its
+    restatement against a second, independent one: plain numpy float64, no torch -- zero 'same' padding, cross-correlation
+    written as nine shifted einsum products over HWIO kernels (DSen2Net.py:9-43 with Keras' conventions).  A layout slip
+    in the torch version (the HWIO -> OIHW permute, channel concatenation order, skip source) cannot hide behind this."""
+    from oracle import dsen2net_oracle as no
+
+    def conv(x, k, b):                                   # x (N,C,H,W), k (3,3,Cin,Cout) HWIO, b (Cout,)
+        n, c, h, w = x.shape
+        xp = np.zeros((n, c, h + 2, w + 2))
+        xp[:, :, 1:-1, 1:-1] = x
+        y = np.zeros((n, k.shape[3], h, w))
+        for dy in range(3):
+            for dx in range(3):
+                y += np.einsum('nchw,co->nohw', xp[:, :, dy:dy + h, dx:dx + w], k[dy, dx].astype(np.float64))
+        return y + b.astype(np.float64)[None, :, None, None]
+
+    rng = np.random.RandomState(4)
+    for chans, L, F in (((4, 6), 3, 16), ((4, 6, 2), 2, 24)):
+        w = no.he_uniform_weights(sum(chans), chans[-1], L, F, seed=5)
+        w = [(k, (rng.randn(*b.shape) * 0.1).astype(np.float32)) for k, b in w]       # non-zero biases
+        xs = [rng.rand(2, c, 12, 10).astype(np.float32) * 3 for c in chans]
+        x = np.concatenate([a.astype(np.float64) for a in xs], axis=1)                 # DSen2Net.py:24,26
+        x = np.maximum(conv(x, *w[0]), 0)                                              # :29
+        for l in range(L):                                                             # :31-32, resBlock :9-15
+            t = np.maximum(conv(x, *w[1 + 2 * l]), 0)
+            x = x + 0.1 * conv(t, *w[2 + 2 * l])
+        ref = conv(x, *w[-1]) + xs[-1]                                                 # :35, :38 / :41
+        got = no.forward(xs, w)
+        assert got.shape == ref.shape
+        np.testing.assert_allclose(got, ref, rtol=2e-5, atol=2e-5)
 
 
 def test_down_pixel_aggr_oracle_against_an_independent_formula():

@@ -117,9 +117,10 @@ __global__ void bilinear_mirror_kernel(const float* __restrict__ in, int p, int 
 
 // Row-band form of the same arithmetic: a block owns kBilRows input rows of one plane (+ one mirrored halo row / column
 // on each side), divides every input value by 30000 ONCE into shared memory (the direct kernel does it four times per
-// output) and produces the s * kBilRows output rows from there; the x taps of a thread's columns are computed once.
+// output) and produces the s * kBilRows output rows from there.  A thread owns FOUR consecutive output columns (their x
+// taps are computed once, the row is written with 16-byte stores; blockDim.x = P / 4) and walks the band's output rows.
 // Same operations per output as bilinear_mirror_kernel => same bits.
-constexpr int kBilRows = 16, kBilTX = 64, kBilTY = 4, kBilMaxX = 4;
+constexpr int kBilRows = 16, kBilThreads = 256, kBilMaxP = 1024;
 
 __device__ __forceinline__ int mirror_index(int g, int n) {
   if (g < 0) g = -g;
@@ -127,75 +128,93 @@ __device__ __forceinline__ int mirror_index(int g, int n) {
   return g < 0 ? 0 : g;
 }
 
-__global__ void __launch_bounds__(kBilTX * kBilTY) bilinear_mirror_band_kernel(const float* __restrict__ in, int p, int s,
-                                                                              int bands, float post_div,
-                                                                              float* __restrict__ out) {
+__global__ void __launch_bounds__(kBilThreads) bilinear_mirror_band_kernel(const float* __restrict__ in, int p, int s, int bands,
+                                                                          float post_div, float* __restrict__ out) {
   extern __shared__ float s_src[];                         // [kBilRows + 2][p + 2], value / 30000
   const int plane = blockIdx.x / bands, band = blockIdx.x - plane * bands;
   const int r0 = band * kBilRows, rows = min(kBilRows, p - r0);
   const int pitch = p + 2, P = p * s;
   const float k = 30000.0f;                                // the reference scales by 1/30000 around the resize
   const float* src = in + (long long)plane * p * p;
-  const int tid = threadIdx.y * kBilTX + threadIdx.x;
-  for (int i = tid; i < (rows + 2) * pitch; i += kBilTX * kBilTY) {
+  const int nthreads = blockDim.x * blockDim.y;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  for (int i = tid; i < (rows + 2) * pitch; i += nthreads) {
     const int lr = i / pitch, lc = i - lr * pitch;
     s_src[i] = __fdiv_rn(__ldg(src + mirror_index(r0 - 1 + lr, p) * p + mirror_index(lc - 1, p)), k);
   }
-  // x taps of this thread's output columns: local column of the left tap and the fraction
-  int xl[kBilMaxX];
-  float fx[kBilMaxX];
+  // x taps of this thread's four output columns: local column of the left tap and the fraction
+  int xl[4];
+  float fx[4];
 #pragma unroll
-  for (int j = 0; j < kBilMaxX; ++j) {
-    const int ox = threadIdx.x + j * kBilTX;
+  for (int j = 0; j < 4; ++j) {
+    const int ox = threadIdx.x * 4 + j;
     const int t = 2 * ox + 1 - s;
     const int i0 = (t >= 0) ? t / (2 * s) : -((-t + 2 * s - 1) / (2 * s));
     fx[j] = (float)(t - i0 * 2 * s) / (float)(2 * s);
     xl[j] = i0 + 1;
   }
   __syncthreads();
-  float* dst = out + (long long)plane * P * P;
-  for (int oyl = threadIdx.y; oyl < rows * s; oyl += kBilTY) {
+  float* dst = out + (long long)plane * P * P + threadIdx.x * 4;
+  for (int oyl = threadIdx.y; oyl < rows * s; oyl += blockDim.y) {
     const int oy = r0 * s + oyl;
     const int t = 2 * oy + 1 - s;
     const int i0 = (t >= 0) ? t / (2 * s) : -((-t + 2 * s - 1) / (2 * s));
     const float fy = (float)(t - i0 * 2 * s) / (float)(2 * s);
     const float* row0 = s_src + (i0 - (r0 - 1)) * pitch;
     const float* row1 = row0 + pitch;
+    float r[4];
 #pragma unroll
-    for (int j = 0; j < kBilMaxX; ++j) {
-      const int ox = threadIdx.x + j * kBilTX;
-      if (ox < P) {
-        const float v00 = row0[xl[j]], v01 = row0[xl[j] + 1], v10 = row1[xl[j]], v11 = row1[xl[j] + 1];
-        const float c0 = v00 * (1.0f - fy) + v10 * fy;   // rows first, then columns (as the oracle)
-        const float c1 = v01 * (1.0f - fy) + v11 * fy;
-        const float r = (c0 * (1.0f - fx[j]) + c1 * fx[j]) * k;
-        dst[(long long)oy * P + ox] = (post_div == 1.0f) ? r : __fdiv_rn(r, post_div);
-      }
+    for (int j = 0; j < 4; ++j) {
+      const float v00 = row0[xl[j]], v01 = row0[xl[j] + 1], v10 = row1[xl[j]], v11 = row1[xl[j] + 1];
+      const float c0 = v00 * (1.0f - fy) + v10 * fy;   // rows first, then columns (as the oracle)
+      const float c1 = v01 * (1.0f - fy) + v11 * fy;
+      const float v = (c0 * (1.0f - fx[j]) + c1 * fx[j]) * k;
+      r[j] = (post_div == 1.0f) ? v : __fdiv_rn(v, post_div);
     }
+    *reinterpret_cast<float4*>(dst + (long long)oy * P) = make_float4(r[0], r[1], r[2], r[3]);
   }
 }
 
 // ------------------------------------------------------------------------------------------ //
-// stitch: thread per (patch, interior pixel), writes the C contiguous HWC floats it owns
+// stitch: one warp per (patch, interior row).  The C band planes of the row are read coalesced, interleaved to HWC in a
+// per-warp shared-memory row, and the contiguous run of pixels the patch OWNS in that row (last writer wins,
+// patches.py:394-403) leaves as one contiguous span of 8-byte stores.
 // ------------------------------------------------------------------------------------------ //
-__global__ void recompose_kernel(const float* __restrict__ pred, int first_patch, int C, int P, int border, int H,
-                                 int W, int ny, int nx, float mul, long long total, float* __restrict__ out) {
+__device__ __forceinline__ int own_lo(int t, int n, int size, int S) {       // first coordinate owned by tile t
+  if (t >= n) return size;
+  return (t == n - 1 && size % S != 0) ? size - S : t * S;
+}
+
+__global__ void __launch_bounds__(256) recompose_kernel(const float* __restrict__ pred, int first_patch, int C, int P, int border,
+                                                        int H, int W, int ny, int nx, float mul, long long total_rows,
+                                                        float* __restrict__ out) {
+  extern __shared__ float s_row[];                         // [warps][S * C]
   const int S = P - 2 * border;
-  const long long SS = (long long)S * S, PP = (long long)P * P;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int local = (int)(idx / SS);
-    const int rem = (int)(idx - (long long)local * SS);
-    const int yy = rem / S, xx = rem - yy * S;
+  const long long PP = (long long)P * P;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+  float* buf = s_row + warp * S * C;
+  for (long long row = (long long)blockIdx.x * warps + warp; row < total_rows; row += (long long)gridDim.x * warps) {
+    const int local = (int)(row / S), yy = (int)(row - (long long)local * S);
     const int patch = first_patch + local;
     if (patch >= ny * nx) continue;
     const int ty = patch / nx, tx = patch - ty * nx;
     const int oy = min(ty * S, H - S), ox = min(tx * S, W - S);
-    const int y = oy + yy, x = ox + xx;
-    if (tile_of(y, H, S, ny) != ty || tile_of(x, W, S, nx) != tx) continue;   // a later patch overwrites it
-    const float* src = pred + (long long)local * C * PP + (long long)(border + yy) * P + (border + xx);
-    float* dst = out + ((long long)y * W + x) * C;
-    for (int c = 0; c < C; ++c) dst[c] = __ldg(src + c * PP) * mul;
+    const int y = oy + yy;
+    if (tile_of(y, H, S, ny) != ty) continue;             // a later patch row overwrites this image row
+    const int xa = own_lo(tx, nx, W, S) - ox, xb = own_lo(tx + 1, nx, W, S) - ox;   // owned pixels [xa, xb) of the row
+    const float* src = pred + (long long)local * C * PP + (long long)(border + yy) * P + border;
+    __syncwarp();
+    for (int c = 0; c < C; ++c)
+      for (int xx = xa + lane; xx < xb; xx += 32) buf[xx * C + c] = __ldg(src + c * PP + xx) * mul;
+    __syncwarp();
+    float* dst = out + ((long long)y * W + ox) * C;
+    const int f0 = xa * C, f1 = xb * C;
+    if (((C | f0) & 1) == 0 && (((long long)y * W + ox) * C & 1) == 0) {
+      for (int f = f0 + 2 * lane; f < f1; f += 64)
+        *reinterpret_cast<float2*>(dst + f) = *reinterpret_cast<const float2*>(buf + f);
+    } else {
+      for (int f = f0 + lane; f < f1; f += 32) dst[f] = buf[f];
+    }
   }
 }
 
@@ -523,8 +542,11 @@ extern "C" int dsen2_bilinear_mirror_up(const float* d_in, int planes, int p, in
   const long long total = (long long)planes * p * s * p * s;
   const int bands = (p + kBilRows - 1) / kBilRows;
   const size_t band_smem = (size_t)(kBilRows + 2) * (p + 2) * sizeof(float);
-  if (p >= 2 && p * s <= kBilTX * kBilMaxX && band_smem <= 48 * 1024 && (long long)planes * bands < (1LL << 31)) {
-    bilinear_mirror_band_kernel<<<(unsigned)(planes * bands), dim3(kBilTX, kBilTY), band_smem, (cudaStream_t)stream>>>(
+  const int P = p * s;
+  if (p >= 2 && P % 4 == 0 && P <= kBilMaxP && band_smem <= 48 * 1024 && (long long)planes * bands < (1LL << 31) &&
+      ((uintptr_t)d_out % 16) == 0) {
+    const int tx = P / 4, ty = kBilThreads / tx > 0 ? kBilThreads / tx : 1;
+    bilinear_mirror_band_kernel<<<(unsigned)(planes * bands), dim3(tx, ty), band_smem, (cudaStream_t)stream>>>(
         d_in, p, s, bands, post_divisor, d_out);
     return check_launch("bilinear_mirror_up");
   }
@@ -545,10 +567,12 @@ extern "C" int dsen2_recompose(const float* d_pred, int first_patch, int num_pat
   DSEN2_REQUIRE(first_patch >= 0 && num_patches >= 0, DSEN2_E_BADARG, "dsen2_recompose: bad patch range");
   if (num_patches == 0) return 0;
   const int ny = ceil_div(H, S), nx = ceil_div(W, S);
-  const long long total = (long long)num_patches * S * S;
-  const int block = 256;
-  recompose_kernel<<<grid_for(total, block), block, 0, (cudaStream_t)stream>>>(d_pred, first_patch, C, P, border, H, W,
-                                                                               ny, nx, mul, total, d_out);
+  const long long rows = (long long)num_patches * S;
+  const int block = 256, warps = block / 32;
+  const size_t smem = (size_t)warps * S * C * sizeof(float);
+  DSEN2_REQUIRE(smem <= 48 * 1024, DSEN2_E_BADARG, "dsen2_recompose: patch interior %d x %d bands too large", S, C);
+  recompose_kernel<<<grid_for((rows + warps - 1) / warps, 1, 32), block, smem, (cudaStream_t)stream>>>(
+      d_pred, first_patch, C, P, border, H, W, ny, nx, mul, rows, d_out);
   return check_launch("recompose");
 }
 

@@ -10,6 +10,8 @@ sys.path.insert(0, ROOT)
 
 
 def _time(torch, fn, iters=10, warm=3):
+    if os.environ.get('DSEN2_DIAG_ONCE'):          # under ncu: one launch of everything
+        iters, warm = 1, 0
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()

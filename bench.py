@@ -441,6 +441,23 @@ def run_train(args):
 
     ms = timed(step_dev)
     ms_e2e = timed(step_e2e)
+    # the one exchange step of the path: all-reduce of the flat fp32 gradient (1.79 M elements), timed on its own
+    allreduce_us = None
+    if world > 1:
+        from dsen2_b200.train import allreduce_gradients
+        g = torch.zeros_like(tr.grads)
+        for _ in range(5):
+            allreduce_gradients(g)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            allreduce_gradients(g)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / 20 * 1e3], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        allreduce_us = float(t.item())
     flop = 3.0 * FLOP_PER_PIXEL[('dsen2', 20)] * n * P * P               # forward + backward-data + weight-gradient
     if rank == 0:
         pk = peaks()
@@ -458,6 +475,8 @@ def run_train(args):
                              "achieved": flop / ms / 1e9, "peak": pk['tf_burst'], "unit": "TFLOP/s",
                              "frac": flop / ms / 1e9 / pk['tf_burst'], "traffic": None,
                              "peak_source": pk['source'] + ", burst figure (millisecond-scale step)"},
+                "allreduce": {"us": allreduce_us, "bytes": int(tr.grads.numel()) * 4, "algo": "NCCL all_reduce(SUM), one bucket, "
+                              "between the gradient graph and the update graph"} if world > 1 else None,
                 "last_loss": losses[-1] if losses else None}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -176,44 +176,68 @@ __global__ void __launch_bounds__(kBilThreads) bilinear_mirror_band_kernel(const
 }
 
 // ------------------------------------------------------------------------------------------ //
-// stitch: one warp per (patch, interior row).  The C band planes of the row are read coalesced, interleaved to HWC in a
-// per-warp shared-memory row, and the contiguous run of pixels the patch OWNS in that row (last writer wins,
-// patches.py:394-403) leaves as one contiguous span of 8-byte stores.
+// stitch (patches.py:374-405): patch t writes the output pixels whose LAST writer it is
 // ------------------------------------------------------------------------------------------ //
-__device__ __forceinline__ int own_lo(int t, int n, int size, int S) {       // first coordinate owned by tile t
-  if (t >= n) return size;
-  return (t == n - 1 && size % S != 0) ? size - S : t * S;
+// generic form: thread per (patch, interior pixel), writes the C contiguous HWC floats it owns
+__global__ void recompose_kernel(const float* __restrict__ pred, int first_patch, int C, int P, int border, int H,
+                                 int W, int ny, int nx, float mul, long long total, float* __restrict__ out) {
+  const int S = P - 2 * border;
+  const long long SS = (long long)S * S, PP = (long long)P * P;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int local = (int)(idx / SS);
+    const int rem = (int)(idx - (long long)local * SS);
+    const int yy = rem / S, xx = rem - yy * S;
+    const int patch = first_patch + local;
+    if (patch >= ny * nx) continue;
+    const int ty = patch / nx, tx = patch - ty * nx;
+    const int oy = min(ty * S, H - S), ox = min(tx * S, W - S);
+    const int y = oy + yy, x = ox + xx;
+    if (tile_of(y, H, S, ny) != ty || tile_of(x, W, S, nx) != tx) continue;   // a later patch overwrites it
+    const float* src = pred + (long long)local * C * PP + (long long)(border + yy) * P + (border + xx);
+    float* dst = out + ((long long)y * W + x) * C;
+    for (int c = 0; c < C; ++c) dst[c] = __ldg(src + c * PP) * mul;
+  }
 }
 
-__global__ void __launch_bounds__(256) recompose_kernel(const float* __restrict__ pred, int first_patch, int C, int P, int border,
-                                                        int H, int W, int ny, int nx, float mul, long long total_rows,
-                                                        float* __restrict__ out) {
-  extern __shared__ float s_row[];                         // [warps][S * C]
-  const int S = P - 2 * border;
+// vector form (C = 2 or 6, S and border multiples of 4, even W): a thread owns FOUR consecutive interior pixels of one
+// patch row -- C 16-byte plane loads in flight, then its 4 * C HWC floats (16 * C contiguous bytes) as 16-byte stores
+template <int C>
+__global__ void __launch_bounds__(256) recompose_vec4_kernel(const float* __restrict__ pred, int first_patch, int P, int border,
+                                                             int H, int W, int ny, int nx, float mul, long long total,
+                                                             float* __restrict__ out) {
+  const int S = P - 2 * border, S4 = S / 4;
   const long long PP = (long long)P * P;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
-  float* buf = s_row + warp * S * C;
-  for (long long row = (long long)blockIdx.x * warps + warp; row < total_rows; row += (long long)gridDim.x * warps) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx / S4;
+    const int xx = (int)(idx - row * S4) * 4;
     const int local = (int)(row / S), yy = (int)(row - (long long)local * S);
     const int patch = first_patch + local;
     if (patch >= ny * nx) continue;
     const int ty = patch / nx, tx = patch - ty * nx;
     const int oy = min(ty * S, H - S), ox = min(tx * S, W - S);
-    const int y = oy + yy;
-    if (tile_of(y, H, S, ny) != ty) continue;             // a later patch row overwrites this image row
-    const int xa = own_lo(tx, nx, W, S) - ox, xb = own_lo(tx + 1, nx, W, S) - ox;   // owned pixels [xa, xb) of the row
-    const float* src = pred + (long long)local * C * PP + (long long)(border + yy) * P + border;
-    __syncwarp();
-    for (int c = 0; c < C; ++c)
-      for (int xx = xa + lane; xx < xb; xx += 32) buf[xx * C + c] = __ldg(src + c * PP + xx) * mul;
-    __syncwarp();
-    float* dst = out + ((long long)y * W + ox) * C;
-    const int f0 = xa * C, f1 = xb * C;
-    if (((C | f0) & 1) == 0 && (((long long)y * W + ox) * C & 1) == 0) {
-      for (int f = f0 + 2 * lane; f < f1; f += 64)
-        *reinterpret_cast<float2*>(dst + f) = *reinterpret_cast<const float2*>(buf + f);
-    } else {
-      for (int f = f0 + lane; f < f1; f += 32) dst[f] = buf[f];
+    const int y = oy + yy, x = ox + xx;
+    if (tile_of(y, H, S, ny) != ty) continue;
+    const bool o0 = tile_of(x, W, S, nx) == tx, o3 = tile_of(x + 3, W, S, nx) == tx;   // ownership is a contiguous run
+    if (!o0 && !o3) continue;
+    const float* src = pred + (long long)local * C * PP + (long long)(border + yy) * P + (border + xx);
+    float4 v[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) v[c] = __ldg(reinterpret_cast<const float4*>(src + c * PP));
+    float o[4 * C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      o[0 * C + c] = v[c].x * mul; o[1 * C + c] = v[c].y * mul; o[2 * C + c] = v[c].z * mul; o[3 * C + c] = v[c].w * mul;
+    }
+    float* dst = out + ((long long)y * W + x) * C;
+    if (o0 && o3) {
+#pragma unroll
+      for (int q = 0; q < C; ++q) reinterpret_cast<float4*>(dst)[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+    } else {                                               // the seam of the clamped last tile column
+      for (int i = 0; i < 4; ++i)
+        if (tile_of(x + i, W, S, nx) == tx)
+          for (int c = 0; c < C; ++c) dst[i * C + c] = o[i * C + c];
     }
   }
 }
@@ -567,12 +591,23 @@ extern "C" int dsen2_recompose(const float* d_pred, int first_patch, int num_pat
   DSEN2_REQUIRE(first_patch >= 0 && num_patches >= 0, DSEN2_E_BADARG, "dsen2_recompose: bad patch range");
   if (num_patches == 0) return 0;
   const int ny = ceil_div(H, S), nx = ceil_div(W, S);
-  const long long rows = (long long)num_patches * S;
-  const int block = 256, warps = block / 32;
-  const size_t smem = (size_t)warps * S * C * sizeof(float);
-  DSEN2_REQUIRE(smem <= 48 * 1024, DSEN2_E_BADARG, "dsen2_recompose: patch interior %d x %d bands too large", S, C);
-  recompose_kernel<<<grid_for((rows + warps - 1) / warps, 1, 32), block, smem, (cudaStream_t)stream>>>(
-      d_pred, first_patch, C, P, border, H, W, ny, nx, mul, rows, d_out);
+  const int block = 256;
+  // vector form: 16-byte plane loads need P, border (and so S) multiples of 4; 16-byte HWC stores need (y * W + x) * C * 4
+  // bytes 16-byte aligned for x a multiple of 4: W * C a multiple of 4
+  if ((C == 2 || C == 6) && P % 4 == 0 && border % 4 == 0 && (W * C) % 4 == 0 && (W - S) % 4 == 0 &&
+      ((uintptr_t)d_pred % 16) == 0 && ((uintptr_t)d_out % 16) == 0) {
+    const long long total4 = (long long)num_patches * S * (S / 4);
+    if (C == 6)
+      recompose_vec4_kernel<6><<<grid_for(total4, block, 32), block, 0, (cudaStream_t)stream>>>(d_pred, first_patch, P, border, H,
+                                                                                              W, ny, nx, mul, total4, d_out);
+    else
+      recompose_vec4_kernel<2><<<grid_for(total4, block, 32), block, 0, (cudaStream_t)stream>>>(d_pred, first_patch, P, border, H,
+                                                                                              W, ny, nx, mul, total4, d_out);
+    return check_launch("recompose");
+  }
+  const long long total = (long long)num_patches * S * S;
+  recompose_kernel<<<grid_for(total, block), block, 0, (cudaStream_t)stream>>>(d_pred, first_patch, C, P, border, H, W,
+                                                                               ny, nx, mul, total, d_out);
   return check_launch("recompose");
 }
 

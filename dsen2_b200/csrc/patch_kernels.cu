@@ -128,6 +128,17 @@ __device__ __forceinline__ int mirror_index(int g, int n) {
   return g < 0 ? 0 : g;
 }
 
+// u = (o + .5)/s - .5 = t / (2 s) with t = 2 o + 1 - s: integer part (floor) and fraction.  SC > 0: compile-time scale
+// (the divisions become multiplications); SC == 0: run-time scale.
+template <int SC>
+__device__ __forceinline__ void bilin_split(int o, int s, int& i0, float& f) {
+  const int d = 2 * (SC > 0 ? SC : s);
+  const int t = 2 * o + 1 - (SC > 0 ? SC : s);
+  i0 = (t >= 0) ? t / d : -((-t + d - 1) / d);
+  f = (float)(t - i0 * d) / (float)d;
+}
+
+template <int SC>
 __global__ void __launch_bounds__(kBilThreads) bilinear_mirror_band_kernel(const float* __restrict__ in, int p, int s, int bands,
                                                                           float post_div, float* __restrict__ out) {
   extern __shared__ float s_src[];                         // [kBilRows + 2][p + 2], value / 30000
@@ -136,30 +147,27 @@ __global__ void __launch_bounds__(kBilThreads) bilinear_mirror_band_kernel(const
   const int pitch = p + 2, P = p * s;
   const float k = 30000.0f;                                // the reference scales by 1/30000 around the resize
   const float* src = in + (long long)plane * p * p;
-  const int nthreads = blockDim.x * blockDim.y;
-  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  for (int i = tid; i < (rows + 2) * pitch; i += nthreads) {
-    const int lr = i / pitch, lc = i - lr * pitch;
-    s_src[i] = __fdiv_rn(__ldg(src + mirror_index(r0 - 1 + lr, p) * p + mirror_index(lc - 1, p)), k);
+  for (int lr = threadIdx.y; lr < rows + 2; lr += blockDim.y) {
+    const float* srow = src + mirror_index(r0 - 1 + lr, p) * p;
+    for (int lc = threadIdx.x; lc < pitch; lc += blockDim.x)
+      s_src[lr * pitch + lc] = __fdiv_rn(__ldg(srow + mirror_index(lc - 1, p)), k);
   }
   // x taps of this thread's four output columns: local column of the left tap and the fraction
   int xl[4];
   float fx[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const int ox = threadIdx.x * 4 + j;
-    const int t = 2 * ox + 1 - s;
-    const int i0 = (t >= 0) ? t / (2 * s) : -((-t + 2 * s - 1) / (2 * s));
-    fx[j] = (float)(t - i0 * 2 * s) / (float)(2 * s);
+    int i0;
+    bilin_split<SC>(threadIdx.x * 4 + j, s, i0, fx[j]);
     xl[j] = i0 + 1;
   }
   __syncthreads();
   float* dst = out + (long long)plane * P * P + threadIdx.x * 4;
   for (int oyl = threadIdx.y; oyl < rows * s; oyl += blockDim.y) {
     const int oy = r0 * s + oyl;
-    const int t = 2 * oy + 1 - s;
-    const int i0 = (t >= 0) ? t / (2 * s) : -((-t + 2 * s - 1) / (2 * s));
-    const float fy = (float)(t - i0 * 2 * s) / (float)(2 * s);
+    int i0;
+    float fy;
+    bilin_split<SC>(oy, s, i0, fy);
     const float* row0 = s_src + (i0 - (r0 - 1)) * pitch;
     const float* row1 = row0 + pitch;
     float r[4];
@@ -570,8 +578,13 @@ extern "C" int dsen2_bilinear_mirror_up(const float* d_in, int planes, int p, in
   if (p >= 2 && P % 4 == 0 && P <= kBilMaxP && band_smem <= 48 * 1024 && (long long)planes * bands < (1LL << 31) &&
       ((uintptr_t)d_out % 16) == 0) {
     const int tx = P / 4, ty = kBilThreads / tx > 0 ? kBilThreads / tx : 1;
-    bilinear_mirror_band_kernel<<<(unsigned)(planes * bands), dim3(tx, ty), band_smem, (cudaStream_t)stream>>>(
-        d_in, p, s, bands, post_divisor, d_out);
+    const dim3 grid((unsigned)(planes * bands)), block(tx, ty);
+    if (s == 2)
+      bilinear_mirror_band_kernel<2><<<grid, block, band_smem, (cudaStream_t)stream>>>(d_in, p, s, bands, post_divisor, d_out);
+    else if (s == 6)
+      bilinear_mirror_band_kernel<6><<<grid, block, band_smem, (cudaStream_t)stream>>>(d_in, p, s, bands, post_divisor, d_out);
+    else
+      bilinear_mirror_band_kernel<0><<<grid, block, band_smem, (cudaStream_t)stream>>>(d_in, p, s, bands, post_divisor, d_out);
     return check_launch("bilinear_mirror_up");
   }
   const int block = 256;

@@ -26,6 +26,8 @@ class S2Model:
             raise ValueError("s2model takes 2 or 3 inputs (10 m, 20 m[, 60 m])")
         if feature_size not in (128, 256):
             raise ValueError("feature_size must be 128 (DSen2) or 256 (VDSen2); got %r" % (feature_size,))
+        if int(num_layers) > 0 and int(input_shape[-1][0]) > 7:
+            raise ValueError("at most 7 output bands (the last input's channel count); got %d" % int(input_shape[-1][0]))
         self.input_shape = tuple(tuple(s) for s in input_shape)
         self.in_channels = [int(s[0]) for s in self.input_shape]
         self.out_channels = self.in_channels[-1]                 # DSen2Net.py:35
@@ -152,6 +154,11 @@ class S2Model:
                     _capi.check(lib.dsen2_pack_head_weights(_capi.ptr(src), cin, F, _capi.ptr(dst), st),
                                 "dsen2_pack_head_weights")
                     cout_pad = F
+                elif tail and self.xin16:
+                    dst = torch.empty((128, F), dtype=torch.float16, device=device)
+                    _capi.check(lib.dsen2_pack_tail16_weights(_capi.ptr(src), F, cout, _capi.ptr(dst), st),
+                                "dsen2_pack_tail16_weights")
+                    cout_pad = 16
                 elif tail:
                     dst = torch.empty((9, 32, F), dtype=torch.float16, device=device)
                     _capi.check(lib.dsen2_pack_tail_weights(_capi.ptr(src), F, cout, _capi.ptr(dst), st),

@@ -30,6 +30,7 @@ SIGNATURES = {
                                         c_void_p, c_void_p]),
     "dsen2_pack_head_weights": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "dsen2_pack_tail_weights": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "dsen2_pack_tail16_weights": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "dsen2_conv_head": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                 c_void_p, c_void_p]),
     "dsen2_conv_res32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p,

@@ -1021,7 +1021,6 @@ using CfgHead = PairCfg<256, kSplitStack, 2, 1, 3, 3, 6, kEpiRelu>;
 using CfgHead16 = PairCfg<128, kSplit3, 2, 1, 9, 1, 6, kEpiHeadQ, 0, 32, true>;
 using CfgHead16_256 = PairCfg<256, kSplit3, 2, 1, 9, 1, 6, kEpiHeadQ, 0, 32, true>;
 using CfgTail = PairCfg<32, kSplitStack, 2, 2, 9, 4, 6, kEpiTail>;
-using CfgTail256 = PairCfg<32, kSplitStack, 2, 4, 9, 4, 6, kEpiTail>;   // 256 -> cout: 8 k-blocks per tile, 72 KB of weights
 
 // x0 / x1: tensor maps of the epilogue's x_hi / x_lo tiles (PairCfg::XT kernels only)
 template <class Cfg>
@@ -1247,13 +1246,13 @@ extern "C" int dsen2_conv_resq256(const void* d_in, const void* d_w, const float
   return resq_common(256, d_in, d_w, d_bias, n, H, W, res_scale, d_x_hi, d_trunk_lo8, d_out_lo, stream);
 }
 
-static int tail_common(PairParams& p, bool xin16, int features, const void* d_x_hi, const void* d_x_lo, const void* d_w,
-                       const float* d_bias, const void* d_xin_hi, const void* d_xin_lo, int skip_ch0, int cout, int n, int H,
-                       int W, float* d_out, void* stream) {
-  DSEN2_REQUIRE(d_x_hi && d_x_lo && d_w && d_bias && d_xin_hi && d_xin_lo && d_out, DSEN2_E_BADARG,
+// Last layer on the 64-channel prepared input (training step, networks without resblocks): pixels on the M side, B =
+// [W_hi ; W_lo] stacked along N.  The inference path uses the swapped form in conv_tail.cu (dsen2_conv_tail16[_stitch]).
+extern "C" int dsen2_conv_tail(const void* d_x_hi, const void* d_x_lo, const void* d_w, const float* d_bias,
+                               const void* d_xin_hi, const void* d_xin_lo, int skip_ch0, int cout, int n, int H, int W,
+                               float* d_pred_nchw, void* stream) {
+  DSEN2_REQUIRE(d_x_hi && d_x_lo && d_w && d_bias && d_xin_hi && d_xin_lo && d_pred_nchw, DSEN2_E_BADARG,
                 "dsen2_conv_tail: null pointer");
-  DSEN2_REQUIRE(features == 128 || features == 256, DSEN2_E_BADARG, "dsen2_conv_tail: feature_size must be 128 or 256 (got %d)",
-                features);
   DSEN2_REQUIRE(n >= 0 && H > 0 && W > 0 && cout > 0 && cout <= 16 && skip_ch0 >= 0 && skip_ch0 + cout <= 16,
                 DSEN2_E_BADARG, "dsen2_conv_tail: bad shape (cout %d, skip_ch0 %d)", cout, skip_ch0);
   DSEN2_REQUIRE(((uintptr_t)d_x_hi % 16) == 0 && ((uintptr_t)d_x_lo % 16) == 0 && ((uintptr_t)d_w % 16) == 0,
@@ -1262,64 +1261,16 @@ static int tail_common(PairParams& p, bool xin16, int features, const void* d_x_
   int sms = 0;
   int rc = device_sm_count_and_check(&sms);
   if (rc) return rc;
+  PairParams p{};
   if ((rc = fill_tiles(p, n, H, W)) != 0) return rc;
-  if (p.tail_mode == 1) {
-    // recompose_images copies only [border, P - border) of every patch (patches.py:402): tile columns that lie inside
-    // the border produce nothing -- leave them out of the tile list (P 128 / border 8: 14 of 16 columns)
-    p.tx0 = p.border / 8;
-    p.tiles_x = (W - p.border - 1) / 8 - p.tx0 + 1;
-    p.num_tiles = (uint32_t)((long long)n * p.tiles_x * p.tiles_y);
-  }
+  p.tail_mode = 0;
+  p.out_mul = 1.0f;
   p.bias = d_bias;
   p.skip_hi = (const __half*)d_xin_hi; p.skip_lo = (const __half*)d_xin_lo; p.skip_ch0 = skip_ch0;
-  p.skip_pitch = xin16 ? 16 : 64; p.skip_off = xin16 ? 0 : 16;
-  p.cout_real = cout; p.out_f32 = d_out;
+  p.skip_pitch = 64; p.skip_off = 16;
+  p.cout_real = cout; p.out_f32 = d_pred_nchw;
   CUtensorMap a0, a1, w;
-  if (features == 256) {
-    rc = make_maps<CfgTail256>(&a0, &a1, &w, d_x_hi, d_x_lo, d_w, n, H, W);
-    if (rc) return rc;
-    return launch_pair<CfgTail256>(a0, a1, w, p, sms, (cudaStream_t)stream, "conv_pair<tail,256>");
-  }
   rc = make_maps<CfgTail>(&a0, &a1, &w, d_x_hi, d_x_lo, d_w, n, H, W);
   if (rc) return rc;
   return launch_pair<CfgTail>(a0, a1, w, p, sms, (cudaStream_t)stream, "conv_pair<tail>");
-}
-
-extern "C" int dsen2_conv_tail(const void* d_x_hi, const void* d_x_lo, const void* d_w, const float* d_bias,
-                               const void* d_xin_hi, const void* d_xin_lo, int skip_ch0, int cout, int n, int H, int W,
-                               float* d_pred_nchw, void* stream) {
-  PairParams p{};
-  p.tail_mode = 0;
-  p.out_mul = 1.0f;
-  return tail_common(p, false, 128, d_x_hi, d_x_lo, d_w, d_bias, d_xin_hi, d_xin_lo, skip_ch0, cout, n, H, W, d_pred_nchw,
-                     stream);
-}
-
-extern "C" int dsen2_conv_tail16(const void* d_x_hi, const void* d_x_lo, const void* d_w, const float* d_bias,
-                                 const void* d_xin_hi, const void* d_xin_lo, int skip_ch0, int cout, int feature_size, int n,
-                                 int H, int W, float* d_pred_nchw, void* stream) {
-  PairParams p{};
-  p.tail_mode = 0;
-  p.out_mul = 1.0f;
-  return tail_common(p, true, feature_size, d_x_hi, d_x_lo, d_w, d_bias, d_xin_hi, d_xin_lo, skip_ch0, cout, n, H, W,
-                     d_pred_nchw, stream);
-}
-
-extern "C" int dsen2_conv_tail16_stitch(const void* d_x_hi, const void* d_x_lo, const void* d_w, const float* d_bias,
-                                        const void* d_xin_hi, const void* d_xin_lo, int skip_ch0, int cout, int feature_size,
-                                        int n, int P, int first_patch, int border, int img_h, int img_w, float mul,
-                                        float* d_canvas, void* stream) {
-  const int S = P - 2 * border;
-  DSEN2_REQUIRE(P > 0 && border >= 0 && S > 0 && img_h >= S && img_w >= S && first_patch >= 0, DSEN2_E_BADARG,
-                "dsen2_conv_tail16_stitch: bad stitch geometry (P %d border %d image %dx%d)", P, border, img_h, img_w);
-  PairParams p{};
-  p.tail_mode = 1;
-  p.out_mul = mul;
-  p.first_patch = first_patch; p.img_h = img_h; p.img_w = img_w; p.border = border;
-  p.grid_ny = ceil_div(img_h, S); p.grid_nx = ceil_div(img_w, S);
-  DSEN2_REQUIRE(first_patch + n <= p.grid_ny * p.grid_nx, DSEN2_E_BADARG,
-                "dsen2_conv_tail16_stitch: patch range [%d,%d) exceeds the %d tiles of the canvas", first_patch,
-                first_patch + n, p.grid_ny * p.grid_nx);
-  return tail_common(p, true, feature_size, d_x_hi, d_x_lo, d_w, d_bias, d_xin_hi, d_xin_lo, skip_ch0, cout, n, P, P,
-                     d_canvas, stream);
 }

@@ -141,7 +141,7 @@ int dsen2_pack_head16_weights(const float* d_hwio, int cin, int feature_size, vo
 
 /* First layer kernel (3,3,cin,F) fp32 HWIO -> [3 vertical taps][2F rows = W_hi ; W_lo][64] fp16. */
 int dsen2_pack_head_weights(const float* d_hwio, int cin, int feature_size, void* d_packed, void* stream);
-/* Last layer kernel (3,3,F,cout) fp32 HWIO -> [9 taps][32 rows = W_hi(16) ; W_lo(16)][F] fp16.    */
+/* Last layer kernel (3,3,F,cout) fp32 HWIO -> [9 taps][32 rows = W_hi(16) ; W_lo(16)][F] fp16 (for dsen2_conv_tail). */
 int dsen2_pack_tail_weights(const float* d_hwio, int feature_size, int cout, void* d_packed, void* stream);
 
 /* Conv2D(F, 3x3, relu) on the concatenated inputs (DSen2Net.py:29), 64-channel x_in -> trunk; feature_size 128.
@@ -194,7 +194,12 @@ int dsen2_conv_tail(const void* d_x_hi, const void* d_x_lo, const void* d_w, con
                     const void* d_xin_hi, const void* d_xin_lo, int skip_ch0, int cout,
                     int n, int H, int W, float* d_pred_nchw, void* stream);
 
-/* dsen2_conv_tail with the global skip read from the 16-channel prepared input; feature_size 128 or 256.            */
+/* The last layer of the inference path (csrc/conv_tail.cu): the same Conv2D(cout) + Add with the global skip read from
+ * the 16-channel prepared input, feature_size 128 or 256, cout <= 7 (DSen2: 6 bands at 20 m, 2 at 60 m).  The GEMM runs
+ * with the operands SWAPPED -- the 18 * cout weight rows (tap x {W_hi, W_lo} x band) on the M side, the 18 x 10 pixel halo
+ * box of a tile on the N side -- so an activation crosses the shared-memory read port once instead of once per tap; the
+ * 3x3 shifts are applied in the epilogue.  d_w from dsen2_pack_tail16_weights: [128 rows][feature_size] fp16.      */
+int dsen2_pack_tail16_weights(const float* d_hwio, int feature_size, int cout, void* d_packed, void* stream);
 int dsen2_conv_tail16(const void* d_x_hi, const void* d_x_lo, const void* d_w, const float* d_bias,
                       const void* d_xin_hi, const void* d_xin_lo, int skip_ch0, int cout, int feature_size,
                       int n, int H, int W, float* d_pred_nchw, void* stream);
@@ -209,7 +214,8 @@ int dsen2_conv_tail16_stitch(const void* d_x_hi, const void* d_x_lo, const void*
 /* Whole s2model forward (model.predict on one batch, supres.py:65) for n patches of (P, P).
  * d_weights[i] / d_bias[i] are the packed layers in Keras topological order (2*num_layers+2 entries):
  *   [0] dsen2_pack_head16_weights (dsen2_pack_head_weights when num_layers == 0, feature_size 128 only),
- *   [1..2L] dsen2_pack_conv_weights(cin_pad = cout_pad = feature_size), [2L+1] dsen2_pack_tail_weights;
+ *   [1..2L] dsen2_pack_conv_weights(cin_pad = cout_pad = feature_size), [2L+1] dsen2_pack_tail16_weights
+ *   (dsen2_pack_tail_weights when num_layers == 0);
  *   biases fp32 of length F / F / 16;
  *   pipeline: prep16_from_patches -> conv_head16_q -> L x (conv_relu, conv_resq[256]) -> conv_tail16
  *   for feature_size 128 (DSen2) and 256 (VDSen2) alike.

@@ -211,8 +211,8 @@ def test_conv_tail16_nchw_fp32_equivalent(env, shape, cout, ch0, F):
     w = rng.uniform(-lim, lim, size=(3, 3, F, cout)).astype(np.float32)
     bias = np.zeros(16, np.float32)
     bias[:cout] = rng.randn(cout) * 0.1
-    tw = torch.empty((9, 32, F), dtype=torch.float16, device='cuda')
-    _capi.check(lib.dsen2_pack_tail_weights(_capi.ptr(torch.from_numpy(w).cuda()), F, cout, _capi.ptr(tw),
+    tw = torch.empty((128, F), dtype=torch.float16, device='cuda')
+    _capi.check(lib.dsen2_pack_tail16_weights(_capi.ptr(torch.from_numpy(w).cuda()), F, cout, _capi.ptr(tw),
                                             _capi.stream_ptr()), 'pack tail')
     dev = [torch.from_numpy(a).cuda() for a in (x_hi, x_lo, xin_hi, xin_lo, bias)]
     out = torch.full((n, cout, H, W), -5.0, device='cuda')
@@ -248,8 +248,8 @@ def test_conv_tail_stitch_matches_recompose(env, tag, F):
     lim = np.sqrt(6.0 / (9 * F))
     w = rng.uniform(-lim, lim, size=(3, 3, F, cout)).astype(np.float32)
     bias = np.zeros(16, np.float32)
-    tw = torch.empty((9, 32, F), dtype=torch.float16, device='cuda')
-    _capi.check(lib.dsen2_pack_tail_weights(_capi.ptr(torch.from_numpy(w).cuda()), F, cout, _capi.ptr(tw),
+    tw = torch.empty((128, F), dtype=torch.float16, device='cuda')
+    _capi.check(lib.dsen2_pack_tail16_weights(_capi.ptr(torch.from_numpy(w).cuda()), F, cout, _capi.ptr(tw),
                                             _capi.stream_ptr()), 'pack tail')
     dev = [torch.from_numpy(a).cuda() for a in (x_hi, x_lo, xin_hi, xin_lo, bias)]
     pred = torch.empty((n, cout, P, P), device='cuda')

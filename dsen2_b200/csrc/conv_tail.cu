@@ -16,8 +16,9 @@
 // The epilogue then adds bias and the global skip, scales, and writes NCHW predictions or the stitched HWC canvas with the
 // last-writer-wins ownership of patches.py:394-403 (supres.py:29), exactly as the pair kernel's tail does.
 //
-// One CTA per SM (cta_group::1), persistent over the tile list.  Warps 0-3 epilogue (TMEM lane quarters), warp 4 TMA
-// producer, warp 5 TMEM alloc + MMA issue; two TMEM accumulators of 192 columns.
+// One CTA per SM (cta_group::1), persistent over the tile list.  Warps 0-7 epilogue (two per TMEM lane quarter: half of the
+// accumulator columns each on the way to shared memory, half of the output bands each in the gather), warp 8 TMA producer,
+// warp 9 TMEM alloc + MMA issue; two TMEM accumulators of 192 columns.
 #include "common.cuh"
 #include "tiling.cuh"
 
@@ -30,7 +31,8 @@ static constexpr int kTN = 192;                                    // UMMA N: th
                                                                    // are whatever follows in shared memory; their columns are never read)
 static constexpr int kTZPitch = 196;                               // floats per accumulator row in shared memory (16-byte stores, conflict-free)
 static constexpr int kTZBytes = 128 * kTZPitch * 4;
-static constexpr int kTThreads = 192;
+static constexpr int kTEpiWarps = 8;                               // two per TMEM lane quarter
+static constexpr int kTThreads = (kTEpiWarps + 2) * 32;
 static constexpr int kTMaxCout = 7;                                // 9 taps * 2 * cout <= 128 rows
 
 struct TailParams {
@@ -80,7 +82,7 @@ conv_tail_swapped_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid
   float* s_z = reinterpret_cast<float*>(bar_base + Cfg::BAR_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 4 && lane == 0) {
+  if (warp == kTEpiWarps && lane == 0) {
     tma_prefetch_desc(&tm_hi);
     tma_prefetch_desc(&tm_lo);
     tma_prefetch_desc(&tm_w);
@@ -91,18 +93,18 @@ conv_tail_swapped_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid
     mbar_init(wfull, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);                 // one arrival per epilogue warp
+      mbar_init(&tmem_empty[i], kTEpiWarps);        // one arrival per epilogue warp
     }
     mbar_fence_init();
   }
-  if (warp == 5) tmem_alloc<512>(tmem_ptr);
+  if (warp == kTEpiWarps + 1) tmem_alloc<512>(tmem_ptr);
   if (threadIdx.x < 16) s_bias[threadIdx.x] = threadIdx.x < p.cout ? p.bias[threadIdx.x] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 4) {
+  if (warp == kTEpiWarps) {
     // ================================ TMA producer ================================
     if (elect_one()) {
       mbar_expect_tx(wfull, Cfg::W_BYTES);
@@ -122,7 +124,7 @@ conv_tail_swapped_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kTEpiWarps + 1) {
     // ================================ MMA issuer ==================================
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_f16(128, kTN);
@@ -151,10 +153,14 @@ conv_tail_swapped_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid
       }
     }
   } else {
-    // ================================ epilogue (128 threads) ======================
-    const int t = threadIdx.x;                     // TMEM lane = accumulator row (tap, hl, c) in phase 1; tile pixel in phase 2
+    // ================================ epilogue (256 threads) ======================
+    // phase 1: thread = (TMEM lane = accumulator row (tap, hl, c), half of the columns); phase 2: thread = (tile pixel, half
+    // of the output bands)
+    const int lane_row = (warp & 3) * 32 + lane, half = warp >> 2;
     const int rows_used = 18 * p.cout;
-    const int yy = t >> 3, xx = t & 7;
+    const int pix_t = threadIdx.x & 127, yy = pix_t >> 3, xx = pix_t & 7;
+    const int cper = (p.cout + 1) >> 1, c_lo = half * cper, c_hi = min(p.cout, c_lo + cper);   // this thread's bands
+    const int hl_stride = p.cout * kTZPitch, tap_stride = 2 * hl_stride;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (uint32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -164,7 +170,7 @@ conv_tail_swapped_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid
       const int y = ty * 16 + yy, x = tx * 8 + xx;
       const bool valid = (b < p.n) && (y < p.H) && (x < p.W);
       // where this pixel goes (and whether this patch owns it), and its global skip -- before the accumulator is ready
-      bool write = valid;
+      bool write = valid && c_lo < c_hi;
       long long obase = 0, ostride = 0;
       if (write) {
         if (p.tail_mode == 0) {
@@ -182,28 +188,28 @@ conv_tail_swapped_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid
           obase = ((long long)gy * p.img_w + gx) * p.cout;
         }
       }
-      float skip[kTMaxCout];
+      float skip[(kTMaxCout + 1) / 2];
 #pragma unroll
-      for (int c = 0; c < kTMaxCout; ++c) skip[c] = 0.f;
+      for (int i = 0; i < (kTMaxCout + 1) / 2; ++i) skip[i] = 0.f;
       if (write) {
         const long long pix = ((long long)b * p.H + y) * p.W + x;
-        const __half* sh = p.skip_hi + pix * 16 + p.skip_ch0;
-        const __half* sl = p.skip_lo + pix * 16 + p.skip_ch0;
+        const __half* sh = p.skip_hi + pix * 16 + p.skip_ch0 + c_lo;
+        const __half* sl = p.skip_lo + pix * 16 + p.skip_ch0 + c_lo;
 #pragma unroll
-        for (int c = 0; c < kTMaxCout; ++c)
-          if (c < p.cout) skip[c] = __half2float(__ldg(sh + c)) + __half2float(__ldg(sl + c));
+        for (int i = 0; i < (kTMaxCout + 1) / 2; ++i)
+          if (c_lo + i < c_hi) skip[i] = __half2float(__ldg(sh + i)) + __half2float(__ldg(sl + i));
       }
-      // ---- phase 1: accumulator rows -> shared memory (thread = TMEM lane)
+      // ---- phase 1: accumulator rows -> shared memory
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * kTN);
-      const uint32_t zrow = smem_u32(s_z) + (uint32_t)(t * kTZPitch * 4);
+      const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(acc * kTN + half * (kTN / 2));
+      const uint32_t zrow = smem_u32(s_z) + (uint32_t)((lane_row * kTZPitch + half * (kTN / 2)) * 4);
 #pragma unroll 1
-      for (int chunk = 0; chunk < kTN / 32; ++chunk) {
+      for (int chunk = 0; chunk < kTN / 64; ++chunk) {
         uint32_t r[32];
         tmem_ld_32x32(taddr + chunk * 32, r);
         tmem_ld_wait();
-        if (t < rows_used) {
+        if (lane_row < rows_used) {
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             sts128(zrow + (uint32_t)((chunk * 32 + q * 4) * 4), make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]));
@@ -212,26 +218,27 @@ conv_tail_swapped_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);          // the TMEM buffer is free for the tile after next
-      asm volatile("bar.sync 1, 128;" ::: "memory");          // all rows of this tile are in shared memory
-      // ---- phase 2: thread = pixel gathers its 18 * cout terms, shifted by the tap offsets
+      asm volatile("bar.sync 1, 256;" ::: "memory");          // all rows of this tile are in shared memory
+      // ---- phase 2: gather the 18 terms of each band of this pixel, shifted by the tap offsets
       if (write) {
-        const int col0 = yy * kTBoxW + xx;                     // box pixel of tap (0, 0)
+        const float* z0 = s_z + c_lo * kTZPitch + yy * kTBoxW + xx;     // band c_lo, tap (0, 0), W_hi row
 #pragma unroll
-        for (int c = 0; c < kTMaxCout; ++c) {
-          if (c < p.cout) {
-            float v = 0.f;
+        for (int i = 0; i < (kTMaxCout + 1) / 2; ++i) {
+          if (c_lo + i < c_hi) {
+            const float* z = z0 + i * kTZPitch;
+            float vh = 0.f, vl = 0.f;
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
-              const int col = col0 + (tap / 3) * kTBoxW + (tap % 3);
-              const float* z = s_z + (size_t)((tap * 2) * p.cout + c) * kTZPitch + col;
-              v += z[0] + z[(size_t)p.cout * kTZPitch];           // W_hi and W_lo rows of this tap
+              const int off = (tap / 3) * kTBoxW + (tap % 3);
+              vh += z[tap * tap_stride + off];                 // W_hi row of this tap
+              vl += z[tap * tap_stride + hl_stride + off];     // W_lo row
             }
-            v += s_bias[c];
-            p.out[obase + c * ostride] = (v + skip[c]) * p.out_mul;   // Add (DSen2Net.py:38), then x SCALE
+            const float v = (vh + vl) + s_bias[c_lo + i];
+            p.out[obase + (c_lo + i) * ostride] = (v + skip[i]) * p.out_mul;   // Add (DSen2Net.py:38), then x SCALE
           }
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");          // the shared-memory copy may be overwritten
+      asm volatile("bar.sync 1, 256;" ::: "memory");          // the shared-memory copy may be overwritten
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -239,7 +246,7 @@ conv_tail_swapped_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 5) tmem_dealloc<512>(tmem_base);
+  if (warp == kTEpiWarps + 1) tmem_dealloc<512>(tmem_base);
 }
 
 // tail weights for the swapped form: [128 rows: (tap * 2 + hl) * cout + c][F channels] fp16, K-major; unused rows zero

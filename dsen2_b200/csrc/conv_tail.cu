@@ -33,6 +33,7 @@ static constexpr int kTZPitch = 196;                               // floats per
 static constexpr int kTZBytes = 128 * kTZPitch * 4;
 static constexpr int kTEpiWarps = 8;                               // two per TMEM lane quarter
 static constexpr int kTThreads = (kTEpiWarps + 2) * 32;
+static constexpr int kTPrefetch = 3;                               // L2 prefetch distance of the activation boxes, in tiles of a CTA
 static constexpr int kTMaxCout = 7;                                // 9 taps * 2 * cout <= 128 rows
 
 struct TailParams {
@@ -115,6 +116,17 @@ conv_tail_swapped_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid
         const uint32_t row = tile / (uint32_t)p.tiles_x;
         const int tx = (int)(tile - row * (uint32_t)p.tiles_x) + p.tx0;
         const int b = (int)(row / (uint32_t)p.tiles_y), ty = (int)(row - (uint32_t)b * (uint32_t)p.tiles_y);
+        // A tile is only ~1500 tensor clocks and the stages hold one tile of look-ahead: pull the boxes of the tile this CTA
+        // loads kTPrefetch iterations from now into L2, so that the loads below are L2 hits
+        const uint32_t tp = tile + kTPrefetch * gridDim.x;
+        if (tp < p.num_tiles) {
+          const uint32_t prow = tp / (uint32_t)p.tiles_x;
+          const int ptx = (int)(tp - prow * (uint32_t)p.tiles_x) + p.tx0;
+          const int pb = (int)(prow / (uint32_t)p.tiles_y), pty = (int)(prow - (uint32_t)pb * (uint32_t)p.tiles_y);
+#pragma unroll
+          for (int kb = 0; kb < 2 * KPM; ++kb)
+            tma_prefetch_4d(kb < KPM ? &tm_hi : &tm_lo, (kb % KPM) * 64, ptx * 8 - 1, pty * 16 - 1, pb);
+        }
 #pragma unroll 1
         for (int kb = 0; kb < 2 * KPM; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);

@@ -33,7 +33,6 @@ static constexpr int kTZPitch = 196;                               // floats per
 static constexpr int kTZBytes = 128 * kTZPitch * 4;
 static constexpr int kTEpiWarps = 8;                               // two per TMEM lane quarter
 static constexpr int kTThreads = (kTEpiWarps + 2) * 32;
-static constexpr int kTPrefetch = 3;                               // L2 prefetch distance of the activation boxes, in tiles of a CTA
 static constexpr int kTMaxCout = 7;                                // 9 taps * 2 * cout <= 128 rows
 
 struct TailParams {
@@ -116,17 +115,6 @@ conv_tail_swapped_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid
         const uint32_t row = tile / (uint32_t)p.tiles_x;
         const int tx = (int)(tile - row * (uint32_t)p.tiles_x) + p.tx0;
         const int b = (int)(row / (uint32_t)p.tiles_y), ty = (int)(row - (uint32_t)b * (uint32_t)p.tiles_y);
-        // A tile is only ~1500 tensor clocks and the stages hold one tile of look-ahead: pull the boxes of the tile this CTA
-        // loads kTPrefetch iterations from now into L2, so that the loads below are L2 hits
-        const uint32_t tp = tile + kTPrefetch * gridDim.x;
-        if (tp < p.num_tiles) {
-          const uint32_t prow = tp / (uint32_t)p.tiles_x;
-          const int ptx = (int)(tp - prow * (uint32_t)p.tiles_x) + p.tx0;
-          const int pb = (int)(prow / (uint32_t)p.tiles_y), pty = (int)(prow - (uint32_t)pb * (uint32_t)p.tiles_y);
-#pragma unroll
-          for (int kb = 0; kb < 2 * KPM; ++kb)
-            tma_prefetch_4d(kb < KPM ? &tm_hi : &tm_lo, (kb % KPM) * 64, ptx * 8 - 1, pty * 16 - 1, pb);
-        }
 #pragma unroll 1
         for (int kb = 0; kb < 2 * KPM; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
@@ -175,42 +163,51 @@ conv_tail_swapped_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid
     const int hl_stride = p.cout * kTZPitch, tap_stride = 2 * hl_stride;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (uint32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    // Where a tile's pixel of this thread goes (and whether this patch owns it), and its global skip.  The skip is loaded
+    // ONE TILE AHEAD: a dependent global load inside the per-tile chain (wait, copy, barrier, gather, barrier) would put
+    // a DRAM latency on every tile -- measured: the tile took 4.4 us for 1.2 us of MMAs.
+    struct Dest { bool write; long long obase, ostride; };
+    auto locate = [&](uint32_t tile, Dest& d, __half (&sk_hi)[(kTMaxCout + 1) / 2], __half (&sk_lo)[(kTMaxCout + 1) / 2]) {
       const uint32_t rowi = tile / (uint32_t)p.tiles_x;
       const int tx = (int)(tile - rowi * (uint32_t)p.tiles_x) + p.tx0;
       const int b = (int)(rowi / (uint32_t)p.tiles_y), ty = (int)(rowi - (uint32_t)b * (uint32_t)p.tiles_y);
       const int y = ty * 16 + yy, x = tx * 8 + xx;
-      const bool valid = (b < p.n) && (y < p.H) && (x < p.W);
-      // where this pixel goes (and whether this patch owns it), and its global skip -- before the accumulator is ready
-      bool write = valid && c_lo < c_hi;
-      long long obase = 0, ostride = 0;
-      if (write) {
+      d.write = tile < p.num_tiles && (b < p.n) && (y < p.H) && (x < p.W) && c_lo < c_hi;
+      d.obase = 0; d.ostride = 0;
+      if (d.write) {
         if (p.tail_mode == 0) {
-          ostride = (long long)p.H * p.W;
-          obase = (long long)b * p.cout * ostride + (long long)y * p.W + x;
+          d.ostride = (long long)p.H * p.W;
+          d.obase = (long long)b * p.cout * d.ostride + (long long)y * p.W + x;
         } else {
           const int S = p.H - 2 * p.border;
           const int patch = p.first_patch + b;
           const int pty = patch / p.grid_nx, ptx = patch - pty * p.grid_nx;
           const int gy = min(pty * S, p.img_h - S) + y - p.border;
           const int gx = min(ptx * S, p.img_w - S) + x - p.border;
-          write = y >= p.border && y < p.H - p.border && x >= p.border && x < p.W - p.border &&
-                  tail_stitch_tile_of(gy, p.img_h, S, p.grid_ny) == pty && tail_stitch_tile_of(gx, p.img_w, S, p.grid_nx) == ptx;
-          ostride = 1;
-          obase = ((long long)gy * p.img_w + gx) * p.cout;
+          d.write = y >= p.border && y < p.H - p.border && x >= p.border && x < p.W - p.border &&
+                    tail_stitch_tile_of(gy, p.img_h, S, p.grid_ny) == pty && tail_stitch_tile_of(gx, p.img_w, S, p.grid_nx) == ptx;
+          d.ostride = 1;
+          d.obase = ((long long)gy * p.img_w + gx) * p.cout;
         }
       }
-      float skip[(kTMaxCout + 1) / 2];
-#pragma unroll
-      for (int i = 0; i < (kTMaxCout + 1) / 2; ++i) skip[i] = 0.f;
-      if (write) {
+      if (d.write) {
         const long long pix = ((long long)b * p.H + y) * p.W + x;
         const __half* sh = p.skip_hi + pix * 16 + p.skip_ch0 + c_lo;
         const __half* sl = p.skip_lo + pix * 16 + p.skip_ch0 + c_lo;
 #pragma unroll
         for (int i = 0; i < (kTMaxCout + 1) / 2; ++i)
-          if (c_lo + i < c_hi) skip[i] = __half2float(__ldg(sh + i)) + __half2float(__ldg(sl + i));
+          if (c_lo + i < c_hi) { sk_hi[i] = __ldg(sh + i); sk_lo[i] = __ldg(sl + i); }
       }
+    };
+    Dest cur, nxt;
+    __half ch[(kTMaxCout + 1) / 2], cl[(kTMaxCout + 1) / 2], nh[(kTMaxCout + 1) / 2], nl[(kTMaxCout + 1) / 2];
+#pragma unroll
+    for (int i = 0; i < (kTMaxCout + 1) / 2; ++i) ch[i] = cl[i] = nh[i] = nl[i] = __float2half_rn(0.f);
+    locate(blockIdx.x, cur, ch, cl);
+    for (uint32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      locate(tile + gridDim.x, nxt, nh, nl);                 // next tile's destination and skip loads, in flight during this tile
+      const bool write = cur.write;
+      const long long obase = cur.obase, ostride = cur.ostride;
       // ---- phase 1: accumulator rows -> shared memory
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -246,11 +243,15 @@ conv_tail_swapped_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid
               vl += z[tap * tap_stride + hl_stride + off];     // W_lo row
             }
             const float v = (vh + vl) + s_bias[c_lo + i];
-            p.out[obase + (c_lo + i) * ostride] = (v + skip[i]) * p.out_mul;   // Add (DSen2Net.py:38), then x SCALE
+            const float skip = __half2float(ch[i]) + __half2float(cl[i]);
+            p.out[obase + (c_lo + i) * ostride] = (v + skip) * p.out_mul;      // Add (DSen2Net.py:38), then x SCALE
           }
         }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");          // the shared-memory copy may be overwritten
+      cur = nxt;
+#pragma unroll
+      for (int i = 0; i < (kTMaxCout + 1) / 2; ++i) { ch[i] = nh[i]; cl[i] = nl[i]; }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }

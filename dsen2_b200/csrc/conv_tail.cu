@@ -8,13 +8,17 @@
 //     A (M = 128 rows)  row (tap * 2 + hl) * cout + c  = W_hl[tap][:, c]   (hl: fp16 hi / lo part of the fp32 kernel)
 //     B (N = 192 rows)  the 18 x 10 pixel halo box of the tile, as it lies in shared memory after ONE TMA load
 //     D[(tap, hl, c)][box pixel] = sum_k W_hl[tap][k, c] * x[box pixel][k]            (x = x_hi k-blocks, then x_lo k-blocks)
-// so an activation element crosses the shared-memory read port once per k-step instead of nine times (98 KB per tile),
-// 16 MMAs of M = 128, N = 192 per tile = 1536 tensor clocks, and the 3x3 structure moves to the epilogue:
+// so an activation element crosses the shared-memory read port once per k-step instead of nine times, 16 MMAs of M = 128,
+// N = 192 per tile (1536 tensor clocks), and the 3x3 structure moves to the epilogue:
 //     out[c][y, x] = sum_tap sum_hl D[(tap, hl, c)][(y + dy) * 10 + (x + dx)]
 // a shifted gather over TMEM LANES, done through a shared-memory copy of the accumulator (thread = lane writes its row,
-// thread = pixel gathers its 18 * cout terms).  All four products (hi + lo) x (W_hi + W_lo) are kept: fp32-equivalent.
+// thread = pixel gathers its 18 terms per band).  All four products (hi + lo) x (W_hi + W_lo) are kept: fp32-equivalent.
 // The epilogue then adds bias and the global skip, scales, and writes NCHW predictions or the stitched HWC canvas with the
-// last-writer-wins ownership of patches.py:394-403 (supres.py:29), exactly as the pair kernel's tail does.
+// last-writer-wins ownership of patches.py:394-403 (supres.py:29).
+// Shared-memory port budget per tile (128 B/clk): MMA operands 160 KB + TMA fill 92 KB + accumulator copy 83 KB in, 55 KB
+// out = 390 KB ~ 3100 clocks (was 590 + 92 KB); measured 28 ms per 10980^2 tile instead of 37, DRAM at 44-53 % of the copy
+// peak (profiles/r02_tail_swapped_ncu.txt).  The global skip is loaded one tile ahead: as a dependent load inside the
+// per-tile chain (wait, copy, barrier, gather, barrier) it cost a DRAM latency per tile (33 ms).
 //
 // One CTA per SM (cta_group::1), persistent over the tile list.  Warps 0-7 epilogue (two per TMEM lane quarter: half of the
 // accumulator columns each on the way to shared memory, half of the output bands each in the gather), warp 8 TMA producer,

@@ -181,8 +181,8 @@ def workload_config(args, cpu=False):
 # ---------------------------------------------------------------------------------------------- #
 # DRAM bytes per patch and launch of the trunk convolutions, dram__bytes_read.sum + dram__bytes_write.sum of an
 # `ncu --set full` capture (a CONSTANT taken from the named file, not measured in the bench run): mean of the RELU layer
-# (660 MB per 84 patches) and the RESIDUALQ layer (1359 MB per 84 patches).
-NCU_TRAFFIC = {128: dict(bytes_per_patch=(7.86e6 + 16.18e6) / 2, source="profiles/r01_q_trunk_ncu_full.txt")}
+# (617 + 572 MB per 147 patches) and the RESIDUALQ layer (1542 + 875 MB per 147 patches).
+NCU_TRAFFIC = {128: dict(bytes_per_patch=(1.189e9 + 2.417e9) / 2 / 147, source="profiles/r02_whole_batch_xt2_pingpong_ncu_full.txt")}
 
 
 def run_ours(args):

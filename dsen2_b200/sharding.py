@@ -68,17 +68,30 @@ def input_rows(first, count, H, W, P, border):
     return r0, r1
 
 
-def plan_chunks(first, count, H, W, P, border, chunk_patch_rows):
+def plan_chunks(first, count, H, W, P, border, chunk_patch_rows, edge_patch_rows=None):
     """Cut the patch range [first, first+count) into chunks of whole patch rows for the host-buffer pipeline.
 
     Returns [(p0, cnt, (r0, r1), rects)]: the chunk's patch range, the 10 m input rows it reads and the output
     rectangles it owns.  Consecutive chunks read monotonically advancing row ranges, so each input row needs to be
-    uploaded once (``supres.HostPipeline`` uploads only the rows beyond the previous chunk's)."""
+    uploaded once (``supres.HostPipeline`` uploads only the rows beyond the previous chunk's).
+    ``edge_patch_rows``: size of the FIRST and the LAST chunk (default: ``chunk_patch_rows``).  The first chunk's upload
+    and the last chunk's download are the only transfers that do not overlap with compute, so they are kept small while
+    the chunks in between are large enough for full-size launches."""
     ny, nx, _ = tile_grid(H, W, P, border)
-    plan, p0, end = [], first, first + count
+    edge = chunk_patch_rows if edge_patch_rows is None else edge_patch_rows
+    end = first + count
+    last_row = (end - 1) // nx if count > 0 else 0
+    plan, p0 = [], first
     while p0 < end:
         row = p0 // nx
-        p1 = min(end, (row + chunk_patch_rows) * nx)
+        rows_left = last_row - row + 1
+        if p0 == first:
+            step = edge
+        elif rows_left <= edge:
+            step = rows_left                           # the last chunk
+        else:
+            step = min(chunk_patch_rows, rows_left - edge)   # keep `edge` rows for the last chunk
+        p1 = min(end, (row + max(1, step)) * nx)
         cnt = p1 - p0
         plan.append((p0, cnt, input_rows(p0, cnt, H, W, P, border), owned_rects(p0, cnt, H, W, P, border)))
         p0 = p1
@@ -86,11 +99,13 @@ def plan_chunks(first, count, H, W, P, border, chunk_patch_rows):
 
 
 def auto_chunk_rows(num_patches, nx):
-    """Patch rows per host-pipeline chunk: the first chunk's upload and the last chunk's download are not hidden behind
-    compute, so a chunk is about a twelfth of the call's share of the tile, between 1 and 3 patch rows (a rank of 8
-    holds ~12 patch rows of a full Sentinel-2 tile, one GPU all 99)."""
+    """Patch rows per host-pipeline chunk -> (middle, edge): three patch rows (a full 297-patch launch on a Sentinel-2
+    tile) in the middle of the range, one at both ends when the range is short (a rank of 8 holds ~12 patch rows of a
+    full tile: its un-overlapped first upload / last download would otherwise be a quarter of its work)."""
     rows = -(-int(num_patches) // int(nx))
-    return max(1, min(3, rows // 12))
+    middle = max(1, min(3, rows // 4))
+    edge = 1 if rows < 48 else middle
+    return middle, edge
 
 
 def assemble(canvas, parts):

@@ -201,10 +201,11 @@ class HostPipeline:
         return hout
 
     def _plan(self, first_patch, num_patches):
-        chunk_rows = self.chunk_rows
-        if chunk_rows is None:
-            chunk_rows = sharding.auto_chunk_rows(num_patches, self.nx)
-        return sharding.plan_chunks(first_patch, num_patches, self.H, self.W, self.P, self.B, int(chunk_rows))
+        if self.chunk_rows is None:
+            middle, edge = sharding.auto_chunk_rows(num_patches, self.nx)
+        else:
+            middle = edge = int(self.chunk_rows)
+        return sharding.plan_chunks(first_patch, num_patches, self.H, self.W, self.P, self.B, middle, edge)
 
     # ---- pageable numpy arrays: pinned staging ring + worker threads -------------------------------------------------
     def _ring(self, plan):

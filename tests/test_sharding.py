@@ -48,7 +48,7 @@ def test_plan_chunks_covers_range_once_with_monotonic_uploads(geom, world, chunk
     cover = np.zeros((H, W), np.uint8)
     for r in range(world):
         first, count = sharding.shard_range(ny * nx, r, world)
-        plan = sharding.plan_chunks(first, count, H, W, P, B, chunk_rows)
+        plan = sharding.plan_chunks(first, count, H, W, P, B, chunk_rows, 1 if chunk_rows > 1 else None)
         assert [p for p, _, _, _ in plan] == sorted(p for p, _, _, _ in plan)
         assert sum(c for _, c, _, _ in plan) == count and plan[0][0] == first
         resident = None                                    # [lo, hi) rows on the device, as HostPipeline tracks them
@@ -148,8 +148,14 @@ def test_batch_and_chunk_sizing_rules():
     assert default_device_batch(10980, 192, 12) == 2 * 66         # 60 m path: two rows of 192-pixel patches
     assert default_device_batch(600, 128, 8) >= 36                # a 600 x 600 scene is one launch
     assert default_device_batch(2352, 128, 8) % 21 == 0
-    assert sharding.auto_chunk_rows(9801, 99) == 3                # one GPU: 99 patch rows
-    assert sharding.auto_chunk_rows(1226, 99) == 1                # a rank of 8
-    assert sharding.auto_chunk_rows(36, 6) == 1                   # small scene
-    plan = sharding.plan_chunks(0, 9801, 10980, 10980, 128, 8, sharding.auto_chunk_rows(9801, 99))
+    assert sharding.auto_chunk_rows(9801, 99) == (3, 3)           # one GPU: 99 patch rows, 33 full launches
+    assert sharding.auto_chunk_rows(1226, 99) == (3, 1)           # a rank of 8: small first / last chunk, big ones between
+    assert sharding.auto_chunk_rows(36, 6) == (1, 1)              # small scene
+    plan = sharding.plan_chunks(0, 9801, 10980, 10980, 128, 8, *sharding.auto_chunk_rows(9801, 99))
     assert len(plan) == 33 and sum(c[1] for c in plan) == 9801 and all(c[1] == 297 for c in plan)
+    # rank 3 of 8: patches [3676, 4901) = rows 37.1 .. 49.5: the rest of row 37, three-row chunks, one row at the end
+    first, count = sharding.shard_range(9801, 3, 8)
+    plan = sharding.plan_chunks(first, count, 10980, 10980, 128, 8, *sharding.auto_chunk_rows(count, 99))
+    sizes = [c[1] for c in plan]
+    assert sum(sizes) == count and [c[0] for c in plan] == [first + sum(sizes[:i]) for i in range(len(sizes))]
+    assert sizes[0] <= 99 and sizes[-1] <= 99 and max(sizes) == 297 and len(plan) <= 7

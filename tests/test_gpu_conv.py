@@ -289,3 +289,27 @@ def test_demo_driver_runs_on_a_scene_file(env, malmo, tmp_path, capsys):
     out = capsys.readouterr().out
     assert rc == 0 and out.count('super-resolved') == 2 and '(240, 240, 6)' in out and '(240, 240, 2)' in out
     assert out.count('skipping') == 5                      # the other scenes of the demo are not in the directory
+
+
+def test_integration_md_ctypes_stub_runs_as_written(env):
+    """The reference-side binding shown in INTEGRATION.md section 2 is executed verbatim (only the library path is
+    resolved) and must give the facade's result bit for bit -- the document cannot drift from the ABI."""
+    import os
+    import re
+    from dsen2_b200 import supres
+    from dsen2_b200.DSen2Net import s2model
+    torch, _capi, lib = env
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, 'INTEGRATION.md')).read()
+    code = re.search(r"```python\n(# testing/supres_b200\.py.*?)```", text, re.S).group(1)
+    code = code.replace('ctypes.CDLL("libdsen2_b200.so")', 'ctypes.CDLL(%r)' % _capi.LIB_PATH)
+    ns = {}
+    exec(compile(code, 'INTEGRATION.md', 'exec'), ns)
+    rng = np.random.RandomState(21)
+    d10 = rng.randint(0, 9000, size=(300, 412, 4)).astype(np.uint16)
+    d20 = rng.randint(0, 9000, size=(150, 206, 6)).astype(np.uint16)
+    model = s2model(((4, None, None), (6, None, None)), num_layers=6, feature_size=128, seed=8)
+    wts, biases, _, _ = model._ensure_packed(torch.device('cuda', torch.cuda.current_device()))
+    got = ns['DSen2_20'](d10, d20, (wts, biases))
+    assert np.array_equal(got, supres.DSen2_20(d10, d20, model=model))
+    assert np.array_equal(ns['DSen2_20'](d10.astype(np.float32), d20.astype(np.float32), (wts, biases)), got)

@@ -98,11 +98,15 @@ def plan_chunks(first, count, H, W, P, border, chunk_patch_rows, edge_patch_rows
     return plan
 
 
-def auto_chunk_rows(num_patches, nx):
+def auto_chunk_rows(num_patches, nx, device_batch=None):
     """Patch rows per host-pipeline chunk -> (middle, edge): three patch rows (a full 297-patch launch on a Sentinel-2
     tile) in the middle of the range, one at both ends when the range is short (a rank of 8 holds ~12 patch rows of a
-    full tile: its un-overlapped first upload / last download would otherwise be a quarter of its work)."""
+    full tile: its un-overlapped first upload / last download would otherwise be a quarter of its work).  A range that
+    fits ONE device batch (a 600 x 600 scene: 36 patches) is a single chunk: there is nothing to overlap, and every
+    extra chunk costs a set of launches."""
     rows = -(-int(num_patches) // int(nx))
+    if device_batch is not None and num_patches <= device_batch:
+        return rows, rows
     middle = max(1, min(3, rows // 4))
     edge = 1 if rows < 48 else middle
     return middle, edge

@@ -202,7 +202,8 @@ class HostPipeline:
 
     def _plan(self, first_patch, num_patches):
         if self.chunk_rows is None:
-            middle, edge = sharding.auto_chunk_rows(num_patches, self.nx)
+            batch = self.device_batch or default_device_batch(self.W, self.P, self.B)
+            middle, edge = sharding.auto_chunk_rows(num_patches, self.nx, batch)
         else:
             middle = edge = int(self.chunk_rows)
         return sharding.plan_chunks(first_patch, num_patches, self.H, self.W, self.P, self.B, middle, edge)

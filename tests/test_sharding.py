@@ -150,7 +150,9 @@ def test_batch_and_chunk_sizing_rules():
     assert default_device_batch(2352, 128, 8) % 21 == 0
     assert sharding.auto_chunk_rows(9801, 99) == (3, 3)           # one GPU: 99 patch rows, 33 full launches
     assert sharding.auto_chunk_rows(1226, 99) == (3, 1)           # a rank of 8: small first / last chunk, big ones between
-    assert sharding.auto_chunk_rows(36, 6) == (1, 1)              # small scene
+    assert sharding.auto_chunk_rows(36, 6) == (1, 1)              # small range, no batch size given
+    assert sharding.auto_chunk_rows(36, 6, 300) == (6, 6)         # a 600 x 600 scene fits one device batch: one chunk
+    assert sharding.auto_chunk_rows(1226, 99, 297) == (3, 1)
     plan = sharding.plan_chunks(0, 9801, 10980, 10980, 128, 8, *sharding.auto_chunk_rows(9801, 99))
     assert len(plan) == 33 and sum(c[1] for c in plan) == 9801 and all(c[1] == 297 for c in plan)
     # rank 3 of 8: patches [3676, 4901) = rows 37.1 .. 49.5: the rest of row 37, three-row chunks, one row at the end

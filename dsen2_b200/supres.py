@@ -340,6 +340,10 @@ def _run(model, arrays, out=None):
     torch = _capi.require_cuda()
     arrays = [np.asarray(a) for a in arrays]
     H, W = int(arrays[0].shape[0]), int(arrays[0].shape[1])
+    for a, div, c in zip(arrays, (1, 2, 6), model.in_channels):
+        if a.ndim != 3 or tuple(a.shape) != (H // div, W // div, c):
+            raise ValueError("expected an image of shape %s (HWC, 10 m size %dx%d / %d), got %s"
+                             % ((H // div, W // div, c), H, W, div, tuple(a.shape)))
     # uint16 digital numbers (GDAL, s2_tiles_supres.py:311-315) stay uint16 up to the input-preparation kernel; everything
     # else is staged as float32 (the reference divides by SCALE in floating point whatever the input type, supres.py:23-24)
     dtype = torch.uint16 if (model.xin16 and all(a.dtype == np.uint16 for a in arrays)) else torch.float32

@@ -77,3 +77,14 @@ def test_facade_60m_uint16(scene):
     assert a.shape == (H, W, 2) and np.array_equal(a, b)
     c = supres.super_resolve_device(model, *[torch.from_numpy(x.astype(np.float32)).cuda() for x in (d10, d20, d60)])
     assert np.array_equal(a, c.cpu().numpy())
+
+
+def test_facade_rejects_mismatched_shapes(scene):
+    torch, model, d10, d20 = scene
+    from dsen2_b200 import supres
+    with pytest.raises(ValueError):
+        supres.DSen2_20(d10, d20[:-1], model=model)
+    with pytest.raises(ValueError):
+        supres.DSen2_20(d10[:, :, :3], d20, model=model)
+    with pytest.raises(ValueError):
+        supres.DSen2_20(d10[:-1], d20, model=model)          # odd 10 m height

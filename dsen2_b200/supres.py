@@ -161,7 +161,8 @@ class HostPipeline:
         return b if done is None else max(done, b)
 
     def run(self, h10, h20, h60=None, hout=None, first_patch=0, num_patches=None, timers=None):
-        """Pinned torch tensors in (dtype = the pipeline's), pinned float32 (H, W, Cout) tensor out."""
+        """Pinned torch tensors in (dtype = the pipeline's), pinned float32 (H, W, Cout) tensor out.  Rows of ``hout`` that
+        the patch range owns only partly (the seam rows of a sharded range) are downloaded whole."""
         torch = self.torch
         filled = self.ny * self.nx
         if num_patches is None:
@@ -192,11 +193,12 @@ class HostPipeline:
             self.down.wait_event(ev_c)
             with torch.cuda.stream(self.down):
                 for (y0, y1, x0, x1) in rects:
-                    if x0 == 0 and x1 == self.W:
-                        hout[y0:y1].copy_(self.canvas[y0:y1], non_blocking=True)
-                    else:
-                        hout[y0:y1, x0:x1].copy_(self.canvas[y0:y1, x0:x1], non_blocking=True)
-                    self.d2h_bytes += (y1 - y0) * (x1 - x0) * self.canvas.shape[2] * 4
+                    # Whole rows, also where the range starts / ends inside a patch row and owns only part of them: a
+                    # strided (partial-width) device -> host copy goes through temporaries and synchronises.  The pixels
+                    # of those rows that another rank owns come along as they are on this device (never computed here);
+                    # `sharding.assemble` / `owned_rects` say which part of a row is this rank's.
+                    hout[y0:y1].copy_(self.canvas[y0:y1], non_blocking=True)
+                    self.d2h_bytes += (y1 - y0) * self.W * self.canvas.shape[2] * 4
         main.wait_stream(self.down)
         return hout
 

@@ -173,6 +173,26 @@ __global__ void pack_dgrad_weights_kernel(const float* __restrict__ hwio, int ci
   }
 }
 
+// All F -> F layers of the network in ONE launch (they are a regular stride apart in the flat Keras-order parameter vector):
+// forward operand fwd[l][t][o][i] = f16(w[t][i][o]) and backward-data operand bwd[l][t][i][o] = f16(s_l * w[8-t][i][o]),
+// s_l = scale_second for the second convolution of a resBlock (odd l), 1 otherwise.  Same arithmetic as
+// pack_weights_kernel / pack_dgrad_weights_kernel, 2 * layers - 1 launches fewer per training step.
+__global__ void pack_trunk_layers_kernel(const float* __restrict__ params, long long layer_stride, int F, float scale_second,
+                                         __half* __restrict__ fwd, __half* __restrict__ bwd) {
+  const int l = blockIdx.y;
+  const float* w = params + (long long)l * layer_stride;
+  const long long per = 9LL * F * F;
+  const float sc = (l & 1) ? scale_second : 1.0f;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < per; idx += (long long)gridDim.x * blockDim.x) {
+    const int o = (int)(idx % F);
+    const int i = (int)((idx / F) % F);
+    const int t = (int)(idx / ((long long)F * F));
+    const float v = w[idx];                                              // w[t][i][o]
+    fwd[l * per + ((long long)t * F + o) * F + i] = __float2half_rn(v);
+    bwd[l * per + ((long long)(8 - t) * F + i) * F + o] = __float2half_rn(sc * v);
+  }
+}
+
 struct TileXY3 { int b, ty, tx; };
 __device__ __forceinline__ TileXY3 decode_tile3(uint32_t tile, uint32_t tiles_x, uint32_t tiles_y) {
   const uint32_t row = tile / tiles_x;
@@ -404,3 +424,17 @@ extern "C" int dsen2_pack_dgrad_weights(const float* d_hwio, int cin, int cout, 
   return check_launch("pack_dgrad_weights");
 }
 
+
+extern "C" int dsen2_pack_trunk_layers(const float* d_first_kernel, long long layer_stride, int num_layers, int feature_size,
+                                       float scale_second, void* d_fwd, void* d_bwd, void* stream) {
+  DSEN2_REQUIRE(d_first_kernel && d_fwd && d_bwd, DSEN2_E_BADARG, "dsen2_pack_trunk_layers: null pointer");
+  DSEN2_REQUIRE(num_layers >= 0 && num_layers < 65536 && feature_size > 0 && feature_size % 64 == 0 &&
+                    layer_stride >= 9LL * feature_size * feature_size,
+                DSEN2_E_BADARG, "dsen2_pack_trunk_layers: bad arguments");
+  if (num_layers == 0) return 0;
+  const long long per = 9LL * feature_size * feature_size;
+  const dim3 grid((unsigned)((per + 255) / 256 < 1024 ? (per + 255) / 256 : 1024), (unsigned)num_layers);
+  pack_trunk_layers_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_first_kernel, layer_stride, feature_size, scale_second,
+                                                                   (__half*)d_fwd, (__half*)d_bwd);
+  return check_launch("pack_trunk_layers");
+}

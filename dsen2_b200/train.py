@@ -129,9 +129,14 @@ class Trainer:
         self.loss_out = torch.zeros(2, dtype=torch.float64, device=self.dev)
         f16 = lambda *s: torch.empty(s, dtype=torch.float16, device=self.dev)
         F, L = self.F, self.L
-        self.w_fwd = [f16(3, 2 * F, 64)] + [f16(9, F, F) for _ in range(2 * L)] + [f16(9, 32, F)]
-        self.w_bwd = [None] + [f16(9, F, F) for _ in range(2 * L)] + [f16(9, F, F)]
-        self.b_fwd = [torch.zeros(max(c, 16), dtype=torch.float32, device=self.dev) for _, c in shapes]
+        # the 2L trunk layers' operands are stacked so that ONE launch repacks them all after every update
+        self.w_fwd_trunk, self.w_bwd_trunk = f16(max(2 * L, 1), 9, F, F), f16(max(2 * L, 1), 9, F, F)
+        self.w_fwd = [f16(3, 2 * F, 64)] + [self.w_fwd_trunk[i] for i in range(2 * L)] + [f16(9, 32, F)]
+        self.w_bwd = [None] + [self.w_bwd_trunk[i] for i in range(2 * L)] + [f16(9, F, F)]
+        # biases: the F-channel layers read theirs straight from the flat parameter vector (a view, nothing to copy after an
+        # update); the last layer's is padded to 16
+        self.b_fwd = [self.bias(i) if c == self.F else torch.zeros(max(c, 16), dtype=torch.float32, device=self.dev)
+                      for i, (_, c) in enumerate(shapes)]
         self.gw_head = torch.zeros((9, 128, 128), dtype=torch.float32, device=self.dev)
         self.gw_tail = torch.zeros((9, 128, 128), dtype=torch.float32, device=self.dev)
         self.gb_tail = torch.zeros(128, dtype=torch.float32, device=self.dev)
@@ -171,19 +176,18 @@ class Trainer:
         F, L, nl = self.F, self.L, 2 * self.L + 2
         with self.torch.cuda.device(self.dev):
             _capi.check(lib.dsen2_pack_head_weights(ptr(self.kernel(0)), self.ctot, F, ptr(self.w_fwd[0]), st), "pack head")
-            for i in range(1, nl - 1):
-                _capi.check(lib.dsen2_pack_conv_weights(ptr(self.kernel(i)), F, F, F, F, ptr(self.w_fwd[i]), st),
-                            "pack trunk")
-                # second conv of a resBlock is followed by Lambda(x * 0.1) (DSen2Net.py:13): fold it into the operand
-                scale = 0.1 if i % 2 == 0 else 1.0
-                _capi.check(lib.dsen2_pack_dgrad_weights(ptr(self.kernel(i)), F, F, F, F, scale, ptr(self.w_bwd[i]), st),
-                            "pack dgrad")
+            if L > 0:
+                # the second conv of a resBlock is followed by Lambda(x * 0.1) (DSen2Net.py:13): folded into its
+                # backward operand; consecutive F -> F kernels lie 9*F*F + F floats apart in the flat parameter vector
+                _capi.check(lib.dsen2_pack_trunk_layers(ptr(self.kernel(1)), 9 * F * F + F, 2 * L, F, 0.1,
+                                                        ptr(self.w_fwd_trunk), ptr(self.w_bwd_trunk), st), "pack trunk layers")
             _capi.check(lib.dsen2_pack_tail_weights(ptr(self.kernel(nl - 1)), F, self.cout, ptr(self.w_fwd[-1]), st), "pack tail")
             _capi.check(lib.dsen2_pack_dgrad_weights(ptr(self.kernel(nl - 1)), F, self.cout, F, F, 1.0, ptr(self.w_bwd[-1]), st),
                         "pack dgrad tail")
             for i in range(nl):
                 c = self.model.layer_shapes[i][1]
-                self.b_fwd[i][:c].copy_(self.bias(i))
+                if c != F:
+                    self.b_fwd[i][:c].copy_(self.bias(i))
 
     def _buffers(self, n, P):
         key = (n, P)
@@ -395,4 +399,4 @@ class Trainer:
         L = self.L
         fwd = 1 + 1 + 2 * L + 1
         bwd = 1 + 1 + 3 + L * 6 + 4
-        return fwd + bwd + 1 + (2 * L + 2) * 2
+        return fwd + bwd + 1 + 3 + (1 if L > 0 else 0)        # ... Nadam, first / last layer operand packing, one launch for the trunk

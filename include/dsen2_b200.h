@@ -242,6 +242,13 @@ int dsen2_s2model_forward(const float* const* d_x, const int* channels, int n_in
 int dsen2_pack_dgrad_weights(const float* d_hwio, int cin, int cout, int rows_pad, int k_pad, float scale,
                              void* d_packed, void* stream);
 
+/* All F -> F layers in one launch: layer l's Keras kernel (3,3,F,F) fp32 at d_first_kernel + l * layer_stride (floats; the
+ * flat Keras-order parameter vector puts them 9*F*F + F apart) -> forward operand d_fwd[l] (dsen2_pack_conv_weights layout)
+ * and backward-data operand d_bwd[l] (dsen2_pack_dgrad_weights layout, scale = scale_second for odd l -- the second
+ * convolution of a resBlock, whose Lambda(x * 0.1) is folded in -- and 1 otherwise).                                  */
+int dsen2_pack_trunk_layers(const float* d_first_kernel, long long layer_stride, int num_layers, int feature_size,
+                            float scale_second, void* d_fwd, void* d_bwd, void* stream);
+
 /* d_out = conv3x3(d_in, d_w) * [d_fwd_act > 0]   (NHWC fp16, 128 channels; d_bias must be zeros) */
 int dsen2_conv_relu_bwd(const void* d_in, const void* d_w, const float* d_bias, const void* d_fwd_act,
                         int n, int H, int W, void* d_out, void* stream);

@@ -1,4 +1,4 @@
-"""numpy statement of the fp16 + 8 bit trunk code of include/dsen2_b200.h (dsen2_conv_head_q / dsen2_conv_resq)."""
+"""numpy statement of the fp16 + 8 bit trunk code of include/dsen2_b200.h (dsen2_conv_head16_q / dsen2_conv_resq)."""
 import numpy as np
 
 NORMAL = np.float32(2.0 ** -14)      # below this x_hi is an fp16 subnormal and the code keeps x to an absolute 2^-24 only

@@ -181,8 +181,8 @@ def workload_config(args, cpu=False):
 # ---------------------------------------------------------------------------------------------- #
 # DRAM bytes per patch and launch of the trunk convolutions, dram__bytes_read.sum + dram__bytes_write.sum of an
 # `ncu --set full` capture (a CONSTANT taken from the named file, not measured in the bench run): mean of the RELU layer
-# (617 + 572 MB per 147 patches) and the RESIDUALQ layer (1542 + 875 MB per 147 patches).
-NCU_TRAFFIC = {128: dict(bytes_per_patch=(1.189e9 + 2.417e9) / 2 / 147, source="profiles/r02_whole_batch_xt2_pingpong_ncu_full.txt")}
+# (619 + 571 MB per 147 patches) and the RESIDUALQ layer (1544 + 877 MB per 147 patches).
+NCU_TRAFFIC = {128: dict(bytes_per_patch=(1.190e9 + 2.421e9) / 2 / 147, source="profiles/r02_whole_batch_final_ncu_full.txt")}
 
 
 def run_ours(args):

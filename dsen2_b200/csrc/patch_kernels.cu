@@ -303,7 +303,9 @@ __global__ void bicubic_kernel(const TIn* __restrict__ in, int h, int w, int C, 
 constexpr int kBicTR = 16;                                // output rows per tile (columns and the intermediate extent follow C)
 constexpr int kBicMaxTaps = 8;                            // taps per dimension the tiled path keeps in registers / smem
 
-template <typename TIn, bool FIRST0>
+// TAPS > 0: both dimensions have exactly TAPS taps (4 for every up-scaling factor: imresize.py:35-47 trims the six
+// candidates to the non-zero columns) -- the tap loops are fully unrolled without predicates; TAPS == 0: run-time counts.
+template <typename TIn, bool FIRST0, int TAPS>
 __global__ void __launch_bounds__(256) bicubic_tiled_kernel(const TIn* __restrict__ in, int h, int w, int C,
                                                             const double* __restrict__ wy, const int32_t* __restrict__ iy,
                                                             int ty, int out_h, const double* __restrict__ wx,
@@ -328,6 +330,8 @@ __global__ void __launch_bounds__(256) bicubic_tiled_kernel(const TIn* __restric
     }
     if (hi >= 0) { atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
   }
+  constexpr int NT = TAPS > 0 ? TAPS : kBicMaxTaps;          // unrolled tap-loop length
+  if (TAPS > 0) { ty = TAPS; tx = TAPS; }                        // compile-time counts from here on
   const bool taps_fit = ty <= kBicMaxTaps && tx <= kBicMaxTaps;
   if (taps_fit)
     for (int i = threadIdx.x; i < tr * ty; i += blockDim.x) {
@@ -346,21 +350,23 @@ __global__ void __launch_bounds__(256) bicubic_tiled_kernel(const TIn* __restric
         const int r = i / colc, cc = i - r * colc;
         const TIn* base = in + (long long)lo * C + cc;
         double inter = 0.0;
-        for (int a = 0; a < ty; ++a) {
-          const double pr = __dmul_rn((double)base[s_iy[r * ty + a] * wc], s_wy[r * ty + a]);
-          inter = (a == 0) ? pr : __dadd_rn(inter, pr);
-        }
+#pragma unroll
+        for (int a = 0; a < NT; ++a)
+          if (TAPS > 0 || a < ty) {
+            const double pr = __dmul_rn((double)base[s_iy[r * ty + a] * wc], s_wy[r * ty + a]);
+            inter = (a == 0) ? pr : __dadd_rn(inter, pr);
+          }
         s_inter[i] = inter;
       }
       __syncthreads();
       // pass 2 along x: a thread keeps its (x, c) and the x taps, walks the tile's rows
       for (int xc = threadIdx.x; xc < rowc; xc += blockDim.x) {
         const int x = xc / C, c = xc - x * C;
-        int off[kBicMaxTaps];
-        double wgt[kBicMaxTaps];
+        int off[NT];
+        double wgt[NT];
 #pragma unroll
-        for (int b = 0; b < kBicMaxTaps; ++b)
-          if (b < tx) {
+        for (int b = 0; b < NT; ++b)
+          if (TAPS > 0 || b < tx) {
             off[b] = (ix[(ox0 + x) * tx + b] - lo) * C + c;
             wgt[b] = wx[(ox0 + x) * tx + b];
           }
@@ -368,8 +374,8 @@ __global__ void __launch_bounds__(256) bicubic_tiled_kernel(const TIn* __restric
         for (int r = 0; r < tr; ++r) {
           double acc = 0.0;
 #pragma unroll
-          for (int b = 0; b < kBicMaxTaps; ++b)
-            if (b < tx) {
+          for (int b = 0; b < NT; ++b)
+            if (TAPS > 0 || b < tx) {
               const double pr = __dmul_rn(s_inter[r * colc + off[b]], wgt[b]);
               acc = (b == 0) ? pr : __dadd_rn(acc, pr);
             }
@@ -380,11 +386,11 @@ __global__ void __launch_bounds__(256) bicubic_tiled_kernel(const TIn* __restric
       // pass 1 along x: inter[row][x][c] = sum_b in[lo + row][ix[ox][b]][c] * wx[ox][b]; a thread keeps (x, c) and the x taps
       for (int xc = threadIdx.x; xc < rowc; xc += blockDim.x) {
         const int x = xc / C, c = xc - x * C;
-        int off[kBicMaxTaps];
-        double wgt[kBicMaxTaps];
+        int off[NT];
+        double wgt[NT];
 #pragma unroll
-        for (int b = 0; b < kBicMaxTaps; ++b)
-          if (b < tx) {
+        for (int b = 0; b < NT; ++b)
+          if (TAPS > 0 || b < tx) {
             off[b] = ix[(ox0 + x) * tx + b] * C + c;
             wgt[b] = wx[(ox0 + x) * tx + b];
           }
@@ -392,8 +398,8 @@ __global__ void __launch_bounds__(256) bicubic_tiled_kernel(const TIn* __restric
           const TIn* base = in + (long long)(lo + row) * w * C;
           double inter = 0.0;
 #pragma unroll
-          for (int b = 0; b < kBicMaxTaps; ++b)
-            if (b < tx) {
+          for (int b = 0; b < NT; ++b)
+            if (TAPS > 0 || b < tx) {
               const double pr = __dmul_rn((double)base[off[b]], wgt[b]);
               inter = (b == 0) ? pr : __dadd_rn(inter, pr);
             }
@@ -406,10 +412,12 @@ __global__ void __launch_bounds__(256) bicubic_tiled_kernel(const TIn* __restric
         double* dst = out + ((long long)oy0 * out_w + ox0) * C + xc;
         for (int r = 0; r < tr; ++r) {
           double acc = 0.0;
-          for (int a = 0; a < ty; ++a) {
-            const double pr = __dmul_rn(s_inter[(s_iy[r * ty + a] - lo) * rowc + xc], s_wy[r * ty + a]);
-            acc = (a == 0) ? pr : __dadd_rn(acc, pr);
-          }
+#pragma unroll
+          for (int a = 0; a < NT; ++a)
+            if (TAPS > 0 || a < ty) {
+              const double pr = __dmul_rn(s_inter[(s_iy[r * ty + a] - lo) * rowc + xc], s_wy[r * ty + a]);
+              acc = (a == 0) ? pr : __dadd_rn(acc, pr);
+            }
           dst[(long long)r * out_w * C] = acc;
         }
       }
@@ -641,11 +649,13 @@ extern "C" int dsen2_bicubic_imresize(const void* d_in, int in_is_f64, int h, in
   const long long gy = ((long long)out_h + kBicTR - 1) / kBicTR;
   if (span_cap >= 8 && gy <= 65535 && (long long)out_w * taps_x < (1LL << 29) && (long long)out_h * taps_y < (1LL << 29)) {
     const dim3 tgrid((unsigned)((out_w + tcol - 1) / tcol), (unsigned)gy);
-#define DSEN2_BIC(T, F0)                                                                                           \
-  bicubic_tiled_kernel<T, F0><<<tgrid, 256, inter_bytes, s>>>((const T*)d_in, h, w, C, d_wy, d_iy, taps_y, out_h, \
-                                                              d_wx, d_ix, taps_x, out_w, tcol, span_cap, d_out)
-    if (in_is_f64) { if (first_dim == 0) DSEN2_BIC(double, true); else DSEN2_BIC(double, false); }
-    else           { if (first_dim == 0) DSEN2_BIC(float, true);  else DSEN2_BIC(float, false); }
+#define DSEN2_BIC(T, F0, NTAPS)                                                                                            \
+  bicubic_tiled_kernel<T, F0, NTAPS><<<tgrid, 256, inter_bytes, s>>>((const T*)d_in, h, w, C, d_wy, d_iy, taps_y, out_h, \
+                                                                     d_wx, d_ix, taps_x, out_w, tcol, span_cap, d_out)
+#define DSEN2_BIC2(T, F0) do { if (taps_y == 4 && taps_x == 4) DSEN2_BIC(T, F0, 4); else DSEN2_BIC(T, F0, 0); } while (0)
+    if (in_is_f64) { if (first_dim == 0) DSEN2_BIC2(double, true); else DSEN2_BIC2(double, false); }
+    else           { if (first_dim == 0) DSEN2_BIC2(float, true);  else DSEN2_BIC2(float, false); }
+#undef DSEN2_BIC2
 #undef DSEN2_BIC
     return check_launch("bicubic_imresize");
   }

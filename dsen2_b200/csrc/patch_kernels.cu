@@ -346,17 +346,26 @@ __global__ void __launch_bounds__(256) bicubic_tiled_kernel(const TIn* __restric
       // pass 1 along y: inter[r][col][c] = sum_a in[iy[oy][a]][lo + col][c] * wy[oy][a]; a thread keeps its (col, c)
       const int colc = span * C;
       const long long wc = (long long)w * C;
-      for (int i = threadIdx.x; i < tr * colc; i += blockDim.x) {
-        const int r = i / colc, cc = i - r * colc;
-        const TIn* base = in + (long long)lo * C + cc;
-        double inter = 0.0;
+      {
+        // flattened over (row, column-channel) so that all threads stay busy; (r, cc) advance incrementally -- a division
+        // by the run-time extent per item was a fifth of this issue-bound kernel's instructions
+        int r = threadIdx.x / colc, cc = threadIdx.x - r * colc;
+        const int dr = blockDim.x / colc, dc = blockDim.x - dr * colc;
+        const TIn* base0 = in + (long long)lo * C;
+        for (int i = threadIdx.x; i < tr * colc; i += blockDim.x) {
+          const TIn* base = base0 + cc;
+          double inter = 0.0;
 #pragma unroll
-        for (int a = 0; a < NT; ++a)
-          if (TAPS > 0 || a < ty) {
-            const double pr = __dmul_rn((double)base[s_iy[r * ty + a] * wc], s_wy[r * ty + a]);
-            inter = (a == 0) ? pr : __dadd_rn(inter, pr);
-          }
-        s_inter[i] = inter;
+          for (int a = 0; a < NT; ++a)
+            if (TAPS > 0 || a < ty) {
+              const double pr = __dmul_rn((double)base[s_iy[r * ty + a] * wc], s_wy[r * ty + a]);
+              inter = (a == 0) ? pr : __dadd_rn(inter, pr);
+            }
+          s_inter[i] = inter;
+          r += dr;
+          cc += dc;
+          if (cc >= colc) { cc -= colc; ++r; }
+        }
       }
       __syncthreads();
       // pass 2 along x: a thread keeps its (x, c) and the x taps, walks the tile's rows
@@ -649,8 +658,11 @@ extern "C" int dsen2_bicubic_imresize(const void* d_in, int in_is_f64, int h, in
   const long long gy = ((long long)out_h + kBicTR - 1) / kBicTR;
   if (span_cap >= 8 && gy <= 65535 && (long long)out_w * taps_x < (1LL << 29) && (long long)out_h * taps_y < (1LL << 29)) {
     const dim3 tgrid((unsigned)((out_w + tcol - 1) / tcol), (unsigned)gy);
+    // a thread owns one (x, c) pair of the tile row in the second pass: 64 x 6 = 384 pairs are two rounds of 192 threads
+    // (a third of the threads would idle in the second round of 256)
+    const int bthreads = (tcol * C) % 256 != 0 && (tcol * C) % 192 == 0 ? 192 : 256;
 #define DSEN2_BIC(T, F0, NTAPS)                                                                                            \
-  bicubic_tiled_kernel<T, F0, NTAPS><<<tgrid, 256, inter_bytes, s>>>((const T*)d_in, h, w, C, d_wy, d_iy, taps_y, out_h, \
+  bicubic_tiled_kernel<T, F0, NTAPS><<<tgrid, bthreads, inter_bytes, s>>>((const T*)d_in, h, w, C, d_wy, d_iy, taps_y, out_h, \
                                                                      d_wx, d_ix, taps_x, out_w, tcol, span_cap, d_out)
 #define DSEN2_BIC2(T, F0) do { if (taps_y == 4 && taps_x == 4) DSEN2_BIC(T, F0, 4); else DSEN2_BIC(T, F0, 0); } while (0)
     if (in_is_f64) { if (first_dim == 0) DSEN2_BIC2(double, true); else DSEN2_BIC2(double, false); }

@@ -52,7 +52,6 @@ SIGNATURES = {
                                    c_void_p, c_void_p]),
     "dsen2_conv_tail": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                 c_int, c_void_p, c_void_p]),
-    "dsen2_debug_divconst_mismatches": (c_int, [c_float, c_void_p, c_void_p]),
     "dsen2_pack_dgrad_weights": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "dsen2_pack_trunk_layers": (c_int, [c_void_p, c_longlong, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "dsen2_conv_relu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),

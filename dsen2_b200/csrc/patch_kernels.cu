@@ -22,7 +22,7 @@ void set_error(const char* fmt, ...) {
 // ------------------------------------------------------------------------------------------ //
 template <int C>
 __global__ void extract_patches_kernel(const float* __restrict__ img, int H, int W, int ratio, int p, int b,
-                                       Tiling tl, int first_patch, long long total, DivC divisor,
+                                       Tiling tl, int first_patch, long long total, float divisor,
                                        float* __restrict__ out) {
   const long long pp = (long long)p * p;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -58,12 +58,12 @@ __global__ void extract_patches_kernel(const float* __restrict__ img, int H, int
     }
     float* dst = out + (long long)local * C * pp + rem;
 #pragma unroll
-    for (int c = 0; c < C; ++c) dst[c * pp] = (divisor.c == 1.0f) ? v[c] : div_c(v[c], divisor);
+    for (int c = 0; c < C; ++c) dst[c * pp] = (divisor == 1.0f) ? v[c] : __fdiv_rn(v[c], divisor);
   }
 }
 
 __global__ void extract_patches_generic_kernel(const float* __restrict__ img, int H, int W, int C, int ratio, int p,
-                                               int b, Tiling tl, int first_patch, long long total, DivC divisor,
+                                               int b, Tiling tl, int first_patch, long long total, float divisor,
                                                float* __restrict__ out) {
   const long long pp = (long long)p * p;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -80,7 +80,7 @@ __global__ void extract_patches_generic_kernel(const float* __restrict__ img, in
       const float* src = img + ((long long)sym_index(si + y - b, H) * W + sym_index(sj + x - b, W)) * C;
       for (int c = 0; c < C; ++c) {
         const float v = __ldg(src + c);
-        dst[c * pp] = (divisor.c == 1.0f) ? v : div_c(v, divisor);
+        dst[c * pp] = (divisor == 1.0f) ? v : __fdiv_rn(v, divisor);
       }
     } else {
       for (int c = 0; c < C; ++c) dst[c * pp] = 0.f;
@@ -91,7 +91,7 @@ __global__ void extract_patches_generic_kernel(const float* __restrict__ img, in
 // ------------------------------------------------------------------------------------------ //
 // bilinear, mirror boundary, integer scale s (patches.py:11-16): u = (o + .5)/s - .5
 // ------------------------------------------------------------------------------------------ //
-__global__ void bilinear_mirror_kernel(const float* __restrict__ in, int p, int s, long long total, DivC post_div,
+__global__ void bilinear_mirror_kernel(const float* __restrict__ in, int p, int s, long long total, float post_div,
                                        float* __restrict__ out) {
   const int P = p * s;
   const long long PP = (long long)P * P;
@@ -106,13 +106,12 @@ __global__ void bilinear_mirror_kernel(const float* __restrict__ in, int p, int 
     bilin_tap(ox, s, p, x0, x1, fx);
     const float* src = in + plane * (long long)p * p;
     const float k = 30000.0f;                // the reference scales by 1/30000 around the resize
-    const DivC dk = {k, 1.0f / k, 1};
-    const float v00 = div_c(__ldg(src + y0 * p + x0), dk), v01 = div_c(__ldg(src + y0 * p + x1), dk);
-    const float v10 = div_c(__ldg(src + y1 * p + x0), dk), v11 = div_c(__ldg(src + y1 * p + x1), dk);
+    const float v00 = __fdiv_rn(__ldg(src + y0 * p + x0), k), v01 = __fdiv_rn(__ldg(src + y0 * p + x1), k);
+    const float v10 = __fdiv_rn(__ldg(src + y1 * p + x0), k), v11 = __fdiv_rn(__ldg(src + y1 * p + x1), k);
     const float c0 = v00 * (1.0f - fy) + v10 * fy;   // rows first, then columns (as the oracle)
     const float c1 = v01 * (1.0f - fy) + v11 * fy;
     const float r = (c0 * (1.0f - fx) + c1 * fx) * k;
-    out[idx] = (post_div.c == 1.0f) ? r : div_c(r, post_div);
+    out[idx] = (post_div == 1.0f) ? r : __fdiv_rn(r, post_div);
   }
 }
 
@@ -141,18 +140,17 @@ __device__ __forceinline__ void bilin_split(int o, int s, int& i0, float& f) {
 
 template <int SC>
 __global__ void __launch_bounds__(kBilThreads) bilinear_mirror_band_kernel(const float* __restrict__ in, int p, int s, int bands,
-                                                                          DivC post_div, float* __restrict__ out) {
+                                                                          float post_div, float* __restrict__ out) {
   extern __shared__ float s_src[];                         // [kBilRows + 2][p + 2], value / 30000
   const int plane = blockIdx.x / bands, band = blockIdx.x - plane * bands;
   const int r0 = band * kBilRows, rows = min(kBilRows, p - r0);
   const int pitch = p + 2, P = p * s;
   const float k = 30000.0f;                                // the reference scales by 1/30000 around the resize
-  const DivC dk = {k, 1.0f / k, 1};
   const float* src = in + (long long)plane * p * p;
   for (int lr = threadIdx.y; lr < rows + 2; lr += blockDim.y) {
     const float* srow = src + mirror_index(r0 - 1 + lr, p) * p;
     for (int lc = threadIdx.x; lc < pitch; lc += blockDim.x)
-      s_src[lr * pitch + lc] = div_c(__ldg(srow + mirror_index(lc - 1, p)), dk);
+      s_src[lr * pitch + lc] = __fdiv_rn(__ldg(srow + mirror_index(lc - 1, p)), k);
   }
   // x taps of this thread's four output columns: local column of the left tap and the fraction
   int xl[4];
@@ -179,7 +177,7 @@ __global__ void __launch_bounds__(kBilThreads) bilinear_mirror_band_kernel(const
       const float c0 = v00 * (1.0f - fy) + v10 * fy;   // rows first, then columns (as the oracle)
       const float c1 = v01 * (1.0f - fy) + v11 * fy;
       const float v = (c0 * (1.0f - fx[j]) + c1 * fx[j]) * k;
-      r[j] = (post_div.c == 1.0f) ? v : div_c(v, post_div);
+      r[j] = (post_div == 1.0f) ? v : __fdiv_rn(v, post_div);
     }
     *reinterpret_cast<float4*>(dst + (long long)oy * P) = make_float4(r[0], r[1], r[2], r[3]);
   }
@@ -531,32 +529,6 @@ __global__ void pack_weights_kernel(const float* __restrict__ hwio, int cin, int
   }
 }
 
-// every bit pattern of x: div_c(x, c) against __fdiv_rn(x, c); out[0] = mismatches, out[1] = patterns checked,
-// out[2] / out[3] = smallest / largest |x| bit pattern that disagrees (initialise to ~0 / 0)
-__global__ void divconst_check_kernel(DivC d, unsigned long long* __restrict__ out) {
-  unsigned long long bad = 0, seen = 0;
-  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < (1ULL << 32);
-       i += (unsigned long long)gridDim.x * blockDim.x) {
-    const float x = __uint_as_float((unsigned)i);
-    const float a = div_c(x, d), b = __fdiv_rn(x, d.c);
-    const bool both_nan = (a != a) && (b != b);
-    if (!both_nan && __float_as_uint(a) != __float_as_uint(b)) {
-      ++bad;
-      atomicMin(out + 2, (unsigned long long)((unsigned)i & 0x7fffffffu));     // smallest / largest |x| that disagrees
-      atomicMax(out + 3, (unsigned long long)((unsigned)i & 0x7fffffffu));
-    }
-    ++seen;
-  }
-  for (int o = 16; o > 0; o >>= 1) {
-    bad += __shfl_xor_sync(0xffffffffu, bad, o);
-    seen += __shfl_xor_sync(0xffffffffu, seen, o);
-  }
-  if ((threadIdx.x & 31) == 0) {
-    atomicAdd(out, bad);
-    atomicAdd(out + 1, seen);
-  }
-}
-
 }  // namespace dsen2
 
 // ============================================================================================ //
@@ -599,13 +571,13 @@ extern "C" int dsen2_extract_patches(const float* d_img, int grid_h, int grid_w,
   cudaStream_t s = (cudaStream_t)stream;
   const bool aligned = ((uintptr_t)d_img % 16) == 0;
   if (C == 4 && aligned)
-    extract_patches_kernel<4><<<grid, block, 0, s>>>(d_img, H, W, ratio, p, b, tl, first_patch, total, make_divc(divisor), d_out);
+    extract_patches_kernel<4><<<grid, block, 0, s>>>(d_img, H, W, ratio, p, b, tl, first_patch, total, divisor, d_out);
   else if (C == 6 && aligned)
-    extract_patches_kernel<6><<<grid, block, 0, s>>>(d_img, H, W, ratio, p, b, tl, first_patch, total, make_divc(divisor), d_out);
+    extract_patches_kernel<6><<<grid, block, 0, s>>>(d_img, H, W, ratio, p, b, tl, first_patch, total, divisor, d_out);
   else if (C == 2 && aligned)
-    extract_patches_kernel<2><<<grid, block, 0, s>>>(d_img, H, W, ratio, p, b, tl, first_patch, total, make_divc(divisor), d_out);
+    extract_patches_kernel<2><<<grid, block, 0, s>>>(d_img, H, W, ratio, p, b, tl, first_patch, total, divisor, d_out);
   else
-    extract_patches_generic_kernel<<<grid, block, 0, s>>>(d_img, H, W, C, ratio, p, b, tl, first_patch, total, make_divc(divisor),
+    extract_patches_generic_kernel<<<grid, block, 0, s>>>(d_img, H, W, C, ratio, p, b, tl, first_patch, total, divisor,
                                                           d_out);
   return check_launch("extract_patches");
 }
@@ -625,15 +597,15 @@ extern "C" int dsen2_bilinear_mirror_up(const float* d_in, int planes, int p, in
     const int tx = P / 4, ty = kBilThreads / tx > 0 ? kBilThreads / tx : 1;
     const dim3 grid((unsigned)(planes * bands)), block(tx, ty);
     if (s == 2)
-      bilinear_mirror_band_kernel<2><<<grid, block, band_smem, (cudaStream_t)stream>>>(d_in, p, s, bands, make_divc(post_divisor), d_out);
+      bilinear_mirror_band_kernel<2><<<grid, block, band_smem, (cudaStream_t)stream>>>(d_in, p, s, bands, post_divisor, d_out);
     else if (s == 6)
-      bilinear_mirror_band_kernel<6><<<grid, block, band_smem, (cudaStream_t)stream>>>(d_in, p, s, bands, make_divc(post_divisor), d_out);
+      bilinear_mirror_band_kernel<6><<<grid, block, band_smem, (cudaStream_t)stream>>>(d_in, p, s, bands, post_divisor, d_out);
     else
-      bilinear_mirror_band_kernel<0><<<grid, block, band_smem, (cudaStream_t)stream>>>(d_in, p, s, bands, make_divc(post_divisor), d_out);
+      bilinear_mirror_band_kernel<0><<<grid, block, band_smem, (cudaStream_t)stream>>>(d_in, p, s, bands, post_divisor, d_out);
     return check_launch("bilinear_mirror_up");
   }
   const int block = 256;
-  bilinear_mirror_kernel<<<grid_for(total, block), block, 0, (cudaStream_t)stream>>>(d_in, p, s, total, make_divc(post_divisor),
+  bilinear_mirror_kernel<<<grid_for(total, block), block, 0, (cudaStream_t)stream>>>(d_in, p, s, total, post_divisor,
                                                                                      d_out);
   return check_launch("bilinear_mirror_up");
 }
@@ -737,12 +709,4 @@ extern "C" int dsen2_pack_conv_weights(const float* d_hwio, int cin, int cout, i
   pack_weights_kernel<<<grid_for(total, block), block, 0, (cudaStream_t)stream>>>(d_hwio, cin, cout, cin_pad, cout_pad, total,
                                                                                   (__half*)d_packed_f16);
   return check_launch("pack_conv_weights");
-}
-
-/* self-test hook: compares the reciprocal-FMA division by the constant c (csrc/tiling.cuh, div_c) with __fdiv_rn for ALL
- * 2^32 bit patterns of the dividend; d_out[0] += mismatches, d_out[1] += patterns checked (zero them first). */
-extern "C" int dsen2_debug_divconst_mismatches(float c, unsigned long long* d_out, void* stream) {
-  DSEN2_REQUIRE(d_out && c != 0.f, DSEN2_E_BADARG, "dsen2_debug_divconst_mismatches: bad arguments");
-  divconst_check_kernel<<<sm_count() * 16, 256, 0, (cudaStream_t)stream>>>(make_divc(c), d_out);
-  return check_launch("divconst_check");
 }

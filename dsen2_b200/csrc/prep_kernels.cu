@@ -49,14 +49,14 @@ __device__ __forceinline__ float ld_px(const uint16_t* p) { return (float)__ldg(
 // value of band c of `src` at 10 m patch pixel (y, x): crop + symmetric pad (+ mirror bilinear) + /divisor
 template <typename T, int C, int OFF>
 __device__ __forceinline__ void prep_gather(const PrepSource& src, int si, int sj, int plr, int blr, int y, int x,
-                                            const DivC& divisor, float (&v)[16]) {
+                                            float divisor, float (&v)[16]) {
   const T* img = reinterpret_cast<const T*>(src.img);
   const int p = plr * src.ratio, b = blr * src.ratio;
   const int oi = si * src.ratio - b, oj = sj * src.ratio - b;
   if (src.s == 1) {
     const T* q = img + ((long long)sym_index(oi + y, src.H) * src.W + sym_index(oj + x, src.W)) * C;
 #pragma unroll
-    for (int c = 0; c < C; ++c) v[OFF + c] = div_c(ld_px(q + c), divisor);
+    for (int c = 0; c < C; ++c) v[OFF + c] = __fdiv_rn(ld_px(q + c), divisor);
     return;
   }
   int y0, y1, x0, x1;
@@ -70,15 +70,14 @@ __device__ __forceinline__ void prep_gather(const PrepSource& src, int si, int s
   const T* p10 = img + (r1 + q0) * C;
   const T* p11 = img + (r1 + q1) * C;
   const float k = 30000.0f;                  // the reference scales by 1/30000 around the resize (patches.py:15)
-  const DivC dk = {k, 1.0f / k, 1};
 #pragma unroll
   for (int c = 0; c < C; ++c) {
-    const float v00 = div_c(ld_px(p00 + c), dk), v01 = div_c(ld_px(p01 + c), dk);
-    const float v10 = div_c(ld_px(p10 + c), dk), v11 = div_c(ld_px(p11 + c), dk);
+    const float v00 = __fdiv_rn(ld_px(p00 + c), k), v01 = __fdiv_rn(ld_px(p01 + c), k);
+    const float v10 = __fdiv_rn(ld_px(p10 + c), k), v11 = __fdiv_rn(ld_px(p11 + c), k);
     const float c0 = v00 * (1.0f - fy) + v10 * fy;   // rows first, then columns (as bilinear_mirror_kernel)
     const float c1 = v01 * (1.0f - fy) + v11 * fy;
     const float r = (c0 * (1.0f - fx) + c1 * fx) * k;
-    v[OFF + c] = div_c(r, divisor);
+    v[OFF + c] = __fdiv_rn(r, divisor);
   }
 }
 
@@ -112,7 +111,7 @@ __global__ void prep16_from_patches_kernel(const float* __restrict__ x0, int c0,
 
 template <typename T>
 __global__ void prep16_from_images_kernel(PrepSource s0, PrepSource s1, PrepSource s2, int nsrc, int plr, int blr, int P,
-                                          Tiling tl, int first_patch, long long total, DivC divisor,
+                                          Tiling tl, int first_patch, long long total, float divisor,
                                           __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
   const int PP = P * P;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -356,10 +355,10 @@ extern "C" int dsen2_prep16_from_images(const void* d_img10, const void* d_img20
   const int block = 256;
   if (img_dtype == DSEN2_IMG_U16)
     prep16_from_images_kernel<uint16_t><<<grid_for(total, block), block, 0, (cudaStream_t)stream>>>(
-        s0, s1, s2, d_img60 ? 3 : 2, plr, blr, patch, tl, first_patch, total, make_divc(divisor), (__half*)d_xin_hi, (__half*)d_xin_lo);
+        s0, s1, s2, d_img60 ? 3 : 2, plr, blr, patch, tl, first_patch, total, divisor, (__half*)d_xin_hi, (__half*)d_xin_lo);
   else
     prep16_from_images_kernel<float><<<grid_for(total, block), block, 0, (cudaStream_t)stream>>>(
-        s0, s1, s2, d_img60 ? 3 : 2, plr, blr, patch, tl, first_patch, total, make_divc(divisor), (__half*)d_xin_hi, (__half*)d_xin_lo);
+        s0, s1, s2, d_img60 ? 3 : 2, plr, blr, patch, tl, first_patch, total, divisor, (__half*)d_xin_hi, (__half*)d_xin_lo);
   return check_launch("prep16_from_images");
 }
 

@@ -44,41 +44,6 @@ __host__ __device__ inline Tiling make_tiling(int grid_h, int grid_w, int patch_
   return t;
 }
 
-// ------------------------------------------------------------------------------------------ //
-// IEEE division by the two constants of the path -- SCALE = 2000 (supres.py:11,23-24) and the 30000 of interp_patches
-// (patches.py:15) -- without the division sequence (MUFU.RCP + 4 FFMA + FCHK + slow-path branch, ~10 issue slots each;
-// the preparation kernel does 34 of them per pixel).  With rc = RN(1 / c):
-//     q0 = RN(x * rc);   r = x - c * q0  (exact in one FMA);   q = RN(q0 + r * rc)
-// is the correctly rounded quotient for every x whose quotient is a normal number; that is verified EXHAUSTIVELY, all 2^32
-// bit patterns of x against __fdiv_rn, for exactly these two constants (dsen2_debug_divconst_mismatches,
-// tests/test_gpu_patches.py) -- any other divisor takes __fdiv_rn.  Outside [kDivLo, kDivHi] (quotients that are denormal,
-// or x so large that c * q0 overflows) the slow path is kept.
-// ------------------------------------------------------------------------------------------ //
-struct DivC {
-  float c, rc;
-  int fast;
-};
-static constexpr float kDivLo = 1e-30f, kDivHi = 1e30f;
-inline DivC make_divc(float c) {
-  DivC d;
-  d.c = c;
-  d.rc = 1.0f / c;
-  d.fast = (c == 2000.0f || c == 30000.0f) ? 1 : 0;
-  return d;
-}
-#ifdef __CUDACC__
-__device__ __forceinline__ float div_fast(float x, float c, float rc) {
-  const float q0 = x * rc;
-  const float r = fmaf(-c, q0, x);
-  return fmaf(r, rc, q0);
-}
-__device__ __forceinline__ float div_c(float x, const DivC& d) {
-  const float ax = fabsf(x);
-  if (d.fast && ax >= kDivLo && ax <= kDivHi) return div_fast(x, d.c, d.rc);
-  return __fdiv_rn(x, d.c);          // zeros (the FMA pair would turn -0 into +0), denormal quotients, huge x, other divisors
-}
-#endif
-
 __device__ __forceinline__ int sym_index(int j, int n) {  // numpy pad(mode='symmetric')
   if (j < 0) j = -j - 1;
   if (j >= n) j = 2 * n - 1 - j;

@@ -279,11 +279,6 @@ int dsen2_nadam_step(float* d_p, const float* d_g, float* d_m, float* d_v, long 
 int dsen2_nadam_step_dev(float* d_p, const float* d_g, float* d_m, float* d_v, long long total,
                          const float* d_hp, void* stream);
 
-/* Self-test hook (tests only): the kernels divide by SCALE = 2000 and by the 30000 of interp_patches through a correctly
- * rounded reciprocal and two FMAs; this compares that with IEEE division for ALL 2^32 bit patterns of the dividend.
- * d_out[0] += mismatches, d_out[1] += patterns checked (zero both first).                                         */
-int dsen2_debug_divconst_mismatches(float c, unsigned long long* d_out, void* stream);
-
 #ifdef __cplusplus
 }
 #endif

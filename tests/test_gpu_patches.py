@@ -195,17 +195,3 @@ def test_training_patch_writers(mods, tmp_path):
     r10, r20 = po.get_test_patches(d10, d20, 32, 4)
     assert np.array_equal(t10, r10)
     np.testing.assert_allclose(t20, r20, rtol=0, atol=2e-3)
-
-
-@pytest.mark.parametrize('c', [2000.0, 30000.0, 3.0])
-def test_division_by_the_path_constants_is_ieee_for_every_float(c):
-    """The kernels divide by SCALE = 2000 and by interp_patches' 30000 through RN(1/c) and two FMAs (csrc/tiling.cuh);
-    bit-exact parity with the reference's numpy division rests on this being the IEEE quotient: all 2^32 bit patterns of
-    the dividend against __fdiv_rn.  (3.0 is not a verified constant: it must take the IEEE path and trivially agree.)"""
-    import torch
-    from dsen2_b200 import _capi
-    out = torch.tensor([0, 0, 1 << 62, 0], dtype=torch.int64, device='cuda')
-    _capi.check(_capi.lib().dsen2_debug_divconst_mismatches(c, _capi.ptr(out), _capi.stream_ptr()), 'divconst')
-    torch.cuda.synchronize()
-    bad, seen, lo, hi = [int(v) for v in out.cpu()]
-    assert seen == 1 << 32 and bad == 0, (bad, seen, hex(lo), hex(hi))

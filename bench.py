@@ -475,6 +475,10 @@ def run_train(args):
                              "achieved": flop / ms / 1e9, "peak": pk['tf_burst'], "unit": "TFLOP/s",
                              "frac": flop / ms / 1e9 / pk['tf_burst'], "traffic": None,
                              "peak_source": pk['source'] + ", burst figure (millisecond-scale step)"},
+                "kernel_shares_ncu": {"note": "CONSTANTS from an ncu gpu__time_duration launch list of this workload (profiles/"
+                                      "r02_train_launch_list.txt), not measured in this run",
+                                      "forward + backward-data convolutions (conv_pair_kernel)": 0.53, "weight gradients (wgrad_direct_kernel)": 0.26,
+                                      "bias gradients (colsum_nhwc_kernel)": 0.086, "operand repacking": 0.064, "loss, Nadam, layout, fills": 0.06},
                 "allreduce": {"us": allreduce_us, "bytes": int(tr.grads.numel()) * 4, "algo": "NCCL all_reduce(SUM), one bucket, "
                               "between the gradient graph and the update graph"} if world > 1 else None,
                 "last_loss": losses[-1] if losses else None}

@@ -107,18 +107,84 @@ class S2Model:
                              % (len(arrays), 2 * len(self.layer_shapes)))
         self.set_weights(arrays)
 
-    def save_weights(self, filepath):
-        """Write a Keras-2-style weight file (layer_names / weight_names attributes, kernel:0 / bias:0)."""
+    def _weights_tree(self, prefix=''):
+        """(tree, attrs) of the Keras-2 weight layout: one group per layer, layer_names / weight_names attributes."""
         self._pull_trained_weights()
         tree, attrs, names = {}, {}, []
         for i, (k, b) in enumerate(self._weights):
             n = 'conv2d_%d' % (i + 1)
             names.append(n.encode())
             tree[n] = {n: {'kernel:0': k, 'bias:0': b}}
-            attrs['/' + n] = {'weight_names': np.array([('%s/kernel:0' % n).encode(), ('%s/bias:0' % n).encode()])}
-        attrs['/'] = {'layer_names': np.array(names), 'backend': np.bytes_(b'dsen2_b200'),
-                      'keras_version': np.bytes_(b'2.2.4')}
+            attrs[prefix + '/' + n] = {'weight_names': np.array([('%s/kernel:0' % n).encode(), ('%s/bias:0' % n).encode()])}
+        attrs[prefix or '/'] = {'layer_names': np.array(names), 'backend': np.bytes_(b'dsen2_b200'),
+                                'keras_version': np.bytes_(b'2.2.4')}
+        return tree, attrs
+
+    def save_weights(self, filepath):
+        """Write a Keras-2-style weight file (layer_names / weight_names attributes, kernel:0 / bias:0)."""
+        tree, attrs = self._weights_tree()
         write_hdf5(filepath, tree, attrs)
+
+    def save(self, filepath):
+        """``model.save(filepath)`` -- what ``ModelCheckpoint(save_weights_only=False)`` writes (supres_train.py:195-201):
+        the Keras-2 full-model layout, ``/model_weights`` (as ``save_weights``), ``/optimizer_weights`` (Nadam: iterations,
+        first moments, second moments -- Keras' ``optimizer.weights`` order) and the ``model_config`` / ``training_config``
+        attributes.  ``load_weights`` reads the file back; ``load_optimizer_weights`` restores the optimizer."""
+        import json
+        wtree, attrs = self._weights_tree('/model_weights')
+        tree = {'model_weights': wtree}
+        root = {'keras_version': np.bytes_(b'2.2.4'), 'backend': np.bytes_(b'dsen2_b200'),
+                'model_config': np.bytes_(json.dumps({'class_name': 'Model', 'config': {
+                    'name': 's2model', 'input_shape': [[c, None, None] for c in self.in_channels],
+                    'num_layers': self.num_layers, 'feature_size': self.feature_size}}).encode())}
+        tr = self._trainer
+        if tr is not None:
+            o = tr.opt
+            root['training_config'] = np.bytes_(json.dumps({
+                'optimizer_config': {'class_name': 'Nadam', 'config': {'lr': o.lr, 'beta_1': o.beta_1, 'beta_2': o.beta_2,
+                                                                       'epsilon': o.epsilon, 'schedule_decay': o.schedule_decay}},
+                'loss': 'mean_absolute_error', 'metrics': ['mean_squared_error']}).encode())
+            m, v = tr.m.cpu().numpy(), tr.v.cpu().numpy()
+            opt, names = {'Nadam': {'iterations:0': np.array(tr.iterations, np.int64)}}, [b'Nadam/iterations:0']
+            grp = {}
+            for kind, flat in (('m', m), ('v', v)):
+                for i in range(2 * len(self.layer_shapes)):
+                    name = '%s_%d:0' % (kind, i)
+                    grp[name] = flat[int(tr.offsets[i]):int(tr.offsets[i + 1])].copy()
+                    names.append(('training/Nadam/' + name).encode())
+            opt['training'] = {'Nadam': grp}
+            tree['optimizer_weights'] = opt
+            # Keras does not store Nadam's running product of the momentum schedule; kept here so that a resume is exact
+            attrs['/optimizer_weights'] = {'weight_names': np.array(names), 'm_schedule': np.array(tr.m_schedule, np.float64)}
+        attrs['/'] = root
+        write_hdf5(filepath, tree, attrs)
+
+    def load_optimizer_weights(self, filepath):
+        """Restore the Nadam state a ``save()`` file carries (after ``compile``); returns False if the file has none."""
+        if self._trainer is None:
+            raise RuntimeError("You must compile a model before restoring its optimizer state.")
+        f = File(filepath)
+        if 'optimizer_weights' not in f.keys():
+            return False
+        g = f['optimizer_weights']
+        tr, torch = self._trainer, _capi.require_cuda()
+        flat = {}
+        for kind in ('m', 'v'):
+            parts = [np.asarray(g['training/Nadam/%s_%d:0' % (kind, i)][()], np.float32).ravel()
+                     for i in range(2 * len(self.layer_shapes))]
+            flat[kind] = np.concatenate(parts)
+        tr.m.copy_(torch.from_numpy(flat['m']).to(tr.dev))
+        tr.v.copy_(torch.from_numpy(flat['v']).to(tr.dev))
+        tr.iterations = int(np.asarray(g['Nadam/iterations:0'][()]))
+        ms = g.attrs['m_schedule'] if 'm_schedule' in g.attrs else None
+        if ms is None:                       # a file written by Keras: rebuild the product from the schedule
+            from .train import nadam_schedule
+            prod = 1.0
+            for t in range(1, tr.iterations + 1):
+                prod = nadam_schedule(t, prod, tr.opt)['sched_new']
+            ms = prod
+        tr.m_schedule = float(np.asarray(ms))
+        return True
 
     # ---- device side ------------------------------------------------------------------- #
     @property

@@ -20,15 +20,16 @@ class Callback:
 class ModelCheckpoint(Callback):
     def __init__(self, filepath, monitor='val_loss', verbose=0, save_best_only=False, save_weights_only=False, mode='auto'):
         self.filepath, self.monitor, self.verbose, self.save_best_only = filepath, monitor, verbose, save_best_only
-        self.save_weights_only = save_weights_only          # the writer stores the weights either way (Keras layout)
+        self.save_weights_only = save_weights_only          # False: model.save (weights + optimizer state, Keras full-model layout)
         self.maximize = mode == 'max' or (mode == 'auto' and ('acc' in monitor or monitor.startswith('fmeasure')))
         self.best = -np.inf if self.maximize else np.inf
 
     def on_epoch_end(self, epoch, logs=None):
         logs = logs or {}
         path = self.filepath.format(epoch=epoch + 1, **logs)
+        write = self.model.save_weights if self.save_weights_only or not hasattr(self.model, 'save') else self.model.save
         if not self.save_best_only:
-            self.model.save_weights(path)
+            write(path)
             return
         cur = logs.get(self.monitor)
         if cur is None:
@@ -37,7 +38,7 @@ class ModelCheckpoint(Callback):
             if self.verbose:
                 print('\nEpoch %05d: %s improved from %0.5f to %0.5f, saving model to %s' % (epoch + 1, self.monitor, self.best, cur, path))
             self.best = cur
-            self.model.save_weights(path)
+            write(path)
 
 
 class ReduceLROnPlateau(Callback):

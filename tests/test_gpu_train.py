@@ -295,3 +295,55 @@ def test_back_to_back_graph_steps_use_their_own_nadam_scalars(env):
         outs.append(tr.params.cpu().numpy())
     d = np.abs(outs[0] - outs[1]) / (1e-3 * 12)
     assert np.median(d) < 1e-3 and np.mean(d > 0.25) < 0.01     # fp32 atomics in the weight gradients: last-bit noise only
+
+
+def test_full_model_checkpoint_resumes_training(env, tmp_path):
+    """model.save (ModelCheckpoint(save_weights_only=False), supres_train.py:195-201) carries the Nadam state: a model rebuilt
+    from the file continues exactly like the one that kept training."""
+    torch, _capi, lib = env
+    from dsen2_b200.DSen2Net import s2model
+    from dsen2_b200.hdf5 import File
+    from dsen2_b200.train import Nadam
+    model, ws, xs, y = _setup(L=1, n=4, P=32)
+    model.compile(optimizer=Nadam(lr=1e-3), loss='mean_absolute_error', metrics=['mean_squared_error'])
+    for _ in range(5):
+        model.train_on_batch(xs, y)
+    ck = str(tmp_path / 'full.hdf5')
+    model.save(ck)
+    f = File(ck)
+    assert sorted(f.keys()) == ['model_weights', 'optimizer_weights']
+    names = [bytes(n).decode() for n in f['optimizer_weights'].attrs['weight_names']]
+    assert names[0] == 'Nadam/iterations:0' and len(names) == 1 + 2 * 2 * len(model.layer_shapes)
+    assert int(np.asarray(f['optimizer_weights/Nadam/iterations:0'][()])) == 5
+    k0 = model.get_weights()[0]
+    assert f['optimizer_weights/training/Nadam/m_0:0'].shape == (k0.size,)
+    for _ in range(4):
+        model.train_on_batch(xs, y)
+    want = np.concatenate([a.ravel() for a in model.get_weights()])
+
+    again = s2model(((4, None, None), (6, None, None)), num_layers=1, feature_size=128, seed=99)
+    again.compile(optimizer=Nadam(lr=1e-3), loss='mean_absolute_error', metrics=['mean_squared_error'])
+    again.load_weights(ck)
+    assert again.load_optimizer_weights(ck)
+    assert again._trainer.iterations == 5 and again._trainer.m_schedule == pytest.approx(model_schedule(5))
+    for _ in range(4):
+        again.train_on_batch(xs, y)
+    got = np.concatenate([a.ravel() for a in again.get_weights()])
+    d = np.abs(got - want) / (1e-3 * 4)
+    assert np.median(d) < 1e-3 and np.mean(d > 0.25) < 0.01     # fp32 atomics in the weight gradients: last-bit noise only
+
+    cold = s2model(((4, None, None), (6, None, None)), num_layers=1, feature_size=128, seed=99)
+    cold.compile(optimizer=Nadam(lr=1e-3), loss='mean_absolute_error', metrics=['mean_squared_error'])
+    cold.load_weights(ck)                                       # weights only: the moments restart from zero
+    for _ in range(4):
+        cold.train_on_batch(xs, y)
+    dc = np.abs(np.concatenate([a.ravel() for a in cold.get_weights()]) - want) / (1e-3 * 4)
+    assert np.mean(dc > 0.25) > 0.2                             # ...which is visibly a different trajectory
+
+
+def model_schedule(t, opt=None):
+    from dsen2_b200.train import Nadam, nadam_schedule
+    prod, opt = 1.0, opt or Nadam()
+    for i in range(1, t + 1):
+        prod = nadam_schedule(i, prod, opt)['sched_new']
+    return prod

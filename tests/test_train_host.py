@@ -3,6 +3,7 @@ torch.optim.NAdam, and the data-parallel gradient exchange under gloo (world_siz
 import os
 
 import numpy as np
+import pytest
 
 from dsen2_b200 import train
 from oracle import train_oracle as to
@@ -193,3 +194,39 @@ def test_training_data_loaders(tmp_path):
     json.dump([10, 20, 58, 68], open(t / 'roi.json', 'w'))
     tr, size = patches.OpenDataFilesTest(str(t), False, 2000)
     assert size == [48, 48] and len(tr) == 2 and tr[1].shape == (4, 6, 32, 32)
+
+
+def test_full_model_file_without_optimizer_state(tmp_path):
+    """model.save of an uncompiled model: Keras' full-model layout (/model_weights + model_config); load_weights reads it."""
+    import json
+    from dsen2_b200.DSen2Net import s2model
+    from dsen2_b200.hdf5 import File
+    shp = ((4, None, None), (6, None, None))
+    m = s2model(shp, num_layers=2, feature_size=128, seed=5)
+    p = str(tmp_path / 'full.hdf5')
+    m.save(p)
+    f = File(p)
+    assert list(f.keys()) == ['model_weights']
+    cfg = json.loads(bytes(f.attrs['model_config']).decode())['config']
+    assert cfg['num_layers'] == 2 and cfg['feature_size'] == 128
+    assert [bytes(n).decode() for n in f['model_weights'].attrs['layer_names']] == ['conv2d_%d' % (i + 1) for i in range(6)]
+    m2 = s2model(shp, num_layers=2, feature_size=128, seed=6)
+    m2.load_weights(p)
+    for a, b in zip(m.get_weights(), m2.get_weights()):
+        assert np.array_equal(a, b)
+    with pytest.raises(RuntimeError):
+        m2.load_optimizer_weights(p)                    # not compiled
+
+
+def test_model_checkpoint_full_model_vs_weights_only():
+    from dsen2_b200.callbacks import ModelCheckpoint
+
+    class M(_FakeModel):
+        def save(self, path):
+            self.saved.append('full:' + path)
+    for weights_only, want in ((False, ['full:a.hdf5']), (True, ['a.hdf5'])):
+        m = M()
+        cb = ModelCheckpoint('a.hdf5', save_weights_only=weights_only)
+        cb.set_model(m)
+        cb.on_epoch_end(0, {'val_loss': 1.0})
+        assert m.saved == want

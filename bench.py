@@ -397,8 +397,10 @@ def run_train(args):
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    n, P = args.train_batch, 32
-    model = s2model(((4, None, None), (6, None, None)), num_layers=6, feature_size=128, seed=0)
+    deep = args.model == 'vdsen2'                                        # supres_train.py:129-131: 32 x 256, batch size 8
+    n, P = (args.train_batch or (8 if deep else 128)), 32
+    L, F = (32, 256) if deep else (6, 128)
+    model = s2model(((4, None, None), (6, None, None)), num_layers=L, feature_size=F, seed=0)
     tr = Trainer(model, Nadam(lr=1e-4), device=dev)
     g = torch.Generator().manual_seed(1234 + rank)
     host = [torch.rand((n, c, P, P), generator=g).mul_(2.5).pin_memory() for c in (4, 6, 6)]
@@ -458,16 +460,19 @@ def run_train(args):
         t = torch.tensor([e0.elapsed_time(e1) / 20 * 1e3], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         allreduce_us = float(t.item())
-    flop = 3.0 * FLOP_PER_PIXEL[('dsen2', 20)] * n * P * P               # forward + backward-data + weight-gradient
+    flop = 3.0 * FLOP_PER_PIXEL[(args.model, 20)] * n * P * P            # forward + backward-data + weight-gradient
     if rank == 0:
         pk = peaks()
         line = {"metric": "train_samples_per_s", "value": world * n / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "fp16 operands / gradients (loss-scaled), fp32 accumulate, fp32 master weights + Nadam",
                 "data": "synthetic",
-                "config": {"workload": "DSen2 (6x128) training step, %d patches 32x32 per GPU, MAE + Keras-2 Nadam, "
-                                       "NCCL all-reduce of 1.79 M fp32 gradients" % n, "batch_per_gpu": n,
-                           "l2": "working set per step ~1.3 GB > L2"},
+                "config": {"workload": "%s training step, %d patches 32x32 per GPU, MAE + Keras-2 Nadam, "
+                                       "NCCL all-reduce of %.2f M fp32 gradients" % ('VDSen2 (32x256)' if deep else 'DSen2 (6x128)', n,
+                                                                                    tr.grads.numel() / 1e6), "batch_per_gpu": n,
+                           "l2": "activations kept for the backward pass: %.2f GB per step%s" % (
+                               (2 * L + 1) * n * P * P * F * 2 / 1e9, " > L2" if (2 * L + 1) * n * P * P * F * 2 > 126e6 else
+                               " (L2-resident: the reference's batch size; weights %.0f MB stream from HBM)" % (tr.grads.numel() * 2 / 1e6))},
                 "e2e": {"value": world * n / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": world * sum(h.numel() * 4 for h in host), "d2h_bytes_per_step": world * 8},
                 "gpu_launches": tr.launches_per_step() * args.steps,
@@ -475,10 +480,11 @@ def run_train(args):
                              "achieved": flop / ms / 1e9, "peak": pk['tf_burst'], "unit": "TFLOP/s",
                              "frac": flop / ms / 1e9 / pk['tf_burst'], "traffic": None,
                              "peak_source": pk['source'] + ", burst figure (millisecond-scale step)"},
-                "kernel_shares_ncu": {"note": "CONSTANTS from an ncu gpu__time_duration launch list of this workload (profiles/"
-                                      "r02_train_launch_list.txt), not measured in this run",
-                                      "forward + backward-data convolutions (conv_pair_kernel)": 0.53, "weight gradients (wgrad_direct_kernel)": 0.26,
-                                      "bias gradients (colsum_nhwc_kernel)": 0.086, "operand repacking": 0.064, "loss, Nadam, layout, fills": 0.06},
+                "kernel_shares_ncu": None if deep else {
+                    "note": "CONSTANTS from an ncu gpu__time_duration launch list of this workload (profiles/"
+                            "r02_train_launch_list.txt), not measured in this run",
+                    "forward + backward-data convolutions (conv_pair_kernel)": 0.53, "weight gradients (wgrad_direct_kernel)": 0.26,
+                    "bias gradients (colsum_nhwc_kernel)": 0.086, "operand repacking": 0.064, "loss, Nadam, layout, fills": 0.06},
                 "allreduce": {"us": allreduce_us, "bytes": int(tr.grads.numel()) * 4, "algo": "NCCL all_reduce(SUM), one bucket, "
                               "between the gradient graph and the update graph"} if world > 1 else None,
                 "last_loss": losses[-1] if losses else None}
@@ -501,7 +507,7 @@ def main():
     ap.add_argument('--no-facade', action='store_true', help='skip the e2e_facade leg (numpy -> supres.DSen2_20 -> numpy)')
     ap.add_argument('--workload', default='tile', choices=['tile', 'train'],
                     help="'tile' = the headline inference benchmark; 'train' = BASELINE.json configs[4] (training step)")
-    ap.add_argument('--train-batch', type=int, default=128)
+    ap.add_argument('--train-batch', type=int, default=0, help='patches per GPU and step (0 = the reference\'s: 128, or 8 with --model vdsen2)')
     args = ap.parse_args()
     if args.workload == 'train' and args.impl == 'ours':
         if args.steps == 3:

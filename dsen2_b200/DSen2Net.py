@@ -175,7 +175,7 @@ class S2Model:
             flat[kind] = np.concatenate(parts)
         tr.m.copy_(torch.from_numpy(flat['m']).to(tr.dev))
         tr.v.copy_(torch.from_numpy(flat['v']).to(tr.dev))
-        tr.iterations = int(np.asarray(g['Nadam/iterations:0'][()]))
+        tr.iterations = int(np.asarray(g['Nadam/iterations:0'][()]).reshape(-1)[0])
         ms = g.attrs['m_schedule'] if 'm_schedule' in g.attrs else None
         if ms is None:                       # a file written by Keras: rebuild the product from the schedule
             from .train import nadam_schedule
@@ -183,7 +183,7 @@ class S2Model:
             for t in range(1, tr.iterations + 1):
                 prod = nadam_schedule(t, prod, tr.opt)['sched_new']
             ms = prod
-        tr.m_schedule = float(np.asarray(ms))
+        tr.m_schedule = float(np.asarray(ms).reshape(-1)[0])
         return True
 
     # ---- device side ------------------------------------------------------------------- #

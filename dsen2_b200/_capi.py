@@ -33,7 +33,7 @@ SIGNATURES = {
     "dsen2_pack_tail16_weights": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "dsen2_conv_head": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                 c_void_p, c_void_p]),
-    "dsen2_conv_res32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
+    "dsen2_conv_res32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                                  c_void_p, c_void_p]),
     "dsen2_conv_resq": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                                 c_void_p, c_void_p]),
@@ -44,6 +44,8 @@ SIGNATURES = {
     "dsen2_pack_head16_weights": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "dsen2_conv_head16_q": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                     c_void_p]),
+    "dsen2_conv_head16_relu": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                       c_void_p]),
     "dsen2_conv_tail16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                   c_int, c_int, c_void_p, c_void_p]),
     "dsen2_conv_tail16_stitch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
@@ -54,12 +56,12 @@ SIGNATURES = {
                                 c_int, c_void_p, c_void_p]),
     "dsen2_pack_dgrad_weights": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "dsen2_pack_trunk_layers": (c_int, [c_void_p, c_longlong, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
-    "dsen2_conv_relu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "dsen2_conv_relu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dsen2_nchw_to_nhwc_f16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                        c_void_p, c_void_p]),
     "dsen2_relu_mask": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p]),
-    "dsen2_colsum_nhwc": (c_int, [c_void_p, c_longlong, c_float, c_void_p, c_void_p]),
-    "dsen2_wgrad_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
+    "dsen2_colsum_nhwc": (c_int, [c_void_p, c_longlong, c_int, c_float, c_void_p, c_void_p]),
+    "dsen2_wgrad_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "dsen2_mae_grad": (c_int, [c_void_p, c_void_p, c_longlong, c_float, c_void_p, c_void_p, c_void_p]),
     "dsen2_nadam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong] + [c_float] * 10 + [c_void_p]),
     "dsen2_nadam_step_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p]),
@@ -85,7 +87,7 @@ def lib():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)  # AttributeError if the symbol is not exported
             fn.restype, fn.argtypes = res, args
-        if handle.dsen2_abi_version() != 2:
+        if handle.dsen2_abi_version() != 3:
             raise DSen2Error("dsen2_b200: ABI version mismatch")
         _lib = handle
     return _lib

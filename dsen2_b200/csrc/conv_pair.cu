@@ -758,73 +758,80 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
         // 8 x 16 contiguous bytes for every 4-channel chunk, and the 32 chunks of that tile row are 4 KB contiguous
         // (DRAM page locality).  The fp16 NHWC copy the next convolution's TMA
         // reads goes through the staged (transposing) store; x_lo is only produced when the tail needs it.
-        constexpr int CPT = Cfg::CH / 2;
-        static_assert(CPT == 64 && !Cfg::SPLIT, "fp32-trunk epilogue: 64 channels per thread");
+        constexpr int CPT = Cfg::CH / 2;            // a thread owns CH / 2 channels of its pixel: one pass of 64 (128 features) or two
+        static_assert(CPT % 64 == 0 && !Cfg::SPLIT, "fp32-trunk epilogue: 64 channels per thread and pass");
         const uint32_t stg = smem_u32(s_stg) + (uint32_t)(warp * 1024);
-        const EpiGeom g = epi_geom<Cfg>(p, tc, wq, half * CPT);
-        // tile-row-major trunk: (n, H, W/8, C/4, 8 px, 4 ch) -- the 32 chunks of a tile row are 4 KB contiguous
+        // tile-row-major trunk: (n, H, W/8, C/4, 8 px, 4 ch) -- the C/4 chunks of a tile row are contiguous
         constexpr long long cpitch = 32;                                // floats between 4-channel chunks
-        float* xp = p.x32 + ((((long long)b * p.H + y) * p.tiles_x + tc.tx) * (Cfg::CH / 4) + half * (CPT / 4)) * cpitch +
-                    (row & 7) * 4;
-        float4 xr[CPT / 4];
-        if (valid) {
+#pragma unroll 1
+        for (int sc = 0; sc < CPT / 64; ++sc) {
+          const int cb = half * CPT + sc * 64;      // first channel of this pass
+          const EpiGeom g = epi_geom<Cfg>(p, tc, wq, cb);
+          float* xp = p.x32 + ((((long long)b * p.H + y) * p.tiles_x + tc.tx) * (Cfg::CH / 4) + cb / 4) * cpitch + (row & 7) * 4;
+          float4 xr[16];
+          if (valid) {
 #pragma unroll
-          for (int q = 0; q < CPT / 4; ++q) xr[q] = *reinterpret_cast<const float4*>(xp + q * cpitch);
-        } else {
+            for (int q = 0; q < 16; ++q) xr[q] = *reinterpret_cast<const float4*>(xp + q * cpitch);
+          } else {
 #pragma unroll
-          for (int q = 0; q < CPT / 4; ++q) xr[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        if (pt + npairs < pair_tiles) {   // the next tile's trunk lines -> L2 (64 lines per warp, 2 per lane)
-          const int ny = tn.ty * 16 + wq * 4 + (lane >> 3);
-          if (tn.b < p.n && ny < p.H) {
-            const float* np = p.x32 + ((((long long)tn.b * p.H + ny) * p.tiles_x + tn.tx) * (Cfg::CH / 4) + half * (CPT / 4) +
-                                       (lane & 7) * 2) * cpitch;
-            prefetch_l2(np);
-            prefetch_l2(np + cpitch);
+            for (int q = 0; q < 16; ++q) xr[q] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
-        }
-        mbar_wait(&tmem_full[acc], acc_phase);
-        tc_fence_after();
-        uint4 vh[8];
-#pragma unroll
-        for (int chunk = 0; chunk < CPT / 32; ++chunk) {
-          const int c0 = half * CPT + chunk * 32;
-          uint32_t r[32];
-          tmem_ld_32x32(taddr + c0, r);
-          tmem_ld_wait();
-          uint32_t* hw = reinterpret_cast<uint32_t*>(vh) + chunk * 16;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 bq = lds_f4(s_bias_addr + (uint32_t)(c0 + j) * 4);   // broadcast LDS.128
-            float4& xv = xr[chunk * 8 + (j >> 2)];
-            xv.x = fmaf(__uint_as_float(r[j]) + bq.x, p.res_scale, xv.x);
-            xv.y = fmaf(__uint_as_float(r[j + 1]) + bq.y, p.res_scale, xv.y);
-            xv.z = fmaf(__uint_as_float(r[j + 2]) + bq.z, p.res_scale, xv.z);
-            xv.w = fmaf(__uint_as_float(r[j + 3]) + bq.w, p.res_scale, xv.w);
-            const __half2 h0 = __floats2half2_rn(xv.x, xv.y), h1 = __floats2half2_rn(xv.z, xv.w);
-            hw[j >> 1] = *reinterpret_cast<const uint32_t*>(&h0);
-            hw[(j >> 1) + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+          if (pt + npairs < pair_tiles) {   // the next tile's trunk lines -> L2 (64 lines per warp and pass, 2 per lane)
+            const int ny = tn.ty * 16 + wq * 4 + (lane >> 3);
+            if (tn.b < p.n && ny < p.H) {
+              const float* np = p.x32 + ((((long long)tn.b * p.H + ny) * p.tiles_x + tn.tx) * (Cfg::CH / 4) + cb / 4 +
+                                         (lane & 7) * 2) * cpitch;
+              prefetch_l2(np);
+              prefetch_l2(np + cpitch);
+            }
           }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
-        if (valid) {
-#pragma unroll
-          for (int q = 0; q < CPT / 4; ++q) *reinterpret_cast<float4*>(xp + q * cpitch) = xr[q];
-        }
-        staged_store(stg, vh, p.out_hi, g, lane);
-        if (p.out_lo != nullptr) {                  // last resblock only: the tail's split operand needs x - fp16(x)
-          uint32_t* lw = reinterpret_cast<uint32_t*>(vh);
-#pragma unroll
-          for (int q = 0; q < CPT / 4; ++q) {
-            const float4 xv = xr[q];
-            const float2 f0 = __half22float2(__floats2half2_rn(xv.x, xv.y)), f1 = __half22float2(__floats2half2_rn(xv.z, xv.w));
-            const __half2 l0 = __floats2half2_rn(xv.x - f0.x, xv.y - f0.y), l1 = __floats2half2_rn(xv.z - f1.x, xv.w - f1.y);
-            lw[2 * q] = *reinterpret_cast<const uint32_t*>(&l0);
-            lw[2 * q + 1] = *reinterpret_cast<const uint32_t*>(&l1);
+          if (sc == 0) {
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
           }
-          staged_store(stg, vh, p.out_lo, g, lane);
+          uint4 vh[8];
+#pragma unroll
+          for (int chunk = 0; chunk < 2; ++chunk) {
+            const int c0 = cb + chunk * 32;
+            uint32_t r[32];
+            tmem_ld_32x32(taddr + c0, r);
+            tmem_ld_wait();
+            uint32_t* hw = reinterpret_cast<uint32_t*>(vh) + chunk * 16;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bq = lds_f4(s_bias_addr + (uint32_t)(c0 + j) * 4);   // broadcast LDS.128
+              float4& xv = xr[chunk * 8 + (j >> 2)];
+              xv.x = fmaf(__uint_as_float(r[j]) + bq.x, p.res_scale, xv.x);
+              xv.y = fmaf(__uint_as_float(r[j + 1]) + bq.y, p.res_scale, xv.y);
+              xv.z = fmaf(__uint_as_float(r[j + 2]) + bq.z, p.res_scale, xv.z);
+              xv.w = fmaf(__uint_as_float(r[j + 3]) + bq.w, p.res_scale, xv.w);
+              const __half2 h0 = __floats2half2_rn(xv.x, xv.y), h1 = __floats2half2_rn(xv.z, xv.w);
+              hw[j >> 1] = *reinterpret_cast<const uint32_t*>(&h0);
+              hw[(j >> 1) + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+            }
+          }
+          if (sc == CPT / 64 - 1) {   // the accumulator has been read: hand the TMEM buffer back before the stores
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+          }
+          if (valid) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) *reinterpret_cast<float4*>(xp + q * cpitch) = xr[q];
+          }
+          staged_store(stg, vh, p.out_hi, g, lane);
+          if (p.out_lo != nullptr) {                  // last resblock only: the tail's split operand needs x - fp16(x)
+            uint32_t* lw = reinterpret_cast<uint32_t*>(vh);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              const float4 xv = xr[q];
+              const float2 f0 = __half22float2(__floats2half2_rn(xv.x, xv.y)), f1 = __half22float2(__floats2half2_rn(xv.z, xv.w));
+              const __half2 l0 = __floats2half2_rn(xv.x - f0.x, xv.y - f0.y), l1 = __floats2half2_rn(xv.z - f1.x, xv.w - f1.y);
+              lw[2 * q] = *reinterpret_cast<const uint32_t*>(&l0);
+              lw[2 * q + 1] = *reinterpret_cast<const uint32_t*>(&l1);
+            }
+            staged_store(stg, vh, p.out_lo, g, lane);
+          }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         continue;
@@ -1015,11 +1022,16 @@ using CfgResidualQLast = PairCfg<128, kSplitNone, 1, 2, 9, 4, 2, kEpiResidualQLa
 using CfgRelu256 = PairCfg<256, kSplitNone, 1, 4, 9, 4, 3, kEpiRelu, 8>;
 using CfgResidualQ256 = PairCfg<256, kSplitNone, 1, 4, 9, 4, 3, kEpiResidualQ, 8>;
 using CfgResidualQLast256 = PairCfg<256, kSplitNone, 1, 4, 9, 4, 3, kEpiResidualQLast, 8>;
+// training step of the 256-feature network: fp32 trunk update and ReLU backward with the streamed weight ring
+using CfgResidual32_256 = PairCfg<256, kSplitNone, 1, 4, 9, 4, 3, kEpiResidual32, 8>;
+using CfgMask256 = PairCfg<256, kSplitNone, 1, 4, 9, 4, 3, kEpiMask, 8>;
 using CfgHead = PairCfg<256, kSplitStack, 2, 1, 3, 3, 6, kEpiRelu>;
 // first layer on the un-gathered 16-channel input: nine taps through shifted descriptors into a 32-byte-row halo box,
 // three products per tap into one accumulator (27 MMAs of N = F per tile pair)
 using CfgHead16 = PairCfg<128, kSplit3, 2, 1, 9, 1, 6, kEpiHeadQ, 0, 32, true>;
 using CfgHead16_256 = PairCfg<256, kSplit3, 2, 1, 9, 1, 6, kEpiHeadQ, 0, 32, true>;
+// the same first layer seeding an fp32 trunk (training step of the 256-feature network)
+using CfgHead16Relu256 = PairCfg<256, kSplit3, 2, 1, 9, 1, 6, kEpiRelu, 0, 32>;
 using CfgTail = PairCfg<32, kSplitStack, 2, 2, 9, 4, 6, kEpiTail>;
 
 // x0 / x1: tensor maps of the epilogue's x_hi / x_lo tiles (PairCfg::XT kernels only)
@@ -1106,9 +1118,11 @@ extern "C" int dsen2_conv_relu(const void* d_in, const void* d_w, const float* d
 }
 
 extern "C" int dsen2_conv_relu_bwd(const void* d_in, const void* d_w, const float* d_bias, const void* d_fwd_act, int n,
-                                   int H, int W, void* d_out, void* stream) {
+                                   int H, int W, int feature_size, void* d_out, void* stream) {
   DSEN2_REQUIRE(d_in && d_w && d_bias && d_fwd_act && d_out, DSEN2_E_BADARG, "dsen2_conv_relu_bwd: null pointer");
   DSEN2_REQUIRE(n >= 0 && H > 0 && W > 0, DSEN2_E_BADARG, "dsen2_conv_relu_bwd: bad shape");
+  DSEN2_REQUIRE(feature_size == 128 || feature_size == 256, DSEN2_E_BADARG,
+                "dsen2_conv_relu_bwd: feature size must be 128 or 256 (got %d)", feature_size);
   DSEN2_REQUIRE(((uintptr_t)d_in % 16) == 0 && ((uintptr_t)d_w % 16) == 0 && ((uintptr_t)d_fwd_act % 16) == 0 &&
                     ((uintptr_t)d_out % 16) == 0,
                 DSEN2_E_ALIGN, "dsen2_conv_relu_bwd: pointers must be 16-byte aligned");
@@ -1122,15 +1136,22 @@ extern "C" int dsen2_conv_relu_bwd(const void* d_in, const void* d_w, const floa
   p.res_hi = (const __half*)d_fwd_act;
   p.out_hi = (__half*)d_out;
   CUtensorMap a0, a1, w;
+  if (feature_size == 256) {
+    rc = make_maps<CfgMask256>(&a0, &a1, &w, d_in, nullptr, d_w, n, H, W);
+    if (rc) return rc;
+    return launch_pair<CfgMask256>(a0, a1, w, p, sms, (cudaStream_t)stream, "conv_pair<relu_bwd,256>");
+  }
   rc = make_maps<CfgMask>(&a0, &a1, &w, d_in, nullptr, d_w, n, H, W);
   if (rc) return rc;
   return launch_pair<CfgMask>(a0, a1, w, p, sms, (cudaStream_t)stream, "conv_pair<relu_bwd>");
 }
 
-extern "C" int dsen2_conv_res32(const void* d_in, const void* d_w, const float* d_bias, int n, int H, int W,
+extern "C" int dsen2_conv_res32(const void* d_in, const void* d_w, const float* d_bias, int n, int H, int W, int feature_size,
                                 float res_scale, float* d_trunk32, void* d_out_hi, void* d_out_lo, void* stream) {
   DSEN2_REQUIRE(d_in && d_w && d_bias && d_trunk32 && d_out_hi, DSEN2_E_BADARG, "dsen2_conv_res32: null pointer");
   DSEN2_REQUIRE(n >= 0 && H > 0 && W > 0, DSEN2_E_BADARG, "dsen2_conv_res32: bad shape");
+  DSEN2_REQUIRE(feature_size == 128 || feature_size == 256, DSEN2_E_BADARG,
+                "dsen2_conv_res32: feature size must be 128 or 256 (got %d)", feature_size);
   DSEN2_REQUIRE(((uintptr_t)d_in % 16) == 0 && ((uintptr_t)d_w % 16) == 0 && ((uintptr_t)d_trunk32 % 16) == 0 &&
                     ((uintptr_t)d_out_hi % 16) == 0 && ((uintptr_t)d_out_lo % 16) == 0,
                 DSEN2_E_ALIGN, "dsen2_conv_res32: pointers must be 16-byte aligned");
@@ -1145,6 +1166,11 @@ extern "C" int dsen2_conv_res32(const void* d_in, const void* d_w, const float* 
   p.x32 = d_trunk32;
   p.out_hi = (__half*)d_out_hi; p.out_lo = (__half*)d_out_lo;
   CUtensorMap a0, a1, w;
+  if (feature_size == 256) {
+    rc = make_maps<CfgResidual32_256>(&a0, &a1, &w, d_in, nullptr, d_w, n, H, W);
+    if (rc) return rc;
+    return launch_pair<CfgResidual32_256>(a0, a1, w, p, sms, (cudaStream_t)stream, "conv_pair<residual32,256>");
+  }
   rc = make_maps<CfgResidual32>(&a0, &a1, &w, d_in, nullptr, d_w, n, H, W);
   if (rc) return rc;
   return launch_pair<CfgResidual32>(a0, a1, w, p, sms, (cudaStream_t)stream, "conv_pair<residual32>");
@@ -1197,6 +1223,15 @@ extern "C" int dsen2_conv_head16_q(const void* d_xin_hi, const void* d_xin_lo, c
                                       nullptr, d_trunk_lo8, stream);
   return head_common<CfgHead16>("dsen2_conv_head16_q", d_xin_hi, d_xin_lo, d_w, d_bias, n, H, W, d_x_hi, nullptr, nullptr,
                                 d_trunk_lo8, stream);
+}
+
+// The training step's first layer of the 256-feature network: the same three-product convolution on the 16-channel prepared
+// input, relu -> NHWC fp16 + the seed of the fp32 trunk (DSen2Net.py:29).
+extern "C" int dsen2_conv_head16_relu(const void* d_xin_hi, const void* d_xin_lo, const void* d_w, const float* d_bias,
+                                      int n, int H, int W, int feature_size, void* d_out_hi, float* d_trunk32, void* stream) {
+  DSEN2_REQUIRE(feature_size == 256, DSEN2_E_BADARG, "dsen2_conv_head16_relu: feature_size 256 only (got %d)", feature_size);
+  return head_common<CfgHead16Relu256>("dsen2_conv_head16_relu", d_xin_hi, d_xin_lo, d_w, d_bias, n, H, W, d_out_hi, nullptr,
+                                       d_trunk32, nullptr, stream);
 }
 
 static int resq_common(int features, const void* d_in, const void* d_w, const float* d_bias, int n, int H, int W,

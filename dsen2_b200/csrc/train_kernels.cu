@@ -58,15 +58,18 @@ __global__ void relu_mask_kernel(const uint4* __restrict__ in, const uint4* __re
   }
 }
 
-// out[c] += scale * sum_pixels in[pixel][c]   (bias gradients from an NHWC fp16 gradient tensor, C = 128)
-// 256 threads = 16 pixel lanes x 16 chunks of 8 channels (one 16-byte load each); block partials -> atomics
-__global__ void colsum_nhwc_kernel(const __half* __restrict__ in, long long npix, float scale, float* __restrict__ out) {
+// out[c] += scale * sum_pixels in[pixel][c]   (bias gradients from an NHWC fp16 gradient tensor, C = 128 or 256)
+// 256 threads = 16 pixel lanes x 16 chunks of 8 channels (one 16-byte load each); blockIdx.y = group of 128 channels;
+// block partials -> atomics
+__global__ void colsum_nhwc_kernel(const __half* __restrict__ in, long long npix, int C, float scale, float* __restrict__ out) {
   const int chunk = threadIdx.x & 15, pl = threadIdx.x >> 4;
+  in += blockIdx.y * 128;
+  out += blockIdx.y * 128;
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   for (long long p = (long long)blockIdx.x * 16 + pl; p < npix; p += (long long)gridDim.x * 16) {
-    const uint4 q = *reinterpret_cast<const uint4*>(in + p * 128 + chunk * 8);
+    const uint4 q = *reinterpret_cast<const uint4*>(in + p * C + chunk * 8);
     const __half2* h = reinterpret_cast<const __half2*>(&q);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -218,7 +221,7 @@ static constexpr int kWdStages = 3;
 
 __global__ void __launch_bounds__(kWdThreads, 1)
 wgrad_direct_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_dy, int tiles_x,
-                    int tiles_y, int num_tiles, int tiles_per_split, float scale, float* __restrict__ dw) {
+                    int tiles_y, int num_tiles, int tiles_per_split, int C, float scale, float* __restrict__ dw) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + kWdStages * kWdStage);
@@ -227,6 +230,8 @@ wgrad_direct_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int dy = blockIdx.y;                                   // vertical tap 0..2
+  // 256 features: blockIdx.z = (block of 128 input channels, block of 128 output channels) of the (C, C) gradient
+  const int ci0 = (int)(blockIdx.z / (C / 128)) * 128, co0 = (int)(blockIdx.z % (C / 128)) * 128;
   const int t0 = blockIdx.x * tiles_per_split;
   const int t1 = min(num_tiles, t0 + tiles_per_split);
   const int nt = t1 - t0;
@@ -253,10 +258,10 @@ wgrad_direct_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
         mbar_wait(&empty[stage], phase ^ 1);
         uint8_t* s = smem + stage * kWdStage;
         mbar_expect_tx(&full[stage], kWdStage);
-        tma_load_4d(s, &tm_x, &full[stage], 0, t.tx * 8 - 1, t.ty * 16 + dy - 1, t.b);
-        tma_load_4d(s + kWdXBox, &tm_x, &full[stage], 64, t.tx * 8 - 1, t.ty * 16 + dy - 1, t.b);
-        tma_load_4d(s + 2 * kWdXBox, &tm_dy, &full[stage], 0, t.tx * 8, t.ty * 16, t.b);
-        tma_load_4d(s + 2 * kWdXBox + kWdYBox, &tm_dy, &full[stage], 64, t.tx * 8, t.ty * 16, t.b);
+        tma_load_4d(s, &tm_x, &full[stage], ci0, t.tx * 8 - 1, t.ty * 16 + dy - 1, t.b);
+        tma_load_4d(s + kWdXBox, &tm_x, &full[stage], ci0 + 64, t.tx * 8 - 1, t.ty * 16 + dy - 1, t.b);
+        tma_load_4d(s + 2 * kWdXBox, &tm_dy, &full[stage], co0, t.tx * 8, t.ty * 16, t.b);
+        tma_load_4d(s + 2 * kWdXBox + kWdYBox, &tm_dy, &full[stage], co0 + 64, t.tx * 8, t.ty * 16, t.b);
         if (++stage == kWdStages) { stage = 0; phase ^= 1; }
       }
     }
@@ -309,7 +314,7 @@ wgrad_direct_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     // each thread adds its own row of the three accumulators; the rotation is undone by splitting the row in two runs
     for (int dx = 0; dx < 3; ++dx) {
       const float* srow = reinterpret_cast<const float*>(smem + dx * 65536) + row * 128;
-      float* grow = dw + ((long long)(dy * 3 + dx) * 128 + row) * 128;
+      float* grow = dw + ((long long)(dy * 3 + dx) * C + ci0 + row) * C + co0;
       const int rot = (row & 31) << 2;           // element offset where column 0 of this row sits
       bulk_reduce_add_f32(grow, srow + rot, (uint32_t)((128 - rot) * 4));
       if (rot) bulk_reduce_add_f32(grow + (128 - rot), srow, (uint32_t)(rot * 4));
@@ -327,10 +332,11 @@ wgrad_direct_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
 
 using namespace dsen2;
 
-extern "C" int dsen2_wgrad_nhwc(const void* d_x, const void* d_dy, int n, int H, int W, float scale, float* d_dw,
+extern "C" int dsen2_wgrad_nhwc(const void* d_x, const void* d_dy, int n, int H, int W, int channels, float scale, float* d_dw,
                                 void* stream) {
   DSEN2_REQUIRE(d_x && d_dy && d_dw, DSEN2_E_BADARG, "dsen2_wgrad_nhwc: null pointer");
   DSEN2_REQUIRE(n > 0 && H > 0 && W > 0, DSEN2_E_BADARG, "dsen2_wgrad_nhwc: bad shape");
+  DSEN2_REQUIRE(channels == 128 || channels == 256, DSEN2_E_BADARG, "dsen2_wgrad_nhwc: 128 or 256 channels (got %d)", channels);
   DSEN2_REQUIRE(((uintptr_t)d_x % 16) == 0 && ((uintptr_t)d_dy % 16) == 0 && ((uintptr_t)d_dw % 16) == 0, DSEN2_E_ALIGN,
                 "dsen2_wgrad_nhwc: pointers must be 16-byte aligned");
   int sms = 0;
@@ -339,12 +345,13 @@ extern "C" int dsen2_wgrad_nhwc(const void* d_x, const void* d_dy, int n, int H,
   const int tiles_x = ceil_div(W, 8), tiles_y = ceil_div(H, 16);
   const long long tiles = (long long)n * tiles_x * tiles_y;
   DSEN2_REQUIRE(tiles < (1LL << 30), DSEN2_E_BADARG, "dsen2_wgrad_nhwc: batch too large");
-  int splits = sms / 3;
+  const int blocks = (channels / 128) * (channels / 128);       // 128 x 128 blocks of the (C, C) gradient
+  int splits = sms / (3 * blocks);
   if (splits > tiles) splits = (int)tiles;
   const int per = (int)((tiles + splits - 1) / splits);
   splits = (int)((tiles + per - 1) / per);
   CUtensorMap tx, ty;
-  const uint64_t dims[4] = {128, (uint64_t)W, (uint64_t)H, (uint64_t)n};
+  const uint64_t dims[4] = {(uint64_t)channels, (uint64_t)W, (uint64_t)H, (uint64_t)n};
   const uint32_t bx[4] = {64, 10, 16, 1};
   rc = make_tmap_f16_sw(&tx, d_x, 4, dims, bx, 128);
   if (rc) return rc;
@@ -357,8 +364,8 @@ extern "C" int dsen2_wgrad_nhwc(const void* d_x, const void* d_dy, int n, int H,
   if (needs_config(configured)) {
     DSEN2_CUDA(cudaFuncSetAttribute(wgrad_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
   }
-  wgrad_direct_kernel<<<dim3(splits, 3), kWdThreads, SMEM, (cudaStream_t)stream>>>(tx, ty, tiles_x, tiles_y, (int)tiles, per,
-                                                                                 scale, d_dw);
+  wgrad_direct_kernel<<<dim3(splits, 3, blocks), kWdThreads, SMEM, (cudaStream_t)stream>>>(tx, ty, tiles_x, tiles_y, (int)tiles,
+                                                                                         per, channels, scale, d_dw);
   return check_launch("wgrad_direct_kernel");
 }
 
@@ -382,12 +389,14 @@ extern "C" int dsen2_relu_mask(const void* d_in, const void* d_act, long long to
   return check_launch("relu_mask");
 }
 
-extern "C" int dsen2_colsum_nhwc(const void* d_in, long long npix, float scale, float* d_out, void* stream) {
+extern "C" int dsen2_colsum_nhwc(const void* d_in, long long npix, int channels, float scale, float* d_out, void* stream) {
   DSEN2_REQUIRE(d_in && d_out && npix > 0, DSEN2_E_BADARG, "dsen2_colsum_nhwc: bad arguments");
+  DSEN2_REQUIRE(channels == 128 || channels == 256, DSEN2_E_BADARG, "dsen2_colsum_nhwc: 128 or 256 channels (got %d)", channels);
   long long blocks = (npix + 15) / 16;
   const long long cap = (long long)sm_count() * 2;
   if (blocks > cap) blocks = cap;
-  colsum_nhwc_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __half*)d_in, npix, scale, d_out);
+  colsum_nhwc_kernel<<<dim3((unsigned)blocks, channels / 128), 256, 0, (cudaStream_t)stream>>>((const __half*)d_in, npix, channels,
+                                                                                              scale, d_out);
   return check_launch("colsum_nhwc");
 }
 

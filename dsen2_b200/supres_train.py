@@ -2,7 +2,7 @@
 
     python -m dsen2_b200.supres_train [--predict F] [--resume F] [--run_60] [--true] [--path P] [--epochs N]
 
-``--deep`` (VDSen2) can be predicted with but not trained here (``Trainer`` covers the 128-feature network).
+``--deep`` trains / predicts with VDSen2 (32 resBlocks x 256 features, batch size 8; ``supres_train.py:129-131``).
 Data parallel: launch with ``python -m torch.distributed.run --nproc-per-node N -m dsen2_b200.supres_train ...``; every
 rank then trains on its strided share of the (identically shuffled) patches and gradients are all-reduced over NCCL.
 """
@@ -65,8 +65,6 @@ def main(argv=None):
             print('Elapsed time: {}.'.format(time.time() - start))
         return 0
 
-    if args.deep:
-        raise SystemExit("training the 256-feature VDSen2 network is not implemented in this build (prediction is)")
     if args.resume_file:                                                # supres_train.py:180-184
         print("Will resume from the weights {}".format(args.resume_file))
         model.load_weights(args.resume_file)

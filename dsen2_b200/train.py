@@ -10,7 +10,8 @@ the forward and backward-data convolutions are the CTA-pair tcgen05 kernels (``c
 flipped / transposed operands), weight gradients are tcgen05 GEMMs over the pixel dimension
 (``csrc/train_kernels.cu``).  Activations and gradients are fp16 operands with fp32 accumulation; gradients carry a
 power-of-two loss scale so that the MAE gradient sign(pred-y)/N enters the fp16 data path as exactly +-2^-4.
-Master weights, gradients and the Nadam moments are fp32.  DSen2 (feature_size 128) only.
+Master weights, gradients and the Nadam moments are fp32.  DSen2 (feature_size 128) and VDSen2 (256; ``--deep``,
+``supres_train.py:129-131``: the 256-channel layers stream their weights, weight gradients run per 128 x 128 block).
 """
 import math
 import os
@@ -97,8 +98,10 @@ class Trainer:
 
     def __init__(self, model, optimizer=None, device=None, group=None):
         torch = _capi.require_cuda()
-        if model.feature_size != 128:
-            raise _capi.DSen2Error("training is implemented for the DSen2 (feature_size 128) network")
+        if model.feature_size not in (128, 256):
+            raise _capi.DSen2Error("training is implemented for feature_size 128 (DSen2) and 256 (VDSen2)")
+        if model.feature_size == 256 and model.out_channels > 7:
+            raise _capi.DSen2Error("feature_size 256: at most 7 output bands (dsen2_conv_tail16)")
         self.torch, self.model, self.opt, self.group = torch, model, optimizer or Nadam(), group
         self.dev = torch.device('cuda', torch.cuda.current_device()) if device is None else device
         self.F, self.L = model.feature_size, model.num_layers
@@ -117,7 +120,11 @@ class Trainer:
         self.v = torch.zeros_like(self.grads)
         self.iterations, self.m_schedule = 0, 1.0
         self.sums = torch.zeros(2, dtype=torch.float64, device=self.dev)
-        self.zero_bias = torch.zeros(128, dtype=torch.float32, device=self.dev)
+        self.zero_bias = torch.zeros(model.feature_size, dtype=torch.float32, device=self.dev)
+        # 128 features: first / last layer on the 64-channel prepared input (dsen2_conv_head / dsen2_conv_tail); 256: the
+        # inference path's 16-channel forms (dsen2_conv_head16_relu / dsen2_conv_tail16), whose N = 512 stacked head does not
+        # fit the tensor memory
+        self.in16 = model.feature_size == 256
         self._bufs = {}
         # replay the whole step as one CUDA graph from the third call of a shape on (DSEN2_TRAIN_NO_GRAPH=1: eager, for ncu)
         self.use_graph = not os.environ.get('DSEN2_TRAIN_NO_GRAPH')
@@ -131,15 +138,16 @@ class Trainer:
         F, L = self.F, self.L
         # the 2L trunk layers' operands are stacked so that ONE launch repacks them all after every update
         self.w_fwd_trunk, self.w_bwd_trunk = f16(max(2 * L, 1), 9, F, F), f16(max(2 * L, 1), 9, F, F)
-        self.w_fwd = [f16(3, 2 * F, 64)] + [self.w_fwd_trunk[i] for i in range(2 * L)] + [f16(9, 32, F)]
+        self.w_fwd = ([f16(9, 2 * F, 16) if self.in16 else f16(3, 2 * F, 64)] + [self.w_fwd_trunk[i] for i in range(2 * L)] +
+                      [f16(128, F) if self.in16 else f16(9, 32, F)])
         self.w_bwd = [None] + [self.w_bwd_trunk[i] for i in range(2 * L)] + [f16(9, F, F)]
         # biases: the F-channel layers read theirs straight from the flat parameter vector (a view, nothing to copy after an
         # update); the last layer's is padded to 16
         self.b_fwd = [self.bias(i) if c == self.F else torch.zeros(max(c, 16), dtype=torch.float32, device=self.dev)
                       for i, (_, c) in enumerate(shapes)]
-        self.gw_head = torch.zeros((9, 128, 128), dtype=torch.float32, device=self.dev)
-        self.gw_tail = torch.zeros((9, 128, 128), dtype=torch.float32, device=self.dev)
-        self.gb_tail = torch.zeros(128, dtype=torch.float32, device=self.dev)
+        self.gw_head = torch.zeros((9, F, F), dtype=torch.float32, device=self.dev)
+        self.gw_tail = torch.zeros((9, F, F), dtype=torch.float32, device=self.dev)
+        self.gb_tail = torch.zeros(F, dtype=torch.float32, device=self.dev)
         self.repack()
 
     # ---- parameter views -------------------------------------------------------------------------------------
@@ -175,13 +183,15 @@ class Trainer:
         lib, ptr, st = _capi.lib(), _capi.ptr, _capi.stream_ptr()
         F, L, nl = self.F, self.L, 2 * self.L + 2
         with self.torch.cuda.device(self.dev):
-            _capi.check(lib.dsen2_pack_head_weights(ptr(self.kernel(0)), self.ctot, F, ptr(self.w_fwd[0]), st), "pack head")
+            pack_head = lib.dsen2_pack_head16_weights if self.in16 else lib.dsen2_pack_head_weights
+            pack_tail = lib.dsen2_pack_tail16_weights if self.in16 else lib.dsen2_pack_tail_weights
+            _capi.check(pack_head(ptr(self.kernel(0)), self.ctot, F, ptr(self.w_fwd[0]), st), "pack head")
             if L > 0:
                 # the second conv of a resBlock is followed by Lambda(x * 0.1) (DSen2Net.py:13): folded into its
                 # backward operand; consecutive F -> F kernels lie 9*F*F + F floats apart in the flat parameter vector
                 _capi.check(lib.dsen2_pack_trunk_layers(ptr(self.kernel(1)), 9 * F * F + F, 2 * L, F, 0.1,
                                                         ptr(self.w_fwd_trunk), ptr(self.w_bwd_trunk), st), "pack trunk layers")
-            _capi.check(lib.dsen2_pack_tail_weights(ptr(self.kernel(nl - 1)), F, self.cout, ptr(self.w_fwd[-1]), st), "pack tail")
+            _capi.check(pack_tail(ptr(self.kernel(nl - 1)), F, self.cout, ptr(self.w_fwd[-1]), st), "pack tail")
             _capi.check(lib.dsen2_pack_dgrad_weights(ptr(self.kernel(nl - 1)), F, self.cout, F, F, 1.0, ptr(self.w_bwd[-1]), st),
                         "pack dgrad tail")
             for i in range(nl):
@@ -195,7 +205,8 @@ class Trainer:
         if b is None:
             torch, F, L = self.torch, self.F, self.L
             f16 = lambda *s: torch.empty(s, dtype=torch.float16, device=self.dev)
-            b = dict(xin_hi=f16(n, P, P, 64), xin_lo=f16(n, P, P, 64), x_hi=[f16(n, P, P, F) for _ in range(L + 1)],
+            cin = 16 if self.in16 else 64
+            b = dict(xin_hi=f16(n, P, P, cin), xin_lo=f16(n, P, P, cin), x_hi=[f16(n, P, P, F) for _ in range(L + 1)],
                      t=[f16(n, P, P, F) for _ in range(L)], x_lo=f16(n, P, P, F),
                      x32=torch.empty((n, P, (P + 7) // 8, F // 4, 8, 4), dtype=torch.float32, device=self.dev),
                      dx32=torch.empty((n, P, (P + 7) // 8, F // 4, 8, 4), dtype=torch.float32, device=self.dev),
@@ -211,20 +222,31 @@ class Trainer:
         lib, ptr, st = _capi.lib(), _capi.ptr, _capi.stream_ptr()
         F, L, ch = self.F, self.L, self.model.in_channels
         x2, c2 = (xs[2], ch[2]) if len(xs) == 3 else (None, 0)
-        _capi.check(lib.dsen2_prep_from_patches(ptr(xs[0]), ch[0], ptr(xs[1]), ch[1], ptr(x2), c2, n, P, ptr(b['xin_hi']),
-                                                ptr(b['xin_lo']), st), "prep")
-        _capi.check(lib.dsen2_conv_head(ptr(b['xin_hi']), ptr(b['xin_lo']), ptr(self.w_fwd[0]), ptr(self.b_fwd[0]), n, P, P, F,
-                                        ptr(b['x_hi'][0]), ptr(b['x_lo']) if L == 0 else None,
-                                        ptr(b['x32']) if L > 0 else None, st), "head")
+        prep = lib.dsen2_prep16_from_patches if self.in16 else lib.dsen2_prep_from_patches
+        _capi.check(prep(ptr(xs[0]), ch[0], ptr(xs[1]), ch[1], ptr(x2), c2, n, P, ptr(b['xin_hi']), ptr(b['xin_lo']), st), "prep")
+        if self.in16:
+            if L == 0:
+                raise _capi.DSen2Error("feature_size 256: training needs at least one resBlock")
+            _capi.check(lib.dsen2_conv_head16_relu(ptr(b['xin_hi']), ptr(b['xin_lo']), ptr(self.w_fwd[0]), ptr(self.b_fwd[0]), n, P, P,
+                                                   F, ptr(b['x_hi'][0]), ptr(b['x32']), st), "head")
+        else:
+            _capi.check(lib.dsen2_conv_head(ptr(b['xin_hi']), ptr(b['xin_lo']), ptr(self.w_fwd[0]), ptr(self.b_fwd[0]), n, P, P, F,
+                                            ptr(b['x_hi'][0]), ptr(b['x_lo']) if L == 0 else None,
+                                            ptr(b['x32']) if L > 0 else None, st), "head")
         for l in range(L):
             _capi.check(lib.dsen2_conv_relu(ptr(b['x_hi'][l]), ptr(self.w_fwd[1 + 2 * l]), ptr(self.b_fwd[1 + 2 * l]), n, P, P, F,
                                             ptr(b['t'][l]), st), "conv1")
-            _capi.check(lib.dsen2_conv_res32(ptr(b['t'][l]), ptr(self.w_fwd[2 + 2 * l]), ptr(self.b_fwd[2 + 2 * l]), n, P, P, 0.1,
+            _capi.check(lib.dsen2_conv_res32(ptr(b['t'][l]), ptr(self.w_fwd[2 + 2 * l]), ptr(self.b_fwd[2 + 2 * l]), n, P, P, F, 0.1,
                                              ptr(b['x32']), ptr(b['x_hi'][l + 1]), ptr(b['x_lo']) if l == L - 1 else None, st),
                         "conv2")
-        _capi.check(lib.dsen2_conv_tail(ptr(b['x_hi'][L]), ptr(b['x_lo']), ptr(self.w_fwd[-1]), ptr(self.b_fwd[-1]),
-                                        ptr(b['xin_hi']), ptr(b['xin_lo']), self.ctot - self.cout, self.cout, n, P, P,
-                                        ptr(b['pred']), st), "tail")
+        if self.in16:
+            _capi.check(lib.dsen2_conv_tail16(ptr(b['x_hi'][L]), ptr(b['x_lo']), ptr(self.w_fwd[-1]), ptr(self.b_fwd[-1]),
+                                              ptr(b['xin_hi']), ptr(b['xin_lo']), self.ctot - self.cout, self.cout, F, n, P, P,
+                                              ptr(b['pred']), st), "tail")
+        else:
+            _capi.check(lib.dsen2_conv_tail(ptr(b['x_hi'][L]), ptr(b['x_lo']), ptr(self.w_fwd[-1]), ptr(self.b_fwd[-1]),
+                                            ptr(b['xin_hi']), ptr(b['xin_lo']), self.ctot - self.cout, self.cout, n, P, P,
+                                            ptr(b['pred']), st), "tail")
         return b['pred']
 
     # ---- one optimisation step ----------------------------------------------------------------------------------
@@ -325,11 +347,11 @@ class Trainer:
             nl = 2 * L + 2
             npix = n * P * P
 
-            def wgrad(x_nhwc, dy_nhwc, scale, out):     # out (9,128,128) fp32 += scale * sum_px X[px+tap] (x) dY[px]
-                _capi.check(lib.dsen2_wgrad_nhwc(ptr(x_nhwc), ptr(dy_nhwc), n, P, P, scale, ptr(out), st), "wgrad")
+            def wgrad(x_nhwc, dy_nhwc, scale, out):     # out (9,F,F) fp32 += scale * sum_px X[px+tap] (x) dY[px]
+                _capi.check(lib.dsen2_wgrad_nhwc(ptr(x_nhwc), ptr(dy_nhwc), n, P, P, F, scale, ptr(out), st), "wgrad")
 
-            def bgrad(dy_nhwc, scale, out):             # out (128,) fp32 += scale * sum_px dY[px]
-                _capi.check(lib.dsen2_colsum_nhwc(ptr(dy_nhwc), npix, scale, ptr(out), st), "bias grad")
+            def bgrad(dy_nhwc, scale, out):             # out (F,) fp32 += scale * sum_px dY[px]
+                _capi.check(lib.dsen2_colsum_nhwc(ptr(dy_nhwc), npix, F, scale, ptr(out), st), "bias grad")
 
             # ---- last layer: Conv2D(cout) (DSen2Net.py:35); the Add of the global skip passes the gradient through
             _capi.check(lib.dsen2_nchw_to_nhwc_f16(ptr(b['dpred']), self.cout, None, 0, None, 0, n, P, P, F, ptr(b['dy_nhwc']), st),
@@ -337,7 +359,7 @@ class Trainer:
             wgrad(b['x_hi'][L], b['dy_nhwc'], inv, self.gw_tail)
             bgrad(b['dy_nhwc'], inv, self.gb_tail)
             b['dx32'].zero_()
-            _capi.check(lib.dsen2_conv_res32(ptr(b['dy_nhwc']), ptr(self.w_bwd[-1]), ptr(self.zero_bias), n, P, P, 1.0,
+            _capi.check(lib.dsen2_conv_res32(ptr(b['dy_nhwc']), ptr(self.w_bwd[-1]), ptr(self.zero_bias), n, P, P, F, 1.0,
                                              ptr(b['dx32']), ptr(b['dx_hi']), None, st), "dgrad tail")
             # ---- resBlocks, last to first (DSen2Net.py:9-15)
             for l in range(L - 1, -1, -1):
@@ -345,10 +367,10 @@ class Trainer:
                 wgrad(b['t'][l], b['dx_hi'], 0.1 * inv, self.kernel(i2, self.grads))       # d x_{l+1} -> conv2 (x 0.1)
                 bgrad(b['dx_hi'], 0.1 * inv, self.bias(i2, self.grads))
                 _capi.check(lib.dsen2_conv_relu_bwd(ptr(b['dx_hi']), ptr(self.w_bwd[i2]), ptr(self.zero_bias), ptr(b['t'][l]),
-                                                    n, P, P, ptr(b['g2']), st), "dgrad conv2 + relu")
+                                                    n, P, P, F, ptr(b['g2']), st), "dgrad conv2 + relu")
                 wgrad(b['x_hi'][l], b['g2'], inv, self.kernel(i1, self.grads))
                 bgrad(b['g2'], inv, self.bias(i1, self.grads))
-                _capi.check(lib.dsen2_conv_res32(ptr(b['g2']), ptr(self.w_bwd[i1]), ptr(self.zero_bias), n, P, P, 1.0,
+                _capi.check(lib.dsen2_conv_res32(ptr(b['g2']), ptr(self.w_bwd[i1]), ptr(self.zero_bias), n, P, P, F, 1.0,
                                                  ptr(b['dx32']), ptr(b['dx_hi']), None, st), "dgrad conv1 + skip")
             # ---- first layer: Conv2D(F, relu) on the concatenated inputs (DSen2Net.py:24-29)
             _capi.check(lib.dsen2_relu_mask(ptr(b['dx_hi']), ptr(b['x_hi'][0]), npix * F, ptr(b['g2']), st), "relu mask")

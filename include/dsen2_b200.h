@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define DSEN2_ABI_VERSION 2
+#define DSEN2_ABI_VERSION 3
 
 #define DSEN2_E_BADARG   (-1)  /* null pointer / non-positive size / unsupported combination */
 #define DSEN2_E_ALIGN    (-2)  /* pointer or channel count not aligned as the kernel requires */
@@ -158,8 +158,8 @@ int dsen2_conv_head(const void* d_xin_hi, const void* d_xin_lo, const void* d_w,
  *   trunk32 <- trunk32 + res_scale * (conv3x3(d_in) + bias)          (in place, tile-row-major fp32)
  *   d_out_hi <- fp16(trunk32) NHWC;  d_out_lo (optional) <- fp16(trunk32 - out_hi) NHWC
  * d_in is the NHWC fp16 output of the block's first convolution (dsen2_conv_relu); d_w from
- * dsen2_pack_conv_weights(cin_pad = cout_pad = 128).  feature_size 128 only.                              */
-int dsen2_conv_res32(const void* d_in, const void* d_w, const float* d_bias, int n, int H, int W,
+ * dsen2_pack_conv_weights(cin_pad = cout_pad = feature_size).  feature_size 128 or 256 (weights streamed).   */
+int dsen2_conv_res32(const void* d_in, const void* d_w, const float* d_bias, int n, int H, int W, int feature_size,
                      float res_scale, float* d_trunk32, void* d_out_hi, void* d_out_lo, void* stream);
 
 /* The trunk of the inference path (fp16 + 8 bits, 19 significant bits):
@@ -186,6 +186,10 @@ int dsen2_conv_resq256(const void* d_in, const void* d_w, const float* d_bias, i
  * hi*W_hi + hi*W_lo + lo*W_hi accumulate into ONE TMEM accumulator (fp32-equivalent first layer).               */
 int dsen2_conv_head16_q(const void* d_xin_hi, const void* d_xin_lo, const void* d_w, const float* d_bias,
                         int n, int H, int W, int feature_size, void* d_x_hi, void* d_trunk_lo8, void* stream);
+/* The same first layer for the training step of the 256-feature network (supres_train.py:129-130): relu -> d_out_hi NHWC
+ * fp16 and the seed of the fp32 trunk d_trunk32 (layout as dsen2_conv_head).  feature_size 256.                  */
+int dsen2_conv_head16_relu(const void* d_xin_hi, const void* d_xin_lo, const void* d_w, const float* d_bias,
+                           int n, int H, int W, int feature_size, void* d_out_hi, float* d_trunk32, void* stream);
 
 /* Conv2D(cout, 3x3) + Add(last input) (DSen2Net.py:35,38,41) on the trunk (hi, lo).  The global skip is
  * read from x_in (centre tap, bands skip_ch0 .. skip_ch0+cout).  Output: NCHW fp32 predictions
@@ -230,8 +234,8 @@ int dsen2_s2model_forward(const float* const* d_x, const int* channels, int n_in
 
 /* ---------------------------------------------------------------------------------------------
  * Training step -- training/supres_train.py:137-144 (Nadam, mean_absolute_error, mean_squared_error
- * metric) and :218-230 (model.fit inner step), feature_size 128.  Forward = the inference kernels
- * with per-layer activation buffers.  Backward data path = the same convolution kernels on
+ * metric) and :218-230 (model.fit inner step), feature_size 128 (DSen2) or 256 (VDSen2, supres_train.py:129-130).
+ * Forward = the inference kernels with per-layer activation buffers.  Backward data path = the same convolution kernels on
  * dsen2_pack_dgrad_weights operands: dsen2_conv_relu_bwd (gradient through Conv2D + ReLU) and
  * dsen2_conv_res32 with scale 1 (gradient through the Add of resBlock, accumulated on an fp32
  * gradient trunk).  Weight gradients = dsen2_wgrad_nhwc, a tcgen05 GEMM over the pixel dimension.
@@ -249,20 +253,22 @@ int dsen2_pack_dgrad_weights(const float* d_hwio, int cin, int cout, int rows_pa
 int dsen2_pack_trunk_layers(const float* d_first_kernel, long long layer_stride, int num_layers, int feature_size,
                             float scale_second, void* d_fwd, void* d_bwd, void* stream);
 
-/* d_out = conv3x3(d_in, d_w) * [d_fwd_act > 0]   (NHWC fp16, 128 channels; d_bias must be zeros) */
+/* d_out = conv3x3(d_in, d_w) * [d_fwd_act > 0]   (NHWC fp16, feature_size = 128 or 256 channels; d_bias must be zeros) */
 int dsen2_conv_relu_bwd(const void* d_in, const void* d_w, const float* d_bias, const void* d_fwd_act,
-                        int n, int H, int W, void* d_out, void* stream);
+                        int n, int H, int W, int feature_size, void* d_out, void* stream);
 
 /* up to three NCHW fp32 inputs concatenated along channels -> NHWC fp16 (n,H,W,cpad), remaining channels zero */
 int dsen2_nchw_to_nhwc_f16(const float* d_x0, int c0, const float* d_x1, int c1, const float* d_x2, int c2,
                            int n, int H, int W, int cpad, void* d_out, void* stream);
 /* d_out = d_in where d_act > 0, else 0 (NHWC fp16, `total` elements, multiple of 8) */
 int dsen2_relu_mask(const void* d_in, const void* d_act, long long total, void* d_out, void* stream);
-/* d_out[c] += scale * sum over pixels of d_in[pixel][c]  (NHWC fp16, 128 channels; bias gradients) */
-int dsen2_colsum_nhwc(const void* d_in, long long npix, float scale, float* d_out, void* stream);
-/* Weight gradient straight from the NHWC fp16 tensors (128 channels each), MN-major tcgen05 operands:
- * d_dw (9,128,128) fp32 += scale * sum_px X[px + tap][ci] * dY[px][co]   (HWIO order).                  */
-int dsen2_wgrad_nhwc(const void* d_x, const void* d_dy, int n, int H, int W, float scale, float* d_dw, void* stream);
+/* d_out[c] += scale * sum over pixels of d_in[pixel][c]  (NHWC fp16, channels = 128 or 256; bias gradients) */
+int dsen2_colsum_nhwc(const void* d_in, long long npix, int channels, float scale, float* d_out, void* stream);
+/* Weight gradient straight from the NHWC fp16 tensors (C = channels = 128 or 256 each), MN-major tcgen05 operands:
+ * d_dw (9,C,C) fp32 += scale * sum_px X[px + tap][ci] * dY[px][co]   (HWIO order; one CTA per vertical tap, pixel
+ * slice and 128 x 128 block of the gradient).                                                               */
+int dsen2_wgrad_nhwc(const void* d_x, const void* d_dy, int n, int H, int W, int channels, float scale, float* d_dw,
+                     void* stream);
 
 /* mean_absolute_error: d_dpred = gscale * sign(pred - y); d_sums[0] += sum|pred-y|, d_sums[1] += sum (pred-y)^2 */
 int dsen2_mae_grad(const float* d_pred, const float* d_y, long long total, float gscale, float* d_dpred,

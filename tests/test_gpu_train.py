@@ -32,41 +32,45 @@ def _wgrad_ref(x_nhwc, dy_nhwc):
     return out
 
 
-@pytest.mark.parametrize('shape', [(4, 32, 32), (128, 32, 32), (3, 16, 24), (2, 40, 8)])
+@pytest.mark.parametrize('shape', [(4, 32, 32), (128, 32, 32), (3, 16, 24), (2, 40, 8), (4, 32, 32, 256), (3, 16, 24, 256)])
 def test_wgrad_nhwc_mn_major(env, shape):
-    """Weight gradient straight from the NHWC tensors (MN-major tcgen05 operands, halo-box taps, bulk fp32 reduction)."""
+    """Weight gradient straight from the NHWC tensors (MN-major tcgen05 operands, halo-box taps, bulk fp32 reduction);
+    256 channels = four 128 x 128 blocks of the gradient."""
     torch, _capi, lib = env
-    n, H, W = shape
+    n, H, W = shape[:3]
+    C = shape[3] if len(shape) == 4 else 128
     rng = np.random.RandomState(n + H)
-    x = rng.randn(n, H, W, 128).astype(np.float16)
-    dy = (rng.randn(n, H, W, 128) * 0.1).astype(np.float16)
+    x = rng.randn(n, H, W, C).astype(np.float16)
+    dy = (rng.randn(n, H, W, C) * 0.1).astype(np.float16)
     tx, tdy = torch.from_numpy(x).cuda(), torch.from_numpy(dy).cuda()
-    dw = torch.full((9, 128, 128), 1.0, device='cuda')                      # accumulates on top of what is there
-    _capi.check(lib.dsen2_wgrad_nhwc(_capi.ptr(tx), _capi.ptr(tdy), n, H, W, 0.5, _capi.ptr(dw), _capi.stream_ptr()), 'wgrad nhwc')
+    dw = torch.full((9, C, C), 1.0, device='cuda')                          # accumulates on top of what is there
+    _capi.check(lib.dsen2_wgrad_nhwc(_capi.ptr(tx), _capi.ptr(tdy), n, H, W, C, 0.5, _capi.ptr(dw), _capi.stream_ptr()), 'wgrad nhwc')
     torch.cuda.synchronize()
     ref = 1.0 + 0.5 * _wgrad_ref(x.astype(np.float64), dy)
     np.testing.assert_allclose(dw.cpu().numpy(), ref, rtol=1e-3, atol=1e-3 * np.abs(ref).max())
 
 
-def test_relu_mask_and_colsum(env):
+@pytest.mark.parametrize('C', [128, 256])
+def test_relu_mask_and_colsum(env, C):
     torch, _capi, lib = env
     rng = np.random.RandomState(2)
-    g = rng.randn(3, 16, 8, 128).astype(np.float16)
-    a = rng.randn(3, 16, 8, 128).astype(np.float16)
+    g = rng.randn(3, 16, 8, C).astype(np.float16)
+    a = rng.randn(3, 16, 8, C).astype(np.float16)
     tg, ta = torch.from_numpy(g).cuda(), torch.from_numpy(a).cuda()
     out = torch.empty_like(tg)
     _capi.check(lib.dsen2_relu_mask(_capi.ptr(tg), _capi.ptr(ta), g.size, _capi.ptr(out), _capi.stream_ptr()), 'mask')
-    cs = torch.full((128,), 2.0, device='cuda')
-    _capi.check(lib.dsen2_colsum_nhwc(_capi.ptr(tg), 3 * 16 * 8, 0.25, _capi.ptr(cs), _capi.stream_ptr()), 'colsum')
+    cs = torch.full((C,), 2.0, device='cuda')
+    _capi.check(lib.dsen2_colsum_nhwc(_capi.ptr(tg), 3 * 16 * 8, C, 0.25, _capi.ptr(cs), _capi.stream_ptr()), 'colsum')
     torch.cuda.synchronize()
     assert np.array_equal(out.cpu().numpy().view(np.uint16), np.where(a.astype(np.float32) > 0, g, np.float16(0)).view(np.uint16))
-    np.testing.assert_allclose(cs.cpu().numpy(), 2.0 + 0.25 * g.astype(np.float64).reshape(-1, 128).sum(0), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(cs.cpu().numpy(), 2.0 + 0.25 * g.astype(np.float64).reshape(-1, C).sum(0), rtol=1e-4, atol=1e-4)
 
 
-def test_conv_relu_bwd_is_the_transposed_convolution(env):
+@pytest.mark.parametrize('C', [128, 256])
+def test_conv_relu_bwd_is_the_transposed_convolution(env, C):
     torch, _capi, lib = env
     import torch.nn.functional as F
-    n, H, W, C = 2, 32, 32, 128
+    n, H, W = 2, 32, 32
     rng = np.random.RandomState(3)
     dy = (rng.randn(n, H, W, C) * 0.1).astype(np.float16)
     act = np.maximum(rng.randn(n, H, W, C), 0).astype(np.float16)
@@ -78,7 +82,7 @@ def test_conv_relu_bwd_is_the_transposed_convolution(env):
     zero = torch.zeros(C, device='cuda')
     out = torch.zeros((n, H, W, C), dtype=torch.float16, device='cuda')
     tdy, tact = torch.from_numpy(dy).cuda(), torch.from_numpy(act).cuda()      # keep both alive across the launch
-    _capi.check(lib.dsen2_conv_relu_bwd(_capi.ptr(tdy), _capi.ptr(tw), _capi.ptr(zero), _capi.ptr(tact), n, H, W,
+    _capi.check(lib.dsen2_conv_relu_bwd(_capi.ptr(tdy), _capi.ptr(tw), _capi.ptr(zero), _capi.ptr(tact), n, H, W, C,
                                         _capi.ptr(out), _capi.stream_ptr()), 'relu bwd')
     torch.cuda.synchronize()
     # reference: gradient of y = conv(x, w) w.r.t. x, times 0.1, masked by the forward activation
@@ -89,11 +93,11 @@ def test_conv_relu_bwd_is_the_transposed_convolution(env):
     np.testing.assert_allclose(out.cpu().numpy().astype(np.float64), ref, rtol=2e-3, atol=2e-3 * np.abs(ref).max())
 
 
-def _setup(L=2, n=4, P=32, run_60=False, seed=0):
+def _setup(L=2, n=4, P=32, run_60=False, seed=0, F=128):
     from dsen2_b200.DSen2Net import s2model
     chans = (4, 6, 2) if run_60 else (4, 6)
     rng = np.random.RandomState(seed)
-    model = s2model(tuple((c, None, None) for c in chans), num_layers=L, feature_size=128, seed=7)
+    model = s2model(tuple((c, None, None) for c in chans), num_layers=L, feature_size=F, seed=7)
     ws = model.get_weights()
     for i in range(1, len(ws), 2):
         ws[i] = (rng.randn(*ws[i].shape) * 0.05).astype(np.float32)
@@ -104,7 +108,8 @@ def _setup(L=2, n=4, P=32, run_60=False, seed=0):
 
 
 @pytest.mark.parametrize('cfg', [dict(L=2, n=4, P=32), dict(L=6, n=8, P=32), dict(L=1, n=2, P=32, run_60=True),
-                                 dict(L=0, n=2, P=16)])
+                                 dict(L=0, n=2, P=16), dict(L=2, n=4, P=32, F=256), dict(L=1, n=2, P=32, run_60=True, F=256),
+                                 dict(L=4, n=8, P=32, F=256)])
 def test_gradients_vs_autograd(env, cfg):
     torch, _capi, lib = env
     from dsen2_b200.train import Trainer
@@ -126,11 +131,12 @@ def test_gradients_vs_autograd(env, cfg):
     print('worst relative gradient error', worst)
 
 
-def test_nadam_steps_vs_oracle(env):
+@pytest.mark.parametrize('F', [128, 256])
+def test_nadam_steps_vs_oracle(env, F):
     torch, _capi, lib = env
     from dsen2_b200.train import Nadam, Trainer
     from oracle import train_oracle as to
-    model, ws, xs, y = _setup(L=2, n=4, P=32)
+    model, ws, xs, y = _setup(L=2, n=4, P=32, F=F)
     lr = 1e-3
     tr = Trainer(model, Nadam(lr=lr))
     dx, dy = [torch.from_numpy(a).cuda() for a in xs], torch.from_numpy(y).cuda()
@@ -170,11 +176,12 @@ def test_keras_like_compile_fit(env):
     assert abs(np.abs(pred - y).mean() - model.train_on_batch(xs, y)[0]) < 5e-3
 
 
-def test_graph_replay_equals_eager_steps(env):
+@pytest.mark.parametrize('F', [128, 256])
+def test_graph_replay_equals_eager_steps(env, F):
     """The CUDA-graph replay of the step (third call on) performs the same updates as the eager path."""
     torch, _capi, lib = env
     from dsen2_b200.train import Nadam, Trainer
-    model, ws, xs, y = _setup(L=2, n=4, P=32)
+    model, ws, xs, y = _setup(L=2, n=4, P=32, F=F)
     dx, dy = [torch.from_numpy(a).cuda() for a in xs], torch.from_numpy(y).cuda()
     runs = []
     for use_graph in (False, True):
@@ -219,8 +226,9 @@ def test_fit_with_validation_and_callbacks(env, tmp_path):
             assert np.array_equal(a, b)
 
 
-def test_supres_train_cli_trains_and_predicts(env, tmp_path):
-    """python -m dsen2_b200.supres_train on a tiny synthetic data set laid out like the reference's ../data/."""
+@pytest.mark.parametrize('deep', [False, True])
+def test_supres_train_cli_trains_and_predicts(env, tmp_path, deep):
+    """python -m dsen2_b200.supres_train [--deep] on a tiny synthetic data set laid out like the reference's ../data/."""
     import json
     from dsen2_b200 import supres_train
     rng = np.random.RandomState(3)
@@ -233,7 +241,8 @@ def test_supres_train_cli_trains_and_predicts(env, tmp_path):
     np.save(d / 'data20_gt.npy', (x20 + 50 * rng.randn(*x20.shape)).astype(np.float32))
     val = np.zeros(16, bool); val[::4] = True
     np.save(tmp_path / 'train' / 'val_index.npy', val)
-    assert supres_train.main(['--path', root, '--epochs', '2']) == 0
+    flags = ['--deep'] if deep else []
+    assert supres_train.main(['--path', root, '--epochs', '2'] + flags) == 0
     ck = root + 'network_data/' + supres_train.model_nr + 'lr_1e-04.hdf5'
     import os
     assert os.path.exists(ck) and 'Finished epoch' in open(root + 'network_data/' + supres_train.model_nr + '_lr_1.0e-04.txt').read()
@@ -241,7 +250,7 @@ def test_supres_train_cli_trains_and_predicts(env, tmp_path):
     t.mkdir(parents=True)
     np.save(t / 'data10.npy', x10[:4]); np.save(t / 'data20.npy', x20[:4])
     json.dump([0, 0, 48, 48], open(t / 'roi.json', 'w'))
-    assert supres_train.main(['--path', root, '--predict', ck]) == 0
+    assert supres_train.main(['--path', root, '--predict', ck] + flags) == 0
     out = np.load(str(t / (ck[-20:-13] + '-predict.npy')))
     assert out.shape == (48, 48, 6) and np.isfinite(out).all()
 
@@ -314,7 +323,7 @@ def test_full_model_checkpoint_resumes_training(env, tmp_path):
     assert sorted(f.keys()) == ['model_weights', 'optimizer_weights']
     names = [bytes(n).decode() for n in f['optimizer_weights'].attrs['weight_names']]
     assert names[0] == 'Nadam/iterations:0' and len(names) == 1 + 2 * 2 * len(model.layer_shapes)
-    assert int(np.asarray(f['optimizer_weights/Nadam/iterations:0'][()])) == 5
+    assert int(np.asarray(f['optimizer_weights/Nadam/iterations:0'][()]).reshape(-1)[0]) == 5
     k0 = model.get_weights()[0]
     assert f['optimizer_weights/training/Nadam/m_0:0'].shape == (k0.size,)
     for _ in range(4):
@@ -347,3 +356,22 @@ def model_schedule(t, opt=None):
     for i in range(1, t + 1):
         prod = nadam_schedule(i, prod, opt)['sched_new']
     return prod
+
+
+def test_vdsen2_training_step_at_depth_32(env):
+    """supres_train.py:129-131 (--deep): 32 resBlocks x 256 features, batch size 8.  The step runs, the loss follows the
+    fp32 oracle and decreases; predict() afterwards sees the trained weights."""
+    torch, _capi, lib = env
+    from dsen2_b200.train import Nadam
+    from oracle import train_oracle as to
+    model, ws, xs, y = _setup(L=32, n=8, P=32, F=256)
+    model.compile(optimizer=Nadam(lr=1e-4), loss='mean_absolute_error', metrics=['mean_squared_error'])
+    losses = [model.train_on_batch(xs, y)[0] for _ in range(6)]
+    with torch.no_grad():                             # the oracle's forward pass only (66 layers x 256 features on the CPU)
+        pred = to.forward([torch.from_numpy(a) for a in xs], to._params([(ws[2 * i], ws[2 * i + 1]) for i in range(len(ws) // 2)]))
+    ref_loss = float((pred - torch.from_numpy(y)).abs().mean())
+    assert np.isfinite(losses).all()
+    assert abs(losses[0] - ref_loss) <= 5e-3 * ref_loss
+    assert losses[-1] < losses[0]
+    pred = model.predict(xs)
+    assert abs(np.abs(pred - y).mean() - model.train_on_batch(xs, y)[0]) < 5e-3

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_capi.SIGNATURES), declared ^ set(_capi.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.dsen2_abi_version() == 2
+    assert lib.dsen2_abi_version() == 3
 
 
 def test_patch_counts_match_reference_arithmetic():

@@ -8,6 +8,7 @@ run 29511 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench_n$N.j
 run 29512 --workload train > gpurun_out/${TAG}_bench_train_n$N.json 2> gpurun_out/${TAG}_bench_train_n$N.err; echo "train n=$N rc=$?"
 if [ -n "$VD" ]; then
   run 29513 --model vdsen2 --steps 2 --warmup 2 --no-cpu-baseline > gpurun_out/${TAG}_bench_vdsen2_n$N.json 2> gpurun_out/${TAG}_bench_vdsen2_n$N.err; echo "vdsen2 n=$N rc=$?"
+  run 29514 --workload train --model vdsen2 > gpurun_out/${TAG}_bench_train_vdsen2_n$N.json 2> gpurun_out/${TAG}_bench_train_vdsen2_n$N.err; echo "train vdsen2 n=$N rc=$?"
 fi
 python - <<PY
 import json, glob

@@ -480,11 +480,15 @@ def run_train(args):
                              "achieved": flop / ms / 1e9, "peak": pk['tf_burst'], "unit": "TFLOP/s",
                              "frac": flop / ms / 1e9 / pk['tf_burst'], "traffic": None,
                              "peak_source": pk['source'] + ", burst figure (millisecond-scale step)"},
-                "kernel_shares_ncu": None if deep else {
-                    "note": "CONSTANTS from an ncu gpu__time_duration launch list of this workload (profiles/"
-                            "r02_train_launch_list.txt), not measured in this run",
-                    "forward + backward-data convolutions (conv_pair_kernel)": 0.53, "weight gradients (wgrad_direct_kernel)": 0.26,
-                    "bias gradients (colsum_nhwc_kernel)": 0.086, "operand repacking": 0.064, "loss, Nadam, layout, fills": 0.06},
+                "kernel_shares_ncu": dict(
+                    {"note": "CONSTANTS from an ncu gpu__time_duration launch list of this workload (profiles/%s), not measured "
+                             "in this run" % ("r02_train_vdsen2_launch_list.txt" if deep else "r02_train_launch_list.txt")},
+                    **({"forward + backward-data convolutions (conv_pair_kernel, conv_tail_swapped_kernel)": 0.648,
+                        "weight + bias gradients (wgrad_direct_kernel)": 0.273, "Nadam": 0.038, "operand repacking": 0.024,
+                        "loss, layout, fills": 0.017} if deep else
+                       {"forward + backward-data convolutions (conv_pair_kernel)": 0.615,
+                        "weight + bias gradients (wgrad_direct_kernel)": 0.316, "Nadam": 0.006, "operand repacking": 0.012,
+                        "loss, layout, fills": 0.051})),
                 "allreduce": {"us": allreduce_us, "bytes": int(tr.grads.numel()) * 4, "algo": "NCCL all_reduce(SUM), one bucket, "
                               "between the gradient graph and the update graph"} if world > 1 else None,
                 "last_loss": losses[-1] if losses else None}

@@ -60,8 +60,7 @@ SIGNATURES = {
     "dsen2_nchw_to_nhwc_f16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                        c_void_p, c_void_p]),
     "dsen2_relu_mask": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p]),
-    "dsen2_colsum_nhwc": (c_int, [c_void_p, c_longlong, c_int, c_float, c_void_p, c_void_p]),
-    "dsen2_wgrad_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
+    "dsen2_wgrad_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "dsen2_mae_grad": (c_int, [c_void_p, c_void_p, c_longlong, c_float, c_void_p, c_void_p, c_void_p]),
     "dsen2_nadam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong] + [c_float] * 10 + [c_void_p]),
     "dsen2_nadam_step_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p]),

@@ -6,7 +6,8 @@
 //   weight gradients     = dsen2_wgrad_nhwc: a tcgen05 GEMM over the pixel dimension straight from the NHWC tensors,
 //                              dW[tap][ci][co] = sum_px X[px + off(tap)][ci] * dY[px][co]
 //                          (MN-major operands, see wgrad_direct_kernel);
-//   the rest             = layout changes, bias gradients (column sums), MAE loss + gradient, Keras-2 Nadam.
+//   bias gradients       = column sums of dY, taken inside the weight-gradient kernel from the tiles it stages;
+//   the rest             = layout changes, MAE loss + gradient, Keras-2 Nadam.
 // Gradients flow in fp16 with a power-of-two loss scale chosen by the host so that d(pred) = +-2^-4 exactly.
 #include <stdlib.h>
 
@@ -58,38 +59,6 @@ __global__ void relu_mask_kernel(const uint4* __restrict__ in, const uint4* __re
   }
 }
 
-// out[c] += scale * sum_pixels in[pixel][c]   (bias gradients from an NHWC fp16 gradient tensor, C = 128 or 256)
-// 256 threads = 16 pixel lanes x 16 chunks of 8 channels (one 16-byte load each); blockIdx.y = group of 128 channels;
-// block partials -> atomics
-__global__ void colsum_nhwc_kernel(const __half* __restrict__ in, long long npix, int C, float scale, float* __restrict__ out) {
-  const int chunk = threadIdx.x & 15, pl = threadIdx.x >> 4;
-  in += blockIdx.y * 128;
-  out += blockIdx.y * 128;
-  float acc[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  for (long long p = (long long)blockIdx.x * 16 + pl; p < npix; p += (long long)gridDim.x * 16) {
-    const uint4 q = *reinterpret_cast<const uint4*>(in + p * C + chunk * 8);
-    const __half2* h = reinterpret_cast<const __half2*>(&q);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = __half22float2(h[j]);
-      acc[2 * j] += f.x;
-      acc[2 * j + 1] += f.y;
-    }
-  }
-  __shared__ float red[16][129];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) red[pl][chunk * 8 + j] = acc[j];
-  __syncthreads();
-  if (threadIdx.x < 128) {
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) s += red[i][threadIdx.x];
-    atomicAdd(out + threadIdx.x, s * scale);
-  }
-}
-
 // ------------------------------------------------------------------------------------------ //
 // loss (mean_absolute_error, metric mean_squared_error; supres_train.py:144)
 // ------------------------------------------------------------------------------------------ //
@@ -122,43 +91,50 @@ __global__ void mae_grad_kernel(const float* __restrict__ pred, const float* __r
 // ------------------------------------------------------------------------------------------ //
 // Keras-2 Nadam (supres_train.py:137-141); the schedule scalars are computed on the host
 // ------------------------------------------------------------------------------------------ //
-__global__ void nadam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                             float* __restrict__ v, long long total, float gmul, float lr, float beta1, float beta2,
-                             float eps, float mu_t, float mu_next, float sched_new, float sched_next, float bias2) {
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const float gr = g[idx] * gmul;
-    const float g_prime = gr / (1.f - sched_new);
-    const float m_t = beta1 * m[idx] + (1.f - beta1) * gr;
-    const float m_prime = m_t / (1.f - sched_next);
-    const float v_t = beta2 * v[idx] + (1.f - beta2) * gr * gr;
-    const float v_prime = v_t / bias2;
-    const float m_bar = (1.f - mu_t) * g_prime + mu_next * m_prime;
-    p[idx] = p[idx] - lr * m_bar / (sqrtf(v_prime) + eps);
-    m[idx] = m_t;
-    v[idx] = v_t;
-  }
+struct NadamHp { float gmul, lr, beta1, beta2, eps, mu_t, mu_next, sched_new, sched_next, bias2; };
+
+__device__ __forceinline__ void nadam_element(float& p, float g, float& m, float& v, const NadamHp& h) {
+  const float gr = g * h.gmul;
+  const float g_prime = gr / (1.f - h.sched_new);
+  const float m_t = h.beta1 * m + (1.f - h.beta1) * gr;
+  const float m_prime = m_t / (1.f - h.sched_next);
+  const float v_t = h.beta2 * v + (1.f - h.beta2) * gr * gr;
+  const float v_prime = v_t / h.bias2;
+  const float m_bar = (1.f - h.mu_t) * g_prime + h.mu_next * m_prime;
+  p = p - h.lr * m_bar / (sqrtf(v_prime) + h.eps);
+  m = m_t;
+  v = v_t;
 }
 
-// same update with the step-dependent scalars read from device memory, so that a captured CUDA graph of the whole
-// training step can be replayed: hp = {grad_mul, lr, beta1, beta2, eps, mu_t, mu_next, sched_new, sched_next, bias2}
+// 28 bytes of traffic per parameter (VDSen2: 37.8 M parameters, 1.06 GB per step): 128-bit accesses, scalar tail
+__device__ __forceinline__ void nadam_sweep(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                            float* __restrict__ v, long long total, const NadamHp& h) {
+  const long long t4 = total >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < t4; i += (long long)gridDim.x * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i], mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    nadam_element(pp.x, gg.x, mm.x, vv.x, h);
+    nadam_element(pp.y, gg.y, mm.y, vv.y, h);
+    nadam_element(pp.z, gg.z, mm.z, vv.z, h);
+    nadam_element(pp.w, gg.w, mm.w, vv.w, h);
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  const long long idx = (t4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx < total) nadam_element(p[idx], g[idx], m[idx], v[idx], h);
+}
+
+__global__ void nadam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, long long total, NadamHp h) {
+  nadam_sweep(p, g, m, v, total, h);
+}
+
+// the same update with the step-dependent scalars read from device memory (CUDA-graph replay)
 __global__ void nadam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                  float* __restrict__ v, long long total, const float* __restrict__ hp) {
-  const float gmul = hp[0], lr = hp[1], beta1 = hp[2], beta2 = hp[3], eps = hp[4], mu_t = hp[5], mu_next = hp[6],
-              sched_new = hp[7], sched_next = hp[8], bias2 = hp[9];
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const float gr = g[idx] * gmul;
-    const float g_prime = gr / (1.f - sched_new);
-    const float m_t = beta1 * m[idx] + (1.f - beta1) * gr;
-    const float m_prime = m_t / (1.f - sched_next);
-    const float v_t = beta2 * v[idx] + (1.f - beta2) * gr * gr;
-    const float v_prime = v_t / bias2;
-    const float m_bar = (1.f - mu_t) * g_prime + mu_next * m_prime;
-    p[idx] = p[idx] - lr * m_bar / (sqrtf(v_prime) + eps);
-    m[idx] = m_t;
-    v[idx] = v_t;
-  }
+  const NadamHp h = {hp[0], hp[1], hp[2], hp[3], hp[4], hp[5], hp[6], hp[7], hp[8], hp[9]};
+  nadam_sweep(p, g, m, v, total, h);
 }
 
 // dgrad weights: the backward-data convolution is a forward convolution of dY with the taps flipped and the channel
@@ -180,20 +156,30 @@ __global__ void pack_dgrad_weights_kernel(const float* __restrict__ hwio, int ci
 // forward operand fwd[l][t][o][i] = f16(w[t][i][o]) and backward-data operand bwd[l][t][i][o] = f16(s_l * w[8-t][i][o]),
 // s_l = scale_second for the second convolution of a resBlock (odd l), 1 otherwise.  Same arithmetic as
 // pack_weights_kernel / pack_dgrad_weights_kernel, 2 * layers - 1 launches fewer per training step.
-__global__ void pack_trunk_layers_kernel(const float* __restrict__ params, long long layer_stride, int F, float scale_second,
-                                         __half* __restrict__ fwd, __half* __restrict__ bwd) {
-  const int l = blockIdx.y;
-  const float* w = params + (long long)l * layer_stride;
-  const long long per = 9LL * F * F;
+// One block = one 32 x 32 tile of one (layer, tap) matrix w[i][o]: read once (coalesced along o), written straight to bwd
+// (same orientation) and, transposed through shared memory, to fwd (coalesced along i; 256 features: 37.7 M elements per
+// step).
+__global__ void __launch_bounds__(256)
+pack_trunk_layers_kernel(const float* __restrict__ params, long long layer_stride, int F, float scale_second,
+                         __half* __restrict__ fwd, __half* __restrict__ bwd) {
+  __shared__ float tile[32][33];
+  const int l = blockIdx.z, t = blockIdx.y;
+  const int tiles = F / 32;
+  const int i0 = (int)(blockIdx.x / tiles) * 32, o0 = (int)(blockIdx.x % tiles) * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* w = params + (long long)l * layer_stride + (long long)t * F * F;          // w[t][i][o]
   const float sc = (l & 1) ? scale_second : 1.0f;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < per; idx += (long long)gridDim.x * blockDim.x) {
-    const int o = (int)(idx % F);
-    const int i = (int)((idx / F) % F);
-    const int t = (int)(idx / ((long long)F * F));
-    const float v = w[idx];                                              // w[t][i][o]
-    fwd[l * per + ((long long)t * F + o) * F + i] = __float2half_rn(v);
-    bwd[l * per + ((long long)(8 - t) * F + i) * F + o] = __float2half_rn(sc * v);
+  __half* f = fwd + ((long long)l * 9 + t) * F * F;
+  __half* b = bwd + ((long long)l * 9 + (8 - t)) * F * F;
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const float v = w[(long long)(i0 + r) * F + o0 + tx];
+    tile[r][tx] = v;
+    b[(long long)(i0 + r) * F + o0 + tx] = __float2half_rn(sc * v);
   }
+  __syncthreads();
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) f[(long long)(o0 + r) * F + i0 + tx] = __float2half_rn(tile[tx][r]);
 }
 
 struct TileXY3 { int b, ty, tx; };
@@ -221,7 +207,8 @@ static constexpr int kWdStages = 3;
 
 __global__ void __launch_bounds__(kWdThreads, 1)
 wgrad_direct_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_dy, int tiles_x,
-                    int tiles_y, int num_tiles, int tiles_per_split, int C, float scale, float* __restrict__ dw) {
+                    int tiles_y, int num_tiles, int tiles_per_split, int C, float scale, float* __restrict__ dw,
+                    float* __restrict__ db) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + kWdStages * kWdStage);
@@ -232,6 +219,12 @@ wgrad_direct_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
   const int dy = blockIdx.y;                                   // vertical tap 0..2
   // 256 features: blockIdx.z = (block of 128 input channels, block of 128 output channels) of the (C, C) gradient
   const int ci0 = (int)(blockIdx.z / (C / 128)) * 128, co0 = (int)(blockIdx.z % (C / 128)) * 128;
+  // bias gradient db[co] += scale * sum_px dY[px][co]: the four drain warps (idle until the last MMA) sum the dY tiles the
+  // CTA stages anyway -- no separate pass over dY.  The 3 * C/128 CTAs that stage the same dY tile (vertical taps x
+  // input-channel blocks) take every (3 * C/128)-th pixel row each: the MMAs keep the shared-memory port busy, and one CTA
+  // reading whole tiles became the straggler of the grid (measured: slower than the separate kernel).
+  const bool colsum = db != nullptr;
+  const int nshare = 3 * (C / 128), share = dy * (C / 128) + ci0 / 128;
   const int t0 = blockIdx.x * tiles_per_split;
   const int t1 = min(num_tiles, t0 + tiles_per_split);
   const int nt = t1 - t0;
@@ -239,7 +232,7 @@ wgrad_direct_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_dy);
-    for (int i = 0; i < kWdStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < kWdStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], colsum ? 5 : 1); }
     mbar_init(done, 1);
     mbar_fence_init();
   }
@@ -290,6 +283,35 @@ wgrad_direct_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     // drain: accumulator dx (128 ci x 128 co fp32) -> smem (row-major, 64 KB, reusing the pipeline stages) -> bulk add
     const int wq = warp & 3;
     const int row = wq * 32 + lane;              // ci
+    if (colsum) {
+      // thread = one channel pair (4 bytes of the 128-byte pixel row; a warp reads one whole row per instruction) and one
+      // half of this CTA's share of the tile's 128 pixels; the tile is SWIZZLE_128B: 16-byte chunk index ^ (pixel row & 7)
+      const int t = (int)threadIdx.x - 64, pair = t & 63, ph = t >> 6;
+      const uint32_t off = (uint32_t)((pair >> 5) * kWdYBox + 2 * kWdXBox + (pair & 3) * 4);
+      const int chunk = (pair & 31) >> 2;
+      float sx = 0.f, sy = 0.f;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < nt; ++i) {
+        mbar_wait(&full[stage], phase);
+        const uint8_t* base = smem + stage * kWdStage + off;
+#pragma unroll 4
+        for (int r = ph * 64 + share; r < ph * 64 + 64; r += nshare) {
+          const __half2 h = *reinterpret_cast<const __half2*>(base + r * 128 + ((chunk ^ (r & 7)) << 4));
+          const float2 f = __half22float2(h);
+          sx += f.x;
+          sy += f.y;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        if (++stage == kWdStages) { stage = 0; phase ^= 1; }
+      }
+      float* d = db + co0 + (pair >> 5) * 64 + (pair & 31) * 2;
+      atomicAdd(d, sx * scale);
+      atomicAdd(d + 1, sy * scale);
+      // the drain below overwrites the pipeline stages: wait until all four warps have read their last dY tile
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     mbar_wait(done, 0);
     tc_fence_after();
 #pragma unroll 1
@@ -333,7 +355,7 @@ wgrad_direct_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
 using namespace dsen2;
 
 extern "C" int dsen2_wgrad_nhwc(const void* d_x, const void* d_dy, int n, int H, int W, int channels, float scale, float* d_dw,
-                                void* stream) {
+                                float* d_db, void* stream) {
   DSEN2_REQUIRE(d_x && d_dy && d_dw, DSEN2_E_BADARG, "dsen2_wgrad_nhwc: null pointer");
   DSEN2_REQUIRE(n > 0 && H > 0 && W > 0, DSEN2_E_BADARG, "dsen2_wgrad_nhwc: bad shape");
   DSEN2_REQUIRE(channels == 128 || channels == 256, DSEN2_E_BADARG, "dsen2_wgrad_nhwc: 128 or 256 channels (got %d)", channels);
@@ -365,7 +387,7 @@ extern "C" int dsen2_wgrad_nhwc(const void* d_x, const void* d_dy, int n, int H,
     DSEN2_CUDA(cudaFuncSetAttribute(wgrad_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
   }
   wgrad_direct_kernel<<<dim3(splits, 3, blocks), kWdThreads, SMEM, (cudaStream_t)stream>>>(tx, ty, tiles_x, tiles_y, (int)tiles,
-                                                                                         per, channels, scale, d_dw);
+                                                                                         per, channels, scale, d_dw, d_db);
   return check_launch("wgrad_direct_kernel");
 }
 
@@ -389,17 +411,6 @@ extern "C" int dsen2_relu_mask(const void* d_in, const void* d_act, long long to
   return check_launch("relu_mask");
 }
 
-extern "C" int dsen2_colsum_nhwc(const void* d_in, long long npix, int channels, float scale, float* d_out, void* stream) {
-  DSEN2_REQUIRE(d_in && d_out && npix > 0, DSEN2_E_BADARG, "dsen2_colsum_nhwc: bad arguments");
-  DSEN2_REQUIRE(channels == 128 || channels == 256, DSEN2_E_BADARG, "dsen2_colsum_nhwc: 128 or 256 channels (got %d)", channels);
-  long long blocks = (npix + 15) / 16;
-  const long long cap = (long long)sm_count() * 2;
-  if (blocks > cap) blocks = cap;
-  colsum_nhwc_kernel<<<dim3((unsigned)blocks, channels / 128), 256, 0, (cudaStream_t)stream>>>((const __half*)d_in, npix, channels,
-                                                                                              scale, d_out);
-  return check_launch("colsum_nhwc");
-}
-
 extern "C" int dsen2_mae_grad(const float* d_pred, const float* d_y, long long total, float gscale, float* d_dpred,
                               double* d_sums, void* stream) {
   DSEN2_REQUIRE(d_pred && d_y && d_dpred && d_sums && total > 0, DSEN2_E_BADARG, "dsen2_mae_grad: bad arguments");
@@ -407,19 +418,28 @@ extern "C" int dsen2_mae_grad(const float* d_pred, const float* d_y, long long t
   return check_launch("mae_grad");
 }
 
+static long long nadam_blocks(long long total) {
+  const long long want = ((total >> 2) + 255) / 256, cap = (long long)sm_count() * 8;
+  return want < 1 ? 1 : (want < cap ? want : cap);
+}
+
 extern "C" int dsen2_nadam_step(float* d_p, const float* d_g, float* d_m, float* d_v, long long total, float grad_mul,
                                 float lr, float beta1, float beta2, float eps, float mu_t, float mu_next,
                                 float sched_new, float sched_next, float bias2, void* stream) {
   DSEN2_REQUIRE(d_p && d_g && d_m && d_v && total > 0, DSEN2_E_BADARG, "dsen2_nadam_step: bad arguments");
-  nadam_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d_p, d_g, d_m, d_v, total, grad_mul, lr, beta1, beta2,
-                                                                      eps, mu_t, mu_next, sched_new, sched_next, bias2);
+  DSEN2_REQUIRE(((uintptr_t)d_p % 16) == 0 && ((uintptr_t)d_g % 16) == 0 && ((uintptr_t)d_m % 16) == 0 && ((uintptr_t)d_v % 16) == 0,
+                DSEN2_E_ALIGN, "dsen2_nadam_step: pointers must be 16-byte aligned");
+  const NadamHp h = {grad_mul, lr, beta1, beta2, eps, mu_t, mu_next, sched_new, sched_next, bias2};
+  nadam_kernel<<<(unsigned)nadam_blocks(total), 256, 0, (cudaStream_t)stream>>>(d_p, d_g, d_m, d_v, total, h);
   return check_launch("nadam_step");
 }
 
 extern "C" int dsen2_nadam_step_dev(float* d_p, const float* d_g, float* d_m, float* d_v, long long total,
                                     const float* d_hp, void* stream) {
   DSEN2_REQUIRE(d_p && d_g && d_m && d_v && d_hp && total > 0, DSEN2_E_BADARG, "dsen2_nadam_step_dev: bad arguments");
-  nadam_dev_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d_p, d_g, d_m, d_v, total, d_hp);
+  DSEN2_REQUIRE(((uintptr_t)d_p % 16) == 0 && ((uintptr_t)d_g % 16) == 0 && ((uintptr_t)d_m % 16) == 0 && ((uintptr_t)d_v % 16) == 0,
+                DSEN2_E_ALIGN, "dsen2_nadam_step_dev: pointers must be 16-byte aligned");
+  nadam_dev_kernel<<<(unsigned)nadam_blocks(total), 256, 0, (cudaStream_t)stream>>>(d_p, d_g, d_m, d_v, total, d_hp);
   return check_launch("nadam_step_dev");
 }
 
@@ -441,8 +461,8 @@ extern "C" int dsen2_pack_trunk_layers(const float* d_first_kernel, long long la
                     layer_stride >= 9LL * feature_size * feature_size,
                 DSEN2_E_BADARG, "dsen2_pack_trunk_layers: bad arguments");
   if (num_layers == 0) return 0;
-  const long long per = 9LL * feature_size * feature_size;
-  const dim3 grid((unsigned)((per + 255) / 256 < 1024 ? (per + 255) / 256 : 1024), (unsigned)num_layers);
+  const int tiles = feature_size / 32;
+  const dim3 grid((unsigned)(tiles * tiles), 9, (unsigned)num_layers);
   pack_trunk_layers_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_first_kernel, layer_stride, feature_size, scale_second,
                                                                    (__half*)d_fwd, (__half*)d_bwd);
   return check_launch("pack_trunk_layers");

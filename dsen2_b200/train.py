@@ -347,29 +347,24 @@ class Trainer:
             nl = 2 * L + 2
             npix = n * P * P
 
-            def wgrad(x_nhwc, dy_nhwc, scale, out):     # out (9,F,F) fp32 += scale * sum_px X[px+tap] (x) dY[px]
-                _capi.check(lib.dsen2_wgrad_nhwc(ptr(x_nhwc), ptr(dy_nhwc), n, P, P, F, scale, ptr(out), st), "wgrad")
-
-            def bgrad(dy_nhwc, scale, out):             # out (F,) fp32 += scale * sum_px dY[px]
-                _capi.check(lib.dsen2_colsum_nhwc(ptr(dy_nhwc), npix, F, scale, ptr(out), st), "bias grad")
+            def wgrad(x_nhwc, dy_nhwc, scale, out_w, out_b):
+                # out_w (9,F,F) fp32 += scale * sum_px X[px+tap] (x) dY[px];  out_b (F,) fp32 += scale * sum_px dY[px]
+                _capi.check(lib.dsen2_wgrad_nhwc(ptr(x_nhwc), ptr(dy_nhwc), n, P, P, F, scale, ptr(out_w), ptr(out_b), st), "wgrad")
 
             # ---- last layer: Conv2D(cout) (DSen2Net.py:35); the Add of the global skip passes the gradient through
             _capi.check(lib.dsen2_nchw_to_nhwc_f16(ptr(b['dpred']), self.cout, None, 0, None, 0, n, P, P, F, ptr(b['dy_nhwc']), st),
                         "dpred nhwc")
-            wgrad(b['x_hi'][L], b['dy_nhwc'], inv, self.gw_tail)
-            bgrad(b['dy_nhwc'], inv, self.gb_tail)
+            wgrad(b['x_hi'][L], b['dy_nhwc'], inv, self.gw_tail, self.gb_tail)
             b['dx32'].zero_()
             _capi.check(lib.dsen2_conv_res32(ptr(b['dy_nhwc']), ptr(self.w_bwd[-1]), ptr(self.zero_bias), n, P, P, F, 1.0,
                                              ptr(b['dx32']), ptr(b['dx_hi']), None, st), "dgrad tail")
             # ---- resBlocks, last to first (DSen2Net.py:9-15)
             for l in range(L - 1, -1, -1):
                 i1, i2 = 1 + 2 * l, 2 + 2 * l
-                wgrad(b['t'][l], b['dx_hi'], 0.1 * inv, self.kernel(i2, self.grads))       # d x_{l+1} -> conv2 (x 0.1)
-                bgrad(b['dx_hi'], 0.1 * inv, self.bias(i2, self.grads))
+                wgrad(b['t'][l], b['dx_hi'], 0.1 * inv, self.kernel(i2, self.grads), self.bias(i2, self.grads))   # conv2 (x 0.1)
                 _capi.check(lib.dsen2_conv_relu_bwd(ptr(b['dx_hi']), ptr(self.w_bwd[i2]), ptr(self.zero_bias), ptr(b['t'][l]),
                                                     n, P, P, F, ptr(b['g2']), st), "dgrad conv2 + relu")
-                wgrad(b['x_hi'][l], b['g2'], inv, self.kernel(i1, self.grads))
-                bgrad(b['g2'], inv, self.bias(i1, self.grads))
+                wgrad(b['x_hi'][l], b['g2'], inv, self.kernel(i1, self.grads), self.bias(i1, self.grads))
                 _capi.check(lib.dsen2_conv_res32(ptr(b['g2']), ptr(self.w_bwd[i1]), ptr(self.zero_bias), n, P, P, F, 1.0,
                                                  ptr(b['dx32']), ptr(b['dx_hi']), None, st), "dgrad conv1 + skip")
             # ---- first layer: Conv2D(F, relu) on the concatenated inputs (DSen2Net.py:24-29)
@@ -377,8 +372,7 @@ class Trainer:
             x2, c2 = (xs[2], self.model.in_channels[2]) if len(xs) == 3 else (None, 0)
             _capi.check(lib.dsen2_nchw_to_nhwc_f16(ptr(xs[0]), self.model.in_channels[0], ptr(xs[1]), self.model.in_channels[1],
                                                    ptr(x2), c2, n, P, P, F, ptr(b['dy_nhwc']), st), "input nhwc")
-            wgrad(b['dy_nhwc'], b['g2'], inv, self.gw_head)
-            bgrad(b['g2'], inv, self.bias(0, self.grads))
+            wgrad(b['dy_nhwc'], b['g2'], inv, self.gw_head, self.bias(0, self.grads))
             self.kernel(0, self.grads).view(9, self.ctot, F).copy_(self.gw_head[:, :self.ctot, :])
             self.kernel(nl - 1, self.grads).view(9, F, self.cout).copy_(self.gw_tail[:, :, :self.cout])
             self.bias(nl - 1, self.grads).copy_(self.gb_tail[:self.cout])
@@ -417,8 +411,8 @@ class Trainer:
         self.repack()
 
     def launches_per_step(self):
-        """Kernels of THIS library per step: forward, loss, backward (dgrad + wgrad + bias grads), Nadam, repacking."""
+        """Kernels of THIS library per step: forward, loss, backward (dgrad + wgrad with the bias gradients), Nadam, repacking."""
         L = self.L
         fwd = 1 + 1 + 2 * L + 1
-        bwd = 1 + 1 + 3 + L * 6 + 4
+        bwd = 1 + 1 + 2 + L * 4 + 3
         return fwd + bwd + 1 + 3 + (1 if L > 0 else 0)        # ... Nadam, first / last layer operand packing, one launch for the trunk

@@ -262,13 +262,12 @@ int dsen2_nchw_to_nhwc_f16(const float* d_x0, int c0, const float* d_x1, int c1,
                            int n, int H, int W, int cpad, void* d_out, void* stream);
 /* d_out = d_in where d_act > 0, else 0 (NHWC fp16, `total` elements, multiple of 8) */
 int dsen2_relu_mask(const void* d_in, const void* d_act, long long total, void* d_out, void* stream);
-/* d_out[c] += scale * sum over pixels of d_in[pixel][c]  (NHWC fp16, channels = 128 or 256; bias gradients) */
-int dsen2_colsum_nhwc(const void* d_in, long long npix, int channels, float scale, float* d_out, void* stream);
 /* Weight gradient straight from the NHWC fp16 tensors (C = channels = 128 or 256 each), MN-major tcgen05 operands:
  * d_dw (9,C,C) fp32 += scale * sum_px X[px + tap][ci] * dY[px][co]   (HWIO order; one CTA per vertical tap, pixel
- * slice and 128 x 128 block of the gradient).                                                               */
+ * slice and 128 x 128 block of the gradient).  d_db (optional, C floats): the bias gradient of the same layer,
+ * d_db[co] += scale * sum_px dY[px][co], summed from the dY tiles the kernel stages anyway.                    */
 int dsen2_wgrad_nhwc(const void* d_x, const void* d_dy, int n, int H, int W, int channels, float scale, float* d_dw,
-                     void* stream);
+                     float* d_db, void* stream);
 
 /* mean_absolute_error: d_dpred = gscale * sign(pred - y); d_sums[0] += sum|pred-y|, d_sums[1] += sum (pred-y)^2 */
 int dsen2_mae_grad(const float* d_pred, const float* d_y, long long total, float gscale, float* d_dpred,

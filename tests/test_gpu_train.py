@@ -44,14 +44,22 @@ def test_wgrad_nhwc_mn_major(env, shape):
     dy = (rng.randn(n, H, W, C) * 0.1).astype(np.float16)
     tx, tdy = torch.from_numpy(x).cuda(), torch.from_numpy(dy).cuda()
     dw = torch.full((9, C, C), 1.0, device='cuda')                          # accumulates on top of what is there
-    _capi.check(lib.dsen2_wgrad_nhwc(_capi.ptr(tx), _capi.ptr(tdy), n, H, W, C, 0.5, _capi.ptr(dw), _capi.stream_ptr()), 'wgrad nhwc')
+    db = torch.full((C,), 2.0, device='cuda')                               # ... and so does the fused bias gradient
+    _capi.check(lib.dsen2_wgrad_nhwc(_capi.ptr(tx), _capi.ptr(tdy), n, H, W, C, 0.5, _capi.ptr(dw), _capi.ptr(db),
+                                     _capi.stream_ptr()), 'wgrad nhwc')
+    dw2 = torch.full((9, C, C), 1.0, device='cuda')
+    _capi.check(lib.dsen2_wgrad_nhwc(_capi.ptr(tx), _capi.ptr(tdy), n, H, W, C, 0.5, _capi.ptr(dw2), None, _capi.stream_ptr()),
+                'wgrad nhwc, no bias gradient')
     torch.cuda.synchronize()
     ref = 1.0 + 0.5 * _wgrad_ref(x.astype(np.float64), dy)
-    np.testing.assert_allclose(dw.cpu().numpy(), ref, rtol=1e-3, atol=1e-3 * np.abs(ref).max())
+    for got in (dw, dw2):
+        np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=1e-3, atol=1e-3 * np.abs(ref).max())
+    ref_b = 2.0 + 0.5 * dy.astype(np.float64).reshape(-1, C).sum(0)
+    np.testing.assert_allclose(db.cpu().numpy(), ref_b, rtol=1e-4, atol=1e-4 * max(1.0, np.abs(ref_b).max()))
 
 
 @pytest.mark.parametrize('C', [128, 256])
-def test_relu_mask_and_colsum(env, C):
+def test_relu_mask(env, C):
     torch, _capi, lib = env
     rng = np.random.RandomState(2)
     g = rng.randn(3, 16, 8, C).astype(np.float16)
@@ -59,11 +67,8 @@ def test_relu_mask_and_colsum(env, C):
     tg, ta = torch.from_numpy(g).cuda(), torch.from_numpy(a).cuda()
     out = torch.empty_like(tg)
     _capi.check(lib.dsen2_relu_mask(_capi.ptr(tg), _capi.ptr(ta), g.size, _capi.ptr(out), _capi.stream_ptr()), 'mask')
-    cs = torch.full((C,), 2.0, device='cuda')
-    _capi.check(lib.dsen2_colsum_nhwc(_capi.ptr(tg), 3 * 16 * 8, C, 0.25, _capi.ptr(cs), _capi.stream_ptr()), 'colsum')
     torch.cuda.synchronize()
     assert np.array_equal(out.cpu().numpy().view(np.uint16), np.where(a.astype(np.float32) > 0, g, np.float16(0)).view(np.uint16))
-    np.testing.assert_allclose(cs.cpu().numpy(), 2.0 + 0.25 * g.astype(np.float64).reshape(-1, C).sum(0), rtol=1e-4, atol=1e-4)
 
 
 @pytest.mark.parametrize('C', [128, 256])
@@ -91,6 +96,28 @@ def test_conv_relu_bwd_is_the_transposed_convolution(env, C):
     g = F.conv_transpose2d(torch.from_numpy(dy.astype(np.float64)).permute(0, 3, 1, 2), wt, padding=1)
     ref = np.where(act.astype(np.float32) > 0, g.permute(0, 2, 3, 1).numpy(), 0)
     np.testing.assert_allclose(out.cpu().numpy().astype(np.float64), ref, rtol=2e-3, atol=2e-3 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize('F', [128, 256])
+def test_pack_trunk_layers_equals_per_layer_packing(env, F):
+    """One launch for all F -> F layers == dsen2_pack_conv_weights / dsen2_pack_dgrad_weights layer by layer (bit-exact)."""
+    torch, _capi, lib = env
+    L = 5
+    rng = np.random.RandomState(F)
+    stride = 9 * F * F + F                                  # kernels lie a kernel + a bias apart in the flat parameter vector
+    flat = torch.from_numpy(rng.randn(L * stride).astype(np.float32)).cuda()
+    fwd = torch.zeros((L, 9, F, F), dtype=torch.float16, device='cuda')
+    bwd = torch.zeros_like(fwd)
+    st = _capi.stream_ptr()
+    _capi.check(lib.dsen2_pack_trunk_layers(_capi.ptr(flat), stride, L, F, 0.1, _capi.ptr(fwd), _capi.ptr(bwd), st), 'pack trunk')
+    one_f = torch.zeros((9, F, F), dtype=torch.float16, device='cuda')
+    one_b = torch.zeros_like(one_f)
+    for l in range(L):
+        k = flat[l * stride:l * stride + 9 * F * F]
+        _capi.check(lib.dsen2_pack_conv_weights(_capi.ptr(k), F, F, F, F, _capi.ptr(one_f), st), 'pack')
+        _capi.check(lib.dsen2_pack_dgrad_weights(_capi.ptr(k), F, F, F, F, 0.1 if l & 1 else 1.0, _capi.ptr(one_b), st), 'pack dgrad')
+        torch.cuda.synchronize()
+        assert torch.equal(fwd[l], one_f) and torch.equal(bwd[l], one_b)
 
 
 def _setup(L=2, n=4, P=32, run_60=False, seed=0, F=128):

@@ -252,7 +252,7 @@ class Trainer:
     # ---- one optimisation step ----------------------------------------------------------------------------------
     def train_step(self, xs, y, apply=True):
         """One optimisation step (see ``_step_body``).  The first call of a batch shape runs eagerly (it also performs the
-        one-time kernel attribute set-up), the second is captured into a CUDA graph (~120 launches, an NCCL all-reduce
+        one-time kernel attribute set-up), the second is captured into a CUDA graph (~65 launches, an NCCL all-reduce
         and the repacking of the weights), later calls copy the batch into the graph's static buffers, upload the ten
         step-dependent Nadam scalars and replay it."""
         torch = self.torch

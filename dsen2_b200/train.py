@@ -82,12 +82,15 @@ def shard_training_set(arrays, label, rank, world):
     return [a[rank:n:world] for a in arrays], label[rank:n:world]
 
 
-def allreduce_gradients(flat, group=None):
-    """Sum the flat gradient over the ranks (NCCL on GPUs, gloo in the CPU tests); returns the world size to divide by."""
+def allreduce_gradients(flat, group=None, async_op=False):
+    """Sum the flat gradient over the ranks (NCCL on GPUs, gloo in the CPU tests); returns the world size to divide by
+    (``async_op``: the pending work handle instead -- the collective then runs beside whatever is launched next)."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()):
-        return 1
+        return None if async_op else 1
     world = dist.get_world_size(group)
+    if async_op:
+        return dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True) if world > 1 else None
     if world > 1:
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     return world
@@ -129,6 +132,11 @@ class Trainer:
         # replay the whole step as one CUDA graph from the third call of a shape on (DSEN2_TRAIN_NO_GRAPH=1: eager, for ncu)
         self.use_graph = not os.environ.get('DSEN2_TRAIN_NO_GRAPH')
         self._graphs, self._calls = {}, {}
+        # Data parallel: the gradient of the LATER layers (the tail of the flat vector; their backward pass runs first) is
+        # all-reduced while the backward pass of the first `split_l` resBlocks and the first layer still runs -- see
+        # `_overlap_allreduce`.  DSEN2_TRAIN_NO_OVERLAP=1 forces the single all-reduce after the whole backward pass.
+        self.split_l = max(1, model.num_layers // 4) if model.num_layers > 0 else 0
+        self.no_overlap = bool(os.environ.get('DSEN2_TRAIN_NO_OVERLAP'))
         # step-dependent Nadam scalars travel through a ring of pinned staging buffers: a slot is rewritten only after the
         # asynchronous upload that last used it has completed (train_step returns without synchronising)
         self.hp_ring = [[torch.zeros(10, dtype=torch.float32).pin_memory(), None] for _ in range(8)]
@@ -274,26 +282,47 @@ class Trainer:
             b['in_y'].copy_(y, non_blocking=True)
             self._advance_schedule(1.0 / self._world())
             multi = self._world() > 1
+            overlap = multi and self._overlap_allreduce(n, P)
             if key not in self._graphs:
-                # one graph on a single GPU; with several ranks the NCCL all-reduce stays an eager call between a
-                # "gradient" graph and an "update" graph (a collective inside the capture deadlocked in testing)
+                # one graph on a single GPU; with several ranks the NCCL all-reduce stays an eager call between
+                # "gradient" graphs and an "update" graph (a collective inside the capture deadlocked in testing)
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    loss, mse = self._step_body(b['in_x'], b['in_y'], not multi, dev_hp=True)
+                    loss, mse = self._step_body(b['in_x'], b['in_y'], not multi, dev_hp=True, part='a' if overlap else None)
                     self.loss_out[0].copy_(loss)
                     self.loss_out[1].copy_(mse)
-                g2 = None
+                gb = g2 = None
+                if overlap:
+                    gb = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gb):
+                        self._step_body(b['in_x'], b['in_y'], False, part='b')
                 if multi:
                     g2 = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g2):
                         self._update_dev()
-                self._graphs[key] = (g, g2)
-            g, g2 = self._graphs[key]
+                self._graphs[key] = (g, gb, g2)
+            g, gb, g2 = self._graphs[key]
             g.replay()
-            if multi:
+            if overlap:
+                off = int(self.offsets[2 * (1 + 2 * self.split_l)])     # first element of resBlock `split_l`'s first kernel
+                late = allreduce_gradients(self.grads[off:], self.group, async_op=True)
+                gb.replay()                                             # ... runs beside the collective
+                early = allreduce_gradients(self.grads[:off], self.group, async_op=True)
+                late.wait()
+                early.wait()
+                g2.replay()
+            elif multi:
                 allreduce_gradients(self.grads, self.group)
                 g2.replay()
             return self.loss_out[0].clone(), self.loss_out[1].clone()
+
+    def _overlap_allreduce(self, n, P):
+        """Two buckets: the all-reduce of the later layers' gradients runs beside the backward pass of the first `split_l`
+        resBlocks and the first layer.  Measured piece by piece on two B200s (tools/gpu_overlap_probe.py): VDSen2, batch 8
+        (64 tiles, half of the SMs idle): the 241 us late all-reduce disappears, the concurrent part of the backward pass
+        slows from 621 to 702 us, step 4.40 -> 4.24 ms; DSen2, batch 128 (a full persistent grid shares its SMs with the
+        collective's CTAs): 62-90 us hidden for 20-30 us of slow-down, step 1.67 -> 1.59 ms."""
+        return not self.no_overlap and self.L > 0
 
     def _update_dev(self):
         """Nadam update with the scalars published in ``hp_dev`` + operand repacking (capturable)."""
@@ -323,43 +352,32 @@ class Trainer:
         slot[1].record()
         return s
 
-    def _step_body(self, xs, y, apply=True, dev_hp=False):
+    def _step_body(self, xs, y, apply=True, dev_hp=False, part=None):
         """xs: list of CUDA float32 (n,C_i,P,P); y: CUDA float32 (n,Cout,P,P).  Returns (loss, mse) device scalars
         of THIS rank's batch (Keras reports the same quantities per batch).  ``apply=False`` stops after the gradient
-        (``self.grads``, flat fp32 in Keras weight order) for inspection."""
+        (``self.grads``, flat fp32 in Keras weight order) for inspection.  ``part``: 'a' = forward, loss and the backward
+        pass down to resBlock ``split_l`` (the later layers' gradients are then final), 'b' = the rest of the backward
+        pass; None = both."""
         torch = self.torch
         lib, ptr = _capi.lib(), _capi.ptr
         n, P = int(xs[0].shape[0]), int(xs[0].shape[2])
         F, L = self.F, self.L
         b = self._buffers(n, P)
+        do_a, do_b = part in (None, 'a'), part in (None, 'b')
+        split = self.split_l if part is not None else 0     # resBlocks >= split belong to part 'a'
+        nl = 2 * L + 2
+        npix = n * P * P
+        total = b['pred'].numel()
+        inv = 1.0 / (self.GSCALE * total)                   # loss scale: d(pred) = GSCALE * sign instead of sign / total
+        loss = mse = None
         with torch.cuda.device(self.dev):
             st = _capi.stream_ptr()
-            pred = self.forward(xs, b, n, P)
-            total = pred.numel()
-            S = self.GSCALE * total                     # loss scale: d(pred) = GSCALE * sign instead of sign / total
-            inv = 1.0 / S
-            self.sums.zero_()
-            self.grads.zero_()
-            self.gw_head.zero_()
-            self.gw_tail.zero_()
-            self.gb_tail.zero_()
-            _capi.check(lib.dsen2_mae_grad(ptr(pred), ptr(y), total, self.GSCALE, ptr(b['dpred']), ptr(self.sums), st), "mae")
-            nl = 2 * L + 2
-            npix = n * P * P
 
             def wgrad(x_nhwc, dy_nhwc, scale, out_w, out_b):
                 # out_w (9,F,F) fp32 += scale * sum_px X[px+tap] (x) dY[px];  out_b (F,) fp32 += scale * sum_px dY[px]
                 _capi.check(lib.dsen2_wgrad_nhwc(ptr(x_nhwc), ptr(dy_nhwc), n, P, P, F, scale, ptr(out_w), ptr(out_b), st), "wgrad")
 
-            # ---- last layer: Conv2D(cout) (DSen2Net.py:35); the Add of the global skip passes the gradient through
-            _capi.check(lib.dsen2_nchw_to_nhwc_f16(ptr(b['dpred']), self.cout, None, 0, None, 0, n, P, P, F, ptr(b['dy_nhwc']), st),
-                        "dpred nhwc")
-            wgrad(b['x_hi'][L], b['dy_nhwc'], inv, self.gw_tail, self.gb_tail)
-            b['dx32'].zero_()
-            _capi.check(lib.dsen2_conv_res32(ptr(b['dy_nhwc']), ptr(self.w_bwd[-1]), ptr(self.zero_bias), n, P, P, F, 1.0,
-                                             ptr(b['dx32']), ptr(b['dx_hi']), None, st), "dgrad tail")
-            # ---- resBlocks, last to first (DSen2Net.py:9-15)
-            for l in range(L - 1, -1, -1):
+            def resblock_bwd(l):                            # DSen2Net.py:9-15, gradient arriving in dx_hi / dx32
                 i1, i2 = 1 + 2 * l, 2 + 2 * l
                 wgrad(b['t'][l], b['dx_hi'], 0.1 * inv, self.kernel(i2, self.grads), self.bias(i2, self.grads))   # conv2 (x 0.1)
                 _capi.check(lib.dsen2_conv_relu_bwd(ptr(b['dx_hi']), ptr(self.w_bwd[i2]), ptr(self.zero_bias), ptr(b['t'][l]),
@@ -367,23 +385,45 @@ class Trainer:
                 wgrad(b['x_hi'][l], b['g2'], inv, self.kernel(i1, self.grads), self.bias(i1, self.grads))
                 _capi.check(lib.dsen2_conv_res32(ptr(b['g2']), ptr(self.w_bwd[i1]), ptr(self.zero_bias), n, P, P, F, 1.0,
                                                  ptr(b['dx32']), ptr(b['dx_hi']), None, st), "dgrad conv1 + skip")
-            # ---- first layer: Conv2D(F, relu) on the concatenated inputs (DSen2Net.py:24-29)
-            _capi.check(lib.dsen2_relu_mask(ptr(b['dx_hi']), ptr(b['x_hi'][0]), npix * F, ptr(b['g2']), st), "relu mask")
-            x2, c2 = (xs[2], self.model.in_channels[2]) if len(xs) == 3 else (None, 0)
-            _capi.check(lib.dsen2_nchw_to_nhwc_f16(ptr(xs[0]), self.model.in_channels[0], ptr(xs[1]), self.model.in_channels[1],
-                                                   ptr(x2), c2, n, P, P, F, ptr(b['dy_nhwc']), st), "input nhwc")
-            wgrad(b['dy_nhwc'], b['g2'], inv, self.gw_head, self.bias(0, self.grads))
-            self.kernel(0, self.grads).view(9, self.ctot, F).copy_(self.gw_head[:, :self.ctot, :])
-            self.kernel(nl - 1, self.grads).view(9, F, self.cout).copy_(self.gw_tail[:, :, :self.cout])
-            self.bias(nl - 1, self.grads).copy_(self.gb_tail[:self.cout])
-            # ---- data-parallel exchange + Nadam
-            if apply and dev_hp:                            # single-GPU graph capture: scalars come from hp_dev
+
+            if do_a:
+                pred = self.forward(xs, b, n, P)
+                self.sums.zero_()
+                self.grads.zero_()
+                self.gw_head.zero_()
+                self.gw_tail.zero_()
+                self.gb_tail.zero_()
+                _capi.check(lib.dsen2_mae_grad(ptr(pred), ptr(y), total, self.GSCALE, ptr(b['dpred']), ptr(self.sums), st), "mae")
+                # ---- last layer: Conv2D(cout) (DSen2Net.py:35); the Add of the global skip passes the gradient through
+                _capi.check(lib.dsen2_nchw_to_nhwc_f16(ptr(b['dpred']), self.cout, None, 0, None, 0, n, P, P, F, ptr(b['dy_nhwc']),
+                                                       st), "dpred nhwc")
+                wgrad(b['x_hi'][L], b['dy_nhwc'], inv, self.gw_tail, self.gb_tail)
+                self.kernel(nl - 1, self.grads).view(9, F, self.cout).copy_(self.gw_tail[:, :, :self.cout])
+                self.bias(nl - 1, self.grads).copy_(self.gb_tail[:self.cout])
+                b['dx32'].zero_()
+                _capi.check(lib.dsen2_conv_res32(ptr(b['dy_nhwc']), ptr(self.w_bwd[-1]), ptr(self.zero_bias), n, P, P, F, 1.0,
+                                                 ptr(b['dx32']), ptr(b['dx_hi']), None, st), "dgrad tail")
+                # ---- resBlocks, last to first
+                for l in range(L - 1, split - 1, -1):
+                    resblock_bwd(l)
+                loss = self.sums[0] / total
+                mse = self.sums[1] / total
+            if do_b:
+                for l in range(split - 1, -1, -1):
+                    resblock_bwd(l)
+                # ---- first layer: Conv2D(F, relu) on the concatenated inputs (DSen2Net.py:24-29)
+                _capi.check(lib.dsen2_relu_mask(ptr(b['dx_hi']), ptr(b['x_hi'][0]), npix * F, ptr(b['g2']), st), "relu mask")
+                x2, c2 = (xs[2], self.model.in_channels[2]) if len(xs) == 3 else (None, 0)
+                _capi.check(lib.dsen2_nchw_to_nhwc_f16(ptr(xs[0]), self.model.in_channels[0], ptr(xs[1]), self.model.in_channels[1],
+                                                       ptr(x2), c2, n, P, P, F, ptr(b['dy_nhwc']), st), "input nhwc")
+                wgrad(b['dy_nhwc'], b['g2'], inv, self.gw_head, self.bias(0, self.grads))
+                self.kernel(0, self.grads).view(9, self.ctot, F).copy_(self.gw_head[:, :self.ctot, :])
+            # ---- data-parallel exchange + Nadam (the two-part form leaves both to train_step)
+            if part is None and apply and dev_hp:           # single-GPU graph capture: scalars come from hp_dev
                 self._update_dev()
-            elif apply:
+            elif part is None and apply:
                 world = allreduce_gradients(self.grads, self.group)
                 self.apply_gradients(1.0 / world)
-            loss = self.sums[0] / total
-            mse = self.sums[1] / total
         return loss, mse
 
     def evaluate(self, xs, y):

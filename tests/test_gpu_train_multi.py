@@ -1,0 +1,62 @@
+"""Data-parallel training step on two GPUs (NCCL): the bucketed all-reduce that overlaps the rest of the backward pass gives the
+same update as the single all-reduce after it, and the replicas stay bit-identical.  Needs two CUDA devices (skipped on the
+one-GPU box of the default run; `gpurun --gpus 2 -- python -m pytest tests/test_gpu_train_multi.py`)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, F, L, n, out):
+    import torch
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    from dsen2_b200.DSen2Net import s2model
+    from dsen2_b200.train import Nadam, Trainer
+    rng = np.random.RandomState(100 + rank)                       # every rank its own batch
+    xs = [torch.from_numpy((0.8 + 0.4 * rng.randn(n, c, 32, 32)).clip(0, 5).astype(np.float32)).cuda() for c in (4, 6)]
+    y = (xs[1] + 0.1 * torch.randn_like(xs[1]))
+    res = {}
+    for mode in ('overlap', 'single'):
+        model = s2model(((4, None, None), (6, None, None)), num_layers=L, feature_size=F, seed=0)
+        tr = Trainer(model, Nadam(lr=1e-3))
+        tr.no_overlap = mode == 'single'
+        assert tr._overlap_allreduce(n, 32) == (mode == 'overlap')
+        losses = [float(tr.train_step(xs, y)[0]) for _ in range(6)]      # eager, capture, four replays
+        torch.cuda.synchronize()
+        p = tr.params.clone()
+        gathered = [torch.empty_like(p) for _ in range(world)]
+        dist.all_gather(gathered, p)
+        assert all(torch.equal(g, gathered[0]) for g in gathered), "replicas diverged (%s)" % mode
+        res[mode] = (losses, p.cpu().numpy())
+    if rank == 0:
+        np.savez(out, lo=res['overlap'][0], ls=res['single'][0], po=res['overlap'][1], ps=res['single'][1])
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('F,L,n', [(256, 4, 4), (128, 4, 2)])
+def test_overlapped_allreduce_equals_single_allreduce(tmp_path, F, L, n):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    out = str(tmp_path / 'res.npz')
+    mp.spawn(_worker, args=(2, _free_port(), F, L, n, out), nprocs=2, join=True)
+    r = np.load(out)
+    np.testing.assert_allclose(r['lo'], r['ls'], rtol=2e-3)
+    assert r['lo'][-1] < r['lo'][0]
+    d = np.abs(r['po'] - r['ps']) / (1e-3 * 6)
+    assert np.median(d) < 1e-3 and np.mean(d > 0.25) < 0.01       # fp32 atomics in the weight gradients: last-bit noise only

@@ -489,9 +489,10 @@ def run_train(args):
                        {"forward + backward-data convolutions (conv_pair_kernel)": 0.615,
                         "weight + bias gradients (wgrad_direct_kernel)": 0.316, "Nadam": 0.006, "operand repacking": 0.012,
                         "loss, layout, fills": 0.051})),
-                "allreduce": {"us": allreduce_us, "bytes": int(tr.grads.numel()) * 4, "algo": "NCCL all_reduce(SUM) in two buckets between the gradient graphs and the update "
-                              "graph: the later layers' bucket runs beside the rest of the backward pass; `us` is ONE all-reduce of the "
-                              "whole gradient, timed alone"} if world > 1 else None,
+                "allreduce": {"us": allreduce_us, "bytes": int(tr.grads.numel()) * 4, "algo": ("NCCL all_reduce(SUM) in two buckets between the gradient graphs and the update "
+                                       "graph: the later layers' bucket runs beside the rest of the backward pass" if tr._overlap_allreduce(n, P)
+                                       else "NCCL all_reduce(SUM), one bucket, between the gradient graph and the update graph") +
+                              "; `us` is ONE all-reduce of the whole gradient, timed alone"} if world > 1 else None,
                 "last_loss": losses[-1] if losses else None}
         print(json.dumps(line), flush=True)
     if world > 1:

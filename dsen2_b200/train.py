@@ -318,11 +318,12 @@ class Trainer:
 
     def _overlap_allreduce(self, n, P):
         """Two buckets: the all-reduce of the later layers' gradients runs beside the backward pass of the first `split_l`
-        resBlocks and the first layer.  Measured piece by piece on two B200s (tools/gpu_overlap_probe.py): VDSen2, batch 8
-        (64 tiles, half of the SMs idle): the 241 us late all-reduce disappears, the concurrent part of the backward pass
-        slows from 621 to 702 us, step 4.40 -> 4.24 ms; DSen2, batch 128 (a full persistent grid shares its SMs with the
-        collective's CTAs): 62-90 us hidden for 20-30 us of slow-down, step 1.67 -> 1.59 ms."""
-        return not self.no_overlap and self.L > 0
+        resBlocks and the first layer.  Measured piece by piece on two B200s (tools/gpu_overlap_probe.py) for VDSen2
+        (151 MB of gradients, batch 8): the 241 us all-reduce of the late bucket disappears behind the concurrent part of
+        the backward pass, which slows from 621 to 702 us; step 4.40 -> 4.24 ms (8 GPUs: 4.45 -> 4.35 ms).  DSen2's 7 MB
+        gradient is a latency-bound collective (44 us on two GPUs, 74 us on eight): two of them cost as much as they hide
+        (8 GPUs: 1.72 ms with one bucket, 1.82 ms with two on another box), so small gradients keep the single all-reduce."""
+        return not self.no_overlap and self.L > 0 and self.grads.numel() * 4 >= (32 << 20)
 
     def _update_dev(self):
         """Nadam update with the scalars published in ``hp_dev`` + operand repacking (capturable)."""

@@ -34,7 +34,8 @@ def _worker(rank, world, port, F, L, n, out):
         model = s2model(((4, None, None), (6, None, None)), num_layers=L, feature_size=F, seed=0)
         tr = Trainer(model, Nadam(lr=1e-3))
         tr.no_overlap = mode == 'single'
-        assert tr._overlap_allreduce(n, 32) == (mode == 'overlap')
+        if mode == 'overlap' and not tr._overlap_allreduce(n, 32):        # small gradients default to one bucket: force two
+            tr._overlap_allreduce = lambda n_, P_: True
         losses = [float(tr.train_step(xs, y)[0]) for _ in range(6)]      # eager, capture, four replays
         torch.cuda.synchronize()
         p = tr.params.clone()

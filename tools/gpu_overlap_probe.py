@@ -20,7 +20,7 @@ deep = '--dsen2' not in sys.argv
 L, F, n = (32, 256, 8) if deep else (6, 128, 128)
 model = s2model(((4, None, None), (6, None, None)), num_layers=L, feature_size=F, seed=0)
 tr = Trainer(model, Nadam(lr=1e-4), device=dev)
-if not deep:
+if not tr._overlap_allreduce(n, 32):
     tr._overlap_allreduce = lambda n_, P_: True      # force the two-part schedule to look at it
 g = torch.Generator().manual_seed(rank)
 xs = [torch.rand((n, c, 32, 32), generator=g).mul_(2.5).to(dev) for c in (4, 6)]

@@ -41,6 +41,18 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert b'null pointer' in lib.dsen2_last_error()
     assert lib.dsen2_conv_relu(None, None, None, 1, 8, 8, 128, None, None) == -1
     assert lib.dsen2_s2model_workspace_bytes(1, 128, 10, 128) >= 128 * 128 * (128 + 3 * 128) * 2
+    # the feature size / channel count of the training-step entry points (ABI 3) is checked before anything touches the device
+    import ctypes
+    buf = (ctypes.c_char * 4096)()
+    p = ctypes.cast(ctypes.byref(buf, 1024 - ctypes.addressof(buf) % 1024), ctypes.c_void_p)      # a non-null, aligned pointer
+    assert lib.dsen2_conv_res32(p, p, p, 1, 8, 8, 192, 0.1, p, p, None, None) == -1
+    assert b'128 or 256' in lib.dsen2_last_error()
+    assert lib.dsen2_conv_relu_bwd(p, p, p, p, 1, 8, 8, 64, p, None) == -1
+    assert b'128 or 256' in lib.dsen2_last_error()
+    assert lib.dsen2_wgrad_nhwc(p, p, 1, 8, 8, 96, 1.0, p, None, None) == -1
+    assert b'128 or 256' in lib.dsen2_last_error()
+    assert lib.dsen2_conv_head16_relu(p, p, p, p, 1, 8, 8, 128, p, p, None) == -1
+    assert b'256 only' in lib.dsen2_last_error()
 
 
 def test_no_cpu_fallback_without_cuda():

@@ -256,6 +256,27 @@ def open_source(path):
     return GdalSource(path)
 
 
+def output_file_formats():
+    """``--list_output_file_formats`` (:64-78): the raster drivers GDAL can create files with, as "name: long name (ext)";
+    ``npz`` is always there (the reference falls back to it when the driver is missing, :409-411)."""
+    lines = ["npz: compressed python/numpy file, one array per band (npz)"]
+    try:
+        from osgeo import gdal
+    except ImportError:
+        return lines
+    for didx in range(gdal.GetDriverCount()):  # pragma: no cover - needs osgeo, which is not in this image
+        driver = gdal.GetDriver(didx)
+        metadata = driver.GetMetadata() if driver else {}
+        if metadata.get(gdal.DCAP_CREATE) == 'YES' and metadata.get(gdal.DCAP_RASTER) == 'YES':
+            name = driver.GetDescription()
+            if "DMD_LONGNAME" in metadata:
+                name += ": " + metadata["DMD_LONGNAME"]
+            if "DMD_EXTENSIONS" in metadata:
+                name += " (" + metadata["DMD_EXTENSIONS"] + ")"
+            lines.append(name)
+    return lines
+
+
 # ---------------------------------------------------------------------------------------------- #
 # command line (same options as the reference, :14-64)
 # ---------------------------------------------------------------------------------------------- #
@@ -270,6 +291,8 @@ def build_parser():
     p.add_argument("--run_60", action="store_true", help="Also super-resolve the 60m bands (B1, B9).")
     p.add_argument("--list_UTM", action="store_true", help="List all UTM zones present in the input file.")
     p.add_argument("--select_UTM", default="", help="Select a UTM zone (default: largest ROI coverage).")
+    p.add_argument("--list_output_file_formats", action="store_true",
+                   help="List the raster output file formats GDAL can create (and npz) and exit.")
     p.add_argument("--output_file_format", default="GTiff", help="GDAL driver name, or npz.")
     p.add_argument("--copy_original_bands", action="store_true", help="Also copy the original 10m bands into the output.")
     p.add_argument("--save_prefix", default="", help="Prefix for all output files.")
@@ -278,6 +301,10 @@ def build_parser():
 
 def main(argv=None, models=None):
     args = build_parser().parse_args(argv)
+    if args.list_output_file_formats:                # before the input is opened, as in the reference (:64-79)
+        for line in output_file_formats():
+            print(line)
+        return 0
     src = open_source(args.data_file)
     if args.roi_lon_lat and not isinstance(src, GdalSource):
         raise SystemExit("--roi_lon_lat needs GDAL/osr for the coordinate transformation; use --roi_x_y")

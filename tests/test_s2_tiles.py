@@ -111,6 +111,8 @@ def test_cli_listings_and_gdal_fallback(tmp_path, capsys, monkeypatch):
     assert 'UTM 32N (21600)' in capsys.readouterr().out
     assert st.main([path, '--list_bands']) == 0
     assert 'Selected 20m bands: B5 B6 B7 B8A B11 B12' in capsys.readouterr().out
+    assert st.main(['not-opened.zip', '--list_output_file_formats']) == 0     # exits before the input is touched (:64-79)
+    assert capsys.readouterr().out.startswith('npz:')
     out = str(tmp_path / 'x.tif')
     assert st.main([path, out]) == 0                          # GTiff requested, no GDAL here: npz fallback like the reference
     assert "Writing to npz as a fallback" in capsys.readouterr().out

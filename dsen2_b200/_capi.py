@@ -20,7 +20,7 @@ SIGNATURES = {
                                 c_void_p]),
     "dsen2_bicubic_imresize": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
                                        c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
-    "dsen2_down_pixel_aggr": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "dsen2_down_pixel_aggr": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "dsen2_pack_conv_weights": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dsen2_conv_relu": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dsen2_s2model_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),

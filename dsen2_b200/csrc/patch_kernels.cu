@@ -562,18 +562,21 @@ __device__ __forceinline__ double gauss_line(const float* __restrict__ base, lon
   return acc;
 }
 
+// integer_input: the image holds integers (the uint16 digital numbers GDAL hands create_patches.py) -- scipy then stores each
+// pass in THAT dtype, i.e. truncates the float64 result towards zero (C cast); the truncated values are exact in float32.
 __global__ void gauss_rows_kernel(const float* __restrict__ img, int H, int W, int C, const double* __restrict__ w, int radius,
-                                  long long total, float* __restrict__ tmp) {
+                                  int integer_input, long long total, float* __restrict__ tmp) {
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const long long col = idx % ((long long)W * C);               // (x, c) flattened: contiguous across threads
     const int y = (int)(idx / ((long long)W * C));
-    tmp[idx] = (float)gauss_line(img + col, (long long)W * C, y, H, w, radius);
+    const double v = gauss_line(img + col, (long long)W * C, y, H, w, radius);
+    tmp[idx] = integer_input ? (float)trunc(v) : (float)v;
   }
 }
 
 __global__ void gauss_cols_mean_kernel(const float* __restrict__ tmp, int H, int W, int C, const double* __restrict__ w,
-                                       int radius, int s, long long total, double* __restrict__ out) {
+                                       int radius, int s, int integer_input, long long total, double* __restrict__ out) {
   const int ow = W / s;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -584,7 +587,8 @@ __global__ void gauss_cols_mean_kernel(const float* __restrict__ tmp, int H, int
     for (int dy = 0; dy < s; ++dy) {
       const float* row = tmp + ((long long)(oy * s + dy) * W) * C + c;
       for (int dx = 0; dx < s; ++dx) {
-        const float blurred = (float)gauss_line(row, C, ox * s + dx, W, w, radius);   // second pass, stored as float32
+        const double v = gauss_line(row, C, ox * s + dx, W, w, radius);
+        const float blurred = integer_input ? (float)trunc(v) : (float)v;              // second pass, stored in the image dtype
         sum = (dy == 0 && dx == 0) ? (double)blurred : __dadd_rn(sum, (double)blurred);
       }
     }
@@ -766,19 +770,20 @@ extern "C" int dsen2_bicubic_imresize(const void* d_in, int in_is_f64, int h, in
   return check_launch("bicubic_imresize");
 }
 
-extern "C" int dsen2_down_pixel_aggr(const float* d_img, int H, int W, int C, int scale, const double* d_weights, int radius,
-                                     float* d_tmp, double* d_out, void* stream) {
+extern "C" int dsen2_down_pixel_aggr(const float* d_img, int integer_input, int H, int W, int C, int scale,
+                                     const double* d_weights, int radius, float* d_tmp, double* d_out, void* stream) {
   DSEN2_REQUIRE(d_img && d_weights && d_tmp && d_out, DSEN2_E_BADARG, "dsen2_down_pixel_aggr: null pointer");
   DSEN2_REQUIRE(H > 0 && W > 0 && C > 0 && scale > 0 && radius >= 0 && H >= scale && W >= scale, DSEN2_E_BADARG,
                 "dsen2_down_pixel_aggr: bad sizes");
   const long long total = (long long)H * W * C;
   const int block = 256;
-  gauss_rows_kernel<<<grid_for(total, block), block, 0, (cudaStream_t)stream>>>(d_img, H, W, C, d_weights, radius, total, d_tmp);
+  gauss_rows_kernel<<<grid_for(total, block), block, 0, (cudaStream_t)stream>>>(d_img, H, W, C, d_weights, radius, integer_input,
+                                                                                total, d_tmp);
   int rc = check_launch("gauss_rows");
   if (rc) return rc;
   const long long ototal = (long long)(H / scale) * (W / scale) * C;
   gauss_cols_mean_kernel<<<grid_for(ototal, block), block, 0, (cudaStream_t)stream>>>(d_tmp, H, W, C, d_weights, radius, scale,
-                                                                                    ototal, d_out);
+                                                                                    integer_input, ototal, d_out);
   return check_launch("gauss_cols_mean");
 }
 

@@ -207,11 +207,16 @@ def OpenDataFilesTest(path, run_60, SCALE, true_scale=False):
 # ------------------------------------------------------------------------------------------ #
 def downPixelAggr(img, SCALE=2):
     """patches.py:353-371: Gaussian blur with sigma = 1/SCALE per band, then SCALE x SCALE pixel aggregation.
-    Returns float64 like the reference (``np.zeros`` default dtype), squeezed."""
+    Returns float64 like the reference (``np.zeros`` default dtype), squeezed.  An integer image (the uint16 digital numbers
+    ``create_patches.py`` reads through GDAL) is blurred the way scipy blurs it: every pass stored in the image's dtype,
+    i.e. truncated towards zero."""
     torch = _capi.require_cuda()
     img = np.asarray(img)
     if img.ndim == 2:
         img = img[:, :, None]
+    integer = int(np.issubdtype(img.dtype, np.integer))
+    if integer and (img.dtype.itemsize > 2 or (img.size and img.min() < 0)):
+        raise ValueError("downPixelAggr: integer images must be uint8 / uint16 / non-negative int16 (exact in float32)")
     sigma = 1.0 / SCALE
     radius = int(4.0 * sigma + 0.5)                      # scipy.ndimage.gaussian_filter1d, truncate = 4.0
     x = np.arange(-radius, radius + 1)
@@ -222,7 +227,7 @@ def downPixelAggr(img, SCALE=2):
     dw = torch.from_numpy(w).cuda()
     tmp = torch.empty_like(d)
     out = torch.empty((H // SCALE, W // SCALE, C), dtype=torch.float64, device=d.device)
-    _capi.check(_capi.lib().dsen2_down_pixel_aggr(_capi.ptr(d), H, W, C, SCALE, _capi.ptr(dw), radius, _capi.ptr(tmp),
+    _capi.check(_capi.lib().dsen2_down_pixel_aggr(_capi.ptr(d), integer, H, W, C, SCALE, _capi.ptr(dw), radius, _capi.ptr(tmp),
                                                   _capi.ptr(out), _capi.stream_ptr()), "dsen2_down_pixel_aggr")
     return np.squeeze(out.cpu().numpy())
 

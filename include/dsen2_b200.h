@@ -87,9 +87,11 @@ int dsen2_bicubic_imresize(const void* d_in, int in_is_f64, int h, int w, int C,
  * passes, 'reflect' boundary, kernel radius int(4/scale + 0.5) -- followed by the scale x scale block mean.
  * d_weights: the 2*radius+1 normalised Gaussian weights (host, scipy's _gaussian_kernel1d); d_tmp (H,W,C)
  * float32 scratch; d_out (H/scale, W/scale, C) float64.
+ * integer_input != 0: d_img holds the values of an INTEGER image (the uint16 digital numbers GDAL hands
+ * training/create_patches.py:189-197) -- scipy then stores each pass in that dtype, i.e. truncates towards zero.
  * ------------------------------------------------------------------------------------------- */
-int dsen2_down_pixel_aggr(const float* d_img, int H, int W, int C, int scale, const double* d_weights, int radius,
-                          float* d_tmp, double* d_out, void* stream);
+int dsen2_down_pixel_aggr(const float* d_img, int integer_input, int H, int W, int C, int scale, const double* d_weights,
+                          int radius, float* d_tmp, double* d_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Network (utils/DSen2Net.py:9-43): tcgen05 implicit-GEMM convolutions on CTA pairs (cta_group::2), fp16 operands,

@@ -168,6 +168,12 @@ def test_down_pixel_aggr_matches_scipy_oracle(mods, shape, scale):
     assert np.array_equal(got, ref)       # same double arithmetic, float32 storage between the passes, same summation order
     got2 = patches.downPixelAggr(img[:, :, 0], SCALE=scale)         # 2-D input is expanded and squeezed again
     assert np.array_equal(got2, ref[..., 0] if ref.ndim == 3 else ref)
+    # uint16 digital numbers (what create_patches.py reads through GDAL): scipy stores each pass as uint16 = truncation
+    dn = (rng.rand(*shape) * 9000).astype(np.uint16)
+    dn[:4, :4] = 1234                                               # a flat patch: sums that land on an integer boundary
+    ref16 = po.downPixelAggr(dn, SCALE=scale)
+    assert np.array_equal(patches.downPixelAggr(dn, SCALE=scale), ref16)
+    assert not np.array_equal(ref16, po.downPixelAggr(dn.astype(np.float32), SCALE=scale))
 
 
 def test_training_patch_writers(mods, tmp_path):
@@ -195,3 +201,34 @@ def test_training_patch_writers(mods, tmp_path):
     r10, r20 = po.get_test_patches(d10, d20, 32, 4)
     assert np.array_equal(t10, r10)
     np.testing.assert_allclose(t20, r20, rtol=0, atol=2e-3)
+
+
+def test_create_patches_cli_on_an_npz_product(mods, tmp_path):
+    """training/create_patches.py end to end on the GPU kernels (degradation, tiling, bilinear upsampling), .npz product:
+    test patches == the oracle's get_test_patches of the oracle-degraded images; random training crops have the documented
+    shapes and the label is the full-resolution 20 m crop."""
+    _, _, po, _ = mods
+    from dsen2_b200 import create_patches as cp
+    rng = np.random.RandomState(4)
+    H, W = 648, 720                  # 60 m after the 6x degradation: 18 x 20 pixels, enough for the 16 x 16 random crops
+    d10 = rng.randint(1, 9000, (H, W, 4)).astype(np.uint16)
+    d20 = rng.randint(1, 9000, (H // 2, W // 2, 6)).astype(np.uint16)
+    d60 = rng.randint(1, 9000, (H // 6, W // 6, 2)).astype(np.uint16)
+    desc = lambda names: np.array(["%s, central wavelength 500 nm" % n for n in names])
+    path = str(tmp_path / 'S2A_TEST.npz')
+    np.savez(path, data10=d10, data20=d20, data60=d60, desc10=desc(['B4', 'B3', 'B2', 'B8']),
+             desc20=desc(['B5', 'B6', 'B7', 'B8A', 'B11', 'B12']), desc60=desc(['B1', 'B9']),
+             geotransform=np.array([3e5, 10., 0., 5e6, 0., -10.]), utm=np.array('UTM 32N'))
+    prefix = str(tmp_path) + '/data/'
+    (tmp_path / 'data').mkdir()
+    assert cp.main([path, '--save_prefix', prefix, '--test_data']) == 0
+    d = tmp_path / 'data' / 'test' / 'S2A_TEST.npz'
+    lr10, lr20 = po.downPixelAggr(d10, 2), po.downPixelAggr(d20, 2)
+    assert np.array_equal(np.load(d / 'no_tiling' / 'data10.npy'), lr10.astype(np.float32))          # bit-identical to scipy
+    p10, p20 = po.get_test_patches(lr10, lr20, 128, 4)
+    assert np.array_equal(np.load(d / 'data10.npy'), p10)
+    np.testing.assert_allclose(np.load(d / 'data20.npy'), p20, rtol=0, atol=2e-3)
+    assert cp.main([path, '--save_prefix', prefix, '--run_60']) == 0                                  # 500 random crops
+    t = tmp_path / 'data' / 'train60' / 'S2A_TEST.npz'
+    assert np.load(t / 'data10.npy').shape == (500, 4, 96, 96) and np.load(t / 'data60.npy').shape == (500, 2, 96, 96)
+    assert np.load(t / 'data60_gt.npy').shape == (500, 2, 96, 96)

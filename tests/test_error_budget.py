@@ -48,3 +48,18 @@ def test_winograd_trunk_feasibility():
     e_wino = np.abs(forward_emulated_winograd(xs, wts) - ref).max()
     print('direct %.2e, winograd %.2e' % (e_direct, e_wino))
     assert e_wino < 5e-3
+
+
+def test_vdsen2_depth_32_budget():
+    """The same budget at VDSen2's real depth (32 resBlocks x 256 features, he_uniform weights as in the GPU test and the
+    bench): the error of the built design is the fp16 rounding of the 64 trunk convolutions' operands -- the fp16 + 8 bit
+    trunk is indistinguishable from an fp32 trunk -- and an fp16-only trunk would break the 5e-3 gate."""
+    rng = np.random.RandomState(3)
+    xs = [(0.8 + 0.45 * rng.randn(1, c, 48, 48)).clip(0, 6).astype(np.float32) for c in (4, 6)]
+    w = no.he_uniform_weights(10, 6, 32, 256, seed=0)
+    ref = forward_exact(xs, w)
+    err = {t: float(np.abs(forward_emulated(xs, w, trunk=t) - ref).max()) for t in ('fp32', 'q8', 'fp16')}
+    print('VDSen2 32 x 256, outputs up to %.1f: max abs error vs float64' % np.abs(ref).max(), err)
+    assert err['q8'] < 5e-3 and err['fp32'] < 5e-3
+    assert abs(err['q8'] - err['fp32']) < 5e-4
+    assert err['fp16'] > 5e-3

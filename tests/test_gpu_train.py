@@ -136,7 +136,7 @@ def _setup(L=2, n=4, P=32, run_60=False, seed=0, F=128):
 
 @pytest.mark.parametrize('cfg', [dict(L=2, n=4, P=32), dict(L=6, n=8, P=32), dict(L=1, n=2, P=32, run_60=True),
                                  dict(L=0, n=2, P=16), dict(L=2, n=4, P=32, F=256), dict(L=1, n=2, P=32, run_60=True, F=256),
-                                 dict(L=4, n=8, P=32, F=256)])
+                                 dict(L=4, n=8, P=32, F=256), dict(L=32, n=2, P=32, F=256)])
 def test_gradients_vs_autograd(env, cfg):
     torch, _capi, lib = env
     from dsen2_b200.train import Trainer

@@ -164,6 +164,49 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def cpu_train_run(deep, steps, warmup, n):
+    """Time the CPU oracle's training step (torch-CPU fp32 autograd of the same graph + NAdam, oracle/train_oracle.py) on n
+    patches of 32 x 32; returns (samples/s, s/step, threads)."""
+    import torch
+    from oracle import dsen2net_oracle as no
+    from oracle import train_oracle as to
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(1234)                              # SURVEY 8(d) config 5
+    xs = [torch.rand((n, c, 32, 32), generator=g).mul_(2.5).numpy() for c in (4, 6)]
+    y = torch.rand((n, 6, 32, 32), generator=g).mul_(2.5).numpy()
+    w = no.he_uniform_weights(10, 6, 32 if deep else 6, 256 if deep else 128, seed=0)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        to.train_steps([(xs, y)], w, lr=1e-4)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    per = float(np.mean(times))
+    return n / per, per, torch.get_num_threads()
+
+
+def run_reference_train(args):
+    """`--impl reference --workload train`: the CPU oracle's training step on the host cores, rank 0 only."""
+    if int(os.environ.get('RANK', '0')) != 0:
+        return
+    deep = args.model == 'vdsen2'
+    n = 8 if deep else 32                                                # a bounded sample: one quarter of the DSen2 batch
+    sps, per, threads = cpu_train_run(deep, min(args.steps, 5), min(args.warmup, 1), n)
+    sample = ("%d patches of 32x32 (the GPU arm: %d per GPU) through the CPU oracle's step: torch-CPU fp32 autograd of the same "
+              "graph, MAE, torch NAdam(momentum_decay=0.004) = the Keras-2 Nadam recurrence; %.2f s per step; TensorFlow/Keras "
+              "not installable" % (n, 8 if deep else 128, per))
+    line = {"impl": "reference", "metric": "train_samples_per_s", "value": sps, "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": min(args.steps, 5), "warmup": min(args.warmup, 1), "ms_per_step": per * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": "%s training step, MAE + Keras-2 Nadam, CPU sample of %d patches 32x32" % (
+                'VDSen2 (32x256)' if deep else 'DSen2 (6x128)', n), "batch_per_gpu": n, "cpu_sample_only": True},
+            "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
 def workload_config(args, cpu=False):
     T = args.tile
     P, B = (192, 12) if args.path == 60 else (128, 8)
@@ -461,6 +504,13 @@ def run_train(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         allreduce_us = float(t.item())
     flop = 3.0 * FLOP_PER_PIXEL[(args.model, 20)] * n * P * P            # forward + backward-data + weight-gradient
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:            # the oracle's step on the host cores, bounded sample
+        ncpu = 8 if deep else 32
+        sps, per, threads = cpu_train_run(deep, 3, 1, ncpu)
+        cpu = {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port",
+               "sample": "%d patches of 32x32 through the CPU oracle's step (torch-CPU fp32 autograd + NAdam), %.2f s per step, "
+                         "3 steps after 1 warm-up" % (ncpu, per)}
     if rank == 0:
         pk = peaks()
         line = {"metric": "train_samples_per_s", "value": world * n / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
@@ -493,6 +543,7 @@ def run_train(args):
                                        "graph: the later layers' bucket runs beside the rest of the backward pass" if tr._overlap_allreduce(n, P)
                                        else "NCCL all_reduce(SUM), one bucket, between the gradient graph and the update graph") +
                               "; `us` is ONE all-reduce of the whole gradient, timed alone"} if world > 1 else None,
+                "cpu_baseline": cpu,
                 "last_loss": losses[-1] if losses else None}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -519,6 +570,8 @@ def main():
         if args.steps == 3:
             args.steps, args.warmup = 50, 10
         run_train(args)
+    elif args.impl == 'reference' and args.workload == 'train':
+        run_reference_train(args)
     elif args.impl == 'reference':
         run_reference(args)
     else:
